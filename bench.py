@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the serving/scoring hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the CPU path, timed on the host cores
+
+Metric (BASELINE.json): queries/sec of exact top-100 retrieval over a 10M-item, d=128 catalog in
+1,024-query batches (configs[2]; the catalog is 5.12 GB and fits one GPU, at N>1 it is row-sharded and the
+per-shard lists are all-gathered over NCCL and merged).  A "step" is one 1,024-query batch over the whole
+catalog.  The same JSON line also carries, under "ranking", the second headline: DCN ranking forward
+samples/sec at batch 65,536 (configs[1]).
+
+`value`  : queries/s with the query batch already in HBM (catalog resident, as in faiss after add()).
+`e2e`    : the same through the faiss-shaped public call with HOST queries in and HOST (D, I) out.
+`roofline`: the dominant kernel, timed with CUDA events on its own stream inside the timed region.
+`cpu_baseline`: the CPU restatement (oracle.search_blas: blocked sgemm + heap, what faiss-cpu does for
+            > 20 queries) on a bounded slice of the same workload, on this box's host cores.
+Under --impl reference the CPU restatement is the timed arm (TensorFlow / faiss cannot be installed in this
+image; kind = "port").
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "queries/sec exact top-100 over 10M items"
+UNIT = "queries/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n-items", type=int, default=10_000_000)
+    ap.add_argument("--nq", type=int, default=1024)
+    ap.add_argument("--k", type=int, default=100)
+    ap.add_argument("--dim", type=int, default=128)
+    ap.add_argument("--mode", default="auto", choices=["auto", "exact", "tensor"])
+    ap.add_argument("--rank-batch", type=int, default=65536)
+    ap.add_argument("--no-ranking", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-rows", type=int, default=1_000_000)
+    return ap.parse_args()
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU arm / baseline
+def cpu_prepare(args, sample_rows: int):
+    import oracle
+    import recsys_b200 as rs
+    oracle.build_chain_lib()
+    rows = min(sample_rows, args.n_items)
+    xb = rs.synth.make_unit_rows(rows, args.dim, 3000)
+    q = rs.synth.make_unit_rows(args.nq, args.dim, 3999)
+    oracle.search_blas(xb[:4096], q[:64], args.k)           # warm the BLAS threads
+    return xb, q
+
+
+def cpu_step(args, xb, q) -> float:
+    """One bounded CPU step: nq queries x the catalog slice; returns seconds scaled to the full catalog."""
+    import oracle
+    t0 = time.perf_counter()
+    oracle.search_blas(xb, q, args.k)
+    return (time.perf_counter() - t0) * (args.n_items / xb.shape[0])
+
+
+def cpu_describe(args, rows, scaled_s):
+    return {"value": args.nq / scaled_s, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+            "sample": f"{args.nq} queries x {rows:,}-row slice ({rows / args.n_items:.0%} of the catalog), blocked "
+                      f"OpenBLAS sgemm + per-query heap (faiss-cpu's >20-query path restated; TF/faiss are not "
+                      f"installable here), time scaled x{args.n_items / rows:.1f} to the full catalog"}
+
+
+def run_reference(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    xb, q = cpu_prepare(args, args.cpu_sample_rows)
+    times = []
+    t_start = time.perf_counter()
+    for i in range(args.warmup + args.steps):
+        dt = cpu_step(args, xb, q)
+        if i >= args.warmup:
+            times.append(dt)
+        if time.perf_counter() - t_start > 240 and times:
+            break
+    scaled = float(np.mean(times))
+    value = args.nq / scaled
+    rows = xb.shape[0]
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": len(times), "warmup": args.warmup, "ms_per_step": 1e3 * scaled, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"exact top-{args.k} over {args.n_items:,} x {args.dim} fp32 catalog, "
+                                   f"{args.nq}-query batches (BASELINE configs[2]); each step = one bounded slice "
+                                   f"of {rows:,} rows, time scaled to the full catalog",
+                       "n_items": args.n_items, "dim": args.dim, "nq": args.nq, "k": args.k},
+            "cpu_baseline": cpu_describe(args, rows, scaled),
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def build_catalog(rs, torch, index, row_begin, row_end, dim, device, block=1 << 20):
+    """Synthetic catalog rows ~ N(0,1) -> unit length, generated on the device per 1M-row block with a
+    per-block seed (3000 + block), so the catalog is the same for every shard count."""
+    b0 = (row_begin // block) * block
+    while b0 < row_end:
+        g = torch.Generator(device=device)
+        g.manual_seed(3000 + b0 // block)
+        x = torch.randn((block, dim), generator=g, device=device, dtype=torch.float32)
+        lo, hi = max(row_begin, b0), min(row_end, b0 + block)
+        x = x[lo - b0:hi - b0].contiguous()
+        rs.normalize_L2(x)                       # K4 on the device
+        index.add(x)                             # copies into the handle's HBM buffer
+        del x
+        b0 += block
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import recsys_b200 as rs
+    from recsys_b200.sharded import ShardedIndexFlatIP, gather_bytes
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a B200; there is no CPU fallback for the product path")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    if args.gpus != world and rank == 0:
+        print(f"note: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
+
+    pk = peaks()
+    N, nq, k, dim = args.n_items, args.nq, args.k, args.dim
+
+    # ---- the catalog shard of this rank, resident in HBM behind the index handle ----
+    sidx = ShardedIndexFlatIP(dim, N)
+    build_catalog(rs, torch, sidx.local, sidx.row_begin, sidx.row_end, dim, device)
+    assert sidx.local.ntotal == sidx.row_end - sidx.row_begin
+    local_search = sidx.local.search
+    sidx._local_search = lambda q_, k_: local_search(q_, k_, id_base=sidx.row_begin, mode=args.mode)
+
+    gq = torch.Generator(device=device)
+    gq.manual_seed(3999)
+    q_dev = torch.randn((nq, dim), generator=gq, device=device, dtype=torch.float32)
+    rs.normalize_L2(q_dev)
+    q_pinned = torch.empty((nq, dim), dtype=torch.float32).pin_memory()
+    q_pinned.copy_(q_dev.cpu())
+    D_host = torch.empty((nq, k), dtype=torch.float32).pin_memory()
+    I_host = torch.empty((nq, k), dtype=torch.int64).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        return sidx.search(q_dev, k)
+
+    def step_e2e():
+        qd = q_pinned.to(device, non_blocking=True)              # H2D of this step's inputs (pinned)
+        D, I = sidx.search(qd, k)
+        D_host.copy_(D, non_blocking=True)                       # D2H of this step's result
+        I_host.copy_(I, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return D_host, I_host
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(3, args.warmup)):
+        step_device()
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    rs._lib.prof_enable(True)
+    launches0 = rs._lib.launch_count()
+    total_ms = timed(step_device, args.steps)
+    launches = rs._lib.launch_count() - launches0
+    prof = {name: rs._lib.prof_read(slot) for name, slot in
+            (("scan", rs._lib.PROF_SCAN), ("merge", rs._lib.PROF_MERGE), ("filter", rs._lib.PROF_FILTER),
+             ("rescore", rs._lib.PROF_RESCORE))}
+    rs._lib.prof_enable(False)
+    clocks = sampler.stop() if rank == 0 else None
+
+    for _ in range(max(3, args.warmup)):
+        step_e2e()
+    e2e_ms = timed(step_e2e, args.steps)
+
+    ms_per_step = total_ms / args.steps
+    value = nq / (ms_per_step / 1e3)
+    e2e_value = nq / (e2e_ms / args.steps / 1e3)
+
+    lt = torch.tensor([launches], device=device, dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(lt)
+    n_local = sidx.row_end - sidx.row_begin
+
+    # ---- roofline of the dominant kernel (largest summed device time on this rank) ----
+    dom = max(prof, key=lambda n_: prof[n_][0])
+    dom_ms, dom_n = prof[dom]
+    roofline = None
+    if dom_n:
+        t = dom_ms / dom_n / 1e3
+        if dom == "filter":
+            flops = 2.0 * nq * n_local * dim
+            ach = flops / t / 1e12
+            peak = pk["bf16_tflops_sustained"]
+            roofline = {"kernel": "tc_filter_kernel", "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                        "frac": ach / peak, "traffic": None, "peak_source": pk["source"] + " (sustained bf16)",
+                        "algorithmic": "2*nq*n_local*d flops per launch", "launches": dom_n,
+                        "ms_per_launch": dom_ms / dom_n,
+                        "hbm_frac": (n_local * dim * 2 / t / 1e9) / pk["hbm_gbs"]}
+        else:
+            byts = float(n_local) * dim * 4
+            ach = byts / t / 1e9
+            roofline = {"kernel": "scan_topk_kernel" if dom == "scan" else dom, "bound": "hbm", "achieved": ach,
+                        "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": None,
+                        "peak_source": pk["source"],
+                        "algorithmic": "n_local*d*4 bytes per launch (one pass over the fp32 catalog shard; the "
+                                       "exact-fp32 mode re-streams it per 8-query group and is FFMA-bound at nq=1024)",
+                        "launches": dom_n, "ms_per_launch": dom_ms / dom_n,
+                        "fp32_tflops": 2.0 * nq * n_local * dim / t / 1e12}
+    kernel_ms = {n_: {"ms_total": round(v[0], 4), "launches": v[1]} for n_, v in prof.items() if v[1]}
+
+    # ---- second headline: DCN ranking forward at batch 65,536 (configs[1]) ----
+    ranking = None
+    if not args.no_ranking:
+        ranking = bench_ranking(rs, torch, dist, args, device, world, rank, pk, timed)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        xb_h, q_h = cpu_prepare(args, args.cpu_sample_rows)
+        cpu = cpu_describe(args, xb_h.shape[0], cpu_step(args, xb_h, q_h))
+        del xb_h
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"exact top-{k} over {N:,} x {dim} fp32 catalog, {nq}-query batches "
+                                       f"(BASELINE configs[2])", "n_items": N, "dim": dim, "nq": nq, "k": k,
+                           "mode": args.mode, "sharding": f"rows/{world} contiguous, all-gather + merge" if world > 1 else "none",
+                           "l2": "inputs larger than L2 (catalog shard %.2f GB per GPU)" % (n_local * dim * 4 / 1e9)},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nq * dim * 4,
+                        "d2h_bytes_per_step": nq * k * 12, "ms_per_step": e2e_ms / args.steps},
+                "gpu_launches": int(lt.item()), "clocks": clocks, "roofline": roofline, "kernels": kernel_ms,
+                "cpu_baseline": cpu, "ranking": ranking}
+        if world > 1:
+            line["exchange_bytes_per_step_per_rank"] = gather_bytes(world, nq, k)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_ranking(rs, torch, dist, args, device, world, rank, pk, timed):
+    """MultiTaskModel forward (ids -> towers -> DCN -> heads) at batch 65,536 per GPU (data-parallel replicas)."""
+    cfg = rs.ModelConfig()
+    n_users, n_items, B = 6040, 3706, args.rank_batch
+    w = rs.synth.make_weights(cfg, n_users, n_items, seed=10)
+    model = rs.MultiTaskModel(cfg, rs.synth.make_vocab(n_users), rs.synth.make_vocab(n_items), {}, device=device)
+    rs.load_weights(model, w)
+    rng = np.random.default_rng(200 + rank)
+    ur = torch.from_numpy(rs.synth.make_ids(rng, n_users, B)).pin_memory()
+    ir = torch.from_numpy(rs.synth.make_ids(rng, n_items, B)).pin_memory()
+    ur_d, ir_d = ur.to(device), ir.to(device)
+    out_host = torch.empty((B, 2), dtype=torch.float32).pin_memory()
+
+    def step():
+        return model({"user_id": ur_d, "movie_id": ir_d})
+
+    def step_e2e():
+        o = model({"user_id": ur.to(device, non_blocking=True), "movie_id": ir.to(device, non_blocking=True)})
+        out_host[:, 0:1].copy_(o["rating_prediction"], non_blocking=True)
+        out_host[:, 1:2].copy_(o["ctr_prediction"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(3):
+        step()
+    l0 = rs._lib.launch_count()
+    ms = timed(step, args.steps) / args.steps
+    launches = rs._lib.launch_count() - l0
+    for _ in range(3):
+        step_e2e()
+    e2e_ms = timed(step_e2e, args.steps) / args.steps
+    flops = 524288.0 * B
+    return {"metric": "DCN ranking forward samples/sec", "value": world * B / (ms / 1e3), "unit": "samples/s",
+            "ms_per_step": ms, "batch_per_gpu": B, "n_gpus": world, "mode": "fp32 FFMA (exact)", "dtype": "f32",
+            "config": {"workload": f"MultiTaskModel forward, 3 cross layers + MLP, emb 128, batch {B} (BASELINE configs[1])"},
+            "e2e": {"value": world * B / (e2e_ms / 1e3), "unit": "samples/s", "h2d_bytes_per_step": 2 * B * 8,
+                    "d2h_bytes_per_step": B * 8},
+            "gemm_tflops": flops / (ms / 1e3) / 1e12, "tensor_frac_of_sustained_bf16": flops / (ms / 1e3) / 1e12 / pk["bf16_tflops_sustained"],
+            "gpu_launches_per_step": launches // max(1, args.steps)}
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,166 @@
+/*
+ * recsys_b200.h -- C ABI of librecsys_b200.so, the B200 (sm_100a) drop-in for the
+ * serving/scoring hot path of OnlyAhad13/Recommendation-System-MAANG-NVIDIA-.
+ *
+ * The reference has no FFI of its own (it is pure Python over TensorFlow and
+ * faiss-cpu); each entry point below names the reference call site it replaces
+ * (paths relative to the reference root).  Conventions:
+ *   - every function returns 0 on success and non-zero on failure; the message is
+ *     then available from rs_last_error() (thread-local, valid until the next call
+ *     on that thread).  There is no CPU fallback: a missing GPU is an error.
+ *   - tensors cross the boundary as borrowed DLPack `DLTensor*` (the struct below is
+ *     ABI-identical to dlpack.h v0.8 / v1.0 `DLTensor`).  The library never frees or
+ *     keeps caller memory; the only memory it owns sits behind opaque handles.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).
+ *     Calls with device tensors are asynchronous with respect to the host.  Calls
+ *     that are handed host tensors (device_type kDLCPU / kDLCUDAHost) stage them
+ *     through the device on `stream` and return after the results are back in the
+ *     host buffers (this is the faiss-like numpy-in / numpy-out path).
+ *   - handles are immutable between rs_index_add calls, so concurrent searches on
+ *     one handle from several host threads are allowed.
+ */
+#ifndef RECSYS_B200_H_
+#define RECSYS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- minimal DLPack tensor ABI (matches dlpack.h; include that instead if you have it) ---- */
+#ifndef DLPACK_DLPACK_H_
+typedef enum { kDLCPU = 1, kDLCUDA = 2, kDLCUDAHost = 3 } DLDeviceType;
+typedef struct { int32_t device_type; int32_t device_id; } DLDevice;
+typedef enum { kDLInt = 0U, kDLUInt = 1U, kDLFloat = 2U, kDLBfloat = 4U } DLDataTypeCode;
+typedef struct { uint8_t code; uint8_t bits; uint16_t lanes; } DLDataType;
+typedef struct {
+  void* data;
+  DLDevice device;
+  int32_t ndim;
+  DLDataType dtype;
+  int64_t* shape;
+  int64_t* strides; /* in elements; NULL = compact row-major */
+  uint64_t byte_offset;
+} DLTensor;
+#endif
+
+#define RS_ABI_VERSION 1
+
+/* activation codes for rs_dense_forward */
+#define RS_ACT_NONE 0
+#define RS_ACT_RELU 1
+#define RS_ACT_SIGMOID 2
+
+/* arithmetic modes of the search and ranking entries */
+#define RS_EXACT_FP32 0 /* fp32 FMA chain; index-exact and bit-exact vs the oracle        */
+#define RS_TENSOR_BF16 1 /* tcgen05 bf16 pre-filter + exact fp32 re-score (same results)   */
+#define RS_AUTO 2        /* library picks by query count and catalog size                 */
+
+int rs_version(void);
+const char* rs_last_error(void);
+/* number of SMs of the current device; fails (no fallback) when no CUDA device is usable */
+int rs_device_sm_count(int* out);
+
+/*
+ * K1. Embedding row gather fused with the concat.
+ * Replaces keras.layers.Embedding lookups (src/models.py:71,74,85,89) and, when several
+ * tables are given, the tf.concat that follows (src/models.py:128).
+ *   tables[t] : float32 [V_t, E_t] device, row-major
+ *   ids[t]    : int32 or int64 [B] device (row numbers, i.e. StringLookup output)
+ *   out       : float32 [B, sum_t E_t] device; row stride may exceed the width
+ * Rows outside [0, V_t) produce zeros (TensorFlow's GPU gather behaviour).
+ */
+int rs_gather_concat(int n_tables, const DLTensor* const* tables, const DLTensor* const* ids,
+                     DLTensor* out, void* stream);
+
+/*
+ * K2. One Keras Dense layer: y = act(x @ kernel + bias), kernel stored (in, out).
+ * Replaces keras.layers.Dense inside user_tower / item_tower / deep_nets
+ * (src/models.py:26-29,76-77).  x: f32 [B, in], y: f32 [B, out]; both may be column
+ * slices of wider buffers (row stride >= width), which is how a tower writes straight
+ * into the concatenated DCN input.  fp32 FMA arithmetic, k ascending.
+ */
+int rs_dense_forward(const DLTensor* x, const DLTensor* kernel, const DLTensor* bias, int act,
+                     DLTensor* y, void* stream);
+
+/*
+ * K3a. DCN-v1 cross stack (src/models.py:38-44):
+ *   for i < n_layers:  s = x_l . w_i  (per row);  x_{l+1} = x0 * s + b_i + x_l
+ *   x0: f32 [B, D]; cross_w: f32 [n_layers, D]; cross_b: f32 [n_layers, D];
+ *   out: f32 [B, D] (may be a column slice of the [B, D + deep] concat, src/models.py:50)
+ */
+int rs_dcn_cross_forward(const DLTensor* x0, const DLTensor* cross_w, const DLTensor* cross_b,
+                         DLTensor* out, void* stream);
+
+/*
+ * K3b. The two ranking heads on the DCN output (src/models.py:119-120,131):
+ *   rating = z . w_r + b_r ;  ctr = sigmoid(z . w_c + b_c)
+ *   z: f32 [B, W]; head_w: f32 [2, W] (row 0 = rating, row 1 = ctr); head_b: f32 [2];
+ *   rating, ctr: f32 [B, 1]
+ */
+int rs_heads_forward(const DLTensor* z, const DLTensor* head_w, const DLTensor* head_b,
+                     DLTensor* rating, DLTensor* ctr, void* stream);
+
+/*
+ * K4. faiss.normalize_L2 (src/trainer.py:240, app/recommendation_service.py:71):
+ * in place x_i *= 1/sqrt(sum_j x_ij^2), all-zero rows untouched.  x: f32 [n, d],
+ * device or host.
+ */
+int rs_normalize_l2(DLTensor* x, void* stream);
+
+/* K5. faiss.IndexFlatIP (src/trainer.py:241-242, app/recommendation_service.py:47-50,72). */
+typedef struct rs_index rs_index_t;
+int rs_index_create(int d, rs_index_t** out);          /* faiss.IndexFlatIP(d)                 */
+int rs_index_free(rs_index_t* h);
+int rs_index_add(rs_index_t* h, const DLTensor* x, void* stream);   /* index.add(x); copies x   */
+int rs_index_ntotal(const rs_index_t* h, int64_t* out);             /* index.ntotal             */
+int rs_index_dim(const rs_index_t* h, int* out);                    /* index.d                  */
+/* copy stored rows [i0, i0 + out.shape[0]) into out (f32 [n, d], host or device); faiss reconstruct_n,
+ * used by write_index (src/trainer.py:243) */
+int rs_index_reconstruct(const rs_index_t* h, int64_t i0, DLTensor* out, void* stream);
+/*
+ * index.search(q, k) -> (D, I): for every query the k largest q.x, score descending then
+ * row ascending; rows short of k are padded with (D = -FLT_MAX, I = -1).
+ *   q: f32 [nq, d]; D: f32 [nq, k]; I: int64 [nq, k]; all device or all host.
+ *   id_base is added to every returned row number (shard offset of a partitioned catalog).
+ *   mode: RS_EXACT_FP32 | RS_TENSOR_BF16 | RS_AUTO -- all three return identical results.
+ */
+int rs_index_search(rs_index_t* h, const DLTensor* q, int k, int64_t id_base, int mode, DLTensor* D,
+                    DLTensor* I, void* stream);
+
+/*
+ * K6. tf.linalg.matvec(item_embeddings, user_embedding[0]) (app/recommendation_service.py:91):
+ * raw, un-normalised dots.  items: f32 [n, d]; user: f32 [d]; out: f32 [n]; device.
+ */
+int rs_matvec(const DLTensor* items, const DLTensor* user, DLTensor* out, void* stream);
+
+/*
+ * K7. Merge of per-shard top-k lists after the all-gather (new in this build; BASELINE
+ * config 3).  Dparts: f32 [nparts, nq, k]; Iparts: int64 [nparts, nq, k] (global ids,
+ * -1 = padding); D: f32 [nq, k]; I: int64 [nq, k]; device.  Order (score desc, id asc).
+ */
+int rs_topk_merge(const DLTensor* Dparts, const DLTensor* Iparts, DLTensor* D, DLTensor* I,
+                  void* stream);
+
+/* counters for the bench's gpu_launches claim: kernels launched by this library so far */
+int64_t rs_launch_count(void);
+
+/*
+ * Per-kernel device timing for the bench's roofline line: when enabled, the library brackets the
+ * launches of each kernel family with CUDA events on the launching stream.  rs_prof_read waits for the
+ * recorded events of one slot and returns their summed duration and count, then clears the slot.
+ */
+#define RS_PROF_SCAN 0     /* scan_topk_kernel (exact fp32 catalog scan)          */
+#define RS_PROF_MERGE 1    /* merge_topk_kernel                                   */
+#define RS_PROF_FILTER 2   /* tcgen05 bf16 pre-filter                             */
+#define RS_PROF_RESCORE 3  /* candidate select + exact re-score                   */
+#define RS_PROF_RANK 4     /* fused ranking forward                               */
+#define RS_PROF_SLOTS 8
+int rs_prof_enable(int on);
+int rs_prof_read(int slot, double* total_ms, int64_t* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RECSYS_B200_H_ */

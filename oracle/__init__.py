@@ -1,0 +1,33 @@
+"""oracle -- TEST INFRASTRUCTURE ONLY.
+
+CPU restatement of the reference's serving/scoring hot path
+(`src/models.py`, `app/recommendation_service.py`, and the faiss-cpu /
+TensorFlow semantics those files delegate to).  It exists to *check* the CUDA
+path and to be timed as the CPU baseline.  Only `tests/`,
+`__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl reference`
+legs may import it; the product package never does.
+
+PARITY UNPINNED: TensorFlow, Keras, tensorflow-recommenders and faiss are not
+importable in this image and the reference ships no golden vectors, fixtures or
+numeric tests for this path.  The restatement is pinned
+by known-answer tests (tests/test_oracle_known_answers.py) and by committed
+fixtures generated from it (tests/golden/), not by reference outputs.
+"""
+
+from .build import build_chain_lib, load_chain_lib  # noqa: F401
+from .flat_ip import (  # noqa: F401
+    IndexFlatIP,
+    matvec,
+    merge_topk,
+    normalize_L2,
+    search_blas,
+    search_chain,
+)
+from .models import (  # noqa: F401
+    DeepCrossNetwork,
+    MultiTaskModel,
+    MultiTowerModel,
+    dense,
+    string_lookup,
+)
+from .service import RecommendationService  # noqa: F401

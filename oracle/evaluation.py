@@ -1,0 +1,38 @@
+"""Restatement of the top-K consumer, AdvancedMetrics (src/evaluation.py:25-81).  TEST INFRASTRUCTURE ONLY.
+
+The reference module cannot be imported here (it imports keras at module scope), so the hand-off test
+(the drop-in's recommend() output feeds these functions unchanged) uses this copy of the signatures:
+predictions: List[List[str]] ranked item ids per user; ground_truth: List[str] one true item per user.
+"""
+
+from typing import List
+
+import numpy as np
+
+
+def recall_at_k(predictions: List[List[str]], ground_truth: List[str], k: int) -> float:      # :25-32
+    r = [1.0 if t in p[:k] else 0.0 for p, t in zip(predictions, ground_truth)]
+    return float(np.mean(r)) if r else 0.0
+
+
+def precision_at_k(predictions: List[List[str]], ground_truth: List[str], k: int) -> float:   # :34-41
+    r = [1.0 / len(p[:k]) if t in p[:k] else 0.0 for p, t in zip(predictions, ground_truth)]
+    return float(np.mean(r)) if r else 0.0
+
+
+def ndcg_at_k(predictions: List[List[str]], ground_truth: List[str], k: int) -> float:        # :43-56
+    out = []
+    for p, t in zip(predictions, ground_truth):
+        top = p[:k]
+        out.append((1.0 / np.log2(top.index(t) + 2)) / (1.0 / np.log2(2)) if t in top else 0.0)
+    return float(np.mean(out)) if out else 0.0
+
+
+def map_at_k(predictions: List[List[str]], ground_truth: List[str], k: int) -> float:         # :58-69
+    out = [1.0 / (p[:k].index(t) + 1) if t in p[:k] else 0.0 for p, t in zip(predictions, ground_truth)]
+    return float(np.mean(out)) if out else 0.0
+
+
+def mrr(predictions: List[List[str]], ground_truth: List[str]) -> float:                      # :71-81
+    out = [1.0 / (p.index(t) + 1) if t in p else 0.0 for p, t in zip(predictions, ground_truth)]
+    return float(np.mean(out)) if out else 0.0

@@ -1,0 +1,176 @@
+"""ctypes binding of librecsys_b200.so (include/recsys_b200.h) with DLPack tensor exchange.
+
+There is no CPU fallback: if the shared library cannot be built/loaded, or no sm_100 device is usable,
+the first call raises.  Tensors are handed to C as borrowed `DLTensor*` taken from the objects' own
+`__dlpack__()` capsules (torch tensors and numpy arrays both provide one); the capsule is kept alive
+for the duration of the call and then dropped, which runs the producer's deleter.
+"""
+
+import ctypes
+import os
+from pathlib import Path
+
+import numpy as np
+import torch
+
+_HERE = Path(__file__).resolve().parent
+_LIB_PATH = _HERE / "librecsys_b200.so"
+
+RS_ACT_NONE, RS_ACT_RELU, RS_ACT_SIGMOID = 0, 1, 2
+RS_EXACT_FP32, RS_TENSOR_BF16, RS_AUTO = 0, 1, 2
+_ACT = {None: RS_ACT_NONE, "linear": RS_ACT_NONE, "relu": RS_ACT_RELU, "sigmoid": RS_ACT_SIGMOID}
+_MODE = {"exact": RS_EXACT_FP32, "tensor": RS_TENSOR_BF16, "auto": RS_AUTO}
+
+
+class DLDevice(ctypes.Structure):
+    _fields_ = [("device_type", ctypes.c_int32), ("device_id", ctypes.c_int32)]
+
+
+class DLDataType(ctypes.Structure):
+    _fields_ = [("code", ctypes.c_uint8), ("bits", ctypes.c_uint8), ("lanes", ctypes.c_uint16)]
+
+
+class DLTensor(ctypes.Structure):
+    _fields_ = [("data", ctypes.c_void_p), ("device", DLDevice), ("ndim", ctypes.c_int32),
+                ("dtype", DLDataType), ("shape", ctypes.POINTER(ctypes.c_int64)),
+                ("strides", ctypes.POINTER(ctypes.c_int64)), ("byte_offset", ctypes.c_uint64)]
+
+
+_DLP = ctypes.POINTER(DLTensor)
+_capsule_get = ctypes.pythonapi.PyCapsule_GetPointer
+_capsule_get.restype = ctypes.c_void_p
+_capsule_get.argtypes = [ctypes.py_object, ctypes.c_char_p]
+
+_lib = None
+
+
+def _needs_build() -> bool:
+    if not _LIB_PATH.exists():
+        return True
+    t = _LIB_PATH.stat().st_mtime
+    srcs = list((_HERE / "csrc").glob("*.cu")) + list((_HERE / "csrc").glob("*.cuh"))
+    srcs.append(_HERE.parent / "include" / "recsys_b200.h")
+    return any(s.exists() and s.stat().st_mtime > t for s in srcs)
+
+
+def load():
+    """Load (building first if the in-tree .so is missing or older than its sources)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if _needs_build():
+        nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+        if os.path.exists(nvcc):
+            from .build import build
+            build()
+        elif not _LIB_PATH.exists():
+            raise RuntimeError(f"{_LIB_PATH} is missing and nvcc is not available to build it; "
+                               "run recommendation-system-maang-nvidia-_b200/build.py where nvcc exists")
+    lib = ctypes.CDLL(str(_LIB_PATH))
+    vp, i32, i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
+    lib.rs_version.restype = i32
+    lib.rs_last_error.restype = ctypes.c_char_p
+    lib.rs_launch_count.restype = i64
+    sigs = {
+        "rs_device_sm_count": [ctypes.POINTER(i32)],
+        "rs_gather_concat": [i32, ctypes.POINTER(_DLP), ctypes.POINTER(_DLP), _DLP, vp],
+        "rs_dense_forward": [_DLP, _DLP, _DLP, i32, _DLP, vp],
+        "rs_dcn_cross_forward": [_DLP, _DLP, _DLP, _DLP, vp],
+        "rs_heads_forward": [_DLP, _DLP, _DLP, _DLP, _DLP, vp],
+        "rs_normalize_l2": [_DLP, vp],
+        "rs_index_create": [i32, ctypes.POINTER(vp)],
+        "rs_index_free": [vp],
+        "rs_index_add": [vp, _DLP, vp],
+        "rs_index_ntotal": [vp, ctypes.POINTER(i64)],
+        "rs_index_dim": [vp, ctypes.POINTER(i32)],
+        "rs_index_reconstruct": [vp, i64, _DLP, vp],
+        "rs_index_search": [vp, _DLP, i32, i64, i32, _DLP, _DLP, vp],
+        "rs_matvec": [_DLP, _DLP, _DLP, vp],
+        "rs_topk_merge": [_DLP, _DLP, _DLP, _DLP, vp],
+        "rs_prof_enable": [i32],
+        "rs_prof_read": [i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64)],
+    }
+    for name, argtypes in sigs.items():
+        fn = getattr(lib, name)
+        fn.restype = i32
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+EXPORTED = ["rs_version", "rs_last_error", "rs_launch_count", "rs_device_sm_count", "rs_gather_concat",
+            "rs_dense_forward", "rs_dcn_cross_forward", "rs_heads_forward", "rs_normalize_l2", "rs_index_create",
+            "rs_index_free", "rs_index_add", "rs_index_ntotal", "rs_index_dim", "rs_index_reconstruct", "rs_index_search",
+            "rs_matvec", "rs_topk_merge", "rs_prof_enable", "rs_prof_read"]
+
+PROF_SCAN, PROF_MERGE, PROF_FILTER, PROF_RESCORE, PROF_RANK = 0, 1, 2, 3, 4
+
+
+def check(status: int) -> None:
+    if status != 0:
+        msg = load().rs_last_error()
+        raise RuntimeError("librecsys_b200: " + (msg.decode() if msg else f"status {status}"))
+
+
+class _Borrowed:
+    """A DLTensor* borrowed from obj.__dlpack__(); keeps the capsule (and obj) alive."""
+
+    __slots__ = ("obj", "capsule", "ptr")
+
+    def __init__(self, obj):
+        self.obj = obj
+        if isinstance(obj, torch.Tensor):
+            self.capsule = obj.__dlpack__(stream=-1) if obj.is_cuda else obj.__dlpack__()
+        elif isinstance(obj, np.ndarray):
+            self.capsule = obj.__dlpack__()
+        else:
+            raise TypeError(f"cannot export {type(obj)} through DLPack")
+        self.ptr = ctypes.cast(_capsule_get(self.capsule, b"dltensor"), _DLP)
+
+
+def dl(obj):
+    """None -> NULL pointer; tensor/array -> borrowed DLTensor*."""
+    if obj is None:
+        return None
+    return _Borrowed(obj)
+
+
+def ptr(b):
+    return b.ptr if b is not None else None
+
+
+def stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def sm_count() -> int:
+    out = ctypes.c_int(0)
+    check(load().rs_device_sm_count(ctypes.byref(out)))
+    return out.value
+
+
+def launch_count() -> int:
+    return int(load().rs_launch_count())
+
+
+def prof_enable(on: bool) -> None:
+    check(load().rs_prof_enable(1 if on else 0))
+
+
+def prof_read(slot: int):
+    """-> (total_ms, launches) of the event-bracketed launches of one kernel family since the last read."""
+    ms, n = ctypes.c_double(0.0), ctypes.c_int64(0)
+    check(load().rs_prof_read(slot, ctypes.byref(ms), ctypes.byref(n)))
+    return ms.value, n.value
+
+
+def act_code(activation) -> int:
+    if activation not in _ACT:
+        raise ValueError(f"unsupported activation {activation!r}")
+    return _ACT[activation]
+
+
+def mode_code(mode) -> int:
+    if mode not in _MODE:
+        raise ValueError(f"mode must be one of {sorted(_MODE)}")
+    return _MODE[mode]

@@ -1,0 +1,234 @@
+// common.cuh -- shared host/device helpers for librecsys_b200 (sm_100a only).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+
+#include "../../include/recsys_b200.h"
+
+// --------------------------------------------------------------------------------------
+// host: errors, DLTensor validation
+// --------------------------------------------------------------------------------------
+namespace rs {
+
+struct Error : public std::runtime_error {
+  explicit Error(const std::string& m) : std::runtime_error(m) {}
+};
+
+void set_last_error(const std::string& m);
+extern std::atomic<int64_t> g_launches;
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+#define RS_CHECK(cond, msg)                                                          \
+  do {                                                                               \
+    if (!(cond)) throw ::rs::Error(std::string(__func__) + ": " + (msg));            \
+  } while (0)
+
+#define RS_CUDA(expr)                                                                \
+  do {                                                                               \
+    cudaError_t _e = (expr);                                                         \
+    if (_e != cudaSuccess)                                                           \
+      throw ::rs::Error(std::string(__func__) + ": " #expr " -> " + cudaGetErrorString(_e)); \
+  } while (0)
+
+#define RS_LAUNCH_CHECK()                                                            \
+  do {                                                                               \
+    cudaError_t _e = cudaGetLastError();                                             \
+    if (_e != cudaSuccess)                                                           \
+      throw ::rs::Error(std::string(__func__) + ": kernel launch -> " + cudaGetErrorString(_e)); \
+    ::rs::count_launch();                                                            \
+  } while (0)
+
+// Every extern "C" entry is `return guard([&]{ ... });`
+template <class F>
+inline int guard(F&& f) {
+  try {
+    f();
+    return 0;
+  } catch (const std::exception& e) {
+    set_last_error(e.what());
+    return 1;
+  } catch (...) {
+    set_last_error("unknown error");
+    return 2;
+  }
+}
+
+inline bool is_dtype(const DLTensor* t, uint8_t code, uint8_t bits) {
+  return t->dtype.code == code && t->dtype.bits == bits && t->dtype.lanes == 1;
+}
+inline bool on_device(const DLTensor* t) { return t->device.device_type == kDLCUDA; }
+inline bool on_host(const DLTensor* t) {
+  return t->device.device_type == kDLCPU || t->device.device_type == kDLCUDAHost;
+}
+inline int64_t stride_of(const DLTensor* t, int dim) {
+  if (t->strides) return t->strides[dim];
+  int64_t s = 1;
+  for (int i = t->ndim - 1; i > dim; --i) s *= t->shape[i];
+  return s;
+}
+inline bool is_compact(const DLTensor* t) {
+  int64_t s = 1;
+  for (int i = t->ndim - 1; i >= 0; --i) {
+    if (t->shape[i] != 1 && stride_of(t, i) != s) return false;
+    s *= t->shape[i];
+  }
+  return true;
+}
+template <class T>
+inline T* data_ptr(const DLTensor* t) {
+  return reinterpret_cast<T*>(static_cast<char*>(t->data) + t->byte_offset);
+}
+inline void require(const DLTensor* t, const char* name, int ndim, uint8_t code, uint8_t bits) {
+  RS_CHECK(t != nullptr, std::string(name) + " is NULL");
+  RS_CHECK(t->ndim == ndim, std::string(name) + ": expected ndim " + std::to_string(ndim) + ", got " +
+                                std::to_string(t->ndim));
+  RS_CHECK(is_dtype(t, code, bits), std::string(name) + ": wrong dtype (code " +
+                                        std::to_string(t->dtype.code) + ", bits " +
+                                        std::to_string(t->dtype.bits) + ")");
+}
+// 2-D tensor whose last dim is contiguous; returns the row stride in elements
+inline int64_t row_stride_2d(const DLTensor* t, const char* name) {
+  RS_CHECK(t->shape[1] == 1 || stride_of(t, 1) == 1, std::string(name) + ": last dim must be contiguous");
+  return t->shape[0] <= 1 ? t->shape[1] : stride_of(t, 0);
+}
+inline void require_aligned16(const void* p, const char* name) {
+  RS_CHECK((reinterpret_cast<uintptr_t>(p) & 15) == 0, std::string(name) + ": data must be 16-byte aligned");
+}
+
+int sm_count();  // SMs of the current device (cached per device)
+
+// Brackets a kernel family's launches with CUDA events when rs_prof_enable(1) is active.
+struct ProfScope {
+  int slot;
+  cudaStream_t st;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  ProfScope(int slot, cudaStream_t st);
+  ~ProfScope();
+};
+
+// cuTensorMapEncodeTiled fetched through the runtime (no -lcuda link)
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+encode_tiled_fn get_encode_tiled();
+
+// 2-D row-major [rows, cols] tensor map with a [box_rows, box_cols] box and 128-byte swizzle
+CUtensorMap make_tmap_2d(const void* base, CUtensorMapDataType dt, int elem_bytes, uint64_t rows, uint64_t cols,
+                         uint64_t row_stride_bytes, uint32_t box_rows, uint32_t box_cols);
+
+}  // namespace rs
+
+// --------------------------------------------------------------------------------------
+// device: PTX wrappers (mbarrier, TMA), packed top-k keys
+// --------------------------------------------------------------------------------------
+namespace rsd {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (the launch fails with an error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("recsys_b200: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y,
+             threadIdx.x);
+      __trap();
+    }
+  }
+}
+
+// L2 cache policies (the fixed encodings CUTLASS uses for createpolicy results)
+constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
+constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
+constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0,
+                                            int c1, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+
+// ---- packed (score, row) keys: larger key == better hit under (score desc, row asc) ----
+__device__ __forceinline__ uint32_t f32_to_ordered(float s) {
+  s += 0.0f;  // -0 -> +0 so that equal floats give equal keys
+  const uint32_t u = __float_as_uint(s);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ordered_to_f32(uint32_t o) {
+  const uint32_t u = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
+  return __uint_as_float(u);
+}
+__device__ __forceinline__ uint64_t pack_key(float s, uint32_t row) {
+  return (static_cast<uint64_t>(f32_to_ordered(s)) << 32) | static_cast<uint64_t>(0xFFFFFFFFu - row);
+}
+__device__ __forceinline__ float key_score(uint64_t k) { return ordered_to_f32(static_cast<uint32_t>(k >> 32)); }
+__device__ __forceinline__ uint32_t key_row(uint64_t k) { return 0xFFFFFFFFu - static_cast<uint32_t>(k); }
+constexpr uint64_t kEmptyKey = 0ull;  // below every real key (ordered(-inf) = 0x007FFFFF)
+
+// CTA-wide bitonic sort, descending, of a[0..CAP) in shared memory; ends with __syncthreads().
+template <int CAP, int NT>
+__device__ __forceinline__ void block_sort_desc(uint64_t* a, int tid) {
+#pragma unroll 1
+  for (int size = 2; size <= CAP; size <<= 1) {
+#pragma unroll 1
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = tid; i < CAP / 2; i += NT) {
+        const int lo = 2 * i - (i & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc = (lo & size) == 0;
+        const uint64_t x = a[lo], y = a[hi];
+        if ((x < y) == desc) {
+          a[lo] = y;
+          a[hi] = x;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+}  // namespace rsd

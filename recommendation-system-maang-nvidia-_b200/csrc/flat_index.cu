@@ -1,0 +1,590 @@
+// flat_index.cu -- K4/K5/K6/K7 (exact fp32 mode): the FAISS IndexFlatIP replacement.
+//
+// Replaces faiss.IndexFlatIP.add/search (src/trainer.py:241-242, app/recommendation_service.py:72),
+// faiss.normalize_L2 (src/trainer.py:240, app/recommendation_service.py:71) and
+// tf.linalg.matvec (app/recommendation_service.py:91).
+//
+// scan_topk_kernel -- the catalog scan.  HBM-bound: the fp32 catalog ([N, d] row-major, the layout
+// faiss keeps) is streamed once per group of QT queries through a 3-stage shared-memory ring filled by
+// TMA (cp.async.bulk.tensor, 128-byte swizzle, one mbarrier per stage).  One thread scores one catalog
+// row of the tile against the QT resident queries with the stated arithmetic -- a single fp32
+// accumulator per (query, row), fused multiply-add, feature index ascending -- which the oracle
+// (oracle/chain.c) reproduces bit for bit.  The swizzle makes the row-per-thread 128-bit shared loads
+// bank-conflict free.  Scores never go to HBM: each is compared in registers with the CTA's running
+// k-th key and only the rare survivors enter the shared-memory candidate buffer (topk.cuh).
+// Algorithmic bytes: N*d*4 per query group (+ nq*d*4 queries, + nq*P*k*8 partial lists).
+//
+// merge_topk_kernel -- one CTA per query merges the P per-CTA lists (or the G per-shard lists after
+// the all-gather) in rank-major order with early termination.
+#include <algorithm>
+#include <cfloat>
+
+#include "flat_index.cuh"
+#include "topk.cuh"
+
+namespace {
+
+using namespace rsd;
+
+constexpr int TILE_ROWS = 128;  // catalog rows per pipeline stage == compute threads
+constexpr int SCAN_NT = 128;
+constexpr int STAGES = 3;
+constexpr int MERGE_NT = 256;
+
+template <int D, int QT, int CAP>
+struct ScanSmem {
+  static constexpr int kStageBytes = TILE_ROWS * D * 4;
+  static constexpr int kKeysOff = STAGES * kStageBytes;
+  static constexpr int kQOff = kKeysOff + QT * CAP * 8;
+  static constexpr int kBarOff = kQOff + QT * D * 4;
+  static constexpr int kCntOff = kBarOff + STAGES * 8;
+  static constexpr int kTotal = kCntOff + QT * 4;
+  static constexpr int kDynamic = kTotal + 1024;  // slack for the 1024-byte alignment of the ring
+};
+
+template <int D, int QT, int CAP>
+__global__ void __launch_bounds__(SCAN_NT, 1)
+scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ q, int64_t n, int nq, int k,
+                 uint64_t* __restrict__ partial) {
+  using L = ScanSmem<D, QT, CAP>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* keys = reinterpret_cast<uint64_t*>(base + L::kKeysOff);
+  float* qs = reinterpret_cast<float*>(base + L::kQOff);
+  uint64_t* full = reinterpret_cast<uint64_t*>(base + L::kBarOff);
+  int* cnt = reinterpret_cast<int*>(base + L::kCntOff);
+
+  const int tid = threadIdx.x;
+  const int qbase = blockIdx.y * QT;
+  const int64_t ntiles = (n + TILE_ROWS - 1) / TILE_ROWS;
+  const int64_t my_tiles = (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tmap);
+    for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
+    fence_mbar_init();
+  }
+  for (int i = tid; i < QT * D; i += SCAN_NT) {
+    const int g = i / D;
+    qs[i] = (qbase + g < nq) ? q[(int64_t)(qbase + g) * D + (i - g * D)] : 0.0f;
+  }
+  for (int i = tid; i < QT * CAP; i += SCAN_NT) keys[i] = kEmptyKey;
+  if (tid < QT) cnt[tid] = 0;
+  __syncthreads();
+
+  auto issue = [&](int stage, int64_t it) {
+    const int64_t tile = blockIdx.x + it * gridDim.x;
+    mbar_arrive_expect_tx(&full[stage], L::kStageBytes);
+#pragma unroll
+    for (int j = 0; j < D / 32; ++j)
+      tma_load_2d(base + stage * L::kStageBytes + j * (TILE_ROWS * 128), &tmap, &full[stage], j * 32,
+                  static_cast<int>(tile * TILE_ROWS), kEvictFirst);
+  };
+  if (tid == 0)
+    for (int s = 0; s < STAGES && s < my_tiles; ++s) issue(s, s);
+
+  uint64_t thr[QT];
+#pragma unroll
+  for (int g = 0; g < QT; ++g) thr[g] = kEmptyKey;
+
+  const uint32_t sw = static_cast<uint32_t>(tid & 7) << 4;
+  for (int64_t it = 0; it < my_tiles; ++it) {
+    const int stage = static_cast<int>(it % STAGES);
+    mbar_wait(&full[stage], static_cast<uint32_t>((it / STAGES) & 1));
+
+    // ---- score: row `tid` of the tile against QT queries, one FMA chain each ----
+    float acc[QT];
+#pragma unroll
+    for (int g = 0; g < QT; ++g) acc[g] = 0.0f;
+    const uint8_t* srow = base + stage * L::kStageBytes + tid * 128;
+#pragma unroll
+    for (int j = 0; j < D / 32; ++j) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float4 xv = *reinterpret_cast<const float4*>(srow + j * (TILE_ROWS * 128) + ((c << 4) ^ sw));
+#pragma unroll
+        for (int g = 0; g < QT; ++g) {
+          const float4 qv = *reinterpret_cast<const float4*>(qs + g * D + j * 32 + c * 4);
+          acc[g] = fmaf(qv.x, xv.x, acc[g]);
+          acc[g] = fmaf(qv.y, xv.y, acc[g]);
+          acc[g] = fmaf(qv.z, xv.z, acc[g]);
+          acc[g] = fmaf(qv.w, xv.w, acc[g]);
+        }
+      }
+    }
+
+    // ---- select: threshold-reject in registers, survivors to the candidate buffers ----
+    const int64_t row = (blockIdx.x + it * gridDim.x) * TILE_ROWS + tid;
+    uint64_t key[QT];
+    uint32_t pend = 0;
+#pragma unroll
+    for (int g = 0; g < QT; ++g) {
+      key[g] = pack_key(acc[g], static_cast<uint32_t>(row));
+      if (row < n && qbase + g < nq && key[g] > thr[g]) pend |= 1u << g;
+    }
+    for (;;) {
+      bool saw_full = false;
+#pragma unroll
+      for (int g = 0; g < QT; ++g) {
+        if (pend & (1u << g)) {
+          const int pos = atomicAdd(&cnt[g], 1);
+          if (pos < CAP) {
+            keys[g * CAP + pos] = key[g];
+            pend &= ~(1u << g);
+          }
+          saw_full |= pos >= CAP - 1;
+        }
+      }
+      // this barrier also orders every thread's reads of the stage before the refill below
+      if (!__syncthreads_or(pend != 0 || saw_full)) break;
+#pragma unroll
+      for (int g = 0; g < QT; ++g) {
+        if (cnt[g] >= CAP) {  // uniform: nobody touches cnt between the barrier and the prune
+          thr[g] = prune_buffer<CAP, SCAN_NT>(keys + g * CAP, &cnt[g], k, tid);
+          if ((pend & (1u << g)) && !(key[g] > thr[g])) pend &= ~(1u << g);
+        }
+      }
+      __syncthreads();
+    }
+    if (tid == 0 && it + STAGES < my_tiles) issue(stage, it + STAGES);
+  }
+
+  // ---- emit this CTA's sorted list for each query ----
+  const int P = gridDim.x;
+#pragma unroll 1
+  for (int g = 0; g < QT; ++g) {
+    if (qbase + g >= nq) break;
+    prune_buffer<CAP, SCAN_NT>(keys + g * CAP, &cnt[g], k, tid);
+    uint64_t* dst = partial + ((int64_t)(qbase + g) * P + blockIdx.x) * k;
+    for (int j = tid; j < k; j += SCAN_NT) dst[j] = keys[g * CAP + j];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// merge of sorted lists.  Source A: packed keys [nq][P][k] (rows local to the index).
+// Source B: (score, id) pairs [P][nq][k] (global ids, -1 = padding) after an all-gather.
+// ------------------------------------------------------------------------------------------------
+struct KeySource {
+  const uint64_t* keys;  // A
+  const float* Dp;       // B
+  const int64_t* Ip;     // B
+  int64_t nq;
+  __device__ __forceinline__ uint64_t load(int64_t qi, int p, int P, int r, int k) const {
+    if (keys) return keys[((int64_t)qi * P + p) * k + r];
+    const int64_t o = ((int64_t)p * nq + qi) * k + r;
+    const int64_t id = Ip[o];
+    return id < 0 ? kEmptyKey : pack_key(Dp[o], static_cast<uint32_t>(id));
+  }
+};
+
+template <int CAP>
+__global__ void __launch_bounds__(MERGE_NT)
+merge_topk_kernel(const KeySource src, int P, int k, int64_t id_base, float* __restrict__ D, int64_t ldD,
+                  int64_t* __restrict__ I, int64_t ldI) {
+  __shared__ uint64_t keys[CAP];
+  __shared__ int cnt;
+  const int tid = threadIdx.x;
+  const int64_t qi = blockIdx.x;
+  for (int i = tid; i < CAP; i += MERGE_NT) keys[i] = kEmptyKey;
+  if (tid == 0) cnt = 0;
+  __syncthreads();
+  uint64_t thr = kEmptyKey;
+  const int64_t total = (int64_t)P * k;
+  int quiet = 0;  // consecutive elements (rank-major) in which no list offered a key
+  for (int64_t e0 = 0; e0 < total; e0 += MERGE_NT) {
+    const int64_t e = e0 + tid;
+    uint64_t key = kEmptyKey;
+    if (e < total) {
+      const int r = static_cast<int>(e / P);
+      const int p = static_cast<int>(e - (int64_t)r * P);
+      key = src.load(qi, p, P, r, k);
+    }
+    const bool any = offer_one<CAP, MERGE_NT>(keys, &cnt, k, key != kEmptyKey, key, thr, tid);
+    quiet = any ? 0 : quiet + MERGE_NT;
+    if (quiet >= P) break;  // every list's next entry already lost; lists are sorted, so we are done
+  }
+  prune_buffer<CAP, MERGE_NT>(keys, &cnt, k, tid);
+  for (int j = tid; j < k; j += MERGE_NT) {
+    const uint64_t key = keys[j];
+    if (key == kEmptyKey) {
+      D[qi * ldD + j] = -FLT_MAX;
+      I[qi * ldI + j] = -1;
+    } else {
+      D[qi * ldD + j] = key_score(key);
+      I[qi * ldI + j] = id_base + static_cast<int64_t>(key_row(key));
+    }
+  }
+}
+
+__global__ void fill_pad_kernel(float* D, int64_t ldD, int64_t* I, int64_t ldI, int64_t nq, int k) {
+  const int64_t total = nq * k;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / k;
+    const int j = static_cast<int>(i - r * k);
+    D[r * ldD + j] = -FLT_MAX;
+    I[r * ldI + j] = -1;
+  }
+}
+
+// K4: one thread per row, the stated chain over x_j^2 then x_j *= 1/sqrt(nr); zero rows untouched
+__global__ void __launch_bounds__(128) normalize_l2_kernel(float* __restrict__ x, int64_t ld, int64_t n, int d) {
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  float* row = x + r * ld;
+  float nr = 0.0f;
+  for (int j = 0; j < d; ++j) nr = fmaf(row[j], row[j], nr);
+  if (nr > 0.0f) {
+    const float inv = 1.0f / sqrtf(nr);
+    for (int j = 0; j < d; ++j) row[j] *= inv;
+  }
+}
+
+// K6: one thread per item row, the stated chain (n <= 100 on the /score path)
+__global__ void __launch_bounds__(128) matvec_kernel(const float* __restrict__ items, int64_t ld,
+                                                     const float* __restrict__ user, float* __restrict__ out,
+                                                     int64_t n, int d) {
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const float* row = items + r * ld;
+  float acc = 0.0f;
+  for (int j = 0; j < d; ++j) acc = fmaf(user[j], row[j], acc);
+  out[r] = acc;
+}
+
+template <int CAP>
+void launch_merge(const KeySource& src, int64_t nq, int P, int k, int64_t id_base, float* D, int64_t ldD, int64_t* I,
+                  int64_t ldI, cudaStream_t st) {
+  rs::ProfScope prof(RS_PROF_MERGE, st);
+  merge_topk_kernel<CAP><<<static_cast<unsigned>(nq), MERGE_NT, 0, st>>>(src, P, k, id_base, D, ldD, I, ldI);
+  RS_LAUNCH_CHECK();
+}
+
+void merge_dispatch(const KeySource& src, int64_t nq, int P, int k, int64_t id_base, float* D, int64_t ldD, int64_t* I,
+                    int64_t ldI, cudaStream_t st) {
+  RS_CHECK(k >= 1 && k <= 1024, "k must be in [1, 1024]");
+  RS_CHECK(nq <= 0x7FFFFFFF, "too many queries");
+  if (k <= 128) launch_merge<256>(src, nq, P, k, id_base, D, ldD, I, ldI, st);
+  else if (k <= 256) launch_merge<512>(src, nq, P, k, id_base, D, ldD, I, ldI, st);
+  else if (k <= 512) launch_merge<1024>(src, nq, P, k, id_base, D, ldD, I, ldI, st);
+  else launch_merge<2048>(src, nq, P, k, id_base, D, ldD, I, ldI, st);
+}
+
+template <int D, int QT, int CAP>
+void launch_scan(const rs_index* h, const float* q, int64_t nq, int k, int P, uint64_t* partial, cudaStream_t st) {
+  using L = ScanSmem<D, QT, CAP>;
+  static std::once_flag once[64];
+  std::call_once(once[h->device & 63], [] {
+    cudaFuncSetAttribute(scan_topk_kernel<D, QT, CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic);
+  });
+  const int64_t groups = (nq + QT - 1) / QT;
+  RS_CHECK(groups <= 65535, "too many queries for one search call (limit 524,280)");
+  dim3 grid(static_cast<unsigned>(P), static_cast<unsigned>(groups));
+  rs::ProfScope prof(RS_PROF_SCAN, st);
+  scan_topk_kernel<D, QT, CAP><<<grid, SCAN_NT, L::kDynamic, st>>>(h->tmap_f32, q, h->ntotal, static_cast<int>(nq), k,
+                                                                  partial);
+  RS_LAUNCH_CHECK();
+}
+
+template <int D>
+void scan_dispatch(const rs_index* h, const float* q, int64_t nq, int k, int P, uint64_t* partial, cudaStream_t st) {
+  if (k > 128) return launch_scan<D, 1, 2048>(h, q, nq, k, P, partial, st);
+  if (nq >= 8) return launch_scan<D, 8, 256>(h, q, nq, k, P, partial, st);
+  if (nq > 2) return launch_scan<D, 4, 256>(h, q, nq, k, P, partial, st);
+  if (nq == 2) return launch_scan<D, 2, 256>(h, q, nq, k, P, partial, st);
+  return launch_scan<D, 1, 256>(h, q, nq, k, P, partial, st);
+}
+
+void rebuild_tmaps(rs_index* h) {
+  if (h->ntotal == 0) return;
+  h->tmap_f32 = rs::make_tmap_2d(h->xb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)h->ntotal, (uint64_t)h->d,
+                                 (uint64_t)h->d * 4, TILE_ROWS, 32);
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+}  // namespace
+
+namespace rs {
+
+void search_exact_device(rs_index* h, const float* q, int64_t nq, int k, int64_t id_base, float* D, int64_t ldD,
+                         int64_t* I, int64_t ldI, cudaStream_t st) {
+  RS_CHECK(k >= 1 && k <= 1024, "k must be in [1, 1024]");
+  if (nq == 0) return;
+  if (h->ntotal == 0) {
+    fill_pad_kernel<<<64, 256, 0, st>>>(D, ldD, I, ldI, nq, k);
+    RS_LAUNCH_CHECK();
+    return;
+  }
+  RS_CHECK(h->ntotal <= 0xFFFFFFFFll, "catalog shards above 2^32 rows are not supported");
+  const int64_t ntiles = (h->ntotal + TILE_ROWS - 1) / TILE_ROWS;
+  const int P = static_cast<int>(std::min<int64_t>(ntiles, sm_count()));
+  uint64_t* partial = nullptr;
+  RS_CUDA(cudaMallocAsync(&partial, sizeof(uint64_t) * (size_t)nq * P * k, st));
+  try {
+    switch (h->d) {
+      case 32: scan_dispatch<32>(h, q, nq, k, P, partial, st); break;
+      case 64: scan_dispatch<64>(h, q, nq, k, P, partial, st); break;
+      case 128: scan_dispatch<128>(h, q, nq, k, P, partial, st); break;
+      default: RS_CHECK(false, "index dimension must be 32, 64 or 128 (got " + std::to_string(h->d) + ")");
+    }
+    KeySource src{partial, nullptr, nullptr, nq};
+    merge_dispatch(src, nq, P, k, id_base, D, ldD, I, ldI, st);
+  } catch (...) {
+    cudaFreeAsync(partial, st);
+    throw;
+  }
+  RS_CUDA(cudaFreeAsync(partial, st));
+}
+
+}  // namespace rs
+
+extern "C" {
+
+int rs_index_create(int d, rs_index_t** out) {
+  return rs::guard([&] {
+    RS_CHECK(out != nullptr, "out is NULL");
+    RS_CHECK(d == 32 || d == 64 || d == 128, "index dimension must be 32, 64 or 128");
+    rs::sm_count();  // fails loudly when there is no usable sm_100 device: no CPU fallback
+    auto* h = new rs_index();
+    h->d = d;
+    RS_CUDA(cudaGetDevice(&h->device));
+    *out = h;
+  });
+}
+
+int rs_index_free(rs_index_t* h) {
+  return rs::guard([&] {
+    if (!h) return;
+    {
+      DeviceGuard g(h->device);
+      cudaFree(h->xb);
+      cudaFree(h->xb_bf16);
+      cudaFree(h->row_norm);
+    }
+    delete h;
+  });
+}
+
+int rs_index_ntotal(const rs_index_t* h, int64_t* out) {
+  return rs::guard([&] {
+    RS_CHECK(h && out, "NULL argument");
+    *out = h->ntotal;
+  });
+}
+
+int rs_index_dim(const rs_index_t* h, int* out) {
+  return rs::guard([&] {
+    RS_CHECK(h && out, "NULL argument");
+    *out = h->d;
+  });
+}
+
+int rs_index_reconstruct(const rs_index_t* h, int64_t i0, DLTensor* out, void* stream) {
+  return rs::guard([&] {
+    using namespace rs;
+    RS_CHECK(h != nullptr, "index is NULL");
+    require(out, "out", 2, kDLFloat, 32);
+    RS_CHECK(out->shape[1] == h->d && is_compact(out), "out must be a contiguous [n, d] tensor");
+    const int64_t n = out->shape[0];
+    RS_CHECK(i0 >= 0 && n >= 0 && i0 + n <= h->ntotal, "row range out of bounds");
+    RS_CHECK(on_device(out) || on_host(out), "out must be a CUDA or host tensor");
+    if (n == 0) return;
+    DeviceGuard g(h->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    RS_CUDA(cudaMemcpyAsync(data_ptr<float>(out), h->xb + i0 * h->d, sizeof(float) * (size_t)n * h->d,
+                            on_device(out) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+    if (on_host(out)) RS_CUDA(cudaStreamSynchronize(st));
+  });
+}
+
+int rs_index_add(rs_index_t* h, const DLTensor* x, void* stream) {
+  return rs::guard([&] {
+    using namespace rs;
+    RS_CHECK(h != nullptr, "index is NULL");
+    require(x, "x", 2, kDLFloat, 32);
+    RS_CHECK(x->shape[1] == h->d, "x must be [n, d] with d == index dimension");
+    RS_CHECK(on_device(x) || on_host(x), "x must be a CUDA or host tensor");
+    const int64_t n = x->shape[0];
+    if (n == 0) return;
+    const int64_t ldx = row_stride_2d(x, "x");
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard g(h->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int64_t need = h->ntotal + n;
+    RS_CHECK(need <= 0xFFFFFFFFll, "catalog shards above 2^32 rows are not supported");
+    if (need > h->capacity) {
+      int64_t cap = h->capacity == 0 ? need : std::max(need, h->capacity + h->capacity / 2);
+      float* nb = nullptr;
+      RS_CUDA(cudaMalloc(&nb, sizeof(float) * (size_t)cap * h->d));
+      if (h->ntotal > 0)
+        RS_CUDA(cudaMemcpyAsync(nb, h->xb, sizeof(float) * (size_t)h->ntotal * h->d, cudaMemcpyDeviceToDevice, st));
+      RS_CUDA(cudaStreamSynchronize(st));
+      cudaFree(h->xb);
+      h->xb = nb;
+      h->capacity = cap;
+      cudaFree(h->xb_bf16);
+      cudaFree(h->row_norm);
+      h->xb_bf16 = nullptr;
+      h->row_norm = nullptr;
+      h->shadow_rows = 0;
+    }
+    RS_CUDA(cudaMemcpy2DAsync(h->xb + h->ntotal * h->d, sizeof(float) * h->d, data_ptr<float>(x), sizeof(float) * ldx,
+                              sizeof(float) * h->d, (size_t)n, on_device(x) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                              st));
+    if (on_host(x)) RS_CUDA(cudaStreamSynchronize(st));
+    h->ntotal = need;
+    rebuild_tmaps(h);
+  });
+}
+
+int rs_index_search(rs_index_t* h, const DLTensor* q, int k, int64_t id_base, int mode, DLTensor* D, DLTensor* I,
+                    void* stream) {
+  return rs::guard([&] {
+    using namespace rs;
+    RS_CHECK(h != nullptr, "index is NULL");
+    require(q, "q", 2, kDLFloat, 32);
+    require(D, "D", 2, kDLFloat, 32);
+    require(I, "I", 2, kDLInt, 64);
+    RS_CHECK(q->shape[1] == h->d, "q must be [nq, d] with d == index dimension");
+    RS_CHECK(k >= 1 && k <= 1024, "k must be in [1, 1024]");
+    const int64_t nq = q->shape[0];
+    RS_CHECK(D->shape[0] == nq && D->shape[1] == k && I->shape[0] == nq && I->shape[1] == k, "D and I must be [nq, k]");
+    RS_CHECK(mode == RS_EXACT_FP32 || mode == RS_TENSOR_BF16 || mode == RS_AUTO, "unknown mode");
+    const bool dev = on_device(q) && on_device(D) && on_device(I);
+    const bool host = on_host(q) && on_host(D) && on_host(I);
+    RS_CHECK(dev || host, "q, D, I must be all CUDA tensors or all host tensors");
+    if (nq == 0) return;
+    DeviceGuard g(h->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    bool tensor = false;
+    if (mode == RS_TENSOR_BF16) {
+      RS_CHECK(tensor_path_supported(h, nq, k), "tensor mode is not applicable to this shape (needs d=128, k<=128, ntotal>=65536)");
+      tensor = true;
+    } else if (mode == RS_AUTO) {
+      tensor = nq > 16 && tensor_path_supported(h, nq, k);
+    }
+    auto run = [&](const float* qp, float* Dp, int64_t ldD, int64_t* Ip, int64_t ldI) {
+      if (tensor) search_tensor_device(h, qp, nq, k, id_base, Dp, ldD, Ip, ldI, st);
+      else search_exact_device(h, qp, nq, k, id_base, Dp, ldD, Ip, ldI, st);
+    };
+    if (dev) {
+      RS_CHECK(is_compact(q), "q must be contiguous");
+      RS_CHECK(q->device.device_id == h->device, "q is on a different device than the index");
+      require_aligned16(data_ptr<float>(q), "q");
+      run(data_ptr<float>(q), data_ptr<float>(D), row_stride_2d(D, "D"), data_ptr<int64_t>(I), row_stride_2d(I, "I"));
+      return;
+    }
+    // host tensors: stage through the device on `st` and return once the results are back
+    RS_CHECK(is_compact(q) && is_compact(D) && is_compact(I), "host q, D, I must be contiguous");
+    float* dq = nullptr;
+    float* dD = nullptr;
+    int64_t* dI = nullptr;
+    RS_CUDA(cudaMallocAsync(&dq, sizeof(float) * (size_t)nq * h->d, st));
+    RS_CUDA(cudaMallocAsync(&dD, sizeof(float) * (size_t)nq * k, st));
+    RS_CUDA(cudaMallocAsync(&dI, sizeof(int64_t) * (size_t)nq * k, st));
+    try {
+      RS_CUDA(cudaMemcpyAsync(dq, data_ptr<float>(q), sizeof(float) * (size_t)nq * h->d, cudaMemcpyHostToDevice, st));
+      run(dq, dD, k, dI, k);
+      RS_CUDA(cudaMemcpyAsync(data_ptr<float>(D), dD, sizeof(float) * (size_t)nq * k, cudaMemcpyDeviceToHost, st));
+      RS_CUDA(cudaMemcpyAsync(data_ptr<int64_t>(I), dI, sizeof(int64_t) * (size_t)nq * k, cudaMemcpyDeviceToHost, st));
+    } catch (...) {
+      cudaFreeAsync(dq, st);
+      cudaFreeAsync(dD, st);
+      cudaFreeAsync(dI, st);
+      cudaStreamSynchronize(st);
+      throw;
+    }
+    cudaFreeAsync(dq, st);
+    cudaFreeAsync(dD, st);
+    cudaFreeAsync(dI, st);
+    RS_CUDA(cudaStreamSynchronize(st));
+  });
+}
+
+int rs_normalize_l2(DLTensor* x, void* stream) {
+  return rs::guard([&] {
+    using namespace rs;
+    require(x, "x", 2, kDLFloat, 32);
+    const int64_t n = x->shape[0];
+    const int d = static_cast<int>(x->shape[1]);
+    if (n == 0 || d == 0) return;
+    const int64_t ld = row_stride_2d(x, "x");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    sm_count();
+    const unsigned blocks = static_cast<unsigned>((n + 127) / 128);
+    if (on_device(x)) {
+      normalize_l2_kernel<<<blocks, 128, 0, st>>>(data_ptr<float>(x), ld, n, d);
+      RS_LAUNCH_CHECK();
+      return;
+    }
+    RS_CHECK(on_host(x), "x must be a CUDA or host tensor");
+    float* dx = nullptr;
+    RS_CUDA(cudaMallocAsync(&dx, sizeof(float) * (size_t)n * d, st));
+    try {
+      RS_CUDA(cudaMemcpy2DAsync(dx, sizeof(float) * d, data_ptr<float>(x), sizeof(float) * ld, sizeof(float) * d, (size_t)n,
+                                cudaMemcpyHostToDevice, st));
+      normalize_l2_kernel<<<blocks, 128, 0, st>>>(dx, d, n, d);
+      RS_LAUNCH_CHECK();
+      RS_CUDA(cudaMemcpy2DAsync(data_ptr<float>(x), sizeof(float) * ld, dx, sizeof(float) * d, sizeof(float) * d, (size_t)n,
+                                cudaMemcpyDeviceToHost, st));
+    } catch (...) {
+      cudaFreeAsync(dx, st);
+      cudaStreamSynchronize(st);
+      throw;
+    }
+    cudaFreeAsync(dx, st);
+    RS_CUDA(cudaStreamSynchronize(st));
+  });
+}
+
+int rs_matvec(const DLTensor* items, const DLTensor* user, DLTensor* out, void* stream) {
+  return rs::guard([&] {
+    using namespace rs;
+    require(items, "items", 2, kDLFloat, 32);
+    require(user, "user", 1, kDLFloat, 32);
+    require(out, "out", 1, kDLFloat, 32);
+    RS_CHECK(on_device(items) && on_device(user) && on_device(out), "all tensors must be CUDA tensors");
+    const int64_t n = items->shape[0];
+    const int d = static_cast<int>(items->shape[1]);
+    RS_CHECK(user->shape[0] == d && out->shape[0] == n, "shape mismatch: items [n, d], user [d], out [n]");
+    RS_CHECK((d <= 1 || stride_of(user, 0) == 1) && (n <= 1 || stride_of(out, 0) == 1), "user and out must be contiguous");
+    if (n == 0) return;
+    sm_count();
+    matvec_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        data_ptr<float>(items), row_stride_2d(items, "items"), data_ptr<float>(user), data_ptr<float>(out), n, d);
+    RS_LAUNCH_CHECK();
+  });
+}
+
+int rs_topk_merge(const DLTensor* Dparts, const DLTensor* Iparts, DLTensor* D, DLTensor* I, void* stream) {
+  return rs::guard([&] {
+    using namespace rs;
+    require(Dparts, "Dparts", 3, kDLFloat, 32);
+    require(Iparts, "Iparts", 3, kDLInt, 64);
+    require(D, "D", 2, kDLFloat, 32);
+    require(I, "I", 2, kDLInt, 64);
+    RS_CHECK(on_device(Dparts) && on_device(Iparts) && on_device(D) && on_device(I), "all tensors must be CUDA tensors");
+    const int64_t P = Dparts->shape[0], nq = Dparts->shape[1], k = Dparts->shape[2];
+    RS_CHECK(Iparts->shape[0] == P && Iparts->shape[1] == nq && Iparts->shape[2] == k, "Iparts must match Dparts");
+    RS_CHECK(D->shape[0] == nq && D->shape[1] == k && I->shape[0] == nq && I->shape[1] == k, "D and I must be [nq, k]");
+    RS_CHECK(is_compact(Dparts) && is_compact(Iparts), "Dparts / Iparts must be contiguous");
+    RS_CHECK(P >= 1 && P <= 4096, "nparts must be in [1, 4096]");
+    if (nq == 0) return;
+    sm_count();
+    KeySource src{nullptr, data_ptr<float>(Dparts), data_ptr<int64_t>(Iparts), nq};
+    merge_dispatch(src, nq, static_cast<int>(P), static_cast<int>(k), 0, data_ptr<float>(D), row_stride_2d(D, "D"),
+                   data_ptr<int64_t>(I), row_stride_2d(I, "I"), static_cast<cudaStream_t>(stream));
+  });
+}
+
+}  // extern "C"

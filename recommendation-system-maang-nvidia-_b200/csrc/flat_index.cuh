@@ -1,0 +1,36 @@
+// flat_index.cuh -- the catalog handle shared by the exact scan (flat_index.cu) and the
+// tensor-core pre-filter (tc_filter.cu).
+#pragma once
+
+#include <mutex>
+
+#include "common.cuh"
+
+struct rs_index {
+  int d = 0;
+  int device = 0;
+  int64_t ntotal = 0;
+  int64_t capacity = 0;
+  float* xb = nullptr;           // fp32 catalog [capacity, d], row-major; rows >= ntotal unused
+  CUtensorMap tmap_f32{};        // over [ntotal, d] fp32, box [128 rows, 32 floats], 128B swizzle
+  // bf16 shadow catalog for the tcgen05 pre-filter (built lazily on the first tensor-mode search)
+  uint16_t* xb_bf16 = nullptr;   // [capacity, d] bf16 bits
+  float* row_norm = nullptr;     // [capacity] ||x_i||_2 (fp32), for the filter's error bound
+  int64_t shadow_rows = 0;       // rows of the shadow that are current
+  float max_norm = 0.0f;         // max_i ||x_i||_2 over the shadow rows (host copy)
+  CUtensorMap tmap_bf16{};       // over [ntotal, d] bf16, box [256 rows, 64 bf16], 128B swizzle
+  std::mutex mu;                 // serialises add / shadow build
+};
+
+namespace rs {
+
+// launches of the exact fp32 scan (flat_index.cu); q/D/I are device pointers
+void search_exact_device(rs_index* h, const float* q, int64_t nq, int k, int64_t id_base, float* D, int64_t ldD,
+                         int64_t* I, int64_t ldI, cudaStream_t st);
+// tensor-core pre-filter + exact re-score (tc_filter.cu); same results as search_exact_device
+void search_tensor_device(rs_index* h, const float* q, int64_t nq, int k, int64_t id_base, float* D, int64_t ldD,
+                          int64_t* I, int64_t ldI, cudaStream_t st);
+// true when the tensor path is applicable to this shape (d, k, sizes)
+bool tensor_path_supported(const rs_index* h, int64_t nq, int k);
+
+}  // namespace rs

@@ -1,0 +1,325 @@
+"""Host-side mirror of the reference's Keras classes for the ranking / encoding forward.
+
+Same class names, constructor arguments, call signatures, attribute names and returned dict keys as
+/root/reference/src/models.py, so code written against the reference (`model.encoder(...)`,
+`model.dcn(x)`, `MultiTaskModel(...)(features)`) runs against this module unchanged:
+
+  DeepCrossNetwork   src/models.py:14-55
+  MultiTowerModel    src/models.py:59-102
+  MultiTaskModel     src/models.py:106-131 (call only; compute_loss and the tfrs tasks are training)
+
+Differences, all forced by the runtime: tensors are torch CUDA tensors instead of tf tensors; string
+ids are Python/numpy strings (torch has no string tensor) looked up on the host through a dict
+(StringLookup semantics: OOV -> 0, vocab[i] -> i+1); an *integer* tensor passed as `user_id` /
+`movie_id` is taken as already-looked-up row numbers (an extension used by the bench).  Every layer
+runs hand-written sm_100a kernels through the C ABI (ops.py); there is no CPU path.
+"""
+
+from typing import Any, Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import ops
+from .config import ModelConfig
+
+
+def _dev(device=None) -> torch.device:
+    if device is not None:
+        return torch.device(device)
+    if not torch.cuda.is_available():
+        raise RuntimeError("recsys_b200 needs a CUDA (sm_100a) device; there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+class StringLookup:
+    """keras.layers.StringLookup(vocabulary=..., mask_token=None): OOV -> 0, vocabulary[i] -> i + 1."""
+
+    def __init__(self, vocabulary: Sequence[str], mask_token=None, device=None):
+        if mask_token is not None:
+            raise ValueError("only mask_token=None is supported (as the reference uses, src/models.py:70,73)")
+        self.vocabulary = list(vocabulary)
+        self._index = {s: i + 1 for i, s in enumerate(self.vocabulary)}
+        self.device = _dev(device)
+
+    def vocabulary_size(self) -> int:
+        return len(self.vocabulary) + 1
+
+    def lookup_host(self, ids) -> np.ndarray:
+        if isinstance(ids, (str, bytes)):
+            ids = [ids]
+        get = self._index.get
+        return np.fromiter((get(s.decode() if isinstance(s, bytes) else str(s), 0) for s in ids), dtype=np.int64,
+                           count=len(ids))
+
+    def __call__(self, ids) -> torch.Tensor:
+        if isinstance(ids, torch.Tensor):
+            if ids.dtype not in (torch.int32, torch.int64):
+                raise TypeError("tensor ids must be int32/int64 row numbers")
+            return ids.to(self.device)
+        rows = self.lookup_host(ids)
+        return torch.from_numpy(rows).to(self.device, non_blocking=True)
+
+
+class Embedding:
+    """keras.layers.Embedding(input_dim, output_dim): a row gather (K1)."""
+
+    def __init__(self, input_dim: int, output_dim: int, device=None, seed: Optional[int] = None):
+        self.input_dim, self.output_dim = int(input_dim), int(output_dim)
+        g = torch.Generator(device="cpu")
+        g.manual_seed(0 if seed is None else seed)
+        w = (torch.rand((self.input_dim, self.output_dim), generator=g, dtype=torch.float32) - 0.5) * 0.1
+        self.embeddings = w.to(_dev(device))
+
+    def __call__(self, rows: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        return ops.gather_concat([self.embeddings], [rows], out=out)
+
+    def get_weights(self):
+        return [self.embeddings.cpu().numpy()]
+
+    def set_weights(self, ws):
+        (w,) = ws
+        w = np.asarray(w, dtype=np.float32)
+        if w.shape != (self.input_dim, self.output_dim):
+            raise ValueError(f"embedding shape {w.shape} != {(self.input_dim, self.output_dim)}")
+        self.embeddings = torch.from_numpy(np.ascontiguousarray(w)).to(self.embeddings.device)
+
+
+class Dense:
+    """keras.layers.Dense(units, activation): act(x @ kernel + bias), kernel (in, out); built lazily (K2)."""
+
+    def __init__(self, units: int, activation=None, name: Optional[str] = None, device=None, **_ignored):
+        self.units, self.activation, self.name = int(units), activation, name
+        self.kernel: Optional[torch.Tensor] = None
+        self.bias: Optional[torch.Tensor] = None
+        self._device = _dev(device)
+
+    def build(self, input_dim: int, seed: int = 0):
+        lim = float(np.sqrt(6.0 / (input_dim + self.units)))
+        g = torch.Generator(device="cpu")
+        g.manual_seed(seed)
+        k = (torch.rand((input_dim, self.units), generator=g, dtype=torch.float32) * 2 - 1) * lim
+        self.kernel = k.to(self._device)
+        self.bias = torch.zeros((self.units,), dtype=torch.float32, device=self._device)
+
+    def __call__(self, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if self.kernel is None:
+            self.build(int(x.shape[-1]))
+        return ops.dense(x, self.kernel, self.bias, self.activation, out=out)
+
+    def get_weights(self):
+        return [self.kernel.cpu().numpy(), self.bias.cpu().numpy()]
+
+    def set_weights(self, ws):
+        k, b = ws
+        k = np.ascontiguousarray(np.asarray(k, dtype=np.float32))
+        b = np.ascontiguousarray(np.asarray(b, dtype=np.float32)).reshape(-1)
+        if k.shape[1] != self.units or b.shape[0] != self.units:
+            raise ValueError("Dense weight shapes do not match units")
+        self.kernel = torch.from_numpy(k).to(self._device)
+        self.bias = torch.from_numpy(b).to(self._device)
+
+
+class Sequential:
+    """keras.Sequential of Dense layers; `out` lets the last layer write into a wider buffer."""
+
+    def __init__(self, layers: List[Dense]):
+        self.layers = list(layers)
+
+    def __call__(self, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        n = len(self.layers)
+        for i, layer in enumerate(self.layers):
+            x = layer(x, out=out if i == n - 1 else None)
+        return x
+
+
+class DeepCrossNetwork:
+    """Deep & Cross Network (src/models.py:14-55): rank-1 cross stack + deep relu MLP, concatenated."""
+
+    def __init__(self, cross_layers: int = 3, deep_layers: List[int] = None, dropout_rate: float = 0.2,
+                 l2_reg: float = 1e-5, device=None, **kwargs):
+        self.cross_layers = cross_layers
+        self.deep_layers = deep_layers or [256, 128, 64]
+        self.dropout_rate = dropout_rate   # accepted and unused, exactly as in the reference (no Dropout layer)
+        self.l2_reg = l2_reg               # training-only regulariser
+        self._device = _dev(device)
+        self.cross_weights: List[torch.Tensor] = []
+        self.cross_biases: List[torch.Tensor] = []
+        self._cross_w: Optional[torch.Tensor] = None   # stacked [L, D] storage the kernel reads
+        self._cross_b: Optional[torch.Tensor] = None
+        self.deep_nets = [Dense(units, activation="relu", device=self._device) for units in self.deep_layers]
+        self.built = False
+
+    def build(self, input_shape):
+        input_dim = int(input_shape[-1])
+        L = self.cross_layers
+        lim = float(np.sqrt(6.0 / (input_dim + 1)))
+        g = torch.Generator(device="cpu")
+        g.manual_seed(7)
+        w = (torch.rand((L, input_dim), generator=g, dtype=torch.float32) * 2 - 1) * lim
+        self._set_cross(w.to(self._device), torch.zeros((L, input_dim), dtype=torch.float32, device=self._device))
+        self.built = True
+
+    def _set_cross(self, w: torch.Tensor, b: torch.Tensor):
+        self._cross_w, self._cross_b = w.contiguous(), b.contiguous()
+        # the reference's variable shapes: cross_w_i (D, 1), cross_b_i (D,)  (src/models.py:34-35)
+        self.cross_weights = [self._cross_w[i].unsqueeze(1) for i in range(w.shape[0])]
+        self.cross_biases = [self._cross_b[i] for i in range(w.shape[0])]
+
+    def set_cross_weights(self, cross_w: Sequence[np.ndarray], cross_b: Sequence[np.ndarray]):
+        w = np.stack([np.asarray(x, dtype=np.float32).reshape(-1) for x in cross_w]) if len(cross_w) else \
+            np.zeros((0, 0), dtype=np.float32)
+        b = np.stack([np.asarray(x, dtype=np.float32).reshape(-1) for x in cross_b]) if len(cross_b) else \
+            np.zeros((0, 0), dtype=np.float32)
+        self.cross_layers = w.shape[0]
+        self._set_cross(torch.from_numpy(w).to(self._device), torch.from_numpy(b).to(self._device))
+        self.built = True
+
+    def __call__(self, inputs: torch.Tensor, training=None) -> torch.Tensor:
+        if not self.built:
+            self.build(inputs.shape)
+        B, D = int(inputs.shape[0]), int(inputs.shape[1])
+        for i, layer in enumerate(self.deep_nets):
+            if layer.kernel is None:
+                layer.build(D if i == 0 else self.deep_layers[i - 1], seed=20 + i)
+        out = torch.empty((B, D + self.deep_layers[-1]), dtype=torch.float32, device=inputs.device)
+        ops.dcn_cross(inputs, self._cross_w, self._cross_b, out=out[:, :D])          # src/models.py:38-44
+        Sequential(self.deep_nets)(inputs, out=out[:, D:])                           # :46-48, concat :50
+        return out
+
+    def get_config(self):
+        return {"cross_layers": self.cross_layers, "deep_layers": self.deep_layers,
+                "dropout_rate": self.dropout_rate, "l2_reg": self.l2_reg}
+
+
+class MultiTowerModel:
+    """Two-tower encoder (src/models.py:59-102)."""
+
+    def __init__(self, config: ModelConfig, user_vocab: List[str], item_vocab: List[str],
+                 feature_specs: Dict[str, Any] = None, device=None, **kwargs):
+        self.config = config
+        self.user_vocab = user_vocab
+        self.item_vocab = item_vocab
+        self.feature_specs = feature_specs   # stored and unused, as in the reference (src/models.py:68)
+        dev = _dev(device)
+        self.device = dev
+        E = config.embedding_dim
+        self.user_lookup = StringLookup(vocabulary=user_vocab, mask_token=None, device=dev)
+        self.user_embedding = Embedding(len(user_vocab) + 1, E, device=dev, seed=1)
+        self.item_lookup = StringLookup(vocabulary=item_vocab, mask_token=None, device=dev)
+        self.item_embedding = Embedding(len(item_vocab) + 1, E, device=dev, seed=2)
+        self.user_tower = Sequential([Dense(u, activation="relu", device=dev) for u in config.user_tower_dims]
+                                     + [Dense(E, device=dev)])
+        self.item_tower = Sequential([Dense(u, activation="relu", device=dev) for u in config.item_tower_dims]
+                                     + [Dense(E, device=dev)])
+        for tower, dims, s in ((self.user_tower, config.user_tower_dims, 100), (self.item_tower, config.item_tower_dims, 200)):
+            fan_in = E
+            for i, layer in enumerate(tower.layers):
+                layer.build(fan_in, seed=s + i)
+                fan_in = layer.units
+
+    def encode_user(self, ids, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        return self.user_tower(self.user_embedding(self.user_lookup(ids)), out=out)        # src/models.py:85
+
+    def encode_item(self, ids, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        return self.item_tower(self.item_embedding(self.item_lookup(ids)), out=out)        # src/models.py:89
+
+    def __call__(self, features: Dict[str, Any], training=None) -> Dict[str, Optional[torch.Tensor]]:
+        user_emb = None
+        item_emb = None
+        if "user_id" in features:
+            user_emb = self.encode_user(features["user_id"])
+        if "movie_id" in features:
+            item_emb = self.encode_item(features["movie_id"])
+        return {"user_embedding": user_emb, "item_embedding": item_emb}
+
+    def get_config(self):
+        return {"config": self.config.to_dict(), "user_vocab": self.user_vocab, "item_vocab": self.item_vocab,
+                "feature_specs": self.feature_specs}
+
+    @classmethod
+    def from_config(cls, config):
+        config = dict(config)
+        config["config"] = ModelConfig(**config.pop("config"))
+        return cls(**config)
+
+
+class MultiTaskModel:
+    """Ranking forward of the multi-task model (src/models.py:106-131)."""
+
+    def __init__(self, config: ModelConfig, user_vocab: List[str], item_vocab: List[str],
+                 feature_specs: Dict[str, Any] = None, class_weights: Dict[int, float] = None, device=None, **kwargs):
+        self.config = config
+        dev = _dev(device)
+        self.device = dev
+        self.encoder = MultiTowerModel(config, user_vocab, item_vocab, feature_specs, device=dev)
+        self.class_weights = class_weights
+        self.dcn = DeepCrossNetwork(config.cross_layers, config.dnn_dims, config.dropout_rate, config.l2_reg, device=dev)
+        self.rating_head = Dense(1, name="rating_pred", device=dev)
+        self.ctr_head = Dense(1, activation="sigmoid", name="ctr_pred", device=dev)
+        W = 2 * config.embedding_dim + config.dnn_dims[-1]
+        self.rating_head.build(W, seed=31)
+        self.ctr_head.build(W, seed=32)
+        self._head_cache = None
+
+    def _heads_packed(self):
+        """[2, W] / [2] packing of the two Dense(1) heads for the fused heads kernel (K3b)."""
+        key = (self.rating_head.kernel.data_ptr(), self.ctr_head.kernel.data_ptr(),
+               self.rating_head.bias.data_ptr(), self.ctr_head.bias.data_ptr())
+        if self._head_cache is None or self._head_cache[0] != key:
+            hw = torch.stack([self.rating_head.kernel[:, 0], self.ctr_head.kernel[:, 0]]).contiguous()
+            hb = torch.cat([self.rating_head.bias, self.ctr_head.bias]).contiguous()
+            self._head_cache = (key, hw, hb)
+        return self._head_cache[1], self._head_cache[2]
+
+    def __call__(self, data, training=None) -> Dict[str, torch.Tensor]:
+        features, _ = data if isinstance(data, tuple) else (data, None)                    # src/models.py:126
+        enc = self.encoder
+        E = self.config.embedding_dim
+        rows_u = enc.user_lookup(features["user_id"])
+        rows_i = enc.item_lookup(features["movie_id"])
+        B = int(rows_u.shape[0])
+        # the towers write straight into the two halves of the DCN input: the concat (:128) is free
+        combined = torch.empty((B, 2 * E), dtype=torch.float32, device=self.device)
+        user_emb = enc.user_tower(enc.user_embedding(rows_u), out=combined[:, :E])         # :127 / :85
+        item_emb = enc.item_tower(enc.item_embedding(rows_i), out=combined[:, E:])         # :127 / :89
+        dcn_out = self.dcn(combined, training=training)                                    # :129
+        hw, hb = self._heads_packed()
+        rating, ctr = ops.heads(dcn_out, hw, hb)                                           # :131
+        return {"user_embedding": user_emb, "item_embedding": item_emb,
+                "rating_prediction": rating, "ctr_prediction": ctr}
+
+    def compute_loss(self, data, training=False):
+        raise NotImplementedError("training (tfrs tasks, src/models.py:133-148) is out of scope of the serving path")
+
+    def get_config(self):
+        return {"config": self.config.to_dict(), "user_vocab": self.encoder.user_vocab,
+                "item_vocab": self.encoder.item_vocab, "feature_specs": self.encoder.feature_specs,
+                "class_weights": self.class_weights}
+
+    @classmethod
+    def from_config(cls, config):
+        config = dict(config)
+        config["config"] = ModelConfig(**config.pop("config"))
+        return cls(**config)
+
+
+def load_weights(model, weights: Dict) -> None:
+    """Install a synth.make_weights()-style dict into a MultiTowerModel or MultiTaskModel."""
+    enc = model.encoder if isinstance(model, MultiTaskModel) else model
+    enc.user_embedding.set_weights([weights["user_embedding"]])
+    enc.item_embedding.set_weights([weights["item_embedding"]])
+    for tower, key in ((enc.user_tower, "user_tower"), (enc.item_tower, "item_tower")):
+        if len(tower.layers) != len(weights[key]):
+            raise ValueError(f"{key}: layer count mismatch")
+        for layer, (k, b) in zip(tower.layers, weights[key]):
+            layer.set_weights([k, b])
+    if isinstance(model, MultiTaskModel):
+        model.dcn.set_cross_weights(weights["cross_w"], weights["cross_b"])
+        if len(model.dcn.deep_nets) != len(weights["deep"]):
+            raise ValueError("deep: layer count mismatch")
+        for layer, (k, b) in zip(model.dcn.deep_nets, weights["deep"]):
+            layer.set_weights([k, b])
+        model.rating_head.set_weights(list(weights["rating_head"]))
+        model.ctr_head.set_weights(list(weights["ctr_head"]))
+        model._head_cache = None

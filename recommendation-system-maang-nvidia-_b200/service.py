@@ -1,0 +1,149 @@
+"""RecommendationService -- the reference's serving API (app/recommendation_service.py:18-110) over the
+B200 kernels.  Same constructor, methods, return types and error behaviour, so app/main.py can import it
+unchanged: `recommend(user_id, k)` -> [{"item_id", "score", "rank"}], `score(user_id, item_ids)` ->
+{item_id: float}, ValueError on an unknown user in score(), the first-k "popular items" cold start for
+an unknown user in recommend(), FileNotFoundError from load() when the model directory is missing.
+
+The whole recommend() path stays on the GPU: host dict lookup -> K1 gather -> K2 user tower ->
+K4 normalise -> K5 catalog scan + top-k; only the k (score, row) pairs come back to the host.
+
+Artifacts.  The reference saves `encoder.keras` (Keras v3 zip holding an HDF5 weight file),
+`vocabs.json`, `item_map.json` and `faiss.idx` (src/trainer.py:228-245).  h5py is not available here,
+so load() reads vocabs.json / item_map.json / faiss.idx as the reference writes them and takes the
+encoder weights from `encoder_weights.npz` (keys: user_embedding, item_embedding,
+user_tower_{i}_kernel/bias, item_tower_{i}_kernel/bias) -- `export_encoder_npz` documents the mapping.
+`from_parts` builds a service from in-memory objects (tests, bench).
+"""
+
+import json
+import logging
+from pathlib import Path
+from typing import Dict, List, Optional
+
+import numpy as np
+
+from .config import ModelConfig
+from .index import IndexFlatIP, normalize_L2, read_index
+from .models import MultiTowerModel, load_weights
+from . import ops
+
+logger = logging.getLogger(__name__)
+
+
+def export_encoder_npz(path, weights: Dict) -> None:
+    """Write the encoder half of a weight dict as the .npz side-file load() reads."""
+    out = {"user_embedding": weights["user_embedding"], "item_embedding": weights["item_embedding"]}
+    for side in ("user", "item"):
+        for i, (k, b) in enumerate(weights[f"{side}_tower"]):
+            out[f"{side}_tower_{i}_kernel"] = k
+            out[f"{side}_tower_{i}_bias"] = b
+    np.savez(path, **out)
+
+
+def _weights_from_npz(z) -> Dict:
+    w = {"user_embedding": z["user_embedding"], "item_embedding": z["item_embedding"]}
+    for side in ("user", "item"):
+        layers = []
+        i = 0
+        while f"{side}_tower_{i}_kernel" in z:
+            layers.append((z[f"{side}_tower_{i}_kernel"], z[f"{side}_tower_{i}_bias"]))
+            i += 1
+        w[f"{side}_tower"] = layers
+    return w
+
+
+class RecommendationService:
+    def __init__(self, model_dir: str = "outputs/models/experiment_001"):
+        self.model_dir = Path(model_dir)
+        self.version = "1.2.0"
+        self.user_vocab: List[str] = []
+        self.item_map: Dict[str, str] = {}
+        self.encoder_model: Optional[MultiTowerModel] = None
+        self.faiss_index: Optional[IndexFlatIP] = None
+        self._user_set = frozenset()
+
+    @classmethod
+    def from_parts(cls, encoder: MultiTowerModel, index: IndexFlatIP, user_vocab: List[str], item_map: Dict[str, str],
+                   model_dir: str = "<memory>") -> "RecommendationService":
+        s = cls(model_dir)
+        s.encoder_model, s.faiss_index = encoder, index
+        s.user_vocab, s.item_map = list(user_vocab), dict(item_map)
+        s._user_set = frozenset(s.user_vocab)
+        return s
+
+    def load(self):
+        logger.info(f"Loading model artifacts from {self.model_dir}...")
+        if not self.model_dir.exists():
+            raise FileNotFoundError(f"Model directory not found: {self.model_dir}")
+        with open(self.model_dir / "vocabs.json", "r") as f:
+            vocabs = json.load(f)
+        self.user_vocab = vocabs["users"]
+        self._user_set = frozenset(self.user_vocab)
+        self.faiss_index = read_index(str(self.model_dir / "faiss.idx"))
+        with open(self.model_dir / "item_map.json", "r") as f:
+            self.item_map = json.load(f)
+        cfg_path = self.model_dir / "config.json"
+        config = ModelConfig(**json.load(open(cfg_path))) if cfg_path.exists() else ModelConfig()
+        item_vocab = vocabs.get("items") or [self.item_map[str(i)] for i in range(len(self.item_map))]
+        npz = self.model_dir / "encoder_weights.npz"
+        if not npz.exists():
+            raise FileNotFoundError(f"{npz} not found: export the Keras encoder weights with export_encoder_npz "
+                                    "(encoder.keras needs h5py, which this image does not have)")
+        w = _weights_from_npz(np.load(npz))
+        config.embedding_dim = int(w["user_embedding"].shape[1])
+        config.user_tower_dims = [int(k.shape[1]) for k, _ in w["user_tower"][:-1]]
+        config.item_tower_dims = [int(k.shape[1]) for k, _ in w["item_tower"][:-1]]
+        self.encoder_model = MultiTowerModel(config, self.user_vocab, item_vocab, {})
+        load_weights(self.encoder_model, w)
+        logger.info(f"Loaded {len(self.user_vocab)} users, index with {self.faiss_index.ntotal} items.")
+
+    def is_ready(self) -> bool:
+        return all([self.encoder_model, self.faiss_index, self.user_vocab, self.item_map])
+
+    def recommend(self, user_id: str, k: int = 10) -> List[Dict]:
+        if user_id not in self._user_set:          # dict/set membership instead of the reference's O(V) list scan
+            logger.warning(f"User '{user_id}' not in vocabulary. Applying cold-start strategy.")
+            return self._get_popular_items(k)
+        q = self.encoder_model({"user_id": [user_id]}, training=False)["user_embedding"]   # [1, E] on device
+        normalize_L2(q)
+        distances, indices = self.faiss_index.search(q, k)
+        distances = distances.cpu().numpy()        # the only device -> host traffic: k scores + k rows
+        indices = indices.cpu().numpy()
+        recommendations = []
+        for i, idx in enumerate(indices[0]):
+            if idx != -1:
+                recommendations.append({"item_id": self.item_map[str(idx)], "score": float(distances[0][i]),
+                                        "rank": i + 1})
+        return recommendations
+
+    def recommend_batch(self, user_ids: List[str], k: int = 10) -> Dict[str, List[Dict]]:
+        """Batched variant (app/model_service.py:200-228): one tower pass + one catalog pass for all users."""
+        known = [u for u in user_ids if u in self._user_set]
+        out: Dict[str, List[Dict]] = {}
+        if known:
+            q = self.encoder_model({"user_id": known}, training=False)["user_embedding"]
+            normalize_L2(q)
+            D, I = self.faiss_index.search(q, k)
+            D, I = D.cpu().numpy(), I.cpu().numpy()
+            for r, u in enumerate(known):
+                out[u] = [{"item_id": self.item_map[str(idx)], "score": float(D[r][i]), "rank": i + 1}
+                          for i, idx in enumerate(I[r]) if idx != -1]
+        for u in user_ids:
+            if u not in out:
+                out[u] = self._get_popular_items(k)
+        return out
+
+    def score(self, user_id: str, item_ids: List[str]) -> Dict[str, float]:
+        if user_id not in self._user_set:
+            raise ValueError(f"User '{user_id}' not found in vocabulary.")
+        emb = self.encoder_model({"user_id": [user_id], "movie_id": list(item_ids)}, training=False)
+        scores = ops.matvec(emb["item_embedding"], emb["user_embedding"][0].contiguous())   # raw, un-normalised
+        return {item_id: float(s) for item_id, s in zip(item_ids, scores.cpu().numpy())}
+
+    def _get_popular_items(self, k: int) -> List[Dict]:
+        return [{"item_id": self.item_map[str(i)], "score": 1.0 - (i * 0.05), "rank": i + 1}
+                for i in range(min(k, len(self.item_map)))]
+
+    def get_model_info(self) -> Dict:
+        return {"version": self.version, "model_path": str(self.model_dir), "num_users": len(self.user_vocab),
+                "faiss_index_items": self.faiss_index.ntotal if self.faiss_index else 0}

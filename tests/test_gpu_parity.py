@@ -1,0 +1,413 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the same inputs.
+
+Bars (stated per BASELINE.json north_star):
+  * gathers, normalisation, retrieval scores and top-K indices: BIT-EXACT (the oracle restates the
+    library's stated arithmetic: one fp32 FMA chain, feature index ascending; tie-break score desc, row asc)
+  * tower / DCN / head outputs in fp32 mode: |gpu - fp64 oracle| <= 1e-5 * max|fp64 oracle| per tensor
+    ("1e-5 relative in fp32"; per-tensor scale because relu/cancellation make per-element ratios meaningless)
+"""
+
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROOT = Path(__file__).resolve().parent.parent
+GOLD = ROOT / "tests" / "golden"
+sys.path.insert(0, str(GOLD))
+
+RTOL32 = 1e-5
+
+
+def close32(got, want64, name=""):
+    got = got.detach().cpu().numpy() if isinstance(got, torch.Tensor) else np.asarray(got)
+    scale = float(np.abs(want64).max())
+    err = float(np.abs(got.astype(np.float64) - want64).max())
+    assert err <= RTOL32 * scale + 1e-12, f"{name}: max err {err:.3e} vs scale {scale:.3e}"
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+# ------------------------------------------------------------------------------------------ K1 gather
+@pytest.mark.parametrize("idtype", [torch.int32, torch.int64])
+def test_gather_concat_bit_exact(rs, idtype):
+    rng = np.random.default_rng(0)
+    t0 = rng.standard_normal((6041, 128)).astype(np.float32)
+    t1 = rng.standard_normal((3707, 128)).astype(np.float32)
+    t2 = rng.standard_normal((19, 32)).astype(np.float32)
+    B = 4099
+    i0, i1, i2 = rs.synth.make_ids(rng, 6040, B), rs.synth.make_ids(rng, 3706, B), rng.integers(0, 19, B)
+    out = rs.ops.gather_concat([dev(t0), dev(t1), dev(t2)], [dev(i0).to(idtype), dev(i1).to(idtype), dev(i2).to(idtype)])
+    want = np.concatenate([t0[i0], t1[i1], t2[i2]], axis=1)
+    np.testing.assert_array_equal(out.cpu().numpy(), want)
+
+
+def test_gather_out_of_range_rows_give_zeros_and_strided_out(rs):
+    t0 = np.arange(40, dtype=np.float32).reshape(10, 4)
+    ids = np.array([0, 9, 10, -1, 3], dtype=np.int64)
+    wide = torch.full((5, 12), -7.0, device="cuda")
+    rs.ops.gather_concat([dev(t0)], [dev(ids)], out=wide[:, 4:8])
+    got = wide.cpu().numpy()
+    want = t0[np.clip(ids, 0, 9)]
+    want[[2, 3]] = 0
+    np.testing.assert_array_equal(got[:, 4:8], want)
+    assert (got[:, :4] == -7).all() and (got[:, 8:] == -7).all()
+    assert rs.ops.gather_concat([dev(t0)], [dev(ids[:0])]).shape == (0, 4)
+
+
+# ------------------------------------------------------------------------------------------ K2 dense
+@pytest.mark.parametrize("B,K,N,act", [(4096, 128, 256, "relu"), (4099, 256, 128, "relu"), (1, 128, 64, "relu"),
+                                       (777, 64, 128, None), (130, 256, 256, "sigmoid"), (33, 384, 1, None),
+                                       (65, 100, 24, "relu")])
+def test_dense_forward(rs, B, K, N, act):
+    from oracle.models import dense
+    rng = np.random.default_rng(B + K + N)
+    x = rng.standard_normal((B, K)).astype(np.float32)
+    w = rs.synth.glorot_uniform(rng, K, N)
+    b = rng.normal(0, 0.1, N).astype(np.float32)
+    y = rs.ops.dense(dev(x), dev(w), dev(b), act)
+    close32(y, dense(x.astype(np.float64), w, b, act), f"dense {B}x{K}x{N}")
+    y2 = rs.ops.dense(dev(x), dev(w), None, act)
+    close32(y2, dense(x.astype(np.float64), w, np.zeros(N), act), "dense no-bias")
+
+
+def test_dense_strided_in_and_out(rs):
+    from oracle.models import dense
+    rng = np.random.default_rng(3)
+    big = rng.standard_normal((300, 512)).astype(np.float32)
+    w = rs.synth.glorot_uniform(rng, 128, 64)
+    b = rng.normal(0, 0.1, 64).astype(np.float32)
+    xb = dev(big)
+    out = torch.zeros((300, 256), device="cuda")
+    rs.ops.dense(xb[:, 128:256], dev(w), dev(b), "relu", out=out[:, 64:128])
+    close32(out[:, 64:128], dense(big[:, 128:256].astype(np.float64), w, b, "relu"), "strided dense")
+    assert float(out[:, :64].abs().max()) == 0 and float(out[:, 128:].abs().max()) == 0
+
+
+# ------------------------------------------------------------------------------------------ K3 DCN
+def test_dcn_known_answers_on_gpu(rs):
+    D = 256
+    dcn = rs.DeepCrossNetwork(cross_layers=3, deep_layers=[256, 128])
+    dcn.set_cross_weights([np.full((D, 1), 1.0 / D, np.float32)] * 3, [np.zeros(D, np.float32)] * 3)
+    out = dcn(torch.ones((5, D), device="cuda"))
+    assert out.shape == (5, D + 128)
+    np.testing.assert_array_equal(out[:, :D].cpu().numpy(), np.full((5, D), 8.0, np.float32))   # x_l = 2^l
+    b = np.arange(D, dtype=np.float32)
+    dcn.set_cross_weights([np.zeros((D, 1), np.float32)], [b])
+    out = dcn(torch.full((2, D), 3.0, device="cuda"))
+    np.testing.assert_array_equal(out[:, :D].cpu().numpy(), np.full((2, D), 3.0, np.float32) + b)  # bias outside
+
+
+@pytest.mark.parametrize("D,L,B", [(256, 3, 4096), (128, 1, 7), (384, 4, 130), (512, 2, 33)])
+def test_dcn_cross_vs_oracle(rs, D, L, B):
+    from oracle.models import DeepCrossNetwork as ODCN
+    rng = np.random.default_rng(D + L)
+    cw = [rs.synth.glorot_uniform(rng, D, 1) for _ in range(L)]
+    cb = [rng.normal(0, 0.05, D).astype(np.float32) for _ in range(L)]
+    x0 = rng.standard_normal((B, D)).astype(np.float32)
+    want = ODCN(cw, cb, deep=[(np.zeros((D, 1), np.float32), np.zeros(1, np.float32))], dtype=np.float64)(x0)[:, :D]
+    got = rs.ops.dcn_cross(dev(x0), dev(np.stack([w[:, 0] for w in cw])), dev(np.stack(cb)))
+    close32(got, want, "cross")
+
+
+def test_dcn_layer_and_heads_vs_oracle(rs):
+    from oracle.models import DeepCrossNetwork as ODCN, dense
+    cfg = rs.ModelConfig()
+    w = rs.synth.make_weights(cfg, 10, 10, seed=5)
+    rng = np.random.default_rng(6)
+    x0 = rng.standard_normal((1000, 256)).astype(np.float32)
+    want = ODCN(w["cross_w"], w["cross_b"], w["deep"], np.float64)(x0)
+    dcn = rs.DeepCrossNetwork(cfg.cross_layers, cfg.dnn_dims, cfg.dropout_rate, cfg.l2_reg)
+    dcn.set_cross_weights(w["cross_w"], w["cross_b"])
+    for layer, (k, b) in zip(dcn.deep_nets, w["deep"]):
+        layer.set_weights([k, b])
+    z = dcn(dev(x0), training=False)
+    assert z.shape == (1000, 384)
+    close32(z, want, "dcn concat")
+    hw = np.stack([w["rating_head"][0][:, 0], w["ctr_head"][0][:, 0]])
+    hb = np.concatenate([w["rating_head"][1], w["ctr_head"][1]])
+    rating, ctr = rs.ops.heads(z, dev(hw), dev(hb))
+    zz = z.cpu().numpy().astype(np.float64)
+    close32(rating, dense(zz, *w["rating_head"]), "rating")
+    close32(ctr, dense(zz, *w["ctr_head"], activation="sigmoid"), "ctr")
+
+
+# ------------------------------------------------------------------------------------------ full ranking forward
+def _models(rs, n_users, n_items, seed):
+    from oracle.models import MultiTaskModel as OMT
+    cfg = rs.ModelConfig()
+    w = rs.synth.make_weights(cfg, n_users, n_items, seed=seed)
+    uv, iv = rs.synth.make_vocab(n_users), rs.synth.make_vocab(n_items)
+    m = rs.MultiTaskModel(cfg, uv, iv, {})
+    rs.load_weights(m, w)
+    return cfg, w, uv, iv, m, OMT(w, uv, iv, np.float64), OMT(w, uv, iv, np.float32)
+
+
+def test_multitask_forward_config1_shapes(rs):
+    """BASELINE config 1: 6,040 users / 3,706 items, emb 128, batch 4096, 1 % OOV."""
+    cfg, w, uv, iv, m, o64, o32 = _models(rs, 6040, 3706, seed=10)
+    rng = np.random.default_rng(100)
+    ur, ir = rs.synth.make_ids(rng, 6040, 4096), rs.synth.make_ids(rng, 3706, 4096)
+    out = m({"user_id": dev(ur), "movie_id": dev(ir)}, training=False)
+    want = o64.rank_rows(ur, ir)
+    assert set(out) == {"user_embedding", "item_embedding", "rating_prediction", "ctr_prediction"}
+    for k_ in want:
+        assert tuple(out[k_].shape) == want[k_].shape
+        close32(out[k_], want[k_], k_)
+    # the embeddings alone through the encoder, with string ids and a missing side
+    users = [uv[i - 1] if i > 0 else "no-such-user" for i in ur[:300]]
+    enc = m.encoder({"user_id": users})
+    assert enc["item_embedding"] is None
+    close32(enc["user_embedding"], want["user_embedding"][:300], "encoder strings")
+    # tuple input (features, labels) is accepted like the reference (src/models.py:126)
+    out2 = m(({"user_id": dev(ur[:8]), "movie_id": dev(ir[:8])}, {"rating": None}))
+    np.testing.assert_array_equal(out2["rating_prediction"].cpu().numpy(), out["rating_prediction"][:8].cpu().numpy())
+
+
+def test_multitask_forward_matches_golden_fixture(rs):
+    import make_golden as mg
+    g = np.load(GOLD / "ranking_case.npz")
+    cfg, w, uv, iv, m, _, _ = _models(rs, mg.RANK["n_users"], mg.RANK["n_items"], seed=mg.RANK["weight_seed"])
+    out = m({"user_id": dev(g["user_rows"]), "movie_id": dev(g["item_rows"])})
+    for k_ in ("user_embedding", "item_embedding", "rating_prediction", "ctr_prediction"):
+        close32(out[k_], g[f"f64_{k_}"], "golden " + k_)
+
+
+def test_different_batch_sizes_per_side(rs):
+    cfg, w, uv, iv, m, o64, _ = _models(rs, 50, 60, seed=12)
+    out = m.encoder({"user_id": [uv[4]], "movie_id": iv[:37]})
+    assert out["user_embedding"].shape == (1, 128) and out["item_embedding"].shape == (37, 128)
+    close32(out["item_embedding"], o64.encoder({"movie_id": iv[:37]})["item_embedding"], "items")
+
+
+# ------------------------------------------------------------------------------------------ K4 normalize
+def test_normalize_l2_bit_exact_device_and_host(rs):
+    from oracle import flat_ip
+    rng = np.random.default_rng(7)
+    for d in (128, 64, 20):
+        x = (rng.standard_normal((1001, d)) * rng.uniform(0.01, 50, (1001, 1))).astype(np.float32)
+        x[17] = 0
+        want = x.copy()
+        flat_ip.normalize_L2(want)
+        xd = dev(x)
+        assert rs.normalize_L2(xd) is None
+        np.testing.assert_array_equal(xd.cpu().numpy(), want)
+        xh = x.copy()
+        rs.normalize_L2(xh)
+        np.testing.assert_array_equal(xh, want)
+        assert (xh[17] == 0).all()
+
+
+# ------------------------------------------------------------------------------------------ K5 search
+def _check_search(rs, xb, q, k, **kw):
+    from oracle import flat_ip
+    index = rs.IndexFlatIP(xb.shape[1])
+    index.add(xb)
+    assert index.ntotal == xb.shape[0]
+    D, I = index.search(q, k, **kw)
+    Dw, Iw = flat_ip.search_chain(xb, q, k)
+    np.testing.assert_array_equal(I, Iw)
+    np.testing.assert_array_equal(D, Dw)
+    return index
+
+
+@pytest.mark.parametrize("n", [1, 100, 127, 128, 129, 3706, 50000])
+@pytest.mark.parametrize("nq,k", [(1, 10), (2, 1), (3, 100), (7, 10), (8, 128), (9, 5), (33, 100)])
+def test_search_exact_parity_shapes(rs, n, nq, k):
+    xb = rs.synth.make_unit_rows(n, 128, 1000 + n)
+    q = rs.synth.make_unit_rows(nq, 128, 2000 + nq)
+    _check_search(rs, xb, q, k, mode="exact")
+
+
+@pytest.mark.parametrize("d", [32, 64])
+def test_search_other_dims_and_large_k(rs, d):
+    xb = rs.synth.make_unit_rows(7001, d, 5)
+    q = rs.synth.make_unit_rows(5, d, 6)
+    _check_search(rs, xb, q, 10, mode="exact")
+    _check_search(rs, xb, q, 300, mode="exact")      # k > 128: wide-buffer instantiation
+    _check_search(rs, xb, q, 1024, mode="exact")
+
+
+def test_search_config1_shape(rs):
+    """BASELINE config 1 retrieval: 4,096 queries x 3,706 items, top-10."""
+    xb = rs.synth.make_unit_rows(3706, 128, 1)
+    q = rs.synth.make_unit_rows(4096, 128, 2)
+    _check_search(rs, xb, q, 10)
+
+
+def test_search_ties_padding_and_one_hot(rs):
+    from oracle import flat_ip
+    rng = np.random.default_rng(8)
+    base = rng.standard_normal((40, 128)).astype(np.float32)
+    xb = np.ascontiguousarray(np.concatenate([base] * 8)[rng.permutation(320)])      # every score 8 times
+    q = rng.standard_normal((6, 128)).astype(np.float32)
+    _check_search(rs, xb, q, 100, mode="exact")
+    _check_search(rs, np.zeros((500, 128), np.float32), q, 10, mode="exact")          # all ties at 0: rows 0..9
+    xb3 = rng.standard_normal((3, 128)).astype(np.float32)
+    index = _check_search(rs, xb3, q, 5, mode="exact")                                # k > n: -1 padding
+    D, I = index.search(q, 5)
+    assert (I[:, 3:] == -1).all() and (D[:, 3:] == flat_ip.NEG_PAD).all()
+    eye = np.eye(128, dtype=np.float32)
+    qq = rng.permutation(128).astype(np.float32)[None, :]
+    D, I = rs.IndexFlatIP(128).search(qq, 4)                                           # empty index
+    assert (I == -1).all()
+    ix = rs.IndexFlatIP(128)
+    ix.add(eye)
+    D, I = ix.search(qq, 10)
+    np.testing.assert_array_equal(I[0], np.argsort(-qq[0])[:10])
+    with pytest.raises(RuntimeError):
+        ix.search(qq, 2000)
+    with pytest.raises(ValueError):
+        ix.search(np.zeros((1, 64), np.float32), 3)
+
+
+def test_search_device_tensors_incremental_add_and_id_base(rs):
+    from oracle import flat_ip
+    xb = rs.synth.make_unit_rows(9000, 128, 9)
+    q = rs.synth.make_unit_rows(11, 128, 10)
+    index = rs.IndexFlatIP(128)
+    index.add(dev(xb[:1000]))
+    index.add(xb[1000:1001])
+    index.add(dev(xb[1001:]))
+    assert index.ntotal == 9000
+    D, I = index.search(dev(q), 20, id_base=5_000_000_000)
+    assert D.is_cuda and I.is_cuda and I.dtype == torch.int64
+    Dw, Iw = flat_ip.search_chain(xb, q, 20, id_base=5_000_000_000)
+    np.testing.assert_array_equal(I.cpu().numpy(), Iw)
+    np.testing.assert_array_equal(D.cpu().numpy(), Dw)
+    np.testing.assert_array_equal(index.reconstruct_n(998, 5), xb[998:1003])
+
+
+def test_search_matches_golden_fixtures(rs):
+    import make_golden as mg
+    for spec, name in ((mg.RETR, "retrieval_d128.npz"), (mg.RETR64, "retrieval_d64.npz")):
+        g = np.load(GOLD / name)
+        xb = rs.synth.make_unit_rows(spec["n"], spec["d"], spec["catalog_seed"])
+        q = rs.synth.make_unit_rows(spec["nq"], spec["d"], spec["query_seed"])
+        index = rs.IndexFlatIP(spec["d"])
+        index.add(xb)
+        D, I = index.search(q, spec["k"])
+        np.testing.assert_array_equal(I, g["I"])
+        np.testing.assert_array_equal(D, g["D"])
+
+
+def test_index_file_roundtrip(rs, tmp_path):
+    xb = rs.synth.make_unit_rows(777, 64, 3)
+    index = rs.IndexFlatIP(64)
+    index.add(xb)
+    rs.write_index(index, str(tmp_path / "faiss.idx"))
+    back = rs.read_index(str(tmp_path / "faiss.idx"))
+    assert back.ntotal == 777 and back.d == 64
+    np.testing.assert_array_equal(back.reconstruct_n(), xb)
+
+
+# ------------------------------------------------------------------------------------------ K6 / K7
+def test_matvec_bit_exact(rs):
+    from oracle import flat_ip
+    rng = np.random.default_rng(11)
+    items = rng.standard_normal((100, 128)).astype(np.float32)
+    user = rng.standard_normal(128).astype(np.float32)
+    got = rs.ops.matvec(dev(items), dev(user))
+    np.testing.assert_array_equal(got.cpu().numpy(), flat_ip.matvec(items, user))
+
+
+@pytest.mark.parametrize("nparts,k", [(2, 10), (8, 100), (5, 300)])
+def test_topk_merge_vs_oracle(rs, nparts, k):
+    from oracle import flat_ip
+    xb = rs.synth.make_unit_rows(6000, 64, 12)
+    q = rs.synth.make_unit_rows(9, 64, 13)
+    bounds = np.linspace(0, 6000, nparts + 1).astype(int)
+    bounds[1] = 7                                            # a shard shorter than k: -1 padding inside the parts
+    parts = [flat_ip.search_chain(np.ascontiguousarray(xb[a:b]), q, k, id_base=int(a)) for a, b in zip(bounds[:-1], bounds[1:])]
+    Dp, Ip = np.stack([p[0] for p in parts]), np.stack([p[1] for p in parts])
+    D, I = rs.ops.topk_merge(dev(Dp), dev(Ip))
+    Dw, Iw = flat_ip.search_chain(xb, q, k)
+    np.testing.assert_array_equal(I.cpu().numpy(), Iw)
+    np.testing.assert_array_equal(D.cpu().numpy(), Dw)
+
+
+# ------------------------------------------------------------------------------------------ service
+def test_service_matches_oracle_service(rs):
+    import oracle
+    from oracle import evaluation as ev, flat_ip
+    from oracle.models import MultiTowerModel as OMT
+    cfg = rs.ModelConfig()
+    n_users, n_items = 500, 3706
+    w = rs.synth.make_weights(cfg, n_users, n_items, seed=14)
+    uv, iv = rs.synth.make_vocab(n_users), rs.synth.make_vocab(n_items)
+    enc = rs.MultiTowerModel(cfg, uv, iv, {})
+    rs.load_weights(enc, w)
+    # catalog build as src/trainer.py:221-226,236-245: item tower in 512-row batches, normalise, add
+    embs = torch.cat([enc({"movie_id": iv[i:i + 512]})["item_embedding"] for i in range(0, n_items, 512)])
+    rs.normalize_L2(embs)
+    index = rs.IndexFlatIP(cfg.embedding_dim)
+    index.add(embs)
+    item_map = {str(i): it for i, it in enumerate(iv)}
+    svc = rs.RecommendationService.from_parts(enc, index, uv, item_map)
+    assert svc.is_ready() and svc.get_model_info()["faiss_index_items"] == n_items
+
+    # oracle service over the SAME catalog bytes (so index parity is exact) and the fp32 oracle encoder
+    oenc = OMT(w, uv, iv, np.float32)
+    oindex = flat_ip.IndexFlatIP(cfg.embedding_dim)
+    oindex.add(index.reconstruct_n())
+    osvc = oracle.RecommendationService(oenc, oindex, uv, item_map)
+    preds = []
+    for u in uv[:20]:
+        recs = svc.recommend(u, 10)
+        assert [r["rank"] for r in recs] == list(range(1, 11))
+        # exactness given the GPU's own query: re-run the oracle index on the query the GPU produced
+        q = enc({"user_id": [u]})["user_embedding"]
+        rs.normalize_L2(q)
+        Dw, Iw = oindex.search(q.cpu().numpy(), 10)
+        assert [r["item_id"] for r in recs] == [item_map[str(i)] for i in Iw[0]]
+        assert [r["score"] for r in recs] == [float(s) for s in Dw[0]]
+        # end to end against the oracle's own encoder: same items unless a near-tie (gap < 1e-5) reorders
+        orecs = osvc.recommend(u, 10)
+        for a, b in zip(recs, orecs):
+            assert abs(a["score"] - b["score"]) <= 1e-5
+        preds.append([r["item_id"] for r in recs])
+    assert 0.0 <= ev.recall_at_k(preds, [p[3] for p in preds], 5) == 1.0     # top-K feeds AdvancedMetrics unchanged
+    cold = svc.recommend("nobody", 3)
+    assert cold == osvc.recommend("nobody", 3)
+    sc, osc = svc.score(uv[7], iv[:100] + ["unknown-item"]), osvc.score(uv[7], iv[:100] + ["unknown-item"])
+    assert list(sc) == list(osc)
+    scale = max(abs(v) for v in osc.values())
+    assert max(abs(sc[i] - osc[i]) for i in sc) <= 1e-5 * scale
+    with pytest.raises(ValueError):
+        svc.score("nobody", iv[:3])
+    batch = svc.recommend_batch([uv[0], "nobody", uv[1]], 5)
+    assert batch[uv[0]] == svc.recommend(uv[0], 5) and batch["nobody"] == svc.recommend("nobody", 5)
+
+
+def test_service_load_from_artifacts(rs, tmp_path):
+    import json
+    cfg = rs.ModelConfig(embedding_dim=64, user_tower_dims=[64], item_tower_dims=[64])
+    uv, iv = rs.synth.make_vocab(30), rs.synth.make_vocab(40)
+    w = rs.synth.make_weights(cfg, 30, 40, seed=16)
+    enc = rs.MultiTowerModel(cfg, uv, iv, {})
+    rs.load_weights(enc, w)
+    embs = enc({"movie_id": iv})["item_embedding"].contiguous()
+    rs.normalize_L2(embs)
+    index = rs.IndexFlatIP(64)
+    index.add(embs)
+    d = tmp_path / "experiment_001"
+    d.mkdir()
+    rs.write_index(index, str(d / "faiss.idx"))
+    json.dump({"users": uv, "items": iv}, open(d / "vocabs.json", "w"))
+    json.dump({str(i): it for i, it in enumerate(iv)}, open(d / "item_map.json", "w"))
+    json.dump(cfg.to_dict(), open(d / "config.json", "w"))
+    rs.export_encoder_npz(d / "encoder_weights.npz", w)
+    svc = rs.RecommendationService(str(d))
+    assert not svc.is_ready()
+    svc.load()
+    assert svc.is_ready()
+    ref = rs.RecommendationService.from_parts(enc, index, uv, {str(i): it for i, it in enumerate(iv)})
+    assert svc.recommend(uv[2], 5) == ref.recommend(uv[2], 5)
+    with pytest.raises(FileNotFoundError):
+        rs.RecommendationService(str(tmp_path / "missing")).load()
