@@ -122,6 +122,8 @@ class _Borrowed:
         if isinstance(obj, torch.Tensor):
             self.capsule = obj.__dlpack__(stream=-1) if obj.is_cuda else obj.__dlpack__()
         elif isinstance(obj, np.ndarray):
+            if not obj.flags.writeable:      # DLPack (unversioned) cannot flag read-only: export a private copy
+                obj = self.obj = obj.copy()
             self.capsule = obj.__dlpack__()
         else:
             raise TypeError(f"cannot export {type(obj)} through DLPack")

@@ -25,6 +25,12 @@ int sm_count() {
   RS_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
   RS_CHECK(major == 10, "this library is built for sm_100a only; device has compute capability major " +
                             std::to_string(major));
+  // keep freed workspace in the stream-ordered pool instead of handing it back to the OS at every sync
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    uint64_t keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
   if (dev < 64) {
     cached[dev] = n;
     have[dev] = true;
