@@ -129,6 +129,13 @@ int rs_index_reconstruct(const rs_index_t* h, int64_t i0, DLTensor* out, void* s
 int rs_index_search(rs_index_t* h, const DLTensor* q, int k, int64_t id_base, int mode, DLTensor* D,
                     DLTensor* I, void* stream);
 
+/* tensor-mode bookkeeping: queries of the last / all tensor-mode searches that failed the filter's
+ * verification and were re-run on the exact scan (results are identical either way) */
+int rs_index_fallbacks(const rs_index_t* h, int64_t* last, int64_t* total);
+/* validation aid: the raw low-precision (bf16 x bf16 -> f32, tcgen05) scores of the tensor path,
+ * out f32 [nq, ntotal]; device tensors; small catalogs only */
+int rs_debug_tensor_scores(rs_index_t* h, const DLTensor* q, DLTensor* out, void* stream);
+
 /*
  * K6. tf.linalg.matvec(item_embeddings, user_embedding[0]) (app/recommendation_service.py:91):
  * raw, un-normalised dots.  items: f32 [n, d]; user: f32 [d]; out: f32 [n]; device.

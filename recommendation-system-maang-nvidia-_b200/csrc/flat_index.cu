@@ -407,6 +407,27 @@ int rs_index_reconstruct(const rs_index_t* h, int64_t i0, DLTensor* out, void* s
   });
 }
 
+int rs_index_fallbacks(const rs_index_t* h, int64_t* last, int64_t* total) {
+  return rs::guard([&] {
+    RS_CHECK(h && last && total, "NULL argument");
+    *last = h->last_fallbacks;
+    *total = h->total_fallbacks;
+  });
+}
+
+int rs_debug_tensor_scores(rs_index_t* h, const DLTensor* q, DLTensor* out, void* stream) {
+  return rs::guard([&] {
+    using namespace rs;
+    RS_CHECK(h != nullptr, "index is NULL");
+    require(q, "q", 2, kDLFloat, 32);
+    require(out, "out", 2, kDLFloat, 32);
+    RS_CHECK(on_device(q) && on_device(out) && is_compact(q) && is_compact(out), "q and out must be contiguous CUDA tensors");
+    RS_CHECK(q->shape[1] == h->d && out->shape[0] == q->shape[0] && out->shape[1] == h->ntotal, "shape mismatch");
+    DeviceGuard g(h->device);
+    tensor_scores_debug(h, data_ptr<float>(q), q->shape[0], data_ptr<float>(out), static_cast<cudaStream_t>(stream));
+  });
+}
+
 int rs_index_add(rs_index_t* h, const DLTensor* x, void* stream) {
   return rs::guard([&] {
     using namespace rs;

@@ -19,6 +19,8 @@ struct rs_index {
   int64_t shadow_rows = 0;       // rows of the shadow that are current
   float max_norm = 0.0f;         // max_i ||x_i||_2 over the shadow rows (host copy)
   CUtensorMap tmap_bf16{};       // over [ntotal, d] bf16, box [256 rows, 64 bf16], 128B swizzle
+  int64_t last_fallbacks = 0;    // queries of the last tensor-mode search that were re-run on the exact scan
+  int64_t total_fallbacks = 0;
   std::mutex mu;                 // serialises add / shadow build
 };
 
@@ -30,6 +32,8 @@ void search_exact_device(rs_index* h, const float* q, int64_t nq, int k, int64_t
 // tensor-core pre-filter + exact re-score (tc_filter.cu); same results as search_exact_device
 void search_tensor_device(rs_index* h, const float* q, int64_t nq, int k, int64_t id_base, float* D, int64_t ldD,
                           int64_t* I, int64_t ldI, cudaStream_t st);
+// every low-precision score of the tensor path, out [nq, ntotal] (validation of the tcgen05 tiles)
+void tensor_scores_debug(rs_index* h, const float* q, int64_t nq, float* out, cudaStream_t st);
 // true when the tensor path is applicable to this shape (d, k, sizes)
 bool tensor_path_supported(const rs_index* h, int64_t nq, int k);
 

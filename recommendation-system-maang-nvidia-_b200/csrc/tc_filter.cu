@@ -1,15 +1,579 @@
-// tc_filter.cu -- tensor-core (tcgen05) pre-filter + exact fp32 re-score for batched retrieval.
-// Placeholder until the tcgen05 path lands: reports "not applicable", so RS_AUTO uses the exact scan
-// and RS_TENSOR_BF16 fails loudly.
+// tc_filter.cu -- K5 (tensor mode): tcgen05 bf16 pre-filter + exact fp32 re-score for batched retrieval.
+//
+// Same results as the exact scan (flat_index.cu) -- bit-exact scores, index-exact top-k -- at tensor-core
+// speed.  The idea: a low-precision score can only *rank* approximately, but it bounds the exact score:
+//   |s_hat(q,x) - s(q,x)| <= eps_q := c * ||q|| * max_i ||x_i||,   c = 2^-8 * 1.0625
+// (bf16 round-to-nearest of both operands, unit roundoff 2^-9 each, Cauchy-Schwarz; the slack covers the
+// fp32 accumulation of either side).  Hence every true top-k item has s_hat >= s_hat_(k) - 2*eps_q, where
+// s_hat_(k) is the k-th largest low-precision score.  The pipeline per query batch:
+//   1. prep:    queries -> bf16 (K-major tile layout for TMA), 2*eps_q
+//   2. sample:  tc_filter_kernel<SAMPLE> over ~131k catalog rows -> per-query block maxima -> a threshold
+//               guess tau_q (the r-th largest sample value; r chosen so that tau_q is below
+//               s_hat_(k) - 2*eps_q with overwhelming probability)
+//   3. filter:  tc_filter_kernel<FILTER> over the whole bf16 shadow catalog: S = Q * X^T on tcgen05
+//               (128 x 256 x 128 tiles, accumulators in TMEM, operands TMA-staged with 128B swizzle); the
+//               epilogue reads the accumulator tile straight out of TMEM, rejects against tau_q in
+//               registers (3-input max tree, one compare per 32 scores) and appends the rare survivors to
+//               per-query candidate lists.  Scores never reach HBM.
+//   4. select:  per query: sort candidates by s_hat, VERIFY  s_hat_(k) - 2*eps_q >= tau_q  (this is what
+//               makes the guess rigorous: if it holds, the list provably contains the whole top-k), keep
+//               the prefix with s_hat >= s_hat_(k) - 2*eps_q, re-score those rows with the stated fp32 FMA
+//               chain from the fp32 catalog, sort by (score desc, row asc), emit top-k.
+//   5. queries that fail verification (or overflow their list) are re-run on the exact scan.  Rare.
+//
+// tc_filter_kernel roles (384 threads, 1 CTA per SM, persistent over item tiles):
+//   warp 0 lane*: TMA producer        warp 1 lane*: tcgen05.mma issuer (+ TMEM alloc)
+//   warps 4-11:   epilogue (TMEM lane quarter = warp % 4, column half = (warp - 4) / 4)
+// Pipelines: smem full/empty per item stage (TMA <-> MMA), TMEM full/empty per accumulator (MMA <->
+// epilogue; two 256-column accumulators so the epilogue of tile i overlaps the MMAs of tile i+1).
+// Tensor roofline: 2*nq*N*128 flops per batch.  HBM: N*128*2 bytes (bf16 shadow), re-read from L2 by the
+// CTA groups that hold different query tiles.
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <vector>
+
 #include "flat_index.cuh"
+#include "tcgen05.cuh"
+#include "topk.cuh"
+
+namespace {
+
+using namespace rsd;
+
+constexpr int BM = 128;                  // queries per tile == TMEM lanes
+constexpr int BN = 256;                  // catalog rows per tile == TMEM columns per accumulator
+constexpr int DK = 128;                  // feature dimension of the tensor path
+constexpr int R_MAX = 2;                 // query tiles resident in shared memory per CTA
+constexpr int NSTAGE = 2;                // catalog tile stages
+constexpr int TC_THREADS = 384;
+constexpr int EPI_WARPS = 8;
+constexpr int QTILE_BYTES = BM * DK * 2;  // 32 KB: two [128 x 64] bf16 swizzled halves
+constexpr int STAGE_BYTES = BN * DK * 2;  // 64 KB: two [256 x 64] bf16 swizzled halves
+constexpr int TC_SMEM = R_MAX * QTILE_BYTES + NSTAGE * STAGE_BYTES + 256 + 1024;
+constexpr int CAND_CAP = 4096;           // candidate list capacity per query
+constexpr int SEL_NT = 256;
+constexpr float C_EPS = 0.00390625f * 1.0625f;
+
+enum { MODE_FILTER = 0, MODE_SAMPLE = 1, MODE_DUMP = 2 };
+
+struct TcParams {
+  int64_t n_items;
+  int nq;
+  int n_qtiles;
+  int64_t n_visit;      // item tiles this launch visits
+  int64_t tile_step;    // visited tile v -> catalog tile v * tile_step
+  int ctas_per_group;
+  int n_groups;
+  const float* thr;     // [nq_pad]      FILTER
+  uint64_t* cand;       // [nq_pad][cap] FILTER
+  int* cand_cnt;        // [nq_pad]      FILTER
+  int cap;
+  float* smax;          // [nq_pad][smax_ld] SAMPLE: maxima per (visited tile, column half)
+  int smax_ld;
+  float* dump;          // [nq_pad][dump_ld] DUMP (debug: every low-precision score)
+  int64_t dump_ld;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_x,
+                 const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* qsm = base;
+  uint8_t* xsm = base + R_MAX * QTILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xsm + NSTAGE * STAGE_BYTES);
+  uint64_t* qfull = bars;
+  uint64_t* full = bars + 1;
+  uint64_t* empty = full + NSTAGE;
+  uint64_t* tfull = empty + NSTAGE;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int group = blockIdx.x / p.ctas_per_group;
+  const int j = blockIdx.x % p.ctas_per_group;
+  if (group >= p.n_groups) return;
+  const int qt0 = group * R_MAX;
+  const int nr = min(R_MAX, p.n_qtiles - qt0);
+  const int64_t cpg = p.ctas_per_group;
+  const int64_t n_my = j < p.n_visit ? (p.n_visit - j + cpg - 1) / cpg : 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_x);
+    mbar_init(qfull, 1);
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], EPI_WARPS);   // lane 0 of every epilogue warp arrives once it has drained its part
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      // ---------------- TMA producer ----------------
+      mbar_arrive_expect_tx(qfull, static_cast<uint32_t>(nr) * QTILE_BYTES);
+      for (int r = 0; r < nr; ++r)
+        for (int h = 0; h < 2; ++h)
+          tma_load_2d(qsm + r * QTILE_BYTES + h * (QTILE_BYTES / 2), &tmap_q, qfull, h * 64, (qt0 + r) * BM, kEvictLast);
+      for (int64_t i = 0; i < n_my; ++i) {
+        const int s = static_cast<int>(i % NSTAGE);
+        const uint32_t ph = static_cast<uint32_t>((i / NSTAGE) & 1);
+        mbar_wait(&empty[s], ph ^ 1u);
+        mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
+        const int64_t tile = (j + i * cpg) * p.tile_step;
+        for (int h = 0; h < 2; ++h)
+          tma_load_2d(xsm + s * STAGE_BYTES + h * (STAGE_BYTES / 2), &tmap_x, &full[s], h * 64,
+                      static_cast<int>(tile * BN), kEvictNormal);
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      // ---------------- MMA issuer ----------------
+      constexpr uint32_t idesc = umma_idesc_bf16_f32(BM, BN);
+      mbar_wait(qfull, 0);
+      uint32_t acc_it = 0;
+      for (int64_t i = 0; i < n_my; ++i) {
+        const int s = static_cast<int>(i % NSTAGE);
+        const uint32_t ph = static_cast<uint32_t>((i / NSTAGE) & 1);
+        mbar_wait(&full[s], ph);
+        tc_fence_after_sync();
+        for (int r = 0; r < nr; ++r, ++acc_it) {
+          const uint32_t a = acc_it & 1u, aph = (acc_it >> 1) & 1u;
+          mbar_wait(&tempty[a], aph ^ 1u);
+          tc_fence_after_sync();
+#pragma unroll
+          for (int k = 0; k < DK / 16; ++k) {
+            const int h = k >> 2;
+            const uint32_t ko = static_cast<uint32_t>(k & 3) * 32u;
+            const uint64_t da = umma_desc_k_sw128(smem_u32(qsm + r * QTILE_BYTES + h * (QTILE_BYTES / 2)) + ko);
+            const uint64_t db = umma_desc_k_sw128(smem_u32(xsm + s * STAGE_BYTES + h * (STAGE_BYTES / 2)) + ko);
+            umma_bf16_ss(tmem_base + a * BN, da, db, idesc, k > 0 ? 1u : 0u);
+          }
+          umma_commit(&tfull[a]);
+        }
+        umma_commit(&empty[s]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ---------------- epilogue ----------------
+    const int quarter = warp & 3;          // TMEM lanes [32*quarter, 32*quarter + 32) are this warp's
+    const int half = (warp - 4) >> 2;      // columns [128*half, 128*half + 128) of the accumulator
+    const int row_in_tile = quarter * 32 + lane;
+    float thr[R_MAX];
+    int qrow[R_MAX];
+#pragma unroll
+    for (int r = 0; r < R_MAX; ++r) {
+      qrow[r] = (qt0 + r) * BM + row_in_tile;
+      thr[r] = INFINITY;
+      if (MODE == MODE_FILTER && r < nr && qrow[r] < p.nq) thr[r] = p.thr[qrow[r]];
+    }
+    uint32_t acc_it = 0;
+    for (int64_t i = 0; i < n_my; ++i) {
+      const int64_t visit = j + i * cpg;
+      const int64_t item0 = visit * p.tile_step * BN + half * 128;
+      for (int r = 0; r < nr; ++r, ++acc_it) {
+        const uint32_t a = acc_it & 1u, aph = (acc_it >> 1) & 1u;
+        mbar_wait(&tfull[a], aph);
+        tc_fence_after_sync();
+        const uint32_t taddr = tmem_base + a * BN + half * 128 + (static_cast<uint32_t>(quarter * 32) << 16);
+        float hmax = -INFINITY;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          float v[32];
+          __syncwarp();
+          tmem_ld_32x32(taddr + c * 32, v);
+          float t[10];
+#pragma unroll
+          for (int u = 0; u < 10; ++u) t[u] = max3(v[3 * u], v[3 * u + 1], v[3 * u + 2]);
+          const float m = fmaxf(fmaxf(max3(t[0], t[1], t[2]), max3(t[3], t[4], t[5])),
+                                fmaxf(max3(t[6], t[7], t[8]), max3(t[9], v[30], v[31])));
+          if (MODE == MODE_FILTER) {
+            if (m >= thr[r]) {
+#pragma unroll
+              for (int e = 0; e < 32; ++e) {   // unrolled so v[] stays in registers
+                const int64_t idx = item0 + c * 32 + e;
+                if (v[e] >= thr[r] && idx < p.n_items) {
+                  const int pos = atomicAdd(&p.cand_cnt[qrow[r]], 1);
+                  if (pos < p.cap) p.cand[(int64_t)qrow[r] * p.cap + pos] = pack_key(v[e], static_cast<uint32_t>(idx));
+                }
+              }
+            }
+          } else if (MODE == MODE_SAMPLE) {
+            hmax = fmaxf(hmax, m);
+          } else {
+            if (qrow[r] < p.nq) {
+#pragma unroll 1
+              for (int e = 0; e < 32; ++e) {
+                const int64_t idx = item0 + c * 32 + e;
+                if (idx < p.n_items) p.dump[(int64_t)qrow[r] * p.dump_ld + idx] = v[e];
+              }
+            }
+          }
+        }
+        if (MODE == MODE_SAMPLE) p.smax[(int64_t)qrow[r] * p.smax_ld + visit * 2 + half] = hmax;
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[a]);
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// small kernels around the filter
+// ------------------------------------------------------------------------------------------------
+
+// fp32 catalog -> bf16 shadow (round to nearest even) + max row norm; one warp per row, d = 128
+__global__ void __launch_bounds__(256) build_shadow_kernel(const float* __restrict__ x, uint16_t* __restrict__ xb,
+                                                           int64_t row0, int64_t n, unsigned int* max_norm_bits) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  float best = 0.0f;
+  for (int64_t r = row0 + warp; r < n; r += nwarps) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x + r * DK) + lane);
+    uint2 o;
+    o.x = pack_bf16x2(v.x, v.y);
+    o.y = pack_bf16x2(v.z, v.w);
+    reinterpret_cast<uint2*>(xb + r * DK)[lane] = o;
+    float s = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+#pragma unroll
+    for (int o2 = 16; o2 > 0; o2 >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o2);
+    best = fmaxf(best, s);
+  }
+  if (lane == 0 && best > 0.0f) atomicMax(max_norm_bits, __float_as_uint(sqrtf(best) * 1.00001f));
+}
+
+// queries -> bf16 rows (zero rows for the padding) and 2*eps_q
+__global__ void __launch_bounds__(128) prep_queries_kernel(const float* __restrict__ q, int nq, int nq_pad,
+                                                           uint16_t* __restrict__ qb, float* __restrict__ eps2,
+                                                           const unsigned int* max_norm_bits) {
+  const int lane = threadIdx.x & 31;
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= nq_pad) return;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (row < nq) v = __ldg(reinterpret_cast<const float4*>(q + (int64_t)row * DK) + lane);
+  uint2 o;
+  o.x = pack_bf16x2(v.x, v.y);
+  o.y = pack_bf16x2(v.z, v.w);
+  reinterpret_cast<uint2*>(qb + (int64_t)row * DK)[lane] = o;
+  float s = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+#pragma unroll
+  for (int o2 = 16; o2 > 0; o2 >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o2);
+  if (lane == 0) eps2[row] = 2.0f * C_EPS * (sqrtf(s) * 1.00001f) * __uint_as_float(*max_norm_bits);
+}
+
+// tau_q = the `rank`-th largest of the query's sample maxima; also clears the candidate counters
+template <int NV>
+__global__ void __launch_bounds__(256) threshold_kernel(const float* __restrict__ smax, int n_vals, int rank,
+                                                        float* __restrict__ thr, int* __restrict__ cand_cnt,
+                                                        int* __restrict__ flags) {
+  __shared__ uint64_t keys[NV];
+  const int tid = threadIdx.x;
+  const int qi = blockIdx.x;
+  for (int i = tid; i < NV; i += 256)
+    keys[i] = i < n_vals ? pack_key(smax[(int64_t)qi * n_vals + i], static_cast<uint32_t>(i)) : kEmptyKey;
+  __syncthreads();
+  block_sort_desc<NV, 256>(keys, tid);
+  if (tid == 0) {
+    thr[qi] = key_score(keys[rank - 1]);
+    cand_cnt[qi] = 0;
+    flags[qi] = 0;
+  }
+}
+
+// bitonic sort, descending, run-time power-of-two length n (<= CAND_CAP); ends with __syncthreads()
+__device__ __forceinline__ void block_sort_desc_rt(uint64_t* a, int n, int tid) {
+  for (int size = 2; size <= n; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = tid; i < n / 2; i += SEL_NT) {
+        const int lo = 2 * i - (i & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc = (lo & size) == 0;
+        const uint64_t x = a[lo], y = a[hi];
+        if ((x < y) == desc) {
+          a[lo] = y;
+          a[hi] = x;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__device__ __forceinline__ int next_pow2(int v) {
+  int p = 2;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+// step 4: verify, cut, exact re-score, final order.  One CTA per query.
+__global__ void __launch_bounds__(SEL_NT) select_rescore_kernel(
+    const uint64_t* __restrict__ cand, const int* __restrict__ cand_cnt, int cap, const float* __restrict__ thr,
+    const float* __restrict__ eps2, const float* __restrict__ q, const float* __restrict__ xb, int k, int64_t id_base,
+    float* __restrict__ D, int64_t ldD, int64_t* __restrict__ I, int64_t ldI, int* __restrict__ flags,
+    int* __restrict__ n_flagged) {
+  __shared__ uint64_t keys[CAND_CAP];
+  __shared__ __align__(16) float qs[DK];
+  __shared__ int s_m;
+  const int tid = threadIdx.x;
+  const int qi = blockIdx.x;
+  const int c_raw = cand_cnt[qi];
+  const int c = min(c_raw, cap);
+  if (tid < DK) qs[tid] = q[(int64_t)qi * DK + tid];
+  const int n1 = next_pow2(max(c, 2));
+  for (int i = tid; i < n1; i += SEL_NT) keys[i] = i < c ? cand[(int64_t)qi * cap + i] : kEmptyKey;
+  __syncthreads();
+  block_sort_desc_rt(keys, n1, tid);
+  bool ok = c_raw <= cap && c >= k;
+  float cutoff = 0.0f;
+  if (ok) {
+    cutoff = key_score(keys[k - 1]) - eps2[qi];
+    ok = cutoff >= thr[qi];          // the guess was low enough: the list provably holds the whole top-k
+  }
+  if (!ok) {
+    if (tid == 0) {
+      flags[qi] = 1;
+      atomicAdd(n_flagged, 1);
+    }
+    return;
+  }
+  // m = length of the prefix with s_hat >= cutoff (list is sorted by s_hat descending)
+  if (tid == 0) s_m = 0;
+  __syncthreads();
+  int local = 0;
+  for (int i = tid; i < c; i += SEL_NT) local += key_score(keys[i]) >= cutoff ? 1 : 0;
+  atomicAdd(&s_m, local);
+  __syncthreads();
+  const int m = s_m;
+  for (int i = tid; i < m; i += SEL_NT) {
+    const uint32_t row = key_row(keys[i]);
+    const float4* xr = reinterpret_cast<const float4*>(xb + (int64_t)row * DK);
+    float acc = 0.0f;
+#pragma unroll 8
+    for (int c4 = 0; c4 < DK / 4; ++c4) {
+      const float4 xv = __ldg(xr + c4);
+      const float4 qv = *reinterpret_cast<const float4*>(qs + c4 * 4);
+      acc = fmaf(qv.x, xv.x, acc);
+      acc = fmaf(qv.y, xv.y, acc);
+      acc = fmaf(qv.z, xv.z, acc);
+      acc = fmaf(qv.w, xv.w, acc);
+    }
+    keys[i] = pack_key(acc, row);
+  }
+  const int n2 = next_pow2(max(m, 2));
+  for (int i = m + tid; i < n2; i += SEL_NT) keys[i] = kEmptyKey;
+  __syncthreads();
+  block_sort_desc_rt(keys, n2, tid);
+  for (int jx = tid; jx < k; jx += SEL_NT) {
+    const uint64_t key = keys[jx];
+    D[qi * ldD + jx] = key_score(key);
+    I[qi * ldI + jx] = id_base + static_cast<int64_t>(key_row(key));
+  }
+}
+
+struct Workspace {
+  uint16_t* qb = nullptr;
+  float* eps2 = nullptr;
+  float* thr = nullptr;
+  float* smax = nullptr;
+  int* cnt = nullptr;
+  int* flags = nullptr;   // [nq_pad + 1]; last entry = number of flagged queries
+  uint64_t* cand = nullptr;
+  cudaStream_t st;
+  explicit Workspace(cudaStream_t s) : st(s) {}
+  ~Workspace() {
+    cudaFreeAsync(qb, st);
+    cudaFreeAsync(eps2, st);
+    cudaFreeAsync(thr, st);
+    cudaFreeAsync(smax, st);
+    cudaFreeAsync(cnt, st);
+    cudaFreeAsync(flags, st);
+    cudaFreeAsync(cand, st);
+  }
+};
+
+void ensure_shadow(rs_index* h, cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (h->shadow_rows == h->ntotal && h->xb_bf16) return;
+  if (!h->xb_bf16) {
+    RS_CUDA(cudaMalloc(&h->xb_bf16, sizeof(uint16_t) * (size_t)h->capacity * DK));
+    RS_CUDA(cudaMalloc(&h->row_norm, sizeof(float) * 4));   // [0] holds max ||x|| as float bits
+    RS_CUDA(cudaMemsetAsync(h->row_norm, 0, sizeof(float) * 4, st));
+    h->shadow_rows = 0;
+  }
+  const int64_t todo = h->ntotal - h->shadow_rows;
+  const int64_t want = (todo * 32 + 255) / 256;
+  const int blocks = static_cast<int>(std::min<int64_t>(want, (int64_t)rs::sm_count() * 16));
+  build_shadow_kernel<<<blocks, 256, 0, st>>>(h->xb, h->xb_bf16, h->shadow_rows, h->ntotal,
+                                              reinterpret_cast<unsigned int*>(h->row_norm));
+  RS_LAUNCH_CHECK();
+  RS_CUDA(cudaMemcpyAsync(&h->max_norm, h->row_norm, sizeof(float), cudaMemcpyDeviceToHost, st));
+  RS_CUDA(cudaStreamSynchronize(st));
+  h->shadow_rows = h->ntotal;
+  h->tmap_bf16 = rs::make_tmap_2d(h->xb_bf16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)h->ntotal, DK,
+                                  (uint64_t)DK * 2, BN, 64);
+}
+
+template <int MODE>
+void launch_filter(const CUtensorMap& tq, const CUtensorMap& tx, const TcParams& p, int device, cudaStream_t st) {
+  static std::once_flag once[64];
+  std::call_once(once[device & 63], [] {
+    cudaFuncSetAttribute(tc_filter_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+  });
+  const int grid = p.n_groups * p.ctas_per_group;
+  tc_filter_kernel<MODE><<<grid, TC_THREADS, TC_SMEM, st>>>(tq, tx, p);
+  RS_LAUNCH_CHECK();
+}
+
+}  // namespace
 
 namespace rs {
 
-bool tensor_path_supported(const rs_index*, int64_t, int) { return false; }
+bool tensor_path_supported(const rs_index* h, int64_t nq, int k) {
+  return h->d == DK && k >= 1 && k <= 128 && h->ntotal >= 65536 && nq >= 1 && h->ntotal <= 0x7FFFFF00ll;
+}
 
-void search_tensor_device(rs_index*, const float*, int64_t, int, int64_t, float*, int64_t, int64_t*, int64_t,
-                          cudaStream_t) {
-  RS_CHECK(false, "tensor-core search path is not built");
+void search_tensor_device(rs_index* h, const float* q, int64_t nq, int k, int64_t id_base, float* D, int64_t ldD,
+                          int64_t* I, int64_t ldI, cudaStream_t st) {
+  RS_CHECK(tensor_path_supported(h, nq, k), "tensor path does not apply to this shape");
+  ensure_shadow(h, st);
+  const int sms = sm_count();
+  // query chunks so that every CTA group gets at least one SM
+  const int64_t max_chunk = (int64_t)sms * R_MAX * BM;
+  for (int64_t q0 = 0; q0 < nq; q0 += max_chunk) {
+    const int cq = static_cast<int>(std::min<int64_t>(max_chunk, nq - q0));
+    const float* qc = q + q0 * DK;
+    const int nq_pad = (cq + BM - 1) / BM * BM;
+    const int n_qtiles = nq_pad / BM;
+    const int64_t ntiles = (h->ntotal + BN - 1) / BN;
+    const int64_t n_sample = std::min<int64_t>(512, (ntiles - 1) / 2);
+    const int64_t sample_step = (ntiles - 1) / n_sample;
+    const int n_vals = static_cast<int>(n_sample * 2);
+    const double rho = double(n_sample * BN) / double(h->ntotal);
+    const double cc = 2.0 * k * rho;
+    int rank = static_cast<int>(std::ceil(std::pow(2.0 + std::sqrt(4.0 + cc), 2.0)));
+    rank = std::max(1, std::min(rank, n_vals / 2));
+
+    Workspace ws(st);
+    RS_CUDA(cudaMallocAsync(&ws.qb, sizeof(uint16_t) * (size_t)nq_pad * DK, st));
+    RS_CUDA(cudaMallocAsync(&ws.eps2, sizeof(float) * nq_pad, st));
+    RS_CUDA(cudaMallocAsync(&ws.thr, sizeof(float) * nq_pad, st));
+    RS_CUDA(cudaMallocAsync(&ws.smax, sizeof(float) * (size_t)nq_pad * n_vals, st));
+    RS_CUDA(cudaMallocAsync(&ws.cnt, sizeof(int) * nq_pad, st));
+    RS_CUDA(cudaMallocAsync(&ws.flags, sizeof(int) * (nq_pad + 1), st));
+    RS_CUDA(cudaMallocAsync(&ws.cand, sizeof(uint64_t) * (size_t)nq_pad * CAND_CAP, st));
+    RS_CUDA(cudaMemsetAsync(ws.flags + nq_pad, 0, sizeof(int), st));
+
+    {
+      ProfScope prof(RS_PROF_RESCORE, st);
+      prep_queries_kernel<<<(nq_pad * 32 + 127) / 128, 128, 0, st>>>(qc, cq, nq_pad, ws.qb, ws.eps2,
+                                                                    reinterpret_cast<unsigned int*>(h->row_norm));
+      RS_LAUNCH_CHECK();
+    }
+    const CUtensorMap tq = make_tmap_2d(ws.qb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)nq_pad, DK,
+                                        (uint64_t)DK * 2, BM, 64);
+    TcParams p{};
+    p.n_items = h->ntotal;
+    p.nq = cq;
+    p.n_qtiles = n_qtiles;
+    p.n_groups = (n_qtiles + R_MAX - 1) / R_MAX;
+    p.ctas_per_group = std::max(1, sms / p.n_groups);
+    p.thr = ws.thr;
+    p.cand = ws.cand;
+    p.cand_cnt = ws.cnt;
+    p.cap = CAND_CAP;
+    p.smax = ws.smax;
+    p.smax_ld = n_vals;
+    {
+      ProfScope prof(RS_PROF_FILTER, st);
+      TcParams ps = p;
+      ps.n_visit = n_sample;
+      ps.tile_step = sample_step;
+      launch_filter<MODE_SAMPLE>(tq, h->tmap_bf16, ps, h->device, st);
+    }
+    {
+      ProfScope prof(RS_PROF_RESCORE, st);
+      if (n_vals <= 256) threshold_kernel<256><<<cq, 256, 0, st>>>(ws.smax, n_vals, rank, ws.thr, ws.cnt, ws.flags);
+      else threshold_kernel<1024><<<cq, 256, 0, st>>>(ws.smax, n_vals, rank, ws.thr, ws.cnt, ws.flags);
+      RS_LAUNCH_CHECK();
+    }
+    {
+      ProfScope prof(RS_PROF_FILTER, st);
+      TcParams pm = p;
+      pm.n_visit = ntiles;
+      pm.tile_step = 1;
+      launch_filter<MODE_FILTER>(tq, h->tmap_bf16, pm, h->device, st);
+    }
+    {
+      ProfScope prof(RS_PROF_RESCORE, st);
+      select_rescore_kernel<<<cq, SEL_NT, 0, st>>>(ws.cand, ws.cnt, CAND_CAP, ws.thr, ws.eps2, qc, h->xb, k, id_base,
+                                                   D + q0 * ldD, ldD, I + q0 * ldI, ldI, ws.flags, ws.flags + nq_pad);
+      RS_LAUNCH_CHECK();
+    }
+    // step 5: the (rare) queries whose guess could not be verified go through the exact scan
+    std::vector<int> flags(nq_pad + 1);
+    RS_CUDA(cudaMemcpyAsync(flags.data(), ws.flags, sizeof(int) * (nq_pad + 1), cudaMemcpyDeviceToHost, st));
+    RS_CUDA(cudaStreamSynchronize(st));
+    if (flags[nq_pad] > 0) {
+      for (int i = 0; i < cq; ++i)
+        if (flags[i])
+          search_exact_device(h, qc + (int64_t)i * DK, 1, k, id_base, D + (q0 + i) * ldD, ldD, I + (q0 + i) * ldI, ldI, st);
+    }
+    h->last_fallbacks = (q0 == 0 ? 0 : h->last_fallbacks) + flags[nq_pad];
+    h->total_fallbacks += flags[nq_pad];
+  }
+}
+
+// debug / validation: every low-precision score of the tensor path, [nq, ntotal] (small catalogs only)
+void tensor_scores_debug(rs_index* h, const float* q, int64_t nq, float* out, cudaStream_t st) {
+  RS_CHECK(h->d == DK && h->ntotal >= 1, "needs d = 128 and a non-empty index");
+  ensure_shadow(h, st);
+  const int sms = sm_count();
+  const int nq_pad = static_cast<int>((nq + BM - 1) / BM * BM);
+  RS_CHECK(nq_pad / BM <= sms * R_MAX, "too many queries for the debug entry");
+  Workspace ws(st);
+  RS_CUDA(cudaMallocAsync(&ws.qb, sizeof(uint16_t) * (size_t)nq_pad * DK, st));
+  RS_CUDA(cudaMallocAsync(&ws.eps2, sizeof(float) * nq_pad, st));
+  prep_queries_kernel<<<(nq_pad * 32 + 127) / 128, 128, 0, st>>>(q, (int)nq, nq_pad, ws.qb, ws.eps2,
+                                                                reinterpret_cast<unsigned int*>(h->row_norm));
+  RS_LAUNCH_CHECK();
+  const CUtensorMap tq = make_tmap_2d(ws.qb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)nq_pad, DK, (uint64_t)DK * 2,
+                                      BM, 64);
+  TcParams p{};
+  p.n_items = h->ntotal;
+  p.nq = (int)nq;
+  p.n_qtiles = nq_pad / BM;
+  p.n_groups = (p.n_qtiles + R_MAX - 1) / R_MAX;
+  p.ctas_per_group = std::max(1, sms / p.n_groups);
+  p.n_visit = (h->ntotal + BN - 1) / BN;
+  p.tile_step = 1;
+  p.dump = out;
+  p.dump_ld = h->ntotal;
+  launch_filter<MODE_DUMP>(tq, h->tmap_bf16, p, h->device, st);
 }
 
 }  // namespace rs

@@ -98,6 +98,19 @@ class IndexFlatIP:
                                              _lib.stream_ptr()))
         return D, I
 
+    def fallbacks(self):
+        """(last, total) tensor-mode queries that were re-run on the exact scan (same results either way)."""
+        a, b = ctypes.c_int64(0), ctypes.c_int64(0)
+        _lib.check(self._lib.rs_index_fallbacks(self._h, ctypes.byref(a), ctypes.byref(b)))
+        return int(a.value), int(b.value)
+
+    def debug_tensor_scores(self, q: torch.Tensor) -> torch.Tensor:
+        """Raw bf16 tensor-core scores [nq, ntotal] (validation of the tcgen05 tiles; small catalogs)."""
+        out = torch.empty((q.shape[0], self.ntotal), dtype=torch.float32, device=q.device)
+        qb, ob = _lib.dl(q.contiguous()), _lib.dl(out)
+        _lib.check(self._lib.rs_debug_tensor_scores(self._h, qb.ptr, ob.ptr, _lib.stream_ptr()))
+        return out
+
     def reconstruct_n(self, i0: int = 0, n: int = None) -> np.ndarray:
         """Stored vectors [i0, i0+n) back on the host (faiss.IndexFlat.reconstruct_n)."""
         nt = self.ntotal

@@ -1,0 +1,147 @@
+"""GPU tests of the tcgen05 retrieval path (tc_filter.cu): the raw tensor-core tiles against a bf16 numpy
+model, and the filter + exact re-score pipeline against the oracle -- bit-exact scores and indices, the
+same bar as the exact scan."""
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def to_bf16(x: np.ndarray) -> np.ndarray:
+    """fp32 -> bf16 round-to-nearest-even, returned as fp32 (what cvt.rn.bf16x2.f32 does)."""
+    u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    r = ((u >> 16) & 1) + 0x7FFF
+    return ((u + r) & 0xFFFF0000).astype(np.uint32).view(np.float32)
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.parametrize("n,nq", [(256, 128), (1000, 3), (5000, 130), (70001, 257)])
+def test_tcgen05_tiles_match_bf16_model(rs, n, nq):
+    """Every (query, row) score out of TMEM equals the fp64 dot of the bf16-rounded operands to fp32 accuracy:
+    validates the TMA swizzle, the UMMA descriptors, the K stepping and the TMEM lane/column mapping."""
+    rng = np.random.default_rng(n + nq)
+    xb = (rng.standard_normal((n, 128)) * rng.uniform(0.5, 2.0, (n, 1))).astype(np.float32)
+    q = rng.standard_normal((nq, 128)).astype(np.float32)
+    index = rs.IndexFlatIP(128)
+    index.add(xb)
+    got = index.debug_tensor_scores(dev(q)).cpu().numpy()
+    want = to_bf16(q).astype(np.float64) @ to_bf16(xb).astype(np.float64).T
+    err = np.abs(got - want).max()
+    assert err < 2e-4 * np.abs(want).max(), f"max err {err}"
+    # and the rigorous filter bound holds against the exact fp32 scores: |s_hat - s| <= c * |q| * max|x|
+    exact = q.astype(np.float64) @ xb.astype(np.float64).T
+    bound = (2.0 ** -8 * 1.0625) * np.linalg.norm(q, axis=1)[:, None] * np.linalg.norm(xb, axis=1).max()
+    assert (np.abs(got - exact) <= bound).all()
+
+
+def _check(rs, xb, q, k, expect_fallback=None):
+    from oracle import flat_ip
+    index = rs.IndexFlatIP(128)
+    index.add(dev(xb))
+    D, I = index.search(dev(q), k, mode="tensor")
+    Dw, Iw = flat_ip.search_chain(xb, q, k)
+    np.testing.assert_array_equal(I.cpu().numpy(), Iw)
+    np.testing.assert_array_equal(D.cpu().numpy(), Dw)
+    last, total = index.fallbacks()
+    if expect_fallback is True:
+        assert last > 0
+    elif expect_fallback is False:
+        assert last == 0, f"{last} of {q.shape[0]} queries fell back to the exact scan"
+    return index
+
+
+@pytest.mark.parametrize("nq,k", [(1, 10), (7, 1), (128, 100), (129, 128), (300, 100), (1024, 10)])
+def test_tensor_search_is_bit_exact(rs, nq, k):
+    xb = rs.synth.make_unit_rows(200_000, 128, 77)
+    q = rs.synth.make_unit_rows(nq, 128, 78 + nq)
+    _check(rs, xb, q, k, expect_fallback=False)
+
+
+def test_tensor_search_odd_catalog_sizes(rs):
+    q = rs.synth.make_unit_rows(40, 128, 5)
+    for n in (65536, 65537, 100_003, 131_071):
+        _check(rs, rs.synth.make_unit_rows(n, 128, n), q, 100)
+
+
+def test_tensor_search_non_unit_norms_and_planted_neighbours(rs):
+    rng = np.random.default_rng(9)
+    n = 150_000
+    xb = (rng.standard_normal((n, 128)) * rng.lognormal(0, 0.5, (n, 1))).astype(np.float32)
+    q = (rng.standard_normal((64, 128)) * rng.lognormal(0, 0.5, (64, 1))).astype(np.float32)
+    for i in range(64):                       # 20 planted near-duplicates of every query direction
+        rows = rng.integers(0, n, 20)
+        xb[rows] = q[i] * rng.uniform(0.8, 1.2, (20, 1)).astype(np.float32) + 0.01 * rng.standard_normal((20, 128)).astype(np.float32)
+    _check(rs, xb, q, 50)
+
+
+def test_tensor_search_ties_and_degenerate_catalogs_fall_back_but_stay_exact(rs):
+    rng = np.random.default_rng(10)
+    base = rs.synth.make_unit_rows(1000, 128, 11)
+    xb = np.ascontiguousarray(np.tile(base, (80, 1)))            # every row 80 times: massive exact ties
+    q = rs.synth.make_unit_rows(9, 128, 12)
+    _check(rs, xb, q, 100)
+    # a catalog whose scores are packed inside the filter margin: lists overflow -> exact-scan fallback
+    centre = rs.synth.make_unit_rows(1, 128, 13)
+    xb = (centre + 1e-4 * rng.standard_normal((80_000, 128))).astype(np.float32)
+    _check(rs, xb, q, 10, expect_fallback=True)
+    _check(rs, np.zeros((70_000, 128), np.float32), q, 10)      # all scores 0: rows 0..9 win
+
+
+def test_auto_mode_equals_exact_mode_and_host_path(rs):
+    xb = rs.synth.make_unit_rows(120_000, 128, 21)
+    q = rs.synth.make_unit_rows(200, 128, 22)
+    index = rs.IndexFlatIP(128)
+    index.add(xb)
+    De, Ie = index.search(q, 100, mode="exact")
+    Da, Ia = index.search(q, 100, mode="auto")
+    Dt, It = index.search(q, 100, mode="tensor")
+    np.testing.assert_array_equal(Ia, Ie)
+    np.testing.assert_array_equal(Da, De)
+    np.testing.assert_array_equal(It, Ie)
+    np.testing.assert_array_equal(Dt, De)
+    index.add(rs.synth.make_unit_rows(5000, 128, 23))            # growing the index refreshes the bf16 shadow
+    D2, I2 = index.search(q[:20], 10, mode="tensor")
+    D3, I3 = index.search(q[:20], 10, mode="exact")
+    np.testing.assert_array_equal(I2, I3)
+    np.testing.assert_array_equal(D2, D3)
+    with pytest.raises(RuntimeError):
+        rs.IndexFlatIP(64).search(np.zeros((1, 64), np.float32), 3, mode="tensor")
+
+
+def test_full_size_catalog_properties(rs):
+    """BASELINE config 3 at full size (10M x 128, 1,024 queries, top-100): the tensor path equals the exact
+    scan on every query, lists are sorted by (score desc, row asc), and the returned scores equal the
+    stated-arithmetic scores of the returned rows."""
+    dev0 = torch.device("cuda", 0)
+    N, nq, k = 10_000_000, 1024, 100
+    index = rs.IndexFlatIP(128)
+    for b0 in range(0, N, 1 << 20):
+        g = torch.Generator(device=dev0)
+        g.manual_seed(3000 + b0 // (1 << 20))
+        x = torch.randn((min(1 << 20, N - b0), 128), generator=g, device=dev0)
+        rs.normalize_L2(x)
+        index.add(x)
+    g = torch.Generator(device=dev0)
+    g.manual_seed(3999)
+    q = torch.randn((nq, 128), generator=g, device=dev0)
+    rs.normalize_L2(q)
+    Dt, It = index.search(q, k, mode="tensor")
+    last, _ = index.fallbacks()
+    assert last <= 2, f"{last} fallbacks"
+    De, Ie = index.search(q[:64].contiguous(), k, mode="exact")
+    assert torch.equal(It[:64], Ie) and torch.equal(Dt[:64], De)
+    assert bool(((Dt[:, :-1] > Dt[:, 1:]) | ((Dt[:, :-1] == Dt[:, 1:]) & (It[:, :-1] < It[:, 1:]))).all())
+    assert int(It.min()) >= 0 and int(It.max()) < N
+    rows = torch.from_numpy(index.reconstruct_n(int(It[5, 0]), 1)).cuda()
+    np.testing.assert_array_equal(rs.ops.matvec(rows, q[5].contiguous()).cpu().numpy(), Dt[5, :1].cpu().numpy())
+    # batch-1 latency mode (config 5): top-10 for single queries, both modes identical
+    for i in (0, 1, 2):
+        D1, I1 = index.search(q[i:i + 1].contiguous(), 10, mode="exact")
+        D2, I2 = index.search(q[i:i + 1].contiguous(), 10, mode="tensor")
+        assert torch.equal(I1, I2) and torch.equal(D1, D2)
+        assert torch.equal(I1[0], It[i, :10])
