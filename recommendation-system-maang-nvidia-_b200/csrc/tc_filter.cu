@@ -31,6 +31,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "flat_index.cuh"
@@ -50,7 +51,8 @@ constexpr int TC_THREADS = 384;
 constexpr int EPI_WARPS = 8;
 constexpr int QTILE_BYTES = BM * DK * 2;  // 32 KB: two [128 x 64] bf16 swizzled halves
 constexpr int STAGE_BYTES = BN * DK * 2;  // 64 KB: two [256 x 64] bf16 swizzled halves
-constexpr int TC_SMEM = R_MAX * QTILE_BYTES + NSTAGE * STAGE_BYTES + 256 + 1024;
+constexpr int WQ_CAP = 64;               // survivor records per epilogue-warp staging queue
+constexpr int TC_SMEM = R_MAX * QTILE_BYTES + NSTAGE * STAGE_BYTES + 256 + EPI_WARPS * WQ_CAP * 16 + 1024;
 constexpr int CAND_CAP = 4096;           // candidate list capacity per query
 constexpr int SEL_NT = 256;
 constexpr float C_EPS = 0.00390625f * 1.0625f;
@@ -69,10 +71,15 @@ struct TcParams {
   uint64_t* cand;       // [nq_pad][cap] FILTER
   int* cand_cnt;        // [nq_pad]      FILTER
   int cap;
+  uint4* rec;           // FILTER: global survivor records {key.lo, key.hi, query row, 0}
+  unsigned* rec_cnt;    // FILTER: number of records appended (may exceed rec_cap: overflow)
+  unsigned rec_cap;
+  int* overflow;        // FILTER: set when a staging queue overran
   float* smax;          // [nq_pad][smax_ld] SAMPLE: maxima per (visited tile, column half)
   int smax_ld;
   float* dump;          // [nq_pad][dump_ld] DUMP (debug: every low-precision score)
   int64_t dump_ld;
+  int debug;            // perf experiments only: 1 = epilogue skips TMEM reads, 2 = issuer skips the MMAs
 };
 
 template <int MODE>
@@ -90,6 +97,8 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   uint64_t* tfull = empty + NSTAGE;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  int* wqueue_cnt = reinterpret_cast<int*>(tmem_slot + 2);             // [EPI_WARPS]
+  uint4* wqueue = reinterpret_cast<uint4*>(bars + 32);                  // [EPI_WARPS][WQ_CAP], 256 B after bars
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -115,6 +124,7 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     }
     fence_mbar_init();
   }
+  if (threadIdx.x < EPI_WARPS) wqueue_cnt[threadIdx.x] = 0;
   if (warp == 1) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
@@ -159,6 +169,7 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           tc_fence_after_sync();
 #pragma unroll
           for (int k = 0; k < DK / 16; ++k) {
+            if (p.debug & 2) break;
             const int h = k >> 2;
             const uint32_t ko = static_cast<uint32_t>(k & 3) * 32u;
             const uint64_t da = umma_desc_k_sw128(smem_u32(qsm + r * QTILE_BYTES + h * (QTILE_BYTES / 2)) + ko);
@@ -172,17 +183,33 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     }
   } else if (warp >= 4) {
     // ---------------- epilogue ----------------
+    const int ew = warp - 4;
     const int quarter = warp & 3;          // TMEM lanes [32*quarter, 32*quarter + 32) are this warp's
-    const int half = (warp - 4) >> 2;      // columns [128*half, 128*half + 128) of the accumulator
+    const int half = ew >> 2;              // columns [128*half, 128*half + 128) of the accumulator
     const int row_in_tile = quarter * 32 + lane;
+    uint4* wq = wqueue + ew * WQ_CAP;      // this warp's staging queue for survivors
+    int* wq_cnt = wqueue_cnt + ew;
     float thr[R_MAX];
     int qrow[R_MAX];
 #pragma unroll
     for (int r = 0; r < R_MAX; ++r) {
       qrow[r] = (qt0 + r) * BM + row_in_tile;
       thr[r] = INFINITY;
-      if (MODE == MODE_FILTER && r < nr && qrow[r] < p.nq) thr[r] = p.thr[qrow[r]];
+      if (MODE == MODE_FILTER && r < nr && qrow[r] < p.nq && !(p.debug & 4)) thr[r] = p.thr[qrow[r]];
     }
+    // Survivors are rare (~1e-4 of the scores).  They go to a per-warp shared-memory queue with a shared
+    // atomic (no global round trip on the MMA-critical path); a queue is flushed to the global record list
+    // with ONE global atomic per flush once it holds >= 32 records.
+    auto flush = [&](int n) {
+      unsigned base = 0;
+      if (lane == 0) base = atomicAdd(p.rec_cnt, static_cast<unsigned>(n));
+      base = __shfl_sync(0xFFFFFFFFu, base, 0);
+      for (int t = lane; t < n; t += 32)
+        if (base + t < p.rec_cap) p.rec[base + t] = wq[t];
+      __syncwarp();
+      if (lane == 0) *wq_cnt = 0;
+      __syncwarp();
+    };
     uint32_t acc_it = 0;
     for (int64_t i = 0; i < n_my; ++i) {
       const int64_t visit = j + i * cpg;
@@ -195,22 +222,36 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         float hmax = -INFINITY;
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
+          if (p.debug & 1) break;
           float v[32];
           __syncwarp();
           tmem_ld_32x32(taddr + c * 32, v);
-          float t[10];
+          // group maxima over 8 consecutive scores with 3-input max: half an instruction per score
+          float g[4];
 #pragma unroll
-          for (int u = 0; u < 10; ++u) t[u] = max3(v[3 * u], v[3 * u + 1], v[3 * u + 2]);
-          const float m = fmaxf(fmaxf(max3(t[0], t[1], t[2]), max3(t[3], t[4], t[5])),
-                                fmaxf(max3(t[6], t[7], t[8]), max3(t[9], v[30], v[31])));
+          for (int u = 0; u < 4; ++u)
+            g[u] = max3(max3(v[8 * u], v[8 * u + 1], v[8 * u + 2]), max3(v[8 * u + 3], v[8 * u + 4], v[8 * u + 5]),
+                        fmaxf(v[8 * u + 6], v[8 * u + 7]));
+          const float m = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
           if (MODE == MODE_FILTER) {
             if (m >= thr[r]) {
 #pragma unroll
-              for (int e = 0; e < 32; ++e) {   // unrolled so v[] stays in registers
-                const int64_t idx = item0 + c * 32 + e;
-                if (v[e] >= thr[r] && idx < p.n_items) {
-                  const int pos = atomicAdd(&p.cand_cnt[qrow[r]], 1);
-                  if (pos < p.cap) p.cand[(int64_t)qrow[r] * p.cap + pos] = pack_key(v[e], static_cast<uint32_t>(idx));
+              for (int u = 0; u < 4; ++u) {
+                if (g[u] >= thr[r]) {
+#pragma unroll
+                  for (int e = 8 * u; e < 8 * u + 8; ++e) {   // unrolled so v[] stays in registers
+                    const int64_t idx = item0 + c * 32 + e;
+                    if (v[e] >= thr[r] && idx < p.n_items) {
+                      const int slot = atomicAdd(wq_cnt, 1);
+                      if (slot < WQ_CAP) {
+                        const uint64_t key = pack_key(v[e], static_cast<uint32_t>(idx));
+                        wq[slot] = make_uint4(static_cast<uint32_t>(key), static_cast<uint32_t>(key >> 32),
+                                              static_cast<uint32_t>(qrow[r]), 0u);
+                      } else {
+                        *p.overflow = 1;   // queue overrun (adversarial data): the host re-runs the chunk exactly
+                      }
+                    }
+                  }
                 }
               }
             }
@@ -218,7 +259,7 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             hmax = fmaxf(hmax, m);
           } else {
             if (qrow[r] < p.nq) {
-#pragma unroll 1
+#pragma unroll
               for (int e = 0; e < 32; ++e) {
                 const int64_t idx = item0 + c * 32 + e;
                 if (idx < p.n_items) p.dump[(int64_t)qrow[r] * p.dump_ld + idx] = v[e];
@@ -230,7 +271,16 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[a]);
+        if (MODE == MODE_FILTER) {
+          const int n = min(*wq_cnt, WQ_CAP);   // uniform: read after the __syncwarp above
+          if (n >= 32) flush(n);
+        }
       }
+    }
+    if (MODE == MODE_FILTER) {
+      __syncwarp();
+      const int n = min(*wq_cnt, WQ_CAP);
+      if (n > 0) flush(n);
     }
   }
 
@@ -401,8 +451,9 @@ struct Workspace {
   float* thr = nullptr;
   float* smax = nullptr;
   int* cnt = nullptr;
-  int* flags = nullptr;   // [nq_pad + 1]; last entry = number of flagged queries
+  int* flags = nullptr;   // [nq_pad + 4]: per-query flag, then {n_flagged, queue overflow, record count, -}
   uint64_t* cand = nullptr;
+  uint4* rec = nullptr;
   cudaStream_t st;
   explicit Workspace(cudaStream_t s) : st(s) {}
   ~Workspace() {
@@ -413,6 +464,7 @@ struct Workspace {
     cudaFreeAsync(cnt, st);
     cudaFreeAsync(flags, st);
     cudaFreeAsync(cand, st);
+    cudaFreeAsync(rec, st);
   }
 };
 
@@ -439,14 +491,27 @@ void ensure_shadow(rs_index* h, cudaStream_t st) {
 }
 
 template <int MODE>
-void launch_filter(const CUtensorMap& tq, const CUtensorMap& tx, const TcParams& p, int device, cudaStream_t st) {
+void launch_filter(const CUtensorMap& tq, const CUtensorMap& tx, TcParams p, int device, cudaStream_t st) {
   static std::once_flag once[64];
   std::call_once(once[device & 63], [] {
     cudaFuncSetAttribute(tc_filter_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
   });
+  if (const char* e = getenv("RS_TC_DEBUG")) p.debug = atoi(e);
   const int grid = p.n_groups * p.ctas_per_group;
   tc_filter_kernel<MODE><<<grid, TC_THREADS, TC_SMEM, st>>>(tq, tx, p);
   RS_LAUNCH_CHECK();
+}
+
+// survivor records -> per-query candidate lists (the global atomics live here, off the MMA-critical path)
+__global__ void __launch_bounds__(256) bucket_kernel(const uint4* __restrict__ rec, const unsigned* __restrict__ rec_cnt,
+                                                     unsigned rec_cap, uint64_t* __restrict__ cand,
+                                                     int* __restrict__ cand_cnt, int cap) {
+  const unsigned n = min(*rec_cnt, rec_cap);
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint4 r = rec[i];
+    const int pos = atomicAdd(&cand_cnt[r.z], 1);
+    if (pos < cap) cand[(int64_t)r.z * cap + pos] = (static_cast<uint64_t>(r.y) << 32) | r.x;
+  }
 }
 
 }  // namespace
@@ -484,9 +549,11 @@ void search_tensor_device(rs_index* h, const float* q, int64_t nq, int k, int64_
     RS_CUDA(cudaMallocAsync(&ws.thr, sizeof(float) * nq_pad, st));
     RS_CUDA(cudaMallocAsync(&ws.smax, sizeof(float) * (size_t)nq_pad * n_vals, st));
     RS_CUDA(cudaMallocAsync(&ws.cnt, sizeof(int) * nq_pad, st));
-    RS_CUDA(cudaMallocAsync(&ws.flags, sizeof(int) * (nq_pad + 1), st));
+    RS_CUDA(cudaMallocAsync(&ws.flags, sizeof(int) * (nq_pad + 4), st));
     RS_CUDA(cudaMallocAsync(&ws.cand, sizeof(uint64_t) * (size_t)nq_pad * CAND_CAP, st));
-    RS_CUDA(cudaMemsetAsync(ws.flags + nq_pad, 0, sizeof(int), st));
+    const unsigned rec_cap = static_cast<unsigned>(nq_pad) * CAND_CAP;
+    RS_CUDA(cudaMallocAsync(&ws.rec, sizeof(uint4) * (size_t)rec_cap, st));
+    RS_CUDA(cudaMemsetAsync(ws.flags + nq_pad, 0, sizeof(int) * 4, st));
 
     {
       ProfScope prof(RS_PROF_RESCORE, st);
@@ -508,6 +575,10 @@ void search_tensor_device(rs_index* h, const float* q, int64_t nq, int k, int64_
     p.cap = CAND_CAP;
     p.smax = ws.smax;
     p.smax_ld = n_vals;
+    p.rec = ws.rec;
+    p.rec_cap = rec_cap;
+    p.overflow = ws.flags + nq_pad + 1;
+    p.rec_cnt = reinterpret_cast<unsigned*>(ws.flags + nq_pad + 2);
     {
       ProfScope prof(RS_PROF_FILTER, st);
       TcParams ps = p;
@@ -530,15 +601,21 @@ void search_tensor_device(rs_index* h, const float* q, int64_t nq, int k, int64_
     }
     {
       ProfScope prof(RS_PROF_RESCORE, st);
+      bucket_kernel<<<sms * 4, 256, 0, st>>>(ws.rec, p.rec_cnt, rec_cap, ws.cand, ws.cnt, CAND_CAP);
+      RS_LAUNCH_CHECK();
       select_rescore_kernel<<<cq, SEL_NT, 0, st>>>(ws.cand, ws.cnt, CAND_CAP, ws.thr, ws.eps2, qc, h->xb, k, id_base,
                                                    D + q0 * ldD, ldD, I + q0 * ldI, ldI, ws.flags, ws.flags + nq_pad);
       RS_LAUNCH_CHECK();
     }
     // step 5: the (rare) queries whose guess could not be verified go through the exact scan
-    std::vector<int> flags(nq_pad + 1);
-    RS_CUDA(cudaMemcpyAsync(flags.data(), ws.flags, sizeof(int) * (nq_pad + 1), cudaMemcpyDeviceToHost, st));
+    std::vector<int> flags(nq_pad + 4);
+    RS_CUDA(cudaMemcpyAsync(flags.data(), ws.flags, sizeof(int) * (nq_pad + 4), cudaMemcpyDeviceToHost, st));
     RS_CUDA(cudaStreamSynchronize(st));
-    if (flags[nq_pad] > 0) {
+    if (flags[nq_pad + 1] != 0 || static_cast<unsigned>(flags[nq_pad + 2]) > rec_cap) {
+      // a staging queue or the record list overran (scores packed inside the margin): nothing is trusted
+      search_exact_device(h, qc, cq, k, id_base, D + q0 * ldD, ldD, I + q0 * ldI, ldI, st);
+      flags[nq_pad] = cq;
+    } else if (flags[nq_pad] > 0) {
       for (int i = 0; i < cq; ++i)
         if (flags[i])
           search_exact_device(h, qc + (int64_t)i * DK, 1, k, id_base, D + (q0 + i) * ldD, ldD, I + (q0 + i) * ldI, ldI, st);
