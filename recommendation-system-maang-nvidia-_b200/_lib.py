@@ -106,7 +106,7 @@ EXPORTED = ["rs_version", "rs_last_error", "rs_launch_count", "rs_device_sm_coun
             "rs_index_fallbacks", "rs_debug_tensor_scores",
             "rs_matvec", "rs_topk_merge", "rs_prof_enable", "rs_prof_read"]
 
-PROF_SCAN, PROF_MERGE, PROF_FILTER, PROF_RESCORE, PROF_RANK = 0, 1, 2, 3, 4
+PROF_SCAN, PROF_MERGE, PROF_FILTER, PROF_RESCORE, PROF_RANK, PROF_SAMPLE = 0, 1, 2, 3, 4, 5
 
 
 def check(status: int) -> None:

@@ -580,7 +580,7 @@ void search_tensor_device(rs_index* h, const float* q, int64_t nq, int k, int64_
     p.overflow = ws.flags + nq_pad + 1;
     p.rec_cnt = reinterpret_cast<unsigned*>(ws.flags + nq_pad + 2);
     {
-      ProfScope prof(RS_PROF_FILTER, st);
+      ProfScope prof(RS_PROF_SAMPLE, st);
       TcParams ps = p;
       ps.n_visit = n_sample;
       ps.tile_step = sample_step;

@@ -55,7 +55,7 @@ def main():
                 rs._lib.prof_enable(True)
                 iters = 20 if nq <= 64 else 5
                 ms = timeit(lambda: index.search(q, k, mode=mode), iters)
-                prof = {n: rs._lib.prof_read(s) for n, s in (("scan", 0), ("merge", 1), ("filter", 2), ("rescore", 3))}
+                prof = {n: rs._lib.prof_read(s) for n, s in (("scan", 0), ("merge", 1), ("filter", 2), ("rescore", 3), ("sample", 5))}
                 rs._lib.prof_enable(False)
                 print(json.dumps({"nq": nq, "k": k, "mode": mode, "ms": round(ms, 4), "qps": round(nq / ms * 1e3, 1),
                                   "catalog_GBps": round(N * d * 4 / ms / 1e6, 1),
