@@ -60,11 +60,13 @@ class ShardedIndexFlatIP:
         Dl, Il = self._local_search(q, k)
         if self.world == 1:
             return Dl, Il
-        Dg = torch.empty((self.world,) + tuple(Dl.shape), dtype=Dl.dtype, device=Dl.device)
-        Ig = torch.empty((self.world,) + tuple(Il.shape), dtype=Il.dtype, device=Il.device)
+        nq, kk = int(Dl.shape[0]), int(Dl.shape[1])
+        # rank-major concatenation along dim 0 (the layout both NCCL and gloo accept), viewed as [G, nq, k]
+        Dg = torch.empty((self.world * nq, kk), dtype=Dl.dtype, device=Dl.device)
+        Ig = torch.empty((self.world * nq, kk), dtype=Il.dtype, device=Il.device)
         dist.all_gather_into_tensor(Dg, Dl.contiguous(), group=self.group)
         dist.all_gather_into_tensor(Ig, Il.contiguous(), group=self.group)
-        return self._merge(Dg, Ig)
+        return self._merge(Dg.view(self.world, nq, kk), Ig.view(self.world, nq, kk))
 
 
 def gather_bytes(world: int, nq: int, k: int) -> int:
