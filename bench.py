@@ -254,13 +254,14 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()                      # samples cover the warm-up and the timed region (both under load)
-    t_w = time.perf_counter()
-    n_warm = 0
-    while n_warm < max(3, args.warmup) or time.perf_counter() - t_w < 1.0:   # >= W steps and >= 1 s so clocks settle
-        step_device()
-        n_warm += 1
-        if n_warm % 8 == 0:
-            torch.cuda.synchronize()
+    # >= W warm-up steps, extended to ~1 s of load so clocks settle and the sampler has data.  The step count
+    # must be identical on every rank (each step contains a collective), so it is derived from a MAX-reduced time.
+    n_warm = max(3, args.warmup)
+    warm_ms = timed(step_device, n_warm)
+    extra = int(min(2000, max(0, (1000.0 - warm_ms) / max(warm_ms / n_warm, 1e-3))))
+    if extra:
+        timed(step_device, extra)
+        n_warm += extra
     barrier()
     rs._lib.prof_enable(True)
     launches0 = rs._lib.launch_count()

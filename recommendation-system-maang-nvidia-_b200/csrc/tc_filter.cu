@@ -47,8 +47,10 @@ constexpr int BN = 256;                  // catalog rows per tile == TMEM column
 constexpr int DK = 128;                  // feature dimension of the tensor path
 constexpr int R_MAX = 2;                 // query tiles resident in shared memory per CTA
 constexpr int NSTAGE = 2;                // catalog tile stages
-constexpr int TC_THREADS = 384;
-constexpr int EPI_WARPS = 8;
+constexpr int EPI_WARPS = 16;              // 4 TMEM lane quarters x EPI_SLICES column slices
+constexpr int EPI_SLICES = EPI_WARPS / 4;
+constexpr int SLICE_COLS = BN / EPI_SLICES; // accumulator columns per epilogue warp
+constexpr int TC_THREADS = 128 + EPI_WARPS * 32;
 constexpr int QTILE_BYTES = BM * DK * 2;  // 32 KB: two [128 x 64] bf16 swizzled halves
 constexpr int STAGE_BYTES = BN * DK * 2;  // 64 KB: two [256 x 64] bf16 swizzled halves
 constexpr int WQ_CAP = 64;               // survivor records per epilogue-warp staging queue
@@ -75,7 +77,7 @@ struct TcParams {
   unsigned* rec_cnt;    // FILTER: number of records appended (may exceed rec_cap: overflow)
   unsigned rec_cap;
   int* overflow;        // FILTER: set when a staging queue overran
-  float* smax;          // [nq_pad][smax_ld] SAMPLE: maxima per (visited tile, column half)
+  unsigned* smax;       // [nq_pad][smax_ld] SAMPLE: ordered-uint maxima; slot = (visit % (smax_ld/S))*S + slice
   int smax_ld;
   float* dump;          // [nq_pad][dump_ld] DUMP (debug: every low-precision score)
   int64_t dump_ld;
@@ -185,7 +187,7 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     // ---------------- epilogue ----------------
     const int ew = warp - 4;
     const int quarter = warp & 3;          // TMEM lanes [32*quarter, 32*quarter + 32) are this warp's
-    const int half = ew >> 2;              // columns [128*half, 128*half + 128) of the accumulator
+    const int slice = ew >> 2;             // columns [SLICE_COLS*slice, SLICE_COLS*(slice+1)) of the accumulator
     const int row_in_tile = quarter * 32 + lane;
     uint4* wq = wqueue + ew * WQ_CAP;      // this warp's staging queue for survivors
     int* wq_cnt = wqueue_cnt + ew;
@@ -213,15 +215,15 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     uint32_t acc_it = 0;
     for (int64_t i = 0; i < n_my; ++i) {
       const int64_t visit = j + i * cpg;
-      const int64_t item0 = visit * p.tile_step * BN + half * 128;
+      const int64_t item0 = visit * p.tile_step * BN + slice * SLICE_COLS;
       for (int r = 0; r < nr; ++r, ++acc_it) {
         const uint32_t a = acc_it & 1u, aph = (acc_it >> 1) & 1u;
         mbar_wait(&tfull[a], aph);
         tc_fence_after_sync();
-        const uint32_t taddr = tmem_base + a * BN + half * 128 + (static_cast<uint32_t>(quarter * 32) << 16);
+        const uint32_t taddr = tmem_base + a * BN + slice * SLICE_COLS + (static_cast<uint32_t>(quarter * 32) << 16);
         float hmax = -INFINITY;
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < SLICE_COLS / 32; ++c) {
           if (p.debug & 1) break;
           float v[32];
           __syncwarp();
@@ -267,7 +269,9 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             }
           }
         }
-        if (MODE == MODE_SAMPLE) p.smax[(int64_t)qrow[r] * p.smax_ld + visit * 2 + half] = hmax;
+        if (MODE == MODE_SAMPLE)   // several sampled tiles share a slot: keep the maximum
+          atomicMax(&p.smax[(int64_t)qrow[r] * p.smax_ld + (visit % (p.smax_ld / EPI_SLICES)) * EPI_SLICES + slice],
+                    f32_to_ordered(hmax));
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[a]);
@@ -338,14 +342,14 @@ __global__ void __launch_bounds__(128) prep_queries_kernel(const float* __restri
 
 // tau_q = the `rank`-th largest of the query's sample maxima; also clears the candidate counters
 template <int NV>
-__global__ void __launch_bounds__(256) threshold_kernel(const float* __restrict__ smax, int n_vals, int rank,
+__global__ void __launch_bounds__(256) threshold_kernel(const unsigned* __restrict__ smax, int n_vals, int rank,
                                                         float* __restrict__ thr, int* __restrict__ cand_cnt,
                                                         int* __restrict__ flags) {
   __shared__ uint64_t keys[NV];
   const int tid = threadIdx.x;
   const int qi = blockIdx.x;
   for (int i = tid; i < NV; i += 256)
-    keys[i] = i < n_vals ? pack_key(smax[(int64_t)qi * n_vals + i], static_cast<uint32_t>(i)) : kEmptyKey;
+    keys[i] = i < n_vals ? (static_cast<uint64_t>(smax[(int64_t)qi * n_vals + i]) << 32) | static_cast<uint32_t>(i) : kEmptyKey;
   __syncthreads();
   block_sort_desc<NV, 256>(keys, tid);
   if (tid == 0) {
@@ -449,7 +453,7 @@ struct Workspace {
   uint16_t* qb = nullptr;
   float* eps2 = nullptr;
   float* thr = nullptr;
-  float* smax = nullptr;
+  unsigned* smax = nullptr;
   int* cnt = nullptr;
   int* flags = nullptr;   // [nq_pad + 4]: per-query flag, then {n_flagged, queue overflow, record count, -}
   uint64_t* cand = nullptr;
@@ -535,9 +539,11 @@ void search_tensor_device(rs_index* h, const float* q, int64_t nq, int k, int64_
     const int nq_pad = (cq + BM - 1) / BM * BM;
     const int n_qtiles = nq_pad / BM;
     const int64_t ntiles = (h->ntotal + BN - 1) / BN;
-    const int64_t n_sample = std::min<int64_t>(512, (ntiles - 1) / 2);
+    // threshold sample: ~5 % of the shard's tiles (64..2048 tiles), never the zero-padded tail tile
+    const int64_t n_sample = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(2048, std::max<int64_t>(64, ntiles / 20)),
+                                                                    (ntiles - 1) / 2));
     const int64_t sample_step = (ntiles - 1) / n_sample;
-    const int n_vals = static_cast<int>(n_sample * 2);
+    const int n_vals = static_cast<int>(std::min<int64_t>(n_sample, 1024 / EPI_SLICES) * EPI_SLICES);
     const double rho = double(n_sample * BN) / double(h->ntotal);
     const double cc = 2.0 * k * rho;
     int rank = static_cast<int>(std::ceil(std::pow(2.0 + std::sqrt(4.0 + cc), 2.0)));
@@ -547,7 +553,8 @@ void search_tensor_device(rs_index* h, const float* q, int64_t nq, int k, int64_
     RS_CUDA(cudaMallocAsync(&ws.qb, sizeof(uint16_t) * (size_t)nq_pad * DK, st));
     RS_CUDA(cudaMallocAsync(&ws.eps2, sizeof(float) * nq_pad, st));
     RS_CUDA(cudaMallocAsync(&ws.thr, sizeof(float) * nq_pad, st));
-    RS_CUDA(cudaMallocAsync(&ws.smax, sizeof(float) * (size_t)nq_pad * n_vals, st));
+    RS_CUDA(cudaMallocAsync(&ws.smax, sizeof(unsigned) * (size_t)nq_pad * n_vals, st));
+    RS_CUDA(cudaMemsetAsync(ws.smax, 0, sizeof(unsigned) * (size_t)nq_pad * n_vals, st));
     RS_CUDA(cudaMallocAsync(&ws.cnt, sizeof(int) * nq_pad, st));
     RS_CUDA(cudaMallocAsync(&ws.flags, sizeof(int) * (nq_pad + 4), st));
     RS_CUDA(cudaMallocAsync(&ws.cand, sizeof(uint64_t) * (size_t)nq_pad * CAND_CAP, st));
