@@ -85,6 +85,43 @@ int rs_dense_forward(const DLTensor* x, const DLTensor* kernel, const DLTensor* 
                      DLTensor* y, void* stream);
 
 /*
+ * K2 (bf16 tensor mode). The same Dense layer on tcgen05 tensor cores: x bf16 [B, in], wt = the Keras
+ * kernel TRANSPOSED to bf16 [out, in], bias f32 [out] or NULL, fp32 accumulation.  Outputs: y_bf16 [B, out]
+ * (the next layer's input) and/or y_f32 [B, out] (may be a column slice of a wider buffer); either may be
+ * NULL.  (in, out) in {64,128,256}^2.  Tolerance vs the fp32 path is stated in tests/test_gpu_ranking_bf16.py.
+ */
+int rs_dense_forward_bf16(const DLTensor* x, const DLTensor* wt, const DLTensor* bias, int act,
+                          DLTensor* y_bf16, DLTensor* y_f32, void* stream);
+/*
+ * K1+K2 / K3 fused (bf16 tensor mode): a whole Dense chain in one tcgen05 kernel, activations kept in tensor
+ * memory between layers.  n_layers = 4: tower chain ids -> Embedding -> 128-256-128-64-128 (tables[p] f32
+ * [V,128], ids[p]); n_layers = 2: deep chain 256-256-128 on x[p] bf16 [B,256].  n_prob = 1 or 2 problems of the
+ * same shape in one launch (the two towers).  wts[p*n_layers+l] bf16 [out,in]; biases likewise (f32, may be NULL);
+ * acts[l] in {RS_ACT_NONE, RS_ACT_RELU}; outputs of the last layer: y_f32[p] and/or y_bf16[p], [B, out], strided.
+ */
+int rs_chain_forward_bf16(int n_prob, int n_layers, const DLTensor* const* wts, const DLTensor* const* biases,
+                          const int* acts, const DLTensor* const* tables, const DLTensor* const* ids,
+                          const DLTensor* const* x, DLTensor* const* y_f32, DLTensor* const* y_bf16, void* stream);
+/*
+ * MultiTaskModel.call (src/models.py:125-131) in bf16 tensor mode behind one handle and one call per batch:
+ * both towers (gather fused) -> deep net -> DCN cross + heads.  The handle COPIES the kernels (bf16 [out,in]; towers
+ * 128-256-128-64-128, index s*4+l with s = 0 user / 1 item; deep net 256-256-128), biases (may be NULL), cross_w /
+ * cross_b f32 [L,256], head_w f32 [2,384] (row 0 rating, row 1 ctr), head_b f32 [2]; it BORROWS the two f32
+ * embedding tables [V,128], which must outlive it.  forward: user_rows/item_rows int32|int64 [B] ->
+ * combined f32 [B,256] (user embedding | item embedding), rating f32 [B,1], ctr f32 [B,1].
+ */
+typedef struct rs_ranker rs_ranker_t;
+int rs_ranker_create(const DLTensor* user_table, const DLTensor* item_table, const DLTensor* const* tower_wt,
+                     const DLTensor* const* tower_b, const DLTensor* const* deep_wt, const DLTensor* const* deep_b,
+                     const DLTensor* cross_w, const DLTensor* cross_b, const DLTensor* head_w, const DLTensor* head_b,
+                     rs_ranker_t** out);
+int rs_ranker_free(rs_ranker_t* h);
+int rs_ranker_forward(rs_ranker_t* h, const DLTensor* user_rows, const DLTensor* item_rows, DLTensor* combined,
+                      DLTensor* rating, DLTensor* ctr, void* stream);
+/* K1 (bf16 tensor mode). Embedding rows gathered from the fp32 table straight into bf16 activations. */
+int rs_gather_bf16(const DLTensor* table, const DLTensor* ids, DLTensor* out, void* stream);
+
+/*
  * K3a. DCN-v1 cross stack (src/models.py:38-44):
  *   for i < n_layers:  s = x_l . w_i  (per row);  x_{l+1} = x0 * s + b_i + x_l
  *   x0: f32 [B, D]; cross_w: f32 [n_layers, D]; cross_b: f32 [n_layers, D];

@@ -1,0 +1,657 @@
+// chain_tc.cu -- K1+K2 / K3 fused (bf16 tensor mode): a whole Dense chain in ONE kernel on tcgen05, with the
+// activations living in tensor memory between layers.
+//   tower chain  (src/models.py:76-77,85,89): ids -> Embedding gather -> Dense256 relu -> Dense128 relu ->
+//                                             Dense64 relu -> Dense128        (both towers in one launch)
+//   deep chain   (src/models.py:26-29,46-48): x0[B,256] -> Dense256 relu -> Dense128 relu
+//
+// Layout of the work, per CTA (one CTA per SM, persistent over 128-row tiles):
+//   * ALL of the chain's kernels (transposed to [out][in] bf16, the K-major B operand) are TMA-loaded once and
+//     stay resident in shared memory: 160 KB for a tower, 192 KB for the deep net.
+//   * The A operand of every layer is read from TENSOR MEMORY (tcgen05.mma with A in TMEM): the epilogue warps
+//     gather the embedding rows (or load the bf16 input rows), convert to bf16 and tcgen05.st them as layer 0's
+//     A operand; after each layer they read the fp32 accumulator (tcgen05.ld), add bias, apply relu, pack to
+//     bf16 and tcgen05.st the result as the next layer's A operand.  Activations never touch shared memory or
+//     HBM: per sample the kernel reads the ids + one 512-byte embedding row and writes the 128-wide output.
+//   * TMEM columns (512 per CTA) are re-used along the chain:  A0 [0,64|128)  acc1 [256,512)  A1 [0,128)
+//     acc2 [128,256)  A2 [0,64)  acc3 [64,128)  A3 [128,160)  acc4 [256,384).
+//   * warp 0: TMA (weights), warp 1: the single tcgen05.mma issuer, warps 4-19: epilogue (TMEM lane quarter =
+//     warp % 4, column slice = (warp-4)/4).  Two mbarriers alternate per layer: a_ready (epilogue -> MMA, the A
+//     operand is in TMEM) and acc_ready (tcgen05.commit -> epilogue).
+// Tensor work per sample: 81,920 MAC per tower, 98,304 MAC for the deep net.
+#include <algorithm>
+#include <memory>
+#include <mutex>
+
+#include "common.cuh"
+#include "tcgen05.cuh"
+
+namespace {
+
+using namespace rsd;
+
+constexpr int BM = 128;
+constexpr int EPI_WARPS = 16;
+constexpr int NTHREADS = 128 + EPI_WARPS * 32;
+constexpr int MAX_L = 4;
+
+struct CfgTower {
+  static constexpr int L = 4;
+  static constexpr bool GATHER = true;
+  __host__ __device__ static constexpr int K(int l) { return l == 0 ? 128 : l == 1 ? 256 : l == 2 ? 128 : 64; }
+  __host__ __device__ static constexpr int N(int l) { return l == 0 ? 256 : l == 1 ? 128 : l == 2 ? 64 : 128; }
+  __host__ __device__ static constexpr int ACOL(int l) { return l == 3 ? 128 : 0; }
+  __host__ __device__ static constexpr int DCOL(int l) { return l == 0 ? 256 : l == 1 ? 128 : l == 2 ? 64 : 256; }
+};
+struct CfgDeep {
+  static constexpr int L = 2;
+  static constexpr bool GATHER = false;
+  __host__ __device__ static constexpr int K(int l) { return 256; }
+  __host__ __device__ static constexpr int N(int l) { return l == 0 ? 256 : 128; }
+  __host__ __device__ static constexpr int ACOL(int l) { return 0; }
+  __host__ __device__ static constexpr int DCOL(int l) { return l == 0 ? 256 : 128; }
+};
+
+template <class C>
+__host__ __device__ constexpr int w_off(int l) {  // byte offset of layer l's kernel in shared memory
+  int o = 0;
+  for (int i = 0; i < l; ++i) o += C::N(i) * C::K(i) * 2;
+  return o;
+}
+template <class C>
+__host__ __device__ constexpr int b_off(int l) {  // float offset of layer l's bias
+  int o = 0;
+  for (int i = 0; i < l; ++i) o += C::N(i);
+  return o;
+}
+template <class C>
+constexpr int chain_smem() {
+  return w_off<C>(C::L) + b_off<C>(C::L) * 4 + 256 /*barriers*/ + 1024 /*align*/;
+}
+
+struct ChainMaps {
+  CUtensorMap w[2][MAX_L];   // [problem][layer]
+};
+
+struct ChainProblem {
+  int64_t rows;
+  const float* bias[MAX_L];
+  const float* table;    // GATHER: fp32 [V, 128]
+  int64_t table_ld;
+  int64_t table_rows;
+  const void* ids;       // GATHER: int32 / int64 [rows]
+  int ids64;
+  const uint16_t* x;     // !GATHER: bf16 [rows, 256]
+  int64_t x_ld;
+  float* y_f32;          // [rows, N_last] or nullptr
+  int64_t ld_f32;
+  uint16_t* y_bf16;      // [rows, N_last] or nullptr
+  int64_t ld_bf16;
+};
+
+struct ChainParams {
+  ChainProblem prob[2];
+  int n_prob;            // 1 or 2 (both towers in one launch)
+  int act[MAX_L];
+};
+
+template <class C>
+__global__ void __launch_bounds__(NTHREADS, 1)
+chain_tc_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* wsm = base;
+  float* bias_s = reinterpret_cast<float*>(base + w_off<C>(C::L));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + b_off<C>(C::L));
+  uint64_t* wfull = bars;
+  uint64_t* a_ready = bars + 1;
+  uint64_t* acc_ready = bars + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int pi = blockIdx.x % p.n_prob;                 // which problem (tower) this CTA works on
+  const int cta = blockIdx.x / p.n_prob;
+  const int ncta = (gridDim.x - pi + p.n_prob - 1) / p.n_prob;
+  const ChainProblem& pr = p.prob[pi];
+  const int64_t ntiles = (pr.rows + BM - 1) / BM;
+  const int64_t n_my = cta < ntiles ? (ntiles - cta + ncta - 1) / ncta : 0;
+
+  if (warp == 0 && lane == 0) {
+    for (int l = 0; l < C::L; ++l) tma_prefetch_desc(&maps.w[pi][l]);
+    mbar_init(wfull, 1);
+    mbar_init(a_ready, EPI_WARPS);
+    mbar_init(acc_ready, 1);
+    fence_mbar_init();
+  }
+#pragma unroll
+  for (int l = 0; l < C::L; ++l)
+    for (int i = threadIdx.x; i < C::N(l); i += NTHREADS) bias_s[b_off<C>(l) + i] = pr.bias[l] ? pr.bias[l][i] : 0.0f;
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(wfull, w_off<C>(C::L));
+#pragma unroll
+      for (int l = 0; l < C::L; ++l)
+        for (int kc = 0; kc < C::K(l) / 64; ++kc)
+          tma_load_2d(wsm + w_off<C>(l) + kc * (C::N(l) * 128), &maps.w[pi][l], wfull, kc * 64, 0, kEvictLast);
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      // ---------------- MMA issuer: one layer at a time, A from TMEM, B from the resident weights ----------------
+      mbar_wait(wfull, 0);
+      uint32_t use = 0;
+      for (int64_t i = 0; i < n_my; ++i) {
+#pragma unroll
+        for (int l = 0; l < C::L; ++l, ++use) {
+          mbar_wait(a_ready, use & 1u);
+          tc_fence_after_sync();
+          const uint32_t idesc = umma_idesc_bf16_f32(BM, C::N(l));
+#pragma unroll
+          for (int k = 0; k < C::K(l) / 16; ++k) {
+            const uint64_t db =
+                umma_desc_k_sw128(smem_u32(wsm + w_off<C>(l) + (k >> 2) * (C::N(l) * 128)) + static_cast<uint32_t>(k & 3) * 32u);
+            umma_bf16_ts(tmem_base + C::DCOL(l), tmem_base + C::ACOL(l) + k * 8, db, idesc, k > 0 ? 1u : 0u);
+          }
+          umma_commit(acc_ready);
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ---------------- epilogue warps: produce A0, then bias/activation/repack between layers ----------------
+    const int quarter = warp & 3;
+    const int slice = (warp - 4) >> 2;
+    const uint32_t lane_sel = static_cast<uint32_t>(quarter * 32) << 16;
+    uint32_t use = 0;
+    for (int64_t i = 0; i < n_my; ++i) {
+      const int64_t tile = cta + i * ncta;
+      const int64_t row = tile * BM + quarter * 32 + lane;
+      // ---- layer-0 A operand: this thread's row, this warp's feature slice, as packed bf16 pairs ----
+      if constexpr (C::GATHER) {
+        uint32_t r[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) r[e] = 0u;
+        if (row < pr.rows) {
+          const int64_t id = pr.ids64 ? static_cast<const int64_t*>(pr.ids)[row]
+                                      : static_cast<int64_t>(static_cast<const int32_t*>(pr.ids)[row]);
+          if (id >= 0 && id < pr.table_rows) {
+            const float4* src = reinterpret_cast<const float4*>(pr.table + id * pr.table_ld + slice * 32);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float4 f = __ldg(src + e);
+              r[2 * e] = pack_bf16x2(f.x, f.y);
+              r[2 * e + 1] = pack_bf16x2(f.z, f.w);
+            }
+          }
+        }
+        __syncwarp();
+        tmem_st_32x32_x16(tmem_base + C::ACOL(0) + slice * 16 + lane_sel, r);
+      } else {
+        uint32_t r0[16], r1[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) r0[e] = r1[e] = 0u;
+        if (row < pr.rows) {
+          const uint4* src = reinterpret_cast<const uint4*>(pr.x + row * pr.x_ld + slice * 64);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const uint4 a = __ldg(src + e), b = __ldg(src + 4 + e);
+            r0[4 * e] = a.x; r0[4 * e + 1] = a.y; r0[4 * e + 2] = a.z; r0[4 * e + 3] = a.w;
+            r1[4 * e] = b.x; r1[4 * e + 1] = b.y; r1[4 * e + 2] = b.z; r1[4 * e + 3] = b.w;
+          }
+        }
+        __syncwarp();
+        tmem_st_32x32_x16(tmem_base + C::ACOL(0) + slice * 32 + lane_sel, r0);
+        tmem_st_32x32_x16(tmem_base + C::ACOL(0) + slice * 32 + 16 + lane_sel, r1);
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_ready);
+
+#pragma unroll
+      for (int l = 0; l < C::L; ++l, ++use) {
+        const int N = C::N(l);
+        const int slices = N >= 128 ? 4 : 2;
+        const int cols = N / slices;                       // accumulator columns per warp: 64, 32 or 32
+        mbar_wait(acc_ready, use & 1u);
+        tc_fence_after_sync();
+        if (slice < slices) {
+#pragma unroll 1
+          for (int c = 0; c < cols / 32; ++c) {
+            const int col0 = slice * cols + c * 32;
+            float v[32];
+            __syncwarp();
+            tmem_ld_32x32(tmem_base + C::DCOL(l) + col0 + lane_sel, v);
+            const float* bs = bias_s + b_off<C>(l) + col0;
+#pragma unroll
+            for (int e = 0; e < 32; e += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(bs + e);
+              v[e] += b4.x; v[e + 1] += b4.y; v[e + 2] += b4.z; v[e + 3] += b4.w;
+            }
+            if (p.act[l] == RS_ACT_RELU) {
+#pragma unroll
+              for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], 0.0f);
+            }
+            if (l + 1 < C::L) {
+              uint32_t r[16];
+#pragma unroll
+              for (int e = 0; e < 16; ++e) r[e] = pack_bf16x2(v[2 * e], v[2 * e + 1]);
+              tmem_st_32x32_x16(tmem_base + C::ACOL(l + 1 < C::L ? l + 1 : l) + (col0 >> 1) + lane_sel, r);
+            } else if (row < pr.rows) {
+              if (pr.y_f32) {
+                float4* dst = reinterpret_cast<float4*>(pr.y_f32 + row * pr.ld_f32 + col0);
+#pragma unroll
+                for (int e = 0; e < 32; e += 4) dst[e >> 2] = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+              }
+              if (pr.y_bf16) {
+                uint4* dst = reinterpret_cast<uint4*>(pr.y_bf16 + row * pr.ld_bf16 + col0);
+#pragma unroll
+                for (int e = 0; e < 32; e += 8)
+                  dst[e >> 3] = make_uint4(pack_bf16x2(v[e], v[e + 1]), pack_bf16x2(v[e + 2], v[e + 3]),
+                                           pack_bf16x2(v[e + 4], v[e + 5]), pack_bf16x2(v[e + 6], v[e + 7]));
+              }
+            }
+          }
+        }
+        if (l + 1 < C::L) {
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(a_ready);
+        }
+      }
+      // the next tile's A0 overwrites TMEM columns this tile's last accumulator does not use, and the last
+      // accumulator is not overwritten before the next tile's layer L (after further a_ready/acc_ready rounds)
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <class C>
+void launch_chain(const ChainMaps& maps, const ChainParams& p, cudaStream_t st) {
+  static std::once_flag once[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::call_once(once[dev & 63], [] {
+    cudaFuncSetAttribute(chain_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, chain_smem<C>());
+  });
+  int64_t max_tiles = 0;
+  for (int i = 0; i < p.n_prob; ++i) max_tiles = std::max<int64_t>(max_tiles, (p.prob[i].rows + BM - 1) / BM);
+  const int sms = rs::sm_count();
+  int grid = static_cast<int>(std::min<int64_t>(max_tiles * p.n_prob, sms - (sms % p.n_prob)));
+  grid = std::max(grid, p.n_prob);
+  rs::ProfScope prof(RS_PROF_RANK, st);
+  chain_tc_kernel<C><<<grid, NTHREADS, chain_smem<C>(), st>>>(maps, p);
+  RS_LAUNCH_CHECK();
+}
+
+}  // namespace
+
+// One entry for both chain shapes.  n_prob = 1 or 2 independent problems with the same layer shapes (the two
+// towers).  Per problem p: wts[p*n_layers + l] bf16 [N_l, K_l], biases[p*n_layers + l] f32 [N_l] or NULL.
+// Tower chain: tables[p] f32 [V,128] + ids[p]; deep chain: x[p] bf16 [B,256].
+extern "C" int rs_chain_forward_bf16(int n_prob, int n_layers, const DLTensor* const* wts, const DLTensor* const* biases,
+                                     const int* acts, const DLTensor* const* tables, const DLTensor* const* ids,
+                                     const DLTensor* const* x, DLTensor* const* y_f32, DLTensor* const* y_bf16,
+                                     void* stream) {
+  return rs::guard([&] {
+    using namespace rs;
+    RS_CHECK(n_prob == 1 || n_prob == 2, "n_prob must be 1 or 2");
+    RS_CHECK(n_layers == 4 || n_layers == 2, "supported chains: 4 layers (tower) or 2 layers (deep net)");
+    const bool tower = n_layers == 4;
+    ChainMaps maps;
+    ChainParams p{};
+    p.n_prob = n_prob;
+    for (int l = 0; l < n_layers; ++l) {
+      RS_CHECK(acts[l] == RS_ACT_NONE || acts[l] == RS_ACT_RELU, "chain activations must be relu or linear");
+      p.act[l] = acts[l];
+    }
+    sm_count();
+    for (int q = 0; q < n_prob; ++q) {
+      ChainProblem& pr = p.prob[q];
+      for (int l = 0; l < n_layers; ++l) {
+        const DLTensor* w = wts[q * n_layers + l];
+        require(w, "wt", 2, kDLBfloat, 16);
+        const int K = tower ? CfgTower::K(l) : CfgDeep::K(l);
+        const int N = tower ? CfgTower::N(l) : CfgDeep::N(l);
+        RS_CHECK(on_device(w) && is_compact(w) && w->shape[0] == N && w->shape[1] == K,
+                 "fused chain supports only 128-256-128-64-128 (tower) and 256-256-128 (deep); layer " + std::to_string(l) +
+                     " has shape [" + std::to_string(w->shape[0]) + ", " + std::to_string(w->shape[1]) + "]");
+        maps.w[q][l] = make_tmap_2d(data_ptr<void>(w), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)N, (uint64_t)K,
+                                    (uint64_t)K * 2, static_cast<uint32_t>(N), 64);
+        const DLTensor* b = biases ? biases[q * n_layers + l] : nullptr;
+        if (b) {
+          require(b, "bias", 1, kDLFloat, 32);
+          RS_CHECK(on_device(b) && b->shape[0] == N && stride_of(b, 0) == 1, "bias must be a contiguous CUDA [out] tensor");
+          pr.bias[l] = data_ptr<float>(b);
+        }
+      }
+      const int n_last = tower ? CfgTower::N(3) : CfgDeep::N(1);
+      int64_t rows = -1;
+      if (tower) {
+        const DLTensor* tb = tables[q];
+        const DLTensor* id = ids[q];
+        require(tb, "table", 2, kDLFloat, 32);
+        RS_CHECK(id && id->ndim == 1 && (is_dtype(id, kDLInt, 32) || is_dtype(id, kDLInt, 64)), "ids must be 1-D int32/int64");
+        RS_CHECK(on_device(tb) && on_device(id) && tb->shape[1] == 128, "table must be a CUDA [V, 128] tensor");
+        RS_CHECK(id->shape[0] <= 1 || stride_of(id, 0) == 1, "ids must be contiguous");
+        pr.table = data_ptr<float>(tb);
+        pr.table_ld = row_stride_2d(tb, "table");
+        pr.table_rows = tb->shape[0];
+        RS_CHECK(pr.table_ld % 4 == 0, "table row stride must be a multiple of 4");
+        require_aligned16(pr.table, "table");
+        pr.ids = data_ptr<void>(id);
+        pr.ids64 = is_dtype(id, kDLInt, 64) ? 1 : 0;
+        rows = id->shape[0];
+      } else {
+        const DLTensor* xx = x[q];
+        require(xx, "x", 2, kDLBfloat, 16);
+        RS_CHECK(on_device(xx) && xx->shape[1] == 256, "x must be a CUDA bf16 [B, 256] tensor");
+        pr.x = data_ptr<uint16_t>(xx);
+        pr.x_ld = row_stride_2d(xx, "x");
+        RS_CHECK(pr.x_ld % 8 == 0, "x row stride must be a multiple of 8");
+        require_aligned16(pr.x, "x");
+        rows = xx->shape[0];
+      }
+      pr.rows = rows;
+      const DLTensor* yf = y_f32 ? y_f32[q] : nullptr;
+      const DLTensor* yb = y_bf16 ? y_bf16[q] : nullptr;
+      RS_CHECK(yf || yb, "each problem needs at least one output");
+      if (yf) {
+        require(yf, "y_f32", 2, kDLFloat, 32);
+        RS_CHECK(on_device(yf) && yf->shape[0] == rows && yf->shape[1] == n_last, "y_f32 must be [B, out]");
+        pr.y_f32 = data_ptr<float>(yf);
+        pr.ld_f32 = row_stride_2d(yf, "y_f32");
+        RS_CHECK(pr.ld_f32 % 4 == 0, "y_f32 row stride must be a multiple of 4");
+        require_aligned16(pr.y_f32, "y_f32");
+      }
+      if (yb) {
+        require(yb, "y_bf16", 2, kDLBfloat, 16);
+        RS_CHECK(on_device(yb) && yb->shape[0] == rows && yb->shape[1] == n_last, "y_bf16 must be [B, out]");
+        pr.y_bf16 = data_ptr<uint16_t>(yb);
+        pr.ld_bf16 = row_stride_2d(yb, "y_bf16");
+        RS_CHECK(pr.ld_bf16 % 8 == 0, "y_bf16 row stride must be a multiple of 8");
+        require_aligned16(pr.y_bf16, "y_bf16");
+      }
+    }
+    bool any = false;
+    for (int q = 0; q < n_prob; ++q) any |= p.prob[q].rows > 0;
+    if (!any) return;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (tower) launch_chain<CfgTower>(maps, p, st);
+    else launch_chain<CfgDeep>(maps, p, st);
+  });
+}
+
+// ================================================================================================
+// rs_ranker: MultiTaskModel.call (src/models.py:125-131) behind one handle and ONE C call per batch.
+// The handle owns bf16 copies of the Dense kernels ([out][in]), the fp32 biases, cross vectors and heads, and the
+// TMA maps over them; the embedding tables are borrowed (they can be tens of GB) and must outlive the handle.
+//   forward: chain<Tower> (both towers, gather fused) -> chain<Deep> -> cross_heads_kernel
+// ================================================================================================
+namespace {
+
+// DCN-v1 cross stack + both heads for D = 256, deep width 128, without materialising the [B,384] concat:
+// one warp per row; x0/x_l live in registers (8 per lane), deep output 4 per lane.
+__global__ void __launch_bounds__(256) cross_heads_kernel(const float* __restrict__ x0p, int64_t ldx,
+                                                          const float* __restrict__ deep, int64_t ldd,
+                                                          const float* __restrict__ cw, const float* __restrict__ cb,
+                                                          int n_layers, const float* __restrict__ hw,
+                                                          const float* __restrict__ hb, float* __restrict__ rating,
+                                                          float* __restrict__ ctr, int64_t B) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  constexpr int D = 256, W = 384;
+  for (int64_t r = warp; r < B; r += nwarps) {
+    float4 x0[2], xl[2];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      x0[c] = __ldg(reinterpret_cast<const float4*>(x0p + r * ldx) + lane + 32 * c);
+      xl[c] = x0[c];
+    }
+    const float4 dv = __ldg(reinterpret_cast<const float4*>(deep + r * ldd) + lane);
+    for (int l = 0; l < n_layers; ++l) {
+      float s = 0.0f;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(cw + (int64_t)l * D) + lane + 32 * c);
+        s = fmaf(xl[c].x, wv.x, s); s = fmaf(xl[c].y, wv.y, s); s = fmaf(xl[c].z, wv.z, s); s = fmaf(xl[c].w, wv.w, s);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const float4 bv = __ldg(reinterpret_cast<const float4*>(cb + (int64_t)l * D) + lane + 32 * c);
+        xl[c].x = (x0[c].x * s + bv.x) + xl[c].x;
+        xl[c].y = (x0[c].y * s + bv.y) + xl[c].y;
+        xl[c].z = (x0[c].z * s + bv.z) + xl[c].z;
+        xl[c].w = (x0[c].w * s + bv.w) + xl[c].w;
+      }
+    }
+    float sr = 0.0f, sc = 0.0f;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const float4 wr = __ldg(reinterpret_cast<const float4*>(hw) + lane + 32 * c);
+      const float4 wc = __ldg(reinterpret_cast<const float4*>(hw + W) + lane + 32 * c);
+      sr = fmaf(xl[c].x, wr.x, sr); sr = fmaf(xl[c].y, wr.y, sr); sr = fmaf(xl[c].z, wr.z, sr); sr = fmaf(xl[c].w, wr.w, sr);
+      sc = fmaf(xl[c].x, wc.x, sc); sc = fmaf(xl[c].y, wc.y, sc); sc = fmaf(xl[c].z, wc.z, sc); sc = fmaf(xl[c].w, wc.w, sc);
+    }
+    {
+      const float4 wr = __ldg(reinterpret_cast<const float4*>(hw + D) + lane);
+      const float4 wc = __ldg(reinterpret_cast<const float4*>(hw + W + D) + lane);
+      sr = fmaf(dv.x, wr.x, sr); sr = fmaf(dv.y, wr.y, sr); sr = fmaf(dv.z, wr.z, sr); sr = fmaf(dv.w, wr.w, sr);
+      sc = fmaf(dv.x, wc.x, sc); sc = fmaf(dv.y, wc.y, sc); sc = fmaf(dv.z, wc.z, sc); sc = fmaf(dv.w, wc.w, sc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sr += __shfl_xor_sync(0xFFFFFFFFu, sr, o);
+      sc += __shfl_xor_sync(0xFFFFFFFFu, sc, o);
+    }
+    if (lane == 0) {
+      rating[r] = sr + hb[0];
+      ctr[r] = 1.0f / (1.0f + expf(-(sc + hb[1])));
+    }
+  }
+}
+
+}  // namespace
+
+struct rs_ranker {
+  int device = 0;
+  int cross_layers = 0;
+  const float* table[2] = {nullptr, nullptr};   // borrowed
+  int64_t table_ld[2] = {0, 0}, table_rows[2] = {0, 0};
+  uint16_t* wts = nullptr;      // all bf16 kernels, [out][in] each: user tower, item tower, deep
+  float* f32 = nullptr;         // biases (user 576, item 576, deep 384), cross_w [L,256], cross_b [L,256], head_w [2,384], head_b [2]
+  size_t off_w[2][4], off_dw[2];
+  size_t off_b[2][4], off_db[2], off_cw, off_cb, off_hw, off_hb;
+  ChainMaps tower_maps, deep_maps;
+};
+
+namespace {
+
+void copy_in(void* dst, const DLTensor* t, size_t bytes, cudaStream_t st) {
+  RS_CUDA(cudaMemcpyAsync(dst, rs::data_ptr<void>(t), bytes, cudaMemcpyDeviceToDevice, st));
+}
+
+}  // namespace
+
+extern "C" int rs_ranker_create(const DLTensor* user_table, const DLTensor* item_table, const DLTensor* const* tower_wt,
+                                const DLTensor* const* tower_b, const DLTensor* const* deep_wt,
+                                const DLTensor* const* deep_b, const DLTensor* cross_w, const DLTensor* cross_b,
+                                const DLTensor* head_w, const DLTensor* head_b, rs_ranker** out) {
+  return rs::guard([&] {
+    using namespace rs;
+    RS_CHECK(out != nullptr, "out is NULL");
+    sm_count();
+    auto h = std::unique_ptr<rs_ranker>(new rs_ranker());
+    RS_CUDA(cudaGetDevice(&h->device));
+    const DLTensor* tabs[2] = {user_table, item_table};
+    for (int s = 0; s < 2; ++s) {
+      require(tabs[s], "table", 2, kDLFloat, 32);
+      RS_CHECK(on_device(tabs[s]) && tabs[s]->shape[1] == 128, "embedding tables must be CUDA [V, 128] tensors");
+      h->table[s] = data_ptr<float>(tabs[s]);
+      h->table_ld[s] = row_stride_2d(tabs[s], "table");
+      h->table_rows[s] = tabs[s]->shape[0];
+      RS_CHECK(h->table_ld[s] % 4 == 0, "table row stride must be a multiple of 4");
+      require_aligned16(h->table[s], "table");
+    }
+    // sizes
+    size_t wb = 0, fb = 0;
+    for (int s = 0; s < 2; ++s)
+      for (int l = 0; l < 4; ++l) {
+        h->off_w[s][l] = wb;
+        wb += (size_t)CfgTower::N(l) * CfgTower::K(l);
+        h->off_b[s][l] = fb;
+        fb += CfgTower::N(l);
+      }
+    for (int l = 0; l < 2; ++l) {
+      h->off_dw[l] = wb;
+      wb += (size_t)CfgDeep::N(l) * CfgDeep::K(l);
+      h->off_db[l] = fb;
+      fb += CfgDeep::N(l);
+    }
+    require(cross_w, "cross_w", 2, kDLFloat, 32);
+    require(cross_b, "cross_b", 2, kDLFloat, 32);
+    require(head_w, "head_w", 2, kDLFloat, 32);
+    require(head_b, "head_b", 1, kDLFloat, 32);
+    const int64_t L = cross_w->shape[0];
+    RS_CHECK(L >= 0 && L <= 8 && cross_w->shape[1] == 256 && cross_b->shape[0] == L && cross_b->shape[1] == 256 &&
+                 is_compact(cross_w) && is_compact(cross_b), "cross_w / cross_b must be contiguous [n_layers, 256]");
+    RS_CHECK(head_w->shape[0] == 2 && head_w->shape[1] == 384 && is_compact(head_w) && head_b->shape[0] == 2,
+             "head_w must be contiguous [2, 384], head_b [2]");
+    h->cross_layers = static_cast<int>(L);
+    h->off_cw = fb; fb += (size_t)L * 256;
+    h->off_cb = fb; fb += (size_t)L * 256;
+    h->off_hw = fb; fb += 2 * 384;
+    h->off_hb = fb; fb += 4;
+    RS_CUDA(cudaMalloc(&h->wts, wb * sizeof(uint16_t)));
+    RS_CUDA(cudaMalloc(&h->f32, fb * sizeof(float)));
+    RS_CUDA(cudaMemset(h->f32, 0, fb * sizeof(float)));
+    cudaStream_t st = nullptr;
+    auto take_w = [&](const DLTensor* w, int N, int K, size_t off, CUtensorMap* map) {
+      require(w, "wt", 2, kDLBfloat, 16);
+      RS_CHECK(on_device(w) && is_compact(w) && w->shape[0] == N && w->shape[1] == K,
+               "the fused ranker supports towers 128-256-128-64-128 and deep net 256-256-128 (kernels as bf16 [out, in])");
+      copy_in(h->wts + off, w, (size_t)N * K * 2, st);
+      *map = make_tmap_2d(h->wts + off, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)N, (uint64_t)K, (uint64_t)K * 2,
+                          static_cast<uint32_t>(N), 64);
+    };
+    auto take_b = [&](const DLTensor* b, int N, size_t off) {
+      if (!b) return;
+      require(b, "bias", 1, kDLFloat, 32);
+      RS_CHECK(on_device(b) && b->shape[0] == N && (N <= 1 || stride_of(b, 0) == 1), "bias must be a contiguous CUDA [out] tensor");
+      copy_in(h->f32 + off, b, (size_t)N * 4, st);
+    };
+    for (int s = 0; s < 2; ++s)
+      for (int l = 0; l < 4; ++l) {
+        take_w(tower_wt[s * 4 + l], CfgTower::N(l), CfgTower::K(l), h->off_w[s][l], &h->tower_maps.w[s][l]);
+        take_b(tower_b ? tower_b[s * 4 + l] : nullptr, CfgTower::N(l), h->off_b[s][l]);
+      }
+    for (int l = 0; l < 2; ++l) {
+      take_w(deep_wt[l], CfgDeep::N(l), CfgDeep::K(l), h->off_dw[l], &h->deep_maps.w[0][l]);
+      take_b(deep_b ? deep_b[l] : nullptr, CfgDeep::N(l), h->off_db[l]);
+    }
+    RS_CHECK(on_device(cross_w) && on_device(cross_b) && on_device(head_w) && on_device(head_b), "weights must be CUDA tensors");
+    if (L > 0) {
+      copy_in(h->f32 + h->off_cw, cross_w, (size_t)L * 256 * 4, st);
+      copy_in(h->f32 + h->off_cb, cross_b, (size_t)L * 256 * 4, st);
+    }
+    copy_in(h->f32 + h->off_hw, head_w, 2 * 384 * 4, st);
+    copy_in(h->f32 + h->off_hb, head_b, 2 * 4, st);
+    RS_CUDA(cudaStreamSynchronize(st));
+    *out = h.release();
+  });
+}
+
+extern "C" int rs_ranker_free(rs_ranker* h) {
+  return rs::guard([&] {
+    if (!h) return;
+    cudaFree(h->wts);
+    cudaFree(h->f32);
+    delete h;
+  });
+}
+
+// user_rows / item_rows: int32|int64 [B]; combined: f32 [B, 256] (user embedding | item embedding, the DCN input);
+// rating, ctr: f32 [B, 1]
+extern "C" int rs_ranker_forward(rs_ranker* h, const DLTensor* user_rows, const DLTensor* item_rows, DLTensor* combined,
+                                 DLTensor* rating, DLTensor* ctr, void* stream) {
+  return rs::guard([&] {
+    using namespace rs;
+    RS_CHECK(h != nullptr, "ranker is NULL");
+    const DLTensor* ids[2] = {user_rows, item_rows};
+    require(combined, "combined", 2, kDLFloat, 32);
+    require(rating, "rating", 2, kDLFloat, 32);
+    require(ctr, "ctr", 2, kDLFloat, 32);
+    const int64_t B = combined->shape[0];
+    RS_CHECK(on_device(combined) && combined->shape[1] == 256 && is_compact(combined), "combined must be a contiguous CUDA [B, 256] tensor");
+    RS_CHECK(on_device(rating) && on_device(ctr) && rating->shape[0] == B && ctr->shape[0] == B && rating->shape[1] == 1 &&
+                 ctr->shape[1] == 1 && is_compact(rating) && is_compact(ctr), "rating / ctr must be contiguous CUDA [B, 1] tensors");
+    require_aligned16(data_ptr<float>(combined), "combined");
+    if (B == 0) return;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    uint16_t* x_bf16 = nullptr;   // [B, 256] bf16 copy of the tower outputs: the deep net's input
+    float* deep_out = nullptr;    // [B, 128]
+    RS_CUDA(cudaMallocAsync(&x_bf16, sizeof(uint16_t) * (size_t)B * 256, st));
+    RS_CUDA(cudaMallocAsync(&deep_out, sizeof(float) * (size_t)B * 128, st));
+    try {
+      ChainParams p{};
+      p.n_prob = 2;
+      p.act[0] = p.act[1] = p.act[2] = RS_ACT_RELU;
+      p.act[3] = RS_ACT_NONE;
+      for (int s = 0; s < 2; ++s) {
+        ChainProblem& pr = p.prob[s];
+        RS_CHECK(ids[s] && ids[s]->ndim == 1 && ids[s]->shape[0] == B && on_device(ids[s]) &&
+                     (is_dtype(ids[s], kDLInt, 32) || is_dtype(ids[s], kDLInt, 64)) && (B <= 1 || stride_of(ids[s], 0) == 1),
+                 "row ids must be contiguous CUDA int32/int64 [B] tensors");
+        pr.rows = B;
+        for (int l = 0; l < 4; ++l) pr.bias[l] = h->f32 + h->off_b[s][l];
+        pr.table = h->table[s];
+        pr.table_ld = h->table_ld[s];
+        pr.table_rows = h->table_rows[s];
+        pr.ids = data_ptr<void>(ids[s]);
+        pr.ids64 = is_dtype(ids[s], kDLInt, 64) ? 1 : 0;
+        pr.y_f32 = data_ptr<float>(combined) + s * 128;
+        pr.ld_f32 = 256;
+        pr.y_bf16 = x_bf16 + s * 128;
+        pr.ld_bf16 = 256;
+      }
+      launch_chain<CfgTower>(h->tower_maps, p, st);
+      ChainParams d{};
+      d.n_prob = 1;
+      d.act[0] = d.act[1] = RS_ACT_RELU;
+      d.prob[0].rows = B;
+      for (int l = 0; l < 2; ++l) d.prob[0].bias[l] = h->f32 + h->off_db[l];
+      d.prob[0].x = x_bf16;
+      d.prob[0].x_ld = 256;
+      d.prob[0].y_f32 = deep_out;
+      d.prob[0].ld_f32 = 128;
+      launch_chain<CfgDeep>(h->deep_maps, d, st);
+      const int64_t want = (B * 32 + 255) / 256;
+      const int blocks = static_cast<int>(std::min<int64_t>(want, (int64_t)sm_count() * 8));
+      cross_heads_kernel<<<blocks, 256, 0, st>>>(data_ptr<float>(combined), 256, deep_out, 128, h->f32 + h->off_cw,
+                                                 h->f32 + h->off_cb, h->cross_layers, h->f32 + h->off_hw,
+                                                 h->f32 + h->off_hb, data_ptr<float>(rating), data_ptr<float>(ctr), B);
+      RS_LAUNCH_CHECK();
+    } catch (...) {
+      cudaFreeAsync(x_bf16, st);
+      cudaFreeAsync(deep_out, st);
+      throw;
+    }
+    cudaFreeAsync(x_bf16, st);
+    cudaFreeAsync(deep_out, st);
+  });
+}

@@ -107,6 +107,28 @@ __device__ __forceinline__ void tmem_ld_32x32_x128(uint32_t taddr, float (&v)[12
   for (int i = 0; i < 128; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+
+// D[tmem] (+)= A[tmem] * B[smem]^T : the A operand (bf16, lane = row, 32-bit column j = k 2j,2j+1) is read from
+// tensor memory, so activations produced by an epilogue never touch shared memory
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// registers -> TMEM: 32 lanes x 16 consecutive 32-bit columns, then wait for the store to land
+__device__ __forceinline__ void tmem_st_32x32_x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n\t"
+      "tcgen05.wait::st.sync.aligned;"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float (&v)[32]) { tmem_ld_32x32(taddr, v); }
 __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float (&v)[64]) { tmem_ld_32x32_x64(taddr, v); }
 __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float (&v)[128]) { tmem_ld_32x32_x128(taddr, v); }

@@ -107,6 +107,20 @@ class Dense:
             self.build(int(x.shape[-1]))
         return ops.dense(x, self.kernel, self.bias, self.activation, out=out)
 
+    def wt_bf16(self) -> torch.Tensor:
+        """The kernel transposed to [out, in] bf16 -- the K-major B operand of the tcgen05 path (cached)."""
+        c = getattr(self, "_wt_cache", None)
+        if c is None or c[0] != self.kernel.data_ptr():
+            c = (self.kernel.data_ptr(), self.kernel.t().contiguous().to(torch.bfloat16))
+            self._wt_cache = c
+        return c[1]
+
+    def call_bf16(self, x_bf16: torch.Tensor, out_bf16=None, out_f32=None, want_bf16=True):
+        if self.kernel is None:
+            self.build(int(x_bf16.shape[-1]))
+        return ops.dense_bf16(x_bf16, self.wt_bf16(), self.bias, self.activation, out_bf16=out_bf16, out_f32=out_f32,
+                              want_bf16=want_bf16)
+
     def get_weights(self):
         return [self.kernel.cpu().numpy(), self.bias.cpu().numpy()]
 
@@ -131,6 +145,22 @@ class Sequential:
         for i, layer in enumerate(self.layers):
             x = layer(x, out=out if i == n - 1 else None)
         return x
+
+    def call_bf16(self, x_bf16: torch.Tensor, out_f32: Optional[torch.Tensor] = None,
+                  out_bf16: Optional[torch.Tensor] = None, want_bf16_out: bool = False):
+        """tcgen05 chain: bf16 activations between layers; the last layer writes fp32 (and optionally bf16)."""
+        n = len(self.layers)
+        y32 = None
+        for i, layer in enumerate(self.layers):
+            last = i == n - 1
+            if last:
+                if out_f32 is None:
+                    out_f32 = torch.empty((x_bf16.shape[0], layer.units), dtype=torch.float32, device=x_bf16.device)
+                x_bf16, y32 = layer.call_bf16(x_bf16, out_bf16=out_bf16, out_f32=out_f32,
+                                              want_bf16=want_bf16_out or out_bf16 is not None)
+            else:
+                x_bf16, _ = layer.call_bf16(x_bf16)
+        return y32, x_bf16
 
 
 class DeepCrossNetwork:
@@ -196,7 +226,10 @@ class MultiTowerModel:
     """Two-tower encoder (src/models.py:59-102)."""
 
     def __init__(self, config: ModelConfig, user_vocab: List[str], item_vocab: List[str],
-                 feature_specs: Dict[str, Any] = None, device=None, **kwargs):
+                 feature_specs: Dict[str, Any] = None, device=None, precision: str = "fp32", **kwargs):
+        if precision not in ("fp32", "bf16"):
+            raise ValueError("precision must be 'fp32' (exact FFMA path) or 'bf16' (tcgen05 path)")
+        self.precision = precision
         self.config = config
         self.user_vocab = user_vocab
         self.item_vocab = item_vocab
@@ -218,11 +251,21 @@ class MultiTowerModel:
                 layer.build(fan_in, seed=s + i)
                 fan_in = layer.units
 
+    def _bf16_ok(self, n: int) -> bool:
+        # the tensor path is for ranking-size batches; tiny batches (the /recommend path) stay on the exact path
+        return self.precision == "bf16" and n >= 128
+
     def encode_user(self, ids, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        return self.user_tower(self.user_embedding(self.user_lookup(ids)), out=out)        # src/models.py:85
+        rows = self.user_lookup(ids)
+        if self._bf16_ok(int(rows.shape[0])):
+            return self.user_tower.call_bf16(ops.gather_bf16(self.user_embedding.embeddings, rows), out_f32=out)[0]
+        return self.user_tower(self.user_embedding(rows), out=out)                          # src/models.py:85
 
     def encode_item(self, ids, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        return self.item_tower(self.item_embedding(self.item_lookup(ids)), out=out)        # src/models.py:89
+        rows = self.item_lookup(ids)
+        if self._bf16_ok(int(rows.shape[0])):
+            return self.item_tower.call_bf16(ops.gather_bf16(self.item_embedding.embeddings, rows), out_f32=out)[0]
+        return self.item_tower(self.item_embedding(rows), out=out)                          # src/models.py:89
 
     def __call__(self, features: Dict[str, Any], training=None) -> Dict[str, Optional[torch.Tensor]]:
         user_emb = None
@@ -244,15 +287,64 @@ class MultiTowerModel:
         return cls(**config)
 
 
+class _FusedRanker:
+    """rs_ranker handle: the whole bf16-mode ranking forward behind ONE C call per batch (chain_tc.cu)."""
+
+    def __init__(self, model: "MultiTaskModel"):
+        import ctypes
+        from . import _lib
+        enc, dcn = model.encoder, model.dcn
+        self._lib = _lib.load()
+        self._tables = (enc.user_embedding.embeddings, enc.item_embedding.embeddings)   # borrowed by the handle
+        tw = [l.wt_bf16() for t in (enc.user_tower, enc.item_tower) for l in t.layers]
+        tb = [l.bias for t in (enc.user_tower, enc.item_tower) for l in t.layers]
+        dw = [l.wt_bf16() for l in dcn.deep_nets]
+        db = [l.bias for l in dcn.deep_nets]
+        hw, hb = model._heads_packed()
+        keep = []
+
+        def arr(objs):
+            bs = [_lib.dl(o) for o in objs]
+            keep.append(bs)
+            return (_lib._DLP * len(bs))(*[_lib.ptr(b) for b in bs])
+
+        singles = [_lib.dl(t) for t in (self._tables[0], self._tables[1], dcn._cross_w, dcn._cross_b, hw, hb)]
+        self._h = ctypes.c_void_p()
+        _lib.check(self._lib.rs_ranker_create(singles[0].ptr, singles[1].ptr, arr(tw), arr(tb), arr(dw), arr(db),
+                                              singles[2].ptr, singles[3].ptr, singles[4].ptr, singles[5].ptr,
+                                              ctypes.byref(self._h)))
+
+    def forward(self, rows_u: torch.Tensor, rows_i: torch.Tensor):
+        from . import _lib
+        B = int(rows_u.shape[0])
+        dev = rows_u.device
+        combined = torch.empty((B, 256), dtype=torch.float32, device=dev)
+        logits = torch.empty((2, B, 1), dtype=torch.float32, device=dev)
+        rating, ctr = logits[0], logits[1]
+        a, b, c, d, e = _lib.dl(rows_u), _lib.dl(rows_i), _lib.dl(combined), _lib.dl(rating), _lib.dl(ctr)
+        _lib.check(self._lib.rs_ranker_forward(self._h, a.ptr, b.ptr, c.ptr, d.ptr, e.ptr, _lib.stream_ptr()))
+        return combined, rating, ctr
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            try:
+                self._lib.rs_ranker_free(h)
+            except Exception:
+                pass
+
+
 class MultiTaskModel:
     """Ranking forward of the multi-task model (src/models.py:106-131)."""
 
     def __init__(self, config: ModelConfig, user_vocab: List[str], item_vocab: List[str],
-                 feature_specs: Dict[str, Any] = None, class_weights: Dict[int, float] = None, device=None, **kwargs):
+                 feature_specs: Dict[str, Any] = None, class_weights: Dict[int, float] = None, device=None,
+                 precision: str = "fp32", **kwargs):
         self.config = config
         dev = _dev(device)
         self.device = dev
-        self.encoder = MultiTowerModel(config, user_vocab, item_vocab, feature_specs, device=dev)
+        self.precision = precision
+        self.encoder = MultiTowerModel(config, user_vocab, item_vocab, feature_specs, device=dev, precision=precision)
         self.class_weights = class_weights
         self.dcn = DeepCrossNetwork(config.cross_layers, config.dnn_dims, config.dropout_rate, config.l2_reg, device=dev)
         self.rating_head = Dense(1, name="rating_pred", device=dev)
@@ -279,6 +371,8 @@ class MultiTaskModel:
         rows_u = enc.user_lookup(features["user_id"])
         rows_i = enc.item_lookup(features["movie_id"])
         B = int(rows_u.shape[0])
+        if self.precision == "bf16" and B >= 128:
+            return self._call_bf16(rows_u, rows_i)
         # the towers write straight into the two halves of the DCN input: the concat (:128) is free
         combined = torch.empty((B, 2 * E), dtype=torch.float32, device=self.device)
         user_emb = enc.user_tower(enc.user_embedding(rows_u), out=combined[:, :E])         # :127 / :85
@@ -287,6 +381,48 @@ class MultiTaskModel:
         hw, hb = self._heads_packed()
         rating, ctr = ops.heads(dcn_out, hw, hb)                                           # :131
         return {"user_embedding": user_emb, "item_embedding": item_emb,
+                "rating_prediction": rating, "ctr_prediction": ctr}
+
+    def _call_bf16(self, rows_u: torch.Tensor, rows_i: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """Ranking forward with every Dense on tcgen05 (bf16 operands, fp32 accumulation).  The tower outputs are
+        produced in fp32 (model outputs, DCN cross input) and in bf16 (deep-net input); cross and heads stay fp32."""
+        enc, E, dev = self.encoder, self.config.embedding_dim, self.device
+        B = int(rows_u.shape[0])
+        D = 2 * E
+        combined = torch.empty((B, D), dtype=torch.float32, device=dev)
+        combined_bf16 = torch.empty((B, D), dtype=torch.bfloat16, device=dev)
+        dcn = self.dcn
+        if not dcn.built:
+            dcn.build(combined.shape)
+        dcn_out = torch.empty((B, D + dcn.deep_layers[-1]), dtype=torch.float32, device=dev)
+        cfg = self.config
+        fused = (E == 128 and list(cfg.user_tower_dims) == [256, 128, 64] and list(cfg.item_tower_dims) == [256, 128, 64]
+                 and list(dcn.deep_layers) == [256, 128] and int(rows_i.shape[0]) == B)
+        if fused and int(dcn._cross_w.shape[1]) == 256:
+            if getattr(self, "_ranker", None) is None:
+                self._ranker = _FusedRanker(self)
+            combined, rating, ctr = self._ranker.forward(rows_u.contiguous(), rows_i.contiguous())
+            return {"user_embedding": combined[:, :E], "item_embedding": combined[:, E:],
+                    "rating_prediction": rating, "ctr_prediction": ctr}
+        if fused:
+            # both towers in ONE kernel (gather + 4 layers each, activations in TMEM), then the deep net in one kernel
+            towers = [[(l.wt_bf16(), l.bias) for l in t.layers] for t in (enc.user_tower, enc.item_tower)]
+            ops.chain_forward_bf16(towers, ["relu", "relu", "relu", None],
+                                   tables=[enc.user_embedding.embeddings, enc.item_embedding.embeddings],
+                                   ids=[rows_u, rows_i], y_f32=[combined[:, :E], combined[:, E:]],
+                                   y_bf16=[combined_bf16[:, :E], combined_bf16[:, E:]])
+            ops.chain_forward_bf16([[(l.wt_bf16(), l.bias) for l in dcn.deep_nets]], ["relu", "relu"], x=[combined_bf16],
+                                   y_f32=[dcn_out[:, D:]])
+        else:
+            enc.user_tower.call_bf16(ops.gather_bf16(enc.user_embedding.embeddings, rows_u), out_f32=combined[:, :E],
+                                     out_bf16=combined_bf16[:, :E])
+            enc.item_tower.call_bf16(ops.gather_bf16(enc.item_embedding.embeddings, rows_i), out_f32=combined[:, E:],
+                                     out_bf16=combined_bf16[:, E:])
+            Sequential(dcn.deep_nets).call_bf16(combined_bf16, out_f32=dcn_out[:, D:])
+        ops.dcn_cross(combined, dcn._cross_w, dcn._cross_b, out=dcn_out[:, :D])
+        hw, hb = self._heads_packed()
+        rating, ctr = ops.heads(dcn_out, hw, hb)
+        return {"user_embedding": combined[:, :E], "item_embedding": combined[:, E:],
                 "rating_prediction": rating, "ctr_prediction": ctr}
 
     def compute_loss(self, data, training=False):
@@ -323,3 +459,4 @@ def load_weights(model, weights: Dict) -> None:
         model.rating_head.set_weights(list(weights["rating_head"]))
         model.ctr_head.set_weights(list(weights["ctr_head"]))
         model._head_cache = None
+        model._ranker = None          # the fused handle copies weights: rebuild it lazily

@@ -5,6 +5,7 @@ launches hand-written sm_100a kernels from librecsys_b200.so on torch's current 
 any failure -- there is no eager/PyTorch fallback.
 """
 
+import ctypes
 from typing import Optional, Sequence
 
 import torch
@@ -45,6 +46,49 @@ def dense(x: torch.Tensor, kernel: torch.Tensor, bias: Optional[torch.Tensor], a
     xb, kb, bb, ob = _lib.dl(x), _lib.dl(kernel), _lib.dl(bias), _lib.dl(out)
     _lib.check(_lib.load().rs_dense_forward(xb.ptr, kb.ptr, _lib.ptr(bb), _lib.act_code(activation), ob.ptr,
                                             _lib.stream_ptr()))
+    return out
+
+
+def dense_bf16(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor], activation=None,
+               out_bf16: Optional[torch.Tensor] = None, out_f32: Optional[torch.Tensor] = None, want_bf16: bool = True):
+    """K2 on tcgen05: x bf16 [B, in], wt bf16 [out, in] (Keras kernel transposed) -> (y_bf16 or None, y_f32 or None)."""
+    _require_cuda(x, wt, bias, out_bf16, out_f32)
+    if out_bf16 is None and want_bf16:
+        out_bf16 = torch.empty((x.shape[0], wt.shape[0]), dtype=torch.bfloat16, device=x.device)
+    xb, wb, bb, ob, of = _lib.dl(x), _lib.dl(wt), _lib.dl(bias), _lib.dl(out_bf16), _lib.dl(out_f32)
+    _lib.check(_lib.load().rs_dense_forward_bf16(xb.ptr, wb.ptr, _lib.ptr(bb), _lib.act_code(activation), _lib.ptr(ob),
+                                                 _lib.ptr(of), _lib.stream_ptr()))
+    return out_bf16, out_f32
+
+
+def chain_forward_bf16(layer_sets, acts, tables=None, ids=None, x=None, y_f32=None, y_bf16=None):
+    """Fused Dense chain(s) on tcgen05 (chain_tc.cu).  layer_sets: one list per problem of (wt_bf16 [out,in], bias or
+    None); acts: activation names per layer; tower chain: tables/ids per problem; deep chain: x per problem;
+    outputs per problem (None entries allowed, at least one of y_f32[p] / y_bf16[p])."""
+    n_prob, n_layers = len(layer_sets), len(layer_sets[0])
+    keep = []
+
+    def arr(objs):
+        if objs is None:
+            return None
+        bs = [_lib.dl(o) for o in objs]
+        keep.append(bs)
+        return (_lib._DLP * len(bs))(*[_lib.ptr(b) for b in bs])
+
+    wts = arr([w for ls in layer_sets for (w, _) in ls])
+    biases = arr([b for ls in layer_sets for (_, b) in ls])
+    act_arr = (ctypes.c_int * n_layers)(*[_lib.act_code(a) for a in acts])
+    _lib.check(_lib.load().rs_chain_forward_bf16(n_prob, n_layers, wts, biases, act_arr, arr(tables), arr(ids), arr(x),
+                                                 arr(y_f32), arr(y_bf16), _lib.stream_ptr()))
+
+
+def gather_bf16(table: torch.Tensor, ids: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """K1 for the tensor path: fp32 embedding rows -> bf16 activations [B, E]."""
+    _require_cuda(table, ids, out)
+    if out is None:
+        out = torch.empty((ids.shape[0], table.shape[1]), dtype=torch.bfloat16, device=table.device)
+    tb, ib, ob = _lib.dl(table), _lib.dl(ids), _lib.dl(out)
+    _lib.check(_lib.load().rs_gather_bf16(tb.ptr, ib.ptr, ob.ptr, _lib.stream_ptr()))
     return out
 
 

@@ -1,0 +1,88 @@
+"""GPU tests of the bf16 tensor-core ranking path (dense_tc.cu: tcgen05 Dense layers, bf16 activations).
+
+Tolerances (north_star: "a separately stated tolerance for bf16"):
+  * one layer, fp32 output: |y - y_model| <= 1e-4 * max|y_model|, where y_model is the fp64 result of the
+    SAME bf16-rounded operands (so only the fp32 accumulation order differs) -- validates the tcgen05 tiles;
+  * one layer, bf16 output: additionally one bf16 rounding (2^-8 relative to each value's magnitude);
+  * full MultiTaskModel forward in bf16 mode vs the fp64 oracle on fp32 weights: <= 1e-2 * max|ref| per tensor
+    (six chained layers with bf16 operands; measured 3.4e-3 .. 3.8e-3, printed by the test).
+"""
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def to_bf16(x):
+    u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    r = ((u >> 16) & 1) + 0x7FFF
+    return ((u + r) & 0xFFFF0000).astype(np.uint32).view(np.float32)
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.parametrize("K,N", [(128, 256), (256, 128), (128, 64), (64, 128), (256, 256), (128, 128)])
+@pytest.mark.parametrize("B,act", [(128, "relu"), (1000, None), (4099, "relu")])
+def test_dense_bf16_matches_bf16_model(rs, K, N, B, act):
+    rng = np.random.default_rng(K + N + B)
+    x = rng.standard_normal((B, K)).astype(np.float32)
+    w = rs.synth.glorot_uniform(rng, K, N)
+    b = rng.normal(0, 0.1, N).astype(np.float32)
+    xb = dev(x).to(torch.bfloat16)
+    wt = dev(w).t().contiguous().to(torch.bfloat16)
+    y16, y32 = rs.ops.dense_bf16(xb, wt, dev(b), act, out_f32=torch.empty((B, N), device="cuda"))
+    want = to_bf16(x).astype(np.float64) @ to_bf16(w).astype(np.float64) + b
+    if act == "relu":
+        want = np.maximum(want, 0)
+    scale = np.abs(want).max()
+    got32 = y32.cpu().numpy().astype(np.float64)
+    assert np.abs(got32 - want).max() <= 1e-4 * scale
+    got16 = y16.float().cpu().numpy().astype(np.float64)
+    assert np.abs(got16 - want).max() <= 2.0 ** -8 * scale + 1e-4 * scale
+    np.testing.assert_array_equal(y16.float().cpu().numpy(), to_bf16(y32.cpu().numpy()))   # the two outputs agree
+
+
+def test_dense_bf16_strided_outputs_and_gather(rs):
+    rng = np.random.default_rng(1)
+    table = rng.standard_normal((500, 128)).astype(np.float32)
+    ids = rng.integers(0, 500, 777)
+    ids[5] = 9999                                                     # out of range -> zeros
+    g = rs.ops.gather_bf16(dev(table), dev(ids))
+    want = to_bf16(table[np.clip(ids, 0, 499)])
+    want[5] = 0
+    np.testing.assert_array_equal(g.float().cpu().numpy(), want)
+    w = rs.synth.glorot_uniform(rng, 128, 128)
+    wide32 = torch.zeros((777, 256), device="cuda")
+    wide16 = torch.zeros((777, 256), device="cuda", dtype=torch.bfloat16)
+    rs.ops.dense_bf16(g, dev(w).t().contiguous().to(torch.bfloat16), None, None, out_bf16=wide16[:, 128:], out_f32=wide32[:, 128:])
+    ref = want.astype(np.float64) @ to_bf16(w).astype(np.float64)
+    assert np.abs(wide32[:, 128:].cpu().numpy() - ref).max() <= 1e-4 * np.abs(ref).max()
+    assert float(wide32[:, :128].abs().max()) == 0 and float(wide16[:, :128].float().abs().max()) == 0
+
+
+def test_multitask_forward_bf16_mode(rs):
+    from oracle.models import MultiTaskModel as OMT
+    cfg = rs.ModelConfig()
+    w = rs.synth.make_weights(cfg, 6040, 3706, seed=10)
+    uv, iv = rs.synth.make_vocab(6040), rs.synth.make_vocab(3706)
+    m = rs.MultiTaskModel(cfg, uv, iv, {}, precision="bf16")
+    rs.load_weights(m, w)
+    rng = np.random.default_rng(100)
+    ur, ir = rs.synth.make_ids(rng, 6040, 4096), rs.synth.make_ids(rng, 3706, 4096)
+    out = m({"user_id": dev(ur), "movie_id": dev(ir)})
+    want = OMT(w, uv, iv, np.float64).rank_rows(ur, ir)
+    for k_ in want:
+        got = out[k_].cpu().numpy().astype(np.float64)
+        rel = np.abs(got - want[k_]).max() / np.abs(want[k_]).max()
+        print(f"bf16 mode {k_}: max err / scale = {rel:.2e}")
+        assert rel <= 1e-2, k_
+    # small batches (the /recommend path) stay on the exact fp32 kernels even in bf16 mode
+    m32 = rs.MultiTaskModel(cfg, uv, iv, {})
+    rs.load_weights(m32, w)
+    a = m.encoder({"user_id": [uv[3]]})["user_embedding"]
+    b = m32.encoder({"user_id": [uv[3]]})["user_embedding"]
+    assert torch.equal(a, b)

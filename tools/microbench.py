@@ -40,13 +40,13 @@ def main():
     N, d = args.n_items, 128
     index = rs.IndexFlatIP(d)
     blk = 1 << 20
-    for b0 in range(0, N, blk):
+    for b0 in range(0, N if args.shapes else 0, blk):
         g = torch.Generator(device=dev)
         g.manual_seed(3000 + b0 // blk)
         x = torch.randn((min(blk, N - b0), d), generator=g, device=dev)
         rs.normalize_L2(x)
         index.add(x)
-    for shape in args.shapes.split(","):
+    for shape in (args.shapes.split(",") if args.shapes else []):
         nq, k = map(int, shape.split(":"))
         q = torch.randn((nq, d), device=dev)
         rs.normalize_L2(q)
@@ -67,14 +67,20 @@ def main():
     if args.ranking:
         cfg = rs.ModelConfig()
         w = rs.synth.make_weights(cfg, 6040, 3706, seed=10)
-        model = rs.MultiTaskModel(cfg, rs.synth.make_vocab(6040), rs.synth.make_vocab(3706), {})
-        rs.load_weights(model, w)
-        for B in (4096, 65536):
-            ur = torch.randint(0, 6041, (B,), device=dev)
-            ir = torch.randint(0, 3707, (B,), device=dev)
-            ms = timeit(lambda: model({"user_id": ur, "movie_id": ir}), 10)
-            print(json.dumps({"ranking_batch": B, "ms": round(ms, 4), "samples_per_s": round(B / ms * 1e3),
-                              "gemm_TFLOPs": round(524288.0 * B / ms / 1e9, 2)}), flush=True)
+        for precision in ("fp32", "bf16"):
+            model = rs.MultiTaskModel(cfg, rs.synth.make_vocab(6040), rs.synth.make_vocab(3706), {}, precision=precision)
+            rs.load_weights(model, w)
+            for B in (4096, 65536, 262144):
+                ur = torch.randint(0, 6041, (B,), device=dev)
+                ir = torch.randint(0, 3707, (B,), device=dev)
+                rs._lib.prof_enable(True)
+                ms = timeit(lambda: model({"user_id": ur, "movie_id": ir}), 10)
+                tc_ms, tc_n = rs._lib.prof_read(4)
+                rs._lib.prof_enable(False)
+                print(json.dumps({"ranking_batch": B, "precision": precision, "ms": round(ms, 4),
+                                  "samples_per_s": round(B / ms * 1e3), "gemm_TFLOPs": round(524288.0 * B / ms / 1e9, 2),
+                                  "dense_tc_ms_per_call": round(tc_ms / 13, 4), "dense_tc_launches_per_call": tc_n / 13}),
+                      flush=True)
 
 
 if __name__ == "__main__":
