@@ -75,6 +75,19 @@ int rs_gather_concat(int n_tables, const DLTensor* const* tables, const DLTensor
                      DLTensor* out, void* stream);
 
 /*
+ * K7b. Sharded embedding tables (BASELINE config 4; new in this build): rows sharded `row mod n_shards`, batch
+ * data-parallel.  The plan kernels bucket a rank's ids by owner; the exchanges themselves are NCCL all-to-alls
+ * issued by the host layer (sharded.py), the owner-side gather and the final un-permute are rs_gather_concat.
+ *   rs_a2a_count:   counts[g] = #ids owned by shard g                      (ids int64 [B], counts int64 [G])
+ *   rs_a2a_scatter: send[base[g] + slot] = id div G, perm[i] = that position (base/cursor int64 [G], send/perm int64 [B])
+ *   rs_hash_table_fill: synthetic, host-replayable table rows row0, row0+row_step, ... into out f32 [n, dim]
+ */
+int rs_a2a_count(const DLTensor* ids, int n_shards, DLTensor* counts, void* stream);
+int rs_a2a_scatter(const DLTensor* ids, int n_shards, const DLTensor* base, DLTensor* cursor, DLTensor* send,
+                   DLTensor* perm, void* stream);
+int rs_hash_table_fill(DLTensor* out, int64_t row0, int64_t row_step, uint64_t seed, void* stream);
+
+/*
  * K2. One Keras Dense layer: y = act(x @ kernel + bias), kernel stored (in, out).
  * Replaces keras.layers.Dense inside user_tower / item_tower / deep_nets
  * (src/models.py:26-29,76-77).  x: f32 [B, in], y: f32 [B, out]; both may be column
@@ -118,6 +131,9 @@ int rs_ranker_create(const DLTensor* user_table, const DLTensor* item_table, con
 int rs_ranker_free(rs_ranker_t* h);
 int rs_ranker_forward(rs_ranker_t* h, const DLTensor* user_rows, const DLTensor* item_rows, DLTensor* combined,
                       DLTensor* rating, DLTensor* ctr, void* stream);
+/* the same forward from already-looked-up embedding rows f32 [B,128] (what a sharded-table lookup returns) */
+int rs_ranker_forward_rows(rs_ranker_t* h, const DLTensor* user_emb, const DLTensor* item_emb, DLTensor* combined,
+                           DLTensor* rating, DLTensor* ctr, void* stream);
 /* K1 (bf16 tensor mode). Embedding rows gathered from the fp32 table straight into bf16 activations. */
 int rs_gather_bf16(const DLTensor* table, const DLTensor* ids, DLTensor* out, void* stream);
 

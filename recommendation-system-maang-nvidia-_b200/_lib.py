@@ -74,6 +74,9 @@ def load():
     sigs = {
         "rs_device_sm_count": [ctypes.POINTER(i32)],
         "rs_gather_concat": [i32, ctypes.POINTER(_DLP), ctypes.POINTER(_DLP), _DLP, vp],
+        "rs_a2a_count": [_DLP, i32, _DLP, vp],
+        "rs_a2a_scatter": [_DLP, i32, _DLP, _DLP, _DLP, _DLP, vp],
+        "rs_hash_table_fill": [_DLP, i64, i64, ctypes.c_uint64, vp],
         "rs_dense_forward": [_DLP, _DLP, _DLP, i32, _DLP, vp],
         "rs_dense_forward_bf16": [_DLP, _DLP, _DLP, i32, _DLP, _DLP, vp],
         "rs_gather_bf16": [_DLP, _DLP, _DLP, vp],
@@ -81,6 +84,7 @@ def load():
                              ctypes.POINTER(_DLP), _DLP, _DLP, _DLP, _DLP, ctypes.POINTER(vp)],
         "rs_ranker_free": [vp],
         "rs_ranker_forward": [vp, _DLP, _DLP, _DLP, _DLP, _DLP, vp],
+        "rs_ranker_forward_rows": [vp, _DLP, _DLP, _DLP, _DLP, _DLP, vp],
         "rs_chain_forward_bf16": [i32, i32, ctypes.POINTER(_DLP), ctypes.POINTER(_DLP), ctypes.POINTER(i32),
                                   ctypes.POINTER(_DLP), ctypes.POINTER(_DLP), ctypes.POINTER(_DLP), ctypes.POINTER(_DLP),
                                   ctypes.POINTER(_DLP), vp],
@@ -109,8 +113,8 @@ def load():
     return lib
 
 
-EXPORTED = ["rs_version", "rs_last_error", "rs_launch_count", "rs_device_sm_count", "rs_gather_concat",
-            "rs_dense_forward", "rs_dense_forward_bf16", "rs_gather_bf16", "rs_chain_forward_bf16", "rs_ranker_create", "rs_ranker_free", "rs_ranker_forward", "rs_dcn_cross_forward", "rs_heads_forward", "rs_normalize_l2", "rs_index_create",
+EXPORTED = ["rs_version", "rs_last_error", "rs_launch_count", "rs_device_sm_count", "rs_gather_concat", "rs_a2a_count", "rs_a2a_scatter", "rs_hash_table_fill",
+            "rs_dense_forward", "rs_dense_forward_bf16", "rs_gather_bf16", "rs_chain_forward_bf16", "rs_ranker_create", "rs_ranker_free", "rs_ranker_forward", "rs_ranker_forward_rows", "rs_dcn_cross_forward", "rs_heads_forward", "rs_normalize_l2", "rs_index_create",
             "rs_index_free", "rs_index_add", "rs_index_ntotal", "rs_index_dim", "rs_index_reconstruct", "rs_index_search",
             "rs_index_fallbacks", "rs_debug_tensor_scores",
             "rs_matvec", "rs_topk_merge", "rs_prof_enable", "rs_prof_read"]

@@ -179,8 +179,9 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
 #pragma unroll
         for (int e = 0; e < 16; ++e) r[e] = 0u;
         if (row < pr.rows) {
-          const int64_t id = pr.ids64 ? static_cast<const int64_t*>(pr.ids)[row]
-                                      : static_cast<int64_t>(static_cast<const int32_t*>(pr.ids)[row]);
+          const int64_t id = !pr.ids ? row   // no ids: the "table" already holds this batch's rows in order
+                             : pr.ids64 ? static_cast<const int64_t*>(pr.ids)[row]
+                                        : static_cast<int64_t>(static_cast<const int32_t*>(pr.ids)[row]);
           if (id >= 0 && id < pr.table_rows) {
             const float4* src = reinterpret_cast<const float4*>(pr.table + id * pr.table_ld + slice * 32);
 #pragma unroll
@@ -587,12 +588,14 @@ extern "C" int rs_ranker_free(rs_ranker* h) {
 
 // user_rows / item_rows: int32|int64 [B]; combined: f32 [B, 256] (user embedding | item embedding, the DCN input);
 // rating, ctr: f32 [B, 1]
-extern "C" int rs_ranker_forward(rs_ranker* h, const DLTensor* user_rows, const DLTensor* item_rows, DLTensor* combined,
-                                 DLTensor* rating, DLTensor* ctr, void* stream) {
+static int ranker_forward_impl(rs_ranker* h, const DLTensor* user_rows, const DLTensor* item_rows,
+                               const DLTensor* user_emb, const DLTensor* item_emb, DLTensor* combined, DLTensor* rating,
+                               DLTensor* ctr, void* stream) {
   return rs::guard([&] {
     using namespace rs;
     RS_CHECK(h != nullptr, "ranker is NULL");
     const DLTensor* ids[2] = {user_rows, item_rows};
+    const DLTensor* embs[2] = {user_emb, item_emb};
     require(combined, "combined", 2, kDLFloat, 32);
     require(rating, "rating", 2, kDLFloat, 32);
     require(ctr, "ctr", 2, kDLFloat, 32);
@@ -614,16 +617,27 @@ extern "C" int rs_ranker_forward(rs_ranker* h, const DLTensor* user_rows, const 
       p.act[3] = RS_ACT_NONE;
       for (int s = 0; s < 2; ++s) {
         ChainProblem& pr = p.prob[s];
-        RS_CHECK(ids[s] && ids[s]->ndim == 1 && ids[s]->shape[0] == B && on_device(ids[s]) &&
-                     (is_dtype(ids[s], kDLInt, 32) || is_dtype(ids[s], kDLInt, 64)) && (B <= 1 || stride_of(ids[s], 0) == 1),
-                 "row ids must be contiguous CUDA int32/int64 [B] tensors");
         pr.rows = B;
         for (int l = 0; l < 4; ++l) pr.bias[l] = h->f32 + h->off_b[s][l];
-        pr.table = h->table[s];
-        pr.table_ld = h->table_ld[s];
-        pr.table_rows = h->table_rows[s];
-        pr.ids = data_ptr<void>(ids[s]);
-        pr.ids64 = is_dtype(ids[s], kDLInt, 64) ? 1 : 0;
+        if (embs[s]) {   // already-looked-up embedding rows (sharded tables): identity gather
+          require(embs[s], "embedding rows", 2, kDLFloat, 32);
+          RS_CHECK(on_device(embs[s]) && embs[s]->shape[0] == B && embs[s]->shape[1] == 128, "embedding rows must be CUDA [B, 128]");
+          pr.table = data_ptr<float>(embs[s]);
+          pr.table_ld = row_stride_2d(embs[s], "embedding rows");
+          pr.table_rows = B;
+          RS_CHECK(pr.table_ld % 4 == 0, "embedding row stride must be a multiple of 4");
+          require_aligned16(pr.table, "embedding rows");
+          pr.ids = nullptr;
+        } else {
+          RS_CHECK(ids[s] && ids[s]->ndim == 1 && ids[s]->shape[0] == B && on_device(ids[s]) &&
+                       (is_dtype(ids[s], kDLInt, 32) || is_dtype(ids[s], kDLInt, 64)) && (B <= 1 || stride_of(ids[s], 0) == 1),
+                   "row ids must be contiguous CUDA int32/int64 [B] tensors");
+          pr.table = h->table[s];
+          pr.table_ld = h->table_ld[s];
+          pr.table_rows = h->table_rows[s];
+          pr.ids = data_ptr<void>(ids[s]);
+          pr.ids64 = is_dtype(ids[s], kDLInt, 64) ? 1 : 0;
+        }
         pr.y_f32 = data_ptr<float>(combined) + s * 128;
         pr.ld_f32 = 256;
         pr.y_bf16 = x_bf16 + s * 128;
@@ -654,4 +668,15 @@ extern "C" int rs_ranker_forward(rs_ranker* h, const DLTensor* user_rows, const 
     cudaFreeAsync(x_bf16, st);
     cudaFreeAsync(deep_out, st);
   });
+}
+
+extern "C" int rs_ranker_forward(rs_ranker* h, const DLTensor* user_rows, const DLTensor* item_rows, DLTensor* combined,
+                                 DLTensor* rating, DLTensor* ctr, void* stream) {
+  return ranker_forward_impl(h, user_rows, item_rows, nullptr, nullptr, combined, rating, ctr, stream);
+}
+
+// same forward from already-looked-up embedding rows f32 [B,128] (the output of a sharded-table lookup)
+extern "C" int rs_ranker_forward_rows(rs_ranker* h, const DLTensor* user_emb, const DLTensor* item_emb, DLTensor* combined,
+                                      DLTensor* rating, DLTensor* ctr, void* stream) {
+  return ranker_forward_impl(h, nullptr, nullptr, user_emb, item_emb, combined, rating, ctr, stream);
 }

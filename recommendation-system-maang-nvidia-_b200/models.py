@@ -314,7 +314,8 @@ class _FusedRanker:
                                               singles[2].ptr, singles[3].ptr, singles[4].ptr, singles[5].ptr,
                                               ctypes.byref(self._h)))
 
-    def forward(self, rows_u: torch.Tensor, rows_i: torch.Tensor):
+    def forward(self, rows_u: torch.Tensor, rows_i: torch.Tensor, from_embedding_rows: bool = False):
+        """rows_*: int row numbers [B] -- or, with from_embedding_rows, the looked-up f32 [B,128] rows themselves."""
         from . import _lib
         B = int(rows_u.shape[0])
         dev = rows_u.device
@@ -322,7 +323,8 @@ class _FusedRanker:
         logits = torch.empty((2, B, 1), dtype=torch.float32, device=dev)
         rating, ctr = logits[0], logits[1]
         a, b, c, d, e = _lib.dl(rows_u), _lib.dl(rows_i), _lib.dl(combined), _lib.dl(rating), _lib.dl(ctr)
-        _lib.check(self._lib.rs_ranker_forward(self._h, a.ptr, b.ptr, c.ptr, d.ptr, e.ptr, _lib.stream_ptr()))
+        fn = self._lib.rs_ranker_forward_rows if from_embedding_rows else self._lib.rs_ranker_forward
+        _lib.check(fn(self._h, a.ptr, b.ptr, c.ptr, d.ptr, e.ptr, _lib.stream_ptr()))
         return combined, rating, ctr
 
     def __del__(self):
@@ -422,6 +424,16 @@ class MultiTaskModel:
         ops.dcn_cross(combined, dcn._cross_w, dcn._cross_b, out=dcn_out[:, :D])
         hw, hb = self._heads_packed()
         rating, ctr = ops.heads(dcn_out, hw, hb)
+        return {"user_embedding": combined[:, :E], "item_embedding": combined[:, E:],
+                "rating_prediction": rating, "ctr_prediction": ctr}
+
+    def rank_from_embedding_rows(self, user_rows: torch.Tensor, item_rows: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """The same forward, fed with already-looked-up embedding rows f32 [B, E] (the output of
+        sharded.ShardedEmbedding.lookup when the tables are partitioned over GPUs; bf16 tensor mode only)."""
+        if getattr(self, "_ranker", None) is None:
+            self._ranker = _FusedRanker(self)
+        E = self.config.embedding_dim
+        combined, rating, ctr = self._ranker.forward(user_rows, item_rows, from_embedding_rows=True)
         return {"user_embedding": combined[:, :E], "item_embedding": combined[:, E:],
                 "rating_prediction": rating, "ctr_prediction": ctr}
 

@@ -72,3 +72,78 @@ class ShardedIndexFlatIP:
 def gather_bytes(world: int, nq: int, k: int) -> int:
     """Bytes each rank receives in the exchange step (f32 score + i64 row per hit)."""
     return world * nq * k * (4 + 8)
+
+
+class ShardedEmbedding:
+    """Embedding table sharded over the ranks of a process group (BASELINE config 4).
+
+    Global row r lives on rank r % G at local row r // G (even load under skew); the batch is data-parallel.
+    lookup(ids) on every rank:
+        plan      K7b kernels: per-owner histogram, then scatter of (r // G) into per-owner send segments + the
+                  permutation that restores the batch order
+        exchange  all-to-all #1 (NCCL over NVLink): local row numbers to their owners
+        gather    K1 kernel on the owner's shard
+        exchange  all-to-all #2: the 512-byte rows back to the requesters
+        restore   K1 kernel with the permutation as ids
+    Bytes over NVLink per looked-up row: 8 (id) out, 4*E (row) back, for the (G-1)/G share that is remote.
+    `plan` / `gather` are injectable so the host logic can run on CPU over gloo with numpy stand-ins (tests).
+    """
+
+    def __init__(self, n_rows_total: int, dim: int, local_table=None, group: Optional[dist.ProcessGroup] = None,
+                 plan: Optional[Callable] = None, gather: Optional[Callable] = None):
+        self.n_rows_total, self.dim, self.group = int(n_rows_total), int(dim), group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.n_local = (self.n_rows_total - self.rank + self.world - 1) // self.world
+        self.local_table = local_table
+        if plan is None:
+            from . import _lib, ops
+
+            def plan(ids, G):
+                counts = torch.empty((G,), dtype=torch.int64, device=ids.device)
+                a, b = _lib.dl(ids), _lib.dl(counts)
+                _lib.check(_lib.load().rs_a2a_count(a.ptr, G, b.ptr, _lib.stream_ptr()))
+                return counts
+
+            def scatter(ids, G, base):
+                cursor = torch.empty((G,), dtype=torch.int64, device=ids.device)
+                send = torch.empty_like(ids)
+                perm = torch.empty_like(ids)
+                a, b, c, d, e = _lib.dl(ids), _lib.dl(base), _lib.dl(cursor), _lib.dl(send), _lib.dl(perm)
+                _lib.check(_lib.load().rs_a2a_scatter(a.ptr, G, b.ptr, c.ptr, d.ptr, e.ptr, _lib.stream_ptr()))
+                return send, perm
+
+            self._count, self._scatter = plan, scatter
+            self._gather = lambda table, rows: ops.gather_concat([table], [rows])
+        else:
+            self._count, self._scatter = plan
+            self._gather = gather
+
+    @staticmethod
+    def fill_synthetic(n_rows_total: int, dim: int, rank: int, world: int, seed: int, device) -> torch.Tensor:
+        """This rank's shard of the host-replayable synthetic table (synth.hash_table_rows gives the same values)."""
+        from . import _lib
+        n_local = (n_rows_total - rank + world - 1) // world
+        out = torch.empty((n_local, dim), dtype=torch.float32, device=device)
+        b = _lib.dl(out)
+        _lib.check(_lib.load().rs_hash_table_fill(b.ptr, rank, world, seed, _lib.stream_ptr()))
+        return out
+
+    def lookup(self, ids: torch.Tensor) -> torch.Tensor:
+        """ids: int64 [B] global rows (this rank's part of the batch) -> float32 [B, dim], in batch order."""
+        G = self.world
+        if G == 1:
+            return self._gather(self.local_table, ids)
+        counts = self._count(ids, G)
+        recv_counts_t = torch.empty_like(counts)
+        dist.all_to_all_single(recv_counts_t, counts, group=self.group)
+        send_counts = counts.cpu().tolist()
+        recv_counts = recv_counts_t.cpu().tolist()
+        base = torch.tensor([sum(send_counts[:g]) for g in range(G)], dtype=torch.int64).to(ids.device)
+        send, perm = self._scatter(ids, G, base)
+        recv_rows = torch.empty((sum(recv_counts),), dtype=torch.int64, device=ids.device)
+        dist.all_to_all_single(recv_rows, send, output_split_sizes=recv_counts, input_split_sizes=send_counts, group=self.group)
+        found = self._gather(self.local_table, recv_rows)                    # [n_recv, dim] on the owner
+        back = torch.empty((int(ids.shape[0]), self.dim), dtype=torch.float32, device=ids.device)
+        dist.all_to_all_single(back, found, output_split_sizes=send_counts, input_split_sizes=recv_counts, group=self.group)
+        return self._gather(back, perm)

@@ -72,3 +72,27 @@ def make_unit_rows(n: int, d: int, seed: int, block: int = 1 << 20) -> np.ndarra
         x /= np.linalg.norm(x, axis=1, keepdims=True)
         out[b0:b1] = x.astype(np.float32)
     return out
+
+
+def hash_table_rows(rows: np.ndarray, dim: int, seed: int) -> np.ndarray:
+    """Host replay of rs_hash_table_fill: T[r, c] = (u32(mix(seed, r*dim + c)) * 2^-32 - 0.5) * 0.1, bit for bit."""
+    with np.errstate(over="ignore"):
+        g = rows.astype(np.uint64)[:, None] * np.uint64(dim) + np.arange(dim, dtype=np.uint64)[None, :]
+        x = np.uint64(seed) * np.uint64(0x9E3779B97F4A7C15) + g
+        x ^= x >> np.uint64(33)
+        x *= np.uint64(0xFF51AFD7ED558CCD)
+        x ^= x >> np.uint64(33)
+        x *= np.uint64(0xC4CEB9FE1A85EC53)
+        x ^= x >> np.uint64(33)
+    u = (x & np.uint64(0xFFFFFFFF)).astype(np.uint32).astype(np.float32)
+    return ((u * np.float32(2.3283064365386963e-10) - np.float32(0.5)) * np.float32(0.1)).astype(np.float32)
+
+
+def zipf_ids(rng, n_rows: int, batch: int, alpha: float = 1.05, perm_seed: int = 4001) -> np.ndarray:
+    """Bounded-Zipf ranks (exponent alpha) mapped to rows through a fixed random permutation, int64."""
+    ranks = np.arange(1, n_rows + 1, dtype=np.float64)
+    cdf = np.cumsum(ranks ** -alpha)
+    cdf /= cdf[-1]
+    r = np.searchsorted(cdf, rng.random(batch)).astype(np.int64)
+    perm = np.random.default_rng(perm_seed).permutation(n_rows)
+    return perm[np.minimum(r, n_rows - 1)].astype(np.int64)

@@ -75,3 +75,53 @@ def test_shard_bounds_cover_the_catalog():
             assert b[0] == 0 and b[-1] == n and all(x <= y for x, y in zip(b, b[1:]))
             assert max(y - x for x, y in zip(b, b[1:])) - min(y - x for x, y in zip(b, b[1:])) <= 1
     assert gather_bytes(8, 1024, 100) == 8 * 1024 * 100 * 12
+
+
+def _emb_worker(rank, world, port, n_rows, batch):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import recsys_b200 as rs
+        from recsys_b200.sharded import ShardedEmbedding
+
+        dim = 16
+        local_rows = np.arange(rank, n_rows, world)
+        table = torch.from_numpy(rs.synth.hash_table_rows(local_rows, dim, seed=7))
+
+        def count(ids, G):
+            return torch.bincount(ids % G, minlength=G)
+
+        def scatter(ids, G, base):
+            owner = (ids % G).numpy()
+            order = np.argsort(owner, kind="stable")
+            send = torch.from_numpy((ids.numpy() // G)[order])
+            perm = np.empty(len(order), dtype=np.int64)
+            perm[order] = np.arange(len(order))
+            return send, torch.from_numpy(perm)
+
+        emb = ShardedEmbedding(n_rows, dim, local_table=table, plan=(count, scatter), gather=lambda t, r: t[r])
+        assert emb.n_local == len(local_rows)
+        rng = np.random.default_rng(100 + rank)
+        ids = rs.synth.zipf_ids(rng, n_rows, batch)
+        got = emb.lookup(torch.from_numpy(ids)).numpy()
+        np.testing.assert_array_equal(got, rs.synth.hash_table_rows(ids, dim, seed=7))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_embedding_lookup_over_gloo(world):
+    mp.spawn(_emb_worker, args=(world, _free_port(), 1000, 257), nprocs=world, join=True)
+
+
+def test_zipf_ids_and_hash_rows_are_deterministic():
+    import recsys_b200 as rs
+    a = rs.synth.zipf_ids(np.random.default_rng(1), 5000, 4096)
+    b = rs.synth.zipf_ids(np.random.default_rng(1), 5000, 4096)
+    np.testing.assert_array_equal(a, b)
+    assert a.min() >= 0 and a.max() < 5000
+    top = np.bincount(a, minlength=5000).max()
+    assert top > 4096 * 0.02                      # skewed: the hottest row takes a few percent of the batch
+    t = rs.synth.hash_table_rows(np.array([0, 1, 49_999_999]), 128, 3)
+    assert t.shape == (3, 128) and np.abs(t).max() <= 0.05 and t.std() > 0.02
