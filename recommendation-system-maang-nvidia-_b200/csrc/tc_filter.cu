@@ -340,49 +340,76 @@ __global__ void __launch_bounds__(128) prep_queries_kernel(const float* __restri
   if (lane == 0) eps2[row] = 2.0f * C_EPS * (sqrtf(s) * 1.00001f) * __uint_as_float(*max_norm_bits);
 }
 
+// Block-wide radix select: the k-th largest (1-based, k <= n) of the n 32-bit values v(0..n-1).  Four 8-bit passes
+// from the top byte; per pass a shared-memory histogram and a one-warp scan.  12 barriers in total (a bitonic
+// sort of 1024 keys needs 55), which is what matters for these latency-bound per-query kernels.
+template <int NT, class F>
+__device__ __forceinline__ uint32_t block_kth_largest(F v, int n, int k, unsigned* hist /*[256]*/,
+                                                      unsigned* state /*[2]*/, int tid) {
+  uint32_t prefix = 0, mask = 0;
+  unsigned kk = static_cast<unsigned>(k);
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    for (int i = tid; i < 256; i += NT) hist[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += NT) {
+      const uint32_t x = v(i);
+      if ((x & mask) == prefix) atomicAdd(&hist[(x >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (tid < 32) {   // lane L owns bins 255-8L .. 248-8L (descending), prefix-summed over lanes
+      unsigned loc[8], sum = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        loc[j] = hist[255 - (tid * 8 + j)];
+        sum += loc[j];
+      }
+      unsigned incl = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (tid >= o) incl += t;
+      }
+      const unsigned excl = incl - sum;
+      if (excl < kk && kk <= incl) {
+        unsigned run = excl;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (run < kk && kk <= run + loc[j]) {
+            state[0] = 255u - (tid * 8 + j);
+            state[1] = kk - run;
+          }
+          run += loc[j];
+        }
+      }
+    }
+    __syncthreads();
+    prefix |= state[0] << shift;
+    mask |= 0xFFu << shift;
+    kk = state[1];
+  }
+  return prefix;
+}
+
 // tau_q = the `rank`-th largest of the query's sample maxima; also clears the candidate counters
-template <int NV>
 __global__ void __launch_bounds__(256) threshold_kernel(const unsigned* __restrict__ smax, int n_vals, int rank,
                                                         float* __restrict__ thr, int* __restrict__ cand_cnt,
                                                         int* __restrict__ flags) {
-  __shared__ uint64_t keys[NV];
+  __shared__ unsigned vals[1024];
+  __shared__ unsigned hist[256];
+  __shared__ unsigned state[2];
   const int tid = threadIdx.x;
   const int qi = blockIdx.x;
-  for (int i = tid; i < NV; i += 256)
-    keys[i] = i < n_vals ? (static_cast<uint64_t>(smax[(int64_t)qi * n_vals + i]) << 32) | static_cast<uint32_t>(i) : kEmptyKey;
+  for (int i = tid; i < n_vals; i += 256) vals[i] = smax[(int64_t)qi * n_vals + i];
   __syncthreads();
-  block_sort_desc<NV, 256>(keys, tid);
+  const uint32_t kth = block_kth_largest<256>([&](int i) { return vals[i]; }, n_vals, rank, hist, state, tid);
   if (tid == 0) {
-    thr[qi] = key_score(keys[rank - 1]);
+    thr[qi] = ordered_to_f32(kth);
     cand_cnt[qi] = 0;
     flags[qi] = 0;
   }
 }
 
-// bitonic sort, descending, run-time power-of-two length n (<= CAND_CAP); ends with __syncthreads()
-__device__ __forceinline__ void block_sort_desc_rt(uint64_t* a, int n, int tid) {
-  for (int size = 2; size <= n; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int i = tid; i < n / 2; i += SEL_NT) {
-        const int lo = 2 * i - (i & (stride - 1));
-        const int hi = lo + stride;
-        const bool desc = (lo & size) == 0;
-        const uint64_t x = a[lo], y = a[hi];
-        if ((x < y) == desc) {
-          a[lo] = y;
-          a[hi] = x;
-        }
-      }
-      __syncthreads();
-    }
-  }
-}
-
-__device__ __forceinline__ int next_pow2(int v) {
-  int p = 2;
-  while (p < v) p <<= 1;
-  return p;
-}
+constexpr int SEL_MAX_M = 1024;   // most survivors of the margin cut that one query may re-score
 
 // step 4: verify, cut, exact re-score, final order.  One CTA per query.
 __global__ void __launch_bounds__(SEL_NT) select_rescore_kernel(
@@ -391,22 +418,36 @@ __global__ void __launch_bounds__(SEL_NT) select_rescore_kernel(
     float* __restrict__ D, int64_t ldD, int64_t* __restrict__ I, int64_t ldI, int* __restrict__ flags,
     int* __restrict__ n_flagged) {
   __shared__ uint64_t keys[CAND_CAP];
+  __shared__ uint32_t sel[SEL_MAX_M];
   __shared__ __align__(16) float qs[DK];
+  __shared__ unsigned hist[256];
+  __shared__ unsigned state[2];
   __shared__ int s_m;
   const int tid = threadIdx.x;
   const int qi = blockIdx.x;
   const int c_raw = cand_cnt[qi];
   const int c = min(c_raw, cap);
   if (tid < DK) qs[tid] = q[(int64_t)qi * DK + tid];
-  const int n1 = next_pow2(max(c, 2));
-  for (int i = tid; i < n1; i += SEL_NT) keys[i] = i < c ? cand[(int64_t)qi * cap + i] : kEmptyKey;
+  if (tid == 0) s_m = 0;
+  for (int i = tid; i < c; i += SEL_NT) keys[i] = cand[(int64_t)qi * cap + i];
   __syncthreads();
-  block_sort_desc_rt(keys, n1, tid);
   bool ok = c_raw <= cap && c >= k;
   float cutoff = 0.0f;
-  if (ok) {
-    cutoff = key_score(keys[k - 1]) - eps2[qi];
+  if (ok) {   // uniform
+    const uint32_t kth = block_kth_largest<SEL_NT>([&](int i) { return static_cast<uint32_t>(keys[i] >> 32); }, c, k, hist,
+                                                   state, tid);
+    cutoff = ordered_to_f32(kth) - eps2[qi];
     ok = cutoff >= thr[qi];          // the guess was low enough: the list provably holds the whole top-k
+  }
+  if (ok) {
+    // survivors of the margin cut: s_hat >= s_hat_(k) - 2 eps
+    for (int i = tid; i < c; i += SEL_NT)
+      if (key_score(keys[i]) >= cutoff) {
+        const int pos = atomicAdd(&s_m, 1);
+        if (pos < SEL_MAX_M) sel[pos] = key_row(keys[i]);
+      }
+    __syncthreads();
+    ok = s_m <= SEL_MAX_M;
   }
   if (!ok) {
     if (tid == 0) {
@@ -415,19 +456,13 @@ __global__ void __launch_bounds__(SEL_NT) select_rescore_kernel(
     }
     return;
   }
-  // m = length of the prefix with s_hat >= cutoff (list is sorted by s_hat descending)
-  if (tid == 0) s_m = 0;
-  __syncthreads();
-  int local = 0;
-  for (int i = tid; i < c; i += SEL_NT) local += key_score(keys[i]) >= cutoff ? 1 : 0;
-  atomicAdd(&s_m, local);
-  __syncthreads();
   const int m = s_m;
+  // exact re-score with the stated fp32 FMA chain; keys[] is free again and receives the exact keys
   for (int i = tid; i < m; i += SEL_NT) {
-    const uint32_t row = key_row(keys[i]);
+    const uint32_t row = sel[i];
     const float4* xr = reinterpret_cast<const float4*>(xb + (int64_t)row * DK);
     float acc = 0.0f;
-#pragma unroll 8
+#pragma unroll 16
     for (int c4 = 0; c4 < DK / 4; ++c4) {
       const float4 xv = __ldg(xr + c4);
       const float4 qv = *reinterpret_cast<const float4*>(qs + c4 * 4);
@@ -438,14 +473,16 @@ __global__ void __launch_bounds__(SEL_NT) select_rescore_kernel(
     }
     keys[i] = pack_key(acc, row);
   }
-  const int n2 = next_pow2(max(m, 2));
-  for (int i = m + tid; i < n2; i += SEL_NT) keys[i] = kEmptyKey;
   __syncthreads();
-  block_sort_desc_rt(keys, n2, tid);
-  for (int jx = tid; jx < k; jx += SEL_NT) {
-    const uint64_t key = keys[jx];
-    D[qi * ldD + jx] = key_score(key);
-    I[qi * ldI + jx] = id_base + static_cast<int64_t>(key_row(key));
+  // final order by counting: keys are distinct (the row is part of the key), so rank = #better keys
+  for (int i = tid; i < m; i += SEL_NT) {
+    const uint64_t mine = keys[i];
+    int rank = 0;
+    for (int jx = 0; jx < m; ++jx) rank += keys[jx] > mine ? 1 : 0;
+    if (rank < k) {
+      D[qi * ldD + rank] = key_score(mine);
+      I[qi * ldI + rank] = id_base + static_cast<int64_t>(key_row(mine));
+    }
   }
 }
 
@@ -595,8 +632,7 @@ void search_tensor_device(rs_index* h, const float* q, int64_t nq, int k, int64_
     }
     {
       ProfScope prof(RS_PROF_RESCORE, st);
-      if (n_vals <= 256) threshold_kernel<256><<<cq, 256, 0, st>>>(ws.smax, n_vals, rank, ws.thr, ws.cnt, ws.flags);
-      else threshold_kernel<1024><<<cq, 256, 0, st>>>(ws.smax, n_vals, rank, ws.thr, ws.cnt, ws.flags);
+      threshold_kernel<<<cq, 256, 0, st>>>(ws.smax, n_vals, rank, ws.thr, ws.cnt, ws.flags);
       RS_LAUNCH_CHECK();
     }
     {
