@@ -312,6 +312,13 @@ def main():
                                        "exact-fp32 mode re-streams it per 8-query group and is FFMA-bound at nq=1024)",
                         "launches": dom_n, "ms_per_launch": dom_ms / dom_n,
                         "fp32_tflops": 2.0 * nq * n_local * dim / t / 1e12}
+    if roofline:
+        tf = ROOT / "profiles" / "traffic.json"
+        if tf.exists():
+            ent = json.loads(tf.read_text()).get(roofline["kernel"])
+            if ent and ent.get("n_local") == n_local and ent.get("nq") == nq:
+                roofline["traffic"] = ent["dram_bytes_per_launch"]
+                roofline["traffic_source"] = ent["source"]
     kernel_ms = {n_: {"ms_total": round(v[0], 4), "launches": v[1]} for n_, v in prof.items() if v[1]}
 
     # ---- second headline: DCN ranking forward at batch 65,536 (configs[1]) ----

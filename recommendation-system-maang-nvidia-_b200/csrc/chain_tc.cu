@@ -19,6 +19,7 @@
 //     operand is in TMEM) and acc_ready (tcgen05.commit -> epilogue).
 // Tensor work per sample: 81,920 MAC per tower, 98,304 MAC for the deep net.
 #include <algorithm>
+#include <cstdlib>
 #include <memory>
 #include <mutex>
 
@@ -92,6 +93,7 @@ struct ChainParams {
   ChainProblem prob[2];
   int n_prob;            // 1 or 2 (both towers in one launch)
   int act[MAX_L];
+  int debug;             // perf experiments: 1 = epilogue skips TMEM traffic, 2 = issuer skips the MMAs
 };
 
 template <class C>
@@ -147,6 +149,9 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
     if (elect_one()) {
       // ---------------- MMA issuer: one layer at a time, A from TMEM, B from the resident weights ----------------
       mbar_wait(wfull, 0);
+      // one descriptor for the start of the weight region; every operand descriptor is this plus a compile-time
+      // offset (the single issuing thread must not spend its time rebuilding descriptors)
+      const uint64_t wdesc0 = umma_desc_k_sw128(smem_u32(wsm));
       uint32_t use = 0;
       for (int64_t i = 0; i < n_my; ++i) {
 #pragma unroll
@@ -156,8 +161,8 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
           const uint32_t idesc = umma_idesc_bf16_f32(BM, C::N(l));
 #pragma unroll
           for (int k = 0; k < C::K(l) / 16; ++k) {
-            const uint64_t db =
-                umma_desc_k_sw128(smem_u32(wsm + w_off<C>(l) + (k >> 2) * (C::N(l) * 128)) + static_cast<uint32_t>(k & 3) * 32u);
+            if (p.debug & 2) break;
+            const uint64_t db = wdesc0 + static_cast<uint64_t>((w_off<C>(l) + (k >> 2) * (C::N(l) * 128) + (k & 3) * 32) >> 4);
             umma_bf16_ts(tmem_base + C::DCOL(l), tmem_base + C::ACOL(l) + k * 8, db, idesc, k > 0 ? 1u : 0u);
           }
           umma_commit(acc_ready);
@@ -170,50 +175,55 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
     const int slice = (warp - 4) >> 2;
     const uint32_t lane_sel = static_cast<uint32_t>(quarter * 32) << 16;
     uint32_t use = 0;
+    // layer-0 A operand of one tile: this thread's row, this warp's feature slice, as packed bf16 pairs.  The
+    // loads for tile i+1 are issued right after tile i's operand is stored, so their latency (id -> row, two
+    // dependent global round trips) hides behind tile i's layers instead of sitting on the critical path.
+    uint32_t a0[C::GATHER ? 16 : 32];
+    auto load_a0 = [&](int64_t tile_) {
+      const int64_t row_ = tile_ * BM + quarter * 32 + lane;
+#pragma unroll
+      for (int e = 0; e < (C::GATHER ? 16 : 32); ++e) a0[e] = 0u;
+      if (row_ >= pr.rows) return;
+      if constexpr (C::GATHER) {
+        const int64_t id = !pr.ids ? row_   // no ids: the "table" already holds this batch's rows in order
+                           : pr.ids64 ? static_cast<const int64_t*>(pr.ids)[row_]
+                                      : static_cast<int64_t>(static_cast<const int32_t*>(pr.ids)[row_]);
+        if (id >= 0 && id < pr.table_rows) {
+          const float4* src = reinterpret_cast<const float4*>(pr.table + id * pr.table_ld + slice * 32);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float4 f = __ldg(src + e);
+            a0[2 * e] = pack_bf16x2(f.x, f.y);
+            a0[2 * e + 1] = pack_bf16x2(f.z, f.w);
+          }
+        }
+      } else {
+        const uint4* src = reinterpret_cast<const uint4*>(pr.x + row_ * pr.x_ld + slice * 64);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const uint4 a = __ldg(src + e);
+          a0[4 * e] = a.x; a0[4 * e + 1] = a.y; a0[4 * e + 2] = a.z; a0[4 * e + 3] = a.w;
+        }
+      }
+    };
+    if (n_my > 0) load_a0(cta);
     for (int64_t i = 0; i < n_my; ++i) {
       const int64_t tile = cta + i * ncta;
       const int64_t row = tile * BM + quarter * 32 + lane;
-      // ---- layer-0 A operand: this thread's row, this warp's feature slice, as packed bf16 pairs ----
+      __syncwarp();
       if constexpr (C::GATHER) {
-        uint32_t r[16];
-#pragma unroll
-        for (int e = 0; e < 16; ++e) r[e] = 0u;
-        if (row < pr.rows) {
-          const int64_t id = !pr.ids ? row   // no ids: the "table" already holds this batch's rows in order
-                             : pr.ids64 ? static_cast<const int64_t*>(pr.ids)[row]
-                                        : static_cast<int64_t>(static_cast<const int32_t*>(pr.ids)[row]);
-          if (id >= 0 && id < pr.table_rows) {
-            const float4* src = reinterpret_cast<const float4*>(pr.table + id * pr.table_ld + slice * 32);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const float4 f = __ldg(src + e);
-              r[2 * e] = pack_bf16x2(f.x, f.y);
-              r[2 * e + 1] = pack_bf16x2(f.z, f.w);
-            }
-          }
-        }
-        __syncwarp();
+        uint32_t (&r)[16] = reinterpret_cast<uint32_t (&)[16]>(a0);
         tmem_st_32x32_x16(tmem_base + C::ACOL(0) + slice * 16 + lane_sel, r);
       } else {
-        uint32_t r0[16], r1[16];
-#pragma unroll
-        for (int e = 0; e < 16; ++e) r0[e] = r1[e] = 0u;
-        if (row < pr.rows) {
-          const uint4* src = reinterpret_cast<const uint4*>(pr.x + row * pr.x_ld + slice * 64);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const uint4 a = __ldg(src + e), b = __ldg(src + 4 + e);
-            r0[4 * e] = a.x; r0[4 * e + 1] = a.y; r0[4 * e + 2] = a.z; r0[4 * e + 3] = a.w;
-            r1[4 * e] = b.x; r1[4 * e + 1] = b.y; r1[4 * e + 2] = b.z; r1[4 * e + 3] = b.w;
-          }
-        }
-        __syncwarp();
+        uint32_t (&r0)[16] = reinterpret_cast<uint32_t (&)[16]>(a0[0]);
+        uint32_t (&r1)[16] = reinterpret_cast<uint32_t (&)[16]>(a0[16]);
         tmem_st_32x32_x16(tmem_base + C::ACOL(0) + slice * 32 + lane_sel, r0);
         tmem_st_32x32_x16(tmem_base + C::ACOL(0) + slice * 32 + 16 + lane_sel, r1);
       }
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(a_ready);
+      if (i + 1 < n_my) load_a0(tile + ncta);   // prefetch the next tile's operand
 
 #pragma unroll
       for (int l = 0; l < C::L; ++l, ++use) {
@@ -222,7 +232,7 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
         const int cols = N / slices;                       // accumulator columns per warp: 64, 32 or 32
         mbar_wait(acc_ready, use & 1u);
         tc_fence_after_sync();
-        if (slice < slices) {
+        if (slice < slices && !(p.debug & 1)) {
 #pragma unroll 1
           for (int c = 0; c < cols / 32; ++c) {
             const int col0 = slice * cols + c * 32;
@@ -279,8 +289,254 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// tower_pp_kernel: the tower chain with TWO 128-row tiles in flight per CTA ("ping-pong").  A single tile's chain
+// is a strict sequence MMA -> epilogue -> MMA ..., so with one tile the tensor pipe idles during every epilogue.
+// Here each tile owns one half of TMEM (256 columns) and 8 of the 16 epilogue warps; the one MMA issuer alternates
+// between the two tiles, so tile X's epilogue overlaps tile Y's MMAs.  To fit a tile into 256 columns layer 1
+// (N = 256) runs as two N = 128 halves that share one accumulator:
+//   columns relative to the tile's base R:  A0 [0,64)  acc [64,192)  A1a [192,256)  A1b [0,64)  A2 [192,256)
+//                                           acc3 [0,64)  A3 [64,96)  acc4 [128,256)
+//   steps: L1a (A0 x W1[0:128])  L1b (A0 x W1[128:256])  L2 (A1a|A1b x W2)  L3 (A2 x W3)  L4 (A3 x W4)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NTHREADS, 1)
+tower_pp_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
+  using C = CfgTower;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* wsm = base;
+  float* bias_s = reinterpret_cast<float*>(base + w_off<C>(C::L));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + b_off<C>(C::L));
+  uint64_t* wfull = bars;
+  uint64_t* a_ready = bars + 1;      // [2]
+  uint64_t* acc_ready = bars + 3;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int pi = blockIdx.x % p.n_prob;
+  const int cta = blockIdx.x / p.n_prob;
+  const int ncta = (gridDim.x - pi + p.n_prob - 1) / p.n_prob;
+  const ChainProblem& pr = p.prob[pi];
+  const int64_t ntiles = (pr.rows + BM - 1) / BM;
+  const int64_t n_my = cta < ntiles ? (ntiles - cta + ncta - 1) / ncta : 0;
+
+  if (warp == 0 && lane == 0) {
+    for (int l = 0; l < C::L; ++l) tma_prefetch_desc(&maps.w[pi][l]);
+    mbar_init(wfull, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&a_ready[s], EPI_WARPS / 2);
+      mbar_init(&acc_ready[s], 1);
+    }
+    fence_mbar_init();
+  }
+#pragma unroll
+  for (int l = 0; l < C::L; ++l)
+    for (int i = threadIdx.x; i < C::N(l); i += NTHREADS) bias_s[b_off<C>(l) + i] = pr.bias[l] ? pr.bias[l][i] : 0.0f;
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(wfull, w_off<C>(C::L));
+#pragma unroll
+      for (int l = 0; l < C::L; ++l)
+        for (int kc = 0; kc < C::K(l) / 64; ++kc)
+          tma_load_2d(wsm + w_off<C>(l) + kc * (C::N(l) * 128), &maps.w[pi][l], wfull, kc * 64, 0, kEvictLast);
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      // ---------------- MMA issuer: step s of tile slot 0, step s of tile slot 1, step s+1 of slot 0, ... ----------------
+      mbar_wait(wfull, 0);
+      const uint64_t wdesc0 = umma_desc_k_sw128(smem_u32(wsm));
+      const int64_t n_slot[2] = {(n_my + 1) / 2, n_my / 2};
+      uint32_t use[2] = {0, 0};
+      for (int64_t r = 0; r < n_slot[0]; ++r) {
+#pragma unroll
+        for (int step = 0; step < 5; ++step) {
+#pragma unroll
+          for (int slot = 0; slot < 2; ++slot) {
+            if (r >= n_slot[slot]) continue;
+            const uint32_t R = tmem_base + slot * 256;
+            mbar_wait(&a_ready[slot], use[slot] & 1u);
+            tc_fence_after_sync();
+            if (step <= 1) {          // L1 half: A0 [R, R+64) x W1 rows [128*step, +128), K = 128
+              const uint32_t idesc = umma_idesc_bf16_f32(BM, 128);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const uint64_t db = wdesc0 + static_cast<uint64_t>((w_off<C>(0) + (k >> 2) * (256 * 128) + step * (128 * 128) + (k & 3) * 32) >> 4);
+                umma_bf16_ts(R + 64, R + k * 8, db, idesc, k > 0 ? 1u : 0u);
+              }
+            } else if (step == 2) {   // L2: A1a [R+192, +64) then A1b [R, +64), W2 (N = 128), K = 256
+              const uint32_t idesc = umma_idesc_bf16_f32(BM, 128);
+#pragma unroll
+              for (int k = 0; k < 16; ++k) {
+                const uint64_t db = wdesc0 + static_cast<uint64_t>((w_off<C>(1) + (k >> 2) * (128 * 128) + (k & 3) * 32) >> 4);
+                umma_bf16_ts(R + 64, k < 8 ? R + 192 + k * 8 : R + (k - 8) * 8, db, idesc, k > 0 ? 1u : 0u);
+              }
+            } else if (step == 3) {   // L3: A2 [R+192, +64), W3 (N = 64), K = 128 -> acc3 [R, +64)
+              const uint32_t idesc = umma_idesc_bf16_f32(BM, 64);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const uint64_t db = wdesc0 + static_cast<uint64_t>((w_off<C>(2) + (k >> 2) * (64 * 128) + (k & 3) * 32) >> 4);
+                umma_bf16_ts(R, R + 192 + k * 8, db, idesc, k > 0 ? 1u : 0u);
+              }
+            } else {                  // L4: A3 [R+64, +32), W4 (N = 128), K = 64 -> acc4 [R+128, +128)
+              const uint32_t idesc = umma_idesc_bf16_f32(BM, 128);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t db = wdesc0 + static_cast<uint64_t>((w_off<C>(3) + (k & 3) * 32) >> 4);
+                umma_bf16_ts(R + 128, R + 64 + k * 8, db, idesc, k > 0 ? 1u : 0u);
+              }
+            }
+            umma_commit(&acc_ready[slot]);
+            ++use[slot];
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ---------------- epilogue: 8 warps per tile slot ----------------
+    const int ew = warp - 4;
+    const int slot = ew >> 3;
+    const int quarter = warp & 3;
+    const int half = (ew >> 2) & 1;
+    const uint32_t lane_sel = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t R = tmem_base + slot * 256 + lane_sel;
+    const int64_t n_slot = slot == 0 ? (n_my + 1) / 2 : n_my / 2;
+    uint32_t use = 0;
+    // A0 of one tile: features [64*half, +64) of this thread's embedding row -> 32 packed columns; prefetched one
+    // tile ahead so the id -> row global round trips overlap the previous tile's layers
+    uint32_t a0[32];
+    auto load_a0 = [&](int64_t tile_) {
+      const int64_t row_ = tile_ * BM + quarter * 32 + lane;
+#pragma unroll
+      for (int e = 0; e < 32; ++e) a0[e] = 0u;
+      if (row_ >= pr.rows) return;
+      const int64_t id = !pr.ids ? row_
+                         : pr.ids64 ? static_cast<const int64_t*>(pr.ids)[row_]
+                                    : static_cast<int64_t>(static_cast<const int32_t*>(pr.ids)[row_]);
+      if (id >= 0 && id < pr.table_rows) {
+        const float4* src = reinterpret_cast<const float4*>(pr.table + id * pr.table_ld + half * 64);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const float4 f = __ldg(src + e);
+          a0[2 * e] = pack_bf16x2(f.x, f.y);
+          a0[2 * e + 1] = pack_bf16x2(f.z, f.w);
+        }
+      }
+    };
+    if (n_slot > 0) load_a0(cta + slot * ncta);
+    for (int64_t r = 0; r < n_slot; ++r) {
+      const int64_t tile = cta + (2 * r + slot) * ncta;
+      const int64_t row = tile * BM + quarter * 32 + lane;
+      {
+        uint32_t (&r0)[16] = reinterpret_cast<uint32_t (&)[16]>(a0[0]);
+        uint32_t (&r1)[16] = reinterpret_cast<uint32_t (&)[16]>(a0[16]);
+        __syncwarp();
+        tmem_st_32x32_x16(R + half * 32, r0);
+        tmem_st_32x32_x16(R + half * 32 + 16, r1);
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_ready[slot]);
+        if (r + 1 < n_slot) load_a0(tile + 2 * ncta);
+      }
+#pragma unroll
+      for (int step = 0; step < 5; ++step, ++use) {
+        // accumulator columns, bias, destination of the repacked activations for this step
+        const int acc_col = step <= 2 ? 64 : step == 3 ? 0 : 128;
+        const int ncols = step == 3 ? 64 : 128;                 // accumulator width
+        const int per_warp = ncols / 2;                          // 64 or 32 columns per warp
+        const int layer = step <= 1 ? 0 : step - 1;
+        const int bias0 = b_off<C>(layer) + (step == 1 ? 128 : 0);
+        const int dst_col = step == 0 ? 192 : step == 1 ? 0 : step == 2 ? 192 : 64;   // A1a, A1b, A2, A3
+        mbar_wait(&acc_ready[slot], use & 1u);
+        tc_fence_after_sync();
+#pragma unroll 1
+        for (int c = 0; c < per_warp / 32; ++c) {
+          const int col0 = half * per_warp + c * 32;
+          float v[32];
+          __syncwarp();
+          tmem_ld_32x32(R + acc_col + col0, v);
+          const float* bs = bias_s + bias0 + col0;
+#pragma unroll
+          for (int e = 0; e < 32; e += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bs + e);
+            v[e] += b4.x; v[e + 1] += b4.y; v[e + 2] += b4.z; v[e + 3] += b4.w;
+          }
+          if (p.act[layer] == RS_ACT_RELU) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], 0.0f);
+          }
+          if (step < 4) {
+            uint32_t rr[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) rr[e] = pack_bf16x2(v[2 * e], v[2 * e + 1]);
+            tmem_st_32x32_x16(R + dst_col + (col0 >> 1), rr);
+          } else if (row < pr.rows) {
+            if (pr.y_f32) {
+              float4* dst = reinterpret_cast<float4*>(pr.y_f32 + row * pr.ld_f32 + col0);
+#pragma unroll
+              for (int e = 0; e < 32; e += 4) dst[e >> 2] = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+            }
+            if (pr.y_bf16) {
+              uint4* dst = reinterpret_cast<uint4*>(pr.y_bf16 + row * pr.ld_bf16 + col0);
+#pragma unroll
+              for (int e = 0; e < 32; e += 8)
+                dst[e >> 3] = make_uint4(pack_bf16x2(v[e], v[e + 1]), pack_bf16x2(v[e + 2], v[e + 3]),
+                                         pack_bf16x2(v[e + 4], v[e + 5]), pack_bf16x2(v[e + 6], v[e + 7]));
+            }
+          }
+        }
+        if (step < 4) {
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&a_ready[slot]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+void launch_tower_pp(const ChainMaps& maps, const ChainParams& p, cudaStream_t st) {
+  static std::once_flag once[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::call_once(once[dev & 63], [] {
+    cudaFuncSetAttribute(tower_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, chain_smem<CfgTower>());
+  });
+  int64_t max_tiles = 0;
+  for (int i = 0; i < p.n_prob; ++i) max_tiles = std::max<int64_t>(max_tiles, (p.prob[i].rows + BM - 1) / BM);
+  const int sms = rs::sm_count();
+  // two tiles per CTA at a time: do not spread fewer than 2 tiles per CTA over more CTAs than needed
+  int grid = static_cast<int>(std::min<int64_t>((max_tiles + 1) / 2 * p.n_prob, sms - (sms % p.n_prob)));
+  grid = std::max(grid, p.n_prob);
+  rs::ProfScope prof(RS_PROF_RANK, st);
+  tower_pp_kernel<<<grid, NTHREADS, chain_smem<CfgTower>(), st>>>(maps, p);
+  RS_LAUNCH_CHECK();
+}
+
+bool use_tower_pp() {
+  const char* e = getenv("RS_TOWER_PP");
+  return !(e && e[0] == '0');
+}
+
 template <class C>
-void launch_chain(const ChainMaps& maps, const ChainParams& p, cudaStream_t st) {
+void launch_chain(const ChainMaps& maps, ChainParams p, cudaStream_t st) {
+  if (const char* e = getenv("RS_CHAIN_DEBUG")) p.debug = atoi(e);
   static std::once_flag once[64];
   int dev = 0;
   cudaGetDevice(&dev);
@@ -390,7 +646,8 @@ extern "C" int rs_chain_forward_bf16(int n_prob, int n_layers, const DLTensor* c
     for (int q = 0; q < n_prob; ++q) any |= p.prob[q].rows > 0;
     if (!any) return;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (tower) launch_chain<CfgTower>(maps, p, st);
+    if (tower && use_tower_pp()) launch_tower_pp(maps, p, st);
+    else if (tower) launch_chain<CfgTower>(maps, p, st);
     else launch_chain<CfgDeep>(maps, p, st);
   });
 }
@@ -643,7 +900,8 @@ static int ranker_forward_impl(rs_ranker* h, const DLTensor* user_rows, const DL
         pr.y_bf16 = x_bf16 + s * 128;
         pr.ld_bf16 = 256;
       }
-      launch_chain<CfgTower>(h->tower_maps, p, st);
+      if (use_tower_pp()) launch_tower_pp(h->tower_maps, p, st);
+      else launch_chain<CfgTower>(h->tower_maps, p, st);
       ChainParams d{};
       d.n_prob = 1;
       d.act[0] = d.act[1] = RS_ACT_RELU;

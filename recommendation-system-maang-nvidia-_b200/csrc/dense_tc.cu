@@ -121,6 +121,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       // ---- MMA issuer ----
       constexpr uint32_t idesc = umma_idesc_bf16_f32(BM, N);
       mbar_wait(wfull, 0);
+      const uint64_t wdesc0 = umma_desc_k_sw128(smem_u32(wsm)), xdesc0 = umma_desc_k_sw128(smem_u32(xsm));
       uint32_t it = 0;
       for (int64_t i = 0; i < n_my; ++i) {
         const uint32_t a = static_cast<uint32_t>(i) & 1u, aph = (static_cast<uint32_t>(i) >> 1) & 1u;
@@ -132,8 +133,8 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
           tc_fence_after_sync();
 #pragma unroll
           for (int k4 = 0; k4 < 4; ++k4) {
-            const uint64_t da = umma_desc_k_sw128(smem_u32(xsm + s * CHUNK_BYTES) + k4 * 32u);
-            const uint64_t db = umma_desc_k_sw128(smem_u32(wsm + kc * (N * 128)) + k4 * 32u);
+            const uint64_t da = xdesc0 + static_cast<uint64_t>((s * CHUNK_BYTES + k4 * 32) >> 4);
+            const uint64_t db = wdesc0 + static_cast<uint64_t>((kc * (N * 128) + k4 * 32) >> 4);
             umma_bf16_ss(tmem_base + a * N, da, db, idesc, (kc | k4) ? 1u : 0u);
           }
           umma_commit(&empty[s]);

@@ -159,6 +159,9 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       // ---------------- MMA issuer ----------------
       constexpr uint32_t idesc = umma_idesc_bf16_f32(BM, BN);
       mbar_wait(qfull, 0);
+      // operand descriptors = one base descriptor per region + small offsets: keeps the issuing thread's per-MMA
+      // overhead to an add (it is a single thread feeding the whole tensor pipe)
+      const uint64_t qdesc0 = umma_desc_k_sw128(smem_u32(qsm)), xdesc0 = umma_desc_k_sw128(smem_u32(xsm));
       uint32_t acc_it = 0;
       for (int64_t i = 0; i < n_my; ++i) {
         const int s = static_cast<int>(i % NSTAGE);
@@ -174,8 +177,8 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             if (p.debug & 2) break;
             const int h = k >> 2;
             const uint32_t ko = static_cast<uint32_t>(k & 3) * 32u;
-            const uint64_t da = umma_desc_k_sw128(smem_u32(qsm + r * QTILE_BYTES + h * (QTILE_BYTES / 2)) + ko);
-            const uint64_t db = umma_desc_k_sw128(smem_u32(xsm + s * STAGE_BYTES + h * (STAGE_BYTES / 2)) + ko);
+            const uint64_t da = qdesc0 + static_cast<uint64_t>((r * QTILE_BYTES + h * (QTILE_BYTES / 2) + static_cast<int>(ko)) >> 4);
+            const uint64_t db = xdesc0 + static_cast<uint64_t>((s * STAGE_BYTES + h * (STAGE_BYTES / 2) + static_cast<int>(ko)) >> 4);
             umma_bf16_ss(tmem_base + a * BN, da, db, idesc, k > 0 ? 1u : 0u);
           }
           umma_commit(&tfull[a]);
