@@ -238,7 +238,11 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
             const int col0 = slice * cols + c * 32;
             float v[32];
             __syncwarp();
-            tmem_ld_32x32(tmem_base + C::DCOL(l) + col0 + lane_sel, v);
+            if (!(p.debug & 8)) tmem_ld_32x32(tmem_base + C::DCOL(l) + col0 + lane_sel, v);
+            else {
+#pragma unroll
+              for (int e = 0; e < 32; ++e) v[e] = static_cast<float>(e + lane);
+            }
             const float* bs = bias_s + b_off<C>(l) + col0;
 #pragma unroll
             for (int e = 0; e < 32; e += 4) {
@@ -253,19 +257,22 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
               uint32_t r[16];
 #pragma unroll
               for (int e = 0; e < 16; ++e) r[e] = pack_bf16x2(v[2 * e], v[2 * e + 1]);
-              tmem_st_32x32_x16(tmem_base + C::ACOL(l + 1 < C::L ? l + 1 : l) + (col0 >> 1) + lane_sel, r);
+              if (!(p.debug & 4)) tmem_st_32x32_x16(tmem_base + C::ACOL(l + 1 < C::L ? l + 1 : l) + (col0 >> 1) + lane_sel, r);
             } else if (row < pr.rows) {
               if (pr.y_f32) {
-                float4* dst = reinterpret_cast<float4*>(pr.y_f32 + row * pr.ld_f32 + col0);
-#pragma unroll
-                for (int e = 0; e < 32; e += 4) dst[e >> 2] = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
-              }
-              if (pr.y_bf16) {
-                uint4* dst = reinterpret_cast<uint4*>(pr.y_bf16 + row * pr.ld_bf16 + col0);
+                float* dst = pr.y_f32 + row * pr.ld_f32 + col0;
 #pragma unroll
                 for (int e = 0; e < 32; e += 8)
-                  dst[e >> 3] = make_uint4(pack_bf16x2(v[e], v[e + 1]), pack_bf16x2(v[e + 2], v[e + 3]),
-                                           pack_bf16x2(v[e + 4], v[e + 5]), pack_bf16x2(v[e + 6], v[e + 7]));
+                  st_global_256(dst + e, v[e], v[e + 1], v[e + 2], v[e + 3], v[e + 4], v[e + 5], v[e + 6], v[e + 7]);
+              }
+              if (pr.y_bf16) {
+                uint16_t* dst = pr.y_bf16 + row * pr.ld_bf16 + col0;
+#pragma unroll
+                for (int e = 0; e < 32; e += 16)
+                  st_global_256(static_cast<void*>(dst + e), pack_bf16x2(v[e], v[e + 1]), pack_bf16x2(v[e + 2], v[e + 3]),
+                                pack_bf16x2(v[e + 4], v[e + 5]), pack_bf16x2(v[e + 6], v[e + 7]),
+                                pack_bf16x2(v[e + 8], v[e + 9]), pack_bf16x2(v[e + 10], v[e + 11]),
+                                pack_bf16x2(v[e + 12], v[e + 13]), pack_bf16x2(v[e + 14], v[e + 15]));
               }
             }
           }
@@ -481,16 +488,19 @@ tower_pp_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
             tmem_st_32x32_x16(R + dst_col + (col0 >> 1), rr);
           } else if (row < pr.rows) {
             if (pr.y_f32) {
-              float4* dst = reinterpret_cast<float4*>(pr.y_f32 + row * pr.ld_f32 + col0);
-#pragma unroll
-              for (int e = 0; e < 32; e += 4) dst[e >> 2] = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
-            }
-            if (pr.y_bf16) {
-              uint4* dst = reinterpret_cast<uint4*>(pr.y_bf16 + row * pr.ld_bf16 + col0);
+              float* dst = pr.y_f32 + row * pr.ld_f32 + col0;
 #pragma unroll
               for (int e = 0; e < 32; e += 8)
-                dst[e >> 3] = make_uint4(pack_bf16x2(v[e], v[e + 1]), pack_bf16x2(v[e + 2], v[e + 3]),
-                                         pack_bf16x2(v[e + 4], v[e + 5]), pack_bf16x2(v[e + 6], v[e + 7]));
+                st_global_256(dst + e, v[e], v[e + 1], v[e + 2], v[e + 3], v[e + 4], v[e + 5], v[e + 6], v[e + 7]);
+            }
+            if (pr.y_bf16) {
+              uint16_t* dst = pr.y_bf16 + row * pr.ld_bf16 + col0;
+#pragma unroll
+              for (int e = 0; e < 32; e += 16)
+                st_global_256(static_cast<void*>(dst + e), pack_bf16x2(v[e], v[e + 1]), pack_bf16x2(v[e + 2], v[e + 3]),
+                              pack_bf16x2(v[e + 4], v[e + 5]), pack_bf16x2(v[e + 6], v[e + 7]),
+                              pack_bf16x2(v[e + 8], v[e + 9]), pack_bf16x2(v[e + 10], v[e + 11]),
+                              pack_bf16x2(v[e + 12], v[e + 13]), pack_bf16x2(v[e + 14], v[e + 15]));
             }
           }
         }
@@ -630,16 +640,14 @@ extern "C" int rs_chain_forward_bf16(int n_prob, int n_layers, const DLTensor* c
         RS_CHECK(on_device(yf) && yf->shape[0] == rows && yf->shape[1] == n_last, "y_f32 must be [B, out]");
         pr.y_f32 = data_ptr<float>(yf);
         pr.ld_f32 = row_stride_2d(yf, "y_f32");
-        RS_CHECK(pr.ld_f32 % 4 == 0, "y_f32 row stride must be a multiple of 4");
-        require_aligned16(pr.y_f32, "y_f32");
+        RS_CHECK(pr.ld_f32 % 8 == 0 && (reinterpret_cast<uintptr_t>(pr.y_f32) & 31) == 0, "y_f32 must be 32-byte aligned with a row stride multiple of 8");
       }
       if (yb) {
         require(yb, "y_bf16", 2, kDLBfloat, 16);
         RS_CHECK(on_device(yb) && yb->shape[0] == rows && yb->shape[1] == n_last, "y_bf16 must be [B, out]");
         pr.y_bf16 = data_ptr<uint16_t>(yb);
         pr.ld_bf16 = row_stride_2d(yb, "y_bf16");
-        RS_CHECK(pr.ld_bf16 % 8 == 0, "y_bf16 row stride must be a multiple of 8");
-        require_aligned16(pr.y_bf16, "y_bf16");
+        RS_CHECK(pr.ld_bf16 % 16 == 0 && (reinterpret_cast<uintptr_t>(pr.y_bf16) & 31) == 0, "y_bf16 must be 32-byte aligned with a row stride multiple of 16");
       }
     }
     bool any = false;

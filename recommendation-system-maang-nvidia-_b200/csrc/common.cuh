@@ -192,6 +192,19 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
 
+// 256-bit global stores (STG.256, new on sm_100): one full 32-byte sector per thread and instruction
+__device__ __forceinline__ void st_global_256(float* p, float a, float b, float c, float d, float e, float f, float g, float h) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d), "f"(e), "f"(f),
+               "f"(g), "f"(h)
+               : "memory");
+}
+__device__ __forceinline__ void st_global_256(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f,
+                                              uint32_t g, uint32_t h) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e), "r"(f),
+               "r"(g), "r"(h)
+               : "memory");
+}
+
 // ---- packed (score, row) keys: larger key == better hit under (score desc, row asc) ----
 __device__ __forceinline__ uint32_t f32_to_ordered(float s) {
   s += 0.0f;  // -0 -> +0 so that equal floats give equal keys
