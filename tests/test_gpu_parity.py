@@ -411,3 +411,47 @@ def test_service_load_from_artifacts(rs, tmp_path):
     assert svc.recommend(uv[2], 5) == ref.recommend(uv[2], 5)
     with pytest.raises(FileNotFoundError):
         rs.RecommendationService(str(tmp_path / "missing")).load()
+
+
+# ------------------------------------------------------------------------------------------ K7b sharded tables
+def test_a2a_plan_kernels_and_hash_table(rs):
+    from recsys_b200 import _lib
+    rng = np.random.default_rng(21)
+    for G, B in ((2, 1000), (8, 65536), (3, 7)):
+        ids = rs.synth.zipf_ids(rng, 100_000, B)
+        ids_d = dev(ids)
+        counts = torch.empty((G,), dtype=torch.int64, device="cuda")
+        a, b = _lib.dl(ids_d), _lib.dl(counts)
+        _lib.check(_lib.load().rs_a2a_count(a.ptr, G, b.ptr, _lib.stream_ptr()))
+        want_counts = np.bincount(ids % G, minlength=G)
+        np.testing.assert_array_equal(counts.cpu().numpy(), want_counts)
+        base = torch.from_numpy(np.concatenate([[0], np.cumsum(want_counts)[:-1]]).astype(np.int64)).cuda()
+        cursor = torch.empty((G,), dtype=torch.int64, device="cuda")
+        send, perm = torch.empty_like(ids_d), torch.empty_like(ids_d)
+        hs = [_lib.dl(t) for t in (ids_d, base, cursor, send, perm)]
+        _lib.check(_lib.load().rs_a2a_scatter(hs[0].ptr, G, hs[1].ptr, hs[2].ptr, hs[3].ptr, hs[4].ptr, _lib.stream_ptr()))
+        send_h, perm_h = send.cpu().numpy(), perm.cpu().numpy()
+        assert sorted(perm_h.tolist()) == list(range(B))                       # a permutation of the slots
+        np.testing.assert_array_equal(send_h[perm_h], ids // G)                # every id's local row sits in its slot
+        seg = np.searchsorted(np.cumsum(want_counts), perm_h, side="right")    # and the slot lies in its owner's segment
+        np.testing.assert_array_equal(seg, ids % G)
+    from recsys_b200.sharded import ShardedEmbedding
+    shard = ShardedEmbedding.fill_synthetic(1000, 128, 1, 3, 77, torch.device("cuda", 0))
+    rows = np.arange(1, 1000, 3)
+    np.testing.assert_array_equal(shard.cpu().numpy(), rs.synth.hash_table_rows(rows, 128, 77))
+    emb = ShardedEmbedding(1000, 128, local_table=ShardedEmbedding.fill_synthetic(1000, 128, 0, 1, 77, "cuda"))
+    ids = rng.integers(0, 1000, 300)
+    np.testing.assert_array_equal(emb.lookup(dev(ids)).cpu().numpy(), rs.synth.hash_table_rows(ids, 128, 77))
+
+
+def test_rank_from_embedding_rows_equals_rank_from_ids(rs):
+    cfg = rs.ModelConfig()
+    w = rs.synth.make_weights(cfg, 500, 400, seed=31)
+    m = rs.MultiTaskModel(cfg, rs.synth.make_vocab(500), rs.synth.make_vocab(400), {}, precision="bf16")
+    rs.load_weights(m, w)
+    rng = np.random.default_rng(32)
+    ur, ir = rs.synth.make_ids(rng, 500, 1000), rs.synth.make_ids(rng, 400, 1000)
+    a = m({"user_id": dev(ur), "movie_id": dev(ir)})
+    b = m.rank_from_embedding_rows(dev(w["user_embedding"][ur]), dev(w["item_embedding"][ir]))
+    for k_ in a:
+        assert torch.equal(a[k_], b[k_]), k_
