@@ -186,6 +186,11 @@ def main():
     args = parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    # stdout must carry exactly ONE JSON line: native libraries (NCCL's version banner) write to fd 1 directly, so
+    # fd 1 is pointed at stderr for the duration of the run and restored for the final print
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
 
     import torch
     import torch.distributed as dist
@@ -350,7 +355,9 @@ def main():
                 "cpu_baseline": cpu, "ranking": ranking, "batch1_latency": batch1}
         if world > 1:
             line["exchange_bytes_per_step_per_rank"] = gather_bytes(world, nq, k)
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
