@@ -231,6 +231,11 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           float v[32];
           __syncwarp();
           tmem_ld_32x32(taddr + c * 32, v);
+          if (c == SLICE_COLS / 32 - 1) {   // last chunk is in registers: hand the accumulator back before processing it
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[a]);
+          }
           // group maxima over 8 consecutive scores with 3-input max: half an instruction per score
           float g[4];
 #pragma unroll
@@ -275,9 +280,12 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         if (MODE == MODE_SAMPLE)   // several sampled tiles share a slot: keep the maximum
           atomicMax(&p.smax[(int64_t)qrow[r] * p.smax_ld + (visit % (p.smax_ld / EPI_SLICES)) * EPI_SLICES + slice],
                     f32_to_ordered(hmax));
-        tc_fence_before_sync();
+        if (p.debug & 1) {   // (experiment: no TMEM reads) still release the accumulator
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[a]);
+        }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[a]);
         if (MODE == MODE_FILTER) {
           const int n = min(*wq_cnt, WQ_CAP);   // uniform: read after the __syncwarp above
           if (n >= 32) flush(n);
