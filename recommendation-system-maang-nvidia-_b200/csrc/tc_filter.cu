@@ -36,7 +36,6 @@
 
 #include "flat_index.cuh"
 #include "tcgen05.cuh"
-#include "topk.cuh"
 
 namespace {
 
