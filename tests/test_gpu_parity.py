@@ -455,3 +455,32 @@ def test_rank_from_embedding_rows_equals_rank_from_ids(rs):
     b = m.rank_from_embedding_rows(dev(w["user_embedding"][ur]), dev(w["item_embedding"][ir]))
     for k_ in a:
         assert torch.equal(a[k_], b[k_]), k_
+
+
+def test_catalog_build_and_recall_eval(rs, tmp_path):
+    """Section 8f: catalog build (src/trainer.py:221-245) and recall evaluation (src/trainer.py:195-219) on the GPU path."""
+    from oracle import evaluation as ev
+    from oracle.models import MultiTowerModel as OMT
+    cfg = rs.ModelConfig()
+    uv, iv = rs.synth.make_vocab(200), rs.synth.make_vocab(1300)
+    w = rs.synth.make_weights(cfg, 200, 1300, seed=41)
+    enc = rs.MultiTowerModel(cfg, uv, iv, {})
+    rs.load_weights(enc, w)
+    index, item_map = rs.build_item_index(enc, iv)
+    assert index.ntotal == 1300 and item_map["7"] == iv[7]
+    rs.save_index_artifacts(index, item_map, tmp_path)
+    assert rs.read_index(str(tmp_path / "faiss.idx")).ntotal == 1300
+    # reference-style evaluation: raw dots, true item = each user's oracle top-1 -> recall@k must be 1 for k >= 1
+    oenc = OMT(w, uv, iv, np.float64)
+    S = oenc({"user_id": uv[:50]})["user_embedding"] @ oenc({"movie_id": iv})["item_embedding"].T
+    top = np.argsort(-S, axis=1)
+    truth = [iv[j] for j in top[:, 0]]
+    rec = rs.evaluate_recall(enc, iv, uv[:50], truth, ks=(1, 5, 10))
+    assert rec["recall@5"] == 1.0 and rec["recall@10"] == 1.0 and rec["recall@1"] >= 0.9
+    far = [iv[j] for j in top[:, 40]]
+    assert rs.evaluate_recall(enc, iv, uv[:50], far, ks=(5,))["recall@5"] == 0.0
+    # ranked id lists feed the AdvancedMetrics signatures unchanged
+    q = enc({"user_id": uv[:50]})["user_embedding"].contiguous()
+    raw_index, raw_map = rs.build_item_index(enc, iv, normalize=False)
+    preds = rs.ranked_item_ids(raw_index, raw_map, q, 10)
+    assert ev.recall_at_k(preds, truth, 10) == 1.0 and ev.mrr(preds, truth) >= 0.9
