@@ -669,17 +669,36 @@ extern "C" int rs_chain_forward_bf16(int n_prob, int n_layers, const DLTensor* c
 namespace {
 
 // DCN-v1 cross stack + both heads for D = 256, deep width 128, without materialising the [B,384] concat:
-// one warp per row; x0/x_l live in registers (8 per lane), deep output 4 per lane.
+// one warp per row; x0/x_l live in registers (8 per lane), deep output 4 per lane.  All cross / head vectors are
+// hoisted into registers once per warp (L is a template parameter), so a row costs three 128-bit loads.
+template <int L>
 __global__ void __launch_bounds__(256) cross_heads_kernel(const float* __restrict__ x0p, int64_t ldx,
                                                           const float* __restrict__ deep, int64_t ldd,
                                                           const float* __restrict__ cw, const float* __restrict__ cb,
-                                                          int n_layers, const float* __restrict__ hw,
-                                                          const float* __restrict__ hb, float* __restrict__ rating,
-                                                          float* __restrict__ ctr, int64_t B) {
+                                                          const float* __restrict__ hw, const float* __restrict__ hb,
+                                                          float* __restrict__ rating, float* __restrict__ ctr, int64_t B) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   constexpr int D = 256, W = 384;
+  float4 wv[L > 0 ? L : 1][2], bv[L > 0 ? L : 1][2], wr[3], wc[3];
+#pragma unroll
+  for (int l = 0; l < L; ++l)
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      wv[l][c] = __ldg(reinterpret_cast<const float4*>(cw + (int64_t)l * D) + lane + 32 * c);
+      bv[l][c] = __ldg(reinterpret_cast<const float4*>(cb + (int64_t)l * D) + lane + 32 * c);
+    }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    wr[c] = __ldg(reinterpret_cast<const float4*>(hw) + lane + 32 * c);
+    wc[c] = __ldg(reinterpret_cast<const float4*>(hw + W) + lane + 32 * c);
+  }
+  const float hb0 = hb[0], hb1 = hb[1];
+  auto dot4 = [](const float4& a, const float4& b, float s) {
+    s = fmaf(a.x, b.x, s); s = fmaf(a.y, b.y, s); s = fmaf(a.z, b.z, s); s = fmaf(a.w, b.w, s);
+    return s;
+  };
   for (int64_t r = warp; r < B; r += nwarps) {
     float4 x0[2], xl[2];
 #pragma unroll
@@ -688,46 +707,29 @@ __global__ void __launch_bounds__(256) cross_heads_kernel(const float* __restric
       xl[c] = x0[c];
     }
     const float4 dv = __ldg(reinterpret_cast<const float4*>(deep + r * ldd) + lane);
-    for (int l = 0; l < n_layers; ++l) {
-      float s = 0.0f;
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const float4 wv = __ldg(reinterpret_cast<const float4*>(cw + (int64_t)l * D) + lane + 32 * c);
-        s = fmaf(xl[c].x, wv.x, s); s = fmaf(xl[c].y, wv.y, s); s = fmaf(xl[c].z, wv.z, s); s = fmaf(xl[c].w, wv.w, s);
-      }
+    for (int l = 0; l < L; ++l) {
+      float s = dot4(xl[1], wv[l][1], dot4(xl[0], wv[l][0], 0.0f));
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
-        const float4 bv = __ldg(reinterpret_cast<const float4*>(cb + (int64_t)l * D) + lane + 32 * c);
-        xl[c].x = (x0[c].x * s + bv.x) + xl[c].x;
-        xl[c].y = (x0[c].y * s + bv.y) + xl[c].y;
-        xl[c].z = (x0[c].z * s + bv.z) + xl[c].z;
-        xl[c].w = (x0[c].w * s + bv.w) + xl[c].w;
+        xl[c].x = (x0[c].x * s + bv[l][c].x) + xl[c].x;   // bias outside the product (src/models.py:44)
+        xl[c].y = (x0[c].y * s + bv[l][c].y) + xl[c].y;
+        xl[c].z = (x0[c].z * s + bv[l][c].z) + xl[c].z;
+        xl[c].w = (x0[c].w * s + bv[l][c].w) + xl[c].w;
       }
     }
-    float sr = 0.0f, sc = 0.0f;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      const float4 wr = __ldg(reinterpret_cast<const float4*>(hw) + lane + 32 * c);
-      const float4 wc = __ldg(reinterpret_cast<const float4*>(hw + W) + lane + 32 * c);
-      sr = fmaf(xl[c].x, wr.x, sr); sr = fmaf(xl[c].y, wr.y, sr); sr = fmaf(xl[c].z, wr.z, sr); sr = fmaf(xl[c].w, wr.w, sr);
-      sc = fmaf(xl[c].x, wc.x, sc); sc = fmaf(xl[c].y, wc.y, sc); sc = fmaf(xl[c].z, wc.z, sc); sc = fmaf(xl[c].w, wc.w, sc);
-    }
-    {
-      const float4 wr = __ldg(reinterpret_cast<const float4*>(hw + D) + lane);
-      const float4 wc = __ldg(reinterpret_cast<const float4*>(hw + W + D) + lane);
-      sr = fmaf(dv.x, wr.x, sr); sr = fmaf(dv.y, wr.y, sr); sr = fmaf(dv.z, wr.z, sr); sr = fmaf(dv.w, wr.w, sr);
-      sc = fmaf(dv.x, wc.x, sc); sc = fmaf(dv.y, wc.y, sc); sc = fmaf(dv.z, wc.z, sc); sc = fmaf(dv.w, wc.w, sc);
-    }
+    float sr = dot4(dv, wr[2], dot4(xl[1], wr[1], dot4(xl[0], wr[0], 0.0f)));
+    float sc = dot4(dv, wc[2], dot4(xl[1], wc[1], dot4(xl[0], wc[0], 0.0f)));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       sr += __shfl_xor_sync(0xFFFFFFFFu, sr, o);
       sc += __shfl_xor_sync(0xFFFFFFFFu, sc, o);
     }
     if (lane == 0) {
-      rating[r] = sr + hb[0];
-      ctr[r] = 1.0f / (1.0f + expf(-(sc + hb[1])));
+      rating[r] = sr + hb0;
+      ctr[r] = 1.0f / (1.0f + expf(-(sc + hb1)));
     }
   }
 }
@@ -794,7 +796,7 @@ extern "C" int rs_ranker_create(const DLTensor* user_table, const DLTensor* item
     require(head_w, "head_w", 2, kDLFloat, 32);
     require(head_b, "head_b", 1, kDLFloat, 32);
     const int64_t L = cross_w->shape[0];
-    RS_CHECK(L >= 0 && L <= 8 && cross_w->shape[1] == 256 && cross_b->shape[0] == L && cross_b->shape[1] == 256 &&
+    RS_CHECK(L >= 0 && L <= 4 && cross_w->shape[1] == 256 && cross_b->shape[0] == L && cross_b->shape[1] == 256 &&
                  is_compact(cross_w) && is_compact(cross_b), "cross_w / cross_b must be contiguous [n_layers, 256]");
     RS_CHECK(head_w->shape[0] == 2 && head_w->shape[1] == 384 && is_compact(head_w) && head_b->shape[0] == 2,
              "head_w must be contiguous [2, 384], head_b [2]");
@@ -922,9 +924,21 @@ static int ranker_forward_impl(rs_ranker* h, const DLTensor* user_rows, const DL
       launch_chain<CfgDeep>(h->deep_maps, d, st);
       const int64_t want = (B * 32 + 255) / 256;
       const int blocks = static_cast<int>(std::min<int64_t>(want, (int64_t)sm_count() * 8));
-      cross_heads_kernel<<<blocks, 256, 0, st>>>(data_ptr<float>(combined), 256, deep_out, 128, h->f32 + h->off_cw,
-                                                 h->f32 + h->off_cb, h->cross_layers, h->f32 + h->off_hw,
-                                                 h->f32 + h->off_hb, data_ptr<float>(rating), data_ptr<float>(ctr), B);
+      const float* x0 = data_ptr<float>(combined);
+      const float* cwp = h->f32 + h->off_cw;
+      const float* cbp = h->f32 + h->off_cb;
+      const float* hwp = h->f32 + h->off_hw;
+      const float* hbp = h->f32 + h->off_hb;
+      float* rp = data_ptr<float>(rating);
+      float* cp = data_ptr<float>(ctr);
+      switch (h->cross_layers) {
+        case 0: cross_heads_kernel<0><<<blocks, 256, 0, st>>>(x0, 256, deep_out, 128, cwp, cbp, hwp, hbp, rp, cp, B); break;
+        case 1: cross_heads_kernel<1><<<blocks, 256, 0, st>>>(x0, 256, deep_out, 128, cwp, cbp, hwp, hbp, rp, cp, B); break;
+        case 2: cross_heads_kernel<2><<<blocks, 256, 0, st>>>(x0, 256, deep_out, 128, cwp, cbp, hwp, hbp, rp, cp, B); break;
+        case 3: cross_heads_kernel<3><<<blocks, 256, 0, st>>>(x0, 256, deep_out, 128, cwp, cbp, hwp, hbp, rp, cp, B); break;
+        case 4: cross_heads_kernel<4><<<blocks, 256, 0, st>>>(x0, 256, deep_out, 128, cwp, cbp, hwp, hbp, rp, cp, B); break;
+        default: RS_CHECK(false, "the fused ranker supports up to 4 cross layers");
+      }
       RS_LAUNCH_CHECK();
     } catch (...) {
       cudaFreeAsync(x_bf16, st);
