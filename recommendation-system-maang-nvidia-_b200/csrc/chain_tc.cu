@@ -734,6 +734,304 @@ __global__ void __launch_bounds__(256) cross_heads_kernel(const float* __restric
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// deep_heads_kernel: the deep chain, the DCN-v1 cross stack and both heads in ONE kernel (src/models.py:38-48 and
+// 119-120,131).  Same tcgen05 pipeline as chain_tc_kernel<CfgDeep>; what is fused around it:
+//   * the layer-0 A operand is packed from the fp32 tower outputs x0 = combined[B,256] (no bf16 copy in HBM), and
+//     while those values are in registers each thread accumulates, in fp32, its 64-feature share of the dots
+//     P_l = x0 . w_l (l < LC), Hr = x0 . head_r[:256], Hc = x0 . head_c[:256];
+//   * the last epilogue dots the fp32 deep output (bias + relu applied) with head_r[256:], head_c[256:] instead of
+//     writing it;
+//   * one thread per row then runs the cross recurrence in closed form.  x_{l+1} = x0 (x_l . w_l) + b_l + x_l keeps
+//     x_l = a_l x0 + c_l with c_l = b_0 + .. + b_{l-1}, so  s_l = a_l P_l + c_l . w_l,  a_{l+1} = a_l + s_l, and
+//     rating = a_L Hr + c_L . head_r[:256] + deep . head_r[256:] + bias  (ctr likewise, through a sigmoid).
+//     The c_l dots are per-model constants computed once per CTA.
+// Per sample the kernel reads 1 KB (x0) and writes 8 bytes.
+// ------------------------------------------------------------------------------------------------
+struct DeepHeadsParams {
+  int64_t rows;
+  const float* x;          // fp32 [rows, 256], row stride 256
+  const float* bias[2];
+  const float* cw;         // [LC, 256]
+  const float* cb;         // [LC, 256]
+  const float* hw;         // [2, 384]
+  const float* hb;         // [2]
+  const float* consts;     // [LC + 2]: c_l . w_l for l < LC, c_L . head_r[:256], c_L . head_c[:256]  (ranker_consts_kernel)
+  float* rating;           // [rows]
+  float* ctr;              // [rows]
+};
+
+// per-model constants of the closed-form cross recurrence, computed once when the ranker handle is created
+__global__ void ranker_consts_kernel(const float* __restrict__ cw, const float* __restrict__ cb,
+                                     const float* __restrict__ hw, int L, float* __restrict__ out) {
+  const int lane = threadIdx.x;
+  float acc[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+  for (int j = lane; j < 256; j += 32) {
+    float c = 0.0f;
+    for (int l = 0; l < L; ++l) {
+      acc[l] = fmaf(c, cw[l * 256 + j], acc[l]);
+      c += cb[l * 256 + j];
+    }
+    acc[4] = fmaf(c, hw[j], acc[4]);
+    acc[5] = fmaf(c, hw[384 + j], acc[5]);
+  }
+#pragma unroll
+  for (int t = 0; t < 6; ++t) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[t] += __shfl_xor_sync(0xFFFFFFFFu, acc[t], o);
+  }
+  if (lane == 0) {
+    for (int l = 0; l < L; ++l) out[l] = acc[l];
+    out[L] = acc[4];
+    out[L + 1] = acc[5];
+  }
+}
+
+template <int LC>
+constexpr int deep_heads_smem() {
+  return w_off<CfgDeep>(2) + (384 + LC * 256 + 768 + 8 + (LC + 4) * 512) * 4 + 256 + 1024;
+}
+
+template <int LC>
+__global__ void __launch_bounds__(NTHREADS, 1)
+deep_heads_kernel(const __grid_constant__ ChainMaps maps, const DeepHeadsParams p) {
+  using C = CfgDeep;
+  constexpr int NP = LC + 2;   // dots taken over x0 per row
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* wsm = base;
+  float* bias_s = reinterpret_cast<float*>(base + w_off<C>(2));
+  float* cw_s = bias_s + 384;                 // [LC][256]
+  float* hw_s = cw_s + LC * 256;              // [2][384]
+  float* const_s = hw_s + 768;                // [LC] c_l . w_l, then c_L . head_r, c_L . head_c
+  float* part = const_s + 8;                  // [(NP + 2)][4 slices][128 rows]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(part + (LC + 4) * 512);
+  uint64_t* wfull = bars;
+  uint64_t* a_ready = bars + 1;
+  uint64_t* acc_ready = bars + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int cta = blockIdx.x;
+  const int ncta = gridDim.x;
+  const int64_t ntiles = (p.rows + BM - 1) / BM;
+  const int64_t n_my = cta < ntiles ? (ntiles - cta + ncta - 1) / ncta : 0;
+
+  if (warp == 0 && lane == 0) {
+    for (int l = 0; l < 2; ++l) tma_prefetch_desc(&maps.w[0][l]);
+    mbar_init(wfull, 1);
+    mbar_init(a_ready, EPI_WARPS);
+    mbar_init(acc_ready, 1);
+    fence_mbar_init();
+  }
+  for (int i = threadIdx.x; i < 384; i += NTHREADS) {
+    const int l = i < 256 ? 0 : 1;
+    const float* b = p.bias[l];
+    bias_s[i] = b ? b[i - l * 256] : 0.0f;
+  }
+  for (int i = threadIdx.x; i < LC * 256; i += NTHREADS) cw_s[i] = p.cw[i];
+  for (int i = threadIdx.x; i < 768; i += NTHREADS) hw_s[i] = p.hw[i];
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  if (threadIdx.x < NP) const_s[threadIdx.x] = p.consts[threadIdx.x];
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(wfull, w_off<C>(2));
+#pragma unroll
+      for (int l = 0; l < 2; ++l)
+        for (int kc = 0; kc < 4; ++kc)
+          tma_load_2d(wsm + w_off<C>(l) + kc * (C::N(l) * 128), &maps.w[0][l], wfull, kc * 64, 0, kEvictLast);
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      mbar_wait(wfull, 0);
+      const uint64_t wdesc0 = umma_desc_k_sw128(smem_u32(wsm));
+      uint32_t use = 0;
+      for (int64_t i = 0; i < n_my; ++i) {
+#pragma unroll
+        for (int l = 0; l < 2; ++l, ++use) {
+          mbar_wait(a_ready, use & 1u);
+          tc_fence_after_sync();
+          const uint32_t idesc = umma_idesc_bf16_f32(BM, C::N(l));
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            const uint64_t db = wdesc0 + static_cast<uint64_t>((w_off<C>(l) + (k >> 2) * (C::N(l) * 128) + (k & 3) * 32) >> 4);
+            umma_bf16_ts(tmem_base + C::DCOL(l), tmem_base + C::ACOL(l) + k * 8, db, idesc, k > 0 ? 1u : 0u);
+          }
+          umma_commit(acc_ready);
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    const int quarter = warp & 3;
+    const int slice = (warp - 4) >> 2;
+    const int trow = quarter * 32 + lane;                 // this thread's row inside a tile
+    const uint32_t lane_sel = static_cast<uint32_t>(quarter * 32) << 16;
+    const float hb0 = p.hb[0], hb1 = p.hb[1];
+    uint32_t use = 0;
+    uint32_t a0[32];
+    float dn[NP], dc[NP];
+    auto load_a0 = [&](int64_t tile_) {
+      const int64_t row_ = tile_ * BM + trow;
+#pragma unroll
+      for (int e = 0; e < 32; ++e) a0[e] = 0u;
+#pragma unroll
+      for (int t = 0; t < NP; ++t) dn[t] = 0.0f;
+      if (row_ >= p.rows) return;
+      const float4* src = reinterpret_cast<const float4*>(p.x + row_ * 256 + slice * 64);
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const float4 f = __ldg(src + e);
+        a0[2 * e] = pack_bf16x2(f.x, f.y);
+        a0[2 * e + 1] = pack_bf16x2(f.z, f.w);
+        const int j = slice * 64 + 4 * e;
+#pragma unroll
+        for (int t = 0; t < NP; ++t) {
+          const float4 w = *reinterpret_cast<const float4*>(t < LC ? cw_s + t * 256 + j : hw_s + (t - LC) * 384 + j);
+          dn[t] = fmaf(f.x, w.x, dn[t]); dn[t] = fmaf(f.y, w.y, dn[t]);
+          dn[t] = fmaf(f.z, w.z, dn[t]); dn[t] = fmaf(f.w, w.w, dn[t]);
+        }
+      }
+    };
+    // cross recurrence + heads for one finished tile: run by the slice-0 warp of each quarter once the other three
+    // warps of the quarter have published their partial dots (named barrier 1 + quarter, 128 threads)
+    auto finish = [&](int64_t tile_) {
+      if (slice != 0) {
+        __threadfence_block();
+        asm volatile("bar.arrive %0, 128;" ::"r"(1 + quarter) : "memory");
+        return;
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + quarter) : "memory");
+      float s[NP + 2];
+#pragma unroll
+      for (int t = 0; t < NP + 2; ++t)
+        s[t] = (part[(t * 4 + 0) * 128 + trow] + part[(t * 4 + 1) * 128 + trow]) +
+               (part[(t * 4 + 2) * 128 + trow] + part[(t * 4 + 3) * 128 + trow]);
+      float a = 1.0f;
+#pragma unroll
+      for (int l = 0; l < LC; ++l) a += fmaf(a, s[l], const_s[l]);
+      const float zr = fmaf(a, s[LC], const_s[LC]) + s[NP] + hb0;
+      const float zc = fmaf(a, s[LC + 1], const_s[LC + 1]) + s[NP + 1] + hb1;
+      const int64_t row_ = tile_ * BM + trow;
+      if (row_ < p.rows) {
+        p.rating[row_] = zr;
+        p.ctr[row_] = 1.0f / (1.0f + expf(-zc));
+      }
+    };
+    if (n_my > 0) load_a0(cta);
+    for (int64_t i = 0; i < n_my; ++i) {
+      const int64_t tile = cta + i * ncta;
+      __syncwarp();
+      {
+        uint32_t (&r0)[16] = reinterpret_cast<uint32_t (&)[16]>(a0[0]);
+        uint32_t (&r1)[16] = reinterpret_cast<uint32_t (&)[16]>(a0[16]);
+        tmem_st_32x32_x16(tmem_base + slice * 32 + lane_sel, r0);
+        tmem_st_32x32_x16(tmem_base + slice * 32 + 16 + lane_sel, r1);
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_ready);
+      if (i > 0) finish(tile - ncta);          // the previous tile's rows, while this tile's layer 0 runs
+#pragma unroll
+      for (int t = 0; t < NP; ++t) dc[t] = dn[t];
+      if (i + 1 < n_my) load_a0(tile + ncta);
+
+      // layer 0: 256 accumulator columns, 64 per warp -> bias, relu, bf16 -> A operand of layer 1
+      mbar_wait(acc_ready, use & 1u);
+      ++use;
+      tc_fence_after_sync();
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        const int col0 = slice * 64 + c * 32;
+        float v[32];
+        __syncwarp();
+        tmem_ld_32x32(tmem_base + C::DCOL(0) + col0 + lane_sel, v);
+        const float* bs = bias_s + col0;
+        uint32_t r[16];
+#pragma unroll
+        for (int e = 0; e < 32; e += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(bs + e);
+          r[e / 2] = pack_bf16x2(fmaxf(v[e] + b4.x, 0.0f), fmaxf(v[e + 1] + b4.y, 0.0f));
+          r[e / 2 + 1] = pack_bf16x2(fmaxf(v[e + 2] + b4.z, 0.0f), fmaxf(v[e + 3] + b4.w, 0.0f));
+        }
+        tmem_st_32x32_x16(tmem_base + (col0 >> 1) + lane_sel, r);
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_ready);
+
+      // layer 1: 128 columns, 32 per warp -> bias, relu, dotted with the deep part of both heads
+      mbar_wait(acc_ready, use & 1u);
+      ++use;
+      tc_fence_after_sync();
+      {
+        const int col0 = slice * 32;
+        float v[32];
+        __syncwarp();
+        tmem_ld_32x32(tmem_base + C::DCOL(1) + col0 + lane_sel, v);
+        const float* bs = bias_s + 256 + col0;
+        const float* wr = hw_s + 256 + col0;
+        const float* wc = hw_s + 384 + 256 + col0;
+        float dr = 0.0f, dq = 0.0f;
+#pragma unroll
+        for (int e = 0; e < 32; e += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(bs + e);
+          const float4 r4 = *reinterpret_cast<const float4*>(wr + e);
+          const float4 c4 = *reinterpret_cast<const float4*>(wc + e);
+          const float y0 = fmaxf(v[e] + b4.x, 0.0f), y1 = fmaxf(v[e + 1] + b4.y, 0.0f);
+          const float y2 = fmaxf(v[e + 2] + b4.z, 0.0f), y3 = fmaxf(v[e + 3] + b4.w, 0.0f);
+          dr = fmaf(y0, r4.x, dr); dr = fmaf(y1, r4.y, dr); dr = fmaf(y2, r4.z, dr); dr = fmaf(y3, r4.w, dr);
+          dq = fmaf(y0, c4.x, dq); dq = fmaf(y1, c4.y, dq); dq = fmaf(y2, c4.z, dq); dq = fmaf(y3, c4.w, dq);
+        }
+#pragma unroll
+        for (int t = 0; t < NP; ++t) part[(t * 4 + slice) * 128 + trow] = dc[t];
+        part[(NP * 4 + slice) * 128 + trow] = dr;
+        part[((NP + 1) * 4 + slice) * 128 + trow] = dq;
+      }
+      // the next tile's A0 (columns [0,128)) does not overlap this tile's last accumulator ([128,256)), which is
+      // fully read above; `part` is re-written only after every warp has passed the next tile's layer-0 barrier,
+      // which needs the slice-0 warps' arrival, made after their finish()
+    }
+    if (n_my > 0) finish(cta + (n_my - 1) * ncta);
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int LC>
+void launch_deep_heads(const ChainMaps& maps, const DeepHeadsParams& p, cudaStream_t st) {
+  static std::once_flag once[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::call_once(once[dev & 63], [] {
+    cudaFuncSetAttribute(deep_heads_kernel<LC>, cudaFuncAttributeMaxDynamicSharedMemorySize, deep_heads_smem<LC>());
+  });
+  const int64_t ntiles = (p.rows + BM - 1) / BM;
+  const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(ntiles, rs::sm_count())));
+  rs::ProfScope prof(RS_PROF_RANK, st);
+  deep_heads_kernel<LC><<<grid, NTHREADS, deep_heads_smem<LC>(), st>>>(maps, p);
+  RS_LAUNCH_CHECK();
+}
+
+bool use_fused_heads() {
+  const char* e = getenv("RS_FUSED_HEADS");
+  return !(e && e[0] == '0');
+}
+
 }  // namespace
 
 struct rs_ranker {
@@ -744,7 +1042,7 @@ struct rs_ranker {
   uint16_t* wts = nullptr;      // all bf16 kernels, [out][in] each: user tower, item tower, deep
   float* f32 = nullptr;         // biases (user 576, item 576, deep 384), cross_w [L,256], cross_b [L,256], head_w [2,384], head_b [2]
   size_t off_w[2][4], off_dw[2];
-  size_t off_b[2][4], off_db[2], off_cw, off_cb, off_hw, off_hb;
+  size_t off_b[2][4], off_db[2], off_cw, off_cb, off_hw, off_hb, off_const;
   ChainMaps tower_maps, deep_maps;
 };
 
@@ -805,6 +1103,7 @@ extern "C" int rs_ranker_create(const DLTensor* user_table, const DLTensor* item
     h->off_cb = fb; fb += (size_t)L * 256;
     h->off_hw = fb; fb += 2 * 384;
     h->off_hb = fb; fb += 4;
+    h->off_const = fb; fb += 8;
     RS_CUDA(cudaMalloc(&h->wts, wb * sizeof(uint16_t)));
     RS_CUDA(cudaMalloc(&h->f32, fb * sizeof(float)));
     RS_CUDA(cudaMemset(h->f32, 0, fb * sizeof(float)));
@@ -839,6 +1138,9 @@ extern "C" int rs_ranker_create(const DLTensor* user_table, const DLTensor* item
     }
     copy_in(h->f32 + h->off_hw, head_w, 2 * 384 * 4, st);
     copy_in(h->f32 + h->off_hb, head_b, 2 * 4, st);
+    ranker_consts_kernel<<<1, 32, 0, st>>>(h->f32 + h->off_cw, h->f32 + h->off_cb, h->f32 + h->off_hw, static_cast<int>(L),
+                                           h->f32 + h->off_const);
+    RS_LAUNCH_CHECK();
     RS_CUDA(cudaStreamSynchronize(st));
     *out = h.release();
   });
@@ -873,10 +1175,13 @@ static int ranker_forward_impl(rs_ranker* h, const DLTensor* user_rows, const DL
     require_aligned16(data_ptr<float>(combined), "combined");
     if (B == 0) return;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    uint16_t* x_bf16 = nullptr;   // [B, 256] bf16 copy of the tower outputs: the deep net's input
-    float* deep_out = nullptr;    // [B, 128]
-    RS_CUDA(cudaMallocAsync(&x_bf16, sizeof(uint16_t) * (size_t)B * 256, st));
-    RS_CUDA(cudaMallocAsync(&deep_out, sizeof(float) * (size_t)B * 128, st));
+    const bool fused = use_fused_heads();   // default: deep chain + cross + heads in one kernel
+    uint16_t* x_bf16 = nullptr;   // unfused path only: [B, 256] bf16 copy of the tower outputs, the deep net's input
+    float* deep_out = nullptr;    // unfused path only: [B, 128]
+    if (!fused) {
+      RS_CUDA(cudaMallocAsync(&x_bf16, sizeof(uint16_t) * (size_t)B * 256, st));
+      RS_CUDA(cudaMallocAsync(&deep_out, sizeof(float) * (size_t)B * 128, st));
+    }
     try {
       ChainParams p{};
       p.n_prob = 2;
@@ -907,11 +1212,33 @@ static int ranker_forward_impl(rs_ranker* h, const DLTensor* user_rows, const DL
         }
         pr.y_f32 = data_ptr<float>(combined) + s * 128;
         pr.ld_f32 = 256;
-        pr.y_bf16 = x_bf16 + s * 128;
+        pr.y_bf16 = fused ? nullptr : x_bf16 + s * 128;
         pr.ld_bf16 = 256;
       }
       if (use_tower_pp()) launch_tower_pp(h->tower_maps, p, st);
       else launch_chain<CfgTower>(h->tower_maps, p, st);
+      if (fused) {
+        DeepHeadsParams q{};
+        q.rows = B;
+        q.x = data_ptr<float>(combined);
+        for (int l = 0; l < 2; ++l) q.bias[l] = h->f32 + h->off_db[l];
+        q.cw = h->f32 + h->off_cw;
+        q.cb = h->f32 + h->off_cb;
+        q.hw = h->f32 + h->off_hw;
+        q.hb = h->f32 + h->off_hb;
+        q.consts = h->f32 + h->off_const;
+        q.rating = data_ptr<float>(rating);
+        q.ctr = data_ptr<float>(ctr);
+        switch (h->cross_layers) {
+          case 0: launch_deep_heads<0>(h->deep_maps, q, st); break;
+          case 1: launch_deep_heads<1>(h->deep_maps, q, st); break;
+          case 2: launch_deep_heads<2>(h->deep_maps, q, st); break;
+          case 3: launch_deep_heads<3>(h->deep_maps, q, st); break;
+          case 4: launch_deep_heads<4>(h->deep_maps, q, st); break;
+          default: RS_CHECK(false, "the fused ranker supports up to 4 cross layers");
+        }
+        return;
+      }
       ChainParams d{};
       d.n_prob = 1;
       d.act[0] = d.act[1] = RS_ACT_RELU;
@@ -941,12 +1268,12 @@ static int ranker_forward_impl(rs_ranker* h, const DLTensor* user_rows, const DL
       }
       RS_LAUNCH_CHECK();
     } catch (...) {
-      cudaFreeAsync(x_bf16, st);
-      cudaFreeAsync(deep_out, st);
+      if (x_bf16) cudaFreeAsync(x_bf16, st);
+      if (deep_out) cudaFreeAsync(deep_out, st);
       throw;
     }
-    cudaFreeAsync(x_bf16, st);
-    cudaFreeAsync(deep_out, st);
+    if (x_bf16) cudaFreeAsync(x_bf16, st);
+    if (deep_out) cudaFreeAsync(deep_out, st);
   });
 }
 

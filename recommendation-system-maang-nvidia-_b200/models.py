@@ -196,6 +196,13 @@ class DeepCrossNetwork:
         self.cross_weights = [self._cross_w[i].unsqueeze(1) for i in range(w.shape[0])]
         self.cross_biases = [self._cross_b[i] for i in range(w.shape[0])]
 
+    def _cross(self, D: int):
+        """The stacked [L, D] cross kernels / biases; with zero cross layers the width comes from the input."""
+        if self._cross_w.shape[0] == 0 and int(self._cross_w.shape[1]) != D:
+            z = torch.zeros((0, D), dtype=torch.float32, device=self._device)
+            self._set_cross(z, z.clone())
+        return self._cross_w, self._cross_b
+
     def set_cross_weights(self, cross_w: Sequence[np.ndarray], cross_b: Sequence[np.ndarray]):
         w = np.stack([np.asarray(x, dtype=np.float32).reshape(-1) for x in cross_w]) if len(cross_w) else \
             np.zeros((0, 0), dtype=np.float32)
@@ -213,7 +220,7 @@ class DeepCrossNetwork:
             if layer.kernel is None:
                 layer.build(D if i == 0 else self.deep_layers[i - 1], seed=20 + i)
         out = torch.empty((B, D + self.deep_layers[-1]), dtype=torch.float32, device=inputs.device)
-        ops.dcn_cross(inputs, self._cross_w, self._cross_b, out=out[:, :D])          # src/models.py:38-44
+        ops.dcn_cross(inputs, *self._cross(D), out=out[:, :D])                      # src/models.py:38-44
         Sequential(self.deep_nets)(inputs, out=out[:, D:])                           # :46-48, concat :50
         return out
 
@@ -301,6 +308,7 @@ class _FusedRanker:
         dw = [l.wt_bf16() for l in dcn.deep_nets]
         db = [l.bias for l in dcn.deep_nets]
         hw, hb = model._heads_packed()
+        dcn._cross(2 * model.config.embedding_dim)
         keep = []
 
         def arr(objs):
@@ -373,7 +381,7 @@ class MultiTaskModel:
         rows_u = enc.user_lookup(features["user_id"])
         rows_i = enc.item_lookup(features["movie_id"])
         B = int(rows_u.shape[0])
-        if self.precision == "bf16" and B >= 128:
+        if self.precision == "bf16" and B >= 1:
             return self._call_bf16(rows_u, rows_i)
         # the towers write straight into the two halves of the DCN input: the concat (:128) is free
         combined = torch.empty((B, 2 * E), dtype=torch.float32, device=self.device)
@@ -400,6 +408,7 @@ class MultiTaskModel:
         cfg = self.config
         fused = (E == 128 and list(cfg.user_tower_dims) == [256, 128, 64] and list(cfg.item_tower_dims) == [256, 128, 64]
                  and list(dcn.deep_layers) == [256, 128] and int(rows_i.shape[0]) == B)
+        dcn._cross(D)
         if fused and int(dcn._cross_w.shape[1]) == 256:
             if getattr(self, "_ranker", None) is None:
                 self._ranker = _FusedRanker(self)

@@ -86,3 +86,37 @@ def test_multitask_forward_bf16_mode(rs):
     a = m.encoder({"user_id": [uv[3]]})["user_embedding"]
     b = m32.encoder({"user_id": [uv[3]]})["user_embedding"]
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("cross_layers", [0, 1, 3, 4])
+def test_fused_deep_cross_heads_kernel(rs, cross_layers, monkeypatch):
+    """deep_heads_kernel (deep chain + closed-form cross recurrence + heads in one launch) against the fp64 oracle and
+    against the three-kernel path it replaces (RS_FUSED_HEADS=0): same bf16 operands, so the two CUDA paths differ only
+    by fp32 re-association (<= 1e-5 of the output scale).  Batch sizes cover <1 tile, ragged tiles and >1 tile per SM."""
+    from oracle.models import MultiTaskModel as OMT
+    cfg = rs.ModelConfig()
+    cfg.cross_layers = cross_layers
+    w = rs.synth.make_weights(cfg, 500, 300, seed=20 + cross_layers)
+    # non-trivial cross biases, so the c_l constants of the closed form are exercised
+    rng = np.random.default_rng(5)
+    w["cross_b"] = [(0.05 * rng.standard_normal(b.shape)).astype(np.float32) for b in w["cross_b"]]
+    uv, iv = rs.synth.make_vocab(500), rs.synth.make_vocab(300)
+    m = rs.MultiTaskModel(cfg, uv, iv, {}, precision="bf16")
+    rs.load_weights(m, w)
+    oracle = OMT(w, uv, iv, np.float64)
+    for B in (1, 77, 129, 1000, 128 * 148 * 2 + 5):
+        ur, ir = rs.synth.make_ids(rng, 500, B), rs.synth.make_ids(rng, 300, B)
+        feats = {"user_id": dev(ur), "movie_id": dev(ir)}
+        monkeypatch.setenv("RS_FUSED_HEADS", "1")
+        fused = {k_: v.clone() for k_, v in m(feats).items()}
+        monkeypatch.setenv("RS_FUSED_HEADS", "0")
+        unfused = m(feats)
+        want = oracle.rank_rows(ur, ir)
+        for k_ in ("rating_prediction", "ctr_prediction"):
+            scale = np.abs(want[k_]).max()
+            got = fused[k_].cpu().numpy().astype(np.float64)
+            assert got.shape == want[k_].shape
+            assert np.abs(got - want[k_]).max() <= 1e-2 * scale, (k_, B)
+            assert (fused[k_] - unfused[k_]).abs().max().item() <= 1e-5 * scale, (k_, B)
+        assert torch.equal(fused["user_embedding"], unfused["user_embedding"])
+        assert torch.equal(fused["item_embedding"], unfused["item_embedding"])
