@@ -35,6 +35,18 @@ constexpr int EPI_WARPS = 16;
 constexpr int NTHREADS = 128 + EPI_WARPS * 32;
 constexpr int MAX_L = 4;
 
+// a_ready / acc_ready hand-offs: the chain is strictly serial per tile, so every wait blocks
+#ifndef RS_CHAIN_SPIN
+#define RS_CHAIN_SPIN 0   // measured: no difference on B200 (the hand-off cost is not wake-up latency)
+#endif
+__device__ __forceinline__ void chain_wait(uint64_t* bar, uint32_t parity) {
+#if RS_CHAIN_SPIN
+  mbar_wait_spin(bar, parity);
+#else
+  mbar_wait(bar, parity);
+#endif
+}
+
 struct CfgTower {
   static constexpr int L = 4;
   static constexpr bool GATHER = true;
@@ -87,6 +99,21 @@ struct ChainProblem {
   int64_t ld_f32;
   uint16_t* y_bf16;      // [rows, N_last] or nullptr
   int64_t ld_bf16;
+  // tower_pp_kernel only, for the fused ranker (all nullptr otherwise):
+  //  * y_il16: bf16 copy of the output in the lane-interleaved layout deep_heads_kernel loads its A operand from.
+  //    16-byte chunk c (8 features) of row (tile T, quarter q, lane) is uint4 number ((T*4 + q)*32 + c)*32 + lane, so
+  //    one 128-bit access per lane is a contiguous 512 bytes per warp on both the writing and the reading side.
+  //  * dots: fp32 dot products of this problem's 128 output columns (still in registers, full precision) with its
+  //    slice of the cross kernels and head rows -- the x0 . w_l, x0 . head terms of the DCN cross stack.  Per row and
+  //    per (problem, column half) h = 2*problem + half: float number (((T*4 + q)*4 + h)*6 + t)*32 + lane,
+  //    t = 0..3 cross layer, 4 rating head, 5 ctr head.
+  uint16_t* y_il16;
+  int il_chunk0;         // first 16-byte chunk of this problem's columns (0 for the user tower, 16 for the item tower)
+  float* dots;
+  int dots_h0;           // 2 * problem
+  const float* dot_cw;   // cross kernels, already offset to this problem's first column; row stride 256
+  int n_cross;
+  const float* dot_hw;   // head rows, already offset to this problem's first column; row stride 384
 };
 
 struct ChainParams {
@@ -156,7 +183,7 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
       for (int64_t i = 0; i < n_my; ++i) {
 #pragma unroll
         for (int l = 0; l < C::L; ++l, ++use) {
-          mbar_wait(a_ready, use & 1u);
+          chain_wait(a_ready, use & 1u);
           tc_fence_after_sync();
           const uint32_t idesc = umma_idesc_bf16_f32(BM, C::N(l));
 #pragma unroll
@@ -230,7 +257,7 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
         const int N = C::N(l);
         const int slices = N >= 128 ? 4 : 2;
         const int cols = N / slices;                       // accumulator columns per warp: 64, 32 or 32
-        mbar_wait(acc_ready, use & 1u);
+        chain_wait(acc_ready, use & 1u);
         tc_fence_after_sync();
         if (slice < slices && !(p.debug & 1)) {
 #pragma unroll 1
@@ -313,7 +340,8 @@ tower_pp_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* wsm = base;
   float* bias_s = reinterpret_cast<float*>(base + w_off<C>(C::L));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + b_off<C>(C::L));
+  float* dotw_s = bias_s + b_off<C>(C::L);   // [6][128]: cross kernels 0..3 (zero beyond n_cross), rating head, ctr head
+  uint64_t* bars = reinterpret_cast<uint64_t*>(dotw_s + 6 * 128);
   uint64_t* wfull = bars;
   uint64_t* a_ready = bars + 1;      // [2]
   uint64_t* acc_ready = bars + 3;    // [2]
@@ -340,6 +368,11 @@ tower_pp_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
 #pragma unroll
   for (int l = 0; l < C::L; ++l)
     for (int i = threadIdx.x; i < C::N(l); i += NTHREADS) bias_s[b_off<C>(l) + i] = pr.bias[l] ? pr.bias[l][i] : 0.0f;
+  if (pr.dots)
+    for (int i = threadIdx.x; i < 6 * 128; i += NTHREADS) {
+      const int t = i >> 7, j = i & 127;
+      dotw_s[i] = t < 4 ? (t < pr.n_cross ? pr.dot_cw[t * 256 + j] : 0.0f) : pr.dot_hw[(t - 4) * 384 + j];
+    }
   if (warp == 1) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
@@ -371,7 +404,7 @@ tower_pp_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
           for (int slot = 0; slot < 2; ++slot) {
             if (r >= n_slot[slot]) continue;
             const uint32_t R = tmem_base + slot * 256;
-            mbar_wait(&a_ready[slot], use[slot] & 1u);
+            chain_wait(&a_ready[slot], use[slot] & 1u);
             tc_fence_after_sync();
             if (step <= 1) {          // L1 half: A0 [R, R+64) x W1 rows [128*step, +128), K = 128
               const uint32_t idesc = umma_idesc_bf16_f32(BM, 128);
@@ -463,8 +496,9 @@ tower_pp_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
         const int layer = step <= 1 ? 0 : step - 1;
         const int bias0 = b_off<C>(layer) + (step == 1 ? 128 : 0);
         const int dst_col = step == 0 ? 192 : step == 1 ? 0 : step == 2 ? 192 : 64;   // A1a, A1b, A2, A3
-        mbar_wait(&acc_ready[slot], use & 1u);
+        chain_wait(&acc_ready[slot], use & 1u);
         tc_fence_after_sync();
+        float dacc[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};   // last step only: this thread's share of pr.dots
 #pragma unroll 1
         for (int c = 0; c < per_warp / 32; ++c) {
           const int col0 = half * per_warp + c * 32;
@@ -477,30 +511,62 @@ tower_pp_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
             const float4 b4 = *reinterpret_cast<const float4*>(bs + e);
             v[e] += b4.x; v[e + 1] += b4.y; v[e + 2] += b4.z; v[e + 3] += b4.w;
           }
-          if (p.act[layer] == RS_ACT_RELU) {
-#pragma unroll
-            for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], 0.0f);
-          }
           if (step < 4) {
             uint32_t rr[16];
+            if (p.act[layer] == RS_ACT_RELU) {
 #pragma unroll
-            for (int e = 0; e < 16; ++e) rr[e] = pack_bf16x2(v[2 * e], v[2 * e + 1]);
-            tmem_st_32x32_x16(R + dst_col + (col0 >> 1), rr);
-          } else if (row < pr.rows) {
-            if (pr.y_f32) {
-              float* dst = pr.y_f32 + row * pr.ld_f32 + col0;
+              for (int e = 0; e < 16; ++e) rr[e] = pack_bf16x2_relu(v[2 * e], v[2 * e + 1]);
+            } else {
 #pragma unroll
-              for (int e = 0; e < 32; e += 8)
-                st_global_256(dst + e, v[e], v[e + 1], v[e + 2], v[e + 3], v[e + 4], v[e + 5], v[e + 6], v[e + 7]);
+              for (int e = 0; e < 16; ++e) rr[e] = pack_bf16x2(v[2 * e], v[2 * e + 1]);
             }
-            if (pr.y_bf16) {
-              uint16_t* dst = pr.y_bf16 + row * pr.ld_bf16 + col0;
+            tmem_st_32x32_x16(R + dst_col + (col0 >> 1), rr);
+          } else {
+            if (p.act[layer] == RS_ACT_RELU) {
 #pragma unroll
-              for (int e = 0; e < 32; e += 16)
-                st_global_256(static_cast<void*>(dst + e), pack_bf16x2(v[e], v[e + 1]), pack_bf16x2(v[e + 2], v[e + 3]),
-                              pack_bf16x2(v[e + 4], v[e + 5]), pack_bf16x2(v[e + 6], v[e + 7]),
-                              pack_bf16x2(v[e + 8], v[e + 9]), pack_bf16x2(v[e + 10], v[e + 11]),
-                              pack_bf16x2(v[e + 12], v[e + 13]), pack_bf16x2(v[e + 14], v[e + 15]));
+              for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], 0.0f);
+            }
+            if (pr.y_il16) {   // rows past the end of the batch land in the scratch's padding
+              uint4* dst = reinterpret_cast<uint4*>(pr.y_il16) +
+                           ((tile * 4 + quarter) * 32 + pr.il_chunk0 + (col0 >> 3)) * 32 + lane;
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                dst[e * 32] = make_uint4(pack_bf16x2(v[8 * e], v[8 * e + 1]), pack_bf16x2(v[8 * e + 2], v[8 * e + 3]),
+                                         pack_bf16x2(v[8 * e + 4], v[8 * e + 5]), pack_bf16x2(v[8 * e + 6], v[8 * e + 7]));
+            }
+            if (pr.dots) {
+              const float* ws = dotw_s + col0;
+#pragma unroll
+              for (int e = 0; e < 32; e += 4) {
+#pragma unroll
+                for (int t = 0; t < 6; ++t) {
+                  const float4 w4 = *reinterpret_cast<const float4*>(ws + t * 128 + e);
+                  dacc[t] = fmaf(v[e], w4.x, dacc[t]); dacc[t] = fmaf(v[e + 1], w4.y, dacc[t]);
+                  dacc[t] = fmaf(v[e + 2], w4.z, dacc[t]); dacc[t] = fmaf(v[e + 3], w4.w, dacc[t]);
+                }
+              }
+              if (c == per_warp / 32 - 1) {
+                float* dst = pr.dots + (((tile * 4 + quarter) * 4 + pr.dots_h0 + half) * 6) * 32 + lane;
+#pragma unroll
+                for (int t = 0; t < 6; ++t) dst[t * 32] = dacc[t];
+              }
+            }
+            if (row < pr.rows) {
+              if (pr.y_f32) {
+                float* dst = pr.y_f32 + row * pr.ld_f32 + col0;
+#pragma unroll
+                for (int e = 0; e < 32; e += 8)
+                  st_global_256(dst + e, v[e], v[e + 1], v[e + 2], v[e + 3], v[e + 4], v[e + 5], v[e + 6], v[e + 7]);
+              }
+              if (pr.y_bf16) {
+                uint16_t* dst = pr.y_bf16 + row * pr.ld_bf16 + col0;
+#pragma unroll
+                for (int e = 0; e < 32; e += 16)
+                  st_global_256(static_cast<void*>(dst + e), pack_bf16x2(v[e], v[e + 1]), pack_bf16x2(v[e + 2], v[e + 3]),
+                                pack_bf16x2(v[e + 4], v[e + 5]), pack_bf16x2(v[e + 6], v[e + 7]),
+                                pack_bf16x2(v[e + 8], v[e + 9]), pack_bf16x2(v[e + 10], v[e + 11]),
+                                pack_bf16x2(v[e + 12], v[e + 13]), pack_bf16x2(v[e + 14], v[e + 15]));
+              }
             }
           }
         }
@@ -526,7 +592,7 @@ void launch_tower_pp(const ChainMaps& maps, const ChainParams& p, cudaStream_t s
   int dev = 0;
   cudaGetDevice(&dev);
   std::call_once(once[dev & 63], [] {
-    cudaFuncSetAttribute(tower_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, chain_smem<CfgTower>());
+    cudaFuncSetAttribute(tower_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, chain_smem<CfgTower>() + 6 * 128 * 4);
   });
   int64_t max_tiles = 0;
   for (int i = 0; i < p.n_prob; ++i) max_tiles = std::max<int64_t>(max_tiles, (p.prob[i].rows + BM - 1) / BM);
@@ -535,7 +601,7 @@ void launch_tower_pp(const ChainMaps& maps, const ChainParams& p, cudaStream_t s
   int grid = static_cast<int>(std::min<int64_t>((max_tiles + 1) / 2 * p.n_prob, sms - (sms % p.n_prob)));
   grid = std::max(grid, p.n_prob);
   rs::ProfScope prof(RS_PROF_RANK, st);
-  tower_pp_kernel<<<grid, NTHREADS, chain_smem<CfgTower>(), st>>>(maps, p);
+  tower_pp_kernel<<<grid, NTHREADS, chain_smem<CfgTower>() + 6 * 128 * 4, st>>>(maps, p);
   RS_LAUNCH_CHECK();
 }
 
@@ -738,28 +804,30 @@ __global__ void __launch_bounds__(256) cross_heads_kernel(const float* __restric
 // ------------------------------------------------------------------------------------------------
 // deep_heads_kernel: the deep chain, the DCN-v1 cross stack and both heads in ONE kernel (src/models.py:38-48 and
 // 119-120,131).  Same tcgen05 pipeline as chain_tc_kernel<CfgDeep>; what is fused around it:
-//   * the layer-0 A operand is packed from the fp32 tower outputs x0 = combined[B,256] (no bf16 copy in HBM), and
-//     while those values are in registers each thread accumulates, in fp32, its 64-feature share of the dots
-//     P_l = x0 . w_l (l < LC), Hr = x0 . head_r[:256], Hc = x0 . head_c[:256];
+//   * the layer-0 A operand comes from tower_pp_kernel's lane-interleaved bf16 copy of x0 (ChainProblem::y_il16):
+//     eight fully coalesced 128-bit loads per thread that land directly in the registers tcgen05.st takes, issued a
+//     whole tile ahead and not touched until then, so their latency and the HBM burst are off the critical path;
+//   * the x0 dots of the cross stack, P_l = x0 . w_l (l < LC), Hr = x0 . head_r[:256], Hc = x0 . head_c[:256], were
+//     taken in fp32 by the tower kernel while x0 was in its registers (ChainProblem::dots, four partials per row);
 //   * the last epilogue dots the fp32 deep output (bias + relu applied) with head_r[256:], head_c[256:] instead of
 //     writing it;
 //   * one thread per row then runs the cross recurrence in closed form.  x_{l+1} = x0 (x_l . w_l) + b_l + x_l keeps
 //     x_l = a_l x0 + c_l with c_l = b_0 + .. + b_{l-1}, so  s_l = a_l P_l + c_l . w_l,  a_{l+1} = a_l + s_l, and
 //     rating = a_L Hr + c_L . head_r[:256] + deep . head_r[256:] + bias  (ctr likewise, through a sigmoid).
-//     The c_l dots are per-model constants computed once per CTA.
-// Per sample the kernel reads 1 KB (x0) and writes 8 bytes.
+//     The c_l dots are per-model constants (ranker_consts_kernel).
+// Per sample the kernel reads 512 + 96 bytes and writes 8.
 // ------------------------------------------------------------------------------------------------
 struct DeepHeadsParams {
   int64_t rows;
-  const float* x;          // fp32 [rows, 256], row stride 256
+  const uint16_t* x_il16;  // bf16 x0, lane-interleaved (ChainProblem::y_il16)
+  const float* dots;       // fp32 partial dots of x0 (ChainProblem::dots)
   const float* bias[2];
-  const float* cw;         // [LC, 256]
-  const float* cb;         // [LC, 256]
   const float* hw;         // [2, 384]
   const float* hb;         // [2]
   const float* consts;     // [LC + 2]: c_l . w_l for l < LC, c_L . head_r[:256], c_L . head_c[:256]  (ranker_consts_kernel)
   float* rating;           // [rows]
   float* ctr;              // [rows]
+  long long* trace;        // RS_CHAIN_TRACE=1: clock64 stamps of CTA 0 ([tile][16]: 0-7 epilogue warp 4, 8-11 MMA issuer)
 };
 
 // per-model constants of the closed-form cross recurrence, computed once when the ranker handle is created
@@ -790,21 +858,20 @@ __global__ void ranker_consts_kernel(const float* __restrict__ cw, const float* 
 
 template <int LC>
 constexpr int deep_heads_smem() {
-  return w_off<CfgDeep>(2) + (384 + LC * 256 + 768 + 8 + (LC + 4) * 512) * 4 + 256 + 1024;
+  return w_off<CfgDeep>(2) + (384 + 256 + 8 + (LC + 4) * 512) * 4 + 256 + 1024;
 }
 
 template <int LC>
 __global__ void __launch_bounds__(NTHREADS, 1)
 deep_heads_kernel(const __grid_constant__ ChainMaps maps, const DeepHeadsParams p) {
   using C = CfgDeep;
-  constexpr int NP = LC + 2;   // dots taken over x0 per row
+  constexpr int NP = LC + 2;   // dots over x0 per row
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* wsm = base;
   float* bias_s = reinterpret_cast<float*>(base + w_off<C>(2));
-  float* cw_s = bias_s + 384;                 // [LC][256]
-  float* hw_s = cw_s + LC * 256;              // [2][384]
-  float* const_s = hw_s + 768;                // [LC] c_l . w_l, then c_L . head_r, c_L . head_c
+  float* hd_s = bias_s + 384;                 // [2][128]: the deep part of the two head rows
+  float* const_s = hd_s + 256;                // [LC] c_l . w_l, then c_L . head_r, c_L . head_c
   float* part = const_s + 8;                  // [(NP + 2)][4 slices][128 rows]
   uint64_t* bars = reinterpret_cast<uint64_t*>(part + (LC + 4) * 512);
   uint64_t* wfull = bars;
@@ -831,13 +898,12 @@ deep_heads_kernel(const __grid_constant__ ChainMaps maps, const DeepHeadsParams 
     const float* b = p.bias[l];
     bias_s[i] = b ? b[i - l * 256] : 0.0f;
   }
-  for (int i = threadIdx.x; i < LC * 256; i += NTHREADS) cw_s[i] = p.cw[i];
-  for (int i = threadIdx.x; i < 768; i += NTHREADS) hw_s[i] = p.hw[i];
+  for (int i = threadIdx.x; i < 256; i += NTHREADS) hd_s[i] = p.hw[(i >> 7) * 384 + 256 + (i & 127)];
+  if (threadIdx.x < NP) const_s[threadIdx.x] = p.consts[threadIdx.x];
   if (warp == 1) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
-  if (threadIdx.x < NP) const_s[threadIdx.x] = p.consts[threadIdx.x];
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -859,8 +925,9 @@ deep_heads_kernel(const __grid_constant__ ChainMaps maps, const DeepHeadsParams 
       for (int64_t i = 0; i < n_my; ++i) {
 #pragma unroll
         for (int l = 0; l < 2; ++l, ++use) {
-          mbar_wait(a_ready, use & 1u);
+          chain_wait(a_ready, use & 1u);
           tc_fence_after_sync();
+          if (p.trace && cta == 0 && i < 8) p.trace[i * 16 + 8 + 2 * l] = clock64();
           const uint32_t idesc = umma_idesc_bf16_f32(BM, C::N(l));
 #pragma unroll
           for (int k = 0; k < 16; ++k) {
@@ -868,6 +935,7 @@ deep_heads_kernel(const __grid_constant__ ChainMaps maps, const DeepHeadsParams 
             umma_bf16_ts(tmem_base + C::DCOL(l), tmem_base + C::ACOL(l) + k * 8, db, idesc, k > 0 ? 1u : 0u);
           }
           umma_commit(acc_ready);
+          if (p.trace && cta == 0 && i < 8) p.trace[i * 16 + 9 + 2 * l] = clock64();
         }
       }
     }
@@ -878,35 +946,23 @@ deep_heads_kernel(const __grid_constant__ ChainMaps maps, const DeepHeadsParams 
     const uint32_t lane_sel = static_cast<uint32_t>(quarter * 32) << 16;
     const float hb0 = p.hb[0], hb1 = p.hb[1];
     uint32_t use = 0;
-    uint32_t a0[32];
+    // One tile ahead, in registers: the A operand (this row's 64-feature slice, 8 x 128 bits) and the tower kernel's
+    // dot partial number `slice` of this row.  Nothing reads them before the next iteration.
+    uint4 a0[8];
     float dn[NP], dc[NP];
-    auto load_a0 = [&](int64_t tile_) {
-      const int64_t row_ = tile_ * BM + trow;
+    auto load_next = [&](int64_t tile_) {
+      const bool valid = tile_ * BM + trow < p.rows;
+      const uint4* src = reinterpret_cast<const uint4*>(p.x_il16) + ((tile_ * 4 + quarter) * 32 + slice * 8) * 32 + lane;
 #pragma unroll
-      for (int e = 0; e < 32; ++e) a0[e] = 0u;
+      for (int e = 0; e < 8; ++e) a0[e] = valid ? __ldg(src + e * 32) : make_uint4(0u, 0u, 0u, 0u);
+      const float* dsrc = p.dots + (((tile_ * 4 + quarter) * 4 + slice) * 6) * 32 + lane;
 #pragma unroll
-      for (int t = 0; t < NP; ++t) dn[t] = 0.0f;
-      if (row_ >= p.rows) return;
-      const float4* src = reinterpret_cast<const float4*>(p.x + row_ * 256 + slice * 64);
-#pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        const float4 f = __ldg(src + e);
-        a0[2 * e] = pack_bf16x2(f.x, f.y);
-        a0[2 * e + 1] = pack_bf16x2(f.z, f.w);
-        const int j = slice * 64 + 4 * e;
-#pragma unroll
-        for (int t = 0; t < NP; ++t) {
-          const float4 w = *reinterpret_cast<const float4*>(t < LC ? cw_s + t * 256 + j : hw_s + (t - LC) * 384 + j);
-          dn[t] = fmaf(f.x, w.x, dn[t]); dn[t] = fmaf(f.y, w.y, dn[t]);
-          dn[t] = fmaf(f.z, w.z, dn[t]); dn[t] = fmaf(f.w, w.w, dn[t]);
-        }
-      }
+      for (int t = 0; t < NP; ++t) dn[t] = valid ? __ldg(dsrc + (t < LC ? t : 4 + t - LC) * 32) : 0.0f;
     };
     // cross recurrence + heads for one finished tile: run by the slice-0 warp of each quarter once the other three
     // warps of the quarter have published their partial dots (named barrier 1 + quarter, 128 threads)
     auto finish = [&](int64_t tile_) {
-      if (slice != 0) {
-        __threadfence_block();
+      if (slice != 0) {   // bar.arrive orders this thread's earlier shared-memory writes before the barrier completes
         asm volatile("bar.arrive %0, 128;" ::"r"(1 + quarter) : "memory");
         return;
       }
@@ -927,28 +983,43 @@ deep_heads_kernel(const __grid_constant__ ChainMaps maps, const DeepHeadsParams 
         p.ctr[row_] = 1.0f / (1.0f + expf(-zc));
       }
     };
-    if (n_my > 0) load_a0(cta);
+    if (n_my > 0) load_next(cta);
     for (int64_t i = 0; i < n_my; ++i) {
       const int64_t tile = cta + i * ncta;
+      const bool tr = p.trace && cta == 0 && i < 8 && warp == 4 && lane == 0;
+      auto stamp = [&](int k) { if (tr) p.trace[i * 16 + k] = clock64(); };
       __syncwarp();
+      stamp(0);
       {
         uint32_t (&r0)[16] = reinterpret_cast<uint32_t (&)[16]>(a0[0]);
-        uint32_t (&r1)[16] = reinterpret_cast<uint32_t (&)[16]>(a0[16]);
+        uint32_t (&r1)[16] = reinterpret_cast<uint32_t (&)[16]>(a0[4]);
         tmem_st_32x32_x16(tmem_base + slice * 32 + lane_sel, r0);
         tmem_st_32x32_x16(tmem_base + slice * 32 + 16 + lane_sel, r1);
       }
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(a_ready);
-      if (i > 0) finish(tile - ncta);          // the previous tile's rows, while this tile's layer 0 runs
+      stamp(1);
 #pragma unroll
       for (int t = 0; t < NP; ++t) dc[t] = dn[t];
-      if (i + 1 < n_my) load_a0(tile + ncta);
+      // the previous tile's rows, while this tile's layer 0 runs; before the loads below are issued, so that the
+      // fence in front of the named barrier has nothing outstanding to wait for
+      if (i > 0) finish(tile - ncta);
+      stamp(12);
+      if (i + 1 < n_my) load_next(tile + ncta);   // in flight for the whole tile
+      stamp(2);
+      if (i + 2 < n_my && warp == 4 && lane == 0) {   // and the tile after that on its way from HBM to L2
+        const int64_t t2 = tile + 2 * ncta;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.x_il16 + t2 * (BM * 256)), "r"(BM * 256 * 2) : "memory");
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.dots + t2 * (BM * 24)), "r"(BM * 24 * 4) : "memory");
+      }
+      stamp(3);
 
       // layer 0: 256 accumulator columns, 64 per warp -> bias, relu, bf16 -> A operand of layer 1
-      mbar_wait(acc_ready, use & 1u);
+      chain_wait(acc_ready, use & 1u);
       ++use;
       tc_fence_after_sync();
+      stamp(4);
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
         const int col0 = slice * 64 + c * 32;
@@ -960,27 +1031,29 @@ deep_heads_kernel(const __grid_constant__ ChainMaps maps, const DeepHeadsParams 
 #pragma unroll
         for (int e = 0; e < 32; e += 4) {
           const float4 b4 = *reinterpret_cast<const float4*>(bs + e);
-          r[e / 2] = pack_bf16x2(fmaxf(v[e] + b4.x, 0.0f), fmaxf(v[e + 1] + b4.y, 0.0f));
-          r[e / 2 + 1] = pack_bf16x2(fmaxf(v[e + 2] + b4.z, 0.0f), fmaxf(v[e + 3] + b4.w, 0.0f));
+          r[e / 2] = pack_bf16x2_relu(v[e] + b4.x, v[e + 1] + b4.y);
+          r[e / 2 + 1] = pack_bf16x2_relu(v[e + 2] + b4.z, v[e + 3] + b4.w);
         }
         tmem_st_32x32_x16(tmem_base + (col0 >> 1) + lane_sel, r);
       }
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(a_ready);
+      stamp(5);
 
       // layer 1: 128 columns, 32 per warp -> bias, relu, dotted with the deep part of both heads
-      mbar_wait(acc_ready, use & 1u);
+      chain_wait(acc_ready, use & 1u);
       ++use;
       tc_fence_after_sync();
+      stamp(6);
       {
         const int col0 = slice * 32;
         float v[32];
         __syncwarp();
         tmem_ld_32x32(tmem_base + C::DCOL(1) + col0 + lane_sel, v);
         const float* bs = bias_s + 256 + col0;
-        const float* wr = hw_s + 256 + col0;
-        const float* wc = hw_s + 384 + 256 + col0;
+        const float* wr = hd_s + col0;
+        const float* wc = hd_s + 128 + col0;
         float dr = 0.0f, dq = 0.0f;
 #pragma unroll
         for (int e = 0; e < 32; e += 4) {
@@ -997,9 +1070,10 @@ deep_heads_kernel(const __grid_constant__ ChainMaps maps, const DeepHeadsParams 
         part[(NP * 4 + slice) * 128 + trow] = dr;
         part[((NP + 1) * 4 + slice) * 128 + trow] = dq;
       }
+      stamp(7);
       // the next tile's A0 (columns [0,128)) does not overlap this tile's last accumulator ([128,256)), which is
       // fully read above; `part` is re-written only after every warp has passed the next tile's layer-0 barrier,
-      // which needs the slice-0 warps' arrival, made after their finish()
+      // whose MMA needs the slice-0 warps' layer-1 operand arrival, made after their finish()
     }
     if (n_my > 0) finish(cta + (n_my - 1) * ncta);
   }
@@ -1175,9 +1249,17 @@ static int ranker_forward_impl(rs_ranker* h, const DLTensor* user_rows, const DL
     require_aligned16(data_ptr<float>(combined), "combined");
     if (B == 0) return;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const bool fused = use_fused_heads();   // default: deep chain + cross + heads in one kernel
     uint16_t* x_bf16 = nullptr;   // unfused path only: [B, 256] bf16 copy of the tower outputs, the deep net's input
     float* deep_out = nullptr;    // unfused path only: [B, 128]
+    const bool pp = use_tower_pp();
+    const bool fused = use_fused_heads() && pp;   // default: deep chain + cross + heads in one kernel (needs tower_pp's extra outputs)
+    const int64_t tiles = (B + BM - 1) / BM;
+    uint16_t* x_il16 = nullptr;   // fused path: bf16 x0, lane-interleaved       (ChainProblem::y_il16)
+    float* dots = nullptr;        // fused path: fp32 partial cross / head dots   (ChainProblem::dots)
+    if (fused) {
+      RS_CUDA(cudaMallocAsync(&x_il16, sizeof(uint16_t) * (size_t)tiles * BM * 256, st));
+      RS_CUDA(cudaMallocAsync(&dots, sizeof(float) * (size_t)tiles * BM * 24, st));
+    }
     if (!fused) {
       RS_CUDA(cudaMallocAsync(&x_bf16, sizeof(uint16_t) * (size_t)B * 256, st));
       RS_CUDA(cudaMallocAsync(&deep_out, sizeof(float) * (size_t)B * 128, st));
@@ -1214,21 +1296,32 @@ static int ranker_forward_impl(rs_ranker* h, const DLTensor* user_rows, const DL
         pr.ld_f32 = 256;
         pr.y_bf16 = fused ? nullptr : x_bf16 + s * 128;
         pr.ld_bf16 = 256;
+        pr.y_il16 = x_il16;
+        pr.il_chunk0 = s * 16;
+        pr.dots = dots;
+        pr.dots_h0 = 2 * s;
+        pr.dot_cw = h->f32 + h->off_cw + s * 128;
+        pr.n_cross = h->cross_layers;
+        pr.dot_hw = h->f32 + h->off_hw + s * 128;
       }
-      if (use_tower_pp()) launch_tower_pp(h->tower_maps, p, st);
+      if (pp) launch_tower_pp(h->tower_maps, p, st);
       else launch_chain<CfgTower>(h->tower_maps, p, st);
       if (fused) {
         DeepHeadsParams q{};
         q.rows = B;
-        q.x = data_ptr<float>(combined);
+        q.x_il16 = x_il16;
+        q.dots = dots;
         for (int l = 0; l < 2; ++l) q.bias[l] = h->f32 + h->off_db[l];
-        q.cw = h->f32 + h->off_cw;
-        q.cb = h->f32 + h->off_cb;
         q.hw = h->f32 + h->off_hw;
         q.hb = h->f32 + h->off_hb;
         q.consts = h->f32 + h->off_const;
         q.rating = data_ptr<float>(rating);
         q.ctr = data_ptr<float>(ctr);
+        const char* tr_env = getenv("RS_CHAIN_TRACE");
+        if (tr_env && tr_env[0] == '1') {
+          RS_CUDA(cudaMalloc(&q.trace, 8 * 16 * sizeof(long long)));
+          RS_CUDA(cudaMemsetAsync(q.trace, 0, 8 * 16 * sizeof(long long), st));
+        }
         switch (h->cross_layers) {
           case 0: launch_deep_heads<0>(h->deep_maps, q, st); break;
           case 1: launch_deep_heads<1>(h->deep_maps, q, st); break;
@@ -1236,6 +1329,19 @@ static int ranker_forward_impl(rs_ranker* h, const DLTensor* user_rows, const DL
           case 3: launch_deep_heads<3>(h->deep_maps, q, st); break;
           case 4: launch_deep_heads<4>(h->deep_maps, q, st); break;
           default: RS_CHECK(false, "the fused ranker supports up to 4 cross layers");
+        }
+        cudaFreeAsync(x_il16, st);
+        cudaFreeAsync(dots, st);
+        if (q.trace) {   // debugging aid: per-tile phase stamps of CTA 0, relative to the first one
+          long long host[8 * 16];
+          RS_CUDA(cudaStreamSynchronize(st));
+          RS_CUDA(cudaMemcpy(host, q.trace, sizeof(host), cudaMemcpyDeviceToHost));
+          cudaFree(q.trace);
+          for (int t = 0; t < 8 && host[t * 16]; ++t) {
+            fprintf(stderr, "deep_heads tile %d:", t);
+            for (int k = 0; k < 13; ++k) fprintf(stderr, " %lld", host[t * 16 + k] ? host[t * 16 + k] - host[0] : -1);
+            fprintf(stderr, "\n");
+          }
         }
         return;
       }
@@ -1268,6 +1374,8 @@ static int ranker_forward_impl(rs_ranker* h, const DLTensor* user_rows, const DL
       }
       RS_LAUNCH_CHECK();
     } catch (...) {
+      if (x_il16) cudaFreeAsync(x_il16, st);
+      if (dots) cudaFreeAsync(dots, st);
       if (x_bf16) cudaFreeAsync(x_bf16, st);
       if (deep_out) cudaFreeAsync(deep_out, st);
       throw;
