@@ -218,6 +218,8 @@ def main():
     assert sidx.local.ntotal == sidx.row_end - sidx.row_begin
     local_search = sidx.local.search
     sidx._local_search = lambda q_, k_: local_search(q_, k_, id_base=sidx.row_begin, mode=args.mode)
+    local_deferred = sidx.local.search_deferred
+    sidx._local_deferred = lambda q_, k_, out: local_deferred(q_, k_, id_base=sidx.row_begin, mode=args.mode, out=out)
 
     gq = torch.Generator(device=device)
     gq.manual_seed(3999)

@@ -181,6 +181,15 @@ int rs_index_reconstruct(const rs_index_t* h, int64_t i0, DLTensor* out, void* s
  */
 int rs_index_search(rs_index_t* h, const DLTensor* q, int k, int64_t id_base, int mode, DLTensor* D,
                     DLTensor* I, void* stream);
+/*
+ * The same search without any host synchronisation, for callers that have more device work to queue behind it
+ * (the sharded catalog's exchange + merge, BASELINE config 3).  Device tensors only.  need_exact: int32 [nq];
+ * need_exact[i] = 1 marks a query whose tensor-mode candidate set could not be verified: row i of D / I is
+ * then NOT final and the caller must search that query again with mode RS_EXACT_FP32 (rs_index_search does
+ * this itself, at the price of a stream synchronise).  Exact mode never sets a flag.
+ */
+int rs_index_search_deferred(rs_index_t* h, const DLTensor* q, int k, int64_t id_base, int mode,
+                             DLTensor* D, DLTensor* I, DLTensor* need_exact, void* stream);
 
 /* tensor-mode bookkeeping: queries of the last / all tensor-mode searches that failed the filter's
  * verification and were re-run on the exact scan (results are identical either way) */
@@ -199,6 +208,8 @@ int rs_matvec(const DLTensor* items, const DLTensor* user, DLTensor* out, void* 
  * K7. Merge of per-shard top-k lists after the all-gather (new in this build; BASELINE
  * config 3).  Dparts: f32 [nparts, nq, k]; Iparts: int64 [nparts, nq, k] (global ids,
  * -1 = padding); D: f32 [nq, k]; I: int64 [nq, k]; device.  Order (score desc, id asc).
+ * Each part is a contiguous [nq, k] block; the stride between parts is free, so the parts can be
+ * slices of one exchange buffer that carries scores, ids and flags of a shard side by side.
  */
 int rs_topk_merge(const DLTensor* Dparts, const DLTensor* Iparts, DLTensor* D, DLTensor* I,
                   void* stream);

@@ -121,6 +121,7 @@ struct ChainParams {
   int n_prob;            // 1 or 2 (both towers in one launch)
   int act[MAX_L];
   int debug;             // perf experiments: 1 = epilogue skips TMEM traffic, 2 = issuer skips the MMAs
+  long long* trace;      // RS_CHAIN_TRACE=1 (tower_pp_kernel): clock64 stamps of block 0, slot 0, warp 4 ([round][16])
 };
 
 template <class C>
@@ -476,6 +477,9 @@ tower_pp_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
     for (int64_t r = 0; r < n_slot; ++r) {
       const int64_t tile = cta + (2 * r + slot) * ncta;
       const int64_t row = tile * BM + quarter * 32 + lane;
+      const bool tr = p.trace && blockIdx.x == 0 && r < 8 && warp == 4 && lane == 0;
+      auto stamp = [&](int k) { if (tr) p.trace[r * 16 + k] = clock64(); };
+      stamp(0);
       {
         uint32_t (&r0)[16] = reinterpret_cast<uint32_t (&)[16]>(a0[0]);
         uint32_t (&r1)[16] = reinterpret_cast<uint32_t (&)[16]>(a0[16]);
@@ -485,7 +489,9 @@ tower_pp_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&a_ready[slot]);
+        stamp(1);
         if (r + 1 < n_slot) load_a0(tile + 2 * ncta);
+        stamp(2);
       }
 #pragma unroll
       for (int step = 0; step < 5; ++step, ++use) {
@@ -498,6 +504,7 @@ tower_pp_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
         const int dst_col = step == 0 ? 192 : step == 1 ? 0 : step == 2 ? 192 : 64;   // A1a, A1b, A2, A3
         chain_wait(&acc_ready[slot], use & 1u);
         tc_fence_after_sync();
+        stamp(3 + 2 * step);
         float dacc[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};   // last step only: this thread's share of pr.dots
 #pragma unroll 1
         for (int c = 0; c < per_warp / 32; ++c) {
@@ -575,6 +582,7 @@ tower_pp_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
           __syncwarp();
           if (lane == 0) mbar_arrive(&a_ready[slot]);
         }
+        stamp(4 + 2 * step);
       }
     }
   }
@@ -600,6 +608,24 @@ void launch_tower_pp(const ChainMaps& maps, const ChainParams& p, cudaStream_t s
   // two tiles per CTA at a time: do not spread fewer than 2 tiles per CTA over more CTAs than needed
   int grid = static_cast<int>(std::min<int64_t>((max_tiles + 1) / 2 * p.n_prob, sms - (sms % p.n_prob)));
   grid = std::max(grid, p.n_prob);
+  const char* tr_env = getenv("RS_CHAIN_TRACE");
+  if (tr_env && tr_env[0] == '1') {   // debugging aid: per-round phase stamps, relative to the first one
+    ChainParams q = p;
+    RS_CUDA(cudaMalloc(&q.trace, 8 * 16 * sizeof(long long)));
+    RS_CUDA(cudaMemsetAsync(q.trace, 0, 8 * 16 * sizeof(long long), st));
+    tower_pp_kernel<<<grid, NTHREADS, chain_smem<CfgTower>() + 6 * 128 * 4, st>>>(maps, q);
+    RS_LAUNCH_CHECK();
+    long long host[8 * 16];
+    RS_CUDA(cudaStreamSynchronize(st));
+    RS_CUDA(cudaMemcpy(host, q.trace, sizeof(host), cudaMemcpyDeviceToHost));
+    cudaFree(q.trace);
+    for (int t = 0; t < 8 && host[t * 16 + 1]; ++t) {
+      fprintf(stderr, "tower_pp round %d:", t);
+      for (int k = 0; k < 13; ++k) fprintf(stderr, " %lld", host[t * 16 + k] ? host[t * 16 + k] - host[0] : -1);
+      fprintf(stderr, "\n");
+    }
+    return;
+  }
   rs::ProfScope prof(RS_PROF_RANK, st);
   tower_pp_kernel<<<grid, NTHREADS, chain_smem<CfgTower>() + 6 * 128 * 4, st>>>(maps, p);
   RS_LAUNCH_CHECK();

@@ -169,11 +169,12 @@ struct KeySource {
   const float* Dp;       // B
   const int64_t* Ip;     // B
   int64_t nq;
+  int64_t part_ld_D, part_ld_I;   // B: elements between consecutive parts (nq * k when the parts are packed)
   __device__ __forceinline__ uint64_t load(int64_t qi, int p, int P, int r, int k) const {
     if (keys) return keys[((int64_t)qi * P + p) * k + r];
-    const int64_t o = ((int64_t)p * nq + qi) * k + r;
-    const int64_t id = Ip[o];
-    return id < 0 ? kEmptyKey : pack_key(Dp[o], static_cast<uint32_t>(id));
+    const int64_t o = qi * k + r;
+    const int64_t id = Ip[p * part_ld_I + o];
+    return id < 0 ? kEmptyKey : pack_key(Dp[p * part_ld_D + o], static_cast<uint32_t>(id));
   }
 };
 
@@ -532,6 +533,41 @@ int rs_index_search(rs_index_t* h, const DLTensor* q, int k, int64_t id_base, in
   });
 }
 
+int rs_index_search_deferred(rs_index_t* h, const DLTensor* q, int k, int64_t id_base, int mode, DLTensor* D, DLTensor* I,
+                             DLTensor* need_exact, void* stream) {
+  return rs::guard([&] {
+    using namespace rs;
+    RS_CHECK(h != nullptr, "index is NULL");
+    require(q, "q", 2, kDLFloat, 32);
+    require(D, "D", 2, kDLFloat, 32);
+    require(I, "I", 2, kDLInt, 64);
+    require(need_exact, "need_exact", 1, kDLInt, 32);
+    RS_CHECK(q->shape[1] == h->d, "q must be [nq, d] with d == index dimension");
+    RS_CHECK(k >= 1 && k <= 1024, "k must be in [1, 1024]");
+    const int64_t nq = q->shape[0];
+    RS_CHECK(D->shape[0] == nq && D->shape[1] == k && I->shape[0] == nq && I->shape[1] == k, "D and I must be [nq, k]");
+    RS_CHECK(need_exact->shape[0] == nq && (nq <= 1 || stride_of(need_exact, 0) == 1), "need_exact must be a contiguous [nq] tensor");
+    RS_CHECK(mode == RS_EXACT_FP32 || mode == RS_TENSOR_BF16 || mode == RS_AUTO, "unknown mode");
+    RS_CHECK(on_device(q) && on_device(D) && on_device(I) && on_device(need_exact), "the deferred search takes CUDA tensors only");
+    if (nq == 0) return;
+    DeviceGuard g(h->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    RS_CHECK(is_compact(q), "q must be contiguous");
+    RS_CHECK(q->device.device_id == h->device, "q is on a different device than the index");
+    require_aligned16(data_ptr<float>(q), "q");
+    const bool supported = tensor_path_supported(h, nq, k);
+    RS_CHECK(mode != RS_TENSOR_BF16 || supported, "tensor mode is not applicable to this shape (needs d=128, k<=128, ntotal>=65536)");
+    if (mode != RS_EXACT_FP32 && supported) {
+      search_tensor_device(h, data_ptr<float>(q), nq, k, id_base, data_ptr<float>(D), row_stride_2d(D, "D"),
+                           data_ptr<int64_t>(I), row_stride_2d(I, "I"), st, data_ptr<int>(need_exact));
+    } else {
+      search_exact_device(h, data_ptr<float>(q), nq, k, id_base, data_ptr<float>(D), row_stride_2d(D, "D"),
+                          data_ptr<int64_t>(I), row_stride_2d(I, "I"), st);
+      RS_CUDA(cudaMemsetAsync(data_ptr<int>(need_exact), 0, sizeof(int) * (size_t)nq, st));
+    }
+  });
+}
+
 int rs_normalize_l2(DLTensor* x, void* stream) {
   return rs::guard([&] {
     using namespace rs;
@@ -598,11 +634,17 @@ int rs_topk_merge(const DLTensor* Dparts, const DLTensor* Iparts, DLTensor* D, D
     const int64_t P = Dparts->shape[0], nq = Dparts->shape[1], k = Dparts->shape[2];
     RS_CHECK(Iparts->shape[0] == P && Iparts->shape[1] == nq && Iparts->shape[2] == k, "Iparts must match Dparts");
     RS_CHECK(D->shape[0] == nq && D->shape[1] == k && I->shape[0] == nq && I->shape[1] == k, "D and I must be [nq, k]");
-    RS_CHECK(is_compact(Dparts) && is_compact(Iparts), "Dparts / Iparts must be contiguous");
+    // each part is a packed [nq, k] block; the parts themselves may be strided (slices of one exchange buffer)
+    auto part_ld = [&](const DLTensor* t) -> int64_t {
+      if (!t->strides) return nq * k;
+      RS_CHECK((k <= 1 || t->strides[2] == 1) && (nq <= 1 || t->strides[1] == k) && (P <= 1 || t->strides[0] >= nq * k),
+               "Dparts / Iparts: each part must be a contiguous [nq, k] block");
+      return P <= 1 ? nq * k : t->strides[0];
+    };
     RS_CHECK(P >= 1 && P <= 4096, "nparts must be in [1, 4096]");
     if (nq == 0) return;
     sm_count();
-    KeySource src{nullptr, data_ptr<float>(Dparts), data_ptr<int64_t>(Iparts), nq};
+    KeySource src{nullptr, data_ptr<float>(Dparts), data_ptr<int64_t>(Iparts), nq, part_ld(Dparts), part_ld(Iparts)};
     merge_dispatch(src, nq, static_cast<int>(P), static_cast<int>(k), 0, data_ptr<float>(D), row_stride_2d(D, "D"),
                    data_ptr<int64_t>(I), row_stride_2d(I, "I"), static_cast<cudaStream_t>(stream));
   });

@@ -30,8 +30,11 @@ namespace rs {
 void search_exact_device(rs_index* h, const float* q, int64_t nq, int k, int64_t id_base, float* D, int64_t ldD,
                          int64_t* I, int64_t ldI, cudaStream_t st);
 // tensor-core pre-filter + exact re-score (tc_filter.cu); same results as search_exact_device
+// need_exact == nullptr: flagged queries are re-run on the exact scan before returning (one stream synchronise).
+// need_exact != nullptr (device int32 [nq]): nothing is synchronised; need_exact[i] = 1 marks rows of D / I that are NOT
+// final and that the caller must re-search with search_exact_device.
 void search_tensor_device(rs_index* h, const float* q, int64_t nq, int k, int64_t id_base, float* D, int64_t ldD,
-                          int64_t* I, int64_t ldI, cudaStream_t st);
+                          int64_t* I, int64_t ldI, cudaStream_t st, int* need_exact = nullptr);
 // every low-precision score of the tensor path, out [nq, ntotal] (validation of the tcgen05 tiles)
 void tensor_scores_debug(rs_index* h, const float* q, int64_t nq, float* out, cudaStream_t st);
 // true when the tensor path is applicable to this shape (d, k, sizes)

@@ -573,8 +573,18 @@ bool tensor_path_supported(const rs_index* h, int64_t nq, int k) {
   return h->d == DK && k >= 1 && k <= 128 && h->ntotal >= 65536 && nq >= 1 && h->ntotal <= 0x7FFFFF00ll;
 }
 
+// flags layout of a search chunk: [0, nq) per-query "guess not verified", [nq_pad] their count, [nq_pad + 1] a staging
+// queue overran, [nq_pad + 2] records written (> rec_cap: the record list overran)
+__global__ void export_flags_kernel(const int* __restrict__ flags, int nq, int nq_pad, unsigned rec_cap,
+                                    int* __restrict__ need_exact) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq) return;
+  const bool all = flags[nq_pad + 1] != 0 || static_cast<unsigned>(flags[nq_pad + 2]) > rec_cap;
+  need_exact[i] = (all || flags[i] != 0) ? 1 : 0;
+}
+
 void search_tensor_device(rs_index* h, const float* q, int64_t nq, int k, int64_t id_base, float* D, int64_t ldD,
-                          int64_t* I, int64_t ldI, cudaStream_t st) {
+                          int64_t* I, int64_t ldI, cudaStream_t st, int* need_exact) {
   RS_CHECK(tensor_path_supported(h, nq, k), "tensor path does not apply to this shape");
   ensure_shadow(h, st);
   const int sms = sm_count();
@@ -659,6 +669,11 @@ void search_tensor_device(rs_index* h, const float* q, int64_t nq, int k, int64_
       select_rescore_kernel<<<cq, SEL_NT, 0, st>>>(ws.cand, ws.cnt, CAND_CAP, ws.thr, ws.eps2, qc, h->xb, k, id_base,
                                                    D + q0 * ldD, ldD, I + q0 * ldI, ldI, ws.flags, ws.flags + nq_pad);
       RS_LAUNCH_CHECK();
+    }
+    if (need_exact) {   // deferred: the caller resolves flagged queries (after its own exchange step)
+      export_flags_kernel<<<(cq + 255) / 256, 256, 0, st>>>(ws.flags, cq, nq_pad, rec_cap, need_exact + q0);
+      RS_LAUNCH_CHECK();
+      continue;
     }
     // step 5: the (rare) queries whose guess could not be verified go through the exact scan
     std::vector<int> flags(nq_pad + 4);

@@ -98,6 +98,30 @@ class IndexFlatIP:
                                              _lib.stream_ptr()))
         return D, I
 
+    def search_deferred(self, x: "torch.Tensor", k: int, *, mode: str = "auto", id_base: int = 0, out=None):
+        """search() without the host synchronisation: -> (D, I, need_exact int32 [n]).  Rows with need_exact == 1 are not
+        final; the caller re-searches those queries with mode="exact" (sharded.ShardedIndexFlatIP does, after its
+        exchange).  `out` = (D, I, need_exact) writes into caller-provided CUDA tensors (views of an exchange buffer)."""
+        _check_2d_f32(x, "x", self.d)
+        k = int(k)
+        if k < 1:
+            raise ValueError("k must be >= 1")
+        if isinstance(x, np.ndarray) or not x.is_cuda:
+            raise TypeError("search_deferred takes CUDA tensors")
+        x = x.contiguous()
+        n = x.shape[0]
+        if out is None:
+            out = (torch.empty((n, k), dtype=torch.float32, device=x.device),
+                   torch.empty((n, k), dtype=torch.int64, device=x.device),
+                   torch.zeros((n,), dtype=torch.int32, device=x.device))
+        D, I, F = out
+        if n == 0:
+            return D, I, F
+        xb, Db, Ib, Fb = _lib.dl(x), _lib.dl(D), _lib.dl(I), _lib.dl(F)
+        _lib.check(self._lib.rs_index_search_deferred(self._h, xb.ptr, k, int(id_base), _lib.mode_code(mode), Db.ptr, Ib.ptr,
+                                                      Fb.ptr, _lib.stream_ptr()))
+        return D, I, F
+
     def fallbacks(self):
         """(last, total) tensor-mode queries that were re-run on the exact scan (same results either way)."""
         a, b = ctypes.c_int64(0), ctypes.c_int64(0)

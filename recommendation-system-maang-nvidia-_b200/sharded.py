@@ -2,8 +2,8 @@
 
 One process per GPU.  Rank g holds the contiguous catalog rows [bounds[g], bounds[g+1]) in its own
 IndexFlatIP; queries are replicated.  A search is: local scan + local top-k (global row numbers via
-id_base) -> one all-gather of the [nq, k] (score, row) lists over NCCL/NVLink (G*nq*k*12 bytes, ~10 MB at
-G=8, nq=1024, k=100) -> on-device G-way merge (K7).  The tie-break (score desc, row asc) makes the merge
+id_base) -> ONE all-gather of each shard's [nq, k] scores, rows and per-query flags over NCCL/NVLink
+(G*nq*(12k+4) bytes, ~10 MB at G=8, nq=1024, k=100) -> on-device G-way merge (K7) straight out of the exchange buffer.  The tie-break (score desc, row asc) makes the merge
 independent of the shard order, so every rank ends with the same lists as a single-GPU search over the
 whole catalog -- bit for bit.
 
@@ -24,9 +24,22 @@ def shard_bounds(n_total: int, world: int) -> List[int]:
     return [n_total * g // world for g in range(world + 1)]
 
 
+def _round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+def exchange_layout(nq: int, k: int) -> Tuple[int, int, int]:
+    """Byte offsets of one shard's message in the fused exchange: scores f32 [nq,k] at 0, rows int64 [nq,k] at
+    off_I, need_exact int32 [nq] at off_F; `total` bytes per shard (16-byte multiples)."""
+    off_I = _round_up(nq * k * 4, 16)
+    off_F = off_I + nq * k * 8
+    return off_I, off_F, _round_up(off_F + nq * 4, 16)
+
+
 class ShardedIndexFlatIP:
     def __init__(self, d: int, n_total: int, group: Optional[dist.ProcessGroup] = None,
-                 local_index=None, local_search: Optional[Callable] = None, merge: Optional[Callable] = None):
+                 local_index=None, local_search: Optional[Callable] = None, merge: Optional[Callable] = None,
+                 local_deferred: Optional[Callable] = None):
         self.d = int(d)
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -34,15 +47,20 @@ class ShardedIndexFlatIP:
         self.bounds = shard_bounds(int(n_total), self.world)
         self.row_begin, self.row_end = self.bounds[self.rank], self.bounds[self.rank + 1]
         self.n_total = int(n_total)
+        self.fallbacks = 0          # queries re-searched exactly after the exchange (results identical either way)
         if local_search is None:
             from .index import IndexFlatIP
             from . import ops
             self.local = local_index if local_index is not None else IndexFlatIP(d)
             self._local_search = lambda q, k: self.local.search(q, k, id_base=self.row_begin)
+            self._local_exact = lambda q, k: self.local.search(q, k, mode="exact", id_base=self.row_begin)
+            self._local_deferred = lambda q, k, out: self.local.search_deferred(q, k, id_base=self.row_begin, out=out)
             self._merge = ops.topk_merge
         else:
             self.local = local_index
             self._local_search = local_search
+            self._local_exact = local_search
+            self._local_deferred = local_deferred
             self._merge = merge
 
     @property
@@ -55,11 +73,7 @@ class ShardedIndexFlatIP:
         if self.local.ntotal > self.row_end - self.row_begin:
             raise ValueError("more rows added than this rank's shard holds")
 
-    def search(self, q, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
-        """q: [nq, d] replicated on every rank -> (D [nq, k], I [nq, k] global rows), identical on every rank."""
-        Dl, Il = self._local_search(q, k)
-        if self.world == 1:
-            return Dl, Il
+    def _gather_merge(self, Dl: torch.Tensor, Il: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         nq, kk = int(Dl.shape[0]), int(Dl.shape[1])
         # rank-major concatenation along dim 0 (the layout both NCCL and gloo accept), viewed as [G, nq, k]
         Dg = torch.empty((self.world * nq, kk), dtype=Dl.dtype, device=Dl.device)
@@ -68,10 +82,47 @@ class ShardedIndexFlatIP:
         dist.all_gather_into_tensor(Ig, Il.contiguous(), group=self.group)
         return self._merge(Dg.view(self.world, nq, kk), Ig.view(self.world, nq, kk))
 
+    def search(self, q, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """q: [nq, d] replicated on every rank -> (D [nq, k], I [nq, k] global rows), identical on every rank.
+
+        With a deferred local search (the default on CUDA) a step is queued without any host synchronisation in the
+        middle: local search -> ONE all-gather of a byte buffer that carries each shard's scores, rows and need_exact
+        flags side by side -> merge straight out of that buffer.  Only then does the host look at the flags (the step's
+        one synchronisation); flagged queries -- the tensor path's rare unverified guesses, on any shard -- are
+        re-searched exactly on every shard and merged again."""
+        if self.world == 1:
+            return self._local_search(q, k)
+        if self._local_deferred is None:
+            return self._gather_merge(*self._local_search(q, k))
+        nq, k = int(q.shape[0]), int(k)
+        G = self.world
+        off_I, off_F, total = exchange_layout(nq, k)
+        dev = q.device if isinstance(q, torch.Tensor) else torch.device("cpu")
+        send = torch.empty((total,), dtype=torch.uint8, device=dev)
+        out = (send[:nq * k * 4].view(torch.float32).view(nq, k),
+               send[off_I:off_I + nq * k * 8].view(torch.int64).view(nq, k),
+               send[off_F:off_F + nq * 4].view(torch.int32))
+        self._local_deferred(q, k, out)
+        recv = torch.empty((G * total,), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(recv, send, group=self.group)
+        R = recv.view(G, total)
+        Dg = R[:, :nq * k * 4].view(torch.float32).view(G, nq, k)            # parts strided by `total` bytes
+        Ig = R[:, off_I:off_I + nq * k * 8].view(torch.int64).view(G, nq, k)
+        Fg = R[:, off_F:off_F + nq * 4].view(torch.int32)                    # [G, nq]
+        D, I = self._merge(Dg, Ig)
+        need = Fg.ne(0).any(dim=0)                                           # the same on every rank
+        if bool(need.any()):                                                 # the step's one host synchronisation
+            idx = need.nonzero().flatten()
+            sub = np.ascontiguousarray(q[idx.cpu().numpy()]) if isinstance(q, np.ndarray) else q[idx].contiguous()
+            De, Ie = self._gather_merge(*self._local_exact(sub, k))
+            D[idx], I[idx] = De, Ie
+            self.fallbacks += int(idx.numel())
+        return D, I
+
 
 def gather_bytes(world: int, nq: int, k: int) -> int:
-    """Bytes each rank receives in the exchange step (f32 score + i64 row per hit)."""
-    return world * nq * k * (4 + 8)
+    """Bytes each rank receives in the exchange step (f32 score + i64 row per hit, int32 flag per query)."""
+    return world * exchange_layout(nq, k)[2]
 
 
 class ShardedEmbedding:

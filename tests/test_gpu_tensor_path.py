@@ -145,3 +145,66 @@ def test_full_size_catalog_properties(rs):
         D2, I2 = index.search(q[i:i + 1].contiguous(), 10, mode="tensor")
         assert torch.equal(I1, I2) and torch.equal(D1, D2)
         assert torch.equal(I1[0], It[i, :10])
+
+
+def test_deferred_search_flags_exactly_what_the_synchronous_search_re_runs(rs):
+    """rs_index_search_deferred: no host synchronisation; rows with need_exact == 0 are final (bit-identical to the
+    oracle), rows with need_exact == 1 are the ones rs_index_search would have re-run on the exact scan."""
+    from oracle import flat_ip
+    xb = rs.synth.make_unit_rows(200_000, 128, 77)
+    q = rs.synth.make_unit_rows(300, 128, 91)
+    index = rs.IndexFlatIP(128)
+    index.add(dev(xb))
+    D, I, F = index.search_deferred(dev(q), 100)
+    assert F.dtype == torch.int32 and int(F.sum()) == 0
+    Dw, Iw = flat_ip.search_chain(xb, q, 100)
+    np.testing.assert_array_equal(I.cpu().numpy(), Iw)
+    np.testing.assert_array_equal(D.cpu().numpy(), Dw)
+    # exact mode and shapes outside the tensor path never flag
+    _, _, F = index.search_deferred(dev(q), 100, mode="exact")
+    assert int(F.sum()) == 0
+    # scores packed inside the filter margin: every query is flagged, and the exact re-search repairs it
+    rng = np.random.default_rng(10)
+    centre = rs.synth.make_unit_rows(1, 128, 13)
+    xb = (centre + 1e-4 * rng.standard_normal((80_000, 128))).astype(np.float32)
+    q9 = rs.synth.make_unit_rows(9, 128, 12)
+    index = rs.IndexFlatIP(128)
+    index.add(dev(xb))
+    D, I, F = index.search_deferred(dev(q9), 10, id_base=1000)
+    assert int(F.sum()) > 0
+    idx = F.nonzero().flatten()
+    D[idx], I[idx] = index.search(dev(q9)[idx].contiguous(), 10, mode="exact", id_base=1000)
+    Dw, Iw = flat_ip.search_chain(xb, q9, 10, id_base=1000)
+    np.testing.assert_array_equal(I.cpu().numpy(), Iw)
+    np.testing.assert_array_equal(D.cpu().numpy(), Dw)
+    # outputs may be views of one exchange buffer (what the sharded search passes)
+    from recsys_b200.sharded import exchange_layout
+    nq, k = 9, 10
+    off_I, off_F, total = exchange_layout(nq, k)
+    buf = torch.zeros((total,), dtype=torch.uint8, device="cuda")
+    out = (buf[:nq * k * 4].view(torch.float32).view(nq, k), buf[off_I:off_I + nq * k * 8].view(torch.int64).view(nq, k),
+           buf[off_F:off_F + nq * 4].view(torch.int32))
+    index.search_deferred(dev(q9), k, mode="exact", id_base=1000, out=out)
+    np.testing.assert_array_equal(out[1].cpu().numpy(), Iw)
+
+
+def test_topk_merge_reads_parts_out_of_a_strided_exchange_buffer(rs):
+    from oracle import flat_ip
+    from recsys_b200.sharded import exchange_layout
+    G, nq, k = 4, 9, 30
+    xb = rs.synth.make_unit_rows(6000, 64, 12)
+    q = rs.synth.make_unit_rows(nq, 64, 13)
+    bounds = np.linspace(0, 6000, G + 1).astype(int)
+    off_I, off_F, total = exchange_layout(nq, k)
+    recv = torch.zeros((G, total), dtype=torch.uint8, device="cuda")
+    for g, (a, b) in enumerate(zip(bounds[:-1], bounds[1:])):
+        Dl, Il = flat_ip.search_chain(np.ascontiguousarray(xb[a:b]), q, k, id_base=int(a))
+        recv[g, :nq * k * 4].view(torch.float32).view(nq, k).copy_(dev(Dl))
+        recv[g, off_I:off_I + nq * k * 8].view(torch.int64).view(nq, k).copy_(dev(Il))
+    Dg = recv[:, :nq * k * 4].view(torch.float32).view(G, nq, k)
+    Ig = recv[:, off_I:off_I + nq * k * 8].view(torch.int64).view(G, nq, k)
+    assert not Dg.is_contiguous()
+    D, I = rs.ops.topk_merge(Dg, Ig)
+    Dw, Iw = flat_ip.search_chain(xb, q, k)
+    np.testing.assert_array_equal(I.cpu().numpy(), Iw)
+    np.testing.assert_array_equal(D.cpu().numpy(), Dw)

@@ -52,6 +52,37 @@ def _worker(rank, world, port, n, nq, k, out_dir):
         np.testing.assert_array_equal(I.numpy(), Iw)
         np.testing.assert_array_equal(D.numpy(), Dw)
         np.save(os.path.join(out_dir, f"I_{rank}.npy"), I.numpy())
+
+        # the fused exchange (one all-gather of scores | rows | flags, merge out of the strided buffer, flagged queries
+        # re-searched after the exchange).  The stand-in for the deferred tensor-mode search returns GARBAGE for the
+        # queries it flags -- rank 1 flags query 2, the last rank flags query 5 -- so only the fallback can fix them.
+        bad = {1: [2], world - 1: [5]}
+
+        def local_deferred(qq, kk, out):
+            Dl, Il = local_search(qq, kk)
+            out[0].copy_(Dl)
+            out[1].copy_(Il)
+            out[2].zero_()
+            for i in bad.get(rank, []):
+                out[0][i] = 123.0
+                out[1][i] = lo
+                out[2][i] = 1
+
+        calls = []
+
+        def merge_strided(Dg, Ig):
+            calls.append((tuple(Dg.shape), Dg.stride(0), Ig.stride(0)))
+            return merge(Dg.contiguous(), Ig.contiguous())
+
+        fused = ShardedIndexFlatIP(64, n, local_search=local_search, merge=merge_strided, local_deferred=local_deferred)
+        D2, I2 = fused.search(q, k)
+        np.testing.assert_array_equal(I2.numpy(), Iw)
+        np.testing.assert_array_equal(D2.numpy(), Dw)
+        assert fused.fallbacks == len({i for v in bad.values() for i in v})
+        from recsys_b200.sharded import exchange_layout
+        off_I, off_F, total = exchange_layout(nq, k)
+        assert calls[0] == ((world, nq, k), total // 4, total // 8)      # parts are slices of the exchange buffer
+        assert off_I % 16 == 0 and total % 16 == 0 and off_F == off_I + nq * k * 8
     finally:
         dist.destroy_process_group()
 
@@ -74,7 +105,7 @@ def test_shard_bounds_cover_the_catalog():
             b = shard_bounds(n, g)
             assert b[0] == 0 and b[-1] == n and all(x <= y for x, y in zip(b, b[1:]))
             assert max(y - x for x, y in zip(b, b[1:])) - min(y - x for x, y in zip(b, b[1:])) <= 1
-    assert gather_bytes(8, 1024, 100) == 8 * 1024 * 100 * 12
+    assert gather_bytes(8, 1024, 100) == 8 * (1024 * 100 * 12 + 1024 * 4)
 
 
 def _emb_worker(rank, world, port, n_rows, batch):

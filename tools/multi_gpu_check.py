@@ -36,11 +36,30 @@ def main():
     Dw, Iw = full.search(q, k)
     sidx = ShardedIndexFlatIP(128, N)
     sidx.add_local(xb[sidx.row_begin:sidx.row_end].contiguous())
+    sd = sidx.local.search_deferred
     for mode in ("tensor", "exact"):
-        ls = sidx.local.search
-        sidx._local_search = lambda q_, k_, m=mode: ls(q_, k_, id_base=sidx.row_begin, mode=m)
+        # fused exchange: deferred local search -> one all-gather (scores | rows | flags) -> merge out of the buffer
+        sidx._local_deferred = lambda q_, k_, out, m=mode: sd(q_, k_, id_base=sidx.row_begin, mode=m, out=out)
         D, I = sidx.search(q, k)
         assert torch.equal(I, Iw) and torch.equal(D, Dw), f"rank {rank}: sharded {mode} search differs"
+    assert sidx.fallbacks == 0
+
+    # a shard that flags queries (and returns garbage for them) is repaired by the post-exchange exact re-search
+    def flagged(q_, k_, out):
+        sd(q_, k_, id_base=sidx.row_begin, out=out)
+        mine = [3 + rank, 100]
+        out[0][mine] = 9.0
+        out[1][mine] = sidx.row_begin
+        out[2][mine] = 1
+    sidx._local_deferred = flagged
+    D, I = sidx.search(q, k)
+    assert torch.equal(I, Iw) and torch.equal(D, Dw), f"rank {rank}: flagged queries were not repaired"
+    assert sidx.fallbacks == world + 1
+    # the two-collective path (no deferred search) stays available
+    sidx._local_deferred = None
+    D, I = sidx.search(q, k)
+    assert torch.equal(I, Iw) and torch.equal(D, Dw)
+    sidx._local_deferred = lambda q_, k_, out: sd(q_, k_, id_base=sidx.row_begin, out=out)
     # batch-1 (config 5)
     D1, I1 = sidx.search(q[:1].contiguous(), 10)
     assert torch.equal(I1, Iw[:1, :10])
