@@ -220,6 +220,7 @@ def main():
     sidx._local_search = lambda q_, k_: local_search(q_, k_, id_base=sidx.row_begin, mode=args.mode)
     local_deferred = sidx.local.search_deferred
     sidx._local_deferred = lambda q_, k_, out: local_deferred(q_, k_, id_base=sidx.row_begin, mode=args.mode, out=out)
+    sidx.shared_threshold = args.mode != "exact" and os.environ.get("RS_SHARED_THRESHOLD", "1") != "0"
 
     gq = torch.Generator(device=device)
     gq.manual_seed(3999)

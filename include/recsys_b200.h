@@ -191,6 +191,39 @@ int rs_index_search(rs_index_t* h, const DLTensor* q, int k, int64_t id_base, in
 int rs_index_search_deferred(rs_index_t* h, const DLTensor* q, int k, int64_t id_base, int mode,
                              DLTensor* D, DLTensor* I, DLTensor* need_exact, void* stream);
 
+/*
+ * Shared-threshold search of ONE SHARD of a catalog partitioned over several indexes / GPUs (BASELINE config 3).
+ * The tensor path filters with a per-query threshold guessed from a sample.  Guessed per shard, every shard keeps
+ * ~6.6 k candidates per query for k = 100; guessed once from the union of all shards' samples, the shards keep
+ * that many TOGETHER, and the price is one small extra exchange.  Protocol, per batch of queries, on every shard:
+ *   rs_index_shared_begin   sample pass; top[nq, R] = the R largest sample maxima of each query (any order)
+ *   (caller)                all-gather the tops -> tops[shards, nq, R]
+ *   rs_index_shared_finish  tau_q = the rank-th largest of the gathered values; filter; exact re-score.  D / I
+ *                           receive the shard's exact top-min(candidates, k) (padded with D = -FLT_MAX, I = -1),
+ *                           bound[q] = tau_q + eps_q of this shard, need_exact[q] = 1 on candidate-list overflow
+ *   (caller)                all-gather D, I, bound, need_exact; rs_topk_merge; rs_topk_verify
+ *   rs_topk_verify          need_exact[q] |= the merged list is short of k or its k-th score < max over shards of
+ *                           bound[q]: only then could a filtered-out row belong to the top-k, and the caller
+ *                           re-searches that query with RS_EXACT_FP32 on every shard.  Otherwise the merged list IS
+ *                           the exact top-k, bit-identical to a single-index search.
+ * rs_tensor_plan: for an index of `ntotal` rows of dimension d, whether the tensor path applies to (nq, k) and
+ * how many rows its sample covers; rs_tensor_threshold_rank: the rank to use for a sample covering the fraction
+ * rho of ALL rows (callers pass rank to finish and R >= min(rank, ...) to begin; R = rank is always enough).
+ * A session belongs to the stream it was begun on; finish (or rs_tc_session_free) releases it.  Device tensors.
+ */
+typedef struct rs_tc_session rs_tc_session_t;
+int rs_tensor_plan(int d, int64_t ntotal, int64_t nq, int k, int64_t* sampled_rows, int* supported);
+int rs_tensor_threshold_rank(int k, double rho, int* rank);
+int rs_index_shared_begin(rs_index_t* h, const DLTensor* q, int k, DLTensor* top, rs_tc_session_t** out,
+                          void* stream);
+int rs_index_shared_finish(rs_tc_session_t* s, const DLTensor* tops, int rank, int64_t id_base, DLTensor* D,
+                           DLTensor* I, DLTensor* need_exact, DLTensor* bound, void* stream);
+int rs_tc_session_free(rs_tc_session_t* s);
+/* D: f32 [nq, k], I: int64 [nq, k] merged lists; bounds: f32 [shards, nq]; flags: int32 [shards, nq] (rows of
+ * both may be strided slices of the exchange buffer); need_exact: int32 [nq] out */
+int rs_topk_verify(const DLTensor* D, const DLTensor* I, const DLTensor* bounds, const DLTensor* flags,
+                   DLTensor* need_exact, void* stream);
+
 /* tensor-mode bookkeeping: queries of the last / all tensor-mode searches that failed the filter's
  * verification and were re-run on the exact scan (results are identical either way) */
 int rs_index_fallbacks(const rs_index_t* h, int64_t* last, int64_t* total);

@@ -99,6 +99,12 @@ def load():
         "rs_index_reconstruct": [vp, i64, _DLP, vp],
         "rs_index_search": [vp, _DLP, i32, i64, i32, _DLP, _DLP, vp],
         "rs_index_search_deferred": [vp, _DLP, i32, i64, i32, _DLP, _DLP, _DLP, vp],
+        "rs_tensor_plan": [i32, i64, i64, i32, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int32)],
+        "rs_tensor_threshold_rank": [i32, ctypes.c_double, ctypes.POINTER(ctypes.c_int32)],
+        "rs_index_shared_begin": [vp, _DLP, i32, _DLP, ctypes.POINTER(ctypes.c_void_p), vp],
+        "rs_index_shared_finish": [vp, _DLP, i32, i64, _DLP, _DLP, _DLP, _DLP, vp],
+        "rs_tc_session_free": [vp],
+        "rs_topk_verify": [_DLP, _DLP, _DLP, _DLP, _DLP, vp],
         "rs_index_fallbacks": [vp, ctypes.POINTER(i64), ctypes.POINTER(i64)],
         "rs_debug_tensor_scores": [vp, _DLP, _DLP, vp],
         "rs_matvec": [_DLP, _DLP, _DLP, vp],
@@ -117,6 +123,7 @@ def load():
 EXPORTED = ["rs_version", "rs_last_error", "rs_launch_count", "rs_device_sm_count", "rs_gather_concat", "rs_a2a_count", "rs_a2a_scatter", "rs_hash_table_fill",
             "rs_dense_forward", "rs_dense_forward_bf16", "rs_gather_bf16", "rs_chain_forward_bf16", "rs_ranker_create", "rs_ranker_free", "rs_ranker_forward", "rs_ranker_forward_rows", "rs_dcn_cross_forward", "rs_heads_forward", "rs_normalize_l2", "rs_index_create",
             "rs_index_free", "rs_index_add", "rs_index_ntotal", "rs_index_dim", "rs_index_reconstruct", "rs_index_search", "rs_index_search_deferred",
+            "rs_tensor_plan", "rs_tensor_threshold_rank", "rs_index_shared_begin", "rs_index_shared_finish", "rs_tc_session_free", "rs_topk_verify",
             "rs_index_fallbacks", "rs_debug_tensor_scores",
             "rs_matvec", "rs_topk_merge", "rs_prof_enable", "rs_prof_read"]
 

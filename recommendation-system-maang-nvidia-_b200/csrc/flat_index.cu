@@ -164,6 +164,23 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
 // merge of sorted lists.  Source A: packed keys [nq][P][k] (rows local to the index).
 // Source B: (score, id) pairs [P][nq][k] (global ids, -1 = padding) after an all-gather.
 // ------------------------------------------------------------------------------------------------
+// after the merge of a shared-threshold search: a query needs the exact re-search iff a shard overflowed, the merged
+// list is short of k, or its k-th score does not clear every shard's bound (tau + eps)
+__global__ void verify_topk_kernel(const float* __restrict__ D, int64_t ldD, const int64_t* __restrict__ I, int64_t ldI, int k,
+                                   const float* __restrict__ bounds, int64_t ld_b, const int* __restrict__ flags, int64_t ld_f,
+                                   int G, int64_t nq, int* __restrict__ need_exact) {
+  const int64_t qi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (qi >= nq) return;
+  float b = -INFINITY;
+  int f = 0;
+  for (int g = 0; g < G; ++g) {
+    b = fmaxf(b, bounds[g * ld_b + qi]);
+    f |= flags[g * ld_f + qi];
+  }
+  const bool ok = f == 0 && I[qi * ldI + (k - 1)] >= 0 && D[qi * ldD + (k - 1)] >= b;
+  need_exact[qi] = ok ? 0 : 1;
+}
+
 struct KeySource {
   const uint64_t* keys;  // A
   const float* Dp;       // B
@@ -301,18 +318,6 @@ void rebuild_tmaps(rs_index* h) {
                                  (uint64_t)h->d * 4, TILE_ROWS, 32);
 }
 
-struct DeviceGuard {
-  int prev = -1;
-  explicit DeviceGuard(int dev) {
-    cudaGetDevice(&prev);
-    if (prev != dev) cudaSetDevice(dev);
-    else prev = -1;
-  }
-  ~DeviceGuard() {
-    if (prev >= 0) cudaSetDevice(prev);
-  }
-};
-
 }  // namespace
 
 namespace rs {
@@ -367,7 +372,7 @@ int rs_index_free(rs_index_t* h) {
   return rs::guard([&] {
     if (!h) return;
     {
-      DeviceGuard g(h->device);
+      rs::DeviceGuard g(h->device);
       cudaFree(h->xb);
       cudaFree(h->xb_bf16);
       cudaFree(h->row_norm);
@@ -619,6 +624,31 @@ int rs_matvec(const DLTensor* items, const DLTensor* user, DLTensor* out, void* 
     sm_count();
     matvec_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
         data_ptr<float>(items), row_stride_2d(items, "items"), data_ptr<float>(user), data_ptr<float>(out), n, d);
+    RS_LAUNCH_CHECK();
+  });
+}
+
+int rs_topk_verify(const DLTensor* D, const DLTensor* I, const DLTensor* bounds, const DLTensor* flags,
+                   DLTensor* need_exact, void* stream) {
+  return rs::guard([&] {
+    using namespace rs;
+    require(D, "D", 2, kDLFloat, 32);
+    require(I, "I", 2, kDLInt, 64);
+    require(bounds, "bounds", 2, kDLFloat, 32);
+    require(flags, "flags", 2, kDLInt, 32);
+    require(need_exact, "need_exact", 1, kDLInt, 32);
+    const int64_t nq = D->shape[0], k = D->shape[1], G = bounds->shape[0];
+    RS_CHECK(I->shape[0] == nq && I->shape[1] == k && bounds->shape[1] == nq && flags->shape[0] == G && flags->shape[1] == nq &&
+                 need_exact->shape[0] == nq, "shapes: D, I [nq, k]; bounds, flags [shards, nq]; need_exact [nq]");
+    RS_CHECK(on_device(D) && on_device(I) && on_device(bounds) && on_device(flags) && on_device(need_exact), "all tensors must be CUDA tensors");
+    RS_CHECK((nq <= 1 || (stride_of(bounds, 1) == 1 && stride_of(flags, 1) == 1 && stride_of(need_exact, 0) == 1)) && k >= 1,
+             "bounds / flags rows and need_exact must have unit stride");
+    if (nq == 0) return;
+    sm_count();
+    verify_topk_kernel<<<static_cast<unsigned>((nq + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        data_ptr<float>(D), row_stride_2d(D, "D"), data_ptr<int64_t>(I), row_stride_2d(I, "I"), static_cast<int>(k),
+        data_ptr<float>(bounds), G > 1 ? stride_of(bounds, 0) : nq, data_ptr<int>(flags), G > 1 ? stride_of(flags, 0) : nq,
+        static_cast<int>(G), nq, data_ptr<int>(need_exact));
     RS_LAUNCH_CHECK();
   });
 }

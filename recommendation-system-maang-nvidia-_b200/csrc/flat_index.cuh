@@ -30,6 +30,28 @@ namespace rs {
 void search_exact_device(rs_index* h, const float* q, int64_t nq, int k, int64_t id_base, float* D, int64_t ldD,
                          int64_t* I, int64_t ldI, cudaStream_t st);
 // tensor-core pre-filter + exact re-score (tc_filter.cu); same results as search_exact_device
+// makes `dev` current for the lifetime of the object
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+// shared-threshold search of one shard of a partitioned catalog (tc_filter.cu)
+int64_t tensor_sample_rows(int64_t ntotal);
+int tensor_threshold_rank(int k, double rho);
+int64_t tensor_max_queries();
+rs_tc_session* shared_begin(rs_index* h, const float* q, int64_t nq, int k, int R, float* top, int64_t ld_top, cudaStream_t st);
+void shared_finish(rs_tc_session* s, const float* tops, int n_parts, int64_t part_ld, int R, int rank, int64_t id_base,
+                   float* D, int64_t ldD, int64_t* I, int64_t ldI, int* need_exact, float* bound);
+void tc_session_free(rs_tc_session* s);
+
 // need_exact == nullptr: flagged queries are re-run on the exact scan before returning (one stream synchronise).
 // need_exact != nullptr (device int32 [nq]): nothing is synchronised; need_exact[i] = 1 marks rows of D / I that are NOT
 // final and that the caller must re-search with search_exact_device.

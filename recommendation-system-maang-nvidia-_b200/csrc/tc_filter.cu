@@ -28,6 +28,8 @@
 // epilogue; two 256-column accumulators so the epilogue of tile i overlaps the MMAs of tile i+1).
 // Tensor roofline: 2*nq*N*128 flops per batch.  HBM: N*128*2 bytes (bf16 shadow), re-read from L2 by the
 // CTA groups that hold different query tiles.
+#include <cfloat>
+#include <memory>
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
@@ -426,7 +428,13 @@ __global__ void __launch_bounds__(SEL_NT) select_rescore_kernel(
     const uint64_t* __restrict__ cand, const int* __restrict__ cand_cnt, int cap, const float* __restrict__ thr,
     const float* __restrict__ eps2, const float* __restrict__ q, const float* __restrict__ xb, int k, int64_t id_base,
     float* __restrict__ D, int64_t ldD, int64_t* __restrict__ I, int64_t ldI, int* __restrict__ flags,
-    int* __restrict__ n_flagged) {
+    int* __restrict__ n_flagged, float* __restrict__ bound) {
+  // bound == nullptr: the threshold was this index's own guess and is verified here (s_hat_(k) - 2 eps >= tau).
+  // bound != nullptr ("shared threshold" mode of a partitioned catalog): tau came from the union of all shards'
+  // samples, so this shard may hold fewer than k survivors.  It returns the exact top-min(c, k) of its survivors
+  // (padded with D = -FLT_MAX, I = -1) and bound[q] = tau + eps; the caller verifies AFTER merging the shards that
+  // the k-th merged score >= every shard's bound (a row that failed a shard's filter has s_hat < tau, hence an exact
+  // score < tau + eps, and cannot belong to the top-k then).
   __shared__ uint64_t keys[CAND_CAP];
   __shared__ uint32_t sel[SEL_MAX_M];
   __shared__ __align__(16) float qs[DK];
@@ -441,14 +449,16 @@ __global__ void __launch_bounds__(SEL_NT) select_rescore_kernel(
   if (tid == 0) s_m = 0;
   for (int i = tid; i < c; i += SEL_NT) keys[i] = cand[(int64_t)qi * cap + i];
   __syncthreads();
-  bool ok = c_raw <= cap && c >= k;
-  float cutoff = 0.0f;
-  if (ok) {   // uniform
+  const bool shared_thr = bound != nullptr;
+  bool ok = c_raw <= cap && (shared_thr || c >= k);
+  float cutoff = -INFINITY;
+  if (ok && c >= k) {   // uniform
     const uint32_t kth = block_kth_largest<SEL_NT>([&](int i) { return static_cast<uint32_t>(keys[i] >> 32); }, c, k, hist,
                                                    state, tid);
     cutoff = ordered_to_f32(kth) - eps2[qi];
-    ok = cutoff >= thr[qi];          // the guess was low enough: the list provably holds the whole top-k
+    if (!shared_thr) ok = cutoff >= thr[qi];   // the guess was low enough: the list provably holds the whole top-k
   }
+  if (shared_thr && tid == 0) bound[qi] = thr[qi] + 0.5f * eps2[qi];
   if (ok) {
     // survivors of the margin cut: s_hat >= s_hat_(k) - 2 eps
     for (int i = tid; i < c; i += SEL_NT)
@@ -493,6 +503,51 @@ __global__ void __launch_bounds__(SEL_NT) select_rescore_kernel(
       D[qi * ldD + rank] = key_score(mine);
       I[qi * ldI + rank] = id_base + static_cast<int64_t>(key_row(mine));
     }
+  }
+  for (int i = m + tid; i < k; i += SEL_NT) {   // shared-threshold mode only: fewer than k survivors in this shard
+    D[qi * ldD + i] = -FLT_MAX;
+    I[qi * ldI + i] = -1;
+  }
+}
+
+// The `R` largest of each query's sample maxima, as floats, in no particular order (what a shard contributes to the
+// shared threshold of a partitioned catalog).  R <= n_vals <= 1024.
+__global__ void __launch_bounds__(256) sample_top_kernel(const unsigned* __restrict__ smax, int n_vals, int R,
+                                                         float* __restrict__ out, int64_t ld_out) {
+  __shared__ unsigned vals[1024];
+  __shared__ unsigned hist[256];
+  __shared__ unsigned state[2];
+  __shared__ int n_gt;
+  const int tid = threadIdx.x;
+  const int qi = blockIdx.x;
+  for (int i = tid; i < n_vals; i += 256) vals[i] = smax[(int64_t)qi * n_vals + i];
+  if (tid == 0) n_gt = 0;
+  __syncthreads();
+  const uint32_t kth = block_kth_largest<256>([&](int i) { return vals[i]; }, n_vals, R, hist, state, tid);
+  float* o = out + (int64_t)qi * ld_out;
+  for (int i = tid; i < n_vals; i += 256)
+    if (vals[i] > kth) o[atomicAdd(&n_gt, 1)] = ordered_to_f32(vals[i]);   // fewer than R of these
+  __syncthreads();
+  for (int i = n_gt + tid; i < R; i += 256) o[i] = ordered_to_f32(kth);    // the rest are ties at the R-th value
+}
+
+// tau_q = the `rank`-th largest of the union of the shards' top-R lists: tops[g * part_ld + q * R + i]
+__global__ void __launch_bounds__(256) threshold_shared_kernel(const float* __restrict__ tops, int n_parts, int64_t part_ld,
+                                                               int R, int rank, float* __restrict__ thr,
+                                                               int* __restrict__ cand_cnt, int* __restrict__ flags) {
+  __shared__ unsigned vals[1024];
+  __shared__ unsigned hist[256];
+  __shared__ unsigned state[2];
+  const int tid = threadIdx.x;
+  const int qi = blockIdx.x;
+  const int n = n_parts * R;
+  for (int i = tid; i < n; i += 256) vals[i] = f32_to_ordered(tops[(i / R) * part_ld + (int64_t)qi * R + (i % R)]);
+  __syncthreads();
+  const uint32_t kth = block_kth_largest<256>([&](int i) { return vals[i]; }, n, rank, hist, state, tid);
+  if (tid == 0) {
+    thr[qi] = ordered_to_f32(kth);
+    cand_cnt[qi] = 0;
+    flags[qi] = 0;
   }
 }
 
@@ -583,93 +638,145 @@ __global__ void export_flags_kernel(const int* __restrict__ flags, int nq, int n
   need_exact[i] = (all || flags[i] != 0) ? 1 : 0;
 }
 
+// Rows covered by the threshold sample of an index with `ntotal` rows: ~5 % of its 256-row tiles (64..2048 tiles),
+// never the zero-padded tail tile.
+static void sample_plan(int64_t ntotal, int64_t* n_sample, int64_t* sample_step) {
+  const int64_t ntiles = (ntotal + BN - 1) / BN;
+  *n_sample = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(2048, std::max<int64_t>(64, ntiles / 20)), (ntiles - 1) / 2));
+  *sample_step = (ntiles - 1) / *n_sample;
+}
+int64_t tensor_sample_rows(int64_t ntotal) {
+  int64_t n_sample, step;
+  sample_plan(ntotal, &n_sample, &step);
+  return n_sample * BN;
+}
+// rank of the sample maximum used as the threshold guess, for a sample covering the fraction rho of the rows
+int tensor_threshold_rank(int k, double rho) {
+  return static_cast<int>(std::ceil(std::pow(2.0 + std::sqrt(4.0 + 2.0 * k * rho), 2.0)));
+}
+int64_t tensor_max_queries() { return (int64_t)sm_count() * R_MAX * BM; }
+
+}  // namespace rs
+
+// One tensor-path search of <= tensor_max_queries() queries, split where the threshold is chosen:
+//   tc_begin   prep queries, sample pass (block maxima of ~5 % of the tiles)
+//   ...        threshold: this index's own guess (threshold_kernel) or one shared by all shards of a partitioned
+//              catalog (sample_top_kernel -> all-gather by the caller -> threshold_shared_kernel)
+//   tc_finish  filter pass, bucket, select + exact re-score
+struct rs_tc_session {
+  rs_index* h;
+  const float* q;
+  int nq, k, nq_pad, n_vals;
+  int64_t ntiles, n_sample;
+  unsigned rec_cap;
+  cudaStream_t st;
+  Workspace ws;
+  CUtensorMap tq;
+  TcParams p;
+  rs_tc_session(cudaStream_t s) : st(s), ws(s) {}
+};
+
+namespace rs {
+
+std::unique_ptr<rs_tc_session> tc_begin(rs_index* h, const float* qc, int cq, int k, cudaStream_t st) {
+  RS_CHECK(tensor_path_supported(h, cq, k) && cq <= tensor_max_queries(), "tensor path does not apply to this shape");
+  ensure_shadow(h, st);
+  const int sms = sm_count();
+  auto sp = std::make_unique<rs_tc_session>(st);
+  rs_tc_session& s = *sp;
+  s.h = h; s.q = qc; s.nq = cq; s.k = k;
+  const int nq_pad = s.nq_pad = (cq + BM - 1) / BM * BM;
+  const int n_qtiles = nq_pad / BM;
+  s.ntiles = (h->ntotal + BN - 1) / BN;
+  int64_t sample_step;
+  sample_plan(h->ntotal, &s.n_sample, &sample_step);
+  const int n_vals = s.n_vals = static_cast<int>(std::min<int64_t>(s.n_sample, 1024 / EPI_SLICES) * EPI_SLICES);
+  Workspace& ws = s.ws;
+  RS_CUDA(cudaMallocAsync(&ws.qb, sizeof(uint16_t) * (size_t)nq_pad * DK, st));
+  RS_CUDA(cudaMallocAsync(&ws.eps2, sizeof(float) * nq_pad, st));
+  RS_CUDA(cudaMallocAsync(&ws.thr, sizeof(float) * nq_pad, st));
+  RS_CUDA(cudaMallocAsync(&ws.smax, sizeof(unsigned) * (size_t)nq_pad * n_vals, st));
+  RS_CUDA(cudaMemsetAsync(ws.smax, 0, sizeof(unsigned) * (size_t)nq_pad * n_vals, st));
+  RS_CUDA(cudaMallocAsync(&ws.cnt, sizeof(int) * nq_pad, st));
+  RS_CUDA(cudaMallocAsync(&ws.flags, sizeof(int) * (nq_pad + 4), st));
+  RS_CUDA(cudaMallocAsync(&ws.cand, sizeof(uint64_t) * (size_t)nq_pad * CAND_CAP, st));
+  s.rec_cap = static_cast<unsigned>(nq_pad) * CAND_CAP;
+  RS_CUDA(cudaMallocAsync(&ws.rec, sizeof(uint4) * (size_t)s.rec_cap, st));
+  RS_CUDA(cudaMemsetAsync(ws.flags + nq_pad, 0, sizeof(int) * 4, st));
+  {
+    ProfScope prof(RS_PROF_RESCORE, st);
+    prep_queries_kernel<<<(nq_pad * 32 + 127) / 128, 128, 0, st>>>(qc, cq, nq_pad, ws.qb, ws.eps2,
+                                                                  reinterpret_cast<unsigned int*>(h->row_norm));
+    RS_LAUNCH_CHECK();
+  }
+  s.tq = make_tmap_2d(ws.qb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)nq_pad, DK, (uint64_t)DK * 2, BM, 64);
+  TcParams& p = s.p;
+  p = TcParams{};
+  p.n_items = h->ntotal;
+  p.nq = cq;
+  p.n_qtiles = n_qtiles;
+  p.n_groups = (n_qtiles + R_MAX - 1) / R_MAX;
+  p.ctas_per_group = std::max(1, sms / p.n_groups);
+  p.thr = ws.thr;
+  p.cand = ws.cand;
+  p.cand_cnt = ws.cnt;
+  p.cap = CAND_CAP;
+  p.smax = ws.smax;
+  p.smax_ld = n_vals;
+  p.rec = ws.rec;
+  p.rec_cap = s.rec_cap;
+  p.overflow = ws.flags + nq_pad + 1;
+  p.rec_cnt = reinterpret_cast<unsigned*>(ws.flags + nq_pad + 2);
+  {
+    ProfScope prof(RS_PROF_SAMPLE, st);
+    TcParams ps = p;
+    ps.n_visit = s.n_sample;
+    ps.tile_step = sample_step;
+    launch_filter<MODE_SAMPLE>(s.tq, h->tmap_bf16, ps, h->device, st);
+  }
+  return sp;
+}
+
+// the threshold must have been written to s.ws.thr (and cnt / flags cleared) by one of the threshold kernels
+void tc_finish(rs_tc_session& s, int64_t id_base, float* D, int64_t ldD, int64_t* I, int64_t ldI, float* bound) {
+  rs_index* h = s.h;
+  cudaStream_t st = s.st;
+  {
+    ProfScope prof(RS_PROF_FILTER, st);
+    TcParams pm = s.p;
+    pm.n_visit = s.ntiles;
+    pm.tile_step = 1;
+    launch_filter<MODE_FILTER>(s.tq, h->tmap_bf16, pm, h->device, st);
+  }
+  ProfScope prof(RS_PROF_RESCORE, st);
+  bucket_kernel<<<sm_count() * 4, 256, 0, st>>>(s.ws.rec, s.p.rec_cnt, s.rec_cap, s.ws.cand, s.ws.cnt, CAND_CAP);
+  RS_LAUNCH_CHECK();
+  select_rescore_kernel<<<s.nq, SEL_NT, 0, st>>>(s.ws.cand, s.ws.cnt, CAND_CAP, s.ws.thr, s.ws.eps2, s.q, h->xb, s.k, id_base,
+                                                 D, ldD, I, ldI, s.ws.flags, s.ws.flags + s.nq_pad, bound);
+  RS_LAUNCH_CHECK();
+}
+
 void search_tensor_device(rs_index* h, const float* q, int64_t nq, int k, int64_t id_base, float* D, int64_t ldD,
                           int64_t* I, int64_t ldI, cudaStream_t st, int* need_exact) {
   RS_CHECK(tensor_path_supported(h, nq, k), "tensor path does not apply to this shape");
-  ensure_shadow(h, st);
-  const int sms = sm_count();
   // query chunks so that every CTA group gets at least one SM
-  const int64_t max_chunk = (int64_t)sms * R_MAX * BM;
+  const int64_t max_chunk = tensor_max_queries();
   for (int64_t q0 = 0; q0 < nq; q0 += max_chunk) {
     const int cq = static_cast<int>(std::min<int64_t>(max_chunk, nq - q0));
     const float* qc = q + q0 * DK;
-    const int nq_pad = (cq + BM - 1) / BM * BM;
-    const int n_qtiles = nq_pad / BM;
-    const int64_t ntiles = (h->ntotal + BN - 1) / BN;
-    // threshold sample: ~5 % of the shard's tiles (64..2048 tiles), never the zero-padded tail tile
-    const int64_t n_sample = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(2048, std::max<int64_t>(64, ntiles / 20)),
-                                                                    (ntiles - 1) / 2));
-    const int64_t sample_step = (ntiles - 1) / n_sample;
-    const int n_vals = static_cast<int>(std::min<int64_t>(n_sample, 1024 / EPI_SLICES) * EPI_SLICES);
-    const double rho = double(n_sample * BN) / double(h->ntotal);
-    const double cc = 2.0 * k * rho;
-    int rank = static_cast<int>(std::ceil(std::pow(2.0 + std::sqrt(4.0 + cc), 2.0)));
-    rank = std::max(1, std::min(rank, n_vals / 2));
-
-    Workspace ws(st);
-    RS_CUDA(cudaMallocAsync(&ws.qb, sizeof(uint16_t) * (size_t)nq_pad * DK, st));
-    RS_CUDA(cudaMallocAsync(&ws.eps2, sizeof(float) * nq_pad, st));
-    RS_CUDA(cudaMallocAsync(&ws.thr, sizeof(float) * nq_pad, st));
-    RS_CUDA(cudaMallocAsync(&ws.smax, sizeof(unsigned) * (size_t)nq_pad * n_vals, st));
-    RS_CUDA(cudaMemsetAsync(ws.smax, 0, sizeof(unsigned) * (size_t)nq_pad * n_vals, st));
-    RS_CUDA(cudaMallocAsync(&ws.cnt, sizeof(int) * nq_pad, st));
-    RS_CUDA(cudaMallocAsync(&ws.flags, sizeof(int) * (nq_pad + 4), st));
-    RS_CUDA(cudaMallocAsync(&ws.cand, sizeof(uint64_t) * (size_t)nq_pad * CAND_CAP, st));
-    const unsigned rec_cap = static_cast<unsigned>(nq_pad) * CAND_CAP;
-    RS_CUDA(cudaMallocAsync(&ws.rec, sizeof(uint4) * (size_t)rec_cap, st));
-    RS_CUDA(cudaMemsetAsync(ws.flags + nq_pad, 0, sizeof(int) * 4, st));
-
+    auto sp = tc_begin(h, qc, cq, k, st);
+    rs_tc_session& s = *sp;
+    const int nq_pad = s.nq_pad;
+    const unsigned rec_cap = s.rec_cap;
+    Workspace& ws = s.ws;
+    const double rho = double(s.n_sample * BN) / double(h->ntotal);
+    const int rank = std::max(1, std::min(tensor_threshold_rank(k, rho), s.n_vals / 2));
     {
       ProfScope prof(RS_PROF_RESCORE, st);
-      prep_queries_kernel<<<(nq_pad * 32 + 127) / 128, 128, 0, st>>>(qc, cq, nq_pad, ws.qb, ws.eps2,
-                                                                    reinterpret_cast<unsigned int*>(h->row_norm));
+      threshold_kernel<<<cq, 256, 0, st>>>(ws.smax, s.n_vals, rank, ws.thr, ws.cnt, ws.flags);
       RS_LAUNCH_CHECK();
     }
-    const CUtensorMap tq = make_tmap_2d(ws.qb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)nq_pad, DK,
-                                        (uint64_t)DK * 2, BM, 64);
-    TcParams p{};
-    p.n_items = h->ntotal;
-    p.nq = cq;
-    p.n_qtiles = n_qtiles;
-    p.n_groups = (n_qtiles + R_MAX - 1) / R_MAX;
-    p.ctas_per_group = std::max(1, sms / p.n_groups);
-    p.thr = ws.thr;
-    p.cand = ws.cand;
-    p.cand_cnt = ws.cnt;
-    p.cap = CAND_CAP;
-    p.smax = ws.smax;
-    p.smax_ld = n_vals;
-    p.rec = ws.rec;
-    p.rec_cap = rec_cap;
-    p.overflow = ws.flags + nq_pad + 1;
-    p.rec_cnt = reinterpret_cast<unsigned*>(ws.flags + nq_pad + 2);
-    {
-      ProfScope prof(RS_PROF_SAMPLE, st);
-      TcParams ps = p;
-      ps.n_visit = n_sample;
-      ps.tile_step = sample_step;
-      launch_filter<MODE_SAMPLE>(tq, h->tmap_bf16, ps, h->device, st);
-    }
-    {
-      ProfScope prof(RS_PROF_RESCORE, st);
-      threshold_kernel<<<cq, 256, 0, st>>>(ws.smax, n_vals, rank, ws.thr, ws.cnt, ws.flags);
-      RS_LAUNCH_CHECK();
-    }
-    {
-      ProfScope prof(RS_PROF_FILTER, st);
-      TcParams pm = p;
-      pm.n_visit = ntiles;
-      pm.tile_step = 1;
-      launch_filter<MODE_FILTER>(tq, h->tmap_bf16, pm, h->device, st);
-    }
-    {
-      ProfScope prof(RS_PROF_RESCORE, st);
-      bucket_kernel<<<sms * 4, 256, 0, st>>>(ws.rec, p.rec_cnt, rec_cap, ws.cand, ws.cnt, CAND_CAP);
-      RS_LAUNCH_CHECK();
-      select_rescore_kernel<<<cq, SEL_NT, 0, st>>>(ws.cand, ws.cnt, CAND_CAP, ws.thr, ws.eps2, qc, h->xb, k, id_base,
-                                                   D + q0 * ldD, ldD, I + q0 * ldI, ldI, ws.flags, ws.flags + nq_pad);
-      RS_LAUNCH_CHECK();
-    }
+    tc_finish(s, id_base, D + q0 * ldD, ldD, I + q0 * ldI, ldI, nullptr);
     if (need_exact) {   // deferred: the caller resolves flagged queries (after its own exchange step)
       export_flags_kernel<<<(cq + 255) / 256, 256, 0, st>>>(ws.flags, cq, nq_pad, rec_cap, need_exact + q0);
       RS_LAUNCH_CHECK();
@@ -693,7 +800,35 @@ void search_tensor_device(rs_index* h, const float* q, int64_t nq, int k, int64_
   }
 }
 
-// debug / validation: every low-precision score of the tensor path, [nq, ntotal] (small catalogs only)
+// ---- shared-threshold search of one shard of a partitioned catalog (see rs_index_shared_begin in the header) ----
+rs_tc_session* shared_begin(rs_index* h, const float* q, int64_t nq, int k, int R, float* top, int64_t ld_top, cudaStream_t st) {
+  RS_CHECK(nq <= tensor_max_queries(), "too many queries for one shared-threshold search");
+  auto sp = tc_begin(h, q, static_cast<int>(nq), k, st);
+  RS_CHECK(R >= 1 && R <= sp->n_vals, "R must be in [1, number of sample maxima]");
+  ProfScope prof(RS_PROF_RESCORE, st);
+  sample_top_kernel<<<static_cast<unsigned>(nq), 256, 0, st>>>(sp->ws.smax, sp->n_vals, R, top, ld_top);
+  RS_LAUNCH_CHECK();
+  return sp.release();
+}
+
+void shared_finish(rs_tc_session* sp, const float* tops, int n_parts, int64_t part_ld, int R, int rank, int64_t id_base,
+                   float* D, int64_t ldD, int64_t* I, int64_t ldI, int* need_exact, float* bound) {
+  std::unique_ptr<rs_tc_session> own(sp);
+  rs_tc_session& s = *sp;
+  RS_CHECK(n_parts >= 1 && R >= 1 && n_parts * R <= 1024, "shards x R must be <= 1024");
+  RS_CHECK(rank >= 1 && rank <= n_parts * R, "rank must be in [1, shards x R]");
+  {
+    ProfScope prof(RS_PROF_RESCORE, s.st);
+    threshold_shared_kernel<<<s.nq, 256, 0, s.st>>>(tops, n_parts, part_ld, R, rank, s.ws.thr, s.ws.cnt, s.ws.flags);
+    RS_LAUNCH_CHECK();
+  }
+  tc_finish(s, id_base, D, ldD, I, ldI, bound);
+  export_flags_kernel<<<(s.nq + 255) / 256, 256, 0, s.st>>>(s.ws.flags, s.nq, s.nq_pad, s.rec_cap, need_exact);
+  RS_LAUNCH_CHECK();
+}
+
+void tc_session_free(rs_tc_session* sp) { delete sp; }
+
 void tensor_scores_debug(rs_index* h, const float* q, int64_t nq, float* out, cudaStream_t st) {
   RS_CHECK(h->d == DK && h->ntotal >= 1, "needs d = 128 and a non-empty index");
   ensure_shadow(h, st);
@@ -722,3 +857,77 @@ void tensor_scores_debug(rs_index* h, const float* q, int64_t nq, float* out, cu
 }
 
 }  // namespace rs
+
+// ------------------------------------------------------------------------------------------------
+// C ABI of the shared-threshold search (declared in include/recsys_b200.h)
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int rs_tensor_plan(int d, int64_t ntotal, int64_t nq, int k, int64_t* sampled_rows, int* supported) {
+  return rs::guard([&] {
+    RS_CHECK(sampled_rows && supported, "output pointer is NULL");
+    *supported = (d == DK && k >= 1 && k <= 128 && ntotal >= 65536 && ntotal <= 0x7FFFFF00ll && nq >= 1 &&
+                  nq <= rs::tensor_max_queries()) ? 1 : 0;
+    *sampled_rows = ntotal > 0 ? rs::tensor_sample_rows(ntotal) : 0;
+  });
+}
+
+int rs_tensor_threshold_rank(int k, double rho, int* rank) {
+  return rs::guard([&] {
+    RS_CHECK(rank != nullptr && k >= 1 && rho > 0.0 && rho <= 1.0, "rank is NULL, k < 1 or rho outside (0, 1]");
+    *rank = rs::tensor_threshold_rank(k, rho);
+  });
+}
+
+int rs_index_shared_begin(rs_index_t* h, const DLTensor* q, int k, DLTensor* top, rs_tc_session_t** out, void* stream) {
+  return rs::guard([&] {
+    using namespace rs;
+    RS_CHECK(h != nullptr && out != nullptr, "index or out is NULL");
+    require(q, "q", 2, kDLFloat, 32);
+    require(top, "top", 2, kDLFloat, 32);
+    const int64_t nq = q->shape[0];
+    RS_CHECK(q->shape[1] == h->d && nq >= 1, "q must be [nq >= 1, d] with d == index dimension");
+    RS_CHECK(on_device(q) && on_device(top) && is_compact(q) && q->device.device_id == h->device, "q / top must be CUDA tensors on the index's device, q contiguous");
+    RS_CHECK(top->shape[0] == nq && top->shape[1] >= 1 && (top->shape[1] == 1 || stride_of(top, 1) == 1), "top must be [nq, R] with unit column stride");
+    require_aligned16(data_ptr<float>(q), "q");
+    DeviceGuard g(h->device);
+    *out = shared_begin(h, data_ptr<float>(q), nq, k, static_cast<int>(top->shape[1]), data_ptr<float>(top),
+                        row_stride_2d(top, "top"), static_cast<cudaStream_t>(stream));
+  });
+}
+
+int rs_index_shared_finish(rs_tc_session_t* s, const DLTensor* tops, int rank, int64_t id_base, DLTensor* D, DLTensor* I,
+                           DLTensor* need_exact, DLTensor* bound, void* stream) {
+  return rs::guard([&] {
+    using namespace rs;
+    RS_CHECK(s != nullptr, "session is NULL");
+    std::unique_ptr<rs_tc_session> own(s);   // freed on every path
+    RS_CHECK(static_cast<cudaStream_t>(stream) == s->st, "finish must use the stream begin was called with");
+    require(tops, "tops", 3, kDLFloat, 32);
+    require(D, "D", 2, kDLFloat, 32);
+    require(I, "I", 2, kDLInt, 64);
+    require(need_exact, "need_exact", 1, kDLInt, 32);
+    require(bound, "bound", 1, kDLFloat, 32);
+    const int64_t nq = s->nq, k = s->k, G = tops->shape[0], R = tops->shape[2];
+    RS_CHECK(tops->shape[1] == nq && on_device(tops), "tops must be a CUDA [shards, nq, R] tensor");
+    int64_t part_ld = nq * R;
+    if (tops->strides) {
+      RS_CHECK((R <= 1 || tops->strides[2] == 1) && (nq <= 1 || tops->strides[1] == R), "tops: each shard's [nq, R] block must be contiguous");
+      if (G > 1) part_ld = tops->strides[0];
+    }
+    RS_CHECK(D->shape[0] == nq && D->shape[1] == k && I->shape[0] == nq && I->shape[1] == k, "D and I must be [nq, k]");
+    RS_CHECK(need_exact->shape[0] == nq && bound->shape[0] == nq && (nq <= 1 || (stride_of(need_exact, 0) == 1 && stride_of(bound, 0) == 1)),
+             "need_exact / bound must be contiguous [nq] tensors");
+    RS_CHECK(on_device(D) && on_device(I) && on_device(need_exact) && on_device(bound), "outputs must be CUDA tensors");
+    DeviceGuard g(s->h->device);
+    shared_finish(own.release(), data_ptr<float>(tops), static_cast<int>(G), part_ld, static_cast<int>(R), rank, id_base,
+                  data_ptr<float>(D), row_stride_2d(D, "D"), data_ptr<int64_t>(I), row_stride_2d(I, "I"),
+                  data_ptr<int>(need_exact), data_ptr<float>(bound));
+  });
+}
+
+int rs_tc_session_free(rs_tc_session_t* s) {
+  return rs::guard([&] { rs::tc_session_free(s); });
+}
+
+}  // extern "C"

@@ -122,6 +122,35 @@ class IndexFlatIP:
                                                       Fb.ptr, _lib.stream_ptr()))
         return D, I, F
 
+    # ---- shared-threshold search of one shard of a partitioned catalog (include/recsys_b200.h) ----
+    @staticmethod
+    def tensor_plan(d: int, ntotal: int, nq: int, k: int) -> Tuple[bool, int]:
+        """(tensor path applies to an index of `ntotal` rows for this (nq, k), rows its threshold sample covers)."""
+        rows, ok = ctypes.c_int64(0), ctypes.c_int32(0)
+        _lib.check(_lib.load().rs_tensor_plan(int(d), int(ntotal), int(nq), int(k), ctypes.byref(rows), ctypes.byref(ok)))
+        return bool(ok.value), int(rows.value)
+
+    @staticmethod
+    def threshold_rank(k: int, rho: float) -> int:
+        r = ctypes.c_int32(0)
+        _lib.check(_lib.load().rs_tensor_threshold_rank(int(k), float(rho), ctypes.byref(r)))
+        return int(r.value)
+
+    def shared_begin(self, x: "torch.Tensor", k: int, top: "torch.Tensor"):
+        """Sample pass; fills top [n, R] with each query's R largest sample maxima.  -> session for shared_finish."""
+        _check_2d_f32(x, "x", self.d)
+        sess = ctypes.c_void_p()
+        xb, tb = _lib.dl(x), _lib.dl(top)
+        _lib.check(self._lib.rs_index_shared_begin(self._h, xb.ptr, int(k), tb.ptr, ctypes.byref(sess), _lib.stream_ptr()))
+        return sess
+
+    def shared_finish(self, sess, tops: "torch.Tensor", rank: int, *, id_base: int = 0, out) -> None:
+        """tops [shards, n, R] gathered from every shard; out = (D, I, need_exact, bound) CUDA tensors.  Ends the session."""
+        D, I, F, B = out
+        tb, Db, Ib, Fb, Bb = _lib.dl(tops), _lib.dl(D), _lib.dl(I), _lib.dl(F), _lib.dl(B)
+        _lib.check(self._lib.rs_index_shared_finish(sess, tb.ptr, int(rank), int(id_base), Db.ptr, Ib.ptr, Fb.ptr, Bb.ptr,
+                                                    _lib.stream_ptr()))
+
     def fallbacks(self):
         """(last, total) tensor-mode queries that were re-run on the exact scan (same results either way)."""
         a, b = ctypes.c_int64(0), ctypes.c_int64(0)

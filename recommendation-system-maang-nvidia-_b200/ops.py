@@ -137,3 +137,13 @@ def topk_merge(Dparts: torch.Tensor, Iparts: torch.Tensor):
     a, b, c, d = _lib.dl(Dparts), _lib.dl(Iparts), _lib.dl(D), _lib.dl(I)
     _lib.check(_lib.load().rs_topk_merge(a.ptr, b.ptr, c.ptr, d.ptr, _lib.stream_ptr()))
     return D, I
+
+
+def topk_verify(D: torch.Tensor, I: torch.Tensor, bounds: torch.Tensor, flags: torch.Tensor) -> torch.Tensor:
+    """After the merge of a shared-threshold sharded search: int32 [nq], 1 = the query needs the exact re-search
+    (a shard overflowed, the merged list is short of k, or its k-th score < some shard's tau + eps)."""
+    _require_cuda(D, I, bounds, flags)
+    need = torch.empty((D.shape[0],), dtype=torch.int32, device=D.device)
+    a, b, c, d, e = _lib.dl(D), _lib.dl(I), _lib.dl(bounds), _lib.dl(flags), _lib.dl(need)
+    _lib.check(_lib.load().rs_topk_verify(a.ptr, b.ptr, c.ptr, d.ptr, e.ptr, _lib.stream_ptr()))
+    return need

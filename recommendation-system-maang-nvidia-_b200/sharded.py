@@ -30,16 +30,18 @@ def _round_up(x: int, m: int) -> int:
 
 def exchange_layout(nq: int, k: int) -> Tuple[int, int, int]:
     """Byte offsets of one shard's message in the fused exchange: scores f32 [nq,k] at 0, rows int64 [nq,k] at
-    off_I, need_exact int32 [nq] at off_F; `total` bytes per shard (16-byte multiples)."""
+    off_I, need_exact int32 [nq] at off_F, then bound f32 [nq] (shared-threshold searches) at off_F + 4*nq;
+    `total` bytes per shard (16-byte multiples)."""
     off_I = _round_up(nq * k * 4, 16)
     off_F = off_I + nq * k * 8
-    return off_I, off_F, _round_up(off_F + nq * 4, 16)
+    return off_I, off_F, _round_up(off_F + nq * 8, 16)
 
 
 class ShardedIndexFlatIP:
     def __init__(self, d: int, n_total: int, group: Optional[dist.ProcessGroup] = None,
                  local_index=None, local_search: Optional[Callable] = None, merge: Optional[Callable] = None,
-                 local_deferred: Optional[Callable] = None):
+                 local_deferred: Optional[Callable] = None, shared: Optional[Tuple[Callable, Callable]] = None,
+                 plan: Optional[Callable] = None, rank: Optional[Callable] = None, verify: Optional[Callable] = None):
         self.d = int(d)
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -56,12 +58,22 @@ class ShardedIndexFlatIP:
             self._local_exact = lambda q, k: self.local.search(q, k, mode="exact", id_base=self.row_begin)
             self._local_deferred = lambda q, k, out: self.local.search_deferred(q, k, id_base=self.row_begin, out=out)
             self._merge = ops.topk_merge
+            self._verify = ops.topk_verify
+            self._shared = (self.local.shared_begin,
+                            lambda sess, tops, rank, out: self.local.shared_finish(sess, tops, rank, id_base=self.row_begin, out=out))
+            self._plan = lambda rows, nq, k: IndexFlatIP.tensor_plan(self.d, rows, nq, k)
+            self._rank = IndexFlatIP.threshold_rank
         else:
             self.local = local_index
             self._local_search = local_search
             self._local_exact = local_search
             self._local_deferred = local_deferred
             self._merge = merge
+            self._verify = verify
+            self._shared = shared        # (begin(q, k, top) -> session, finish(session, tops, rank, out))
+            self._plan = plan            # (shard rows, nq, k) -> (tensor path applies, rows its sample covers)
+            self._rank = rank            # (k, rho) -> rank of the sample maximum to use as the threshold
+        self.shared_threshold = True     # set False to keep per-shard thresholds (one exchange fewer, ~8x the candidates)
 
     @property
     def ntotal(self) -> int:
@@ -72,6 +84,22 @@ class ShardedIndexFlatIP:
         self.local.add(x)
         if self.local.ntotal > self.row_end - self.row_begin:
             raise ValueError("more rows added than this rank's shard holds")
+
+    def _shared_rank(self, nq: int, k: int) -> int:
+        """Rank of the sample maximum that serves as the threshold shared by all shards; 0 = not applicable (some shard
+        is outside the tensor path for this (nq, k), or the union of the top lists would not fit the kernel)."""
+        key = (nq, k)
+        cache = self.__dict__.setdefault("_rank_cache", {})
+        if key not in cache:
+            sampled, ok = 0, True
+            for g in range(self.world):
+                fits, rows = self._plan(self.bounds[g + 1] - self.bounds[g], nq, k)
+                ok = ok and fits
+                sampled += rows
+            r = self._rank(k, sampled / max(1, self.n_total)) if ok else 0
+            # every shard sends its r largest sample maxima; its sample has at least 256 of them
+            cache[key] = r if (ok and r <= 128 and r * self.world <= 1024) else 0
+        return cache[key]
 
     def _gather_merge(self, Dl: torch.Tensor, Il: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         nq, kk = int(Dl.shape[0]), int(Dl.shape[1])
@@ -86,10 +114,16 @@ class ShardedIndexFlatIP:
         """q: [nq, d] replicated on every rank -> (D [nq, k], I [nq, k] global rows), identical on every rank.
 
         With a deferred local search (the default on CUDA) a step is queued without any host synchronisation in the
-        middle: local search -> ONE all-gather of a byte buffer that carries each shard's scores, rows and need_exact
-        flags side by side -> merge straight out of that buffer.  Only then does the host look at the flags (the step's
-        one synchronisation); flagged queries -- the tensor path's rare unverified guesses, on any shard -- are
-        re-searched exactly on every shard and merged again."""
+        middle: local search -> ONE all-gather of a byte buffer that carries each shard's scores, rows, need_exact
+        flags and bounds side by side -> merge straight out of that buffer.  Only then does the host look at the flags
+        (the step's one synchronisation); flagged queries -- the tensor path's rare unverified guesses -- are
+        re-searched exactly on every shard and merged again.
+
+        shared_threshold (default): the tensor path's filter threshold is guessed once from the union of all shards'
+        samples (a small extra all-gather of [nq, rank] floats) instead of once per shard, so the shards together keep
+        as many candidates as one index over the whole catalog would (~6.6 per cent of that each at G = 8 ... the
+        filter's survivor path and the re-score shrink with it), and the guarantee moves behind the merge
+        (ops.topk_verify: the k-th merged score must clear every shard's tau + eps)."""
         if self.world == 1:
             return self._local_search(q, k)
         if self._local_deferred is None:
@@ -101,8 +135,19 @@ class ShardedIndexFlatIP:
         send = torch.empty((total,), dtype=torch.uint8, device=dev)
         out = (send[:nq * k * 4].view(torch.float32).view(nq, k),
                send[off_I:off_I + nq * k * 8].view(torch.int64).view(nq, k),
-               send[off_F:off_F + nq * 4].view(torch.int32))
-        self._local_deferred(q, k, out)
+               send[off_F:off_F + nq * 4].view(torch.int32),
+               send[off_F + nq * 4:off_F + nq * 8].view(torch.float32))
+        rank = self._shared_rank(nq, k) if (self.shared_threshold and self._shared is not None) else 0
+        if rank > 0:
+            # threshold shared by all shards: each contributes the `rank` largest maxima of its own sample
+            begin, finish = self._shared
+            top = torch.empty((nq, rank), dtype=torch.float32, device=dev)
+            sess = begin(q, k, top)
+            tops = torch.empty((G * nq, rank), dtype=torch.float32, device=dev)
+            dist.all_gather_into_tensor(tops, top, group=self.group)
+            finish(sess, tops.view(G, nq, rank), rank, out)
+        else:
+            self._local_deferred(q, k, out[:3])
         recv = torch.empty((G * total,), dtype=torch.uint8, device=dev)
         dist.all_gather_into_tensor(recv, send, group=self.group)
         R = recv.view(G, total)
@@ -110,7 +155,11 @@ class ShardedIndexFlatIP:
         Ig = R[:, off_I:off_I + nq * k * 8].view(torch.int64).view(G, nq, k)
         Fg = R[:, off_F:off_F + nq * 4].view(torch.int32)                    # [G, nq]
         D, I = self._merge(Dg, Ig)
-        need = Fg.ne(0).any(dim=0)                                           # the same on every rank
+        if rank > 0:
+            Bg = R[:, off_F + nq * 4:off_F + nq * 8].view(torch.float32)     # [G, nq]: every shard's tau + eps
+            need = self._verify(D, I, Bg, Fg).ne(0)
+        else:
+            need = Fg.ne(0).any(dim=0)                                       # the same on every rank
         if bool(need.any()):                                                 # the step's one host synchronisation
             idx = need.nonzero().flatten()
             sub = np.ascontiguousarray(q[idx.cpu().numpy()]) if isinstance(q, np.ndarray) else q[idx].contiguous()

@@ -208,3 +208,56 @@ def test_topk_merge_reads_parts_out_of_a_strided_exchange_buffer(rs):
     Dw, Iw = flat_ip.search_chain(xb, q, k)
     np.testing.assert_array_equal(I.cpu().numpy(), Iw)
     np.testing.assert_array_equal(D.cpu().numpy(), Dw)
+
+
+def test_shared_threshold_protocol_over_simulated_shards(rs):
+    """The sharded catalog's shared-threshold search with the shards as four indexes on one GPU (the all-gathers become
+    torch.stack): begin -> tops -> finish -> merge -> verify must give the single-index result bit for bit, with no
+    query flagged, while single shards keep fewer than k candidates."""
+    from oracle import flat_ip
+    G, n_shard, nq, k = 4, 100_000, 300, 100
+    xb = rs.synth.make_unit_rows(G * n_shard, 128, 501)
+    q = rs.synth.make_unit_rows(nq, 128, 502)
+    qd = dev(q)
+    shards = []
+    for g in range(G):
+        ix = rs.IndexFlatIP(128)
+        ix.add(dev(xb[g * n_shard:(g + 1) * n_shard]))
+        shards.append(ix)
+    ok, rows = rs.IndexFlatIP.tensor_plan(128, n_shard, nq, k)
+    assert ok and rows >= 64 * 256
+    assert rs.IndexFlatIP.tensor_plan(128, 1000, nq, k)[0] is False and rs.IndexFlatIP.tensor_plan(64, n_shard, nq, k)[0] is False
+    rank = rs.IndexFlatIP.threshold_rank(k, G * rows / (G * n_shard))
+    assert 4 < rank <= 128
+
+    def run(rank_):
+        tops, sess = [], []
+        for ix in shards:
+            top = torch.empty((nq, rank), dtype=torch.float32, device="cuda")
+            sess.append(ix.shared_begin(qd, k, top))
+            tops.append(top)
+        tops = torch.stack(tops)
+        outs = []
+        for g, ix in enumerate(shards):
+            out = (torch.empty((nq, k), dtype=torch.float32, device="cuda"), torch.empty((nq, k), dtype=torch.int64, device="cuda"),
+                   torch.empty((nq,), dtype=torch.int32, device="cuda"), torch.empty((nq,), dtype=torch.float32, device="cuda"))
+            ix.shared_finish(sess[g], tops, rank_, id_base=g * n_shard, out=out)
+            outs.append(out)
+        D, I = rs.ops.topk_merge(torch.stack([o[0] for o in outs]), torch.stack([o[1] for o in outs]))
+        need = rs.ops.topk_verify(D, I, torch.stack([o[3] for o in outs]), torch.stack([o[2] for o in outs]))
+        return D, I, need, outs
+
+    D, I, need, outs = run(rank)
+    assert int(need.sum()) == 0
+    Dw, Iw = flat_ip.search_chain(xb, q, k)
+    np.testing.assert_array_equal(I.cpu().numpy(), Iw)
+    np.testing.assert_array_equal(D.cpu().numpy(), Dw)
+    # the top lists really are each query's largest sample maxima: the shared tau is below every shard's best score
+    per_shard = torch.stack([(o[1] >= 0).sum(dim=1) for o in outs]).float()
+    assert float(per_shard.sum(dim=0).min()) >= k            # together the shards hold at least k candidates per query
+    assert bool((per_shard < k).any())                       # ... while single shards come back short (padded lists)
+    # a threshold guessed far too high (rank 1 = the largest sample maximum): lists come back short, verify flags them
+    D, I, need, _ = run(1)
+    assert int(need.sum()) > 0.9 * nq
+    ok_rows = (need == 0).cpu().numpy()
+    np.testing.assert_array_equal(I.cpu().numpy()[ok_rows], Iw[ok_rows])     # whatever verify lets through is exact

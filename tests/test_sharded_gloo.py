@@ -83,6 +83,55 @@ def _worker(rank, world, port, n, nq, k, out_dir):
         off_I, off_F, total = exchange_layout(nq, k)
         assert calls[0] == ((world, nq, k), total // 4, total // 8)      # parts are slices of the exchange buffer
         assert off_I % 16 == 0 and total % 16 == 0 and off_F == off_I + nq * k * 8
+
+        # shared-threshold protocol (begin -> all-gather of the top lists -> finish -> fused exchange -> merge ->
+        # verify), with numpy stand-ins for the kernels: the filter here is an fp32 matmul whose scores may differ
+        # from the chain scores by rounding, covered by the 1e-5 margin in `bound` exactly as eps covers bf16.
+        FLT_MAX = np.finfo(np.float32).max
+
+        def begin(qq, kk, top):
+            scores = qq @ shard.T
+            sample = scores[:, ::5]
+            R = top.shape[1]
+            top.copy_(torch.from_numpy(-np.sort(-sample, axis=1)[:, :R].copy()))
+            return scores
+
+        def finish(scores, tops, rank_, out):
+            allv = tops.numpy().transpose(1, 0, 2).reshape(scores.shape[0], -1)
+            tau = -np.sort(-allv, axis=1)[:, rank_ - 1]
+            for i in range(scores.shape[0]):
+                rows = np.nonzero(scores[i] >= tau[i])[0]
+                Dl = np.full(k, -FLT_MAX, np.float32)
+                Il = np.full(k, -1, np.int64)
+                if len(rows):
+                    d, ix = flat_ip.search_chain(np.ascontiguousarray(shard[rows]), q[i:i + 1], min(k, len(rows)))
+                    Dl[:len(rows)][:k] = d[0][:k]
+                    Il[:min(k, len(rows))] = rows[ix[0]] + lo
+                out[0][i] = torch.from_numpy(Dl)
+                out[1][i] = torch.from_numpy(Il)
+            out[2].zero_()
+            out[3].copy_(torch.from_numpy((tau + 1e-5).astype(np.float32)))
+
+        def verify(D_, I_, Bg, Fg):
+            b = Bg.numpy().max(axis=0)
+            bad_ = (Fg.numpy() != 0).any(axis=0) | (I_.numpy()[:, k - 1] < 0) | (D_.numpy()[:, k - 1] < b)
+            return torch.from_numpy(bad_.astype(np.int32))
+
+        for rank_fn, expect_fallbacks in ((lambda kk, rho: int(np.ceil((2 + np.sqrt(4 + 2 * kk * rho)) ** 2)), False),
+                                          (lambda kk, rho: 2, True)):       # rank 2: tau far too high -> repaired
+            sh = ShardedIndexFlatIP(64, n, local_search=local_search, merge=merge_strided, local_deferred=local_deferred,
+                                    shared=(begin, finish), plan=lambda rows, nq_, kk: (True, (rows + 4) // 5),
+                                    rank=rank_fn, verify=verify)
+            if k > 128 and not expect_fallbacks:
+                assert sh._shared_rank(nq, k) == 0      # rank too large for the kernels: per-shard thresholds
+                D3, I3 = sh.search(q, k)
+                np.testing.assert_array_equal(I3.numpy(), Iw)
+                continue
+            assert sh._shared_rank(nq, k) > 0
+            D3, I3 = sh.search(q, k)
+            np.testing.assert_array_equal(I3.numpy(), Iw)
+            np.testing.assert_array_equal(D3.numpy(), Dw)
+            assert (sh.fallbacks > 0) == expect_fallbacks, sh.fallbacks
     finally:
         dist.destroy_process_group()
 
@@ -105,7 +154,7 @@ def test_shard_bounds_cover_the_catalog():
             b = shard_bounds(n, g)
             assert b[0] == 0 and b[-1] == n and all(x <= y for x, y in zip(b, b[1:]))
             assert max(y - x for x, y in zip(b, b[1:])) - min(y - x for x, y in zip(b, b[1:])) <= 1
-    assert gather_bytes(8, 1024, 100) == 8 * (1024 * 100 * 12 + 1024 * 4)
+    assert gather_bytes(8, 1024, 100) == 8 * (1024 * 100 * 12 + 1024 * 8)
 
 
 def _emb_worker(rank, world, port, n_rows, batch):

@@ -36,6 +36,12 @@ def main():
     Dw, Iw = full.search(q, k)
     sidx = ShardedIndexFlatIP(128, N)
     sidx.add_local(xb[sidx.row_begin:sidx.row_end].contiguous())
+    # default: threshold shared by all shards (one extra small all-gather), verification after the merge
+    assert sidx._shared_rank(nq, k) > 0
+    D, I = sidx.search(q, k)
+    assert torch.equal(I, Iw) and torch.equal(D, Dw), f"rank {rank}: shared-threshold sharded search differs"
+    assert sidx.fallbacks == 0
+    sidx.shared_threshold = False
     sd = sidx.local.search_deferred
     for mode in ("tensor", "exact"):
         # fused exchange: deferred local search -> one all-gather (scores | rows | flags) -> merge out of the buffer
@@ -60,6 +66,7 @@ def main():
     D, I = sidx.search(q, k)
     assert torch.equal(I, Iw) and torch.equal(D, Dw)
     sidx._local_deferred = lambda q_, k_, out: sd(q_, k_, id_base=sidx.row_begin, out=out)
+    sidx.shared_threshold = True
     # batch-1 (config 5)
     D1, I1 = sidx.search(q[:1].contiguous(), 10)
     assert torch.equal(I1, Iw[:1, :10])
