@@ -413,7 +413,7 @@ def bench_ranking(rs, torch, dist, args, device, world, rank, pk, timed):
                           "gpu_launches_per_step": launches // max(1, steps)}
         if precision == "bf16" and tc_n:
             t = tc_ms / steps / 1e3          # device time of the tcgen05 chain kernels per step
-            res[precision]["roofline"] = {"kernel": "chain_tc_kernel (towers + deep net)", "bound": "tensor",
+            res[precision]["roofline"] = {"kernel": "tower_pp_kernel + deep_heads_kernel (chain_tc.cu)", "bound": "tensor",
                                           "achieved": flops / t / 1e12, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                                           "frac": flops / t / 1e12 / pk["bf16_tflops_sustained"], "traffic": None,
                                           "algorithmic": "524,288 GEMM flop per sample", "ms_per_step": tc_ms / steps,
