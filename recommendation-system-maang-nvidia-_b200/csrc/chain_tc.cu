@@ -89,6 +89,7 @@ struct ChainProblem {
   int64_t rows;
   const float* bias[MAX_L];
   const float* table;    // GATHER: fp32 [V, 128]
+  const uint16_t* table16;   // tower_pp_kernel: bf16 copy of `table` ([V, 128] packed) or nullptr
   int64_t table_ld;
   int64_t table_rows;
   const void* ids;       // GATHER: int32 / int64 [rows]
@@ -464,12 +465,23 @@ tower_pp_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
                          : pr.ids64 ? static_cast<const int64_t*>(pr.ids)[row_]
                                     : static_cast<int64_t>(static_cast<const int32_t*>(pr.ids)[row_]);
       if (id >= 0 && id < pr.table_rows) {
-        const float4* src = reinterpret_cast<const float4*>(pr.table + id * pr.table_ld + half * 64);
+        if (pr.table16) {
+          // bf16 copy of the table: the eight loads land in the very registers tcgen05.st takes next round, so
+          // nothing waits for them here and they stay in flight behind this tile's layers
+          const uint4* src = reinterpret_cast<const uint4*>(pr.table16 + id * 128 + half * 64);
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const float4 f = __ldg(src + e);
-          a0[2 * e] = pack_bf16x2(f.x, f.y);
-          a0[2 * e + 1] = pack_bf16x2(f.z, f.w);
+          for (int e = 0; e < 8; ++e) {
+            const uint4 u = __ldg(src + e);
+            a0[4 * e] = u.x; a0[4 * e + 1] = u.y; a0[4 * e + 2] = u.z; a0[4 * e + 3] = u.w;
+          }
+        } else {
+          const float4* src = reinterpret_cast<const float4*>(pr.table + id * pr.table_ld + half * 64);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const float4 f = __ldg(src + e);
+            a0[2 * e] = pack_bf16x2(f.x, f.y);
+            a0[2 * e + 1] = pack_bf16x2(f.z, f.w);
+          }
         }
       }
     };
@@ -533,7 +545,7 @@ tower_pp_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
 #pragma unroll
               for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], 0.0f);
             }
-            if (pr.y_il16) {   // rows past the end of the batch land in the scratch's padding
+            if (pr.y_il16 && !(p.debug & 64)) {   // rows past the end of the batch land in the scratch's padding
               uint4* dst = reinterpret_cast<uint4*>(pr.y_il16) +
                            ((tile * 4 + quarter) * 32 + pr.il_chunk0 + (col0 >> 3)) * 32 + lane;
 #pragma unroll
@@ -541,7 +553,7 @@ tower_pp_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
                 dst[e * 32] = make_uint4(pack_bf16x2(v[8 * e], v[8 * e + 1]), pack_bf16x2(v[8 * e + 2], v[8 * e + 3]),
                                          pack_bf16x2(v[8 * e + 4], v[8 * e + 5]), pack_bf16x2(v[8 * e + 6], v[8 * e + 7]));
             }
-            if (pr.dots) {
+            if (pr.dots && !(p.debug & 32)) {
               const float* ws = dotw_s + col0;
 #pragma unroll
               for (int e = 0; e < 32; e += 4) {
@@ -559,7 +571,7 @@ tower_pp_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
               }
             }
             if (row < pr.rows) {
-              if (pr.y_f32) {
+              if (pr.y_f32 && !(p.debug & 16)) {
                 float* dst = pr.y_f32 + row * pr.ld_f32 + col0;
 #pragma unroll
                 for (int e = 0; e < 32; e += 8)
@@ -611,6 +623,7 @@ void launch_tower_pp(const ChainMaps& maps, const ChainParams& p, cudaStream_t s
   const char* tr_env = getenv("RS_CHAIN_TRACE");
   if (tr_env && tr_env[0] == '1') {   // debugging aid: per-round phase stamps, relative to the first one
     ChainParams q = p;
+    if (const char* e = getenv("RS_CHAIN_DEBUG")) q.debug = atoi(e);   // 16 / 32 / 64: skip the fp32 / dot / bf16 outputs
     RS_CUDA(cudaMalloc(&q.trace, 8 * 16 * sizeof(long long)));
     RS_CUDA(cudaMemsetAsync(q.trace, 0, 8 * 16 * sizeof(long long), st));
     tower_pp_kernel<<<grid, NTHREADS, chain_smem<CfgTower>() + 6 * 128 * 4, st>>>(maps, q);
@@ -1138,15 +1151,35 @@ struct rs_ranker {
   int device = 0;
   int cross_layers = 0;
   const float* table[2] = {nullptr, nullptr};   // borrowed
+  uint16_t* table16[2] = {nullptr, nullptr};    // owned bf16 copies of small tables (what the tower kernel gathers from)
   int64_t table_ld[2] = {0, 0}, table_rows[2] = {0, 0};
   uint16_t* wts = nullptr;      // all bf16 kernels, [out][in] each: user tower, item tower, deep
   float* f32 = nullptr;         // biases (user 576, item 576, deep 384), cross_w [L,256], cross_b [L,256], head_w [2,384], head_b [2]
   size_t off_w[2][4], off_dw[2];
   size_t off_b[2][4], off_db[2], off_cw, off_cb, off_hw, off_hb, off_const;
   ChainMaps tower_maps, deep_maps;
+  ~rs_ranker() {
+    cudaFree(wts);
+    cudaFree(f32);
+    cudaFree(table16[0]);
+    cudaFree(table16[1]);
+  }
 };
 
 namespace {
+
+// tables up to this many rows are copied to bf16 when the handle is created (<= 256 MB per table)
+constexpr int64_t kShadowTableRows = 1 << 20;
+
+__global__ void table_to_bf16_kernel(const float* __restrict__ src, int64_t ld, int64_t rows, uint16_t* __restrict__ dst) {
+  const int64_t n = rows * 64;   // bf16 pairs
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i >> 6;
+    const int c = static_cast<int>(i & 63) * 2;
+    const float2 f = *reinterpret_cast<const float2*>(src + r * ld + c);
+    reinterpret_cast<uint32_t*>(dst)[i] = pack_bf16x2(f.x, f.y);
+  }
+}
 
 void copy_in(void* dst, const DLTensor* t, size_t bytes, cudaStream_t st) {
   RS_CUDA(cudaMemcpyAsync(dst, rs::data_ptr<void>(t), bytes, cudaMemcpyDeviceToDevice, st));
@@ -1238,6 +1271,13 @@ extern "C" int rs_ranker_create(const DLTensor* user_table, const DLTensor* item
     }
     copy_in(h->f32 + h->off_hw, head_w, 2 * 384 * 4, st);
     copy_in(h->f32 + h->off_hb, head_b, 2 * 4, st);
+    for (int s = 0; s < 2; ++s) {
+      if (h->table_rows[s] < 1 || h->table_rows[s] > kShadowTableRows) continue;
+      RS_CUDA(cudaMalloc(&h->table16[s], sizeof(uint16_t) * (size_t)h->table_rows[s] * 128));
+      const int blocks = static_cast<int>(std::min<int64_t>((h->table_rows[s] * 64 + 255) / 256, (int64_t)sm_count() * 8));
+      table_to_bf16_kernel<<<blocks, 256, 0, st>>>(h->table[s], h->table_ld[s], h->table_rows[s], h->table16[s]);
+      RS_LAUNCH_CHECK();
+    }
     ranker_consts_kernel<<<1, 32, 0, st>>>(h->f32 + h->off_cw, h->f32 + h->off_cb, h->f32 + h->off_hw, static_cast<int>(L),
                                            h->f32 + h->off_const);
     RS_LAUNCH_CHECK();
@@ -1249,8 +1289,6 @@ extern "C" int rs_ranker_create(const DLTensor* user_table, const DLTensor* item
 extern "C" int rs_ranker_free(rs_ranker* h) {
   return rs::guard([&] {
     if (!h) return;
-    cudaFree(h->wts);
-    cudaFree(h->f32);
     delete h;
   });
 }
@@ -1313,6 +1351,7 @@ static int ranker_forward_impl(rs_ranker* h, const DLTensor* user_rows, const DL
                        (is_dtype(ids[s], kDLInt, 32) || is_dtype(ids[s], kDLInt, 64)) && (B <= 1 || stride_of(ids[s], 0) == 1),
                    "row ids must be contiguous CUDA int32/int64 [B] tensors");
           pr.table = h->table[s];
+          pr.table16 = h->table16[s];
           pr.table_ld = h->table_ld[s];
           pr.table_rows = h->table_rows[s];
           pr.ids = data_ptr<void>(ids[s]);
