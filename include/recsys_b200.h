@@ -117,11 +117,13 @@ int rs_chain_forward_bf16(int n_prob, int n_layers, const DLTensor* const* wts, 
                           const DLTensor* const* x, DLTensor* const* y_f32, DLTensor* const* y_bf16, void* stream);
 /*
  * MultiTaskModel.call (src/models.py:125-131) in bf16 tensor mode behind one handle and one call per batch:
- * both towers (gather fused) -> deep net -> DCN cross + heads.  The handle COPIES the kernels (bf16 [out,in]; towers
- * 128-256-128-64-128, index s*4+l with s = 0 user / 1 item; deep net 256-256-128), biases (may be NULL), cross_w /
- * cross_b f32 [L,256], head_w f32 [2,384] (row 0 rating, row 1 ctr), head_b f32 [2]; it BORROWS the two f32
- * embedding tables [V,128], which must outlive it.  forward: user_rows/item_rows int32|int64 [B] ->
- * combined f32 [B,256] (user embedding | item embedding), rating f32 [B,1], ctr f32 [B,1].
+ * both towers (gather fused) -> deep net + DCN cross + heads (two kernel launches).  The handle COPIES the kernels
+ * (bf16 [out,in]; towers 128-256-128-64-128, index s*4+l with s = 0 user / 1 item; deep net 256-256-128), biases (may
+ * be NULL), cross_w / cross_b f32 [L,256], head_w f32 [2,384] (row 0 rating, row 1 ctr), head_b f32 [2]; it BORROWS
+ * the two f32 embedding tables [V,128], which must outlive it, and for tables of up to 2^20 rows also keeps a bf16 copy
+ * (what the tower kernel gathers from): create a new handle after the tables or weights change.
+ * forward: user_rows/item_rows int32|int64 [B] -> combined f32 [B,256] (user embedding | item embedding),
+ * rating f32 [B,1], ctr f32 [B,1].
  */
 typedef struct rs_ranker rs_ranker_t;
 int rs_ranker_create(const DLTensor* user_table, const DLTensor* item_table, const DLTensor* const* tower_wt,
