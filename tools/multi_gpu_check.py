@@ -67,12 +67,22 @@ def main():
     assert torch.equal(I, Iw) and torch.equal(D, Dw)
     sidx._local_deferred = lambda q_, k_, out: sd(q_, k_, id_base=sidx.row_begin, out=out)
     sidx.shared_threshold = True
+    # the same step replayed as a CUDA graph (kernels + both NCCL collectives captured once per (nq, k))
+    sidx.use_graph = True
+    for _ in range(3):
+        D, I = sidx.search(q, k)
+        assert torch.equal(I, Iw) and torch.equal(D, Dw), f"rank {rank}: graph-replayed sharded search differs"
+    q2 = torch.roll(q, 7, dims=0).contiguous()                      # new queries through the captured graph
+    D, I = sidx.search(q2, k)
+    assert torch.equal(I, torch.roll(Iw, 7, dims=0)) and torch.equal(D, torch.roll(Dw, 7, dims=0))
+    sidx.use_graph = False
     # batch-1 (config 5)
     D1, I1 = sidx.search(q[:1].contiguous(), 10)
     assert torch.equal(I1, Iw[:1, :10])
+    sidx.close()
     dist.barrier()
     if rank == 0:
-        print(f"multi-GPU parity OK on {world} GPUs: sharded == single-GPU, bit-exact (N={N}, nq={nq}, k={k})")
+        print(f"multi-GPU parity OK on {world} GPUs: sharded == single-GPU, bit-exact (N={N}, nq={nq}, k={k})", flush=True)
     dist.destroy_process_group()
 
 
