@@ -21,6 +21,7 @@ from .models import (  # noqa: F401
     Embedding,
     MultiTaskModel,
     MultiTowerModel,
+    RankingSession,
     Sequential,
     StringLookup,
     load_weights,

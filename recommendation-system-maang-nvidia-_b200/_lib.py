@@ -38,8 +38,11 @@ class DLTensor(ctypes.Structure):
 
 _DLP = ctypes.POINTER(DLTensor)
 _capsule_get = ctypes.pythonapi.PyCapsule_GetPointer
-_capsule_get.restype = ctypes.c_void_p
+_capsule_get.restype = _DLP                    # DLManagedTensor starts with its DLTensor
 _capsule_get.argtypes = [ctypes.py_object, ctypes.c_char_p]
+# torch's C++ exporter: the same capsule tensor.__dlpack__() returns, without the Python-level stream handling
+# (we pass stream=-1 there anyway: the library is stream-ordered behind the caller's current stream)
+_torch_to_dlpack = getattr(torch._C, "_to_dlpack", None)
 
 _lib = None
 
@@ -144,14 +147,17 @@ class _Borrowed:
     def __init__(self, obj):
         self.obj = obj
         if isinstance(obj, torch.Tensor):
-            self.capsule = obj.__dlpack__(stream=-1) if obj.is_cuda else obj.__dlpack__()
+            if _torch_to_dlpack is not None:
+                self.capsule = _torch_to_dlpack(obj)
+            else:
+                self.capsule = obj.__dlpack__(stream=-1) if obj.is_cuda else obj.__dlpack__()
         elif isinstance(obj, np.ndarray):
             if not obj.flags.writeable:      # DLPack (unversioned) cannot flag read-only: export a private copy
                 obj = self.obj = obj.copy()
             self.capsule = obj.__dlpack__()
         else:
             raise TypeError(f"cannot export {type(obj)} through DLPack")
-        self.ptr = ctypes.cast(_capsule_get(self.capsule, b"dltensor"), _DLP)
+        self.ptr = _capsule_get(self.capsule, b"dltensor")
 
 
 def dl(obj):

@@ -83,6 +83,7 @@ constexpr int chain_smem() {
 
 struct ChainMaps {
   CUtensorMap w[2][MAX_L];   // [problem][layer]
+  CUtensorMap y[2];          // tower_pp_kernel, ChainProblem::y_tma: the fp32 output, box 16 rows x 32 floats, 128B swizzle
 };
 
 struct ChainProblem {
@@ -104,17 +105,9 @@ struct ChainProblem {
   //  * y_il16: bf16 copy of the output in the lane-interleaved layout deep_heads_kernel loads its A operand from.
   //    16-byte chunk c (8 features) of row (tile T, quarter q, lane) is uint4 number ((T*4 + q)*32 + c)*32 + lane, so
   //    one 128-bit access per lane is a contiguous 512 bytes per warp on both the writing and the reading side.
-  //  * dots: fp32 dot products of this problem's 128 output columns (still in registers, full precision) with its
-  //    slice of the cross kernels and head rows -- the x0 . w_l, x0 . head terms of the DCN cross stack.  Per row and
-  //    per (problem, column half) h = 2*problem + half: float number (((T*4 + q)*4 + h)*6 + t)*32 + lane,
-  //    t = 0..3 cross layer, 4 rating head, 5 ctr head.
   uint16_t* y_il16;
   int il_chunk0;         // first 16-byte chunk of this problem's columns (0 for the user tower, 16 for the item tower)
-  float* dots;
-  int dots_h0;           // 2 * problem
-  const float* dot_cw;   // cross kernels, already offset to this problem's first column; row stride 256
-  int n_cross;
-  const float* dot_hw;   // head rows, already offset to this problem's first column; row stride 384
+  int y_tma;             // ChainMaps::y[problem] describes y_f32: the kernel may store it with TMA
 };
 
 struct ChainParams {
@@ -122,6 +115,7 @@ struct ChainParams {
   int n_prob;            // 1 or 2 (both towers in one launch)
   int act[MAX_L];
   int debug;             // perf experiments: 1 = epilogue skips TMEM traffic, 2 = issuer skips the MMAs
+  int lag;               // tower_pp_kernel: MMA steps of slot 0 issued before slot 1 may start (RS_TOWER_LAG, default 3)
   long long* trace;      // RS_CHAIN_TRACE=1 (tower_pp_kernel): clock64 stamps of block 0, slot 0, warp 4 ([round][16])
 };
 
@@ -334,20 +328,51 @@ chain_tc_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
 //   columns relative to the tile's base R:  A0 [0,64)  acc [64,192)  A1a [192,256)  A1b [0,64)  A2 [192,256)
 //                                           acc3 [0,64)  A3 [64,96)  acc4 [128,256)
 //   steps: L1a (A0 x W1[0:128])  L1b (A0 x W1[128:256])  L2 (A1a|A1b x W2)  L3 (A2 x W3)  L4 (A3 x W4)
+//
+// Data movement, MODE (RS_TOWER_STAGE=0/1/2 for A/B runs, default 2).  A tcgen05 epilogue thread owns one ROW, so a
+// gather load or an output store issued per thread touches 32 different 128-byte lines per instruction.
+//   0  direct: thread-per-row loads and 256-bit stores.
+//   1  staged: gather and fp32 output go through a per-warp shared-memory buffer (16-byte chunks XOR-swizzled by row,
+//      every access conflict-free); the global side is issued 8 lanes per row, 4 lines per instruction.  The gather
+//      keeps its "in flight for a whole tile" property: the raw chunks land in registers one tile ahead (ids two tiles
+//      ahead) and are only transposed when the tile starts.  Measured: same speed as 0 -- the output step is bound
+//      by the SM's global-store rate (~32 B/clk), not by the number of lines per instruction.
+//   2  staged + TMA stores: the outputs are written to the stage buffers only and leave through the async proxy
+//      (cp.async.bulk[.tensor] shared -> global, bulk groups), two 2 KB buffers per warp in alternation, so the
+//      epilogue warps go back to the chain while the stores drain.  Uses all 227 KB of shared memory.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NTHREADS, 1)
+constexpr int TOWER_STAGE_BYTES = 2048;   // per epilogue warp and buffer (MODE 1: one buffer, MODE 2: two)
+// warp 0: TMA, warp 1: MMA issuer, warps 4-19: epilogue (register allocation is per 4 warps, so dropping the two idle
+// warps would not raise the 96-register cap; setmaxnreg made ptxas spill more, not less)
+constexpr int PP_THREADS = NTHREADS;
+constexpr int PP_EPI0 = 4;
+
+constexpr int TOWER_FIXED_SMEM = w_off<CfgTower>(CfgTower::L) + b_off<CfgTower>(CfgTower::L) * 4 + 256;   // kernels, biases, barriers
+constexpr int TOWER_STAGE_OFF = (TOWER_FIXED_SMEM + 1023) / 1024 * 1024;
+constexpr int tower_pp_smem(int mode) {   // modes 0/1 carry 1 KB of alignment slack; mode 2 relies on __align__(1024)
+  return mode == 0 ? TOWER_FIXED_SMEM + 1024
+         : mode == 1 ? TOWER_STAGE_OFF + EPI_WARPS * TOWER_STAGE_BYTES + 1024
+                     : TOWER_STAGE_OFF + EPI_WARPS * 2 * TOWER_STAGE_BYTES;
+}
+static_assert(tower_pp_smem(2) <= 232448, "tower_pp_kernel mode 2 must fit the 227 KB of shared memory per CTA");
+
+template <int MODE>
+__global__ void __launch_bounds__(PP_THREADS, 1)
 tower_pp_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
   using C = CfgTower;
-  extern __shared__ uint8_t smem_raw[];
+  constexpr bool STAGED = MODE >= 1;
+  constexpr bool TMAST = MODE == 2;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  if (TMAST && base != smem_raw) __trap();   // no room for slack in mode 2
   uint8_t* wsm = base;
   float* bias_s = reinterpret_cast<float*>(base + w_off<C>(C::L));
-  float* dotw_s = bias_s + b_off<C>(C::L);   // [6][128]: cross kernels 0..3 (zero beyond n_cross), rating head, ctr head
-  uint64_t* bars = reinterpret_cast<uint64_t*>(dotw_s + 6 * 128);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + b_off<C>(C::L));
   uint64_t* wfull = bars;
   uint64_t* a_ready = bars + 1;      // [2]
   uint64_t* acc_ready = bars + 3;    // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  uint8_t* stage = base + TOWER_STAGE_OFF;   // STAGED: [EPI_WARPS][1 or 2][TOWER_STAGE_BYTES], 1024-byte aligned
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -369,12 +394,7 @@ tower_pp_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
   }
 #pragma unroll
   for (int l = 0; l < C::L; ++l)
-    for (int i = threadIdx.x; i < C::N(l); i += NTHREADS) bias_s[b_off<C>(l) + i] = pr.bias[l] ? pr.bias[l][i] : 0.0f;
-  if (pr.dots)
-    for (int i = threadIdx.x; i < 6 * 128; i += NTHREADS) {
-      const int t = i >> 7, j = i & 127;
-      dotw_s[i] = t < 4 ? (t < pr.n_cross ? pr.dot_cw[t * 256 + j] : 0.0f) : pr.dot_hw[(t - 4) * 384 + j];
-    }
+    for (int i = threadIdx.x; i < C::N(l); i += PP_THREADS) bias_s[b_off<C>(l) + i] = pr.bias[l] ? pr.bias[l][i] : 0.0f;
   if (warp == 1) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
@@ -397,55 +417,73 @@ tower_pp_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
       // ---------------- MMA issuer: step s of tile slot 0, step s of tile slot 1, step s+1 of slot 0, ... ----------------
       mbar_wait(wfull, 0);
       const uint64_t wdesc0 = umma_desc_k_sw128(smem_u32(wsm));
-      const int64_t n_slot[2] = {(n_my + 1) / 2, n_my / 2};
+      // Ready-driven: whichever slot has its A operand in TMEM gets its next step issued.  Slot 1 starts only after
+      // slot 0 has had `p.lag` steps issued, which puts the two tiles half a period apart for the rest of the kernel:
+      // one slot's output step (bound by the SM's global-store rate) then overlaps the other slot's MMA / TMEM steps
+      // instead of both bursts sharing the store path at the same time.
+      int64_t left[2] = {(n_my + 1) / 2, n_my / 2};
       uint32_t use[2] = {0, 0};
-      for (int64_t r = 0; r < n_slot[0]; ++r) {
+      int step_of[2] = {0, 0};
+      int lag = left[1] > 0 ? p.lag : 0;
+      auto issue = [&](int slot, int step) {
+        const uint32_t R = tmem_base + slot * 256;
+        if (step <= 1) {          // L1 half: A0 [R, R+64) x W1 rows [128*step, +128), K = 128
+          const uint32_t idesc = umma_idesc_bf16_f32(BM, 128);
 #pragma unroll
-        for (int step = 0; step < 5; ++step) {
+          for (int k = 0; k < 8; ++k) {
+            const uint64_t db = wdesc0 + static_cast<uint64_t>((w_off<C>(0) + (k >> 2) * (256 * 128) + step * (128 * 128) + (k & 3) * 32) >> 4);
+            umma_bf16_ts(R + 64, R + k * 8, db, idesc, k > 0 ? 1u : 0u);
+          }
+        } else if (step == 2) {   // L2: A1a [R+192, +64) then A1b [R, +64), W2 (N = 128), K = 256
+          const uint32_t idesc = umma_idesc_bf16_f32(BM, 128);
 #pragma unroll
-          for (int slot = 0; slot < 2; ++slot) {
-            if (r >= n_slot[slot]) continue;
-            const uint32_t R = tmem_base + slot * 256;
-            chain_wait(&a_ready[slot], use[slot] & 1u);
-            tc_fence_after_sync();
-            if (step <= 1) {          // L1 half: A0 [R, R+64) x W1 rows [128*step, +128), K = 128
-              const uint32_t idesc = umma_idesc_bf16_f32(BM, 128);
+          for (int k = 0; k < 16; ++k) {
+            const uint64_t db = wdesc0 + static_cast<uint64_t>((w_off<C>(1) + (k >> 2) * (128 * 128) + (k & 3) * 32) >> 4);
+            umma_bf16_ts(R + 64, k < 8 ? R + 192 + k * 8 : R + (k - 8) * 8, db, idesc, k > 0 ? 1u : 0u);
+          }
+        } else if (step == 3) {   // L3: A2 [R+192, +64), W3 (N = 64), K = 128 -> acc3 [R, +64)
+          const uint32_t idesc = umma_idesc_bf16_f32(BM, 64);
 #pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                const uint64_t db = wdesc0 + static_cast<uint64_t>((w_off<C>(0) + (k >> 2) * (256 * 128) + step * (128 * 128) + (k & 3) * 32) >> 4);
-                umma_bf16_ts(R + 64, R + k * 8, db, idesc, k > 0 ? 1u : 0u);
-              }
-            } else if (step == 2) {   // L2: A1a [R+192, +64) then A1b [R, +64), W2 (N = 128), K = 256
-              const uint32_t idesc = umma_idesc_bf16_f32(BM, 128);
+          for (int k = 0; k < 8; ++k) {
+            const uint64_t db = wdesc0 + static_cast<uint64_t>((w_off<C>(2) + (k >> 2) * (64 * 128) + (k & 3) * 32) >> 4);
+            umma_bf16_ts(R, R + 192 + k * 8, db, idesc, k > 0 ? 1u : 0u);
+          }
+        } else {                  // L4: A3 [R+64, +32), W4 (N = 128), K = 64 -> acc4 [R+128, +128)
+          const uint32_t idesc = umma_idesc_bf16_f32(BM, 128);
 #pragma unroll
-              for (int k = 0; k < 16; ++k) {
-                const uint64_t db = wdesc0 + static_cast<uint64_t>((w_off<C>(1) + (k >> 2) * (128 * 128) + (k & 3) * 32) >> 4);
-                umma_bf16_ts(R + 64, k < 8 ? R + 192 + k * 8 : R + (k - 8) * 8, db, idesc, k > 0 ? 1u : 0u);
-              }
-            } else if (step == 3) {   // L3: A2 [R+192, +64), W3 (N = 64), K = 128 -> acc3 [R, +64)
-              const uint32_t idesc = umma_idesc_bf16_f32(BM, 64);
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t db = wdesc0 + static_cast<uint64_t>((w_off<C>(3) + (k & 3) * 32) >> 4);
+            umma_bf16_ts(R + 128, R + 64 + k * 8, db, idesc, k > 0 ? 1u : 0u);
+          }
+        }
+      };
+      uint32_t idle = 0;
+      while (left[0] > 0 || left[1] > 0) {
+        if (++idle > (1u << 27)) {   // seconds without progress: fail loudly instead of hanging the device
+          printf("recsys_b200: tower_pp_kernel MMA issuer made no progress (block %d)\n", blockIdx.x);
+          __trap();
+        }
 #pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                const uint64_t db = wdesc0 + static_cast<uint64_t>((w_off<C>(2) + (k >> 2) * (64 * 128) + (k & 3) * 32) >> 4);
-                umma_bf16_ts(R, R + 192 + k * 8, db, idesc, k > 0 ? 1u : 0u);
-              }
-            } else {                  // L4: A3 [R+64, +32), W4 (N = 128), K = 64 -> acc4 [R+128, +128)
-              const uint32_t idesc = umma_idesc_bf16_f32(BM, 128);
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const uint64_t db = wdesc0 + static_cast<uint64_t>((w_off<C>(3) + (k & 3) * 32) >> 4);
-                umma_bf16_ts(R + 128, R + 64 + k * 8, db, idesc, k > 0 ? 1u : 0u);
-              }
-            }
-            umma_commit(&acc_ready[slot]);
-            ++use[slot];
+        for (int slot = 0; slot < 2; ++slot) {
+          if (left[slot] == 0) continue;
+          if (slot == 1 && lag > 0 && left[0] > 0) continue;
+          if (!mbar_test_wait(&a_ready[slot], use[slot] & 1u)) continue;
+          idle = 0;
+          tc_fence_after_sync();
+          issue(slot, step_of[slot]);
+          umma_commit(&acc_ready[slot]);
+          ++use[slot];
+          if (slot == 0 && lag > 0) --lag;
+          if (++step_of[slot] == 5) {
+            step_of[slot] = 0;
+            --left[slot];
           }
         }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= PP_EPI0) {
     // ---------------- epilogue: 8 warps per tile slot ----------------
-    const int ew = warp - 4;
+    const int ew = warp - PP_EPI0;
     const int slot = ew >> 3;
     const int quarter = warp & 3;
     const int half = (ew >> 2) & 1;
@@ -485,14 +523,91 @@ tower_pp_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
         }
       }
     };
-    if (n_slot > 0) load_a0(cta + slot * ncta);
+    // STAGED gather (bf16 table only): a0[4e..4e+3] = 16-byte chunk (lane & 7) of the half-row of tile row
+    // 4e + (lane >> 3) -- eight lanes read one 128-byte half-row, so a load instruction touches 4 lines.  The row ids
+    // are loaded one per lane (coalesced) a tile earlier still and handed round by shuffles.
+    const bool staged_gather = STAGED && pr.table16 != nullptr;
+    uint8_t* const stg0 = stage + ew * (TMAST ? 2 : 1) * TOWER_STAGE_BYTES;
+    // MODE 2: lane 0 issues every bulk store of the warp, one bulk group each; store number n reads buffer n & 1, so a
+    // buffer may be refilled once at most one group (the other buffer's) is still reading
+    uint32_t nst = 0;
+    auto stage_acquire = [&]() -> uint8_t* {
+      if (TMAST) {
+        if (lane == 0) bulk_wait_read<1>();
+        __syncwarp();
+        return stg0 + (nst & 1u) * TOWER_STAGE_BYTES;
+      }
+      __syncwarp();
+      return stg0;
+    };
+    const int l8 = lane & 7, l3 = lane >> 3;
+    auto load_id = [&](int64_t tile_) -> int64_t {
+      const int64_t row_ = tile_ * BM + quarter * 32 + lane;
+      if (row_ >= pr.rows) return -1;
+      return !pr.ids ? row_
+             : pr.ids64 ? static_cast<const int64_t*>(pr.ids)[row_]
+                        : static_cast<int64_t>(static_cast<const int32_t*>(pr.ids)[row_]);
+    };
+    // (Issuing these loads costs the warp 2-3 k cycles per tile in every variant tried -- all eight at once here, or two
+    // per step spread over the tile, thread-per-row or 8 lanes per row: it is not the number of lines in flight.)
+    auto load_a0_staged = [&](int64_t my_id) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int64_t id = __shfl_sync(0xffffffffu, my_id, 4 * e + l3);
+        uint4 u = make_uint4(0u, 0u, 0u, 0u);
+        if (id >= 0 && id < pr.table_rows) u = __ldg(reinterpret_cast<const uint4*>(pr.table16 + id * 128 + half * 64) + l8);
+        a0[4 * e] = u.x; a0[4 * e + 1] = u.y; a0[4 * e + 2] = u.z; a0[4 * e + 3] = u.w;
+      }
+    };
+    int64_t id_next = -1;   // STAGED: this lane's row id for the tile after the one whose rows are in flight
+    if (n_slot > 0) {
+      if (staged_gather) {
+        load_a0_staged(load_id(cta + slot * ncta));
+        if (n_slot > 1) id_next = load_id(cta + (2 + slot) * ncta);
+      } else {
+        load_a0(cta + slot * ncta);
+      }
+    }
     for (int64_t r = 0; r < n_slot; ++r) {
       const int64_t tile = cta + (2 * r + slot) * ncta;
       const int64_t row = tile * BM + quarter * 32 + lane;
-      const bool tr = p.trace && blockIdx.x == 0 && r < 8 && warp == 4 && lane == 0;
-      auto stamp = [&](int k) { if (tr) p.trace[r * 16 + k] = clock64(); };
+      const bool tr = p.trace && blockIdx.x == 0 && r < 8 && (ew & 7) == 0 && lane == 0;
+      auto stamp = [&](int k) { if (tr) p.trace[(slot * 8 + r) * 16 + k] = clock64(); };
       stamp(0);
-      {
+      if (staged_gather) {
+        // transpose through the stage buffer, 32 features (four 16-byte chunks) of all 32 rows at a time: chunk c of
+        // row rr sits at rr*64 + ((c ^ ((rr >> 1) & 3)) << 4) -- conflict-free for the 8-lane phases of both sides
+        uint8_t* const stg = stage_acquire();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t t[16];
+          __syncwarp();
+          if ((l8 >> 2) == h) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int rr = 4 * e + l3;
+              *reinterpret_cast<uint4*>(stg + rr * 64 + (((l8 & 3) ^ ((rr >> 1) & 3)) << 4)) =
+                  make_uint4(a0[4 * e], a0[4 * e + 1], a0[4 * e + 2], a0[4 * e + 3]);
+            }
+          }
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 u = *reinterpret_cast<const uint4*>(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4));
+            t[4 * j] = u.x; t[4 * j + 1] = u.y; t[4 * j + 2] = u.z; t[4 * j + 3] = u.w;
+          }
+          tmem_st_32x32_x16(R + half * 32 + h * 16, t);
+        }
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_ready[slot]);
+        stamp(1);
+        if (r + 1 < n_slot) {
+          load_a0_staged(id_next);
+          id_next = r + 2 < n_slot ? load_id(tile + 4 * ncta) : -1;
+        }
+        stamp(2);
+      } else {
         uint32_t (&r0)[16] = reinterpret_cast<uint32_t (&)[16]>(a0[0]);
         uint32_t (&r1)[16] = reinterpret_cast<uint32_t (&)[16]>(a0[16]);
         __syncwarp();
@@ -517,7 +632,6 @@ tower_pp_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
         chain_wait(&acc_ready[slot], use & 1u);
         tc_fence_after_sync();
         stamp(3 + 2 * step);
-        float dacc[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};   // last step only: this thread's share of pr.dots
 #pragma unroll 1
         for (int c = 0; c < per_warp / 32; ++c) {
           const int col0 = half * per_warp + c * 32;
@@ -546,32 +660,77 @@ tower_pp_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
               for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], 0.0f);
             }
             if (pr.y_il16 && !(p.debug & 64)) {   // rows past the end of the batch land in the scratch's padding
-              uint4* dst = reinterpret_cast<uint4*>(pr.y_il16) +
-                           ((tile * 4 + quarter) * 32 + pr.il_chunk0 + (col0 >> 3)) * 32 + lane;
+              uint4* gdst = reinterpret_cast<uint4*>(pr.y_il16) + ((tile * 4 + quarter) * 32 + pr.il_chunk0 + (col0 >> 3)) * 32;
+              uint4* dst = gdst + lane;
+              uint8_t* buf = nullptr;
+              if (TMAST) {   // this warp's four 512-byte chunks are 2 KB contiguous: one bulk store
+                buf = stage_acquire();
+                dst = reinterpret_cast<uint4*>(buf) + lane;
+              }
 #pragma unroll
               for (int e = 0; e < 4; ++e)
                 dst[e * 32] = make_uint4(pack_bf16x2(v[8 * e], v[8 * e + 1]), pack_bf16x2(v[8 * e + 2], v[8 * e + 3]),
                                          pack_bf16x2(v[8 * e + 4], v[8 * e + 5]), pack_bf16x2(v[8 * e + 6], v[8 * e + 7]));
-            }
-            if (pr.dots && !(p.debug & 32)) {
-              const float* ws = dotw_s + col0;
-#pragma unroll
-              for (int e = 0; e < 32; e += 4) {
-#pragma unroll
-                for (int t = 0; t < 6; ++t) {
-                  const float4 w4 = *reinterpret_cast<const float4*>(ws + t * 128 + e);
-                  dacc[t] = fmaf(v[e], w4.x, dacc[t]); dacc[t] = fmaf(v[e + 1], w4.y, dacc[t]);
-                  dacc[t] = fmaf(v[e + 2], w4.z, dacc[t]); dacc[t] = fmaf(v[e + 3], w4.w, dacc[t]);
+              if (TMAST) {
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                  bulk_store_1d(gdst, buf, 2048);
+                  bulk_commit();
                 }
+                ++nst;
               }
-              if (c == per_warp / 32 - 1) {
-                float* dst = pr.dots + (((tile * 4 + quarter) * 4 + pr.dots_h0 + half) * 6) * 32 + lane;
+            }
+            if (TMAST && pr.y_f32 && pr.y_tma && !(p.debug & 16)) {
+              // fp32 output: 16 rows x 128 B per buffer in the 128B-swizzle layout, one TMA store each (rows past the
+              // end of the batch are clipped by the tensor map)
 #pragma unroll
-                for (int t = 0; t < 6; ++t) dst[t * 32] = dacc[t];
+              for (int h = 0; h < 2; ++h) {
+                uint8_t* buf = stage_acquire();
+                if ((lane >> 4) == h) {
+                  const int rr = lane & 15;
+#pragma unroll
+                  for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<float4*>(buf + rr * 128 + ((j ^ (rr & 7)) << 4)) =
+                        make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                  tma_store_2d(&maps.y[pi], buf, col0, static_cast<int>(tile * BM + quarter * 32 + h * 16));
+                  bulk_commit();
+                }
+                ++nst;
+              }
+            } else if (STAGED && pr.y_f32 && !(p.debug & 16)) {
+              // fp32 output through the stage buffer, 16 rows at a time; stored 8 lanes per 128-byte row segment
+              if (TMAST) {
+                if (lane == 0) bulk_wait_read<0>();
+                __syncwarp();
+              }
+              uint8_t* const stg = stg0;
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                __syncwarp();
+                if ((lane >> 4) == h) {
+                  const int rr = lane & 15;
+#pragma unroll
+                  for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<float4*>(stg + rr * 128 + ((j ^ (rr & 7)) << 4)) =
+                        make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const int rr = 4 * i + l3;
+                  const int64_t grow = tile * BM + quarter * 32 + h * 16 + rr;
+                  const float4 x = *reinterpret_cast<const float4*>(stg + rr * 128 + ((l8 ^ (rr & 7)) << 4));
+                  if (grow < pr.rows) *reinterpret_cast<float4*>(pr.y_f32 + grow * pr.ld_f32 + col0 + 4 * l8) = x;
+                }
               }
             }
             if (row < pr.rows) {
-              if (pr.y_f32 && !(p.debug & 16)) {
+              if (!STAGED && pr.y_f32 && !(p.debug & 16)) {
                 float* dst = pr.y_f32 + row * pr.ld_f32 + col0;
 #pragma unroll
                 for (int e = 0; e < 32; e += 8)
@@ -597,6 +756,7 @@ tower_pp_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
         stamp(4 + 2 * step);
       }
     }
+    if (TMAST && lane == 0) bulk_wait_all();   // the stage buffers (and this CTA) outlive every store
   }
 
   tc_fence_before_sync();
@@ -611,36 +771,48 @@ void launch_tower_pp(const ChainMaps& maps, const ChainParams& p, cudaStream_t s
   static std::once_flag once[64];
   int dev = 0;
   cudaGetDevice(&dev);
-  std::call_once(once[dev & 63], [] {
-    cudaFuncSetAttribute(tower_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, chain_smem<CfgTower>() + 6 * 128 * 4);
+  static int mode_ok[64];   // highest mode whose shared-memory request the device accepted
+  std::call_once(once[dev & 63], [dev] {
+    cudaFuncSetAttribute(tower_pp_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tower_pp_smem(0));
+    cudaFuncSetAttribute(tower_pp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tower_pp_smem(1));
+    const cudaError_t e2 = cudaFuncSetAttribute(tower_pp_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tower_pp_smem(2));
+    if (e2 != cudaSuccess) cudaGetLastError();
+    mode_ok[dev & 63] = e2 == cudaSuccess ? 2 : 1;
   });
+  static const int want = [] { const char* e = getenv("RS_TOWER_STAGE"); return e && e[0] >= '0' && e[0] <= '2' ? e[0] - '0' : 2; }();
+  const int mode = std::min(want, mode_ok[dev & 63]);
+  auto kern = mode == 2 ? tower_pp_kernel<2> : mode == 1 ? tower_pp_kernel<1> : tower_pp_kernel<0>;
+  const int smem = tower_pp_smem(mode);
   int64_t max_tiles = 0;
   for (int i = 0; i < p.n_prob; ++i) max_tiles = std::max<int64_t>(max_tiles, (p.prob[i].rows + BM - 1) / BM);
   const int sms = rs::sm_count();
   // two tiles per CTA at a time: do not spread fewer than 2 tiles per CTA over more CTAs than needed
   int grid = static_cast<int>(std::min<int64_t>((max_tiles + 1) / 2 * p.n_prob, sms - (sms % p.n_prob)));
   grid = std::max(grid, p.n_prob);
+  static const int lag = [] { const char* e = getenv("RS_TOWER_LAG"); return e && e[0] >= '0' && e[0] <= '5' ? e[0] - '0' : 3; }();
+  ChainParams q = p;
+  q.lag = lag;
   const char* tr_env = getenv("RS_CHAIN_TRACE");
-  if (tr_env && tr_env[0] == '1') {   // debugging aid: per-round phase stamps, relative to the first one
-    ChainParams q = p;
-    if (const char* e = getenv("RS_CHAIN_DEBUG")) q.debug = atoi(e);   // 16 / 32 / 64: skip the fp32 / dot / bf16 outputs
-    RS_CUDA(cudaMalloc(&q.trace, 8 * 16 * sizeof(long long)));
-    RS_CUDA(cudaMemsetAsync(q.trace, 0, 8 * 16 * sizeof(long long), st));
-    tower_pp_kernel<<<grid, NTHREADS, chain_smem<CfgTower>() + 6 * 128 * 4, st>>>(maps, q);
+  if (tr_env && tr_env[0] == '1') {   // debugging aid: per-round phase stamps of CTA 0 (both slots), relative to the first one
+    if (const char* e = getenv("RS_CHAIN_DEBUG")) q.debug = atoi(e);   // 16 / 64: skip the fp32 / interleaved bf16 output
+    RS_CUDA(cudaMalloc(&q.trace, 16 * 16 * sizeof(long long)));
+    RS_CUDA(cudaMemsetAsync(q.trace, 0, 16 * 16 * sizeof(long long), st));
+    kern<<<grid, PP_THREADS, smem, st>>>(maps, q);
     RS_LAUNCH_CHECK();
-    long long host[8 * 16];
+    long long host[16 * 16];
     RS_CUDA(cudaStreamSynchronize(st));
     RS_CUDA(cudaMemcpy(host, q.trace, sizeof(host), cudaMemcpyDeviceToHost));
     cudaFree(q.trace);
-    for (int t = 0; t < 8 && host[t * 16 + 1]; ++t) {
-      fprintf(stderr, "tower_pp round %d:", t);
+    for (int t = 0; t < 16; ++t) {
+      if (!host[t * 16 + 1]) continue;
+      fprintf(stderr, "tower_pp slot %d round %d:", t / 8, t % 8);
       for (int k = 0; k < 13; ++k) fprintf(stderr, " %lld", host[t * 16 + k] ? host[t * 16 + k] - host[0] : -1);
       fprintf(stderr, "\n");
     }
     return;
   }
   rs::ProfScope prof(RS_PROF_RANK, st);
-  tower_pp_kernel<<<grid, NTHREADS, chain_smem<CfgTower>() + 6 * 128 * 4, st>>>(maps, p);
+  kern<<<grid, PP_THREADS, smem, st>>>(maps, q);
   RS_LAUNCH_CHECK();
 }
 
@@ -846,20 +1018,24 @@ __global__ void __launch_bounds__(256) cross_heads_kernel(const float* __restric
 //   * the layer-0 A operand comes from tower_pp_kernel's lane-interleaved bf16 copy of x0 (ChainProblem::y_il16):
 //     eight fully coalesced 128-bit loads per thread that land directly in the registers tcgen05.st takes, issued a
 //     whole tile ahead and not touched until then, so their latency and the HBM burst are off the critical path;
-//   * the x0 dots of the cross stack, P_l = x0 . w_l (l < LC), Hr = x0 . head_r[:256], Hc = x0 . head_c[:256], were
-//     taken in fp32 by the tower kernel while x0 was in its registers (ChainProblem::dots, four partials per row);
+//   * the x0 dots of the cross stack, P_l = x0 . w_l (l < LC), Hr = x0 . head_r[:256], Hc = x0 . head_c[:256], ride on
+//     the tensor pipe: layer 0 gets 16 extra output columns (one more N = 16 MMA group on the same A operand) whose
+//     "kernel" rows are the bf16 hi and lo halves of each vector (w = hi + lo to ~2^-17, so only x0's own bf16
+//     rounding -- the one the deep net sees anyway -- is left), accumulated in fp32 in 16 spare TMEM columns.  The
+//     tower kernel used to take these dots on the CUDA cores (6 x 128 FMAs per row fed by broadcast shared-memory
+//     loads); at 128 B/clk of shared-memory return bandwidth that was 6 k cycles per pair of tiles, the largest
+//     single item of its output step (measured with RS_CHAIN_TRACE=1 RS_CHAIN_DEBUG=..);
 //   * the last epilogue dots the fp32 deep output (bias + relu applied) with head_r[256:], head_c[256:] instead of
 //     writing it;
 //   * one thread per row then runs the cross recurrence in closed form.  x_{l+1} = x0 (x_l . w_l) + b_l + x_l keeps
 //     x_l = a_l x0 + c_l with c_l = b_0 + .. + b_{l-1}, so  s_l = a_l P_l + c_l . w_l,  a_{l+1} = a_l + s_l, and
 //     rating = a_L Hr + c_L . head_r[:256] + deep . head_r[256:] + bias  (ctr likewise, through a sigmoid).
 //     The c_l dots are per-model constants (ranker_consts_kernel).
-// Per sample the kernel reads 512 + 96 bytes and writes 8.
+// Per sample the kernel reads 512 bytes and writes 8.
 // ------------------------------------------------------------------------------------------------
 struct DeepHeadsParams {
   int64_t rows;
   const uint16_t* x_il16;  // bf16 x0, lane-interleaved (ChainProblem::y_il16)
-  const float* dots;       // fp32 partial dots of x0 (ChainProblem::dots)
   const float* bias[2];
   const float* hw;         // [2, 384]
   const float* hb;         // [2]
@@ -895,9 +1071,28 @@ __global__ void ranker_consts_kernel(const float* __restrict__ cw, const float* 
   }
 }
 
+constexpr int DOTW_ROWS = 16;                       // extra layer-0 output columns: (hi, lo) x (LC + 2 <= 6 vectors), zero-padded
+constexpr int DOTW_BYTES = DOTW_ROWS * 256 * 2;     // bf16 [16][256], K-major, SWIZZLE_128B: 4 K chunks of [16][64]
+
+// the 16 extra layer-0 rows of the deep net: row 2t = bf16(v_t), row 2t+1 = bf16(v_t - bf16(v_t)) for the vectors
+// v_t = cross kernel t (t < L), then head_r[:256], head_c[:256]; rows beyond 2(L + 2) are zero
+__global__ void ranker_dotw_kernel(const float* __restrict__ cw, const float* __restrict__ hw, int L, uint16_t* __restrict__ out) {
+  const int j = threadIdx.x;   // 256 threads: one feature each
+  for (int t = 0; t < DOTW_ROWS / 2; ++t) {
+    float v = 0.0f;
+    if (t < L) v = cw[t * 256 + j];
+    else if (t < L + 2) v = hw[(t - L) * 384 + j];
+    const uint32_t hi = pack_bf16x2(v, 0.0f) & 0xFFFFu;
+    const float hif = __uint_as_float(hi << 16);
+    const uint32_t lo = pack_bf16x2(v - hif, 0.0f) & 0xFFFFu;
+    out[(2 * t) * 256 + j] = static_cast<uint16_t>(hi);
+    out[(2 * t + 1) * 256 + j] = static_cast<uint16_t>(lo);
+  }
+}
+
 template <int LC>
 constexpr int deep_heads_smem() {
-  return w_off<CfgDeep>(2) + (384 + 256 + 8 + (LC + 4) * 512) * 4 + 256 + 1024;
+  return w_off<CfgDeep>(2) + DOTW_BYTES + (384 + 256 + 8 + 2 * 512) * 4 + 256 + 1024;
 }
 
 template <int LC>
@@ -908,11 +1103,12 @@ deep_heads_kernel(const __grid_constant__ ChainMaps maps, const DeepHeadsParams 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* wsm = base;
-  float* bias_s = reinterpret_cast<float*>(base + w_off<C>(2));
+  uint8_t* dotw_s = base + w_off<C>(2);       // the 16 extra layer-0 "kernel" rows (maps.w[0][2])
+  float* bias_s = reinterpret_cast<float*>(dotw_s + DOTW_BYTES);
   float* hd_s = bias_s + 384;                 // [2][128]: the deep part of the two head rows
   float* const_s = hd_s + 256;                // [LC] c_l . w_l, then c_L . head_r, c_L . head_c
-  float* part = const_s + 8;                  // [(NP + 2)][4 slices][128 rows]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(part + (LC + 4) * 512);
+  float* part = const_s + 8;                  // [2][4 slices][128 rows]: deep . head_r[256:], deep . head_c[256:] partials
+  uint64_t* bars = reinterpret_cast<uint64_t*>(part + 2 * 512);
   uint64_t* wfull = bars;
   uint64_t* a_ready = bars + 1;
   uint64_t* acc_ready = bars + 2;
@@ -926,7 +1122,7 @@ deep_heads_kernel(const __grid_constant__ ChainMaps maps, const DeepHeadsParams 
   const int64_t n_my = cta < ntiles ? (ntiles - cta + ncta - 1) / ncta : 0;
 
   if (warp == 0 && lane == 0) {
-    for (int l = 0; l < 2; ++l) tma_prefetch_desc(&maps.w[0][l]);
+    for (int l = 0; l < 3; ++l) tma_prefetch_desc(&maps.w[0][l]);
     mbar_init(wfull, 1);
     mbar_init(a_ready, EPI_WARPS);
     mbar_init(acc_ready, 1);
@@ -950,11 +1146,13 @@ deep_heads_kernel(const __grid_constant__ ChainMaps maps, const DeepHeadsParams 
 
   if (warp == 0) {
     if (elect_one()) {
-      mbar_arrive_expect_tx(wfull, w_off<C>(2));
+      mbar_arrive_expect_tx(wfull, w_off<C>(2) + DOTW_BYTES);
 #pragma unroll
       for (int l = 0; l < 2; ++l)
         for (int kc = 0; kc < 4; ++kc)
           tma_load_2d(wsm + w_off<C>(l) + kc * (C::N(l) * 128), &maps.w[0][l], wfull, kc * 64, 0, kEvictLast);
+      for (int kc = 0; kc < 4; ++kc)
+        tma_load_2d(dotw_s + kc * (DOTW_ROWS * 128), &maps.w[0][2], wfull, kc * 64, 0, kEvictLast);
     }
   } else if (warp == 1) {
     if (elect_one()) {
@@ -973,6 +1171,14 @@ deep_heads_kernel(const __grid_constant__ ChainMaps maps, const DeepHeadsParams 
             const uint64_t db = wdesc0 + static_cast<uint64_t>((w_off<C>(l) + (k >> 2) * (C::N(l) * 128) + (k & 3) * 32) >> 4);
             umma_bf16_ts(tmem_base + C::DCOL(l), tmem_base + C::ACOL(l) + k * 8, db, idesc, k > 0 ? 1u : 0u);
           }
+          if (l == 0) {   // the x0 dots: same A operand, 16 more output columns -> TMEM [128, 144) (free until layer 1)
+            const uint32_t idesc_d = umma_idesc_bf16_f32(BM, DOTW_ROWS);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              const uint64_t db = wdesc0 + static_cast<uint64_t>((w_off<C>(2) + (k >> 2) * (DOTW_ROWS * 128) + (k & 3) * 32) >> 4);
+              umma_bf16_ts(tmem_base + 128, tmem_base + k * 8, db, idesc_d, k > 0 ? 1u : 0u);
+            }
+          }
           umma_commit(acc_ready);
           if (p.trace && cta == 0 && i < 8) p.trace[i * 16 + 9 + 2 * l] = clock64();
         }
@@ -985,18 +1191,17 @@ deep_heads_kernel(const __grid_constant__ ChainMaps maps, const DeepHeadsParams 
     const uint32_t lane_sel = static_cast<uint32_t>(quarter * 32) << 16;
     const float hb0 = p.hb[0], hb1 = p.hb[1];
     uint32_t use = 0;
-    // One tile ahead, in registers: the A operand (this row's 64-feature slice, 8 x 128 bits) and the tower kernel's
-    // dot partial number `slice` of this row.  Nothing reads them before the next iteration.
+    // One tile ahead, in registers: the A operand (this row's 64-feature slice, 8 x 128 bits).  Nothing reads it
+    // before the next iteration.
     uint4 a0[8];
-    float dn[NP], dc[NP];
+    float pd[NP];   // slice-0 warps: this row's x0 dots of the tile in progress (read from TMEM after layer 0)
+#pragma unroll
+    for (int t = 0; t < NP; ++t) pd[t] = 0.0f;
     auto load_next = [&](int64_t tile_) {
       const bool valid = tile_ * BM + trow < p.rows;
       const uint4* src = reinterpret_cast<const uint4*>(p.x_il16) + ((tile_ * 4 + quarter) * 32 + slice * 8) * 32 + lane;
 #pragma unroll
       for (int e = 0; e < 8; ++e) a0[e] = valid ? __ldg(src + e * 32) : make_uint4(0u, 0u, 0u, 0u);
-      const float* dsrc = p.dots + (((tile_ * 4 + quarter) * 4 + slice) * 6) * 32 + lane;
-#pragma unroll
-      for (int t = 0; t < NP; ++t) dn[t] = valid ? __ldg(dsrc + (t < LC ? t : 4 + t - LC) * 32) : 0.0f;
     };
     // cross recurrence + heads for one finished tile: run by the slice-0 warp of each quarter once the other three
     // warps of the quarter have published their partial dots (named barrier 1 + quarter, 128 threads)
@@ -1008,9 +1213,11 @@ deep_heads_kernel(const __grid_constant__ ChainMaps maps, const DeepHeadsParams 
       asm volatile("bar.sync %0, 128;" ::"r"(1 + quarter) : "memory");
       float s[NP + 2];
 #pragma unroll
-      for (int t = 0; t < NP + 2; ++t)
-        s[t] = (part[(t * 4 + 0) * 128 + trow] + part[(t * 4 + 1) * 128 + trow]) +
-               (part[(t * 4 + 2) * 128 + trow] + part[(t * 4 + 3) * 128 + trow]);
+      for (int t = 0; t < NP; ++t) s[t] = pd[t];
+#pragma unroll
+      for (int t = 0; t < 2; ++t)
+        s[NP + t] = (part[(t * 4 + 0) * 128 + trow] + part[(t * 4 + 1) * 128 + trow]) +
+                    (part[(t * 4 + 2) * 128 + trow] + part[(t * 4 + 3) * 128 + trow]);
       float a = 1.0f;
 #pragma unroll
       for (int l = 0; l < LC; ++l) a += fmaf(a, s[l], const_s[l]);
@@ -1039,8 +1246,6 @@ deep_heads_kernel(const __grid_constant__ ChainMaps maps, const DeepHeadsParams 
       __syncwarp();
       if (lane == 0) mbar_arrive(a_ready);
       stamp(1);
-#pragma unroll
-      for (int t = 0; t < NP; ++t) dc[t] = dn[t];
       // the previous tile's rows, while this tile's layer 0 runs; before the loads below are issued, so that the
       // fence in front of the named barrier has nothing outstanding to wait for
       if (i > 0) finish(tile - ncta);
@@ -1050,7 +1255,6 @@ deep_heads_kernel(const __grid_constant__ ChainMaps maps, const DeepHeadsParams 
       if (i + 2 < n_my && warp == 4 && lane == 0) {   // and the tile after that on its way from HBM to L2
         const int64_t t2 = tile + 2 * ncta;
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.x_il16 + t2 * (BM * 256)), "r"(BM * 256 * 2) : "memory");
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.dots + t2 * (BM * 24)), "r"(BM * 24 * 4) : "memory");
       }
       stamp(3);
 
@@ -1074,6 +1278,12 @@ deep_heads_kernel(const __grid_constant__ ChainMaps maps, const DeepHeadsParams 
           r[e / 2 + 1] = pack_bf16x2_relu(v[e + 2] + b4.z, v[e + 3] + b4.w);
         }
         tmem_st_32x32_x16(tmem_base + (col0 >> 1) + lane_sel, r);
+      }
+      if (slice == 0) {   // the x0 dots of this row: columns [128, 144) hold (hi, lo) pairs
+        float d[16];
+        tmem_ld_32x32_x16(tmem_base + 128 + lane_sel, d);
+#pragma unroll
+        for (int t = 0; t < NP; ++t) pd[t] = d[2 * t] + d[2 * t + 1];
       }
       tc_fence_before_sync();
       __syncwarp();
@@ -1104,10 +1314,8 @@ deep_heads_kernel(const __grid_constant__ ChainMaps maps, const DeepHeadsParams 
           dr = fmaf(y0, r4.x, dr); dr = fmaf(y1, r4.y, dr); dr = fmaf(y2, r4.z, dr); dr = fmaf(y3, r4.w, dr);
           dq = fmaf(y0, c4.x, dq); dq = fmaf(y1, c4.y, dq); dq = fmaf(y2, c4.z, dq); dq = fmaf(y3, c4.w, dq);
         }
-#pragma unroll
-        for (int t = 0; t < NP; ++t) part[(t * 4 + slice) * 128 + trow] = dc[t];
-        part[(NP * 4 + slice) * 128 + trow] = dr;
-        part[((NP + 1) * 4 + slice) * 128 + trow] = dq;
+        part[(0 * 4 + slice) * 128 + trow] = dr;
+        part[(1 * 4 + slice) * 128 + trow] = dq;
       }
       stamp(7);
       // the next tile's A0 (columns [0,128)) does not overlap this tile's last accumulator ([128,256)), which is
@@ -1155,7 +1363,7 @@ struct rs_ranker {
   int64_t table_ld[2] = {0, 0}, table_rows[2] = {0, 0};
   uint16_t* wts = nullptr;      // all bf16 kernels, [out][in] each: user tower, item tower, deep
   float* f32 = nullptr;         // biases (user 576, item 576, deep 384), cross_w [L,256], cross_b [L,256], head_w [2,384], head_b [2]
-  size_t off_w[2][4], off_dw[2];
+  size_t off_w[2][4], off_dw[2], off_dotw;
   size_t off_b[2][4], off_db[2], off_cw, off_cb, off_hw, off_hb, off_const;
   ChainMaps tower_maps, deep_maps;
   ~rs_ranker() {
@@ -1222,6 +1430,8 @@ extern "C" int rs_ranker_create(const DLTensor* user_table, const DLTensor* item
       h->off_db[l] = fb;
       fb += CfgDeep::N(l);
     }
+    h->off_dotw = wb;
+    wb += (size_t)DOTW_ROWS * 256;
     require(cross_w, "cross_w", 2, kDLFloat, 32);
     require(cross_b, "cross_b", 2, kDLFloat, 32);
     require(head_w, "head_w", 2, kDLFloat, 32);
@@ -1278,6 +1488,10 @@ extern "C" int rs_ranker_create(const DLTensor* user_table, const DLTensor* item
       table_to_bf16_kernel<<<blocks, 256, 0, st>>>(h->table[s], h->table_ld[s], h->table_rows[s], h->table16[s]);
       RS_LAUNCH_CHECK();
     }
+    ranker_dotw_kernel<<<1, 256, 0, st>>>(h->f32 + h->off_cw, h->f32 + h->off_hw, static_cast<int>(L), h->wts + h->off_dotw);
+    RS_LAUNCH_CHECK();
+    h->deep_maps.w[0][2] = make_tmap_2d(h->wts + h->off_dotw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)DOTW_ROWS, 256,
+                                        256 * 2, DOTW_ROWS, 64);
     ranker_consts_kernel<<<1, 32, 0, st>>>(h->f32 + h->off_cw, h->f32 + h->off_cb, h->f32 + h->off_hw, static_cast<int>(L),
                                            h->f32 + h->off_const);
     RS_LAUNCH_CHECK();
@@ -1319,10 +1533,8 @@ static int ranker_forward_impl(rs_ranker* h, const DLTensor* user_rows, const DL
     const bool fused = use_fused_heads() && pp;   // default: deep chain + cross + heads in one kernel (needs tower_pp's extra outputs)
     const int64_t tiles = (B + BM - 1) / BM;
     uint16_t* x_il16 = nullptr;   // fused path: bf16 x0, lane-interleaved       (ChainProblem::y_il16)
-    float* dots = nullptr;        // fused path: fp32 partial cross / head dots   (ChainProblem::dots)
     if (fused) {
       RS_CUDA(cudaMallocAsync(&x_il16, sizeof(uint16_t) * (size_t)tiles * BM * 256, st));
-      RS_CUDA(cudaMallocAsync(&dots, sizeof(float) * (size_t)tiles * BM * 24, st));
     }
     if (!fused) {
       RS_CUDA(cudaMallocAsync(&x_bf16, sizeof(uint16_t) * (size_t)B * 256, st));
@@ -1363,19 +1575,21 @@ static int ranker_forward_impl(rs_ranker* h, const DLTensor* user_rows, const DL
         pr.ld_bf16 = 256;
         pr.y_il16 = x_il16;
         pr.il_chunk0 = s * 16;
-        pr.dots = dots;
-        pr.dots_h0 = 2 * s;
-        pr.dot_cw = h->f32 + h->off_cw + s * 128;
-        pr.n_cross = h->cross_layers;
-        pr.dot_hw = h->f32 + h->off_hw + s * 128;
       }
-      if (pp) launch_tower_pp(h->tower_maps, p, st);
-      else launch_chain<CfgTower>(h->tower_maps, p, st);
+      if (pp) {
+        ChainMaps maps = h->tower_maps;
+        for (int s = 0; s < 2; ++s) {
+          maps.y[s] = make_tmap_2d(p.prob[s].y_f32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)B, 128, 256 * 4, 16, 32);
+          p.prob[s].y_tma = 1;
+        }
+        launch_tower_pp(maps, p, st);
+      } else {
+        launch_chain<CfgTower>(h->tower_maps, p, st);
+      }
       if (fused) {
         DeepHeadsParams q{};
         q.rows = B;
         q.x_il16 = x_il16;
-        q.dots = dots;
         for (int l = 0; l < 2; ++l) q.bias[l] = h->f32 + h->off_db[l];
         q.hw = h->f32 + h->off_hw;
         q.hb = h->f32 + h->off_hb;
@@ -1396,7 +1610,6 @@ static int ranker_forward_impl(rs_ranker* h, const DLTensor* user_rows, const DL
           default: RS_CHECK(false, "the fused ranker supports up to 4 cross layers");
         }
         cudaFreeAsync(x_il16, st);
-        cudaFreeAsync(dots, st);
         if (q.trace) {   // debugging aid: per-tile phase stamps of CTA 0, relative to the first one
           long long host[8 * 16];
           RS_CUDA(cudaStreamSynchronize(st));
@@ -1440,7 +1653,6 @@ static int ranker_forward_impl(rs_ranker* h, const DLTensor* user_rows, const DL
       RS_LAUNCH_CHECK();
     } catch (...) {
       if (x_il16) cudaFreeAsync(x_il16, st);
-      if (dots) cudaFreeAsync(dots, st);
       if (x_bf16) cudaFreeAsync(x_bf16, st);
       if (deep_out) cudaFreeAsync(deep_out, st);
       throw;

@@ -91,8 +91,11 @@ def test_multitask_forward_bf16_mode(rs):
 @pytest.mark.parametrize("cross_layers", [0, 1, 3, 4])
 def test_fused_deep_cross_heads_kernel(rs, cross_layers, monkeypatch):
     """deep_heads_kernel (deep chain + closed-form cross recurrence + heads in one launch) against the fp64 oracle and
-    against the three-kernel path it replaces (RS_FUSED_HEADS=0): same bf16 operands, so the two CUDA paths differ only
-    by fp32 re-association (<= 1e-5 of the output scale).  Batch sizes cover <1 tile, ragged tiles and >1 tile per SM."""
+    against the three-kernel path it replaces (RS_FUSED_HEADS=0).  The deep net sees the same bf16 operands on both
+    paths; the cross / head dots over x0 differ: the fused kernel takes them on the tensor pipe from the bf16 copy of
+    x0 (kernel vectors split hi + lo, so only x0's rounding is left), the three-kernel path from fp32 x0.  The two
+    therefore agree to bf16 level, 5e-3 of the output scale (measured up to 2.2e-3) (both stay inside the 1e-2 oracle tolerance).  Batch sizes
+    cover <1 tile, ragged tiles and >1 tile per SM."""
     from oracle.models import MultiTaskModel as OMT
     cfg = rs.ModelConfig()
     cfg.cross_layers = cross_layers
@@ -117,6 +120,27 @@ def test_fused_deep_cross_heads_kernel(rs, cross_layers, monkeypatch):
             got = fused[k_].cpu().numpy().astype(np.float64)
             assert got.shape == want[k_].shape
             assert np.abs(got - want[k_]).max() <= 1e-2 * scale, (k_, B)
-            assert (fused[k_] - unfused[k_]).abs().max().item() <= 1e-5 * scale, (k_, B)
+            assert (fused[k_] - unfused[k_]).abs().max().item() <= 5e-3 * scale, (k_, B)
         assert torch.equal(fused["user_embedding"], unfused["user_embedding"])
         assert torch.equal(fused["item_embedding"], unfused["item_embedding"])
+
+
+@pytest.mark.parametrize("B", [77, 4096])
+def test_ranking_session_replays_the_eager_forward(rs, B):
+    """RankingSession (one CUDA graph per fixed batch) == the eager call, bit for bit, also after new ids are copied in."""
+    cfg = rs.ModelConfig()
+    w = rs.synth.make_weights(cfg, 500, 300, seed=31)
+    uv, iv = rs.synth.make_vocab(500), rs.synth.make_vocab(300)
+    m = rs.MultiTaskModel(cfg, uv, iv, {}, precision="bf16")
+    rs.load_weights(m, w)
+    sess = m.ranking_session(B)
+    rng = np.random.default_rng(B)
+    for _ in range(2):
+        ur, ir = rs.synth.make_ids(rng, 500, B), rs.synth.make_ids(rng, 300, B)
+        got = sess({"user_id": dev(ur.astype(np.int32)), "movie_id": dev(ir.astype(np.int32))})
+        got = {k_: v.clone() for k_, v in got.items()}
+        want = m({"user_id": dev(ur), "movie_id": dev(ir)})
+        for k_ in want:
+            assert torch.equal(got[k_], want[k_]), k_
+    with pytest.raises(ValueError):
+        sess({"user_id": dev(ur[:5]), "movie_id": dev(ir[:5])})
