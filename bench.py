@@ -222,6 +222,8 @@ def main():
     sidx._local_deferred = lambda q_, k_, out: local_deferred(q_, k_, id_base=sidx.row_begin, mode=args.mode, out=out)
     sidx.shared_threshold = args.mode != "exact" and os.environ.get("RS_SHARED_THRESHOLD", "1") != "0"
     sidx.use_graph = world > 1 and os.environ.get("RS_SHARDED_GRAPH", "1") != "0"   # one CUDA-graph replay per step
+    # both exchanges of a step through NVLink peer memory (csrc/peer.cu; "nccl" = two NCCL all-gathers)
+    sidx.exchange = os.environ.get("RS_SHARDED_EXCHANGE", "p2p") if world > 1 else "nccl"
 
     gq = torch.Generator(device=device)
     gq.manual_seed(3999)
@@ -374,6 +376,9 @@ def main():
                 "cpu_baseline": cpu, "ranking": ranking, "batch1_latency": batch1}
         if world > 1:
             line["exchange_bytes_per_step_per_rank"] = gather_bytes(world, nq, k)
+            line["config"]["exchange"] = ("NVLink peer memory: each rank stores its message into every peer's region and raises a flag "
+                                          "(rs_peer_publish / wait / ack, no NCCL on the step)" if sidx.exchange == "p2p"
+                                          else "two NCCL all-gathers per step")
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)

@@ -249,6 +249,30 @@ int rs_matvec(const DLTensor* items, const DLTensor* user, DLTensor* out, void* 
 int rs_topk_merge(const DLTensor* Dparts, const DLTensor* Iparts, DLTensor* D, DLTensor* I,
                   void* stream);
 
+/*
+ * K7p. The exchange step of the sharded search over NVLink peer memory instead of an NCCL all-gather (new in this
+ * build; SURVEY.md section 8e "write partial lists straight into peers' buffers").  One process per GPU.  Every rank
+ * creates a region of `world` slots of slot_bytes (multiple of 16) and gets a 64-byte CUDA IPC handle for it; the
+ * caller exchanges the handles once (any transport; the Python side uses one torch.distributed all-gather) and
+ * passes all of them, rank-major, to rs_peer_connect.  Per step and rank, stream-ordered and graph-capturable:
+ *   rs_peer_publish  copy src (uint8 [bytes <= slot_bytes], 16-byte aligned) into slot `rank` of EVERY rank's region
+ *                    and release this step's number into every rank's flags; waits first until all peers have
+ *                    acknowledged the previous step, so one region is enough and its address never changes
+ *   rs_peer_wait     returns (on the stream) once the local region holds this step's message of all `world` ranks;
+ *                    rs_peer_local gives the region: message g at data + g * slot_bytes
+ *   rs_peer_ack      after the kernels that read the region: tell every rank this step has been consumed
+ * All ranks must issue the same sequence.  A peer that never arrives trips a ~10 s device-side timeout (trap) rather
+ * than a hang.  world <= 16.
+ */
+typedef struct rs_peer rs_peer_t;
+int rs_peer_create(int rank, int world, int64_t slot_bytes, rs_peer_t** out, void* handle_out /* 64 bytes, host */);
+int rs_peer_connect(rs_peer_t* h, const void* handles /* world x 64 bytes, host */);
+int rs_peer_local(rs_peer_t* h, void** data, int64_t* bytes);
+int rs_peer_publish(rs_peer_t* h, const DLTensor* src, void* stream);
+int rs_peer_wait(rs_peer_t* h, void* stream);
+int rs_peer_ack(rs_peer_t* h, void* stream);
+int rs_peer_free(rs_peer_t* h);
+
 /* counters for the bench's gpu_launches claim: kernels launched by this library so far */
 int64_t rs_launch_count(void);
 

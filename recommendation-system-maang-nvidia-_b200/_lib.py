@@ -112,6 +112,13 @@ def load():
         "rs_debug_tensor_scores": [vp, _DLP, _DLP, vp],
         "rs_matvec": [_DLP, _DLP, _DLP, vp],
         "rs_topk_merge": [_DLP, _DLP, _DLP, _DLP, vp],
+        "rs_peer_create": [i32, i32, i64, ctypes.POINTER(vp), vp],
+        "rs_peer_connect": [vp, vp],
+        "rs_peer_local": [vp, ctypes.POINTER(vp), ctypes.POINTER(i64)],
+        "rs_peer_publish": [vp, _DLP, vp],
+        "rs_peer_wait": [vp, vp],
+        "rs_peer_ack": [vp, vp],
+        "rs_peer_free": [vp],
         "rs_prof_enable": [i32],
         "rs_prof_read": [i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64)],
     }
@@ -128,7 +135,8 @@ EXPORTED = ["rs_version", "rs_last_error", "rs_launch_count", "rs_device_sm_coun
             "rs_index_free", "rs_index_add", "rs_index_ntotal", "rs_index_dim", "rs_index_reconstruct", "rs_index_search", "rs_index_search_deferred",
             "rs_tensor_plan", "rs_tensor_threshold_rank", "rs_index_shared_begin", "rs_index_shared_finish", "rs_tc_session_free", "rs_topk_verify",
             "rs_index_fallbacks", "rs_debug_tensor_scores",
-            "rs_matvec", "rs_topk_merge", "rs_prof_enable", "rs_prof_read"]
+            "rs_matvec", "rs_topk_merge", "rs_prof_enable", "rs_prof_read",
+            "rs_peer_create", "rs_peer_connect", "rs_peer_local", "rs_peer_publish", "rs_peer_wait", "rs_peer_ack", "rs_peer_free"]
 
 PROF_SCAN, PROF_MERGE, PROF_FILTER, PROF_RESCORE, PROF_RANK, PROF_SAMPLE = 0, 1, 2, 3, 4, 5
 

@@ -37,6 +37,63 @@ def exchange_layout(nq: int, k: int) -> Tuple[int, int, int]:
     return off_I, off_F, _round_up(off_F + nq * 8, 16)
 
 
+class _DeviceBytes:
+    """Raw device memory as a __cuda_array_interface__ object, so torch can view it without a copy."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+class PeerExchange:
+    """All-gather of one byte message per rank over NVLink peer memory (csrc/peer.cu) instead of NCCL.
+
+    Every rank owns a region of `world` slots, exported through CUDA IPC; `publish(msg)` copies the message into slot
+    `rank` of every rank's region and raises a flag there, `gathered()` returns -- stream-ordered behind a kernel that
+    waits for all flags -- the local region as a uint8 [world, slot_bytes] tensor (no copy: the merge kernel reads
+    the parts in place), `done()` tells the peers the region may be overwritten by the next step.  Construction is
+    collective (the IPC handles are all-gathered once through torch.distributed); the three per-step calls are plain
+    kernel launches and can be captured in a CUDA graph."""
+
+    def __init__(self, slot_bytes: int, device: torch.device, group: Optional[dist.ProcessGroup] = None):
+        import ctypes
+        from . import _lib
+        self._lib_mod, self._lib = _lib, _lib.load()
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.slot_bytes = _round_up(int(slot_bytes), 16)
+        self.device = device
+        self._h = ctypes.c_void_p()
+        handle = (ctypes.c_uint8 * 64)()
+        _lib.check(self._lib.rs_peer_create(self.rank, self.world, self.slot_bytes, ctypes.byref(self._h), handle))
+        mine = torch.tensor(list(handle), dtype=torch.uint8).to(device)
+        everyone = torch.empty((self.world * 64,), dtype=torch.uint8, device=device)
+        dist.all_gather_into_tensor(everyone, mine, group=group)
+        blob = bytes(everyone.cpu().tolist())
+        _lib.check(self._lib.rs_peer_connect(self._h, ctypes.c_char_p(blob)))
+        ptr, n = ctypes.c_void_p(), ctypes.c_int64()
+        _lib.check(self._lib.rs_peer_local(self._h, ctypes.byref(ptr), ctypes.byref(n)))
+        self._mem = _DeviceBytes(ptr.value, n.value)
+        self.region = torch.as_tensor(self._mem, device=device).view(self.world, self.slot_bytes)
+        dist.barrier(group=group)          # nobody publishes into a region that is not mapped everywhere yet
+
+    def publish(self, msg: torch.Tensor) -> None:
+        b = self._lib_mod.dl(msg)
+        self._lib_mod.check(self._lib.rs_peer_publish(self._h, b.ptr, self._lib_mod.stream_ptr()))
+
+    def gathered(self) -> torch.Tensor:
+        self._lib_mod.check(self._lib.rs_peer_wait(self._h, self._lib_mod.stream_ptr()))
+        return self.region
+
+    def done(self) -> None:
+        self._lib_mod.check(self._lib.rs_peer_ack(self._h, self._lib_mod.stream_ptr()))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.region = None
+            self._lib_mod.check(self._lib.rs_peer_free(self._h))
+            self._h = None
+
+
 class ShardedIndexFlatIP:
     def __init__(self, d: int, n_total: int, group: Optional[dist.ProcessGroup] = None,
                  local_index=None, local_search: Optional[Callable] = None, merge: Optional[Callable] = None,
@@ -75,6 +132,8 @@ class ShardedIndexFlatIP:
             self._rank = rank            # (k, rho) -> rank of the sample maximum to use as the threshold
         self.shared_threshold = True     # set False to keep per-shard thresholds (one exchange fewer, ~8x the candidates)
         self.use_graph = False           # replay each (nq, k) step as one CUDA graph (CUDA queries only)
+        self.exchange = "nccl"           # "p2p": both exchanges of a step through NVLink peer memory (PeerExchange)
+        self._peers = {}
         self._graphs = {}
         self._last_need = None
 
@@ -151,6 +210,19 @@ class ShardedIndexFlatIP:
             torch.cuda.synchronize()
             self._graphs.clear()
             torch.cuda.synchronize()
+        for pair in self._peers.values():
+            for pe in pair:
+                if pe is not None:
+                    pe.close()
+        self._peers.clear()
+
+    def _peer_pair(self, nq: int, k: int, rank_pad: int, dev):
+        """(tops exchange or None, lists exchange) for this (nq, k): created collectively on first use."""
+        key = (nq, k, rank_pad)
+        if key not in self._peers:
+            tops = PeerExchange(nq * rank_pad * 4, dev, self.group) if rank_pad > 0 else None
+            self._peers[key] = (tops, PeerExchange(exchange_layout(nq, k)[2], dev, self.group))
+        return self._peers[key]
 
     def _step(self, q, k: int):
         """Queues one whole search step (no host synchronisation) -> (D, I, need bool [nq])."""
@@ -164,19 +236,33 @@ class ShardedIndexFlatIP:
                send[off_F:off_F + nq * 4].view(torch.int32),
                send[off_F + nq * 4:off_F + nq * 8].view(torch.float32))
         rank = self._shared_rank(nq, k) if (self.shared_threshold and self._shared is not None) else 0
+        p2p = self.exchange == "p2p" and dev.type == "cuda"
+        # peer-memory messages are copied with 128-bit stores: the tops carry rank rounded up to 4 columns
+        rank_pad = _round_up(rank, 4) if p2p else rank
+        pe_tops, pe_lists = self._peer_pair(nq, k, rank_pad, dev) if p2p else (None, None)
         if rank > 0:
             # threshold shared by all shards: each contributes the `rank` largest maxima of its own sample
             begin, finish = self._shared
-            top = torch.empty((nq, rank), dtype=torch.float32, device=dev)
+            top = torch.empty((nq, rank_pad), dtype=torch.float32, device=dev)
             sess = begin(q, k, top)
-            tops = torch.empty((G * nq, rank), dtype=torch.float32, device=dev)
-            dist.all_gather_into_tensor(tops, top, group=self.group)
-            finish(sess, tops.view(G, nq, rank), rank, out)
+            if p2p:
+                pe_tops.publish(top.view(-1).view(torch.uint8))
+                tops = pe_tops.gathered().view(torch.float32).view(G, nq, rank_pad)
+                finish(sess, tops, rank, out)
+                pe_tops.done()
+            else:
+                tops = torch.empty((G * nq, rank), dtype=torch.float32, device=dev)
+                dist.all_gather_into_tensor(tops, top, group=self.group)
+                finish(sess, tops.view(G, nq, rank), rank, out)
         else:
             self._local_deferred(q, k, out[:3])
-        recv = torch.empty((G * total,), dtype=torch.uint8, device=dev)
-        dist.all_gather_into_tensor(recv, send, group=self.group)
-        R = recv.view(G, total)
+        if p2p:
+            pe_lists.publish(send)
+            R = pe_lists.gathered()                                              # [G, total] in place, no copy
+        else:
+            recv = torch.empty((G * total,), dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(recv, send, group=self.group)
+            R = recv.view(G, total)
         Dg = R[:, :nq * k * 4].view(torch.float32).view(G, nq, k)            # parts strided by `total` bytes
         Ig = R[:, off_I:off_I + nq * k * 8].view(torch.int64).view(G, nq, k)
         Fg = R[:, off_F:off_F + nq * 4].view(torch.int32)                    # [G, nq]
@@ -186,6 +272,8 @@ class ShardedIndexFlatIP:
             need = self._verify(D, I, Bg, Fg).ne(0)
         else:
             need = Fg.ne(0).any(dim=0)                                       # the same on every rank
+        if p2p:
+            pe_lists.done()                                                  # merge / verify have read the region
         self._last_need = need
         return D, I, need
 

@@ -1,0 +1,41 @@
+"""GPU test of the peer-memory exchange kernels (csrc/peer.cu) with a single rank: publish / wait / ack over several
+steps, message sizes that are not multiples of 16 bytes, and the region view.  The multi-rank protocol (remote stores
+over NVLink, flags from other GPUs) is exercised by tools/multi_gpu_check.py on 2 and 8 GPUs."""
+
+import ctypes
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_peer_exchange_single_rank_steps(rs):
+    _lib = rs._lib
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    handle = (ctypes.c_uint8 * 64)()
+    slot = 4096
+    _lib.check(lib.rs_peer_create(0, 1, slot, ctypes.byref(h), handle))
+    _lib.check(lib.rs_peer_connect(h, ctypes.c_char_p(bytes(handle))))
+    ptr, n = ctypes.c_void_p(), ctypes.c_int64()
+    _lib.check(lib.rs_peer_local(h, ctypes.byref(ptr), ctypes.byref(n)))
+    assert n.value == slot
+
+    from recsys_b200.sharded import _DeviceBytes
+    region = torch.as_tensor(_DeviceBytes(ptr.value, n.value), device="cuda")
+    g = torch.Generator(device="cuda").manual_seed(7)
+    for step, nbytes in enumerate((4096, 16, 1000, 4093, 0, 2048)):
+        msg = torch.randint(0, 256, (max(nbytes, 1),), dtype=torch.uint8, device="cuda", generator=g)[:nbytes]
+        b = _lib.dl(msg)
+        _lib.check(lib.rs_peer_publish(h, b.ptr, _lib.stream_ptr()))
+        _lib.check(lib.rs_peer_wait(h, _lib.stream_ptr()))
+        got = region[:nbytes].clone()
+        _lib.check(lib.rs_peer_ack(h, _lib.stream_ptr()))
+        torch.cuda.synchronize()
+        assert torch.equal(got, msg), (step, nbytes)
+    too_long = torch.zeros(slot + 16, dtype=torch.uint8, device="cuda")
+    b = _lib.dl(too_long)
+    with pytest.raises(RuntimeError):
+        _lib.check(lib.rs_peer_publish(h, b.ptr, _lib.stream_ptr()))
+    _lib.check(lib.rs_peer_free(h))

@@ -76,6 +76,27 @@ def main():
     D, I = sidx.search(q2, k)
     assert torch.equal(I, torch.roll(Iw, 7, dims=0)) and torch.equal(D, torch.roll(Dw, 7, dims=0))
     sidx.use_graph = False
+    # both exchanges of the step through NVLink peer memory (csrc/peer.cu) instead of NCCL: eager, graph, other shapes
+    sidx.exchange = "p2p"
+    for _ in range(3):
+        D, I = sidx.search(q, k)
+        assert torch.equal(I, Iw) and torch.equal(D, Dw), f"rank {rank}: peer-memory sharded search differs"
+    sidx.use_graph = True
+    for shift in (0, 0, 5, 11):
+        qs = torch.roll(q, shift, dims=0).contiguous()
+        D, I = sidx.search(qs, k)
+        assert torch.equal(I, torch.roll(Iw, shift, dims=0)) and torch.equal(D, torch.roll(Dw, shift, dims=0)), \
+            f"rank {rank}: graph-replayed peer-memory search differs (shift {shift})"
+    sidx.use_graph = False
+    sidx.shared_threshold = False                                   # per-shard thresholds: one exchange per step
+    D, I = sidx.search(q, k)
+    assert torch.equal(I, Iw) and torch.equal(D, Dw), f"rank {rank}: peer-memory search (per-shard thresholds) differs"
+    sidx.shared_threshold = True
+    D7, I7 = sidx.search(q[:7].contiguous(), 10)                    # ragged shape: rank padded to 4 columns
+    assert torch.equal(I7, Iw[:7, :10]) and torch.equal(D7, Dw[:7, :10])
+    assert sidx.fallbacks == world + 1
+    if rank == 0:
+        print("peer-memory exchange OK (eager, CUDA graph, per-shard thresholds, ragged shapes)", flush=True)
     # batch-1 (config 5)
     D1, I1 = sidx.search(q[:1].contiguous(), 10)
     assert torch.equal(I1, Iw[:1, :10])
