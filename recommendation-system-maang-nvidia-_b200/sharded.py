@@ -134,6 +134,7 @@ class ShardedIndexFlatIP:
         self.use_graph = False           # replay each (nq, k) step as one CUDA graph (CUDA queries only)
         self.exchange = "nccl"           # "p2p": both exchanges of a step through NVLink peer memory (PeerExchange)
         self._peers = {}
+        self._peer_factory = None        # tests: nbytes -> object with publish / gathered / done / close
         self._graphs = {}
         self._last_need = None
 
@@ -217,11 +218,30 @@ class ShardedIndexFlatIP:
         self._peers.clear()
 
     def _peer_pair(self, nq: int, k: int, rank_pad: int, dev):
-        """(tops exchange or None, lists exchange) for this (nq, k): created collectively on first use."""
+        """(tops exchange or None, lists exchange) for this (nq, k): created collectively on first use.  If any rank
+        cannot map its peers (no CUDA IPC / peer access on this box) every rank falls back to the NCCL all-gathers."""
         key = (nq, k, rank_pad)
         if key not in self._peers:
-            tops = PeerExchange(nq * rank_pad * 4, dev, self.group) if rank_pad > 0 else None
-            self._peers[key] = (tops, PeerExchange(exchange_layout(nq, k)[2], dev, self.group))
+            make = self._peer_factory or (lambda nbytes: PeerExchange(nbytes, dev, self.group))
+            pair, ok = [None, None], 1
+            try:
+                if rank_pad > 0:
+                    pair[0] = make(nq * rank_pad * 4)
+                pair[1] = make(exchange_layout(nq, k)[2])
+            except RuntimeError as e:          # librecsys_b200 reports CUDA errors as RuntimeError
+                ok, self._peer_error = 0, str(e)
+            flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+            if int(flag.item()) == 0:
+                for pe in pair:
+                    if pe is not None:
+                        pe.close()
+                import warnings
+                warnings.warn("peer-memory exchange unavailable on some rank (%s); using NCCL all-gathers"
+                              % getattr(self, "_peer_error", "failure on another rank"))
+                self.exchange = "nccl"
+                return None
+            self._peers[key] = tuple(pair)
         return self._peers[key]
 
     def _step(self, q, k: int):
@@ -236,10 +256,16 @@ class ShardedIndexFlatIP:
                send[off_F:off_F + nq * 4].view(torch.int32),
                send[off_F + nq * 4:off_F + nq * 8].view(torch.float32))
         rank = self._shared_rank(nq, k) if (self.shared_threshold and self._shared is not None) else 0
-        p2p = self.exchange == "p2p" and dev.type == "cuda"
-        # peer-memory messages are copied with 128-bit stores: the tops carry rank rounded up to 4 columns
+        p2p = self.exchange == "p2p" and (dev.type == "cuda" or self._peer_factory is not None)
+        pe_tops = pe_lists = None
+        if p2p:
+            # peer-memory messages are copied with 128-bit stores: the tops carry rank rounded up to 4 columns
+            pair = self._peer_pair(nq, k, _round_up(rank, 4), dev)
+            if pair is None:
+                p2p = False
+            else:
+                pe_tops, pe_lists = pair
         rank_pad = _round_up(rank, 4) if p2p else rank
-        pe_tops, pe_lists = self._peer_pair(nq, k, rank_pad, dev) if p2p else (None, None)
         if rank > 0:
             # threshold shared by all shards: each contributes the `rank` largest maxima of its own sample
             begin, finish = self._shared

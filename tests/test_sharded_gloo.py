@@ -132,6 +132,59 @@ def _worker(rank, world, port, n, nq, k, out_dir):
             np.testing.assert_array_equal(I3.numpy(), Iw)
             np.testing.assert_array_equal(D3.numpy(), Dw)
             assert (sh.fallbacks > 0) == expect_fallbacks, sh.fallbacks
+
+        # exchange="p2p" host logic (csrc/peer.cu does this with NVLink stores on the GPU): the messages travel through
+        # an object with publish / gathered / done -- here a gloo stand-in that keeps the region layout [world, slot]
+        # -- the tops carry the rank padded to 4 columns, and the consumers read the parts out of the region in place.
+        class FakePeer:
+            log = []
+
+            def __init__(self, nbytes):
+                assert nbytes % 16 == 0
+                self.slot, self.region, self.pending = nbytes, torch.zeros((world, nbytes), dtype=torch.uint8), None
+
+            def publish(self, msg):
+                assert msg.dtype == torch.uint8 and msg.dim() == 1 and msg.numel() <= self.slot
+                self.pending = torch.zeros(self.slot, dtype=torch.uint8)
+                self.pending[:msg.numel()] = msg
+
+            def gathered(self):
+                dist.all_gather_into_tensor(self.region.view(-1), self.pending)
+                return self.region
+
+            def done(self):
+                FakePeer.log.append(self.slot)
+
+            def close(self):
+                pass
+
+        if k <= 128:
+            sh = ShardedIndexFlatIP(64, n, local_search=local_search, merge=merge_strided, local_deferred=local_deferred,
+                                    shared=(begin, finish), plan=lambda rows, nq_, kk: (True, (rows + 4) // 5),
+                                    rank=lambda kk, rho: int(np.ceil((2 + np.sqrt(4 + 2 * kk * rho)) ** 2)), verify=verify)
+            sh.exchange, sh._peer_factory = "p2p", FakePeer
+            r_ = sh._shared_rank(nq, k)
+            for _ in range(2):
+                D4, I4 = sh.search(q, k)
+                np.testing.assert_array_equal(I4.numpy(), Iw)
+                np.testing.assert_array_equal(D4.numpy(), Dw)
+            r_pad = (r_ + 3) // 4 * 4
+            assert FakePeer.log == [nq * r_pad * 4, total] * 2          # tops then lists, every step; created once
+            assert len(sh._peers) == 1
+
+            # a rank that cannot map its peers makes EVERY rank fall back to the NCCL / gloo all-gathers
+            def broken(nbytes):
+                if rank == world - 1:
+                    raise RuntimeError("librecsys_b200: cudaIpcOpenMemHandle failed (stand-in)")
+                return FakePeer(nbytes)
+            sh2 = ShardedIndexFlatIP(64, n, local_search=local_search, merge=merge_strided, local_deferred=local_deferred)
+            sh2.exchange, sh2._peer_factory = "p2p", broken
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                D5, I5 = sh2.search(q, k)
+            np.testing.assert_array_equal(I5.numpy(), Iw)
+            assert sh2.exchange == "nccl" and not sh2._peers
     finally:
         dist.destroy_process_group()
 
