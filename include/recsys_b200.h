@@ -272,6 +272,26 @@ int rs_peer_publish(rs_peer_t* h, const DLTensor* src, void* stream);
 int rs_peer_wait(rs_peer_t* h, void* stream);
 int rs_peer_ack(rs_peer_t* h, void* stream);
 int rs_peer_free(rs_peer_t* h);
+/*
+ * K7q. Sharded embedding lookups (BASELINE config 4) over the same peer regions: both all-to-alls of a lookup are
+ * stores into peer memory with device-known counts (no NCCL, no host synchronisation, exact byte counts), and the
+ * owner-side row gather writes straight into the requester's region.  Rows are sharded `row mod G`.
+ *   rs_a2a_plan_peer  ids int64 [B] -> counts [G], stage [G, b_max] (local row numbers `row div G` per owner) and
+ *                     inv [B] (row of this rank's rows region [G * b_max, dim] where each id's embedding will land).
+ *                     dedup != 0: each distinct id is requested once (open-addressing hash table in keys [H] int64 /
+ *                     vals [H] int32, H a power of two >= 2B; slot_of [B] int32 scratch); dedup == 0: keys / vals /
+ *                     slot_of may be NULL.  Negative ids are clamped to 0 (as rs_a2a_scatter does).
+ *   rs_peer_a2a_ids   ids region (slots of >= 16 + 8 * b_max bytes): list for owner g -> slot `rank` of g's region
+ *   (rs_peer_wait on the ids region)
+ *   rs_peer_a2a_rows  on the owner: table f32 [n_local, dim] rows named by every requester's list -> slot `rank` of
+ *                     that requester's rows region (slots of >= b_max * dim * 4 bytes); out-of-range rows are zeros
+ *   (rs_peer_ack on the ids region; rs_peer_wait on the rows region; gather the rows region with inv as ids --
+ *    rs_gather_concat; rs_peer_ack on the rows region)
+ */
+int rs_a2a_plan_peer(const DLTensor* ids, int n_shards, int dedup, DLTensor* keys, DLTensor* vals, DLTensor* slot_of,
+                     DLTensor* counts, DLTensor* stage, DLTensor* inv, void* stream);
+int rs_peer_a2a_ids(rs_peer_t* ids_region, const DLTensor* stage, const DLTensor* counts, void* stream);
+int rs_peer_a2a_rows(rs_peer_t* ids_region, rs_peer_t* rows_region, const DLTensor* table, void* stream);
 
 /* counters for the bench's gpu_launches claim: kernels launched by this library so far */
 int64_t rs_launch_count(void);

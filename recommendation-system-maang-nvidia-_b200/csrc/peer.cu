@@ -16,6 +16,7 @@
 //
 // The step number lives in device memory and is advanced by publish itself, so the three launches can be captured in
 // a CUDA graph and replayed.  Every spin has a ~10 s budget and traps with a message instead of hanging the device.
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <memory>
@@ -82,14 +83,35 @@ __device__ __forceinline__ void spin_until(const uint64_t* p, uint64_t want, con
   }
 }
 
-__global__ void __launch_bounds__(256) peer_publish_kernel(uint8_t* const* __restrict__ bases, const PeerLayout L,
-                                                            const uint8_t* __restrict__ src, int64_t bytes) {
-  uint8_t* local = bases[L.rank];
+// Every CTA of a publishing kernel: the step number this launch will publish, after every peer has acknowledged the
+// previous step (its slot in their regions may then be overwritten).
+__device__ __forceinline__ uint64_t peer_begin(const uint8_t* local, const PeerLayout& L) {
   const uint64_t seq = *reinterpret_cast<const uint64_t*>(local + L.off_seq) + 1;
-  // every peer must have consumed the previous message before its slot is overwritten
   if (threadIdx.x < L.world)
     spin_until(reinterpret_cast<const uint64_t*>(local + L.off_acks) + threadIdx.x, seq - 1, "a peer's ack");
   __syncthreads();
+  return seq;
+}
+// Every CTA, after its last store into the peers' regions: the last CTA to get here raises this rank's flag in every
+// region (system-scope release, behind a fence that covers all CTAs' stores) and advances the local step number.
+__device__ __forceinline__ void peer_finish(uint8_t* const* bases, const PeerLayout& L, uint64_t seq) {
+  uint8_t* local = bases[L.rank];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int* done = reinterpret_cast<unsigned int*>(local + L.off_done);
+    if (atomicAdd(done, 1u) == gridDim.x - 1) {
+      *done = 0;
+      __threadfence_system();
+      for (int g = 0; g < L.world; ++g) st_release_sys(reinterpret_cast<uint64_t*>(bases[g] + L.off_flags) + L.rank, seq);
+      *reinterpret_cast<uint64_t*>(local + L.off_seq) = seq;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) peer_publish_kernel(uint8_t* const* __restrict__ bases, const PeerLayout L,
+                                                            const uint8_t* __restrict__ src, int64_t bytes) {
+  const uint64_t seq = peer_begin(bases[L.rank], L);
   const int64_t n16 = bytes >> 4;
   const uint4* s4 = reinterpret_cast<const uint4*>(src);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x) {
@@ -99,17 +121,7 @@ __global__ void __launch_bounds__(256) peer_publish_kernel(uint8_t* const* __res
   if (blockIdx.x == 0)
     for (int64_t i = (n16 << 4) + threadIdx.x; i < bytes; i += blockDim.x)
       for (int g = 0; g < L.world; ++g) (bases[g] + L.rank * L.slot_bytes)[i] = src[i];
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned int* done = reinterpret_cast<unsigned int*>(local + L.off_done);
-    if (atomicAdd(done, 1u) == gridDim.x - 1) {   // every CTA's stores are ordered before this point
-      *done = 0;
-      __threadfence_system();
-      for (int g = 0; g < L.world; ++g) st_release_sys(reinterpret_cast<uint64_t*>(bases[g] + L.off_flags) + L.rank, seq);
-      *reinterpret_cast<uint64_t*>(local + L.off_seq) = seq;
-    }
-  }
+  peer_finish(bases, L, seq);
 }
 
 __global__ void peer_wait_kernel(const uint8_t* __restrict__ local, const PeerLayout L) {
@@ -121,6 +133,134 @@ __global__ void peer_wait_kernel(const uint8_t* __restrict__ local, const PeerLa
 __global__ void peer_ack_kernel(uint8_t* const* __restrict__ bases, const PeerLayout L) {
   const uint64_t seq = *reinterpret_cast<const uint64_t*>(bases[L.rank] + L.off_seq);
   if (threadIdx.x < L.world) st_release_sys(reinterpret_cast<uint64_t*>(bases[threadIdx.x] + L.off_acks) + L.rank, seq);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Sharded embedding lookups (BASELINE config 4) over the same regions: both all-to-alls of a lookup are stores into
+// peer memory with DEVICE-known counts -- no NCCL, no host synchronisation, exact byte counts, and the owner-side
+// row gather is fused with the way back (the gathered rows are written straight into the requester's region).
+//   plan      (lookup_* kernels) optional de-duplication through an open-addressing hash table, per-owner lists of
+//             local row numbers (row div G), inv[i] = where id i's row will land in this rank's rows region
+//   ids out   a2a_ids_kernel: list for owner g -> slot `rank` of g's ids region, [count | pad | rows ...]
+//   rows back a2a_rows_kernel (on the owner): one warp per requested row, table row -> slot `rank` of the
+//             requester's rows region
+//   restore   gather_concat_kernel over the local rows region with inv as ids
+// ------------------------------------------------------------------------------------------------
+constexpr unsigned long long kEmptyKey = ~0ull;
+constexpr int kIdsHeader = 16;   // bytes in front of the row numbers of an ids message: int64 count + padding
+
+__device__ __forceinline__ uint32_t hash_u64(uint64_t x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+  return static_cast<uint32_t>(x);
+}
+__device__ __forceinline__ int64_t clamp_id(int64_t id) { return id < 0 ? 0 : id; }   // as rs_a2a_scatter does
+
+// pass 1: slot_of[i] = hash-table slot of ids[i]; bit 31 set for the one thread that inserted the key
+__global__ void __launch_bounds__(256) lookup_insert_kernel(const int64_t* __restrict__ ids, int64_t B,
+                                                            unsigned long long* __restrict__ keys, uint32_t mask,
+                                                            uint32_t* __restrict__ slot_of) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < B; i += (int64_t)gridDim.x * blockDim.x) {
+    const unsigned long long id = static_cast<unsigned long long>(clamp_id(ids[i]));
+    uint32_t h = hash_u64(id) & mask;
+    for (;;) {
+      const unsigned long long old = atomicCAS(&keys[h], kEmptyKey, id);
+      if (old == kEmptyKey) { slot_of[i] = h | 0x80000000u; break; }
+      if (old == id) { slot_of[i] = h; break; }
+      h = (h + 1) & mask;
+    }
+  }
+}
+
+// pass 2: every first occurrence (all ids when slot_of == nullptr: no de-duplication) takes the next position of its
+// owner's list; block-aggregated so that a block costs one global atomic per owner
+__global__ void __launch_bounds__(256) lookup_assign_kernel(const int64_t* __restrict__ ids, int64_t B, int G, int64_t b_max,
+                                                            const uint32_t* __restrict__ slot_of, int32_t* __restrict__ vals,
+                                                            unsigned long long* __restrict__ counts,
+                                                            int64_t* __restrict__ stage, int64_t* __restrict__ inv) {
+  __shared__ unsigned int local[kMaxWorld];
+  __shared__ unsigned long long start[kMaxWorld];
+  if (threadIdx.x < kMaxWorld) local[threadIdx.x] = 0;
+  __syncthreads();
+  for (int64_t c0 = blockIdx.x * (int64_t)blockDim.x; c0 < B; c0 += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = c0 + threadIdx.x;
+    int64_t id = 0;
+    int g = -1;
+    unsigned int slot = 0;
+    if (i < B && (!slot_of || (slot_of[i] & 0x80000000u))) {
+      id = clamp_id(ids[i]);
+      g = static_cast<int>(id % G);
+      slot = atomicAdd(&local[g], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < G) start[threadIdx.x] = local[threadIdx.x] ? atomicAdd(&counts[threadIdx.x], (unsigned long long)local[threadIdx.x]) : 0ull;
+    __syncthreads();
+    if (g >= 0) {
+      const int64_t pos = static_cast<int64_t>(start[g]) + slot;
+      stage[g * b_max + pos] = id / G;
+      if (slot_of) vals[slot_of[i] & 0x7FFFFFFFu] = static_cast<int32_t>(pos);
+      else inv[i] = g * b_max + pos;
+    }
+    __syncthreads();
+    if (threadIdx.x < kMaxWorld) local[threadIdx.x] = 0;
+    __syncthreads();
+  }
+}
+
+// pass 3 (de-duplication only): every id finds its key's position
+__global__ void __launch_bounds__(256) lookup_inverse_kernel(const int64_t* __restrict__ ids, int64_t B, int G, int64_t b_max,
+                                                             const uint32_t* __restrict__ slot_of, const int32_t* __restrict__ vals,
+                                                             int64_t* __restrict__ inv) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < B; i += (int64_t)gridDim.x * blockDim.x)
+    inv[i] = (clamp_id(ids[i]) % G) * b_max + vals[slot_of[i] & 0x7FFFFFFFu];
+}
+
+__global__ void __launch_bounds__(256) a2a_ids_kernel(uint8_t* const* __restrict__ bases, const PeerLayout L,
+                                                       const int64_t* __restrict__ stage, int64_t b_max,
+                                                       const unsigned long long* __restrict__ counts) {
+  const uint64_t seq = peer_begin(bases[L.rank], L);
+  const int64_t total = (int64_t)L.world * b_max;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = static_cast<int>(i / b_max);
+    const int64_t j = i - g * b_max;
+    const int64_t n = static_cast<int64_t>(counts[g]);
+    uint8_t* slot = bases[g] + L.rank * L.slot_bytes;
+    if (j == 0) *reinterpret_cast<int64_t*>(slot) = n;
+    if (j < n) reinterpret_cast<int64_t*>(slot + kIdsHeader)[j] = stage[i];
+  }
+  peer_finish(bases, L, seq);
+}
+
+// on the owner: requester r asked for LA.count(r) rows; row j of that list goes to slot `rank` of r's rows region
+__global__ void __launch_bounds__(256) a2a_rows_kernel(const uint8_t* __restrict__ ids_local, const PeerLayout LA,
+                                                        uint8_t* const* __restrict__ row_bases, const PeerLayout LB,
+                                                        const float* __restrict__ table, int64_t n_local, int64_t ld, int dim) {
+  const uint64_t seq = peer_begin(row_bases[LB.rank], LB);
+  __shared__ int64_t prefix[kMaxWorld + 1];
+  if (threadIdx.x == 0) {
+    int64_t acc = 0;
+    for (int r = 0; r < LA.world; ++r) {
+      prefix[r] = acc;
+      acc += *reinterpret_cast<const int64_t*>(ids_local + r * LA.slot_bytes);
+    }
+    prefix[LA.world] = acc;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int chunks = dim >> 2;
+  const int64_t row_bytes = (int64_t)dim * 4;
+  for (int64_t t = warp0; t < prefix[LA.world]; t += nwarps) {
+    int r = 0;
+    while (t >= prefix[r + 1]) ++r;
+    const int64_t j = t - prefix[r];
+    const int64_t lr = reinterpret_cast<const int64_t*>(ids_local + r * LA.slot_bytes + kIdsHeader)[j];
+    float4* dst = reinterpret_cast<float4*>(row_bases[r] + LB.rank * LB.slot_bytes + j * row_bytes);
+    const bool ok = lr >= 0 && lr < n_local;
+    const float4* src = reinterpret_cast<const float4*>(table + (ok ? lr : 0) * ld);
+    for (int c = lane; c < chunks; c += 32) dst[c] = ok ? __ldg(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  peer_finish(row_bases, LB, seq);
 }
 
 }  // namespace
@@ -203,6 +343,89 @@ int rs_peer_ack(rs_peer_t* h, void* stream) {
   return rs::guard([&] {
     RS_CHECK(h != nullptr && h->connected, "peer region is not connected");
     peer_ack_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(h->d_bases, layout_of(h));
+    RS_LAUNCH_CHECK();
+  });
+}
+
+int rs_a2a_plan_peer(const DLTensor* ids, int n_shards, int dedup, DLTensor* keys, DLTensor* vals, DLTensor* slot_of,
+                     DLTensor* counts, DLTensor* stage, DLTensor* inv, void* stream) {
+  return rs::guard([&] {
+    using namespace rs;
+    require(ids, "ids", 1, kDLInt, 64);
+    require(counts, "counts", 1, kDLInt, 64);
+    require(stage, "stage", 2, kDLInt, 64);
+    require(inv, "inv", 1, kDLInt, 64);
+    const int64_t B = ids->shape[0], G = n_shards, b_max = stage->shape[1];
+    RS_CHECK(G >= 1 && G <= kMaxWorld, "n_shards must be in [1, 16]");
+    RS_CHECK(on_device(ids) && on_device(counts) && on_device(stage) && on_device(inv), "all tensors must be CUDA tensors");
+    RS_CHECK(counts->shape[0] == G && stage->shape[0] == G && is_compact(stage) && inv->shape[0] == B && B <= b_max,
+             "counts [G], stage [G, b_max] contiguous, inv [B], B <= b_max");
+    RS_CHECK((B <= 1 || stride_of(ids, 0) == 1) && (B <= 1 || stride_of(inv, 0) == 1), "ids / inv must be contiguous");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    RS_CUDA(cudaMemsetAsync(data_ptr<void>(counts), 0, sizeof(int64_t) * G, st));
+    if (B == 0) return;
+    const int blocks = static_cast<int>(std::min<int64_t>((B + 255) / 256, (int64_t)sm_count() * 8));
+    uint32_t* so = nullptr;
+    int32_t* vp = nullptr;
+    if (dedup) {
+      require(keys, "keys", 1, kDLInt, 64);
+      require(vals, "vals", 1, kDLInt, 32);
+      require(slot_of, "slot_of", 1, kDLInt, 32);
+      const int64_t H = keys->shape[0];
+      RS_CHECK(on_device(keys) && on_device(vals) && on_device(slot_of) && vals->shape[0] == H && slot_of->shape[0] >= B &&
+                   H >= 2 * B && (H & (H - 1)) == 0 && H <= (int64_t(1) << 30),
+               "keys / vals [H] with H a power of two >= 2B, slot_of [>= B]");
+      RS_CUDA(cudaMemsetAsync(data_ptr<void>(keys), 0xFF, sizeof(int64_t) * H, st));
+      so = data_ptr<uint32_t>(slot_of);
+      vp = data_ptr<int32_t>(vals);
+      lookup_insert_kernel<<<blocks, 256, 0, st>>>(data_ptr<int64_t>(ids), B, data_ptr<unsigned long long>(keys),
+                                                   static_cast<uint32_t>(H - 1), so);
+      RS_LAUNCH_CHECK();
+    }
+    lookup_assign_kernel<<<blocks, 256, 0, st>>>(data_ptr<int64_t>(ids), B, static_cast<int>(G), b_max, so, vp,
+                                                 data_ptr<unsigned long long>(counts), data_ptr<int64_t>(stage), data_ptr<int64_t>(inv));
+    RS_LAUNCH_CHECK();
+    if (dedup) {
+      lookup_inverse_kernel<<<blocks, 256, 0, st>>>(data_ptr<int64_t>(ids), B, static_cast<int>(G), b_max, so, vp, data_ptr<int64_t>(inv));
+      RS_LAUNCH_CHECK();
+    }
+  });
+}
+
+int rs_peer_a2a_ids(rs_peer_t* h, const DLTensor* stage, const DLTensor* counts, void* stream) {
+  return rs::guard([&] {
+    using namespace rs;
+    RS_CHECK(h != nullptr && h->connected, "peer region is not connected");
+    require(stage, "stage", 2, kDLInt, 64);
+    require(counts, "counts", 1, kDLInt, 64);
+    const int64_t b_max = stage->shape[1];
+    RS_CHECK(on_device(stage) && on_device(counts) && is_compact(stage) && stage->shape[0] == h->world && counts->shape[0] == h->world,
+             "stage must be a contiguous CUDA [world, b_max] tensor, counts [world]");
+    RS_CHECK(kIdsHeader + b_max * 8 <= h->slot_bytes, "ids region slots are too small for b_max row numbers");
+    const int64_t total = (int64_t)h->world * b_max;
+    const int blocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((total + 255) / 256, sm_count())));
+    a2a_ids_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(h->d_bases, layout_of(h), data_ptr<int64_t>(stage), b_max,
+                                                                         data_ptr<unsigned long long>(counts));
+    RS_LAUNCH_CHECK();
+  });
+}
+
+int rs_peer_a2a_rows(rs_peer_t* ids_region, rs_peer_t* rows_region, const DLTensor* table, void* stream) {
+  return rs::guard([&] {
+    using namespace rs;
+    RS_CHECK(ids_region != nullptr && ids_region->connected && rows_region != nullptr && rows_region->connected,
+             "peer regions are not connected");
+    RS_CHECK(ids_region->world == rows_region->world && ids_region->rank == rows_region->rank, "the two regions belong to different groups");
+    require(table, "table", 2, kDLFloat, 32);
+    RS_CHECK(on_device(table) && table->shape[1] % 4 == 0, "table must be a CUDA [n_local, dim] tensor, dim a multiple of 4");
+    const int64_t ld = row_stride_2d(table, "table");
+    RS_CHECK(ld % 4 == 0, "table row stride must be a multiple of 4 floats");
+    require_aligned16(data_ptr<float>(table), "table");
+    const int64_t b_max = (ids_region->slot_bytes - kIdsHeader) / 8;
+    RS_CHECK(b_max * table->shape[1] * 4 <= rows_region->slot_bytes, "rows region slots are too small for b_max rows");
+    a2a_rows_kernel<<<sm_count(), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        ids_region->local, layout_of(ids_region), rows_region->d_bases, layout_of(rows_region), data_ptr<float>(table),
+        table->shape[0], ld, static_cast<int>(table->shape[1]));
     RS_LAUNCH_CHECK();
   });
 }

@@ -59,22 +59,26 @@ class PeerExchange:
         import ctypes
         from . import _lib
         self._lib_mod, self._lib = _lib, _lib.load()
-        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        multi = dist.is_initialized()
+        self.world, self.rank = (dist.get_world_size(group), dist.get_rank(group)) if multi else (1, 0)
         self.slot_bytes = _round_up(int(slot_bytes), 16)
         self.device = device
         self._h = ctypes.c_void_p()
         handle = (ctypes.c_uint8 * 64)()
         _lib.check(self._lib.rs_peer_create(self.rank, self.world, self.slot_bytes, ctypes.byref(self._h), handle))
-        mine = torch.tensor(list(handle), dtype=torch.uint8).to(device)
-        everyone = torch.empty((self.world * 64,), dtype=torch.uint8, device=device)
-        dist.all_gather_into_tensor(everyone, mine, group=group)
-        blob = bytes(everyone.cpu().tolist())
+        blob = bytes(handle)
+        if multi:
+            mine = torch.tensor(list(handle), dtype=torch.uint8).to(device)
+            everyone = torch.empty((self.world * 64,), dtype=torch.uint8, device=device)
+            dist.all_gather_into_tensor(everyone, mine, group=group)
+            blob = bytes(everyone.cpu().tolist())
         _lib.check(self._lib.rs_peer_connect(self._h, ctypes.c_char_p(blob)))
         ptr, n = ctypes.c_void_p(), ctypes.c_int64()
         _lib.check(self._lib.rs_peer_local(self._h, ctypes.byref(ptr), ctypes.byref(n)))
         self._mem = _DeviceBytes(ptr.value, n.value)
         self.region = torch.as_tensor(self._mem, device=device).view(self.world, self.slot_bytes)
-        dist.barrier(group=group)          # nobody publishes into a region that is not mapped everywhere yet
+        if multi:
+            dist.barrier(group=group)      # nobody publishes into a region that is not mapped everywhere yet
 
     def publish(self, msg: torch.Tensor) -> None:
         b = self._lib_mod.dl(msg)
@@ -386,9 +390,65 @@ class ShardedEmbedding:
         _lib.check(_lib.load().rs_hash_table_fill(b.ptr, rank, world, seed, _lib.stream_ptr()))
         return out
 
+    def enable_peer_exchange(self, max_batch: int, dedup: bool = True) -> None:
+        """Switch lookup() to the peer-memory path (csrc/peer.cu): both all-to-alls become stores into NVLink peer
+        memory with device-known counts, the owner-side gather writes straight into the requester's region, hot ids
+        are requested once per batch (dedup) -- no NCCL, no host synchronisation, capturable in a CUDA graph.
+        Collective: every rank calls it with the same max_batch (regions: world * max_batch * (8 + 4 * dim) bytes)."""
+        from . import _lib
+        dev = self.local_table.device
+        G, bm = self.world, int(max_batch)
+        self._p2p = {
+            "b_max": bm, "dedup": bool(dedup),
+            "ids": PeerExchange(16 + 8 * bm, dev, self.group), "rows": PeerExchange(bm * self.dim * 4, dev, self.group),
+            "counts": torch.zeros((G,), dtype=torch.int64, device=dev),
+            "stage": torch.zeros((G, bm), dtype=torch.int64, device=dev),
+        }
+        if dedup:
+            H = 1 << max(4, (2 * bm - 1).bit_length())
+            self._p2p.update(keys=torch.empty((H,), dtype=torch.int64, device=dev), vals=torch.empty((H,), dtype=torch.int32, device=dev),
+                             slot_of=torch.empty((bm,), dtype=torch.int32, device=dev))
+        self._p2p["rows_view"] = self._p2p["rows"].region.view(torch.float32).view(G * bm, self.dim)
+        self._lib_mod, self._lib = _lib, _lib.load()
+
+    def close(self) -> None:
+        p = getattr(self, "_p2p", None)
+        if p:
+            torch.cuda.synchronize()
+            p["rows_view"] = None
+            p["ids"].close()
+            p["rows"].close()
+            self._p2p = None
+
+    def _lookup_p2p(self, ids: torch.Tensor) -> torch.Tensor:
+        p, L, lib = self._p2p, self._lib_mod, self._lib
+        B = int(ids.shape[0])
+        if B > p["b_max"]:
+            raise ValueError(f"batch {B} exceeds the max_batch {p['b_max']} the peer regions were sized for")
+        st = L.stream_ptr()
+        inv = torch.empty((B,), dtype=torch.int64, device=ids.device)
+        b_ids, b_counts, b_stage, b_inv = L.dl(ids), L.dl(p["counts"]), L.dl(p["stage"]), L.dl(inv)
+        if p["dedup"]:
+            b_k, b_v, b_s = L.dl(p["keys"]), L.dl(p["vals"]), L.dl(p["slot_of"])
+            L.check(lib.rs_a2a_plan_peer(b_ids.ptr, self.world, 1, b_k.ptr, b_v.ptr, b_s.ptr, b_counts.ptr, b_stage.ptr, b_inv.ptr, st))
+        else:
+            L.check(lib.rs_a2a_plan_peer(b_ids.ptr, self.world, 0, None, None, None, b_counts.ptr, b_stage.ptr, b_inv.ptr, st))
+        h_ids, h_rows = p["ids"]._h, p["rows"]._h
+        L.check(lib.rs_peer_a2a_ids(h_ids, b_stage.ptr, b_counts.ptr, st))
+        L.check(lib.rs_peer_wait(h_ids, st))
+        b_table = L.dl(self.local_table)
+        L.check(lib.rs_peer_a2a_rows(h_ids, h_rows, b_table.ptr, st))      # owner-side gather fused with the way back
+        L.check(lib.rs_peer_ack(h_ids, st))
+        L.check(lib.rs_peer_wait(h_rows, st))
+        out = self._gather(p["rows_view"], inv)                            # batch order; duplicates read the same row
+        L.check(lib.rs_peer_ack(h_rows, st))
+        return out
+
     def lookup(self, ids: torch.Tensor) -> torch.Tensor:
         """ids: int64 [B] global rows (this rank's part of the batch) -> float32 [B, dim], in batch order."""
         G = self.world
+        if getattr(self, "_p2p", None):
+            return self._lookup_p2p(ids)
         if G == 1:
             return self._gather(self.local_table, ids)
         counts = self._count(ids, G)

@@ -39,3 +39,33 @@ def test_peer_exchange_single_rank_steps(rs):
     with pytest.raises(RuntimeError):
         _lib.check(lib.rs_peer_publish(h, b.ptr, _lib.stream_ptr()))
     _lib.check(lib.rs_peer_free(h))
+
+
+@pytest.mark.parametrize("dedup", [True, False])
+def test_peer_memory_lookup_single_rank(rs, dedup):
+    """ShardedEmbedding.lookup through the peer-memory path with one rank (owner == requester): plan kernels (hash
+    de-duplication or plain bucketing), ids message, owner-side gather into the rows region, restore -- against a
+    plain row gather, bit for bit; duplicates, a negative id (clamped to 0), out-of-range ids (zeros), ragged batches
+    and several steps through the same regions."""
+    import numpy as np
+    from recsys_b200.sharded import ShardedEmbedding
+    n_rows, dim, bmax = 5000, 128, 4096
+    table = torch.from_numpy(rs.synth.hash_table_rows(np.arange(n_rows), dim, seed=9)).cuda()
+    emb = ShardedEmbedding(n_rows, dim, local_table=table)
+    emb.enable_peer_exchange(bmax, dedup=dedup)
+    rng = np.random.default_rng(3)
+    for B in (1, 77, 4096, 1000):
+        ids = rs.synth.zipf_ids(rng, n_rows, B).astype(np.int64)
+        if B >= 77:
+            ids[5] = -3            # clamped to row 0
+            ids[9] = n_rows + 11   # not a row of the table: zeros
+            ids[10:20] = ids[3]    # a run of duplicates
+        got = emb.lookup(torch.from_numpy(ids).cuda()).cpu().numpy()
+        want = table.cpu().numpy()[np.clip(ids, 0, n_rows - 1)]
+        want[ids >= n_rows] = 0
+        np.testing.assert_array_equal(got, want)
+    if dedup:      # the owner was asked once per distinct id
+        assert int(emb._p2p["counts"].sum()) == len(np.unique(np.clip(ids, 0, None)))
+    with pytest.raises(ValueError):
+        emb.lookup(torch.zeros(bmax + 1, dtype=torch.int64, device="cuda"))
+    emb.close()

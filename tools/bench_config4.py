@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """BASELINE config 4: Zipf-skewed lookups into embedding tables sharded over the GPUs (row mod G), all-to-all
-exchanges over NCCL/NVLink, feeding the DCN ranking forward.  Run under torchrun, one rank per GPU:
+exchanges feeding the DCN ranking forward -- timed three ways in one run: NCCL all-to-alls (host-sized splits),
+peer-memory exchange (csrc/peer.cu) without and with per-batch de-duplication.  Run under torchrun, one rank per GPU:
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node G --master-addr 127.0.0.1 --master-port 29520 \
         tools/bench_config4.py [--users 50000000 --items 10000000 --batch 65536]
@@ -93,18 +94,33 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    ms_lookup = timed(step_lookup, args.steps)
-    ms_full = timed(step_full, args.steps)
+    res = {}
+    res["nccl"] = (timed(step_lookup, args.steps), timed(step_full, args.steps))
+    for label, dedup in (("peer", False), ("peer_dedup", True)):
+        for name, seed in (("user", 41), ("item", 42)):
+            tables[name].close()
+            tables[name].enable_peer_exchange(B, dedup=dedup)
+            for _ in range(2):       # twice: the second pass re-uses the regions
+                got = tables[name].lookup(ids_d[name]).cpu().numpy()
+                assert np.array_equal(got, rs.synth.hash_table_rows(ids[name], E, seed)), f"rank {rank}: {name} rows differ ({label})"
+        res[label] = (timed(step_lookup, args.steps), timed(step_full, args.steps))
+    uniq = torch.tensor([float(len(np.unique(ids["user"])) + len(np.unique(ids["item"]))) / (2 * B)], device=dev, dtype=torch.float64)
+    dist.all_reduce(uniq, op=dist.ReduceOp.SUM)
+    for t in tables.values():
+        t.close()
     if rank == 0:
         remote = (world - 1) / world
-        print(json.dumps({
+        line = {
             "workload": f"config 4: tables {args.users:,} x 128 + {args.items:,} x 128 sharded row mod {world}, Zipf(1.05) ids, "
-                        f"local batch {B}, NCCL all-to-all lookups feeding the bf16 DCN ranking forward",
-            "n_gpus": world, "parity": "looked-up rows bit-identical to host replay; logits within 1e-2 of fp64 oracle",
-            "lookup_ms": round(ms_lookup, 4), "lookup_samples_per_s": round(world * B / ms_lookup * 1e3),
-            "lookup_plus_ranking_ms": round(ms_full, 4), "samples_per_s": round(world * B / ms_full * 1e3),
-            "nvlink_bytes_per_sample_each_way": round(2 * (8 + 4 * E) * remote, 1),
-            "nvlink_GBps_per_gpu_effective": round(2 * 4 * E * remote * B / ms_lookup / 1e6, 1)}))
+                        f"local batch {B}, all-to-all lookups feeding the bf16 DCN ranking forward",
+            "n_gpus": world, "parity": "looked-up rows bit-identical to host replay on all three paths; logits within 1e-2 of fp64 oracle",
+            "distinct_id_fraction": round(float(uniq.item()) / world, 4),
+            "nvlink_bytes_per_sample_each_way_no_dedup": round(2 * (8 + 4 * E) * remote, 1)}
+        for label, (ms_lookup, ms_full) in res.items():
+            line[label] = {"lookup_ms": round(ms_lookup, 4), "lookup_samples_per_s": round(world * B / ms_lookup * 1e3),
+                           "lookup_plus_ranking_ms": round(ms_full, 4), "samples_per_s": round(world * B / ms_full * 1e3),
+                           "nvlink_GBps_per_gpu_effective": round(2 * 4 * E * remote * B / ms_lookup / 1e6, 1)}
+        print(json.dumps(line))
     dist.destroy_process_group()
 
 
