@@ -104,6 +104,25 @@ def main():
                 got = tables[name].lookup(ids_d[name]).cpu().numpy()
                 assert np.array_equal(got, rs.synth.hash_table_rows(ids[name], E, seed)), f"rank {rank}: {name} rows differ ({label})"
         res[label] = (timed(step_lookup, args.steps), timed(step_full, args.steps))
+    # the peer-memory step has no host synchronisation: capture lookups + ranking once, replay as one CUDA graph
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        step_full()
+    torch.cuda.current_stream(dev).wait_stream(side)
+    dist.barrier()
+    torch.cuda.synchronize()
+    g_lookup, g_full = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g_lookup):
+        rows_static = step_lookup()
+    with torch.cuda.graph(g_full):
+        out_static = step_full()
+    g_full.replay()
+    torch.cuda.synchronize()
+    for key in ("rating_prediction", "ctr_prediction"):
+        assert torch.equal(out_static[key], out[key]), f"rank {rank}: graph replay differs from the eager step ({key})"
+    res["peer_dedup_graph"] = (timed(g_lookup.replay, args.steps), timed(g_full.replay, args.steps))
+    del g_lookup, g_full, rows_static, out_static
     uniq = torch.tensor([float(len(np.unique(ids["user"])) + len(np.unique(ids["item"]))) / (2 * B)], device=dev, dtype=torch.float64)
     dist.all_reduce(uniq, op=dist.ReduceOp.SUM)
     for t in tables.values():
