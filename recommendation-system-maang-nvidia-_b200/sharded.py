@@ -347,6 +347,9 @@ class ShardedEmbedding:
         exchange  all-to-all #2: the 512-byte rows back to the requesters
         restore   K1 kernel with the permutation as ids
     Bytes over NVLink per looked-up row: 8 (id) out, 4*E (row) back, for the (G-1)/G share that is remote.
+    enable_peer_exchange(max_batch) replaces both all-to-alls by stores into NVLink peer memory (csrc/peer.cu): hash
+    de-duplication of the batch, device-known counts, owner-side gather written straight into the requester's region,
+    no host synchronisation -- see _lookup_p2p.
     `plan` / `gather` are injectable so the host logic can run on CPU over gloo with numpy stand-ins (tests).
     """
 
