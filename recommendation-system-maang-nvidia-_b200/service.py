@@ -8,10 +8,11 @@ The whole recommend() path stays on the GPU: host dict lookup -> K1 gather -> K2
 K4 normalise -> K5 catalog scan + top-k; only the k (score, row) pairs come back to the host.
 
 Artifacts.  The reference saves `encoder.keras` (Keras v3 zip holding an HDF5 weight file),
-`vocabs.json`, `item_map.json` and `faiss.idx` (src/trainer.py:228-245).  h5py is not available here,
-so load() reads vocabs.json / item_map.json / faiss.idx as the reference writes them and takes the
-encoder weights from `encoder_weights.npz` (keys: user_embedding, item_embedding,
-user_tower_{i}_kernel/bias, item_tower_{i}_kernel/bias) -- `export_encoder_npz` documents the mapping.
+`vocabs.json`, `item_map.json` and `faiss.idx` (src/trainer.py:228-245).  load() reads all of them as the
+reference writes them; the HDF5 member of encoder.keras goes through this repo's own minimal reader
+(keras_io.py -- h5py is not available here, and the reader could not be checked against a file written by
+h5py itself).  If `encoder_weights.npz` exists (keys: user_embedding, item_embedding,
+user_tower_{i}_kernel/bias, item_tower_{i}_kernel/bias; `export_encoder_npz` documents the mapping) it wins.
 `from_parts` builds a service from in-memory objects (tests, bench).
 """
 
@@ -85,11 +86,14 @@ class RecommendationService:
         cfg_path = self.model_dir / "config.json"
         config = ModelConfig(**json.load(open(cfg_path))) if cfg_path.exists() else ModelConfig()
         item_vocab = vocabs.get("items") or [self.item_map[str(i)] for i in range(len(self.item_map))]
-        npz = self.model_dir / "encoder_weights.npz"
-        if not npz.exists():
-            raise FileNotFoundError(f"{npz} not found: export the Keras encoder weights with export_encoder_npz "
-                                    "(encoder.keras needs h5py, which this image does not have)")
-        w = _weights_from_npz(np.load(npz))
+        npz, keras_zip = self.model_dir / "encoder_weights.npz", self.model_dir / "encoder.keras"
+        if npz.exists():
+            w = _weights_from_npz(np.load(npz))
+        elif keras_zip.exists():
+            from .keras_io import load_keras_encoder           # the reference's own artifact (src/trainer.py:230)
+            w = load_keras_encoder(keras_zip)
+        else:
+            raise FileNotFoundError(f"neither {keras_zip} nor {npz} found in the model directory")
         config.embedding_dim = int(w["user_embedding"].shape[1])
         config.user_tower_dims = [int(k.shape[1]) for k, _ in w["user_tower"][:-1]]
         config.item_tower_dims = [int(k.shape[1]) for k, _ in w["item_tower"][:-1]]

@@ -411,6 +411,16 @@ def test_service_load_from_artifacts(rs, tmp_path):
     assert svc.recommend(uv[2], 5) == ref.recommend(uv[2], 5)
     with pytest.raises(FileNotFoundError):
         rs.RecommendationService(str(tmp_path / "missing")).load()
+    # the reference's own artifact: encoder.keras (zip + HDF5 weights, read by keras_io) instead of the .npz side file
+    from recsys_b200.keras_io import save_keras_encoder
+    (d / "encoder_weights.npz").unlink()
+    with pytest.raises(FileNotFoundError):
+        rs.RecommendationService(str(d)).load()
+    save_keras_encoder(d / "encoder.keras", w)
+    svc2 = rs.RecommendationService(str(d))
+    svc2.load()
+    assert svc2.recommend(uv[2], 5) == ref.recommend(uv[2], 5)
+    assert svc2.score(uv[3], iv[:4]) == ref.score(uv[3], iv[:4])
 
 
 # ------------------------------------------------------------------------------------------ K7b sharded tables
