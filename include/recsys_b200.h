@@ -282,16 +282,20 @@ int rs_peer_free(rs_peer_t* h);
  *                     vals [H] int32, H a power of two >= 2B; slot_of [B] int32 scratch); dedup == 0: keys / vals /
  *                     slot_of may be NULL.  Negative ids are clamped to 0 (as rs_a2a_scatter does).
  *   rs_peer_a2a_ids   ids region (slots of >= 16 + 8 * b_max bytes): list for owner g -> slot `rank` of g's region
- *   (rs_peer_wait on the ids region)
- *   rs_peer_a2a_rows  on the owner: table f32 [n_local, dim] rows named by every requester's list -> slot `rank` of
- *                     that requester's rows region (slots of >= b_max * dim * 4 bytes); out-of-range rows are zeros
- *   (rs_peer_ack on the ids region; rs_peer_wait on the rows region; gather the rows region with inv as ids --
- *    rs_gather_concat; rs_peer_ack on the rows region)
+ *   rs_peer_a2a_rows  on the owner: waits for every requester's list, then table f32 [n_local, dim] rows named by
+ *                     the lists -> slot `rank` of that requester's rows region (slots of exactly b_max * dim * 4
+ *                     bytes); out-of-range rows are zeros; acknowledges the ids messages itself
+ *   rs_peer_a2a_restore  waits for every owner's rows, then out[i] = row of ids[i] out of the local rows region --
+ *                     position from the hash table (slot_of / vals, de-duplication; inv may then be NULL in both
+ *                     calls) or from inv (slot_of = vals = NULL); acknowledges the rows messages itself
+ * No rs_peer_wait / rs_peer_ack calls are needed around these three.
  */
 int rs_a2a_plan_peer(const DLTensor* ids, int n_shards, int dedup, DLTensor* keys, DLTensor* vals, DLTensor* slot_of,
                      DLTensor* counts, DLTensor* stage, DLTensor* inv, void* stream);
 int rs_peer_a2a_ids(rs_peer_t* ids_region, const DLTensor* stage, const DLTensor* counts, void* stream);
 int rs_peer_a2a_rows(rs_peer_t* ids_region, rs_peer_t* rows_region, const DLTensor* table, void* stream);
+int rs_peer_a2a_restore(rs_peer_t* rows_region, const DLTensor* ids, const DLTensor* slot_of, const DLTensor* vals,
+                        const DLTensor* inv, DLTensor* out, void* stream);
 
 /* counters for the bench's gpu_launches claim: kernels launched by this library so far */
 int64_t rs_launch_count(void);

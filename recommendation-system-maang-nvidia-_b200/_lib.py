@@ -122,6 +122,7 @@ def load():
         "rs_a2a_plan_peer": [_DLP, i32, i32, _DLP, _DLP, _DLP, _DLP, _DLP, _DLP, vp],
         "rs_peer_a2a_ids": [vp, _DLP, _DLP, vp],
         "rs_peer_a2a_rows": [vp, vp, _DLP, vp],
+        "rs_peer_a2a_restore": [vp, _DLP, _DLP, _DLP, _DLP, _DLP, vp],
         "rs_prof_enable": [i32],
         "rs_prof_read": [i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64)],
     }
@@ -140,7 +141,7 @@ EXPORTED = ["rs_version", "rs_last_error", "rs_launch_count", "rs_device_sm_coun
             "rs_index_fallbacks", "rs_debug_tensor_scores",
             "rs_matvec", "rs_topk_merge", "rs_prof_enable", "rs_prof_read",
             "rs_peer_create", "rs_peer_connect", "rs_peer_local", "rs_peer_publish", "rs_peer_wait", "rs_peer_ack", "rs_peer_free",
-            "rs_a2a_plan_peer", "rs_peer_a2a_ids", "rs_peer_a2a_rows"]
+            "rs_a2a_plan_peer", "rs_peer_a2a_ids", "rs_peer_a2a_rows", "rs_peer_a2a_restore"]
 
 PROF_SCAN, PROF_MERGE, PROF_FILTER, PROF_RESCORE, PROF_RANK, PROF_SAMPLE = 0, 1, 2, 3, 4, 5
 

@@ -94,7 +94,11 @@ __device__ __forceinline__ uint64_t peer_begin(const uint8_t* local, const PeerL
 }
 // Every CTA, after its last store into the peers' regions: the last CTA to get here raises this rank's flag in every
 // region (system-scope release, behind a fence that covers all CTAs' stores) and advances the local step number.
-__device__ __forceinline__ void peer_finish(uint8_t* const* bases, const PeerLayout& L, uint64_t seq) {
+// consumed / consumed_L / consumed_seq (optional): a second region whose messages this launch has finished reading;
+// the same last CTA acknowledges them to every peer (what a separate peer_ack_kernel would do).
+__device__ __forceinline__ void peer_finish(uint8_t* const* bases, const PeerLayout& L, uint64_t seq,
+                                            uint8_t* const* consumed = nullptr, const PeerLayout* consumed_L = nullptr,
+                                            uint64_t consumed_seq = 0) {
   uint8_t* local = bases[L.rank];
   __threadfence_system();
   __syncthreads();
@@ -105,6 +109,29 @@ __device__ __forceinline__ void peer_finish(uint8_t* const* bases, const PeerLay
       __threadfence_system();
       for (int g = 0; g < L.world; ++g) st_release_sys(reinterpret_cast<uint64_t*>(bases[g] + L.off_flags) + L.rank, seq);
       *reinterpret_cast<uint64_t*>(local + L.off_seq) = seq;
+      if (consumed)
+        for (int g = 0; g < consumed_L->world; ++g)
+          st_release_sys(reinterpret_cast<uint64_t*>(consumed[g] + consumed_L->off_acks) + consumed_L->rank, consumed_seq);
+    }
+  }
+}
+// Every CTA of a kernel that only CONSUMES the local region: wait until this step's message of every rank is there.
+__device__ __forceinline__ uint64_t peer_arrived(const uint8_t* local, const PeerLayout& L) {
+  const uint64_t seq = *reinterpret_cast<const uint64_t*>(local + L.off_seq);
+  if (threadIdx.x < L.world)
+    spin_until(reinterpret_cast<const uint64_t*>(local + L.off_flags) + threadIdx.x, seq, "a peer's message");
+  __syncthreads();
+  return seq;
+}
+// ... and, once every CTA has finished reading it, acknowledge the step to every peer (last CTA).
+__device__ __forceinline__ void peer_consumed(uint8_t* const* bases, const PeerLayout& L, uint64_t seq) {
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int* done = reinterpret_cast<unsigned int*>(bases[L.rank] + L.off_done);
+    if (atomicAdd(done, 1u) == gridDim.x - 1) {
+      *done = 0;
+      for (int g = 0; g < L.world; ++g) st_release_sys(reinterpret_cast<uint64_t*>(bases[g] + L.off_acks) + L.rank, seq);
     }
   }
 }
@@ -142,9 +169,12 @@ __global__ void peer_ack_kernel(uint8_t* const* __restrict__ bases, const PeerLa
 //   plan      (lookup_* kernels) optional de-duplication through an open-addressing hash table, per-owner lists of
 //             local row numbers (row div G), inv[i] = where id i's row will land in this rank's rows region
 //   ids out   a2a_ids_kernel: list for owner g -> slot `rank` of g's ids region, [count | pad | rows ...]
-//   rows back a2a_rows_kernel (on the owner): one warp per requested row, table row -> slot `rank` of the
-//             requester's rows region
-//   restore   gather_concat_kernel over the local rows region with inv as ids
+//   rows back a2a_rows_kernel (on the owner): waits for every requester's list, one warp per requested row,
+//             table row -> slot `rank` of the requester's rows region; acknowledges the ids messages
+//   restore   a2a_restore_kernel: waits for every owner's rows, copies them into batch order out of the local rows
+//             region (in de-duplication mode the position comes from the hash table: no inverse pass), acknowledges
+// Seven stream operations per lookup (two memsets, insert, assign, ids, rows, restore); the waits and acknowledgements
+// ride inside the kernels that need them.
 // ------------------------------------------------------------------------------------------------
 constexpr unsigned long long kEmptyKey = ~0ull;
 constexpr int kIdsHeader = 16;   // bytes in front of the row numbers of an ids message: int64 count + padding
@@ -231,9 +261,11 @@ __global__ void __launch_bounds__(256) a2a_ids_kernel(uint8_t* const* __restrict
 }
 
 // on the owner: requester r asked for LA.count(r) rows; row j of that list goes to slot `rank` of r's rows region
-__global__ void __launch_bounds__(256) a2a_rows_kernel(const uint8_t* __restrict__ ids_local, const PeerLayout LA,
+__global__ void __launch_bounds__(256) a2a_rows_kernel(uint8_t* const* __restrict__ ids_bases, const PeerLayout LA,
                                                         uint8_t* const* __restrict__ row_bases, const PeerLayout LB,
                                                         const float* __restrict__ table, int64_t n_local, int64_t ld, int dim) {
+  const uint8_t* ids_local = ids_bases[LA.rank];
+  const uint64_t seq_ids = peer_arrived(ids_local, LA);
   const uint64_t seq = peer_begin(row_bases[LB.rank], LB);
   __shared__ int64_t prefix[kMaxWorld + 1];
   if (threadIdx.x == 0) {
@@ -260,7 +292,28 @@ __global__ void __launch_bounds__(256) a2a_rows_kernel(const uint8_t* __restrict
     const float4* src = reinterpret_cast<const float4*>(table + (ok ? lr : 0) * ld);
     for (int c = lane; c < chunks; c += 32) dst[c] = ok ? __ldg(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  peer_finish(row_bases, LB, seq);
+  peer_finish(row_bases, LB, seq, ids_bases, &LA, seq_ids);
+}
+
+// on the requester: out[i] = the row of ids[i], wherever its owner put it in the local rows region
+__global__ void __launch_bounds__(256) a2a_restore_kernel(uint8_t* const* __restrict__ row_bases, const PeerLayout LB,
+                                                           const int64_t* __restrict__ ids, int64_t B, int G, int64_t b_max,
+                                                           const uint32_t* __restrict__ slot_of, const int32_t* __restrict__ vals,
+                                                           const int64_t* __restrict__ inv, float* __restrict__ out,
+                                                           int64_t ld_out, int dim) {
+  const uint8_t* local = row_bases[LB.rank];
+  const uint64_t seq = peer_arrived(local, LB);
+  const int chunks = dim >> 2;
+  const int64_t total = B * chunks;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = t / chunks;
+    const int c = static_cast<int>(t - i * chunks);
+    const int64_t pos = slot_of ? (clamp_id(ids[i]) % G) * b_max + vals[slot_of[i] & 0x7FFFFFFFu] : inv[i];
+    // plain loads: the region was written by other GPUs during this launch's lifetime (no read-only path)
+    const float4 v = reinterpret_cast<const float4*>(local + pos * (int64_t)dim * 4)[c];
+    *reinterpret_cast<float4*>(out + i * ld_out + 4 * c) = v;
+  }
+  peer_consumed(row_bases, LB, seq);
 }
 
 }  // namespace
@@ -354,13 +407,17 @@ int rs_a2a_plan_peer(const DLTensor* ids, int n_shards, int dedup, DLTensor* key
     require(ids, "ids", 1, kDLInt, 64);
     require(counts, "counts", 1, kDLInt, 64);
     require(stage, "stage", 2, kDLInt, 64);
-    require(inv, "inv", 1, kDLInt, 64);
     const int64_t B = ids->shape[0], G = n_shards, b_max = stage->shape[1];
     RS_CHECK(G >= 1 && G <= kMaxWorld, "n_shards must be in [1, 16]");
-    RS_CHECK(on_device(ids) && on_device(counts) && on_device(stage) && on_device(inv), "all tensors must be CUDA tensors");
-    RS_CHECK(counts->shape[0] == G && stage->shape[0] == G && is_compact(stage) && inv->shape[0] == B && B <= b_max,
-             "counts [G], stage [G, b_max] contiguous, inv [B], B <= b_max");
-    RS_CHECK((B <= 1 || stride_of(ids, 0) == 1) && (B <= 1 || stride_of(inv, 0) == 1), "ids / inv must be contiguous");
+    RS_CHECK(inv != nullptr || dedup, "inv may only be NULL with de-duplication");
+    if (inv) {
+      require(inv, "inv", 1, kDLInt, 64);
+      RS_CHECK(on_device(inv) && inv->shape[0] == B && (B <= 1 || stride_of(inv, 0) == 1), "inv must be a contiguous CUDA [B] tensor");
+    }
+    RS_CHECK(on_device(ids) && on_device(counts) && on_device(stage), "all tensors must be CUDA tensors");
+    RS_CHECK(counts->shape[0] == G && stage->shape[0] == G && is_compact(stage) && B <= b_max,
+             "counts [G], stage [G, b_max] contiguous, B <= b_max");
+    RS_CHECK(B <= 1 || stride_of(ids, 0) == 1, "ids must be contiguous");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     RS_CUDA(cudaMemsetAsync(data_ptr<void>(counts), 0, sizeof(int64_t) * G, st));
     if (B == 0) return;
@@ -383,9 +440,10 @@ int rs_a2a_plan_peer(const DLTensor* ids, int n_shards, int dedup, DLTensor* key
       RS_LAUNCH_CHECK();
     }
     lookup_assign_kernel<<<blocks, 256, 0, st>>>(data_ptr<int64_t>(ids), B, static_cast<int>(G), b_max, so, vp,
-                                                 data_ptr<unsigned long long>(counts), data_ptr<int64_t>(stage), data_ptr<int64_t>(inv));
+                                                 data_ptr<unsigned long long>(counts), data_ptr<int64_t>(stage),
+                                                 inv ? data_ptr<int64_t>(inv) : nullptr);
     RS_LAUNCH_CHECK();
-    if (dedup) {
+    if (dedup && inv) {   // callers that restore with rs_peer_a2a_restore pass inv = NULL: it reads the hash table itself
       lookup_inverse_kernel<<<blocks, 256, 0, st>>>(data_ptr<int64_t>(ids), B, static_cast<int>(G), b_max, so, vp, data_ptr<int64_t>(inv));
       RS_LAUNCH_CHECK();
     }
@@ -424,8 +482,46 @@ int rs_peer_a2a_rows(rs_peer_t* ids_region, rs_peer_t* rows_region, const DLTens
     const int64_t b_max = (ids_region->slot_bytes - kIdsHeader) / 8;
     RS_CHECK(b_max * table->shape[1] * 4 <= rows_region->slot_bytes, "rows region slots are too small for b_max rows");
     a2a_rows_kernel<<<sm_count(), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        ids_region->local, layout_of(ids_region), rows_region->d_bases, layout_of(rows_region), data_ptr<float>(table),
+        ids_region->d_bases, layout_of(ids_region), rows_region->d_bases, layout_of(rows_region), data_ptr<float>(table),
         table->shape[0], ld, static_cast<int>(table->shape[1]));
+    RS_LAUNCH_CHECK();
+  });
+}
+
+int rs_peer_a2a_restore(rs_peer_t* rows_region, const DLTensor* ids, const DLTensor* slot_of, const DLTensor* vals,
+                        const DLTensor* inv, DLTensor* out, void* stream) {
+  return rs::guard([&] {
+    using namespace rs;
+    RS_CHECK(rows_region != nullptr && rows_region->connected, "peer region is not connected");
+    require(ids, "ids", 1, kDLInt, 64);
+    require(out, "out", 2, kDLFloat, 32);
+    const int64_t B = ids->shape[0], dim = out->shape[1];
+    RS_CHECK(on_device(ids) && on_device(out) && out->shape[0] == B && dim % 4 == 0 && (B <= 1 || stride_of(ids, 0) == 1),
+             "ids must be a contiguous CUDA [B] tensor, out a CUDA [B, dim] tensor with dim a multiple of 4");
+    const int64_t ld_out = row_stride_2d(out, "out");
+    RS_CHECK(ld_out % 4 == 0, "out row stride must be a multiple of 4 floats");
+    require_aligned16(data_ptr<float>(out), "out");
+    const int64_t b_max = rows_region->slot_bytes / (dim * 4);
+    RS_CHECK(b_max * dim * 4 == rows_region->slot_bytes, "rows region slots must hold a whole number of rows of this width");
+    const uint32_t* so = nullptr;
+    const int32_t* vp = nullptr;
+    const int64_t* ip = nullptr;
+    if (slot_of) {
+      require(slot_of, "slot_of", 1, kDLInt, 32);
+      require(vals, "vals", 1, kDLInt, 32);
+      RS_CHECK(on_device(slot_of) && on_device(vals) && slot_of->shape[0] >= B, "slot_of [>= B] / vals must be CUDA tensors");
+      so = data_ptr<uint32_t>(slot_of);
+      vp = data_ptr<int32_t>(vals);
+    } else {
+      require(inv, "inv", 1, kDLInt, 64);
+      RS_CHECK(on_device(inv) && inv->shape[0] == B && (B <= 1 || stride_of(inv, 0) == 1), "inv must be a contiguous CUDA [B] tensor");
+      ip = data_ptr<int64_t>(inv);
+    }
+    const int64_t total = std::max<int64_t>(1, B * (dim / 4));
+    const int blocks = static_cast<int>(std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 8));
+    a2a_restore_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(rows_region->d_bases, layout_of(rows_region),
+                                                                             data_ptr<int64_t>(ids), B, rows_region->world, b_max, so,
+                                                                             vp, ip, data_ptr<float>(out), ld_out, static_cast<int>(dim));
     RS_LAUNCH_CHECK();
   });
 }

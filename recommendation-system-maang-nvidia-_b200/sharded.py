@@ -423,35 +423,38 @@ class ShardedEmbedding:
             p["rows"].close()
             self._p2p = None
 
-    def _lookup_p2p(self, ids: torch.Tensor) -> torch.Tensor:
+    def _lookup_p2p(self, ids: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         p, L, lib = self._p2p, self._lib_mod, self._lib
         B = int(ids.shape[0])
         if B > p["b_max"]:
             raise ValueError(f"batch {B} exceeds the max_batch {p['b_max']} the peer regions were sized for")
         st = L.stream_ptr()
-        inv = torch.empty((B,), dtype=torch.int64, device=ids.device)
-        b_ids, b_counts, b_stage, b_inv = L.dl(ids), L.dl(p["counts"]), L.dl(p["stage"]), L.dl(inv)
+        if out is None:
+            out = torch.empty((B, self.dim), dtype=torch.float32, device=ids.device)
+        b_ids, b_counts, b_stage, b_out = L.dl(ids), L.dl(p["counts"]), L.dl(p["stage"]), L.dl(out)
+        h_ids, h_rows = p["ids"]._h, p["rows"]._h
         if p["dedup"]:
             b_k, b_v, b_s = L.dl(p["keys"]), L.dl(p["vals"]), L.dl(p["slot_of"])
-            L.check(lib.rs_a2a_plan_peer(b_ids.ptr, self.world, 1, b_k.ptr, b_v.ptr, b_s.ptr, b_counts.ptr, b_stage.ptr, b_inv.ptr, st))
+            L.check(lib.rs_a2a_plan_peer(b_ids.ptr, self.world, 1, b_k.ptr, b_v.ptr, b_s.ptr, b_counts.ptr, b_stage.ptr, None, st))
         else:
+            inv = torch.empty((B,), dtype=torch.int64, device=ids.device)
+            b_inv = L.dl(inv)
             L.check(lib.rs_a2a_plan_peer(b_ids.ptr, self.world, 0, None, None, None, b_counts.ptr, b_stage.ptr, b_inv.ptr, st))
-        h_ids, h_rows = p["ids"]._h, p["rows"]._h
         L.check(lib.rs_peer_a2a_ids(h_ids, b_stage.ptr, b_counts.ptr, st))
-        L.check(lib.rs_peer_wait(h_ids, st))
         b_table = L.dl(self.local_table)
         L.check(lib.rs_peer_a2a_rows(h_ids, h_rows, b_table.ptr, st))      # owner-side gather fused with the way back
-        L.check(lib.rs_peer_ack(h_ids, st))
-        L.check(lib.rs_peer_wait(h_rows, st))
-        out = self._gather(p["rows_view"], inv)                            # batch order; duplicates read the same row
-        L.check(lib.rs_peer_ack(h_rows, st))
+        if p["dedup"]:
+            L.check(lib.rs_peer_a2a_restore(h_rows, b_ids.ptr, b_s.ptr, b_v.ptr, None, b_out.ptr, st))
+        else:
+            L.check(lib.rs_peer_a2a_restore(h_rows, b_ids.ptr, None, None, b_inv.ptr, b_out.ptr, st))
         return out
 
-    def lookup(self, ids: torch.Tensor) -> torch.Tensor:
-        """ids: int64 [B] global rows (this rank's part of the batch) -> float32 [B, dim], in batch order."""
+    def lookup(self, ids: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """ids: int64 [B] global rows (this rank's part of the batch) -> float32 [B, dim], in batch order.
+        out (peer-memory path only): a preallocated result tensor."""
         G = self.world
         if getattr(self, "_p2p", None):
-            return self._lookup_p2p(ids)
+            return self._lookup_p2p(ids, out)
         if G == 1:
             return self._gather(self.local_table, ids)
         counts = self._count(ids, G)
@@ -467,3 +470,32 @@ class ShardedEmbedding:
         back = torch.empty((int(ids.shape[0]), self.dim), dtype=torch.float32, device=ids.device)
         dist.all_to_all_single(back, found, output_split_sizes=send_counts, input_split_sizes=recv_counts, group=self.group)
         return self._gather(back, perm)
+
+
+_SIDE_STREAMS = {}
+
+
+def lookup_many(pairs):
+    """[(ShardedEmbedding, ids), ...] -> [rows, ...].  A peer-memory lookup is a chain of small kernels and two NVLink
+    round trips -- bound by latency, not by bandwidth -- so the tables are looked up CONCURRENTLY, each on its own
+    side stream (their regions are independent); the results are joined back onto the current stream.  Capturable
+    in a CUDA graph (the side streams become parallel branches).  Tables on the NCCL path are looked up one after
+    the other: collectives of one communicator must be issued in the same order on every rank."""
+    if not all(getattr(emb, "_p2p", None) for emb, _ in pairs) or len(pairs) < 2:
+        return [emb.lookup(ids) for emb, ids in pairs]
+    dev = pairs[0][1].device
+    cur = torch.cuda.current_stream(dev)
+    streams = _SIDE_STREAMS.setdefault(dev.index, [])
+    while len(streams) < len(pairs):
+        streams.append(torch.cuda.Stream(device=dev))
+    # results are allocated on the CURRENT stream (the side streams only fill them), so that freeing them later
+    # needs no cross-stream bookkeeping in the caching allocator
+    outs = [torch.empty((int(ids.shape[0]), emb.dim), dtype=torch.float32, device=dev) for emb, ids in pairs]
+    for (emb, ids), out, st in zip(pairs, outs, streams):
+        st.wait_stream(cur)
+        with torch.cuda.stream(st):
+            emb.lookup(ids, out=out)
+    for st in streams[:len(pairs)]:
+        cur.wait_stream(st)
+    return outs
+

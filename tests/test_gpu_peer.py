@@ -69,3 +69,31 @@ def test_peer_memory_lookup_single_rank(rs, dedup):
     with pytest.raises(ValueError):
         emb.lookup(torch.zeros(bmax + 1, dtype=torch.int64, device="cuda"))
     emb.close()
+
+
+def test_lookup_many_runs_tables_concurrently_and_matches(rs):
+    import numpy as np
+    from recsys_b200.sharded import ShardedEmbedding, lookup_many
+    rng = np.random.default_rng(8)
+    pairs, want = [], []
+    for n_rows, seed in ((3000, 1), (1700, 2), (900, 3)):
+        table = torch.from_numpy(rs.synth.hash_table_rows(np.arange(n_rows), 128, seed=seed)).cuda()
+        emb = ShardedEmbedding(n_rows, 128, local_table=table)
+        emb.enable_peer_exchange(2048, dedup=seed != 2)
+        ids = rs.synth.zipf_ids(rng, n_rows, 2048).astype(np.int64)
+        pairs.append((emb, torch.from_numpy(ids).cuda()))
+        want.append(table.cpu().numpy()[ids])
+    for _ in range(3):
+        got = lookup_many(pairs)
+        torch.cuda.synchronize()
+        for g, w in zip(got, want):
+            np.testing.assert_array_equal(g.cpu().numpy(), w)
+    g = torch.cuda.CUDAGraph()                      # the same, captured: side streams become branches of the graph
+    with torch.cuda.graph(g):
+        static = lookup_many(pairs)
+    g.replay()
+    torch.cuda.synchronize()
+    for s_, w in zip(static, want):
+        np.testing.assert_array_equal(s_.cpu().numpy(), w)
+    for emb, _ in pairs:
+        emb.close()

@@ -22,7 +22,7 @@ import torch.distributed as dist
 
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import recsys_b200 as rs  # noqa: E402
-from recsys_b200.sharded import ShardedEmbedding  # noqa: E402
+from recsys_b200.sharded import ShardedEmbedding, lookup_many  # noqa: E402
 
 
 def main():
@@ -60,8 +60,8 @@ def main():
     model = rs.MultiTaskModel(cfg, rs.synth.make_vocab(8), rs.synth.make_vocab(8), {}, device=dev, precision="bf16")
     rs.load_weights(model, w)
 
-    def step_lookup():
-        return tables["user"].lookup(ids_d["user"]), tables["item"].lookup(ids_d["item"])
+    def step_lookup():       # peer-memory tables are looked up concurrently (two streams); NCCL tables one after the other
+        return lookup_many([(tables["user"], ids_d["user"]), (tables["item"], ids_d["item"])])
 
     def step_full():
         u, it = step_lookup()
