@@ -271,6 +271,10 @@ int rs_peer_local(rs_peer_t* h, void** data, int64_t* bytes);
 int rs_peer_publish(rs_peer_t* h, const DLTensor* src, void* stream);
 int rs_peer_wait(rs_peer_t* h, void* stream);
 int rs_peer_ack(rs_peer_t* h, void* stream);
+/* Teardown across ranks: an owner must not free a region a peer still has mapped, and nobody may still be writing
+ * into it.  Order: every rank's work finished (caller's barrier) -> rs_peer_disconnect on every rank (unmaps the
+ * peers' regions) -> barrier -> rs_peer_free.  rs_peer_free alone is enough for a single rank. */
+int rs_peer_disconnect(rs_peer_t* h);
 int rs_peer_free(rs_peer_t* h);
 /*
  * K7q. Sharded embedding lookups (BASELINE config 4) over the same peer regions: both all-to-alls of a lookup are

@@ -119,6 +119,7 @@ def load():
         "rs_peer_wait": [vp, vp],
         "rs_peer_ack": [vp, vp],
         "rs_peer_free": [vp],
+        "rs_peer_disconnect": [vp],
         "rs_a2a_plan_peer": [_DLP, i32, i32, _DLP, _DLP, _DLP, _DLP, _DLP, _DLP, vp],
         "rs_peer_a2a_ids": [vp, _DLP, _DLP, vp],
         "rs_peer_a2a_rows": [vp, vp, _DLP, vp],
@@ -140,7 +141,7 @@ EXPORTED = ["rs_version", "rs_last_error", "rs_launch_count", "rs_device_sm_coun
             "rs_tensor_plan", "rs_tensor_threshold_rank", "rs_index_shared_begin", "rs_index_shared_finish", "rs_tc_session_free", "rs_topk_verify",
             "rs_index_fallbacks", "rs_debug_tensor_scores",
             "rs_matvec", "rs_topk_merge", "rs_prof_enable", "rs_prof_read",
-            "rs_peer_create", "rs_peer_connect", "rs_peer_local", "rs_peer_publish", "rs_peer_wait", "rs_peer_ack", "rs_peer_free",
+            "rs_peer_create", "rs_peer_connect", "rs_peer_local", "rs_peer_publish", "rs_peer_wait", "rs_peer_ack", "rs_peer_free", "rs_peer_disconnect",
             "rs_a2a_plan_peer", "rs_peer_a2a_ids", "rs_peer_a2a_rows", "rs_peer_a2a_restore"]
 
 PROF_SCAN, PROF_MERGE, PROF_FILTER, PROF_RESCORE, PROF_RANK, PROF_SAMPLE = 0, 1, 2, 3, 4, 5

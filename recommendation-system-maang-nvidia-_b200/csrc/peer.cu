@@ -526,6 +526,20 @@ int rs_peer_a2a_restore(rs_peer_t* rows_region, const DLTensor* ids, const DLTen
   });
 }
 
+int rs_peer_disconnect(rs_peer_t* h) {
+  return rs::guard([&] {
+    if (!h) return;
+    RS_CUDA(cudaDeviceSynchronize());
+    for (int g = 0; g < h->world; ++g)
+      if (h->opened[g]) {
+        cudaIpcCloseMemHandle(h->bases[g]);
+        h->opened[g] = false;
+        h->bases[g] = nullptr;
+      }
+    h->connected = false;
+  });
+}
+
 int rs_peer_free(rs_peer_t* h) {
   return rs::guard([&] {
     if (!h) return;

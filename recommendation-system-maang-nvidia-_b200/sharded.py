@@ -63,16 +63,37 @@ class PeerExchange:
         self.world, self.rank = (dist.get_world_size(group), dist.get_rank(group)) if multi else (1, 0)
         self.slot_bytes = _round_up(int(slot_bytes), 16)
         self.device = device
+        self._group = group
         self._h = ctypes.c_void_p()
+        # Every rank walks through the same collectives whether or not its own CUDA calls succeed; the outcome is
+        # agreed on (MIN over ranks) and a failure anywhere raises RuntimeError on EVERY rank.
         handle = (ctypes.c_uint8 * 64)()
-        _lib.check(self._lib.rs_peer_create(self.rank, self.world, self.slot_bytes, ctypes.byref(self._h), handle))
+        ok, err = 1, ""
+        try:
+            _lib.check(self._lib.rs_peer_create(self.rank, self.world, self.slot_bytes, ctypes.byref(self._h), handle))
+        except RuntimeError as e:
+            ok, err = 0, str(e)
         blob = bytes(handle)
         if multi:
             mine = torch.tensor(list(handle), dtype=torch.uint8).to(device)
             everyone = torch.empty((self.world * 64,), dtype=torch.uint8, device=device)
             dist.all_gather_into_tensor(everyone, mine, group=group)
             blob = bytes(everyone.cpu().tolist())
-        _lib.check(self._lib.rs_peer_connect(self._h, ctypes.c_char_p(blob)))
+        if ok:
+            try:
+                _lib.check(self._lib.rs_peer_connect(self._h, ctypes.c_char_p(blob)))
+            except RuntimeError as e:
+                ok, err = 0, str(e)
+        if multi:
+            flag = torch.tensor([ok], dtype=torch.int32, device=device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            ok_all = int(flag.item())
+        else:
+            ok_all = ok
+        if not ok_all:
+            self.region = None
+            self.close()
+            raise RuntimeError("peer-memory region could not be set up on every rank" + (f": {err}" if err else ""))
         ptr, n = ctypes.c_void_p(), ctypes.c_int64()
         _lib.check(self._lib.rs_peer_local(self._h, ctypes.byref(ptr), ctypes.byref(n)))
         self._mem = _DeviceBytes(ptr.value, n.value)
@@ -92,10 +113,22 @@ class PeerExchange:
         self._lib_mod.check(self._lib.rs_peer_ack(self._h, self._lib_mod.stream_ptr()))
 
     def close(self) -> None:
-        if getattr(self, "_h", None) is not None and self._h.value:
-            self.region = None
+        """Collective: every rank of the group calls it.  Nobody frees a region that a peer may still write into or
+        still has mapped: finish all work -> barrier -> unmap the peers' regions -> barrier -> free the own one."""
+        if getattr(self, "_h", None) is None:
+            return
+        multi = self.world > 1 and dist.is_initialized()
+        torch.cuda.synchronize(self.device)
+        if multi:
+            dist.barrier(group=self._group)
+        self.region = None
+        if self._h.value:
+            self._lib_mod.check(self._lib.rs_peer_disconnect(self._h))
+        if multi:
+            dist.barrier(group=self._group)
+        if self._h.value:
             self._lib_mod.check(self._lib.rs_peer_free(self._h))
-            self._h = None
+        self._h = None
 
 
 class ShardedIndexFlatIP:
