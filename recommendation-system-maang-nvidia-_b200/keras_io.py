@@ -320,9 +320,12 @@ def read_hdf5(data) -> Dict[str, np.ndarray]:
 # ---------------------------------------------------------------------------------------------------------------
 # writer (the h5py-default subset: superblock v0, v1 object headers, symbol-table groups, contiguous datasets)
 # ---------------------------------------------------------------------------------------------------------------
-def write_hdf5(path, datasets: Dict[str, np.ndarray]) -> None:
-    """Write {"group/sub/name": array} as an HDF5 file laid out the way h5py lays out a default file."""
+def write_hdf5(path, datasets: Dict[str, np.ndarray], chunks: Dict[str, Tuple[int, ...]] = None, deflate: bool = False) -> None:
+    """Write {"group/sub/name": array} as an HDF5 file laid out the way h5py lays out a default file.  Datasets named in
+    `chunks` ({path: chunk shape}) are stored chunked behind a one-node B-tree (<= 64 chunks), shuffled + deflated when
+    `deflate` is set -- what h5py produces for create_dataset(..., chunks=..., compression="gzip", shuffle=True)."""
     tree: Dict = {}
+    chunk_of = {}
     for full, arr in datasets.items():
         node = tree
         parts = [p for p in full.split("/") if p]
@@ -331,6 +334,8 @@ def write_hdf5(path, datasets: Dict[str, np.ndarray]) -> None:
             if not isinstance(node, dict):
                 raise ValueError(f"{full}: a dataset is in the way")
         node[parts[-1]] = np.require(arr, requirements="C")
+        if chunks and full in chunks:
+            chunk_of[id(node[parts[-1]])] = tuple(int(c) for c in chunks[full])
     buf = bytearray(96)                                           # superblock v0 with 8-byte offsets: 24 + 32 + 40
 
     def alloc(n: int) -> int:
@@ -366,8 +371,46 @@ def write_hdf5(path, datasets: Dict[str, np.ndarray]) -> None:
             dt = struct.pack("<BBBBI", 0x10, 0x08 if arr.dtype.kind == "i" else 0, 0, 0, size) + struct.pack("<HH", 0, size * 8)
         else:
             raise NotImplementedError(f"dtype {arr.dtype}")
-        layout = struct.pack("<BBQQ", 3, 1, data, len(raw))
-        return header([message(0x01, space), message(0x03, dt), message(0x08, layout)])
+        cdims = chunk_of.get(id(arr))
+        if cdims is None or arr.ndim == 0 or arr.size == 0:
+            layout = struct.pack("<BBQQ", 3, 1, data, len(raw))
+            return header([message(0x01, space), message(0x03, dt), message(0x08, layout)])
+        # chunked: every chunk is a full cdims block (edge chunks zero-padded), indexed by one leaf B-tree node
+        little = arr.astype(arr.dtype.newbyteorder("<"))
+        grid = [range(0, s, c) for s, c in zip(arr.shape, cdims)]
+        entries = []
+        for offs in np.ndindex(*[len(g) for g in grid]):
+            start = [g[i] for g, i in zip(grid, offs)]
+            block = np.zeros(cdims, little.dtype)
+            sl = tuple(slice(o, min(o + c, s)) for o, c, s in zip(start, cdims, arr.shape))
+            block[tuple(slice(0, x.stop - x.start) for x in sl)] = little[sl]
+            payload = block.tobytes()
+            if deflate:
+                payload = np.frombuffer(payload, np.uint8).reshape(-1, arr.dtype.itemsize).T.tobytes()   # shuffle
+                payload = zlib.compress(payload, 4)
+            a = alloc(len(payload))
+            buf[a:a + len(payload)] = payload
+            entries.append((start, a, len(payload)))
+        if len(entries) > 64:
+            raise NotImplementedError("more than 64 chunks in one dataset")
+        nd = arr.ndim
+        ksz = 8 + 8 * (nd + 1)
+        bt = alloc(24 + (ksz + 8) * 64 + ksz)
+        buf[bt:bt + 24] = b"TREE" + struct.pack("<BBHQQ", 1, 0, len(entries), _UNDEF, _UNDEF)
+        q = bt + 24
+        for start, a, nbytes in entries:
+            buf[q:q + ksz] = struct.pack("<II", nbytes, 0) + b"".join(struct.pack("<Q", o) for o in start) + struct.pack("<Q", 0)
+            buf[q + ksz:q + ksz + 8] = struct.pack("<Q", a)
+            q += ksz + 8
+        buf[q:q + ksz] = struct.pack("<II", 0, 0) + b"".join(struct.pack("<Q", s) for s in arr.shape) + struct.pack("<Q", 0)
+        layout = struct.pack("<BBBQ", 3, 2, nd + 1, bt) + b"".join(struct.pack("<I", c) for c in cdims) + struct.pack("<I", arr.dtype.itemsize)
+        msgs = [message(0x01, space), message(0x03, dt), message(0x08, layout)]
+        if deflate:   # filter pipeline v1: shuffle (id 2, element size), then deflate (id 1, level)
+            pipe = struct.pack("<BB6x", 1, 2)
+            pipe += struct.pack("<HHHHI4x", 2, 0, 0, 1, arr.dtype.itemsize)
+            pipe += struct.pack("<HHHHI4x", 1, 0, 0, 1, 4)
+            msgs.append(message(0x0B, pipe))
+        return header(msgs)
 
     def write_group(node: Dict) -> int:
         entries = []

@@ -91,3 +91,16 @@ def test_encoder_mapping_tolerates_prefixes_and_orders_layers_numerically():
     del ds["encoder/item_tower/layers/dense_4/vars/1"]
     with pytest.raises(KeyError):
         keras_io.encoder_weights_from_datasets(ds)
+
+
+@pytest.mark.parametrize("deflate", [False, True])
+def test_reader_handles_chunked_and_compressed_datasets(tmp_path, deflate):
+    """Chunked storage behind a B-tree v1 index, optionally shuffle + deflate, with ragged edge chunks."""
+    rng = np.random.default_rng(4)
+    ds = {"w/kernel": rng.standard_normal((37, 21)).astype(np.float32), "w/ids": rng.integers(0, 1 << 40, (50,)),
+          "w/plain": rng.standard_normal(9).astype(np.float32)}
+    path = tmp_path / "c.h5"
+    keras_io.write_hdf5(path, ds, chunks={"w/kernel": (16, 8), "w/ids": (16,)}, deflate=deflate)
+    got = keras_io.read_hdf5(path)
+    for k, v in ds.items():
+        np.testing.assert_array_equal(got[k], v)
