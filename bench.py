@@ -354,6 +354,15 @@ def main():
     if not args.no_batch1:
         batch1 = bench_batch1(rs, torch, dist, sidx, args, device, world)
 
+    # configs[0], the reference's own CPU-runnable case (MovieLens-1M-shaped, batch 4096): times only, on rank 0 at N=1;
+    # its outputs are compared with the oracle by tests/test_gpu_parity.py.  Never allowed to take the headline down.
+    config1 = None
+    if world == 1 and not args.no_ranking:
+        try:
+            config1 = bench_config1(rs, torch, device, timed)
+        except Exception as e:  # noqa: BLE001
+            config1 = {"error": f"{type(e).__name__}: {e}"}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         xb_h, q_h = cpu_prepare(args, args.cpu_sample_rows)
@@ -373,7 +382,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nq * dim * 4,
                         "d2h_bytes_per_step": nq * k * 12, "ms_per_step": e2e_ms / args.steps},
                 "gpu_launches": int(lt.item()), "clocks": clocks, "roofline": roofline, "kernels": kernel_ms,
-                "cpu_baseline": cpu, "ranking": ranking, "batch1_latency": batch1}
+                "cpu_baseline": cpu, "ranking": ranking, "batch1_latency": batch1, "config1": config1}
         if world > 1:
             line["exchange_bytes_per_step_per_rank"] = gather_bytes(world, nq, k)
             line["config"]["exchange"] = ("NVLink peer memory: each rank stores its message into every peer's region and raises a flag "
@@ -476,6 +485,43 @@ def bench_ranking(rs, torch, dist, args, device, world, rank, pk, timed):
             "fp32_mode": {"value": res["fp32"]["value"], "ms_per_step": res["fp32"]["ms_per_step"], "dtype": "f32",
                           "tolerance": "1e-5 of tensor scale", "e2e": res["fp32"]["e2e"],
                           "gemm_tflops_per_gpu": res["fp32"]["gemm_tflops_per_gpu"]}}
+
+
+def bench_config1(rs, torch, device, timed, steps=20):
+    """BASELINE configs[0]: 6,040 users / 3,706 items, emb 128, batch 4,096 -- MultiTaskModel forward (fp32 exact mode, the
+    reference's arithmetic) and exact top-10 over the item-tower catalog for the batch's user embeddings.  The whole
+    problem sits in L2, so this is a launch/latency figure, not a roofline one."""
+    cfg = rs.ModelConfig()
+    n_users, n_items, B = 6040, 3706, 4096
+    uv, iv = rs.synth.make_vocab(n_users), rs.synth.make_vocab(n_items)
+    model = rs.MultiTaskModel(cfg, uv, iv, {}, device=device)
+    rs.load_weights(model, rs.synth.make_weights(cfg, n_users, n_items, seed=10))
+    rng = np.random.default_rng(100)
+    ur = torch.from_numpy(rs.synth.make_ids(rng, n_users, B)).to(device)
+    ir = torch.from_numpy(rs.synth.make_ids(rng, n_items, B)).to(device)
+    items = model.encoder({"movie_id": torch.arange(1, n_items + 1, device=device)})["item_embedding"].contiguous()
+    rs.normalize_L2(items)
+    index = rs.IndexFlatIP(cfg.embedding_dim)
+    index.add(items)
+
+    def forward():
+        return model({"user_id": ur, "movie_id": ir})
+
+    q = forward()["user_embedding"].contiguous()
+    rs.normalize_L2(q)
+
+    def search():
+        return index.search(q, 10)
+
+    for _ in range(3):
+        forward()
+        search()
+    f_ms = timed(forward, steps) / steps
+    s_ms = timed(search, steps) / steps
+    return {"workload": "MovieLens-1M-shaped synthetic (6,040 users / 3,706 items, emb 128, batch 4096): MultiTaskModel forward "
+                        "in fp32 exact mode + exact top-10 over the 3,706-item catalog (BASELINE configs[0])",
+            "forward_ms": f_ms, "forward_samples_per_s": B / (f_ms / 1e3), "top10_ms": s_ms,
+            "top10_queries_per_s": B / (s_ms / 1e3), "note": "problem is L2-resident: launch/latency-bound, no roofline fraction"}
 
 
 def bench_batch1(rs, torch, dist, sidx, args, device, world, n_queries=200, k=10):
