@@ -548,15 +548,22 @@ tower_pp_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
              : pr.ids64 ? static_cast<const int64_t*>(pr.ids)[row_]
                         : static_cast<int64_t>(static_cast<const int32_t*>(pr.ids)[row_]);
     };
-    // (Issuing these loads costs the warp 2-3 k cycles per tile in every variant tried -- all eight at once here, or two
-    // per step spread over the tile, thread-per-row or 8 lanes per row: it is not the number of lines in flight.)
+    // The loads are UNCONDITIONAL (an invalid id reads row 0) and land directly in a0; which chunks are real is kept
+    // in vmask and applied when the tile starts.  (Written as "u = 0; if (ok) u = load" the compiler loads into a
+    // temporary and moves it under the predicate right away, a use of the loaded value.)  Issuing the eight loads
+    // still costs the warp 2-3 k cycles per tile in every form measured -- conditional or not, all at once or two
+    // per step, thread-per-row or 8 lanes per row: 32 KB of L2 reads per slot and tile against what one SM keeps
+    // in flight with all of its shared memory carved out.
+    uint32_t vmask = 0;
     auto load_a0_staged = [&](int64_t my_id) {
+      vmask = 0;
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const int64_t id = __shfl_sync(0xffffffffu, my_id, 4 * e + l3);
-        uint4 u = make_uint4(0u, 0u, 0u, 0u);
-        if (id >= 0 && id < pr.table_rows) u = __ldg(reinterpret_cast<const uint4*>(pr.table16 + id * 128 + half * 64) + l8);
+        const bool ok = id >= 0 && id < pr.table_rows;
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(pr.table16 + (ok ? id : 0) * 128 + half * 64) + l8);
         a0[4 * e] = u.x; a0[4 * e + 1] = u.y; a0[4 * e + 2] = u.z; a0[4 * e + 3] = u.w;
+        vmask |= (ok ? 1u : 0u) << e;
       }
     };
     int64_t id_next = -1;   // STAGED: this lane's row id for the tile after the one whose rows are in flight
@@ -586,8 +593,9 @@ tower_pp_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
               const int rr = 4 * e + l3;
+              const bool ok = (vmask >> e) & 1u;
               *reinterpret_cast<uint4*>(stg + rr * 64 + (((l8 & 3) ^ ((rr >> 1) & 3)) << 4)) =
-                  make_uint4(a0[4 * e], a0[4 * e + 1], a0[4 * e + 2], a0[4 * e + 3]);
+                  ok ? make_uint4(a0[4 * e], a0[4 * e + 1], a0[4 * e + 2], a0[4 * e + 3]) : make_uint4(0u, 0u, 0u, 0u);
             }
           }
           __syncwarp();
@@ -1197,11 +1205,13 @@ deep_heads_kernel(const __grid_constant__ ChainMaps maps, const DeepHeadsParams 
     float pd[NP];   // slice-0 warps: this row's x0 dots of the tile in progress (read from TMEM after layer 0)
 #pragma unroll
     for (int t = 0; t < NP; ++t) pd[t] = 0.0f;
+    // unconditional: x_il16 is padded to whole tiles and the tower kernel writes every row of every tile (rows past the
+    // end of the batch hold the towers' output for an all-zero embedding; their results are never stored), and a
+    // "valid ? load : 0" select would be a use of the loaded value right here
     auto load_next = [&](int64_t tile_) {
-      const bool valid = tile_ * BM + trow < p.rows;
       const uint4* src = reinterpret_cast<const uint4*>(p.x_il16) + ((tile_ * 4 + quarter) * 32 + slice * 8) * 32 + lane;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) a0[e] = valid ? __ldg(src + e * 32) : make_uint4(0u, 0u, 0u, 0u);
+      for (int e = 0; e < 8; ++e) a0[e] = __ldg(src + e * 32);
     };
     // cross recurrence + heads for one finished tile: run by the slice-0 warp of each quarter once the other three
     // warps of the quarter have published their partial dots (named barrier 1 + quarter, 128 threads)
