@@ -333,7 +333,15 @@ void search_exact_device(rs_index* h, const float* q, int64_t nq, int k, int64_t
   }
   RS_CHECK(h->ntotal <= 0xFFFFFFFFll, "catalog shards above 2^32 rows are not supported");
   const int64_t ntiles = (h->ntotal + TILE_ROWS - 1) / TILE_ROWS;
-  const int P = static_cast<int>(std::min<int64_t>(ntiles, sm_count()));
+  int P = static_cast<int>(std::min<int64_t>(ntiles, sm_count()));
+  if (ntiles < sm_count()) {
+    // Small catalog, many queries (BASELINE config 1: 4,096 queries x 3,706 rows): one CTA per (tile, query group) is
+    // 14,848 CTAs that each pay the pipeline start-up for a single 128-row tile.  Give every query group just enough
+    // row slices to fill the machine about twice; a CTA then walks several tiles and fewer lists need merging.
+    const int qt = k > 128 ? 1 : nq >= 8 ? 8 : nq > 2 ? 4 : static_cast<int>(nq);   // as scan_dispatch picks it
+    const int64_t groups = (nq + qt - 1) / qt;
+    P = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(P, (2 * (int64_t)sm_count() + groups - 1) / groups)));
+  }
   uint64_t* partial = nullptr;
   RS_CUDA(cudaMallocAsync(&partial, sizeof(uint64_t) * (size_t)nq * P * k, st));
   try {
