@@ -357,7 +357,8 @@ class RankingSession:
         sess.user_rows.copy_(rows_u, non_blocking=True); sess.item_rows.copy_(rows_i, non_blocking=True)
         out = sess.run()                      # or: out = sess({"user_id": rows_u, "movie_id": rows_i})
 
-    Same kernels, same arithmetic as the eager call (bit-identical outputs, tests/test_gpu_ranking_bf16.py)."""
+    Same kernels, same arithmetic as the eager call (bit-identical outputs, tests/test_gpu_ranking_bf16.py).  A session
+    snapshots the model's weights at capture time."""
 
     def __init__(self, model: "MultiTaskModel", batch: int, ids_dtype=torch.int32):
         if model.precision != "bf16":
@@ -377,6 +378,10 @@ class RankingSession:
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph):
             self.outputs = model(feats)
+        # the captured launches point into the ranker handle's own copies of the weights: keep that handle alive for as
+        # long as the graph can be replayed (load_weights on the model builds a NEW handle; this session then still
+        # computes with the weights it was captured with -- create a new session after changing weights)
+        self._ranker = getattr(model, "_ranker", None)
 
     def run(self) -> Dict[str, torch.Tensor]:
         self._graph.replay()
