@@ -5,6 +5,7 @@ hand-assembled variants cover structures the writer does not emit (compact layou
 
 import struct
 import zipfile
+from pathlib import Path
 
 import numpy as np
 import pytest
@@ -104,3 +105,40 @@ def test_reader_handles_chunked_and_compressed_datasets(tmp_path, deflate):
     got = keras_io.read_hdf5(path)
     for k, v in ds.items():
         np.testing.assert_array_equal(got[k], v)
+
+
+def test_hdf5_roundtrip_random_trees():
+    """Property test: any tree of groups / datasets the writer accepts comes back identical through the reader."""
+    from hypothesis import given, settings, strategies as st
+
+    names = st.text(alphabet="abcdefghijklmnopqrstuvwxyz_0123456789", min_size=1, max_size=12)
+    dtypes = st.sampled_from([np.float32, np.float64, np.float16, np.int64, np.int32, np.uint8])
+    shapes = st.lists(st.integers(0, 9), min_size=0, max_size=3).map(tuple)
+
+    @st.composite
+    def datasets(draw):
+        out = {}
+        for _ in range(draw(st.integers(1, 12))):
+            path = "/".join(draw(st.lists(names, min_size=1, max_size=4)))
+            if any(path == p or path.startswith(p + "/") or p.startswith(path + "/") for p in out):
+                continue                                   # a name cannot be both a group and a dataset
+            dt, shp = draw(dtypes), draw(shapes)
+            seed = draw(st.integers(0, 2 ** 31))
+            a = np.random.default_rng(seed).integers(0, 200, size=shp)
+            out[path] = a.astype(dt)
+        return out
+
+    @settings(max_examples=40, deadline=None)
+    @given(datasets())
+    def check(ds):
+        import tempfile
+        with tempfile.TemporaryDirectory() as tmp:
+            path = Path(tmp) / "t.h5"
+            keras_io.write_hdf5(path, ds)
+            got = keras_io.read_hdf5(path)
+        assert set(got) == set(ds)
+        for k, v in ds.items():
+            assert got[k].dtype == v.dtype and got[k].shape == v.shape
+            np.testing.assert_array_equal(got[k], v)
+
+    check()
