@@ -73,9 +73,12 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.t0 = index, [], None, None
 
-    def start(self):
+    def prestart(self):
+        """Spawn nvidia-smi early (it needs ~1 s before its first line); samples only count from start() on."""
+        if self.proc is not None:
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
@@ -84,9 +87,13 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def start(self):
+        self.prestart()
+        self.t0 = time.monotonic()
+
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.monotonic(), line.strip()))
 
     def stop(self):
         if self.proc is None:
@@ -94,7 +101,9 @@ class ClockSampler:
         time.sleep(0.15)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        rows = list(self.rows)
+        under_load = [x for x in rows if self.t0 is None or x[0] >= self.t0]   # drop idle-clock samples from before start()
+        for t, r in (under_load or rows[-3:]):
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue
@@ -209,6 +218,10 @@ def main():
     if args.gpus != world and rank == 0:
         print(f"note: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.prestart()                   # nvidia-smi streams by the time the warm-up begins
+
     pk = peaks()
     N, nq, k, dim = args.n_items, args.nq, args.k, args.dim
 
@@ -263,7 +276,6 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()                      # samples cover the warm-up and the timed region (both under load)
     # >= W warm-up steps, extended to ~1 s of load so clocks settle and the sampler has data.  The step count
