@@ -8,7 +8,8 @@ independent of the shard order, so every rank ends with the same lists as a sing
 whole catalog -- bit for bit.
 
 torch.distributed is the plumbing (process group, all_gather_into_tensor); the scan and the merge are this
-repo's kernels.  `local_search` / `merge` are injectable so the host logic (bounds, id offsets, gather
+repo's kernels -- and with exchange = "p2p" so is the exchange itself: PeerExchange (csrc/peer.cu) stores every rank's
+message straight into its peers' memory over NVLink, and the merge reads the parts in place.  `local_search` / `merge` are injectable so the host logic (bounds, id offsets, gather
 layout) can be exercised on CPU with gloo, where the tests plug the oracle in as the checker.
 """
 
