@@ -69,7 +69,19 @@ class Embedding:
         g = torch.Generator(device="cpu")
         g.manual_seed(0 if seed is None else seed)
         w = (torch.rand((self.input_dim, self.output_dim), generator=g, dtype=torch.float32) - 0.5) * 0.1
+        self._version = 0
         self.embeddings = w.to(_dev(device))
+
+    # every assignment of the table bumps `_version`; handles that copy or borrow weights (the fused ranker, CUDA-graph
+    # sessions) compare version signatures instead of data pointers, which the caching allocator may reuse
+    @property
+    def embeddings(self) -> torch.Tensor:
+        return self._embeddings
+
+    @embeddings.setter
+    def embeddings(self, w: torch.Tensor) -> None:
+        self._embeddings = w
+        self._version += 1
 
     def __call__(self, rows: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         return ops.gather_concat([self.embeddings], [rows], out=out)
@@ -90,9 +102,32 @@ class Dense:
 
     def __init__(self, units: int, activation=None, name: Optional[str] = None, device=None, **_ignored):
         self.units, self.activation, self.name = int(units), activation, name
-        self.kernel: Optional[torch.Tensor] = None
-        self.bias: Optional[torch.Tensor] = None
+        self._version = 0
+        self._wt_cache = None
+        self._kernel: Optional[torch.Tensor] = None
+        self._bias: Optional[torch.Tensor] = None
         self._device = _dev(device)
+
+    # assigning kernel / bias (build, set_weights, or directly) bumps `_version`: the bf16 copy below and every handle
+    # built from this layer (fused ranker, head packing, CUDA-graph sessions) are keyed on it
+    @property
+    def kernel(self) -> Optional[torch.Tensor]:
+        return self._kernel
+
+    @kernel.setter
+    def kernel(self, k: Optional[torch.Tensor]) -> None:
+        self._kernel = k
+        self._version += 1
+        self._wt_cache = None
+
+    @property
+    def bias(self) -> Optional[torch.Tensor]:
+        return self._bias
+
+    @bias.setter
+    def bias(self, b: Optional[torch.Tensor]) -> None:
+        self._bias = b
+        self._version += 1
 
     def build(self, input_dim: int, seed: int = 0):
         lim = float(np.sqrt(6.0 / (input_dim + self.units)))
@@ -109,9 +144,9 @@ class Dense:
 
     def wt_bf16(self) -> torch.Tensor:
         """The kernel transposed to [out, in] bf16 -- the K-major B operand of the tcgen05 path (cached)."""
-        c = getattr(self, "_wt_cache", None)
-        if c is None or c[0] != self.kernel.data_ptr():
-            c = (self.kernel.data_ptr(), self.kernel.t().contiguous().to(torch.bfloat16))
+        c = self._wt_cache
+        if c is None or c[0] != self._version:
+            c = (self._version, self.kernel.t().contiguous().to(torch.bfloat16))
             self._wt_cache = c
         return c[1]
 
@@ -192,6 +227,7 @@ class DeepCrossNetwork:
 
     def _set_cross(self, w: torch.Tensor, b: torch.Tensor):
         self._cross_w, self._cross_b = w.contiguous(), b.contiguous()
+        self._version = getattr(self, "_version", 0) + 1
         # the reference's variable shapes: cross_w_i (D, 1), cross_b_i (D,)  (src/models.py:34-35)
         self.cross_weights = [self._cross_w[i].unsqueeze(1) for i in range(w.shape[0])]
         self.cross_biases = [self._cross_b[i] for i in range(w.shape[0])]
@@ -358,7 +394,7 @@ class RankingSession:
         out = sess.run()                      # or: out = sess({"user_id": rows_u, "movie_id": rows_i})
 
     Same kernels, same arithmetic as the eager call (bit-identical outputs, tests/test_gpu_ranking_bf16.py).  A session
-    snapshots the model's weights at capture time."""
+    snapshots the model's weights at capture time and re-captures itself when the model's weights_signature() changes."""
 
     def __init__(self, model: "MultiTaskModel", batch: int, ids_dtype=torch.int32):
         if model.precision != "bf16":
@@ -367,6 +403,10 @@ class RankingSession:
         dev = model.device
         self.user_rows = torch.zeros((self.batch,), dtype=ids_dtype, device=dev)
         self.item_rows = torch.zeros((self.batch,), dtype=ids_dtype, device=dev)
+        self._capture()
+
+    def _capture(self) -> None:
+        model, dev = self.model, self.model.device
         feats = {"user_id": self.user_rows, "movie_id": self.item_rows}
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
@@ -379,11 +419,13 @@ class RankingSession:
         with torch.cuda.graph(self._graph):
             self.outputs = model(feats)
         # the captured launches point into the ranker handle's own copies of the weights: keep that handle alive for as
-        # long as the graph can be replayed (load_weights on the model builds a NEW handle; this session then still
-        # computes with the weights it was captured with -- create a new session after changing weights)
+        # long as the graph can be replayed, and remember which weights it was captured with
         self._ranker = getattr(model, "_ranker", None)
+        self._sig = model.weights_signature()
 
     def run(self) -> Dict[str, torch.Tensor]:
+        if self._sig != self.model.weights_signature():      # weights changed since capture: capture again (rare)
+            self._capture()
         self._graph.replay()
         return self.outputs
 
@@ -420,10 +462,19 @@ class MultiTaskModel:
         self.ctr_head.build(W, seed=32)
         self._head_cache = None
 
+    def weights_signature(self) -> tuple:
+        """Version counters of every weight the forward reads.  Handles that copy or borrow weights (the fused ranker,
+        the head packing, CUDA-graph sessions) remember the signature they were built from and are rebuilt when it
+        changes -- so Keras-style `layer.set_weights(...)`, `set_cross_weights` or a plain attribute assignment can never
+        leave a stale copy in use.  (Versions, not data pointers: the caching allocator reuses addresses.)"""
+        enc, dcn = self.encoder, self.dcn
+        layers = list(enc.user_tower.layers) + list(enc.item_tower.layers) + list(dcn.deep_nets) + [self.rating_head, self.ctr_head]
+        return (enc.user_embedding._version, enc.item_embedding._version, getattr(dcn, "_version", 0),
+                tuple(l._version for l in layers))
+
     def _heads_packed(self):
         """[2, W] / [2] packing of the two Dense(1) heads for the fused heads kernel (K3b)."""
-        key = (self.rating_head.kernel.data_ptr(), self.ctr_head.kernel.data_ptr(),
-               self.rating_head.bias.data_ptr(), self.ctr_head.bias.data_ptr())
+        key = (self.rating_head._version, self.ctr_head._version)
         if self._head_cache is None or self._head_cache[0] != key:
             hw = torch.stack([self.rating_head.kernel[:, 0], self.ctr_head.kernel[:, 0]]).contiguous()
             hb = torch.cat([self.rating_head.bias, self.ctr_head.bias]).contiguous()
@@ -466,9 +517,7 @@ class MultiTaskModel:
                  and list(dcn.deep_layers) == [256, 128] and int(rows_i.shape[0]) == B)
         dcn._cross(D)
         if fused and int(dcn._cross_w.shape[1]) == 256:
-            if getattr(self, "_ranker", None) is None:
-                self._ranker = _FusedRanker(self)
-            combined, rating, ctr = self._ranker.forward(rows_u.contiguous(), rows_i.contiguous())
+            combined, rating, ctr = self._fused_ranker().forward(rows_u.contiguous(), rows_i.contiguous())
             return {"user_embedding": combined[:, :E], "item_embedding": combined[:, E:],
                     "rating_prediction": rating, "ctr_prediction": ctr}
         if fused:
@@ -492,6 +541,16 @@ class MultiTaskModel:
         return {"user_embedding": combined[:, :E], "item_embedding": combined[:, E:],
                 "rating_prediction": rating, "ctr_prediction": ctr}
 
+    def _fused_ranker(self) -> "_FusedRanker":
+        """The rs_ranker handle for the CURRENT weights (rebuilt whenever weights_signature() has changed)."""
+        sig = self.weights_signature()
+        r = getattr(self, "_ranker", None)
+        if r is None or getattr(self, "_ranker_sig", None) != sig:
+            self.dcn._cross(2 * self.config.embedding_dim)
+            r = self._ranker = _FusedRanker(self)
+            self._ranker_sig = self.weights_signature()      # _cross() above may have bumped the DCN version
+        return r
+
     def ranking_session(self, batch: int, ids_dtype=torch.int32) -> RankingSession:
         """A CUDA-graph replay of this forward for one fixed batch size (see RankingSession)."""
         return RankingSession(self, batch, ids_dtype)
@@ -499,10 +558,8 @@ class MultiTaskModel:
     def rank_from_embedding_rows(self, user_rows: torch.Tensor, item_rows: torch.Tensor) -> Dict[str, torch.Tensor]:
         """The same forward, fed with already-looked-up embedding rows f32 [B, E] (the output of
         sharded.ShardedEmbedding.lookup when the tables are partitioned over GPUs; bf16 tensor mode only)."""
-        if getattr(self, "_ranker", None) is None:
-            self._ranker = _FusedRanker(self)
         E = self.config.embedding_dim
-        combined, rating, ctr = self._ranker.forward(user_rows, item_rows, from_embedding_rows=True)
+        combined, rating, ctr = self._fused_ranker().forward(user_rows, item_rows, from_embedding_rows=True)
         return {"user_embedding": combined[:, :E], "item_embedding": combined[:, E:],
                 "rating_prediction": rating, "ctr_prediction": ctr}
 
@@ -540,4 +597,4 @@ def load_weights(model, weights: Dict) -> None:
         model.rating_head.set_weights(list(weights["rating_head"]))
         model.ctr_head.set_weights(list(weights["ctr_head"]))
         model._head_cache = None
-        model._ranker = None          # the fused handle copies weights: rebuild it lazily
+        model._ranker = None          # (redundant with the version signature; kept so the old handle is freed at once)

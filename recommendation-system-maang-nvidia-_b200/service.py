@@ -120,22 +120,38 @@ class RecommendationService:
                                         "rank": i + 1})
         return recommendations
 
-    def recommend_batch(self, user_ids: List[str], k: int = 10) -> Dict[str, List[Dict]]:
-        """Batched variant (app/model_service.py:200-228): one tower pass + one catalog pass for all users."""
-        known = [u for u in user_ids if u in self._user_set]
-        out: Dict[str, List[Dict]] = {}
+    def recommend_batch(self, user_ids: List[str], k: int = 10) -> List[Dict]:
+        """Batched variant with the reference's return shape (app/model_service.py:200-228): one entry per input id, in
+        input order -- {"user_id", "recommendations", "status": "success"} or, when that user's recommendations could
+        not be produced, {"user_id", "recommendations": [], "status": "error", "error": message}.  Duplicate ids give
+        duplicate entries.  Unknown users get the cold-start list (status "success", as recommend() would return).
+        Underneath it is ONE user-tower pass + ONE catalog pass for all known users of the call."""
+        known = [u for u in dict.fromkeys(user_ids) if u in self._user_set]
+        recs: Dict[str, List[Dict]] = {}
+        error: Optional[str] = None
         if known:
-            q = self.encoder_model({"user_id": known}, training=False)["user_embedding"]
-            normalize_L2(q)
-            D, I = self.faiss_index.search(q, k)
-            D, I = D.cpu().numpy(), I.cpu().numpy()
-            for r, u in enumerate(known):
-                out[u] = [{"item_id": self.item_map[str(idx)], "score": float(D[r][i]), "rank": i + 1}
-                          for i, idx in enumerate(I[r]) if idx != -1]
+            try:
+                q = self.encoder_model({"user_id": known}, training=False)["user_embedding"]
+                normalize_L2(q)
+                D, I = self.faiss_index.search(q, k)
+                D, I = D.cpu().numpy(), I.cpu().numpy()
+                for r, u in enumerate(known):
+                    recs[u] = [{"item_id": self.item_map[str(idx)], "score": float(D[r][i]), "rank": i + 1}
+                               for i, idx in enumerate(I[r]) if idx != -1]
+            except Exception as e:  # noqa: BLE001 -- the reference catches per user; the batched pass fails as a whole
+                error = str(e)
+        results = []
         for u in user_ids:
-            if u not in out:
-                out[u] = self._get_popular_items(k)
-        return out
+            if u in recs:
+                results.append({"user_id": u, "recommendations": [dict(r) for r in recs[u]], "status": "success"})
+            elif u in self._user_set:
+                results.append({"user_id": u, "recommendations": [], "status": "error", "error": error or "unknown error"})
+            else:
+                try:
+                    results.append({"user_id": u, "recommendations": self._get_popular_items(k), "status": "success"})
+                except Exception as e:  # noqa: BLE001
+                    results.append({"user_id": u, "recommendations": [], "status": "error", "error": str(e)})
+        return results
 
     def score(self, user_id: str, item_ids: List[str]) -> Dict[str, float]:
         if user_id not in self._user_set:

@@ -381,8 +381,12 @@ def test_service_matches_oracle_service(rs):
     assert max(abs(sc[i] - osc[i]) for i in sc) <= 1e-5 * scale
     with pytest.raises(ValueError):
         svc.score("nobody", iv[:3])
-    batch = svc.recommend_batch([uv[0], "nobody", uv[1]], 5)
-    assert batch[uv[0]] == svc.recommend(uv[0], 5) and batch["nobody"] == svc.recommend("nobody", 5)
+    # recommend_batch returns the reference's shape (app/model_service.py:200-228): one entry per input, in order
+    ids = [uv[0], "nobody", uv[1], uv[0]]
+    batch = svc.recommend_batch(ids, 5)
+    assert [b["user_id"] for b in batch] == ids and all(b["status"] == "success" for b in batch)
+    for b in batch:
+        assert b["recommendations"] == svc.recommend(b["user_id"], 5)
 
 
 def test_service_load_from_artifacts(rs, tmp_path):
