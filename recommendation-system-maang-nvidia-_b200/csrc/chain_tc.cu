@@ -20,6 +20,7 @@
 // Tensor work per sample: 81,920 MAC per tower, 98,304 MAC for the deep net.
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <memory>
 #include <mutex>
 
@@ -117,6 +118,12 @@ struct ChainParams {
   int debug;             // perf experiments: 1 = epilogue skips TMEM traffic, 2 = issuer skips the MMAs
   int lag;               // tower_pp_kernel: MMA steps of slot 0 issued before slot 1 may start (RS_TOWER_LAG, default 3)
   long long* trace;      // RS_CHAIN_TRACE=1 (tower_pp_kernel): clock64 stamps of block 0, slot 0, warp 4 ([round][16])
+  const void* zero_row;  // tower_sp_kernel: 512 zero bytes in global memory (what an invalid row id gathers)
+  // tower_sp_kernel: the biases BY VALUE ([problem][b_off(layer) + column]).  Kernel parameters live in the constant bank,
+  // so the epilogue reads them with LDC (same address in every lane) instead of LDS: the shared-memory / L1 pipe is the
+  // one the gather warps saturate with their thread-per-row loads (32 lines per instruction), and bias loads queued
+  // behind them made an epilogue step take 2 k cycles instead of 0.6 k (RS_CHAIN_TRACE)
+  float biasv[2][576];
 };
 
 template <class C>
@@ -775,7 +782,443 @@ tower_pp_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// tower_sp_kernel ("shared ping-pong", round 2).  Same tensor-memory layout, same five MMA steps per tile and the same
+// arithmetic as tower_pp_kernel (bit-identical outputs); what changed is who does what, after the round-1 traces and
+// tools/ubench_tc.cu showed where a 20 k-cycle tile went (MMA 2.6 k):
+//   * ALL 16 epilogue warps serve BOTH tile slots in a fixed order (slot 0 step s, slot 1 step s, slot 0 step s+1 ..).
+//     A step's accumulator (128 columns) is 32 columns per warp -- one tcgen05.ld, one tcgen05.st -- so a step's
+//     epilogue takes ~450 cycles instead of ~1000 (8 warps x 64 columns), and while the warps work on one slot the
+//     tensor pipe runs the other slot's step: a half-step costs max(MMA, epilogue + hand-off) instead of their sum.
+//   * The embedding gather has its own four warps (one per TMEM lane quarter): thread-per-row loads of the whole 256-byte
+//     bf16 row, held in registers until the slot's A0 columns are free, then four tcgen05.st.  It used to cost the
+//     epilogue warps ~3.9 k cycles per tile (issue + transpose) on the critical path.
+//   * The MMA issuer follows the same fixed order with blocking (suspending) waits instead of polling both slots.
+//   * The output step is bound by the SM's store path (32 B/clk measured, tools/ubench_tc.cu: 96 KB per tile = 3.1 k
+//     cycles): it still goes through two 2 KB stage buffers per warp and TMA / bulk stores, but a warp releases the
+//     accumulator columns as soon as its tcgen05.ld has landed, so the next tile's first MMA step overlaps the stores.
+// Barriers per slot: a0_ready (gather -> issuer), a0_free (epilogue step 3 -> gather: columns [0,64) are dead),
+// a_ready (epilogue -> issuer: next step's A operand is in TMEM / after step 4: the accumulator columns are free),
+// acc_ready (tcgen05.commit -> epilogue).
+// ------------------------------------------------------------------------------------------------
+// warps 0-3 gather, warps 4-19 epilogue (TMEM lane quarter = warp % 4 for both), warp 20: one thread loads the kernels
+// (TMA) and then issues every MMA.  21 warps = 672 threads leave 96 registers per thread: with the usual 4 + 4 + 16 warps
+// (80 registers) the gather rows and a handful of loop scalars spilled, and a spill is an L2 round trip here -- the
+// 227 KB of shared memory leave the SM almost no L1.
+constexpr int SP_THREADS = 672;
+constexpr int SP_EPI0 = 4;
+constexpr int SP_EPI_WARPS = 16;
+constexpr int SP_ISSUER = SP_EPI0 + SP_EPI_WARPS;
+
+template <bool TRACE>
+__global__ void __launch_bounds__(SP_THREADS, 1)
+tower_sp_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ ChainParams p) {
+  using C = CfgTower;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* base = smem_raw;
+  if ((smem_u32(base) & 1023u) != 0) __trap();   // all 227 KB are in use: no room for alignment slack
+  uint8_t* wsm = base;
+  float* bias_s = reinterpret_cast<float*>(base + w_off<C>(C::L));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + b_off<C>(C::L));
+  uint64_t* wfull = bars;
+  uint64_t* a0_ready = bars + 1;    // [2]
+  uint64_t* a0_free = bars + 3;     // [2]
+  uint64_t* a_ready = bars + 5;     // [2]
+  uint64_t* acc_ready = bars + 7;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint8_t* stage = base + TOWER_STAGE_OFF;   // [16 epilogue warps][2][TOWER_STAGE_BYTES]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int pi = blockIdx.x % p.n_prob;
+  const int cta = blockIdx.x / p.n_prob;
+  const int ncta = (gridDim.x - pi + p.n_prob - 1) / p.n_prob;
+  const ChainProblem& pr = p.prob[pi];
+  // 32-bit tile arithmetic throughout (a tile is 128 rows: 2^31 rows is far beyond any batch): every register counts,
+  // the cap is 80 and a spill is an L2 round trip
+  const int ntiles = static_cast<int>((pr.rows + BM - 1) / BM);
+  const int n_my = cta < ntiles ? (ntiles - cta + ncta - 1) / ncta : 0;
+  const int n_slot0 = (n_my + 1) / 2, n_slot1 = n_my / 2;   // tiles of slot 0 / slot 1 (tile j of this CTA -> slot j & 1)
+
+  if (warp == SP_ISSUER && lane == 0) {
+    for (int l = 0; l < C::L; ++l) tma_prefetch_desc(&maps.w[pi][l]);
+    tma_prefetch_desc(&maps.y[pi]);
+    mbar_init(wfull, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&a0_ready[s], 4);
+      mbar_init(&a0_free[s], SP_EPI_WARPS);
+      mbar_init(&a_ready[s], SP_EPI_WARPS);
+      mbar_init(&acc_ready[s], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == SP_ISSUER) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == SP_ISSUER) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(wfull, w_off<C>(C::L));
+#pragma unroll
+      for (int l = 0; l < C::L; ++l)
+        for (int kc = 0; kc < C::K(l) / 64; ++kc)
+          tma_load_2d(wsm + w_off<C>(l) + kc * (C::N(l) * 128), &maps.w[pi][l], wfull, kc * 64, 0, kEvictLast);
+      // ---------------- MMA issuer ----------------
+      // Event order (shared with the epilogue warps): slot 0 step k of its tile r, then slot 1 step (k + 3) % 5 -- slot 1
+      // runs two steps behind slot 0, so the two output steps (96 KB each into a store path that drains ~20 B/clk) are
+      // half a round apart instead of back to back.  The slot is a RUN-TIME value and the steps share code where they
+      // can: this kernel's first version unrolled (step x slot) and was 68 KB of SASS -- twice the 32 KB instruction
+      // cache -- and the single issuing thread then paid an instruction-cache miss per MMA group (~470 cycles from an
+      // epilogue's arrive to the next MMA, RS_CHAIN_TRACE).
+      mbar_wait(wfull, 0);
+      uint64_t wdesc0 = umma_desc_k_sw128(smem_u32(wsm));
+      constexpr uint32_t idesc128 = umma_idesc_bf16_f32(BM, 128);
+      constexpr uint32_t idesc64 = umma_idesc_bf16_f32(BM, 64);
+      uint32_t use0 = 0, use1 = 0;
+      for (int r = 0; r <= n_slot0; ++r) {
+#pragma unroll 1
+        for (int k = 0; k < 5; ++k) {
+#pragma unroll 1
+          for (int slot = 0; slot < 2; ++slot) {
+            const int step = slot == 0 ? k : (k >= 2 ? k - 2 : k + 3);
+            const int t = slot == 0 ? r : (k < 2 ? r - 1 : r);   // this slot's tile number
+            if (t < 0 || t >= (slot == 0 ? n_slot0 : n_slot1)) continue;
+            uint32_t& use = slot == 0 ? use0 : use1;
+            if (step == 0) mbar_wait(&a0_ready[slot], static_cast<uint32_t>(t & 1));
+            if (step != 0 || t > 0) {   // step 0: the previous tile's last accumulator has been read
+              mbar_wait(&a_ready[slot], use & 1u);
+              ++use;
+            }
+            tc_fence_after_sync();
+            if (TRACE && blockIdx.x == 0 && t < 4) p.trace[80 + (t * 2 + slot) * 5 + step] = clock64();
+            const uint32_t R = tmem_base + slot * 256;
+            asm volatile("" : "+l"(wdesc0));   // keeps the 36 operand descriptors from being hoisted (and spilled) as loop invariants
+            switch (step) {
+              case 0:
+              case 1: {   // L1 half: A0 [R, R+64) x W1 rows [128*step, +128), K = 128 -> acc [R+64, +128)
+                const uint64_t wd = wdesc0 + static_cast<uint64_t>((w_off<C>(0) + step * (128 * 128)) >> 4);
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk)
+                  umma_bf16_ts(R + 64, R + kk * 8, wd + static_cast<uint64_t>(((kk >> 2) * (256 * 128) + (kk & 3) * 32) >> 4), idesc128,
+                               kk > 0 ? 1u : 0u);
+                break;
+              }
+              case 2: {   // L2: A1a [R+192, +64) then A1b [R, +64), W2 (N = 128), K = 256 -> acc
+#pragma unroll
+                for (int kk = 0; kk < 16; ++kk)
+                  umma_bf16_ts(R + 64, kk < 8 ? R + 192 + kk * 8 : R + (kk - 8) * 8,
+                               wdesc0 + static_cast<uint64_t>((w_off<C>(1) + (kk >> 2) * (128 * 128) + (kk & 3) * 32) >> 4), idesc128,
+                               kk > 0 ? 1u : 0u);
+                break;
+              }
+              case 3: {   // L3: A2 [R+192, +64), W3 (N = 64), K = 128 -> acc3 [R, +64)
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk)
+                  umma_bf16_ts(R, R + 192 + kk * 8,
+                               wdesc0 + static_cast<uint64_t>((w_off<C>(2) + (kk >> 2) * (64 * 128) + (kk & 3) * 32) >> 4), idesc64,
+                               kk > 0 ? 1u : 0u);
+                break;
+              }
+              default: {  // L4: A3 [R+64, +32), W4 (N = 128), K = 64 -> acc4 [R+128, +128)
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                  umma_bf16_ts(R + 128, R + 64 + kk * 8, wdesc0 + static_cast<uint64_t>((w_off<C>(3) + (kk & 3) * 32) >> 4), idesc128,
+                               kk > 0 ? 1u : 0u);
+                break;
+              }
+            }
+            umma_commit(&acc_ready[slot]);
+          }
+        }
+      }
+    }
+  } else if (warp < SP_EPI0) {
+    // ---------------- gather: one embedding row per thread -> A0 of the slot, as soon as its columns are free ----------------
+    const int quarter = warp & 3;
+    const uint32_t lane_sel = static_cast<uint32_t>(quarter * 32) << 16;
+#pragma unroll 1
+    for (int j = 0; j < n_my; ++j) {
+      const int slot = j & 1;
+      const int r = j >> 1;
+      const int64_t row_ = static_cast<int64_t>(cta + j * ncta) * BM + quarter * 32 + lane;
+      int64_t id = -1;
+      if (row_ < pr.rows)
+        id = !pr.ids ? row_
+             : pr.ids64 ? static_cast<const int64_t*>(pr.ids)[row_]
+                        : static_cast<int64_t>(static_cast<const int32_t*>(pr.ids)[row_]);
+      const bool ok = id >= 0 && id < pr.table_rows;   // rows past the batch and out-of-range ids read as zeros
+      const uint32_t R = tmem_base + slot * 256 + lane_sel;
+      const bool tr = TRACE && blockIdx.x == 0 && j < 8 && quarter == 0 && lane == 0;
+      if (tr) p.trace[120 + j * 3] = clock64();
+      if (pr.table16) {
+        // the whole 256-byte bf16 row: sixteen 128-bit loads in flight, untouched until the columns are free.  An invalid
+        // row reads a row of zeros (p.zero_row) instead of being masked afterwards: no selects, no extra live registers.
+        uint32_t a0[64];
+        const uint4* src = ok ? reinterpret_cast<const uint4*>(pr.table16 + id * 128) : reinterpret_cast<const uint4*>(p.zero_row);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const uint4 u = __ldg(src + e);
+          a0[4 * e] = u.x; a0[4 * e + 1] = u.y; a0[4 * e + 2] = u.z; a0[4 * e + 3] = u.w;
+        }
+        if (r > 0) mbar_wait(&a0_free[slot], static_cast<uint32_t>((r - 1) & 1));
+        tc_fence_after_sync();
+        if (tr) p.trace[120 + j * 3 + 1] = clock64();
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_st_32x32_x16_nowait(R + c * 16, a0 + c * 16);
+        tmem_st_wait();
+      } else {
+        // fp32 rows (no bf16 copy of the table; looked-up rows of a sharded table): half a row at a time
+        const float4* src = ok ? reinterpret_cast<const float4*>(pr.table + id * pr.table_ld) : reinterpret_cast<const float4*>(p.zero_row);
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          uint32_t a[32];
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            float4 f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = __ldg(src + h * 16 + b * 8 + e);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              a[b * 16 + 2 * e] = pack_bf16x2(f[e].x, f[e].y);
+              a[b * 16 + 2 * e + 1] = pack_bf16x2(f[e].z, f[e].w);
+            }
+          }
+          if (h == 0) {
+            if (r > 0) mbar_wait(&a0_free[slot], static_cast<uint32_t>((r - 1) & 1));
+            tc_fence_after_sync();
+            if (tr) p.trace[120 + j * 3 + 1] = clock64();
+          }
+          __syncwarp();
+          tmem_st_32x32_x16_nowait(R + h * 32, a);
+          tmem_st_32x32_x16_nowait(R + h * 32 + 16, a + 16);
+          tmem_st_wait();
+        }
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a0_ready[slot]);
+      if (tr) p.trace[120 + j * 3 + 2] = clock64();
+    }
+  } else {
+    // ---------------- epilogue: 16 warps, both slots, 32 accumulator columns per warp and step ----------------
+    const int ew = warp - SP_EPI0;
+    const int quarter = warp & 3;
+    const int cg = ew >> 2;   // column group: accumulator columns [32 cg, +32) (step 3: [16 cg, +16))
+    const uint32_t lane_sel = static_cast<uint32_t>(quarter * 32) << 16;
+    uint8_t* const stg0 = stage + ew * 2 * TOWER_STAGE_BYTES;
+    uint32_t nst = 0;   // bulk store number: store n reads buffer n & 1
+    auto stage_acquire = [&]() -> uint8_t* {
+      if (lane == 0) bulk_wait_read<1>();
+      __syncwarp();
+      return stg0 + (nst & 1u) * TOWER_STAGE_BYTES;
+    };
+    uint32_t cnt0 = 0, cnt1 = 0;
+    for (int rr_ = 0; rr_ <= n_slot0; ++rr_) {
+#pragma unroll 1
+      for (int k = 0; k < 5; ++k) {
+#pragma unroll 1
+        for (int slot = 0; slot < 2; ++slot) {
+          const int step = slot == 0 ? k : (k >= 2 ? k - 2 : k + 3);   // the issuer's event order (see there)
+          const int r = slot == 0 ? rr_ : (k < 2 ? rr_ - 1 : rr_);
+          if (r < 0 || r >= (slot == 0 ? n_slot0 : n_slot1)) continue;
+          const uint32_t R = tmem_base + slot * 256 + lane_sel;
+          const int tile = cta + (2 * r + slot) * ncta;
+          const bool tr = TRACE && blockIdx.x == 0 && r < 4 && ew == 0 && lane == 0;
+          uint32_t& cnt = slot == 0 ? cnt0 : cnt1;
+          chain_wait(&acc_ready[slot], cnt & 1u);
+          ++cnt;
+          tc_fence_after_sync();
+          if (tr) p.trace[((r * 2 + slot) * 5 + step) * 2] = clock64();
+          if (step <= 2) {
+            // one code path for the three 128-column steps: bias offset, activation and destination are run-time values
+            const int layer = step == 2 ? 1 : 0;
+            const float* bs = p.biasv[pi] + (step == 2 ? b_off<C>(1) : step * 128) + cg * 32;   // constant bank
+            const uint32_t dst = R + (step == 1 ? 0 : 192) + cg * 16;   // A1a, A1b, A2
+            float v[32];
+            __syncwarp();
+            tmem_ld_32x32(R + 64 + cg * 32, v);
+#pragma unroll
+            for (int e = 0; e < 32; e += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(bs + e);
+              v[e] += b4.x; v[e + 1] += b4.y; v[e + 2] += b4.z; v[e + 3] += b4.w;
+            }
+            uint32_t rr[16];
+            if (p.act[layer] == RS_ACT_RELU) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) rr[e] = pack_bf16x2_relu(v[2 * e], v[2 * e + 1]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) rr[e] = pack_bf16x2(v[2 * e], v[2 * e + 1]);
+            }
+            tmem_st_32x32_x16(dst, rr);
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a_ready[slot]);
+          } else if (step == 3) {
+            const float* bs = p.biasv[pi] + b_off<C>(2) + cg * 16;
+            float v[16];
+            __syncwarp();
+            tmem_ld_32x32_x16(R + cg * 16, v);
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a0_free[slot]);   // columns [0,64) are dead: the gather warps may write the next A0
+#pragma unroll
+            for (int e = 0; e < 16; e += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(bs + e);
+              v[e] += b4.x; v[e + 1] += b4.y; v[e + 2] += b4.z; v[e + 3] += b4.w;
+            }
+            uint32_t rr[8];
+            if (p.act[2] == RS_ACT_RELU) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) rr[e] = pack_bf16x2_relu(v[2 * e], v[2 * e + 1]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) rr[e] = pack_bf16x2(v[2 * e], v[2 * e + 1]);
+            }
+            tmem_st_32x32_x8(R + 64 + cg * 8, rr);   // A3
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a_ready[slot]);
+          } else {
+            const int col0 = cg * 32;
+            const float* bs = p.biasv[pi] + b_off<C>(3) + col0;
+            float v[32];
+            __syncwarp();
+            tmem_ld_32x32(R + 128 + col0, v);
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a_ready[slot]);   // the accumulator columns may be overwritten by the next tile's L1
+#pragma unroll
+            for (int e = 0; e < 32; e += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(bs + e);
+              v[e] += b4.x; v[e + 1] += b4.y; v[e + 2] += b4.z; v[e + 3] += b4.w;
+            }
+            if (p.act[3] == RS_ACT_RELU) {
+#pragma unroll
+              for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], 0.0f);
+            }
+            // fp32 output: 16 rows x 128 B per buffer in the 128B-swizzle layout, one TMA store each (rows past the end of
+            // the batch are clipped by the tensor map).  Exactly the warp's two stage buffers.
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              if (p.debug & 16) break;   // perf experiments only: no fp32 output
+              uint8_t* buf = stage_acquire();
+              if ((lane >> 4) == h) {
+                const int rw = lane & 15;
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj)
+                  *reinterpret_cast<float4*>(buf + rw * 128 + ((jj ^ (rw & 7)) << 4)) =
+                      make_float4(v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]);
+              }
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(&maps.y[pi], buf, col0, static_cast<int>(tile * BM + quarter * 32 + h * 16));
+                bulk_commit();
+              }
+              ++nst;
+            }
+            if (pr.y_il16 && !(p.debug & 64)) {
+              // lane-interleaved bf16 copy for the deep kernel: this warp's four 512-byte chunks are 2 KB contiguous;
+              // coalesced 128-bit stores straight from registers
+              uint4* dst = reinterpret_cast<uint4*>(pr.y_il16) + ((static_cast<int64_t>(tile) * 4 + quarter) * 32 + pr.il_chunk0 + (col0 >> 3)) * 32 + lane;
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                dst[e * 32] = make_uint4(pack_bf16x2(v[8 * e], v[8 * e + 1]), pack_bf16x2(v[8 * e + 2], v[8 * e + 3]),
+                                         pack_bf16x2(v[8 * e + 4], v[8 * e + 5]), pack_bf16x2(v[8 * e + 6], v[8 * e + 7]));
+            }
+          }
+          if (tr) p.trace[((r * 2 + slot) * 5 + step) * 2 + 1] = clock64();
+        }
+      }
+    }
+    if (lane == 0) bulk_wait_all();   // the stage buffers (and this CTA) outlive every store
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == SP_ISSUER) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+bool use_tower_sp() {
+  static const bool on = [] { const char* e = getenv("RS_TOWER_SP"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
+// the new kernel serves the fused ranker's call shape: fp32 output through a TMA map (+ optional interleaved bf16 copy)
+bool tower_sp_applies(const ChainParams& p) {
+  for (int i = 0; i < p.n_prob; ++i)
+    if (!p.prob[i].y_f32 || !p.prob[i].y_tma || p.prob[i].y_bf16) return false;
+  return true;
+}
+
+void launch_tower_sp(const ChainMaps& maps, const ChainParams& p, cudaStream_t st) {
+  static std::once_flag once[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  static cudaError_t attr_err[64];
+  std::call_once(once[dev & 63], [dev] {
+    attr_err[dev & 63] = cudaFuncSetAttribute(tower_sp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tower_pp_smem(2));
+    cudaFuncSetAttribute(tower_sp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tower_pp_smem(2));
+    if (attr_err[dev & 63] != cudaSuccess) cudaGetLastError();
+  });
+  RS_CHECK(attr_err[dev & 63] == cudaSuccess, "tower_sp_kernel needs 227 KB of shared memory per block");
+  int64_t max_tiles = 0;
+  for (int i = 0; i < p.n_prob; ++i) max_tiles = std::max<int64_t>(max_tiles, (p.prob[i].rows + BM - 1) / BM);
+  const int sms = rs::sm_count();
+  int grid = static_cast<int>(std::min<int64_t>((max_tiles + 1) / 2 * p.n_prob, sms - (sms % p.n_prob)));
+  grid = std::max(grid, p.n_prob);
+  ChainParams q = p;
+  static void* zero_row[64];   // per device: 512 zero bytes (what an invalid row id gathers); lives as long as the library
+  static std::once_flag zonce[64];
+  std::call_once(zonce[dev & 63], [dev] {
+    if (cudaMalloc(&zero_row[dev & 63], 512) == cudaSuccess) cudaMemset(zero_row[dev & 63], 0, 512);
+    else zero_row[dev & 63] = nullptr;
+  });
+  RS_CHECK(zero_row[dev & 63] != nullptr, "could not allocate the zero row");
+  q.zero_row = zero_row[dev & 63];
+  static const int dbg = [] { const char* e = getenv("RS_CHAIN_DEBUG"); return e ? atoi(e) : 0; }();
+  q.debug = dbg;   // perf experiments: 16 / 64 skip the fp32 / interleaved bf16 output
+  const char* tr_env = getenv("RS_CHAIN_TRACE");
+  if (tr_env && tr_env[0] == '1') {   // debugging aid: phase stamps of CTA 0, relative to the first one
+    RS_CUDA(cudaMalloc(&q.trace, 256 * sizeof(long long)));
+    RS_CUDA(cudaMemsetAsync(q.trace, 0, 256 * sizeof(long long), st));
+    tower_sp_kernel<true><<<grid, SP_THREADS, tower_pp_smem(2), st>>>(maps, q);
+    RS_LAUNCH_CHECK();
+    long long host[256];
+    RS_CUDA(cudaStreamSynchronize(st));
+    RS_CUDA(cudaMemcpy(host, q.trace, sizeof(host), cudaMemcpyDeviceToHost));
+    cudaFree(q.trace);
+    long long t0 = host[120] ? host[120] : host[0];
+    for (int t = 0; t < 8; ++t) {   // (round, slot)
+      if (!host[t * 10]) continue;
+      fprintf(stderr, "tower_sp round %d slot %d: issue", t / 2, t % 2);
+      for (int k = 0; k < 5; ++k) fprintf(stderr, " %lld", host[80 + t * 5 + k] - t0);
+      fprintf(stderr, " | epilogue (acc seen, done) x5:");
+      for (int k = 0; k < 10; ++k) fprintf(stderr, " %lld", host[t * 10 + k] - t0);
+      fprintf(stderr, "\n");
+    }
+    for (int j = 0; j < 8; ++j)
+      if (host[120 + j * 3]) fprintf(stderr, "tower_sp gather tile %d: start %lld columns free %lld A0 ready %lld\n", j, host[120 + j * 3] - t0,
+                                     host[121 + j * 3] - t0, host[122 + j * 3] - t0);
+    return;
+  }
+  rs::ProfScope prof(RS_PROF_RANK, st);
+  tower_sp_kernel<false><<<grid, SP_THREADS, tower_pp_smem(2), st>>>(maps, q);
+  RS_LAUNCH_CHECK();
+}
+
 void launch_tower_pp(const ChainMaps& maps, const ChainParams& p, cudaStream_t st) {
+  if (use_tower_sp() && tower_sp_applies(p)) return launch_tower_sp(maps, p, st);
   static std::once_flag once[64];
   int dev = 0;
   cudaGetDevice(&dev);
@@ -1051,6 +1494,10 @@ struct DeepHeadsParams {
   float* rating;           // [rows]
   float* ctr;              // [rows]
   long long* trace;        // RS_CHAIN_TRACE=1: clock64 stamps of CTA 0 ([tile][16]: 0-7 epilogue warp 4, 8-11 MMA issuer)
+  // deep_heads2_kernel: biases (256 + 128) and the deep part of the two head rows ([2][128]) BY VALUE -- kernel parameters
+  // sit in the constant bank, so the epilogues read them with LDC instead of LDS (see ChainParams::biasv)
+  float biasv[384];
+  float hdv[256];
 };
 
 // per-model constants of the closed-form cross recurrence, computed once when the ranker handle is created
@@ -1236,7 +1683,8 @@ deep_heads_kernel(const __grid_constant__ ChainMaps maps, const DeepHeadsParams 
       const int64_t row_ = tile_ * BM + trow;
       if (row_ < p.rows) {
         p.rating[row_] = zr;
-        p.ctr[row_] = 1.0f / (1.0f + expf(-zc));
+        p.ctr[row_] = __fdividef(1.0f, 1.0f + __expf(-zc));   // MUFU only: an IEEE division / expf has a slow path that is an ABI
+                                                                // call, and a call inside the epilogue spills everything live
       }
     };
     if (n_my > 0) load_next(cta);
@@ -1358,6 +1806,324 @@ void launch_deep_heads(const ChainMaps& maps, const DeepHeadsParams& p, cudaStre
   RS_LAUNCH_CHECK();
 }
 
+// ------------------------------------------------------------------------------------------------
+// deep_heads2_kernel (round 2): the same arithmetic as deep_heads_kernel (bit-identical outputs), pipelined INSIDE a tile.
+// deep_heads_kernel runs a tile as MMA(L0) -> epilogue -> MMA(L1) -> epilogue, one after the other (8.2 k cycles per tile
+// for 3.3 k of MMA, RS_CHAIN_TRACE), and two tiles in flight do not fit tensor memory (A0 128 + accumulator 272 columns).
+// Here layer 0 runs as two N halves into two accumulator regions and layer 1 as two K halves:
+//     L0a: A0 x [W1 rows 0-127 | 16 dot rows] -> X   (N = 144: the x0 dots ride in the same MMAs; they used to be 16
+//                                                     extra N = 16 instructions, which cost 45 cycles each like any MMA
+//                                                     with N <= 64 -- tools/ubench_tc.cu -- 720 cycles per tile)
+//     L0b: A0 x  W1 rows 128-255                -> Y     || epilogue a: X -> bias, relu, bf16 -> A1a; dots -> registers
+//     L1a: A1a x W2[:, 0:128]                   -> X     || epilogue b: Y -> A1b (over A0's first half, dead by then)
+//     L1b: A1b x W2[:, 128:256]                 -> X (accumulate)
+//     epilogue 1: next tile's A0 -> tensor memory first (the issuer starts its L0a at once), then X -> heads.
+// X / Y swap every tile, so the next tile's L0a never waits for this tile's last epilogue.
+// Tensor memory columns: A0 [0,128)  RA [128,272)  RB [272,416)  A1a [416,480).
+// ------------------------------------------------------------------------------------------------
+constexpr int DH2_W1B_OFF = 128 * 128 + DOTW_ROWS * 128;          // within a K chunk: W1 rows 0-127 | dot rows | W1 rows 128-255
+constexpr int DH2_KC_BYTES = DH2_W1B_OFF + 128 * 128;             // 34,816 bytes per 64-wide K chunk of layer 0
+constexpr int DH2_W2_OFF = 4 * DH2_KC_BYTES;
+constexpr int DH2_W_BYTES = DH2_W2_OFF + 4 * 128 * 128;           // 204,800: what deep_heads_kernel keeps resident as well
+constexpr int DH2_A0 = 0, DH2_RA = 128, DH2_RB = 272, DH2_A1A = 416;
+// warps 0-15 epilogue (TMEM lane quarter = warp % 4, column slice = warp / 4), warp 16: one thread loads the kernels (TMA) and
+// issues every MMA.  17 warps = 544 threads: 120 registers per thread, nothing spills (a spill is an L2 round trip here)
+constexpr int DH2_ISSUER = EPI_WARPS;
+constexpr int DH2_THREADS = (EPI_WARPS + 1) * 32;
+static_assert(DH2_KC_BYTES % 1024 == 0 && DH2_W1B_OFF % 1024 == 0, "operand tiles must stay 1024-byte aligned (128B swizzle)");
+
+template <int LC>
+constexpr int deep_heads2_smem() {
+  return DH2_W_BYTES + (384 + 256 + 8 + 2 * 512) * 4 + 256 + 1024;
+}
+
+template <int LC, bool TRACE>
+__global__ void __launch_bounds__(DH2_THREADS, 1)
+deep_heads2_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ DeepHeadsParams p) {
+  constexpr int NP = LC + 2;   // dots over x0 per row
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* wsm = base;
+  float* bias_s = reinterpret_cast<float*>(base + DH2_W_BYTES);
+  float* hd_s = bias_s + 384;                 // [2][128]: the deep part of the two head rows
+  float* const_s = hd_s + 256;                // [LC] c_l . w_l, then c_L . head_r, c_L . head_c
+  float* part = const_s + 8;                  // [2][4 slices][128 rows]: deep . head_r[256:], deep . head_c[256:] partials
+  uint64_t* bars = reinterpret_cast<uint64_t*>(part + 2 * 512);
+  uint64_t* wfull = bars;
+  uint64_t* a0_ready = bars + 1;     // 16 epilogue warps: this tile's A0 is in tensor memory
+  uint64_t* acc_a = bars + 2;        // commit: L0a (and the dots) done
+  uint64_t* acc_b = bars + 3;        // commit: L0b done
+  uint64_t* a1a_ready = bars + 4;    // 16: A1a written (X has been read)
+  uint64_t* a1b_ready = bars + 5;    // 16: A1b written (Y has been read)
+  uint64_t* acc1_ready = bars + 6;   // commit: layer 1 done
+  uint64_t* acc1_read = bars + 7;    // 16: X has been read again -> the next tile may use it as its Y
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int cta = blockIdx.x;
+  const int ncta = gridDim.x;
+  const int ntiles = static_cast<int>((p.rows + BM - 1) / BM);   // 32-bit tile arithmetic: registers are scarce
+  const int n_my = cta < ntiles ? (ntiles - cta + ncta - 1) / ncta : 0;
+
+  if (warp == DH2_ISSUER && lane == 0) {
+    tma_prefetch_desc(&maps.w[1][0]);
+    tma_prefetch_desc(&maps.w[0][1]);
+    tma_prefetch_desc(&maps.w[0][2]);
+    mbar_init(wfull, 1);
+    mbar_init(a0_ready, EPI_WARPS);
+    mbar_init(acc_a, 1);
+    mbar_init(acc_b, 1);
+    mbar_init(a1a_ready, EPI_WARPS);
+    mbar_init(a1b_ready, EPI_WARPS);
+    mbar_init(acc1_ready, 1);
+    mbar_init(acc1_read, EPI_WARPS);
+    fence_mbar_init();
+  }
+  if (threadIdx.x < NP) const_s[threadIdx.x] = p.consts[threadIdx.x];
+  if (warp == DH2_ISSUER) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == DH2_ISSUER) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(wfull, DH2_W_BYTES);
+      for (int kc = 0; kc < 4; ++kc) {   // maps.w[1][0]: W1 [256, 256] with a 128-row box
+        tma_load_2d(wsm + kc * DH2_KC_BYTES, &maps.w[1][0], wfull, kc * 64, 0, kEvictLast);
+        tma_load_2d(wsm + kc * DH2_KC_BYTES + 128 * 128, &maps.w[0][2], wfull, kc * 64, 0, kEvictLast);
+        tma_load_2d(wsm + kc * DH2_KC_BYTES + DH2_W1B_OFF, &maps.w[1][0], wfull, kc * 64, 128, kEvictLast);
+      }
+      for (int kc = 0; kc < 4; ++kc)
+        tma_load_2d(wsm + DH2_W2_OFF + kc * (128 * 128), &maps.w[0][1], wfull, kc * 64, 0, kEvictLast);
+      mbar_wait(wfull, 0);
+      uint64_t wdesc0 = umma_desc_k_sw128(smem_u32(wsm));
+      constexpr uint32_t idesc_a = umma_idesc_bf16_f32(BM, 128 + DOTW_ROWS);
+      constexpr uint32_t idesc_h = umma_idesc_bf16_f32(BM, 128);
+      for (int i = 0; i < n_my; ++i) {
+        // opaque to the optimiser: otherwise all 48 operand descriptors (wdesc0 + constant) are hoisted out of the loop as
+        // loop invariants, 96 registers' worth, and come back as spill loads on the issue path
+        asm volatile("" : "+l"(wdesc0));
+        const uint32_t ph = static_cast<uint32_t>(i & 1);
+        const uint32_t X = tmem_base + (ph ? DH2_RB : DH2_RA), Y = tmem_base + (ph ? DH2_RA : DH2_RB);
+        mbar_wait(a0_ready, ph);
+        tc_fence_after_sync();
+        if (TRACE && cta == 0 && i < 8) p.trace[i * 16 + 8] = clock64();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const uint64_t db = wdesc0 + static_cast<uint64_t>(((k >> 2) * DH2_KC_BYTES + (k & 3) * 32) >> 4);
+          umma_bf16_ts(X, tmem_base + DH2_A0 + k * 8, db, idesc_a, k > 0 ? 1u : 0u);
+        }
+        umma_commit(acc_a);
+        if (i > 0) {   // Y is the previous tile's X: its layer-1 accumulator must have been read
+          mbar_wait(acc1_read, static_cast<uint32_t>((i - 1) & 1));
+          tc_fence_after_sync();
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const uint64_t db = wdesc0 + static_cast<uint64_t>(((k >> 2) * DH2_KC_BYTES + DH2_W1B_OFF + (k & 3) * 32) >> 4);
+          umma_bf16_ts(Y, tmem_base + DH2_A0 + k * 8, db, idesc_h, k > 0 ? 1u : 0u);
+        }
+        umma_commit(acc_b);
+        if (TRACE && cta == 0 && i < 8) p.trace[i * 16 + 9] = clock64();
+        mbar_wait(a1a_ready, ph);
+        tc_fence_after_sync();
+        if (TRACE && cta == 0 && i < 8) p.trace[i * 16 + 10] = clock64();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint64_t db = wdesc0 + static_cast<uint64_t>((DH2_W2_OFF + (k >> 2) * (128 * 128) + (k & 3) * 32) >> 4);
+          umma_bf16_ts(X, tmem_base + DH2_A1A + k * 8, db, idesc_h, k > 0 ? 1u : 0u);
+        }
+        mbar_wait(a1b_ready, ph);
+        tc_fence_after_sync();
+#pragma unroll
+        for (int k = 8; k < 16; ++k) {
+          const uint64_t db = wdesc0 + static_cast<uint64_t>((DH2_W2_OFF + (k >> 2) * (128 * 128) + (k & 3) * 32) >> 4);
+          umma_bf16_ts(X, tmem_base + DH2_A0 + (k - 8) * 8, db, idesc_h, 1u);
+        }
+        umma_commit(acc1_ready);
+        if (TRACE && cta == 0 && i < 8) p.trace[i * 16 + 11] = clock64();
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int slice = warp >> 2;
+    const int trow = quarter * 32 + lane;                 // this thread's row inside a tile
+    const uint32_t lane_sel = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t T = tmem_base + lane_sel;
+    const float hb0 = p.hb[0], hb1 = p.hb[1];
+    // One tile ahead, in registers: this row's 64-feature slice of x0 (8 x 128 bits, lane-interleaved layout).  Nothing
+    // reads it before it is stored to tensor memory.  Unconditional: x_il16 is padded to whole tiles.
+    uint4 a0[8];
+    float pd[NP];
+#pragma unroll
+    for (int t = 0; t < NP; ++t) pd[t] = 0.0f;
+    auto load_next = [&](int tile_) {
+      const uint4* src = reinterpret_cast<const uint4*>(p.x_il16) + ((static_cast<int64_t>(tile_) * 4 + quarter) * 32 + slice * 8) * 32 + lane;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) a0[e] = __ldg(src + e * 32);
+    };
+    auto store_a0 = [&]() {
+      uint32_t (&r0)[16] = reinterpret_cast<uint32_t (&)[16]>(a0[0]);
+      uint32_t (&r1)[16] = reinterpret_cast<uint32_t (&)[16]>(a0[4]);
+      __syncwarp();
+      tmem_st_32x32_x16(T + DH2_A0 + slice * 32, r0);
+      tmem_st_32x32_x16(T + DH2_A0 + slice * 32 + 16, r1);
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a0_ready);
+    };
+    // cross recurrence + heads of one finished tile: the slice-0 warp of each quarter, once the other three warps of the
+    // quarter have published their partial dots (named barrier 1 + quarter, 128 threads)
+    auto finish = [&](int tile_) {
+      if (slice != 0) {   // bar.arrive orders this thread's earlier shared-memory writes before the barrier completes
+        asm volatile("bar.arrive %0, 128;" ::"r"(1 + quarter) : "memory");
+        return;
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + quarter) : "memory");
+      float s[NP + 2];
+#pragma unroll
+      for (int t = 0; t < NP; ++t) s[t] = pd[t];
+#pragma unroll
+      for (int t = 0; t < 2; ++t)
+        s[NP + t] = (part[(t * 4 + 0) * 128 + trow] + part[(t * 4 + 1) * 128 + trow]) +
+                    (part[(t * 4 + 2) * 128 + trow] + part[(t * 4 + 3) * 128 + trow]);
+      float a = 1.0f;
+#pragma unroll
+      for (int l = 0; l < LC; ++l) a += fmaf(a, s[l], const_s[l]);
+      const float zr = fmaf(a, s[LC], const_s[LC]) + s[NP] + hb0;
+      const float zc = fmaf(a, s[LC + 1], const_s[LC + 1]) + s[NP + 1] + hb1;
+      const int64_t row_ = static_cast<int64_t>(tile_) * BM + trow;
+      if (row_ < p.rows) {
+        p.rating[row_] = zr;
+        p.ctr[row_] = __fdividef(1.0f, 1.0f + __expf(-zc));   // MUFU only: an IEEE division / expf has a slow path that is an ABI
+                                                                // call, and a call inside the epilogue spills everything live
+      }
+    };
+    if (n_my > 0) {
+      load_next(cta);
+      store_a0();
+    }
+    for (int i = 0; i < n_my; ++i) {
+      const int tile = cta + i * ncta;
+      const uint32_t ph = static_cast<uint32_t>(i & 1);
+      const uint32_t X = T + (ph ? DH2_RB : DH2_RA), Y = T + (ph ? DH2_RA : DH2_RB);
+      const bool tr = TRACE && cta == 0 && i < 8 && warp == 0 && lane == 0;
+      auto stamp = [&](int k) { if (tr) p.trace[i * 16 + k] = clock64(); };
+      // ---- epilogues a / b (one code path): 128 deep columns each -> bias, relu, bf16 -> A1a / A1b.  A1b lands on the
+      //      first half of A0 (L0b has completed).  Epilogue a of the slice-0 warps also takes this row's x0 dots. ----
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        chain_wait(half ? acc_b : acc_a, ph);
+        tc_fence_after_sync();
+        stamp(2 * half);
+        {
+          float v[32];
+          __syncwarp();
+          tmem_ld_32x32((half ? Y : X) + slice * 32, v);
+          const float* bs = p.biasv + half * 128 + slice * 32;   // constant bank
+          uint32_t r[16];
+#pragma unroll
+          for (int e = 0; e < 32; e += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bs + e);
+            r[e / 2] = pack_bf16x2_relu(v[e] + b4.x, v[e + 1] + b4.y);
+            r[e / 2 + 1] = pack_bf16x2_relu(v[e + 2] + b4.z, v[e + 3] + b4.w);
+          }
+          tmem_st_32x32_x16(T + (half ? DH2_A0 : DH2_A1A) + slice * 16, r);
+        }
+        if (half == 0 && slice == 0) {
+          float d[16];
+          tmem_ld_32x32_x16(X + 128, d);
+#pragma unroll
+          for (int t = 0; t < NP; ++t) pd[t] = d[2 * t] + d[2 * t + 1];
+        }
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(half ? a1b_ready : a1a_ready);
+        stamp(2 * half + 1);
+      }
+      // ---- the next tile's rows: issued here, landing while layer 1 runs (~900 cycles; the rows were prefetched into L2 a
+      //      tile earlier), so that the 32 registers are live only across the wait below -- not across the epilogues,
+      //      where every register is needed (this kernel has no L1 to spill into) ----
+      if (i + 1 < n_my) load_next(tile + ncta);
+      if (i + 2 < n_my && warp == 0 && lane == 0) {
+        const int64_t t2 = tile + 2 * ncta;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.x_il16 + t2 * (BM * 256)), "r"(BM * 256 * 2) : "memory");
+      }
+      // ---- layer 1 done: hand the next tile's A0 to the tensor pipe first (its L0 then runs under this tile's last
+      //      epilogue), then finish this tile on the CUDA cores ----
+      chain_wait(acc1_ready, ph);
+      tc_fence_after_sync();
+      stamp(4);
+      if (i + 1 < n_my) store_a0();
+      stamp(5);
+      {
+        const int col0 = slice * 32;
+        float v[32];
+        __syncwarp();
+        tmem_ld_32x32(X + col0, v);
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc1_read);
+        const float* bs = p.biasv + 256 + col0;   // constant bank, like the two head rows
+        const float* wr = p.hdv + col0;
+        const float* wc = p.hdv + 128 + col0;
+        float dr = 0.0f, dq = 0.0f;
+#pragma unroll
+        for (int e = 0; e < 32; e += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(bs + e);
+          const float4 r4 = *reinterpret_cast<const float4*>(wr + e);
+          const float4 c4 = *reinterpret_cast<const float4*>(wc + e);
+          const float y0 = fmaxf(v[e] + b4.x, 0.0f), y1 = fmaxf(v[e + 1] + b4.y, 0.0f);
+          const float y2 = fmaxf(v[e + 2] + b4.z, 0.0f), y3 = fmaxf(v[e + 3] + b4.w, 0.0f);
+          dr = fmaf(y0, r4.x, dr); dr = fmaf(y1, r4.y, dr); dr = fmaf(y2, r4.z, dr); dr = fmaf(y3, r4.w, dr);
+          dq = fmaf(y0, c4.x, dq); dq = fmaf(y1, c4.y, dq); dq = fmaf(y2, c4.z, dq); dq = fmaf(y3, c4.w, dq);
+        }
+        part[(0 * 4 + slice) * 128 + trow] = dr;
+        part[(1 * 4 + slice) * 128 + trow] = dq;
+      }
+      stamp(6);
+      // `part` is re-written by the next tile's last epilogue, which runs behind a1b_ready of that tile: every warp,
+      // the slice-0 warps after their finish() below, has arrived there by then
+      finish(tile);
+      stamp(7);
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == DH2_ISSUER) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+bool use_deep_v2() {
+  static const bool on = [] { const char* e = getenv("RS_DEEP_V2"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
+template <int LC>
+void launch_deep_heads2(const ChainMaps& maps, const DeepHeadsParams& p, cudaStream_t st) {
+  static std::once_flag once[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::call_once(once[dev & 63], [] {
+    cudaFuncSetAttribute(deep_heads2_kernel<LC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, deep_heads2_smem<LC>());
+    cudaFuncSetAttribute(deep_heads2_kernel<LC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, deep_heads2_smem<LC>());
+  });
+  const int64_t ntiles = (p.rows + BM - 1) / BM;
+  const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(ntiles, rs::sm_count())));
+  rs::ProfScope prof(RS_PROF_RANK, st);
+  if (p.trace) deep_heads2_kernel<LC, true><<<grid, DH2_THREADS, deep_heads2_smem<LC>(), st>>>(maps, p);
+  else deep_heads2_kernel<LC, false><<<grid, DH2_THREADS, deep_heads2_smem<LC>(), st>>>(maps, p);
+  RS_LAUNCH_CHECK();
+}
+
 bool use_fused_heads() {
   const char* e = getenv("RS_FUSED_HEADS");
   return !(e && e[0] == '0');
@@ -1376,6 +2142,9 @@ struct rs_ranker {
   size_t off_w[2][4], off_dw[2], off_dotw;
   size_t off_b[2][4], off_db[2], off_cw, off_cb, off_hw, off_hb, off_const;
   ChainMaps tower_maps, deep_maps;
+  float h_tower_bias[2][576] = {};   // host copy of the tower biases: tower_sp_kernel takes them as kernel parameters
+  float h_deep_bias[384] = {};       // likewise for deep_heads2_kernel: deep biases and the deep part of the head rows
+  float h_hd[256] = {};
   ~rs_ranker() {
     cudaFree(wts);
     cudaFree(f32);
@@ -1484,6 +2253,8 @@ extern "C" int rs_ranker_create(const DLTensor* user_table, const DLTensor* item
       take_w(deep_wt[l], CfgDeep::N(l), CfgDeep::K(l), h->off_dw[l], &h->deep_maps.w[0][l]);
       take_b(deep_b ? deep_b[l] : nullptr, CfgDeep::N(l), h->off_db[l]);
     }
+    // deep_heads2_kernel loads layer 0's kernel as two 128-row halves (the 16 dot rows sit between them in shared memory)
+    h->deep_maps.w[1][0] = make_tmap_2d(h->wts + h->off_dw[0], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 256, 256, 256 * 2, 128, 64);
     RS_CHECK(on_device(cross_w) && on_device(cross_b) && on_device(head_w) && on_device(head_b), "weights must be CUDA tensors");
     if (L > 0) {
       copy_in(h->f32 + h->off_cw, cross_w, (size_t)L * 256 * 4, st);
@@ -1506,6 +2277,11 @@ extern "C" int rs_ranker_create(const DLTensor* user_table, const DLTensor* item
                                            h->f32 + h->off_const);
     RS_LAUNCH_CHECK();
     RS_CUDA(cudaStreamSynchronize(st));
+    for (int sdx = 0; sdx < 2; ++sdx)
+      RS_CUDA(cudaMemcpy(h->h_tower_bias[sdx], h->f32 + h->off_b[sdx][0], sizeof(float) * 576, cudaMemcpyDeviceToHost));
+    RS_CUDA(cudaMemcpy(h->h_deep_bias, h->f32 + h->off_db[0], sizeof(float) * 384, cudaMemcpyDeviceToHost));
+    for (int t = 0; t < 2; ++t)
+      RS_CUDA(cudaMemcpy(h->h_hd + t * 128, h->f32 + h->off_hw + t * 384 + 256, sizeof(float) * 128, cudaMemcpyDeviceToHost));
     *out = h.release();
   });
 }
@@ -1587,6 +2363,7 @@ static int ranker_forward_impl(rs_ranker* h, const DLTensor* user_rows, const DL
         pr.il_chunk0 = s * 16;
       }
       if (pp) {
+        std::memcpy(p.biasv, h->h_tower_bias, sizeof(p.biasv));
         ChainMaps maps = h->tower_maps;
         for (int s = 0; s < 2; ++s) {
           maps.y[s] = make_tmap_2d(p.prob[s].y_f32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)B, 128, 256 * 4, 16, 32);
@@ -1606,17 +2383,20 @@ static int ranker_forward_impl(rs_ranker* h, const DLTensor* user_rows, const DL
         q.consts = h->f32 + h->off_const;
         q.rating = data_ptr<float>(rating);
         q.ctr = data_ptr<float>(ctr);
+        std::memcpy(q.biasv, h->h_deep_bias, sizeof(q.biasv));
+        std::memcpy(q.hdv, h->h_hd, sizeof(q.hdv));
         const char* tr_env = getenv("RS_CHAIN_TRACE");
         if (tr_env && tr_env[0] == '1') {
           RS_CUDA(cudaMalloc(&q.trace, 8 * 16 * sizeof(long long)));
           RS_CUDA(cudaMemsetAsync(q.trace, 0, 8 * 16 * sizeof(long long), st));
         }
+        const bool v2 = use_deep_v2();
         switch (h->cross_layers) {
-          case 0: launch_deep_heads<0>(h->deep_maps, q, st); break;
-          case 1: launch_deep_heads<1>(h->deep_maps, q, st); break;
-          case 2: launch_deep_heads<2>(h->deep_maps, q, st); break;
-          case 3: launch_deep_heads<3>(h->deep_maps, q, st); break;
-          case 4: launch_deep_heads<4>(h->deep_maps, q, st); break;
+          case 0: v2 ? launch_deep_heads2<0>(h->deep_maps, q, st) : launch_deep_heads<0>(h->deep_maps, q, st); break;
+          case 1: v2 ? launch_deep_heads2<1>(h->deep_maps, q, st) : launch_deep_heads<1>(h->deep_maps, q, st); break;
+          case 2: v2 ? launch_deep_heads2<2>(h->deep_maps, q, st) : launch_deep_heads<2>(h->deep_maps, q, st); break;
+          case 3: v2 ? launch_deep_heads2<3>(h->deep_maps, q, st) : launch_deep_heads<3>(h->deep_maps, q, st); break;
+          case 4: v2 ? launch_deep_heads2<4>(h->deep_maps, q, st) : launch_deep_heads<4>(h->deep_maps, q, st); break;
           default: RS_CHECK(false, "the fused ranker supports up to 4 cross layers");
         }
         cudaFreeAsync(x_il16, st);

@@ -164,15 +164,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (the launch fails with an error) instead of hanging the GPU.
+// Bounded wait: a protocol bug traps (the launch fails with "unspecified launch failure") instead of hanging the GPU.
+// No printf and no out-of-line helper here on purpose: either is an ABI call, and a call inside a warp-specialised
+// kernel makes the compiler spill every register that is live across the wait site (measured: the gather warps of
+// tower_sp_kernel spilled 16 of their 64 row registers around each wait) -- and a spill is an L2 round trip in kernels
+// that leave the SM no L1 (227 KB of shared memory).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 22)) {   // each failed try sleeps up to the hint, so this is seconds, not microseconds
-      printf("recsys_b200: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
-      __trap();
-    }
+    if (++spins > (1u << 22)) __trap();   // each failed try sleeps up to the hint, so this is seconds, not microseconds
   }
 }
 
@@ -192,10 +193,7 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_test_wait(bar, parity)) {
-    if (++spins > (1u << 28)) {
-      printf("recsys_b200: mbarrier spin wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
-      __trap();
-    }
+    if (++spins > (1u << 28)) __trap();
   }
 }
 

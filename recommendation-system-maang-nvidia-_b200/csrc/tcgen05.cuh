@@ -144,6 +144,23 @@ __device__ __forceinline__ void tmem_st_32x32_x16(uint32_t taddr, const uint32_t
       : "memory");
 }
 
+// registers -> TMEM: 8 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_st_32x32_x8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n\t"
+      "tcgen05.wait::st.sync.aligned;"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+      : "memory");
+}
+// the same as tmem_st_32x32_x16 without the wait: callers issue several and then tmem_st_wait() once
+__device__ __forceinline__ void tmem_st_32x32_x16_nowait(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float (&v)[32]) { tmem_ld_32x32(taddr, v); }
 __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float (&v)[64]) { tmem_ld_32x32_x64(taddr, v); }
 __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float (&v)[128]) { tmem_ld_32x32_x128(taddr, v); }
