@@ -313,8 +313,9 @@ int64_t rs_launch_count(void);
 #define RS_PROF_MERGE 1    /* merge_topk_kernel                                   */
 #define RS_PROF_FILTER 2   /* tcgen05 bf16 pre-filter                             */
 #define RS_PROF_RESCORE 3  /* candidate select + exact re-score                   */
-#define RS_PROF_RANK 4     /* fused ranking forward                               */
+#define RS_PROF_RANK 4     /* fused ranking forward: towers (and unfused chains)  */
 #define RS_PROF_SAMPLE 5   /* tcgen05 pre-filter, threshold-sampling pass         */
+#define RS_PROF_DEEP 6     /* fused ranking forward: deep net + cross + heads     */
 #define RS_PROF_SLOTS 8
 int rs_prof_enable(int on);
 int rs_prof_read(int slot, double* total_ms, int64_t* launches);

@@ -144,7 +144,7 @@ EXPORTED = ["rs_version", "rs_last_error", "rs_launch_count", "rs_device_sm_coun
             "rs_peer_create", "rs_peer_connect", "rs_peer_local", "rs_peer_publish", "rs_peer_wait", "rs_peer_ack", "rs_peer_free", "rs_peer_disconnect",
             "rs_a2a_plan_peer", "rs_peer_a2a_ids", "rs_peer_a2a_rows", "rs_peer_a2a_restore"]
 
-PROF_SCAN, PROF_MERGE, PROF_FILTER, PROF_RESCORE, PROF_RANK, PROF_SAMPLE = 0, 1, 2, 3, 4, 5
+PROF_SCAN, PROF_MERGE, PROF_FILTER, PROF_RESCORE, PROF_RANK, PROF_SAMPLE, PROF_DEEP = 0, 1, 2, 3, 4, 5, 6
 
 
 def check(status: int) -> None:

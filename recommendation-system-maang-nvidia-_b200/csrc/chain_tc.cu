@@ -810,7 +810,11 @@ constexpr int SP_EPI0 = 4;
 constexpr int SP_EPI_WARPS = 16;
 constexpr int SP_ISSUER = SP_EPI0 + SP_EPI_WARPS;
 
-template <bool TRACE>
+// TEAMS = false: all 16 epilogue warps serve both slots in a fixed event order (32 accumulator columns per warp and step).
+// TEAMS = true: eight warps per slot (64 columns per warp and step, as two 32-column chunks) and a polling issuer: a
+// team that sits in its output step -- waiting for the store path, 96 KB per tile at ~20 B/clk -- no longer holds up the
+// other slot's chain steps, which is what bounded the shared order (two output steps of ~3.3 k cycles per 15 k round).
+template <bool TEAMS, bool TRACE>
 __global__ void __launch_bounds__(SP_THREADS, 1)
 tower_sp_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ ChainParams p) {
   using C = CfgTower;
@@ -828,7 +832,9 @@ tower_sp_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
   uint8_t* stage = base + TOWER_STAGE_OFF;   // [16 epilogue warps][2][TOWER_STAGE_BYTES]
 
-  const int warp = threadIdx.x >> 5;
+  // broadcast from lane 0: the compiler then knows the warp index is uniform and keeps everything derived from it (role
+  // branches, bias addresses in the constant bank) on the uniform datapath
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int pi = blockIdx.x % p.n_prob;
   const int cta = blockIdx.x / p.n_prob;
@@ -846,8 +852,8 @@ tower_sp_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
     mbar_init(wfull, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&a0_ready[s], 4);
-      mbar_init(&a0_free[s], SP_EPI_WARPS);
-      mbar_init(&a_ready[s], SP_EPI_WARPS);
+      mbar_init(&a0_free[s], TEAMS ? SP_EPI_WARPS / 2 : SP_EPI_WARPS);
+      mbar_init(&a_ready[s], TEAMS ? SP_EPI_WARPS / 2 : SP_EPI_WARPS);
       mbar_init(&acc_ready[s], 1);
     }
     fence_mbar_init();
@@ -879,6 +885,72 @@ tower_sp_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
       uint64_t wdesc0 = umma_desc_k_sw128(smem_u32(wsm));
       constexpr uint32_t idesc128 = umma_idesc_bf16_f32(BM, 128);
       constexpr uint32_t idesc64 = umma_idesc_bf16_f32(BM, 64);
+      auto issue = [&](int slot, int step) {
+        const uint32_t R = tmem_base + slot * 256;
+        asm volatile("" : "+l"(wdesc0));   // keeps the 36 operand descriptors from being hoisted (and spilled) as loop invariants
+        switch (step) {
+          case 0:
+          case 1: {   // L1 half: A0 [R, R+64) x W1 rows [128*step, +128), K = 128 -> acc [R+64, +128)
+            const uint64_t wd = wdesc0 + static_cast<uint64_t>((w_off<C>(0) + step * (128 * 128)) >> 4);
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk)
+              umma_bf16_ts(R + 64, R + kk * 8, wd + static_cast<uint64_t>(((kk >> 2) * (256 * 128) + (kk & 3) * 32) >> 4), idesc128,
+                           kk > 0 ? 1u : 0u);
+            break;
+          }
+          case 2: {   // L2: A1a [R+192, +64) then A1b [R, +64), W2 (N = 128), K = 256 -> acc
+#pragma unroll
+            for (int kk = 0; kk < 16; ++kk)
+              umma_bf16_ts(R + 64, kk < 8 ? R + 192 + kk * 8 : R + (kk - 8) * 8,
+                           wdesc0 + static_cast<uint64_t>((w_off<C>(1) + (kk >> 2) * (128 * 128) + (kk & 3) * 32) >> 4), idesc128,
+                           kk > 0 ? 1u : 0u);
+            break;
+          }
+          case 3: {   // L3: A2 [R+192, +64), W3 (N = 64), K = 128 -> acc3 [R, +64)
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk)
+              umma_bf16_ts(R, R + 192 + kk * 8,
+                           wdesc0 + static_cast<uint64_t>((w_off<C>(2) + (kk >> 2) * (64 * 128) + (kk & 3) * 32) >> 4), idesc64,
+                           kk > 0 ? 1u : 0u);
+            break;
+          }
+          default: {  // L4: A3 [R+64, +32), W4 (N = 128), K = 64 -> acc4 [R+128, +128)
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_bf16_ts(R + 128, R + 64 + kk * 8, wdesc0 + static_cast<uint64_t>((w_off<C>(3) + (kk & 3) * 32) >> 4), idesc128,
+                           kk > 0 ? 1u : 0u);
+            break;
+          }
+        }
+      };
+      if constexpr (TEAMS) {
+        // ready-driven: whichever slot has its next operand in tensor memory gets its next step issued
+        int left[2] = {n_slot0, n_slot1}, stp[2] = {0, 0}, til[2] = {0, 0};
+        uint32_t use[2] = {0, 0};
+        uint32_t idle = 0;
+        while (left[0] > 0 || left[1] > 0) {
+          if (++idle > (1u << 27)) __trap();   // seconds without progress: fail instead of hanging the device
+#pragma unroll
+          for (int slot = 0; slot < 2; ++slot) {
+            if (left[slot] == 0) continue;
+            const int step = stp[slot], t = til[slot];
+            const bool need_a = step != 0 || t > 0;   // step 0 of a later tile: the previous tile's last accumulator has been read
+            if (step == 0 && !mbar_test_wait(&a0_ready[slot], static_cast<uint32_t>(t & 1))) continue;
+            if (need_a && !mbar_test_wait(&a_ready[slot], use[slot] & 1u)) continue;
+            if (need_a) ++use[slot];
+            idle = 0;
+            tc_fence_after_sync();
+            if (TRACE && blockIdx.x == 0 && t < 4) p.trace[80 + (t * 2 + slot) * 5 + step] = clock64();
+            issue(slot, step);
+            umma_commit(&acc_ready[slot]);
+            if (++stp[slot] == 5) {
+              stp[slot] = 0;
+              ++til[slot];
+              --left[slot];
+            }
+          }
+        }
+      } else {
       uint32_t use0 = 0, use1 = 0;
       for (int r = 0; r <= n_slot0; ++r) {
 #pragma unroll 1
@@ -896,45 +968,11 @@ tower_sp_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
             }
             tc_fence_after_sync();
             if (TRACE && blockIdx.x == 0 && t < 4) p.trace[80 + (t * 2 + slot) * 5 + step] = clock64();
-            const uint32_t R = tmem_base + slot * 256;
-            asm volatile("" : "+l"(wdesc0));   // keeps the 36 operand descriptors from being hoisted (and spilled) as loop invariants
-            switch (step) {
-              case 0:
-              case 1: {   // L1 half: A0 [R, R+64) x W1 rows [128*step, +128), K = 128 -> acc [R+64, +128)
-                const uint64_t wd = wdesc0 + static_cast<uint64_t>((w_off<C>(0) + step * (128 * 128)) >> 4);
-#pragma unroll
-                for (int kk = 0; kk < 8; ++kk)
-                  umma_bf16_ts(R + 64, R + kk * 8, wd + static_cast<uint64_t>(((kk >> 2) * (256 * 128) + (kk & 3) * 32) >> 4), idesc128,
-                               kk > 0 ? 1u : 0u);
-                break;
-              }
-              case 2: {   // L2: A1a [R+192, +64) then A1b [R, +64), W2 (N = 128), K = 256 -> acc
-#pragma unroll
-                for (int kk = 0; kk < 16; ++kk)
-                  umma_bf16_ts(R + 64, kk < 8 ? R + 192 + kk * 8 : R + (kk - 8) * 8,
-                               wdesc0 + static_cast<uint64_t>((w_off<C>(1) + (kk >> 2) * (128 * 128) + (kk & 3) * 32) >> 4), idesc128,
-                               kk > 0 ? 1u : 0u);
-                break;
-              }
-              case 3: {   // L3: A2 [R+192, +64), W3 (N = 64), K = 128 -> acc3 [R, +64)
-#pragma unroll
-                for (int kk = 0; kk < 8; ++kk)
-                  umma_bf16_ts(R, R + 192 + kk * 8,
-                               wdesc0 + static_cast<uint64_t>((w_off<C>(2) + (kk >> 2) * (64 * 128) + (kk & 3) * 32) >> 4), idesc64,
-                               kk > 0 ? 1u : 0u);
-                break;
-              }
-              default: {  // L4: A3 [R+64, +32), W4 (N = 128), K = 64 -> acc4 [R+128, +128)
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk)
-                  umma_bf16_ts(R + 128, R + 64 + kk * 8, wdesc0 + static_cast<uint64_t>((w_off<C>(3) + (kk & 3) * 32) >> 4), idesc128,
-                               kk > 0 ? 1u : 0u);
-                break;
-              }
-            }
+            issue(slot, step);
             umma_commit(&acc_ready[slot]);
           }
         }
+      }
       }
     }
   } else if (warp < SP_EPI0) {
@@ -1018,123 +1056,180 @@ tower_sp_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
       __syncwarp();
       return stg0 + (nst & 1u) * TOWER_STAGE_BYTES;
     };
-    uint32_t cnt0 = 0, cnt1 = 0;
-    for (int rr_ = 0; rr_ <= n_slot0; ++rr_) {
+    const float* const bv = p.biasv[pi];   // constant bank
+    // One 32-column accumulator chunk of a chain step: bias, activation, bf16 -> the next layer's A operand.
+    auto chunk32 = [&](uint32_t src, const float* bs, bool relu, uint32_t dst) {
+      float v[32];
+      __syncwarp();
+      tmem_ld_32x32(src, v);
+#pragma unroll
+      for (int e = 0; e < 32; e += 4) {
+        const float4 b4 = *reinterpret_cast<const float4*>(bs + e);
+        v[e] += b4.x; v[e + 1] += b4.y; v[e + 2] += b4.z; v[e + 3] += b4.w;
+      }
+      uint32_t rr[16];
+      if (relu) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) rr[e] = pack_bf16x2_relu(v[2 * e], v[2 * e + 1]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) rr[e] = pack_bf16x2(v[2 * e], v[2 * e + 1]);
+      }
+      tmem_st_32x32_x16(dst, rr);
+    };
+    auto arrive = [&](uint64_t* bar) {
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar);
+    };
+    // One 32-column chunk of the last accumulator: fp32 rows through the warp's two stage buffers (TMA stores, rows past
+    // the batch are clipped by the tensor map) and the lane-interleaved bf16 copy for the deep kernel straight from
+    // registers (coalesced 128-bit stores; a third staged piece would make the warp wait for a buffer every time).
+    // `release` != nullptr: arrive there once the chunk is in registers (the accumulator columns are free again).
+    auto out_chunk = [&](uint32_t R, int tile, int col0, uint64_t* release) {
+      const float* bs = bv + b_off<C>(3) + col0;
+      float v[32];
+      __syncwarp();
+      tmem_ld_32x32(R + 128 + col0, v);
+      if (release) arrive(release);
+#pragma unroll
+      for (int e = 0; e < 32; e += 4) {
+        const float4 b4 = *reinterpret_cast<const float4*>(bs + e);
+        v[e] += b4.x; v[e + 1] += b4.y; v[e + 2] += b4.z; v[e + 3] += b4.w;
+      }
+      if (p.act[3] == RS_ACT_RELU) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], 0.0f);
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (p.debug & 16) break;   // perf experiments only: no fp32 output
+        uint8_t* buf = stage_acquire();
+        if ((lane >> 4) == h) {
+          const int rw = lane & 15;
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj)
+            *reinterpret_cast<float4*>(buf + rw * 128 + ((jj ^ (rw & 7)) << 4)) =
+                make_float4(v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&maps.y[pi], buf, col0, tile * BM + quarter * 32 + h * 16);
+          bulk_commit();
+        }
+        ++nst;
+      }
+      if (pr.y_il16 && !(p.debug & 64)) {
+        uint4* dst = reinterpret_cast<uint4*>(pr.y_il16) + ((static_cast<int64_t>(tile) * 4 + quarter) * 32 + pr.il_chunk0 + (col0 >> 3)) * 32 + lane;
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          dst[e * 32] = make_uint4(pack_bf16x2(v[8 * e], v[8 * e + 1]), pack_bf16x2(v[8 * e + 2], v[8 * e + 3]),
+                                   pack_bf16x2(v[8 * e + 4], v[8 * e + 5]), pack_bf16x2(v[8 * e + 6], v[8 * e + 7]));
+      }
+    };
+    if constexpr (TEAMS) {
+      // ---------------- eight warps per slot: 64 accumulator columns per warp and step ----------------
+      const int slot = ew >> 3;
+      const int hf = (ew >> 2) & 1;
+      const uint32_t R = tmem_base + slot * 256 + lane_sel;
+      const int n_slot = slot == 0 ? n_slot0 : n_slot1;
+      uint32_t cnt = 0;
+      for (int r = 0; r < n_slot; ++r) {
+        const int tile = cta + (2 * r + slot) * ncta;
 #pragma unroll 1
-      for (int k = 0; k < 5; ++k) {
-#pragma unroll 1
-        for (int slot = 0; slot < 2; ++slot) {
-          const int step = slot == 0 ? k : (k >= 2 ? k - 2 : k + 3);   // the issuer's event order (see there)
-          const int r = slot == 0 ? rr_ : (k < 2 ? rr_ - 1 : rr_);
-          if (r < 0 || r >= (slot == 0 ? n_slot0 : n_slot1)) continue;
-          const uint32_t R = tmem_base + slot * 256 + lane_sel;
-          const int tile = cta + (2 * r + slot) * ncta;
-          const bool tr = TRACE && blockIdx.x == 0 && r < 4 && ew == 0 && lane == 0;
-          uint32_t& cnt = slot == 0 ? cnt0 : cnt1;
+        for (int step = 0; step < 5; ++step) {
+          const bool tr = TRACE && blockIdx.x == 0 && r < 4 && (ew & 7) == 0 && lane == 0;
           chain_wait(&acc_ready[slot], cnt & 1u);
           ++cnt;
           tc_fence_after_sync();
           if (tr) p.trace[((r * 2 + slot) * 5 + step) * 2] = clock64();
           if (step <= 2) {
-            // one code path for the three 128-column steps: bias offset, activation and destination are run-time values
-            const int layer = step == 2 ? 1 : 0;
-            const float* bs = p.biasv[pi] + (step == 2 ? b_off<C>(1) : step * 128) + cg * 32;   // constant bank
-            const uint32_t dst = R + (step == 1 ? 0 : 192) + cg * 16;   // A1a, A1b, A2
+            const bool relu = p.act[step == 2 ? 1 : 0] == RS_ACT_RELU;
+            const int b0 = (step == 2 ? b_off<C>(1) : step * 128) + hf * 64;
+            const uint32_t dst = R + (step == 1 ? 0 : 192) + hf * 32;   // A1a, A1b, A2
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) chunk32(R + 64 + hf * 64 + c * 32, bv + b0 + c * 32, relu, dst + c * 16);
+            arrive(&a_ready[slot]);
+          } else if (step == 3) {
+            // acc3 [0,64): 32 columns per warp; once they are in registers columns [0,64) are dead and the gather warps may
+            // write the next A0 (chunk32 arrives too late for that: split by hand)
             float v[32];
             __syncwarp();
-            tmem_ld_32x32(R + 64 + cg * 32, v);
+            tmem_ld_32x32(R + hf * 32, v);
+            arrive(&a0_free[slot]);
+            const float* bs = bv + b_off<C>(2) + hf * 32;
 #pragma unroll
             for (int e = 0; e < 32; e += 4) {
               const float4 b4 = *reinterpret_cast<const float4*>(bs + e);
               v[e] += b4.x; v[e + 1] += b4.y; v[e + 2] += b4.z; v[e + 3] += b4.w;
             }
             uint32_t rr[16];
-            if (p.act[layer] == RS_ACT_RELU) {
+            if (p.act[2] == RS_ACT_RELU) {
 #pragma unroll
               for (int e = 0; e < 16; ++e) rr[e] = pack_bf16x2_relu(v[2 * e], v[2 * e + 1]);
             } else {
 #pragma unroll
               for (int e = 0; e < 16; ++e) rr[e] = pack_bf16x2(v[2 * e], v[2 * e + 1]);
             }
-            tmem_st_32x32_x16(dst, rr);
-            tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&a_ready[slot]);
-          } else if (step == 3) {
-            const float* bs = p.biasv[pi] + b_off<C>(2) + cg * 16;
-            float v[16];
-            __syncwarp();
-            tmem_ld_32x32_x16(R + cg * 16, v);
-            tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&a0_free[slot]);   // columns [0,64) are dead: the gather warps may write the next A0
-#pragma unroll
-            for (int e = 0; e < 16; e += 4) {
-              const float4 b4 = *reinterpret_cast<const float4*>(bs + e);
-              v[e] += b4.x; v[e + 1] += b4.y; v[e + 2] += b4.z; v[e + 3] += b4.w;
-            }
-            uint32_t rr[8];
-            if (p.act[2] == RS_ACT_RELU) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) rr[e] = pack_bf16x2_relu(v[2 * e], v[2 * e + 1]);
-            } else {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) rr[e] = pack_bf16x2(v[2 * e], v[2 * e + 1]);
-            }
-            tmem_st_32x32_x8(R + 64 + cg * 8, rr);   // A3
-            tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&a_ready[slot]);
+            tmem_st_32x32_x16(R + 64 + hf * 16, rr);   // A3
+            arrive(&a_ready[slot]);
           } else {
-            const int col0 = cg * 32;
-            const float* bs = p.biasv[pi] + b_off<C>(3) + col0;
-            float v[32];
-            __syncwarp();
-            tmem_ld_32x32(R + 128 + col0, v);
-            tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&a_ready[slot]);   // the accumulator columns may be overwritten by the next tile's L1
-#pragma unroll
-            for (int e = 0; e < 32; e += 4) {
-              const float4 b4 = *reinterpret_cast<const float4*>(bs + e);
-              v[e] += b4.x; v[e + 1] += b4.y; v[e + 2] += b4.z; v[e + 3] += b4.w;
-            }
-            if (p.act[3] == RS_ACT_RELU) {
-#pragma unroll
-              for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], 0.0f);
-            }
-            // fp32 output: 16 rows x 128 B per buffer in the 128B-swizzle layout, one TMA store each (rows past the end of
-            // the batch are clipped by the tensor map).  Exactly the warp's two stage buffers.
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              if (p.debug & 16) break;   // perf experiments only: no fp32 output
-              uint8_t* buf = stage_acquire();
-              if ((lane >> 4) == h) {
-                const int rw = lane & 15;
-#pragma unroll
-                for (int jj = 0; jj < 8; ++jj)
-                  *reinterpret_cast<float4*>(buf + rw * 128 + ((jj ^ (rw & 7)) << 4)) =
-                      make_float4(v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]);
-              }
-              fence_proxy_async_smem();
-              __syncwarp();
-              if (lane == 0) {
-                tma_store_2d(&maps.y[pi], buf, col0, static_cast<int>(tile * BM + quarter * 32 + h * 16));
-                bulk_commit();
-              }
-              ++nst;
-            }
-            if (pr.y_il16 && !(p.debug & 64)) {
-              // lane-interleaved bf16 copy for the deep kernel: this warp's four 512-byte chunks are 2 KB contiguous;
-              // coalesced 128-bit stores straight from registers
-              uint4* dst = reinterpret_cast<uint4*>(pr.y_il16) + ((static_cast<int64_t>(tile) * 4 + quarter) * 32 + pr.il_chunk0 + (col0 >> 3)) * 32 + lane;
-#pragma unroll
-              for (int e = 0; e < 4; ++e)
-                dst[e * 32] = make_uint4(pack_bf16x2(v[8 * e], v[8 * e + 1]), pack_bf16x2(v[8 * e + 2], v[8 * e + 3]),
-                                         pack_bf16x2(v[8 * e + 4], v[8 * e + 5]), pack_bf16x2(v[8 * e + 6], v[8 * e + 7]));
-            }
+            out_chunk(R, tile, hf * 64, nullptr);
+            out_chunk(R, tile, hf * 64 + 32, &a_ready[slot]);   // the accumulator may be overwritten by the next tile's L1
           }
           if (tr) p.trace[((r * 2 + slot) * 5 + step) * 2 + 1] = clock64();
+        }
+      }
+    } else {
+      // ---------------- all 16 warps, both slots, the issuer's fixed event order ----------------
+      uint32_t cnt0 = 0, cnt1 = 0;
+      for (int rr_ = 0; rr_ <= n_slot0; ++rr_) {
+#pragma unroll 1
+        for (int k = 0; k < 5; ++k) {
+#pragma unroll 1
+          for (int slot = 0; slot < 2; ++slot) {
+            const int step = slot == 0 ? k : (k >= 2 ? k - 2 : k + 3);
+            const int r = slot == 0 ? rr_ : (k < 2 ? rr_ - 1 : rr_);
+            if (r < 0 || r >= (slot == 0 ? n_slot0 : n_slot1)) continue;
+            const uint32_t R = tmem_base + slot * 256 + lane_sel;
+            const int tile = cta + (2 * r + slot) * ncta;
+            const bool tr = TRACE && blockIdx.x == 0 && r < 4 && ew == 0 && lane == 0;
+            uint32_t& cnt = slot == 0 ? cnt0 : cnt1;
+            chain_wait(&acc_ready[slot], cnt & 1u);
+            ++cnt;
+            tc_fence_after_sync();
+            if (tr) p.trace[((r * 2 + slot) * 5 + step) * 2] = clock64();
+            if (step <= 2) {
+              chunk32(R + 64 + cg * 32, bv + (step == 2 ? b_off<C>(1) : step * 128) + cg * 32, p.act[step == 2 ? 1 : 0] == RS_ACT_RELU,
+                      R + (step == 1 ? 0 : 192) + cg * 16);   // A1a, A1b, A2
+              arrive(&a_ready[slot]);
+            } else if (step == 3) {
+              const float* bs = bv + b_off<C>(2) + cg * 16;
+              float v[16];
+              __syncwarp();
+              tmem_ld_32x32_x16(R + cg * 16, v);
+              arrive(&a0_free[slot]);   // columns [0,64) are dead: the gather warps may write the next A0
+#pragma unroll
+              for (int e = 0; e < 16; e += 4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(bs + e);
+                v[e] += b4.x; v[e + 1] += b4.y; v[e + 2] += b4.z; v[e + 3] += b4.w;
+              }
+              uint32_t rr[8];
+              if (p.act[2] == RS_ACT_RELU) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) rr[e] = pack_bf16x2_relu(v[2 * e], v[2 * e + 1]);
+              } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) rr[e] = pack_bf16x2(v[2 * e], v[2 * e + 1]);
+              }
+              tmem_st_32x32_x8(R + 64 + cg * 8, rr);   // A3
+              arrive(&a_ready[slot]);
+            } else {
+              out_chunk(R, tile, cg * 32, &a_ready[slot]);
+            }
+            if (tr) p.trace[((r * 2 + slot) * 5 + step) * 2 + 1] = clock64();
+          }
         }
       }
     }
@@ -1149,10 +1244,13 @@ tower_sp_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
   }
 }
 
-bool use_tower_sp() {
-  static const bool on = [] { const char* e = getenv("RS_TOWER_SP"); return !(e && e[0] == '0'); }();
-  return on;
+// RS_TOWER_SP: 0 = tower_pp_kernel (round 1), 1 (default) = tower_sp_kernel with the shared event order, 2 = with teams
+// (measured equal within noise: the teams overlap the output steps but their chain steps are twice as long)
+int tower_sp_mode() {
+  static const int m = [] { const char* e = getenv("RS_TOWER_SP"); return e && e[0] >= '0' && e[0] <= '2' ? e[0] - '0' : 1; }();
+  return m;
 }
+bool use_tower_sp() { return tower_sp_mode() != 0; }
 
 // the new kernel serves the fused ranker's call shape: fp32 output through a TMA map (+ optional interleaved bf16 copy)
 bool tower_sp_applies(const ChainParams& p) {
@@ -1167,8 +1265,10 @@ void launch_tower_sp(const ChainMaps& maps, const ChainParams& p, cudaStream_t s
   cudaGetDevice(&dev);
   static cudaError_t attr_err[64];
   std::call_once(once[dev & 63], [dev] {
-    attr_err[dev & 63] = cudaFuncSetAttribute(tower_sp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tower_pp_smem(2));
-    cudaFuncSetAttribute(tower_sp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tower_pp_smem(2));
+    attr_err[dev & 63] = cudaFuncSetAttribute(tower_sp_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tower_pp_smem(2));
+    cudaFuncSetAttribute(tower_sp_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tower_pp_smem(2));
+    cudaFuncSetAttribute(tower_sp_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tower_pp_smem(2));
+    cudaFuncSetAttribute(tower_sp_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tower_pp_smem(2));
     if (attr_err[dev & 63] != cudaSuccess) cudaGetLastError();
   });
   RS_CHECK(attr_err[dev & 63] == cudaSuccess, "tower_sp_kernel needs 227 KB of shared memory per block");
@@ -1192,7 +1292,8 @@ void launch_tower_sp(const ChainMaps& maps, const ChainParams& p, cudaStream_t s
   if (tr_env && tr_env[0] == '1') {   // debugging aid: phase stamps of CTA 0, relative to the first one
     RS_CUDA(cudaMalloc(&q.trace, 256 * sizeof(long long)));
     RS_CUDA(cudaMemsetAsync(q.trace, 0, 256 * sizeof(long long), st));
-    tower_sp_kernel<true><<<grid, SP_THREADS, tower_pp_smem(2), st>>>(maps, q);
+    if (tower_sp_mode() == 2) tower_sp_kernel<true, true><<<grid, SP_THREADS, tower_pp_smem(2), st>>>(maps, q);
+    else tower_sp_kernel<false, true><<<grid, SP_THREADS, tower_pp_smem(2), st>>>(maps, q);
     RS_LAUNCH_CHECK();
     long long host[256];
     RS_CUDA(cudaStreamSynchronize(st));
@@ -1213,7 +1314,8 @@ void launch_tower_sp(const ChainMaps& maps, const ChainParams& p, cudaStream_t s
     return;
   }
   rs::ProfScope prof(RS_PROF_RANK, st);
-  tower_sp_kernel<false><<<grid, SP_THREADS, tower_pp_smem(2), st>>>(maps, q);
+  if (tower_sp_mode() == 2) tower_sp_kernel<true, false><<<grid, SP_THREADS, tower_pp_smem(2), st>>>(maps, q);
+  else tower_sp_kernel<false, false><<<grid, SP_THREADS, tower_pp_smem(2), st>>>(maps, q);
   RS_LAUNCH_CHECK();
 }
 
@@ -1801,7 +1903,7 @@ void launch_deep_heads(const ChainMaps& maps, const DeepHeadsParams& p, cudaStre
   });
   const int64_t ntiles = (p.rows + BM - 1) / BM;
   const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(ntiles, rs::sm_count())));
-  rs::ProfScope prof(RS_PROF_RANK, st);
+  rs::ProfScope prof(RS_PROF_DEEP, st);
   deep_heads_kernel<LC><<<grid, NTHREADS, deep_heads_smem<LC>(), st>>>(maps, p);
   RS_LAUNCH_CHECK();
 }
@@ -1859,7 +1961,9 @@ deep_heads2_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant
   uint64_t* acc1_read = bars + 7;    // 16: X has been read again -> the next tile may use it as its Y
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
-  const int warp = threadIdx.x >> 5;
+  // broadcast from lane 0: a provably uniform warp index keeps the role branches and the constant-bank addresses derived
+  // from it (biases, head rows) on the uniform datapath -- the adds then take their bias straight from uniform registers
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int cta = blockIdx.x;
   const int ncta = gridDim.x;
@@ -2072,17 +2176,25 @@ deep_heads2_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant
         const float* bs = p.biasv + 256 + col0;   // constant bank, like the two head rows
         const float* wr = p.hdv + col0;
         const float* wc = p.hdv + 128 + col0;
-        float dr = 0.0f, dq = 0.0f;
+        // packed fp32 arithmetic (FADD2 / FFMA2, two lanes per instruction): this loop is 3 fma-pipe operations per
+        // accumulator element and was the longest phase of a tile (1.8 k cycles, RS_CHAIN_TRACE); each dot is kept as an
+        // (even, odd) pair of partial sums
+        float2 dr2 = make_float2(0.0f, 0.0f), dq2 = make_float2(0.0f, 0.0f);
 #pragma unroll
         for (int e = 0; e < 32; e += 4) {
           const float4 b4 = *reinterpret_cast<const float4*>(bs + e);
           const float4 r4 = *reinterpret_cast<const float4*>(wr + e);
           const float4 c4 = *reinterpret_cast<const float4*>(wc + e);
-          const float y0 = fmaxf(v[e] + b4.x, 0.0f), y1 = fmaxf(v[e + 1] + b4.y, 0.0f);
-          const float y2 = fmaxf(v[e + 2] + b4.z, 0.0f), y3 = fmaxf(v[e + 3] + b4.w, 0.0f);
-          dr = fmaf(y0, r4.x, dr); dr = fmaf(y1, r4.y, dr); dr = fmaf(y2, r4.z, dr); dr = fmaf(y3, r4.w, dr);
-          dq = fmaf(y0, c4.x, dq); dq = fmaf(y1, c4.y, dq); dq = fmaf(y2, c4.z, dq); dq = fmaf(y3, c4.w, dq);
+          float2 y01 = __fadd2_rn(make_float2(v[e], v[e + 1]), make_float2(b4.x, b4.y));
+          float2 y23 = __fadd2_rn(make_float2(v[e + 2], v[e + 3]), make_float2(b4.z, b4.w));
+          y01.x = fmaxf(y01.x, 0.0f); y01.y = fmaxf(y01.y, 0.0f);
+          y23.x = fmaxf(y23.x, 0.0f); y23.y = fmaxf(y23.y, 0.0f);
+          dr2 = __ffma2_rn(y01, make_float2(r4.x, r4.y), dr2);
+          dq2 = __ffma2_rn(y01, make_float2(c4.x, c4.y), dq2);
+          dr2 = __ffma2_rn(y23, make_float2(r4.z, r4.w), dr2);
+          dq2 = __ffma2_rn(y23, make_float2(c4.z, c4.w), dq2);
         }
+        const float dr = dr2.x + dr2.y, dq = dq2.x + dq2.y;
         part[(0 * 4 + slice) * 128 + trow] = dr;
         part[(1 * 4 + slice) * 128 + trow] = dq;
       }
@@ -2118,7 +2230,7 @@ void launch_deep_heads2(const ChainMaps& maps, const DeepHeadsParams& p, cudaStr
   });
   const int64_t ntiles = (p.rows + BM - 1) / BM;
   const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(ntiles, rs::sm_count())));
-  rs::ProfScope prof(RS_PROF_RANK, st);
+  rs::ProfScope prof(RS_PROF_DEEP, st);
   if (p.trace) deep_heads2_kernel<LC, true><<<grid, DH2_THREADS, deep_heads2_smem<LC>(), st>>>(maps, p);
   else deep_heads2_kernel<LC, false><<<grid, DH2_THREADS, deep_heads2_smem<LC>(), st>>>(maps, p);
   RS_LAUNCH_CHECK();

@@ -25,16 +25,17 @@ def child():
         model({"user_id": ur, "movie_id": ir})
     torch.cuda.synchronize()
     k_ms, k_n = rs._lib.prof_read(rs._lib.PROF_RANK)
+    d_ms, d_n = rs._lib.prof_read(rs._lib.PROF_DEEP)
     rs._lib.prof_enable(False)
     sess = model.ranking_session(B)
     sess.user_rows.copy_(ur); sess.item_rows.copy_(ir)
-    print(json.dumps({"kernels_ms": round(k_ms / 20, 4), "graph_ms": round(timeit(sess.run, 50), 4)}))
+    print(json.dumps({"tower_ms": round(k_ms / 20, 4), "deep_ms": round(d_ms / 20, 4), "graph_ms": round(timeit(sess.run, 50), 4)}))
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "child":
         child()
     else:
         for dbg in ("0", "16", "64", "80"):
-            for deep in ("1", "0"):
-                r = subprocess.run([sys.executable, __file__, "child"], env=dict(os.environ, RS_CHAIN_DEBUG=dbg, RS_DEEP_V2=deep), capture_output=True, text=True)
-                print("RS_CHAIN_DEBUG=" + dbg, "RS_DEEP_V2=" + deep, r.stdout.strip().splitlines()[-1] if r.returncode == 0 else r.stderr[-1500:], flush=True)
+            for sp in ("2", "1"):
+                r = subprocess.run([sys.executable, __file__, "child"], env=dict(os.environ, RS_CHAIN_DEBUG=dbg, RS_TOWER_SP=sp), capture_output=True, text=True)
+                print("RS_CHAIN_DEBUG=" + dbg, "RS_TOWER_SP=" + sp, r.stdout.strip().splitlines()[-1] if r.returncode == 0 else r.stderr[-1500:], flush=True)
