@@ -424,8 +424,8 @@ int rs_index_reconstruct(const rs_index_t* h, int64_t i0, DLTensor* out, void* s
 int rs_index_fallbacks(const rs_index_t* h, int64_t* last, int64_t* total) {
   return rs::guard([&] {
     RS_CHECK(h && last && total, "NULL argument");
-    *last = h->last_fallbacks;
-    *total = h->total_fallbacks;
+    *last = h->last_fallbacks.load(std::memory_order_relaxed);
+    *total = h->total_fallbacks.load(std::memory_order_relaxed);
   });
 }
 

@@ -19,8 +19,10 @@ struct rs_index {
   int64_t shadow_rows = 0;       // rows of the shadow that are current
   float max_norm = 0.0f;         // max_i ||x_i||_2 over the shadow rows (host copy)
   CUtensorMap tmap_bf16{};       // over [ntotal, d] bf16, box [256 rows, 64 bf16], 128B swizzle
-  int64_t last_fallbacks = 0;    // queries of the last tensor-mode search that were re-run on the exact scan
-  int64_t total_fallbacks = 0;
+  // queries of the last / all tensor-mode searches that were re-run on the exact scan; atomics: concurrent searches on one
+  // handle from several host threads are allowed (include/recsys_b200.h)
+  std::atomic<int64_t> last_fallbacks{0};
+  std::atomic<int64_t> total_fallbacks{0};
   std::mutex mu;                 // serialises add / shadow build
 };
 

@@ -18,6 +18,7 @@
 // a CUDA graph and replayed.  Every spin has a ~10 s budget and traps with a message instead of hanging the device.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 
@@ -43,6 +44,19 @@ struct rs_peer {
 namespace {
 
 constexpr int kMaxWorld = 16;
+
+// makes the region's device current for the lifetime of the object (launches must target the device that owns it)
+struct PeerDeviceGuard {
+  int prev = -1;
+  explicit PeerDeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~PeerDeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
 
 struct PeerLayout {
   int64_t slot_bytes;
@@ -71,11 +85,16 @@ __device__ __forceinline__ void st_release_sys(uint64_t* p, uint64_t v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// spins until *p >= want; ~10 s budget (ranks may be seconds apart on their first step)
+// Spin budget in iterations of ~100 ns (ld.acquire.sys + nanosleep): default 2^27 (over a minute -- ranks can be seconds
+// apart on a first step, after a GC pause or while one side runs the host-synchronised exact fallback); RS_PEER_TIMEOUT_S
+// overrides it.  A peer that never arrives still ends in a trap with a message rather than a hung device.
+__device__ unsigned long long g_peer_spin_budget = 1ull << 27;
+
+// spins until *p >= want
 __device__ __forceinline__ void spin_until(const uint64_t* p, uint64_t want, const char* what) {
-  for (uint32_t it = 0; ld_acquire_sys(p) < want; ++it) {
+  for (unsigned long long it = 0; ld_acquire_sys(p) < want; ++it) {
     __nanosleep(64);
-    if (it > (1u << 23)) {
+    if (it > g_peer_spin_budget) {
       printf("recsys_b200: peer exchange timed out waiting for %s (have %llu, want %llu)\n", what,
              (unsigned long long)ld_acquire_sys(p), (unsigned long long)want);
       __trap();
@@ -155,6 +174,27 @@ __global__ void peer_wait_kernel(const uint8_t* __restrict__ local, const PeerLa
   const uint64_t seq = *reinterpret_cast<const uint64_t*>(local + L.off_seq);
   if (threadIdx.x < L.world)
     spin_until(reinterpret_cast<const uint64_t*>(local + L.off_flags) + threadIdx.x, seq, "a peer's message");
+}
+
+// One warp that waits for what a machine-filling kernel queued behind it would otherwise spin on at entry.  The lookup's
+// rows / restore kernels launch up to 8 CTAs per SM; with several tables looked up concurrently (side streams, parallel
+// graph branches) such grids could fill every SM of rank A with restore(user) waiting for B's rows(user) while B is full
+// of restore(item) waiting for A's rows(item) -- neither rows kernel would ever get an SM.  With the wait in a single
+// warp ahead of them, the big grids only start once their data has arrived and never spin.
+//   arrived != nullptr: this step's message of every rank is in region `arrived` (peer_arrived's condition)
+//   begin   != nullptr: every peer has acknowledged the previous step of region `begin` (peer_begin's condition)
+__global__ void peer_prewait_kernel(const uint8_t* __restrict__ arrived, const PeerLayout LA, const uint8_t* __restrict__ begin,
+                                    const PeerLayout LB) {
+  if (arrived) {
+    const uint64_t seq = *reinterpret_cast<const uint64_t*>(arrived + LA.off_seq);
+    if (threadIdx.x < LA.world)
+      spin_until(reinterpret_cast<const uint64_t*>(arrived + LA.off_flags) + threadIdx.x, seq, "a peer's message");
+  }
+  if (begin) {
+    const uint64_t seq = *reinterpret_cast<const uint64_t*>(begin + LB.off_seq);
+    if (threadIdx.x < LB.world)
+      spin_until(reinterpret_cast<const uint64_t*>(begin + LB.off_acks) + threadIdx.x, seq, "a peer's ack");
+  }
 }
 
 __global__ void peer_ack_kernel(uint8_t* const* __restrict__ bases, const PeerLayout L) {
@@ -357,6 +397,13 @@ int rs_peer_connect(rs_peer_t* h, const void* handles) {
     }
     RS_CUDA(cudaMalloc(&h->d_bases, sizeof(uint8_t*) * kMaxWorld));
     RS_CUDA(cudaMemcpy(h->d_bases, h->bases, sizeof(uint8_t*) * kMaxWorld, cudaMemcpyHostToDevice));
+    if (const char* e = getenv("RS_PEER_TIMEOUT_S")) {   // seconds a kernel may wait for a peer before it traps
+      const double sec = atof(e);
+      if (sec > 0) {
+        const unsigned long long iters = static_cast<unsigned long long>(sec * 1.0e7);   // ~100 ns per iteration
+        RS_CUDA(cudaMemcpyToSymbol(g_peer_spin_budget, &iters, sizeof(iters)));
+      }
+    }
     h->connected = true;
   });
 }
@@ -378,6 +425,7 @@ int rs_peer_publish(rs_peer_t* h, const DLTensor* src, void* stream) {
     const int64_t bytes = src->shape[0];
     RS_CHECK(bytes >= 0 && bytes <= h->slot_bytes, "message longer than the slot");
     require_aligned16(data_ptr<uint8_t>(src), "src");
+    PeerDeviceGuard g(h->device);
     const int blocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((bytes / 16 + 255) / 256, sm_count())));
     peer_publish_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(h->d_bases, layout_of(h), data_ptr<uint8_t>(src), bytes);
     RS_LAUNCH_CHECK();
@@ -387,6 +435,7 @@ int rs_peer_publish(rs_peer_t* h, const DLTensor* src, void* stream) {
 int rs_peer_wait(rs_peer_t* h, void* stream) {
   return rs::guard([&] {
     RS_CHECK(h != nullptr && h->connected, "peer region is not connected");
+    PeerDeviceGuard g(h->device);
     peer_wait_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(h->local, layout_of(h));
     RS_LAUNCH_CHECK();
   });
@@ -395,6 +444,7 @@ int rs_peer_wait(rs_peer_t* h, void* stream) {
 int rs_peer_ack(rs_peer_t* h, void* stream) {
   return rs::guard([&] {
     RS_CHECK(h != nullptr && h->connected, "peer region is not connected");
+    PeerDeviceGuard g(h->device);
     peer_ack_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(h->d_bases, layout_of(h));
     RS_LAUNCH_CHECK();
   });
@@ -481,6 +531,10 @@ int rs_peer_a2a_rows(rs_peer_t* ids_region, rs_peer_t* rows_region, const DLTens
     require_aligned16(data_ptr<float>(table), "table");
     const int64_t b_max = (ids_region->slot_bytes - kIdsHeader) / 8;
     RS_CHECK(b_max * table->shape[1] * 4 <= rows_region->slot_bytes, "rows region slots are too small for b_max rows");
+    PeerDeviceGuard g(rows_region->device);
+    peer_prewait_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(ids_region->local, layout_of(ids_region), rows_region->local,
+                                                                          layout_of(rows_region));
+    RS_LAUNCH_CHECK();
     a2a_rows_kernel<<<sm_count(), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         ids_region->d_bases, layout_of(ids_region), rows_region->d_bases, layout_of(rows_region), data_ptr<float>(table),
         table->shape[0], ld, static_cast<int>(table->shape[1]));
@@ -519,6 +573,10 @@ int rs_peer_a2a_restore(rs_peer_t* rows_region, const DLTensor* ids, const DLTen
     }
     const int64_t total = std::max<int64_t>(1, B * (dim / 4));
     const int blocks = static_cast<int>(std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 8));
+    PeerDeviceGuard g(rows_region->device);
+    peer_prewait_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(rows_region->local, layout_of(rows_region), nullptr,
+                                                                          layout_of(rows_region));
+    RS_LAUNCH_CHECK();
     a2a_restore_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(rows_region->d_bases, layout_of(rows_region),
                                                                              data_ptr<int64_t>(ids), B, rows_region->world, b_max, so,
                                                                              vp, ip, data_ptr<float>(out), ld_out, static_cast<int>(dim));

@@ -795,8 +795,9 @@ void search_tensor_device(rs_index* h, const float* q, int64_t nq, int k, int64_
         if (flags[i])
           search_exact_device(h, qc + (int64_t)i * DK, 1, k, id_base, D + (q0 + i) * ldD, ldD, I + (q0 + i) * ldI, ldI, st);
     }
-    h->last_fallbacks = (q0 == 0 ? 0 : h->last_fallbacks) + flags[nq_pad];
-    h->total_fallbacks += flags[nq_pad];
+    if (q0 == 0) h->last_fallbacks.store(flags[nq_pad], std::memory_order_relaxed);
+    else h->last_fallbacks.fetch_add(flags[nq_pad], std::memory_order_relaxed);
+    h->total_fallbacks.fetch_add(flags[nq_pad], std::memory_order_relaxed);
   }
 }
 

@@ -68,7 +68,9 @@ class RecommendationService:
                    model_dir: str = "<memory>") -> "RecommendationService":
         s = cls(model_dir)
         s.encoder_model, s.faiss_index = encoder, index
-        s.user_vocab, s.item_map = list(user_vocab), dict(item_map)
+        # a plain dict is copied; any other mapping (a lazy row -> item-id view of a 10M-item catalog, say) is used as is:
+        # recommend() only ever does item_map[str(row)] and len(item_map)
+        s.user_vocab, s.item_map = list(user_vocab), (dict(item_map) if isinstance(item_map, dict) else item_map)
         s._user_set = frozenset(s.user_vocab)
         return s
 
@@ -104,15 +106,26 @@ class RecommendationService:
     def is_ready(self) -> bool:
         return all([self.encoder_model, self.faiss_index, self.user_vocab, self.item_map])
 
+    def _device_ctx(self):
+        """Makes the encoder's GPU current for the calling thread: a threaded HTTP server (or the micro-batcher's worker
+        thread, serving.py) calls in from threads whose current device is still 0."""
+        import contextlib
+        import torch
+        dev = getattr(self.encoder_model, "device", None)
+        if dev is None or not torch.cuda.is_available():
+            return contextlib.nullcontext()
+        return torch.cuda.device(dev)
+
     def recommend(self, user_id: str, k: int = 10) -> List[Dict]:
         if user_id not in self._user_set:          # dict/set membership instead of the reference's O(V) list scan
             logger.warning(f"User '{user_id}' not in vocabulary. Applying cold-start strategy.")
             return self._get_popular_items(k)
-        q = self.encoder_model({"user_id": [user_id]}, training=False)["user_embedding"]   # [1, E] on device
-        normalize_L2(q)
-        distances, indices = self.faiss_index.search(q, k)
-        distances = distances.cpu().numpy()        # the only device -> host traffic: k scores + k rows
-        indices = indices.cpu().numpy()
+        with self._device_ctx():
+            q = self.encoder_model({"user_id": [user_id]}, training=False)["user_embedding"]   # [1, E] on device
+            normalize_L2(q)
+            distances, indices = self.faiss_index.search(q, k)
+            distances = distances.cpu().numpy()        # the only device -> host traffic: k scores + k rows
+            indices = indices.cpu().numpy()
         recommendations = []
         for i, idx in enumerate(indices[0]):
             if idx != -1:
@@ -131,10 +144,11 @@ class RecommendationService:
         error: Optional[str] = None
         if known:
             try:
-                q = self.encoder_model({"user_id": known}, training=False)["user_embedding"]
-                normalize_L2(q)
-                D, I = self.faiss_index.search(q, k)
-                D, I = D.cpu().numpy(), I.cpu().numpy()
+                with self._device_ctx():
+                    q = self.encoder_model({"user_id": known}, training=False)["user_embedding"]
+                    normalize_L2(q)
+                    D, I = self.faiss_index.search(q, k)
+                    D, I = D.cpu().numpy(), I.cpu().numpy()
                 for r, u in enumerate(known):
                     recs[u] = [{"item_id": self.item_map[str(idx)], "score": float(D[r][i]), "rank": i + 1}
                                for i, idx in enumerate(I[r]) if idx != -1]
@@ -156,9 +170,10 @@ class RecommendationService:
     def score(self, user_id: str, item_ids: List[str]) -> Dict[str, float]:
         if user_id not in self._user_set:
             raise ValueError(f"User '{user_id}' not found in vocabulary.")
-        emb = self.encoder_model({"user_id": [user_id], "movie_id": list(item_ids)}, training=False)
-        scores = ops.matvec(emb["item_embedding"], emb["user_embedding"][0].contiguous())   # raw, un-normalised
-        return {item_id: float(s) for item_id, s in zip(item_ids, scores.cpu().numpy())}
+        with self._device_ctx():
+            emb = self.encoder_model({"user_id": [user_id], "movie_id": list(item_ids)}, training=False)
+            scores = ops.matvec(emb["item_embedding"], emb["user_embedding"][0].contiguous())   # raw, un-normalised
+            return {item_id: float(s) for item_id, s in zip(item_ids, scores.cpu().numpy())}
 
     def _get_popular_items(self, k: int) -> List[Dict]:
         return [{"item_id": self.item_map[str(i)], "score": 1.0 - (i * 0.05), "rank": i + 1}

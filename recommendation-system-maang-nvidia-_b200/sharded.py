@@ -144,6 +144,9 @@ class ShardedIndexFlatIP:
         self.bounds = shard_bounds(int(n_total), self.world)
         self.row_begin, self.row_end = self.bounds[self.rank], self.bounds[self.rank + 1]
         self.n_total = int(n_total)
+        if self.n_total > 0xFFFFFFFF:
+            # the merge packs (score, global row) into one 64-bit key with a 32-bit row field (csrc/flat_index.cu)
+            raise ValueError("sharded catalogs above 2^32 rows are not supported (global row numbers are merged as 32-bit keys)")
         self.fallbacks = 0          # queries re-searched exactly after the exchange (results identical either way)
         if local_search is None:
             from .index import IndexFlatIP

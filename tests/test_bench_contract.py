@@ -66,3 +66,43 @@ def test_clock_sampler_counts_only_samples_taken_under_load(tmp_path, monkeypatc
     s2 = bench.ClockSampler(0)
     s2.start()
     assert s2.stop()["sm_mhz"] is None
+
+
+def _load_bench():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod2", ROOT / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    return bench
+
+
+def test_cpu_baselines_of_the_other_configs_run_and_describe_themselves():
+    """The CPU legs bench.py attaches to `ranking` and `batch1_latency`: bounded samples, explicit
+    thread count (all host cores whatever OMP_NUM_THREADS says), kind = "port"."""
+    import argparse
+    import numpy as np
+    import recsys_b200 as rs
+    bench = _load_bench()
+    r = bench.cpu_ranking(rs, 4096, reps=1)
+    assert r["kind"] == "port" and r["unit"] == "samples/s" and r["value"] > 0 and r["cores"] == (os.cpu_count() or 1)
+    args = argparse.Namespace(dim=128, n_items=10_000_000)
+    xb = rs.synth.make_unit_rows(20000, 128, 3000)
+    b1 = bench.cpu_batch1(args, xb, n_queries=2)
+    assert b1["kind"] == "port" and b1["ms_p50"] > 0 and "scaled" in b1["sample"]
+
+
+def test_cpu_legs_use_every_host_core_even_under_torchrun(monkeypatch):
+    """torch.distributed.run exports OMP_NUM_THREADS=1; the CPU arm must not silently become single-threaded."""
+    import torch
+    bench = _load_bench()
+    before = torch.get_num_threads()
+    torch.set_num_threads(1)
+    try:
+        with bench.all_host_cores():
+            assert torch.get_num_threads() == (os.cpu_count() or 1)
+            from threadpoolctl import threadpool_info
+            blas = [p_ for p_ in threadpool_info() if p_.get("user_api") == "blas"]
+            assert all(p_["num_threads"] == (os.cpu_count() or 1) for p_ in blas)
+        assert torch.get_num_threads() == 1
+    finally:
+        torch.set_num_threads(before)

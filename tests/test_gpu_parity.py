@@ -498,3 +498,45 @@ def test_catalog_build_and_recall_eval(rs, tmp_path):
     raw_index, raw_map = rs.build_item_index(enc, iv, normalize=False)
     preds = rs.ranked_item_ids(raw_index, raw_map, q, 10)
     assert ev.recall_at_k(preds, truth, 10) == 1.0 and ev.mrr(preds, truth) >= 0.9
+
+
+def test_concurrent_searches_on_one_index_from_two_host_threads(rs, oracle_mod):
+    """include/recsys_b200.h promises that an index handle is immutable between add() calls and that several host threads
+    may search it at once (faiss's contract: the C++ call releases the GIL, app/main.py runs one search per worker but a
+    threaded server would not).  Two threads, each with its own CUDA stream, hammer one handle with different query sets
+    on both the tensor path and the exact path; every result must equal the oracle's, and the fallback counters
+    (atomics) must stay consistent."""
+    import threading
+    from oracle import flat_ip
+    xb = rs.synth.make_unit_rows(70000, 128, 11)
+    index = rs.IndexFlatIP(128)
+    index.add(xb)
+    index.search(rs.synth.make_unit_rows(4, 128, 12), 10)        # builds the bf16 shadow once, before the threads start
+    results, errors = {}, []
+
+    def worker(tid):
+        try:
+            torch.cuda.set_device(0)
+            stream = torch.cuda.Stream()
+            with torch.cuda.stream(stream):
+                for it in range(6):
+                    q = rs.synth.make_unit_rows(33 + 7 * tid, 128, 100 * tid + it)
+                    mode = "exact" if (it + tid) % 3 == 0 else "auto"
+                    D, I = index.search(torch.from_numpy(q).cuda(), 20, mode=mode)
+                    stream.synchronize()
+                    results[(tid, it)] = (q, D.cpu().numpy(), I.cpu().numpy())
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    assert len(results) == 12
+    for (tid, it), (q, D, I) in results.items():
+        Dw, Iw = flat_ip.search_chain(xb, q, 20)
+        assert np.array_equal(I, Iw) and np.array_equal(D, Dw), (tid, it)
+    last, total = index.fallbacks()
+    assert 0 <= last <= total

@@ -14,6 +14,11 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
+# Stated tolerance of the bf16 tensor mode against the fp64 oracle: 5e-3 of each output tensor's largest magnitude
+# (measured 3.4e-3 - 3.8e-3 at these shapes: bf16 operands, fp32 accumulation, six layers deep).
+BF16_TOL = 5e-3
+
+
 
 def to_bf16(x):
     u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32).astype(np.uint64)
@@ -79,7 +84,7 @@ def test_multitask_forward_bf16_mode(rs):
         got = out[k_].cpu().numpy().astype(np.float64)
         rel = np.abs(got - want[k_]).max() / np.abs(want[k_]).max()
         print(f"bf16 mode {k_}: max err / scale = {rel:.2e}")
-        assert rel <= 1e-2, k_
+        assert rel <= BF16_TOL, k_
     # small batches (the /recommend path) stay on the exact fp32 kernels even in bf16 mode
     m32 = rs.MultiTaskModel(cfg, uv, iv, {})
     rs.load_weights(m32, w)
@@ -119,7 +124,7 @@ def test_fused_deep_cross_heads_kernel(rs, cross_layers, monkeypatch):
             scale = np.abs(want[k_]).max()
             got = fused[k_].cpu().numpy().astype(np.float64)
             assert got.shape == want[k_].shape
-            assert np.abs(got - want[k_]).max() <= 1e-2 * scale, (k_, B)
+            assert np.abs(got - want[k_]).max() <= BF16_TOL * scale, (k_, B)
             assert (fused[k_] - unfused[k_]).abs().max().item() <= 5e-3 * scale, (k_, B)
         assert torch.equal(fused["user_embedding"], unfused["user_embedding"])
         assert torch.equal(fused["item_embedding"], unfused["item_embedding"])
@@ -144,3 +149,105 @@ def test_ranking_session_replays_the_eager_forward(rs, B):
             assert torch.equal(got[k_], want[k_]), k_
     with pytest.raises(ValueError):
         sess({"user_id": dev(ur[:5]), "movie_id": dev(ir[:5])})
+
+
+def test_bf16_ranking_at_the_baseline_batch(rs):
+    """BASELINE configs[1] at its real size: batch 65,536, every output against the fp64 oracle at the stated 5e-3 of the
+    tensor's scale, plus the distribution of the per-element relative error (so that "max-norm relative" cannot hide a
+    wrong region of the batch): at least 99 % of the elements whose magnitude is above a tenth of the scale agree to
+    2e-2 relative, and no 128-row tile is worse than the whole batch's bound."""
+    from oracle.models import MultiTaskModel as OMT
+    cfg = rs.ModelConfig()
+    w = rs.synth.make_weights(cfg, 6040, 3706, seed=10)
+    uv, iv = rs.synth.make_vocab(6040), rs.synth.make_vocab(3706)
+    m = rs.MultiTaskModel(cfg, uv, iv, {}, precision="bf16")
+    rs.load_weights(m, w)
+    B = 65536
+    rng = np.random.default_rng(200)
+    ur, ir = rs.synth.make_ids(rng, 6040, B), rs.synth.make_ids(rng, 3706, B)
+    out = m({"user_id": dev(ur.astype(np.int32)), "movie_id": dev(ir.astype(np.int32))})
+    want = OMT(w, uv, iv, np.float64).rank_rows(ur, ir)
+    for k_ in want:
+        got = out[k_].cpu().numpy().astype(np.float64)
+        assert got.shape == want[k_].shape
+        scale = np.abs(want[k_]).max()
+        err = np.abs(got - want[k_])
+        assert err.max() <= BF16_TOL * scale, (k_, err.max() / scale)
+        big = np.abs(want[k_]) >= 0.1 * scale
+        rel = err[big] / np.abs(want[k_][big])
+        hist = np.percentile(rel, [50, 90, 99, 100])
+        print(f"B=65536 {k_}: max err / scale {err.max() / scale:.2e}; relative error p50/p90/p99/max {hist}")
+        assert hist[2] <= 2e-2, (k_, hist)
+        per_tile = err.reshape(B // 128, -1).max(axis=1)
+        assert per_tile.max() <= BF16_TOL * scale        # every tile of every CTA, including the last round's
+
+
+def test_tower_kernel_variants_agree(rs, monkeypatch):
+    """The three tower kernels (round-1 tower_pp_kernel, tower_sp_kernel with the shared event order / with teams) compute
+    the same arithmetic: identical embeddings bit for bit.  The knob is read once per process, so each variant runs in a
+    child process."""
+    import json
+    import subprocess
+    import sys
+    code = (
+        "import sys, json, numpy as np, torch; sys.path.insert(0, %r); import recsys_b200 as rs\n"
+        "cfg = rs.ModelConfig(); w = rs.synth.make_weights(cfg, 500, 300, seed=3)\n"
+        "m = rs.MultiTaskModel(cfg, rs.synth.make_vocab(500), rs.synth.make_vocab(300), {}, precision='bf16'); rs.load_weights(m, w)\n"
+        "rng = np.random.default_rng(9); res = {}\n"
+        "for B in (1, 129, 5000, 128 * 148 * 2 + 77):\n"
+        "    ur, ir = rs.synth.make_ids(rng, 500, B), rs.synth.make_ids(rng, 300, B)\n"
+        "    o = m({'user_id': torch.from_numpy(ur).cuda(), 'movie_id': torch.from_numpy(ir).cuda()})\n"
+        "    res[B] = [float(o[k].double().sum()) for k in ('user_embedding', 'item_embedding')] + [float(o[k].double().abs().sum()) for k in ('user_embedding', 'item_embedding')]\n"
+        "print(json.dumps(res))\n") % str(__import__("pathlib").Path(__file__).resolve().parent.parent)
+    outs = {}
+    for mode in ("0", "1", "2"):
+        env = dict(__import__("os").environ, RS_TOWER_SP=mode)
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-3000:]
+        outs[mode] = json.loads(r.stdout.strip().splitlines()[-1])
+    assert outs["0"] == outs["1"] == outs["2"]
+
+
+def test_set_weights_invalidates_the_fused_handle_and_the_session(rs):
+    """Keras-style weight updates after a bf16 forward: the fused ranker handle copies weights (and a CUDA-graph session
+    captures launches over them), so every way of changing a weight must rebuild them -- layer.set_weights, a direct
+    attribute assignment, set_cross_weights, Embedding.set_weights, and two updates with no forward in between (the case
+    a data_ptr-keyed cache gets wrong when the allocator hands the old address out again)."""
+    from oracle.models import MultiTaskModel as OMT
+    cfg = rs.ModelConfig()
+    uv, iv = rs.synth.make_vocab(300), rs.synth.make_vocab(200)
+    w = rs.synth.make_weights(cfg, 300, 200, seed=41)
+    m = rs.MultiTaskModel(cfg, uv, iv, {}, precision="bf16")
+    rs.load_weights(m, w)
+    rng = np.random.default_rng(3)
+    B = 512
+    ur, ir = rs.synth.make_ids(rng, 300, B), rs.synth.make_ids(rng, 200, B)
+    feats = {"user_id": dev(ur), "movie_id": dev(ir)}
+    sess = m.ranking_session(B, ids_dtype=torch.int64)
+
+    def check(weights, what):
+        want = OMT(weights, uv, iv, np.float64).rank_rows(ur, ir)
+        for name, out in (("eager", m(feats)), ("session", sess(feats))):
+            for k_ in want:
+                got = out[k_].cpu().numpy().astype(np.float64)
+                assert np.abs(got - want[k_]).max() <= BF16_TOL * np.abs(want[k_]).max(), (what, name, k_)
+
+    check(w, "initial")
+    w2 = rs.synth.make_weights(cfg, 300, 200, seed=42)
+    m.encoder.user_tower.layers[0].set_weights(list(w2["user_tower"][0]))             # Dense.set_weights
+    w["user_tower"][0] = w2["user_tower"][0]
+    check(w, "Dense.set_weights")
+    m.encoder.item_embedding.set_weights([w2["item_embedding"]])                      # Embedding.set_weights
+    w["item_embedding"] = w2["item_embedding"]
+    check(w, "Embedding.set_weights")
+    m.dcn.set_cross_weights(w2["cross_w"], w2["cross_b"])                             # cross stack
+    w["cross_w"], w["cross_b"] = w2["cross_w"], w2["cross_b"]
+    check(w, "set_cross_weights")
+    m.rating_head.kernel = dev(w2["rating_head"][0])                                  # plain attribute assignment
+    w["rating_head"] = (w2["rating_head"][0], w["rating_head"][1])
+    check(w, "kernel assignment")
+    w3 = rs.synth.make_weights(cfg, 300, 200, seed=43)                                # two updates, no forward in between
+    m.dcn.deep_nets[0].set_weights(list(w2["deep"][0]))
+    m.dcn.deep_nets[0].set_weights(list(w3["deep"][0]))
+    w["deep"][0] = w3["deep"][0]
+    check(w, "two set_weights in a row")
