@@ -301,6 +301,48 @@ int rs_peer_a2a_rows(rs_peer_t* ids_region, rs_peer_t* rows_region, const DLTens
 int rs_peer_a2a_restore(rs_peer_t* rows_region, const DLTensor* ids, const DLTensor* slot_of, const DLTensor* vals,
                         const DLTensor* inv, DLTensor* out, void* stream);
 
+/*
+ * K7s. The multi-GPU paths behind one call each, for hosts in any language (new in this build).
+ * One process per GPU.  A communicator is this rank's view of the group plus ONE host-side all-gather callback the caller
+ * supplies (torch.distributed, MPI, a socket ...): recv[g * bytes .. (g+1) * bytes) = rank g's `bytes` bytes of send, host
+ * memory, 0 on success.  The library calls it during set-up and teardown only -- it carries the CUDA IPC handles of the
+ * peer-memory regions and serves as the barrier around mapping / unmapping them; every per-step byte moves through this
+ * library's kernels over NVLink peer memory (no NCCL, no host synchronisation inside a step).  All ranks must issue the
+ * same sequence of rs_comm_* / rs_index_search_sharded / rs_sharded_table_* / rs_embedding_a2a_lookup calls; creation and
+ * destruction calls are collective.  world <= 16.
+ *
+ * rs_index_search_sharded: index.search(q, k) (app/recommendation_service.py:72) over a catalog of n_total rows
+ *   partitioned by contiguous ranges -- rank g's `shard` holds rows [n_total*g/world, n_total*(g+1)/world).  q f32 [nq, d]
+ *   replicated on every rank; D f32 [nq, k] / I int64 [nq, k] (global row numbers) come out identical on every rank and
+ *   bit-identical to one index over the whole catalog.  Device tensors.  The first call for a new (nq, k) builds the
+ *   peer regions (collective, not capturable); later calls are pure stream work and can be captured in a CUDA graph.
+ *   need_exact != NULL (int32 [nq]): nothing is synchronised; rows of flagged queries are not final -- call again for
+ *   those queries with mode RS_EXACT_FP32 (every rank sees the same flags).  need_exact == NULL: the library does that
+ *   itself (one stream synchronise).  mode: RS_AUTO / RS_TENSOR_BF16 (shared-threshold tensor path where it applies) or
+ *   RS_EXACT_FP32 (fp32 scan of every shard); same results.
+ *
+ * rs_sharded_table_*: an embedding table sharded `row mod world` (global row r = local row r div world of rank r mod world;
+ *   replaces keras.layers.Embedding of src/models.py:71,74 for tables that do not fit one GPU, BASELINE config 4).
+ *   local_rows f32 [n_local, dim] is BORROWED and must outlive the handle.  rs_embedding_a2a_lookup: ids int64 [B <=
+ *   max_batch] global rows of this rank's part of the batch -> out f32 [B, dim] in batch order; both all-to-alls are stores
+ *   into peer memory with device-known counts; dedup != 0 requests each distinct id once per batch.  Stream-ordered,
+ *   capturable in a CUDA graph.
+ */
+typedef int (*rs_allgather_fn)(void* ctx, const void* send, void* recv, int64_t bytes);
+typedef struct rs_comm rs_comm_t;
+typedef struct rs_sharded_table rs_sharded_table_t;
+int rs_comm_init(int rank, int world, rs_allgather_fn allgather, void* ctx, rs_comm_t** out);
+int rs_comm_rank(const rs_comm_t* c, int* rank, int* world);
+int rs_comm_free(rs_comm_t* c);
+int rs_index_search_sharded(rs_index_t* shard, rs_comm_t* c, int64_t n_total, const DLTensor* q, int k, int mode, DLTensor* D,
+                            DLTensor* I, DLTensor* need_exact, void* stream);
+int rs_sharded_table_create(rs_comm_t* c, const DLTensor* local_rows, int64_t max_batch, int dedup, rs_sharded_table_t** out);
+int rs_sharded_table_free(rs_sharded_table_t* t);
+int rs_embedding_a2a_lookup(rs_sharded_table_t* t, const DLTensor* ids, DLTensor* out, void* stream);
+/* rows this rank requested from each owner in the last lookup queued on `stream` (synchronises it): counts_out int64
+ * [world], host.  With de-duplication their sum is the number of distinct ids of the batch. */
+int rs_sharded_table_last_counts(rs_sharded_table_t* t, int64_t* counts_out, void* stream);
+
 /* counters for the bench's gpu_launches claim: kernels launched by this library so far */
 int64_t rs_launch_count(void);
 

@@ -44,6 +44,9 @@ _capsule_get.argtypes = [ctypes.py_object, ctypes.c_char_p]
 # (we pass stream=-1 there anyway: the library is stream-ordered behind the caller's current stream)
 _torch_to_dlpack = getattr(torch._C, "_to_dlpack", None)
 
+# rs_allgather_fn of include/recsys_b200.h: (ctx, send, recv, bytes per rank) -> 0 on success; host memory
+ALLGATHER_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64)
+
 _lib = None
 
 
@@ -124,6 +127,14 @@ def load():
         "rs_peer_a2a_ids": [vp, _DLP, _DLP, vp],
         "rs_peer_a2a_rows": [vp, vp, _DLP, vp],
         "rs_peer_a2a_restore": [vp, _DLP, _DLP, _DLP, _DLP, _DLP, vp],
+        "rs_comm_init": [i32, i32, ALLGATHER_FN, vp, ctypes.POINTER(vp)],
+        "rs_comm_rank": [vp, ctypes.POINTER(i32), ctypes.POINTER(i32)],
+        "rs_comm_free": [vp],
+        "rs_index_search_sharded": [vp, vp, i64, _DLP, i32, i32, _DLP, _DLP, _DLP, vp],
+        "rs_sharded_table_create": [vp, _DLP, i64, i32, ctypes.POINTER(vp)],
+        "rs_sharded_table_free": [vp],
+        "rs_embedding_a2a_lookup": [vp, _DLP, _DLP, vp],
+        "rs_sharded_table_last_counts": [vp, ctypes.POINTER(i64), vp],
         "rs_prof_enable": [i32],
         "rs_prof_read": [i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64)],
     }
@@ -142,7 +153,9 @@ EXPORTED = ["rs_version", "rs_last_error", "rs_launch_count", "rs_device_sm_coun
             "rs_index_fallbacks", "rs_debug_tensor_scores",
             "rs_matvec", "rs_topk_merge", "rs_prof_enable", "rs_prof_read",
             "rs_peer_create", "rs_peer_connect", "rs_peer_local", "rs_peer_publish", "rs_peer_wait", "rs_peer_ack", "rs_peer_free", "rs_peer_disconnect",
-            "rs_a2a_plan_peer", "rs_peer_a2a_ids", "rs_peer_a2a_rows", "rs_peer_a2a_restore"]
+            "rs_a2a_plan_peer", "rs_peer_a2a_ids", "rs_peer_a2a_rows", "rs_peer_a2a_restore",
+            "rs_comm_init", "rs_comm_rank", "rs_comm_free", "rs_index_search_sharded", "rs_sharded_table_create", "rs_sharded_table_free",
+            "rs_embedding_a2a_lookup", "rs_sharded_table_last_counts"]
 
 PROF_SCAN, PROF_MERGE, PROF_FILTER, PROF_RESCORE, PROF_RANK, PROF_SAMPLE, PROF_DEEP = 0, 1, 2, 3, 4, 5, 6
 

@@ -20,6 +20,7 @@
 #include <cfloat>
 
 #include "flat_index.cuh"
+#include "peer.cuh"
 #include "topk.cuh"
 
 namespace {
@@ -195,14 +196,29 @@ struct KeySource {
   }
 };
 
+// What the sharded search (sharded.cu) folds into the merge: the wait for / acknowledgement of the peer-memory region the
+// parts live in, and the per-query verdict that rs_topk_verify computes (OR of the shards' flags; with bounds also the
+// shared-threshold verification).  All pointers null: a plain merge.
+struct MergeExtras {
+  uint8_t* const* peer_bases = nullptr;
+  rsp::PeerLayout PL{};
+  const float* bounds = nullptr;
+  int64_t ld_b = 0;
+  const int* flags = nullptr;
+  int64_t ld_f = 0;
+  int* need_exact = nullptr;
+};
+
 template <int CAP>
 __global__ void __launch_bounds__(MERGE_NT)
 merge_topk_kernel(const KeySource src, int P, int k, int64_t id_base, float* __restrict__ D, int64_t ldD,
-                  int64_t* __restrict__ I, int64_t ldI) {
+                  int64_t* __restrict__ I, int64_t ldI, const MergeExtras ex) {
   __shared__ uint64_t keys[CAP];
   __shared__ int cnt;
   const int tid = threadIdx.x;
   const int64_t qi = blockIdx.x;
+  uint64_t seq = 0;
+  if (ex.peer_bases) seq = rsp::peer_arrived(ex.peer_bases[ex.PL.rank], ex.PL);
   for (int i = tid; i < CAP; i += MERGE_NT) keys[i] = kEmptyKey;
   if (tid == 0) cnt = 0;
   __syncthreads();
@@ -232,6 +248,18 @@ merge_topk_kernel(const KeySource src, int P, int k, int64_t id_base, float* __r
       I[qi * ldI + j] = id_base + static_cast<int64_t>(key_row(key));
     }
   }
+  if (ex.need_exact && tid == 0) {   // verify_topk_kernel's verdict for this query
+    float b = -INFINITY;
+    int f = 0;
+    for (int g = 0; g < P; ++g) {
+      if (ex.bounds) b = fmaxf(b, ex.bounds[g * ex.ld_b + qi]);
+      f |= ex.flags[g * ex.ld_f + qi];
+    }
+    const uint64_t kth = keys[k - 1];
+    const bool ok = f == 0 && (!ex.bounds || (kth != kEmptyKey && key_score(kth) >= b));
+    ex.need_exact[qi] = ok ? 0 : 1;
+  }
+  if (ex.peer_bases) rsp::peer_consumed(ex.peer_bases, ex.PL, seq);
 }
 
 __global__ void fill_pad_kernel(float* D, int64_t ldD, int64_t* I, int64_t ldI, int64_t nq, int k) {
@@ -271,20 +299,20 @@ __global__ void __launch_bounds__(128) matvec_kernel(const float* __restrict__ i
 
 template <int CAP>
 void launch_merge(const KeySource& src, int64_t nq, int P, int k, int64_t id_base, float* D, int64_t ldD, int64_t* I,
-                  int64_t ldI, cudaStream_t st) {
+                  int64_t ldI, cudaStream_t st, const MergeExtras& ex) {
   rs::ProfScope prof(RS_PROF_MERGE, st);
-  merge_topk_kernel<CAP><<<static_cast<unsigned>(nq), MERGE_NT, 0, st>>>(src, P, k, id_base, D, ldD, I, ldI);
+  merge_topk_kernel<CAP><<<static_cast<unsigned>(nq), MERGE_NT, 0, st>>>(src, P, k, id_base, D, ldD, I, ldI, ex);
   RS_LAUNCH_CHECK();
 }
 
 void merge_dispatch(const KeySource& src, int64_t nq, int P, int k, int64_t id_base, float* D, int64_t ldD, int64_t* I,
-                    int64_t ldI, cudaStream_t st) {
+                    int64_t ldI, cudaStream_t st, const MergeExtras& ex = MergeExtras{}) {
   RS_CHECK(k >= 1 && k <= 1024, "k must be in [1, 1024]");
   RS_CHECK(nq <= 0x7FFFFFFF, "too many queries");
-  if (k <= 128) launch_merge<256>(src, nq, P, k, id_base, D, ldD, I, ldI, st);
-  else if (k <= 256) launch_merge<512>(src, nq, P, k, id_base, D, ldD, I, ldI, st);
-  else if (k <= 512) launch_merge<1024>(src, nq, P, k, id_base, D, ldD, I, ldI, st);
-  else launch_merge<2048>(src, nq, P, k, id_base, D, ldD, I, ldI, st);
+  if (k <= 128) launch_merge<256>(src, nq, P, k, id_base, D, ldD, I, ldI, st, ex);
+  else if (k <= 256) launch_merge<512>(src, nq, P, k, id_base, D, ldD, I, ldI, st, ex);
+  else if (k <= 512) launch_merge<1024>(src, nq, P, k, id_base, D, ldD, I, ldI, st, ex);
+  else launch_merge<2048>(src, nq, P, k, id_base, D, ldD, I, ldI, st, ex);
 }
 
 template <int D, int QT, int CAP>
@@ -321,6 +349,26 @@ void rebuild_tmaps(rs_index* h) {
 }  // namespace
 
 namespace rs {
+
+void merge_lists_device(const float* Dparts, int64_t part_ld_D, const int64_t* Iparts, int64_t part_ld_I, int P, int64_t nq,
+                        int k, float* D, int64_t ldD, int64_t* I, int64_t ldI, rs_peer* lists_region, const float* bounds,
+                        int64_t ld_b, const int* flags, int64_t ld_f, int* need_exact, cudaStream_t st) {
+  RS_CHECK(P >= 1 && P <= 4096, "nparts must be in [1, 4096]");
+  RS_CHECK(need_exact == nullptr || flags != nullptr, "need_exact needs the shards' flags");
+  if (nq == 0) return;
+  MergeExtras ex;
+  if (lists_region) {
+    ex.peer_bases = lists_region->d_bases;
+    ex.PL = rsp::layout_of(lists_region);
+  }
+  ex.bounds = bounds;
+  ex.ld_b = ld_b;
+  ex.flags = flags;
+  ex.ld_f = ld_f;
+  ex.need_exact = need_exact;
+  KeySource src{nullptr, Dparts, Iparts, nq, part_ld_D, part_ld_I};
+  merge_dispatch(src, nq, P, k, 0, D, ldD, I, ldI, st, ex);
+}
 
 void search_exact_device(rs_index* h, const float* q, int64_t nq, int k, int64_t id_base, float* D, int64_t ldD,
                          int64_t* I, int64_t ldI, cudaStream_t st) {

@@ -6,6 +6,8 @@
 
 #include "common.cuh"
 
+struct rs_peer;
+
 struct rs_index {
   int d = 0;
   int device = 0;
@@ -50,8 +52,20 @@ int64_t tensor_sample_rows(int64_t ntotal);
 int tensor_threshold_rank(int k, double rho);
 int64_t tensor_max_queries();
 rs_tc_session* shared_begin(rs_index* h, const float* q, int64_t nq, int k, int R, float* top, int64_t ld_top, cudaStream_t st);
+// tops_region != nullptr: `tops` is that peer-memory region's local data; the threshold kernel waits for every rank's
+// message and acknowledges the step itself (no rs_peer_wait / rs_peer_ack around the call)
 void shared_finish(rs_tc_session* s, const float* tops, int n_parts, int64_t part_ld, int R, int rank, int64_t id_base,
-                   float* D, int64_t ldD, int64_t* I, int64_t ldI, int* need_exact, float* bound);
+                   float* D, int64_t ldD, int64_t* I, int64_t ldI, int* need_exact, float* bound,
+                   rs_peer* tops_region = nullptr);
+
+// G-way merge of per-shard (score, global row) lists -- parts strided by part_ld_* elements, each a packed [nq, k] block --
+// optionally fused with the steps around it in the sharded search (sharded.cu):
+//   lists_region  the parts live in that peer-memory region: wait for every rank's message at entry, acknowledge at the end
+//   need_exact    per query: OR of the shards' flags [G rows, stride ld_f]; with bounds [G rows, stride ld_b] also the
+//                 shared-threshold verification (rs_topk_verify): merged list full and its k-th score >= every bound
+void merge_lists_device(const float* Dparts, int64_t part_ld_D, const int64_t* Iparts, int64_t part_ld_I, int P, int64_t nq,
+                        int k, float* D, int64_t ldD, int64_t* I, int64_t ldI, rs_peer* lists_region, const float* bounds,
+                        int64_t ld_b, const int* flags, int64_t ld_f, int* need_exact, cudaStream_t st);
 void tc_session_free(rs_tc_session* s);
 
 // need_exact == nullptr: flagged queries are re-run on the exact scan before returning (one stream synchronise).

@@ -37,6 +37,7 @@
 #include <vector>
 
 #include "flat_index.cuh"
+#include "peer.cuh"
 #include "tcgen05.cuh"
 
 namespace {
@@ -532,17 +533,24 @@ __global__ void __launch_bounds__(256) sample_top_kernel(const unsigned* __restr
 }
 
 // tau_q = the `rank`-th largest of the union of the shards' top-R lists: tops[g * part_ld + q * R + i]
-__global__ void __launch_bounds__(256) threshold_shared_kernel(const float* __restrict__ tops, int n_parts, int64_t part_ld,
+// peer_bases != nullptr: `tops` is the local peer-memory region of a tops exchange (csrc/peer.cu); the kernel itself waits
+// for every rank's message at entry and acknowledges the step to the peers once all CTAs have read their part (what
+// separate rs_peer_wait / rs_peer_ack launches would do).  The region is written by other GPUs: plain loads only.
+__global__ void __launch_bounds__(256) threshold_shared_kernel(const float* tops, int n_parts, int64_t part_ld,
                                                                int R, int rank, float* __restrict__ thr,
-                                                               int* __restrict__ cand_cnt, int* __restrict__ flags) {
+                                                               int* __restrict__ cand_cnt, int* __restrict__ flags,
+                                                               uint8_t* const* __restrict__ peer_bases, const rsp::PeerLayout PL) {
   __shared__ unsigned vals[1024];
   __shared__ unsigned hist[256];
   __shared__ unsigned state[2];
   const int tid = threadIdx.x;
   const int qi = blockIdx.x;
   const int n = n_parts * R;
+  uint64_t seq = 0;
+  if (peer_bases) seq = rsp::peer_arrived(peer_bases[PL.rank], PL);
   for (int i = tid; i < n; i += 256) vals[i] = f32_to_ordered(tops[(i / R) * part_ld + (int64_t)qi * R + (i % R)]);
   __syncthreads();
+  if (peer_bases) rsp::peer_consumed(peer_bases, PL, seq);
   const uint32_t kth = block_kth_largest<256>([&](int i) { return vals[i]; }, n, rank, hist, state, tid);
   if (tid == 0) {
     thr[qi] = ordered_to_f32(kth);
@@ -813,14 +821,16 @@ rs_tc_session* shared_begin(rs_index* h, const float* q, int64_t nq, int k, int 
 }
 
 void shared_finish(rs_tc_session* sp, const float* tops, int n_parts, int64_t part_ld, int R, int rank, int64_t id_base,
-                   float* D, int64_t ldD, int64_t* I, int64_t ldI, int* need_exact, float* bound) {
+                   float* D, int64_t ldD, int64_t* I, int64_t ldI, int* need_exact, float* bound, rs_peer* tops_region) {
   std::unique_ptr<rs_tc_session> own(sp);
   rs_tc_session& s = *sp;
   RS_CHECK(n_parts >= 1 && R >= 1 && n_parts * R <= 1024, "shards x R must be <= 1024");
   RS_CHECK(rank >= 1 && rank <= n_parts * R, "rank must be in [1, shards x R]");
   {
     ProfScope prof(RS_PROF_RESCORE, s.st);
-    threshold_shared_kernel<<<s.nq, 256, 0, s.st>>>(tops, n_parts, part_ld, R, rank, s.ws.thr, s.ws.cnt, s.ws.flags);
+    threshold_shared_kernel<<<s.nq, 256, 0, s.st>>>(tops, n_parts, part_ld, R, rank, s.ws.thr, s.ws.cnt, s.ws.flags,
+                                                    tops_region ? tops_region->d_bases : nullptr,
+                                                    tops_region ? rsp::layout_of(tops_region) : rsp::PeerLayout{});
     RS_LAUNCH_CHECK();
   }
   tc_finish(s, id_base, D, ldD, I, ldI, bound);

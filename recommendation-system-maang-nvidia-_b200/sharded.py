@@ -132,6 +132,70 @@ class PeerExchange:
         self._h = None
 
 
+class Comm:
+    """rs_comm_t (include/recsys_b200.h) over a torch.distributed process group: this rank's view of the group plus the
+    host all-gather callback the library uses to set up and tear down its peer-memory regions (CUDA IPC handles,
+    barriers).  Per-step traffic never goes through it.  One communicator per (group, device), shared by the sharded
+    index and the sharded tables; construction, close() and everything created on it are collective."""
+
+    _live = {}
+
+    @classmethod
+    def get(cls, device: torch.device, group: Optional[dist.ProcessGroup] = None) -> "Comm":
+        key = (id(group) if group is not None else 0, torch.device(device).index)
+        c = cls._live.get(key)
+        if c is None or c._h is None:
+            c = cls._live[key] = cls(device, group)
+        c._refs += 1
+        return c
+
+    def release(self) -> None:
+        """Drop one user; the last one frees the communicator (collective: every rank releases in the same order)."""
+        self._refs -= 1
+        if self._refs <= 0:
+            self.close()
+
+    def __init__(self, device: torch.device, group: Optional[dist.ProcessGroup] = None):
+        import ctypes
+        from . import _lib
+        self._lib_mod, self._lib = _lib, _lib.load()
+        multi = dist.is_initialized()
+        self.world, self.rank = (dist.get_world_size(group), dist.get_rank(group)) if multi else (1, 0)
+        self.group, self.device = group, torch.device(device)
+        on_dev = multi and dist.get_backend(group) == "nccl"
+        world = self.world
+
+        def allgather(ctx, send, recv, n):
+            # called by the library with host pointers; every rank calls it at the same point of the same C function
+            try:
+                n = int(n)
+                mine = torch.frombuffer(bytearray(ctypes.string_at(send, n)), dtype=torch.uint8)
+                if on_dev:
+                    mine = mine.to(self.device)
+                everyone = torch.empty((world * n,), dtype=torch.uint8, device=mine.device)
+                dist.all_gather_into_tensor(everyone, mine, group=group)
+                host = everyone.cpu().contiguous()
+                ctypes.memmove(recv, host.data_ptr(), world * n)
+                return 0
+            except Exception:           # must not propagate through the C frames: the library reports the failure
+                import traceback
+                traceback.print_exc()
+                return 1
+
+        self._refs = 0
+        self._cb = _lib.ALLGATHER_FN(allgather)          # kept alive as long as the communicator
+        self._h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.rs_comm_init(self.rank, self.world, self._cb, None, ctypes.byref(self._h)))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is None:
+            return
+        h, self._h = self._h, None
+        with torch.cuda.device(self.device):
+            self._lib_mod.check(self._lib.rs_comm_free(h))
+
+
 class ShardedIndexFlatIP:
     def __init__(self, d: int, n_total: int, group: Optional[dist.ProcessGroup] = None,
                  local_index=None, local_search: Optional[Callable] = None, merge: Optional[Callable] = None,
@@ -176,6 +240,8 @@ class ShardedIndexFlatIP:
         self.exchange = "nccl"           # "p2p": both exchanges of a step through NVLink peer memory (PeerExchange)
         self._peers = {}
         self._peer_factory = None        # tests: nbytes -> object with publish / gathered / done / close
+        self.native = local_search is None   # exchange == "p2p": one rs_index_search_sharded call per step (csrc/sharded.cu)
+        self._comm = None
         self._graphs = {}
         self._last_need = None
 
@@ -241,10 +307,33 @@ class ShardedIndexFlatIP:
             need = self._last_need
             idx = need.nonzero().flatten()
             sub = np.ascontiguousarray(q[idx.cpu().numpy()]) if isinstance(q, np.ndarray) else q[idx].contiguous()
-            De, Ie = self._gather_merge(*self._local_exact(sub, k))
+            if self._use_native(sub):
+                De, Ie, _ = self._native_step(sub, int(k), mode="exact")    # the flags are the same on every rank
+            else:
+                De, Ie = self._gather_merge(*self._local_exact(sub, k))
             D[idx], I[idx] = De, Ie
             self.fallbacks += int(idx.numel())
         return D, I
+
+    def _use_native(self, q) -> bool:
+        return (self.native and self.exchange == "p2p" and self.shared_threshold and self._peer_factory is None
+                and isinstance(q, torch.Tensor) and q.is_cuda)
+
+    def _native_step(self, q: torch.Tensor, k: int, mode: str = "auto"):
+        """One whole step as ONE C call (rs_index_search_sharded): sample, both peer-memory exchanges, filter, re-score,
+        merge and verification are sequenced by the library on the current stream -> (D, I, need bool [nq])."""
+        import ctypes
+        from . import _lib
+        if self._comm is None:
+            self._comm = Comm.get(q.device, self.group)
+        nq = int(q.shape[0])
+        D = torch.empty((nq, k), dtype=torch.float32, device=q.device)
+        I = torch.empty((nq, k), dtype=torch.int64, device=q.device)
+        need = torch.empty((nq,), dtype=torch.int32, device=q.device)
+        bq, bD, bI, bN = _lib.dl(q.contiguous()), _lib.dl(D), _lib.dl(I), _lib.dl(need)
+        _lib.check(_lib.load().rs_index_search_sharded(self.local._h, self._comm._h, self.n_total, bq.ptr, k, _lib.mode_code(mode),
+                                                       bD.ptr, bI.ptr, bN.ptr, _lib.stream_ptr()))
+        return D, I, need.ne(0)
 
     def close(self) -> None:
         """Drop the captured graphs (they hold NCCL work of the process group: release them before destroying it)."""
@@ -257,6 +346,10 @@ class ShardedIndexFlatIP:
                 if pe is not None:
                     pe.close()
         self._peers.clear()
+        if self._comm is not None:
+            torch.cuda.synchronize()
+            self._comm.release()
+            self._comm = None
 
     def _peer_pair(self, nq: int, k: int, rank_pad: int, dev):
         """(tops exchange or None, lists exchange) for this (nq, k): created collectively on first use.  If any rank
@@ -287,6 +380,18 @@ class ShardedIndexFlatIP:
 
     def _step(self, q, k: int):
         """Queues one whole search step (no host synchronisation) -> (D, I, need bool [nq])."""
+        if self._use_native(q):
+            try:
+                D, I, need = self._native_step(q, k)
+                self._last_need = need
+                return D, I, need
+            except RuntimeError as e:
+                # regions are set up collectively inside the call: a failure anywhere is raised on every rank
+                if "could not be set up on every rank" not in str(e):
+                    raise
+                import warnings
+                warnings.warn(f"peer-memory exchange unavailable ({e}); using NCCL all-gathers")
+                self.exchange = "nccl"
         nq = int(q.shape[0])
         G = self.world
         off_I, off_F, total = exchange_layout(nq, k)
@@ -430,7 +535,7 @@ class ShardedEmbedding:
         _lib.check(_lib.load().rs_hash_table_fill(b.ptr, rank, world, seed, _lib.stream_ptr()))
         return out
 
-    def enable_peer_exchange(self, max_batch: int, dedup: bool = True) -> None:
+    def enable_peer_exchange(self, max_batch: int, dedup: bool = True, native: bool = True) -> None:
         """Switch lookup() to the peer-memory path (csrc/peer.cu): both all-to-alls become stores into NVLink peer
         memory with device-known counts, the owner-side gather writes straight into the requester's region, hot ids
         are requested once per batch (dedup) -- no NCCL, no host synchronisation, capturable in a CUDA graph.
@@ -438,6 +543,17 @@ class ShardedEmbedding:
         from . import _lib
         dev = self.local_table.device
         G, bm = self.world, int(max_batch)
+        if native:
+            # the whole lookup behind one C call (rs_embedding_a2a_lookup): regions and plan buffers live in the library
+            import ctypes
+            self._lib_mod, self._lib = _lib, _lib.load()
+            self._comm = Comm.get(dev, self.group)
+            h = ctypes.c_void_p()
+            bt = _lib.dl(self.local_table)
+            with torch.cuda.device(dev):
+                _lib.check(self._lib.rs_sharded_table_create(self._comm._h, bt.ptr, bm, 1 if dedup else 0, ctypes.byref(h)))
+            self._p2p = {"b_max": bm, "dedup": bool(dedup), "native": h}
+            return
         self._p2p = {
             "b_max": bm, "dedup": bool(dedup),
             "ids": PeerExchange(16 + 8 * bm, dev, self.group), "rows": PeerExchange(bm * self.dim * 4, dev, self.group),
@@ -453,12 +569,30 @@ class ShardedEmbedding:
 
     def close(self) -> None:
         p = getattr(self, "_p2p", None)
-        if p:
+        if p and "native" in p:
+            torch.cuda.synchronize()
+            with torch.cuda.device(self.local_table.device):
+                self._lib_mod.check(self._lib.rs_sharded_table_free(p["native"]))
+            self._p2p = None
+            self._comm.release()
+            self._comm = None
+        elif p:
             torch.cuda.synchronize()
             p["rows_view"] = None
             p["ids"].close()
             p["rows"].close()
             self._p2p = None
+
+    def last_request_counts(self) -> List[int]:
+        """Rows this rank requested from each owner in its last peer-memory lookup (with de-duplication their sum is the
+        number of distinct ids of the batch); synchronises the current stream."""
+        import ctypes
+        p = self._p2p
+        if "native" in p:
+            out = (ctypes.c_int64 * self.world)()
+            self._lib_mod.check(self._lib.rs_sharded_table_last_counts(p["native"], out, self._lib_mod.stream_ptr()))
+            return list(out)
+        return p["counts"].cpu().tolist()
 
     def _lookup_p2p(self, ids: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         p, L, lib = self._p2p, self._lib_mod, self._lib
@@ -468,6 +602,10 @@ class ShardedEmbedding:
         st = L.stream_ptr()
         if out is None:
             out = torch.empty((B, self.dim), dtype=torch.float32, device=ids.device)
+        if "native" in p:
+            b_ids, b_out = L.dl(ids), L.dl(out)
+            L.check(lib.rs_embedding_a2a_lookup(p["native"], b_ids.ptr, b_out.ptr, st))
+            return out
         b_ids, b_counts, b_stage, b_out = L.dl(ids), L.dl(p["counts"]), L.dl(p["stage"]), L.dl(out)
         h_ids, h_rows = p["ids"]._h, p["rows"]._h
         if p["dedup"]:

@@ -41,8 +41,9 @@ def test_peer_exchange_single_rank_steps(rs):
     _lib.check(lib.rs_peer_free(h))
 
 
+@pytest.mark.parametrize("native", [True, False])
 @pytest.mark.parametrize("dedup", [True, False])
-def test_peer_memory_lookup_single_rank(rs, dedup):
+def test_peer_memory_lookup_single_rank(rs, dedup, native):
     """ShardedEmbedding.lookup through the peer-memory path with one rank (owner == requester): plan kernels (hash
     de-duplication or plain bucketing), ids message, owner-side gather into the rows region, restore -- against a
     plain row gather, bit for bit; duplicates, a negative id (clamped to 0), out-of-range ids (zeros), ragged batches
@@ -52,7 +53,7 @@ def test_peer_memory_lookup_single_rank(rs, dedup):
     n_rows, dim, bmax = 5000, 128, 4096
     table = torch.from_numpy(rs.synth.hash_table_rows(np.arange(n_rows), dim, seed=9)).cuda()
     emb = ShardedEmbedding(n_rows, dim, local_table=table)
-    emb.enable_peer_exchange(bmax, dedup=dedup)
+    emb.enable_peer_exchange(bmax, dedup=dedup, native=native)   # one C call per lookup / the Python-sequenced kernels
     rng = np.random.default_rng(3)
     for B in (1, 77, 4096, 1000):
         ids = rs.synth.zipf_ids(rng, n_rows, B).astype(np.int64)
@@ -65,7 +66,7 @@ def test_peer_memory_lookup_single_rank(rs, dedup):
         want[ids >= n_rows] = 0
         np.testing.assert_array_equal(got, want)
     if dedup:      # the owner was asked once per distinct id
-        assert int(emb._p2p["counts"].sum()) == len(np.unique(np.clip(ids, 0, None)))
+        assert sum(emb.last_request_counts()) == len(np.unique(np.clip(ids, 0, None)))
     with pytest.raises(ValueError):
         emb.lookup(torch.zeros(bmax + 1, dtype=torch.int64, device="cuda"))
     emb.close()
@@ -97,3 +98,71 @@ def test_lookup_many_runs_tables_concurrently_and_matches(rs):
         np.testing.assert_array_equal(s_.cpu().numpy(), w)
     for emb, _ in pairs:
         emb.close()
+
+
+def test_sharded_search_entry_point_single_rank(rs):
+    """rs_index_search_sharded / rs_comm_* (csrc/sharded.cu) with a group of one: the whole protocol -- tops exchange,
+    threshold kernel that waits and acknowledges by itself, lists exchange, merge fused with the verification -- runs
+    through the peer-memory regions of a single rank and must equal the plain index search bit for bit; also exact mode,
+    the library-side repair of (artificially) flagged queries, a shape outside the tensor path and CUDA-graph capture."""
+    import os
+    from recsys_b200.sharded import Comm
+    _lib = rs._lib
+    lib = _lib.load()
+    dev = torch.device("cuda", 0)
+    N, nq, k = 70_001, 33, 20
+    xb = torch.from_numpy(rs.synth.make_unit_rows(N, 128, 5)).cuda()
+    q = torch.from_numpy(rs.synth.make_unit_rows(nq, 128, 6)).cuda()
+    index = rs.IndexFlatIP(128)
+    index.add(xb)
+    Dw, Iw = index.search(q, k, mode="exact")
+    comm = Comm.get(dev)
+
+    def native(qq, kk, mode, need, idx=index, n_total=N):
+        Dn = torch.empty((qq.shape[0], kk), dtype=torch.float32, device=dev)
+        In = torch.empty((qq.shape[0], kk), dtype=torch.int64, device=dev)
+        bq, bD, bI, bN = _lib.dl(qq), _lib.dl(Dn), _lib.dl(In), _lib.dl(need)
+        _lib.check(lib.rs_index_search_sharded(idx._h, comm._h, n_total, bq.ptr, kk, _lib.mode_code(mode), bD.ptr, bI.ptr,
+                                               bN.ptr if need is not None else None, _lib.stream_ptr()))
+        return Dn, In
+
+    need = torch.full((nq,), 5, dtype=torch.int32, device=dev)
+    for mode in ("auto", "tensor", "exact"):
+        for _ in range(2):                                   # several steps through the same regions
+            Dn, In = native(q, k, mode, need)
+            assert torch.equal(In, Iw) and torch.equal(Dn, Dw), mode
+            assert int(need.abs().sum()) == 0
+    Dn, In = native(q, k, "auto", None)
+    assert torch.equal(In, Iw) and torch.equal(Dn, Dw)
+    os.environ["RS_DEBUG_FLAG_QUERIES"] = "0,7,32"
+    try:
+        Dn, In = native(q, k, "auto", None)
+    finally:
+        del os.environ["RS_DEBUG_FLAG_QUERIES"]
+    assert torch.equal(In, Iw) and torch.equal(Dn, Dw)
+    assert index.fallbacks()[0] == 3
+    # fewer queries through the plan of the larger batch, and a new k (new regions)
+    Dn, In = native(q[:4].contiguous(), k, "auto", None)
+    assert torch.equal(In, Iw[:4]) and torch.equal(Dn, Dw[:4])
+    Dn, In = native(q, 7, "auto", None)
+    assert torch.equal(In, Iw[:, :7]) and torch.equal(Dn, Dw[:, :7])
+    # captured in a CUDA graph after the regions exist
+    g = torch.cuda.CUDAGraph()
+    static_q = q.clone()
+    with torch.cuda.graph(g):
+        Dg, Ig = native(static_q, k, "auto", need)
+    static_q.copy_(torch.roll(q, 3, dims=0))
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(Ig, torch.roll(Iw, 3, dims=0)) and torch.equal(Dg, torch.roll(Dw, 3, dims=0))
+    del g
+    # a catalog below the tensor path's minimum: every "shard" runs the exact scan behind the same exchange
+    small = rs.IndexFlatIP(128)
+    small.add(xb[:3000].contiguous())
+    Ds, Is = small.search(q, k, mode="exact")
+    Dn, In = native(q, k, "auto", need, idx=small, n_total=3000)
+    assert torch.equal(In, Is) and torch.equal(Dn, Ds)
+    with pytest.raises(RuntimeError):                        # the shard must hold exactly this rank's range
+        native(q, k, "auto", need, idx=small, n_total=3001)
+    torch.cuda.synchronize()
+    comm.release()
