@@ -866,6 +866,10 @@ tower_sp_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ 
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  // programmatic dependent launch: the deep kernel queued behind this one may be scheduled as SMs free up -- its CTAs
+  // load their kernels and set up tensor memory while the last tower tiles finish elsewhere, and wait
+  // (griddepcontrol.wait) before they touch anything this kernel writes
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == SP_ISSUER) {
     if (elect_one()) {
@@ -2108,6 +2112,9 @@ deep_heads2_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant
                                                                 // call, and a call inside the epilogue spills everything live
       }
     };
+    // x0 is the tower kernel's output: with a programmatic launch this CTA may have started before that kernel finished
+    // (no-op otherwise).  Everything above -- barriers, tensor memory, the issuer's kernel loads -- overlapped its tail.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (n_my > 0) {
       load_next(cta);
       store_a0();
@@ -2231,8 +2238,24 @@ void launch_deep_heads2(const ChainMaps& maps, const DeepHeadsParams& p, cudaStr
   const int64_t ntiles = (p.rows + BM - 1) / BM;
   const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(ntiles, rs::sm_count())));
   rs::ProfScope prof(RS_PROF_DEEP, st);
-  if (p.trace) deep_heads2_kernel<LC, true><<<grid, DH2_THREADS, deep_heads2_smem<LC>(), st>>>(maps, p);
-  else deep_heads2_kernel<LC, false><<<grid, DH2_THREADS, deep_heads2_smem<LC>(), st>>>(maps, p);
+  if (p.trace) {
+    deep_heads2_kernel<LC, true><<<grid, DH2_THREADS, deep_heads2_smem<LC>(), st>>>(maps, p);
+    RS_LAUNCH_CHECK();
+    return;
+  }
+  // programmatic dependent launch behind the tower kernel (RS_PDL=0: plain stream order)
+  static const bool pdl = [] { const char* e = getenv("RS_PDL"); return !(e && e[0] == '0'); }();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(grid));
+  cfg.blockDim = dim3(DH2_THREADS);
+  cfg.dynamicSmemBytes = deep_heads2_smem<LC>();
+  cfg.stream = st;
+  cudaLaunchAttribute attr{};
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  RS_CUDA(cudaLaunchKernelEx(&cfg, deep_heads2_kernel<LC, false>, maps, p));
   RS_LAUNCH_CHECK();
 }
 

@@ -234,7 +234,10 @@ def test_set_weights_invalidates_the_fused_handle_and_the_session(rs):
         for name, out in (("eager", m(feats)), ("session", sess(feats))):
             for k_ in want:
                 got = out[k_].cpu().numpy().astype(np.float64)
-                assert np.abs(got - want[k_]).max() <= BF16_TOL * np.abs(want[k_]).max(), (what, name, k_)
+                # 2 x BF16_TOL: this test is about STALE weights (errors of the order of the tensor scale), and the small
+                # 300 x 200 model's rating head is a near-cancelling sum (scale 0.045): measured 5.7e-3 of it after the
+                # cross-weight update, against <= 3.8e-3 on the BASELINE-shaped models of the tolerance tests above
+                assert np.abs(got - want[k_]).max() <= 2 * BF16_TOL * np.abs(want[k_]).max(), (what, name, k_)
 
     check(w, "initial")
     w2 = rs.synth.make_weights(cfg, 300, 200, seed=42)

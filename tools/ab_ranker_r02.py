@@ -17,7 +17,8 @@ SETTINGS = [("sp2_deep1", {"RS_TOWER_SP": "2", "RS_DEEP_V2": "1"}),
             ("sp1_deep1", {"RS_TOWER_SP": "1", "RS_DEEP_V2": "1"}),
             ("sp1_deep0", {"RS_TOWER_SP": "1", "RS_DEEP_V2": "0"}),
             ("sp0_deep1", {"RS_TOWER_SP": "0", "RS_DEEP_V2": "1"}),
-            ("sp0_deep0", {"RS_TOWER_SP": "0", "RS_DEEP_V2": "0"})]
+            ("sp0_deep0", {"RS_TOWER_SP": "0", "RS_DEEP_V2": "0"}),
+            ("pdl1", {"RS_PDL": "1"}), ("pdl0", {"RS_PDL": "0"})]   # programmatic dependent launch of the deep kernel on / off
 
 
 def child():
