@@ -106,6 +106,20 @@ int rs_dense_forward(const DLTensor* x, const DLTensor* kernel, const DLTensor* 
 int rs_dense_forward_bf16(const DLTensor* x, const DLTensor* wt, const DLTensor* bias, int act,
                           DLTensor* y_bf16, DLTensor* y_f32, void* stream);
 /*
+ * K2 (fp32 tensor mode). The same Dense layer at fp32 accuracy on the tensor cores: every fp32 operand is split into two
+ * fp16 numbers (v = hi + lo * 2^-11) and x.w is taken as hi.hi + 2^-11 (hi.lo + lo.hi) with fp32 accumulation (three
+ * tcgen05.mma per K step; csrc/dense_x3.cu).  Tolerance vs the fp64 oracle: 1e-5 of tensor scale, the same as the FFMA
+ * kernel behind rs_dense_forward (stated and measured in tests/test_gpu_dense_x3.py).  |values| < 65504.
+ *   rs_dense_x3_prepare  kernel f32 [in, out] -> wt_hi, wt_lo fp16 [out, in] (once per weight change)
+ *   rs_dense_x3_supported  1 when (in, out, act) is served: in, out in {64,128,256}, act RS_ACT_NONE / RS_ACT_RELU
+ *   rs_dense_forward_x3  x f32 [B, in] (row stride % 4 == 0), bias f32 [out] or NULL -> y f32 [B, out] (may be a column
+ *                        slice of a wider buffer; 32-byte aligned, row stride % 8 == 0)
+ */
+int rs_dense_x3_prepare(const DLTensor* kernel, DLTensor* wt_hi, DLTensor* wt_lo, void* stream);
+int rs_dense_x3_supported(int64_t in, int64_t out, int act);
+int rs_dense_forward_x3(const DLTensor* x, const DLTensor* wt_hi, const DLTensor* wt_lo, const DLTensor* bias, int act,
+                        DLTensor* y, void* stream);
+/*
  * K1+K2 / K3 fused (bf16 tensor mode): a whole Dense chain in one tcgen05 kernel, activations kept in tensor
  * memory between layers.  n_layers = 4: tower chain ids -> Embedding -> 128-256-128-64-128 (tables[p] f32
  * [V,128], ids[p]); n_layers = 2: deep chain 256-256-128 on x[p] bf16 [B,256].  n_prob = 1 or 2 problems of the

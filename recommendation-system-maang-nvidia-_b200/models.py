@@ -17,6 +17,8 @@ runs hand-written sm_100a kernels through the C ABI (ops.py); there is no CPU pa
 
 from typing import Any, Dict, List, Optional, Sequence
 
+import os
+
 import numpy as np
 import torch
 
@@ -104,6 +106,7 @@ class Dense:
         self.units, self.activation, self.name = int(units), activation, name
         self._version = 0
         self._wt_cache = None
+        self._x3_cache = None
         self._kernel: Optional[torch.Tensor] = None
         self._bias: Optional[torch.Tensor] = None
         self._device = _dev(device)
@@ -119,6 +122,7 @@ class Dense:
         self._kernel = k
         self._version += 1
         self._wt_cache = None
+        self._x3_cache = None
 
     @property
     def bias(self) -> Optional[torch.Tensor]:
@@ -140,7 +144,34 @@ class Dense:
     def __call__(self, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         if self.kernel is None:
             self.build(int(x.shape[-1]))
+        if self._x3_applies(x, out):
+            hi, lo = self.wt_x3()
+            return ops.dense_x3(x, hi, lo, self.bias, self.activation, out=out)
         return ops.dense(x, self.kernel, self.bias, self.activation, out=out)
+
+    # fp32 mode has two kernels with the same stated tolerance (1e-5 of tensor scale): the FFMA GEMM (dense.cu) and, from
+    # X3_MIN_ROWS rows, the tcgen05 kernel that splits every fp32 operand into two fp16 numbers (dense_x3.cu).
+    # RS_FP32_TENSOR=0 keeps everything on the FFMA kernel.
+    X3_MIN_ROWS = 512
+
+    def _x3_applies(self, x: torch.Tensor, out: Optional[torch.Tensor]) -> bool:
+        if x.shape[0] < self.X3_MIN_ROWS or os.environ.get("RS_FP32_TENSOR", "1") == "0":
+            return False
+        if not ops.dense_x3_supported(int(x.shape[1]), self.units, self.activation):
+            return False
+        if x.dtype != torch.float32 or x.stride(1) != 1 or x.stride(0) % 4 or x.data_ptr() % 16:
+            return False
+        if out is not None and (out.stride(1) != 1 or out.stride(0) % 8 or out.data_ptr() % 32):
+            return False
+        return True
+
+    def wt_x3(self):
+        """(hi, lo) fp16 [out, in] images of the kernel for the fp32 tensor mode (cached per weight version)."""
+        c = self._x3_cache
+        if c is None or c[0] != self._version:
+            c = (self._version, ops.dense_x3_prepare(self.kernel))
+            self._x3_cache = c
+        return c[1]
 
     def wt_bf16(self) -> torch.Tensor:
         """The kernel transposed to [out, in] bf16 -- the K-major B operand of the tcgen05 path (cached)."""

@@ -49,6 +49,37 @@ def dense(x: torch.Tensor, kernel: torch.Tensor, bias: Optional[torch.Tensor], a
     return out
 
 
+def dense_x3_prepare(kernel: torch.Tensor):
+    """Keras kernel f32 [in, out] -> (wt_hi, wt_lo) fp16 [out, in]: the split B operand of the fp32 tensor mode."""
+    _require_cuda(kernel)
+    K, N = int(kernel.shape[0]), int(kernel.shape[1])
+    hi = torch.empty((N, K), dtype=torch.float16, device=kernel.device)
+    lo = torch.empty((N, K), dtype=torch.float16, device=kernel.device)
+    kb, hb, lb = _lib.dl(kernel), _lib.dl(hi), _lib.dl(lo)
+    _lib.check(_lib.load().rs_dense_x3_prepare(kb.ptr, hb.ptr, lb.ptr, _lib.stream_ptr()))
+    return hi, lo
+
+
+def dense_x3_supported(in_dim: int, out_dim: int, activation=None) -> bool:
+    try:
+        act = _lib.act_code(activation)
+    except ValueError:
+        return False
+    return bool(_lib.load().rs_dense_x3_supported(int(in_dim), int(out_dim), act))
+
+
+def dense_x3(x: torch.Tensor, wt_hi: torch.Tensor, wt_lo: torch.Tensor, bias: Optional[torch.Tensor], activation=None,
+             out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """K2 at fp32 accuracy on tcgen05 (3 x fp16 split products, csrc/dense_x3.cu); same contract as dense()."""
+    _require_cuda(x, wt_hi, wt_lo, bias, out)
+    if out is None:
+        out = torch.empty((x.shape[0], wt_hi.shape[0]), dtype=torch.float32, device=x.device)
+    xb, hb, lb, bb, ob = _lib.dl(x), _lib.dl(wt_hi), _lib.dl(wt_lo), _lib.dl(bias), _lib.dl(out)
+    _lib.check(_lib.load().rs_dense_forward_x3(xb.ptr, hb.ptr, lb.ptr, _lib.ptr(bb), _lib.act_code(activation), ob.ptr,
+                                               _lib.stream_ptr()))
+    return out
+
+
 def dense_bf16(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor], activation=None,
                out_bf16: Optional[torch.Tensor] = None, out_f32: Optional[torch.Tensor] = None, want_bf16: bool = True):
     """K2 on tcgen05: x bf16 [B, in], wt bf16 [out, in] (Keras kernel transposed) -> (y_bf16 or None, y_f32 or None)."""
