@@ -110,15 +110,31 @@ int rs_dense_forward_bf16(const DLTensor* x, const DLTensor* wt, const DLTensor*
  * fp16 numbers (v = hi + lo * 2^-11) and x.w is taken as hi.hi + 2^-11 (hi.lo + lo.hi) with fp32 accumulation (three
  * tcgen05.mma per K step; csrc/dense_x3.cu).  Tolerance vs the fp64 oracle: 1e-5 of tensor scale, the same as the FFMA
  * kernel behind rs_dense_forward (stated and measured in tests/test_gpu_dense_x3.py).  |values| < 65504.
- *   rs_dense_x3_prepare  kernel f32 [in, out] -> wt_hi, wt_lo fp16 [out, in] (once per weight change)
+ *   rs_dense_x3_prepare    kernel f32 [in, out] -> wt_hi, wt_lo fp16 [out, in] (once per weight change)
  *   rs_dense_x3_supported  1 when (in, out, act) is served: in, out in {64,128,256}, act RS_ACT_NONE / RS_ACT_RELU
- *   rs_dense_forward_x3  x f32 [B, in] (row stride % 4 == 0), bias f32 [out] or NULL -> y f32 [B, out] (may be a column
- *                        slice of a wider buffer; 32-byte aligned, row stride % 8 == 0)
+ *   rs_dense_forward_x3    one layer, or two independent layers of the same shape in one launch (the two towers).
+ * A layer's input is EITHER x f32 [B, in] (row stride % 4 == 0; with ids int32 / int64 [B]: x is an embedding table [V, in]
+ * and input row b is x[ids[b]], zeros outside [0, V) -- the Embedding gather of src/models.py:85,89 fused into the tower's
+ * first layer) OR the split planes x_hi, x_lo fp16 [B, in] a previous layer wrote.  Its output is y f32 [B, out] (may be a
+ * column slice of a wider buffer; 32-byte aligned, row stride % 8 == 0) and / or the split planes y_hi, y_lo fp16 [B, out]
+ * (32-byte aligned, row stride % 16 == 0) for the next layer -- same bytes as fp32, but the next layer then loads its
+ * operands by TMA instead of converting them.  bias f32 [out] or NULL.  Unused pointers are NULL.
  */
+typedef struct {
+  const DLTensor* x;
+  const DLTensor* ids;
+  const DLTensor* x_hi;
+  const DLTensor* x_lo;
+  const DLTensor* wt_hi;
+  const DLTensor* wt_lo;
+  const DLTensor* bias;
+  DLTensor* y;
+  DLTensor* y_hi;
+  DLTensor* y_lo;
+} rs_x3_layer_t;
 int rs_dense_x3_prepare(const DLTensor* kernel, DLTensor* wt_hi, DLTensor* wt_lo, void* stream);
 int rs_dense_x3_supported(int64_t in, int64_t out, int act);
-int rs_dense_forward_x3(const DLTensor* x, const DLTensor* wt_hi, const DLTensor* wt_lo, const DLTensor* bias, int act,
-                        DLTensor* y, void* stream);
+int rs_dense_forward_x3(int n_layers, const rs_x3_layer_t* layers, int act, void* stream);
 /*
  * K1+K2 / K3 fused (bf16 tensor mode): a whole Dense chain in one tcgen05 kernel, activations kept in tensor
  * memory between layers.  n_layers = 4: tower chain ids -> Embedding -> 128-256-128-64-128 (tables[p] f32
@@ -170,6 +186,15 @@ int rs_dcn_cross_forward(const DLTensor* x0, const DLTensor* cross_w, const DLTe
  */
 int rs_heads_forward(const DLTensor* z, const DLTensor* head_w, const DLTensor* head_b,
                      DLTensor* rating, DLTensor* ctr, void* stream);
+
+/*
+ * K3a + K3b in one pass, without materialising the [B, 384] concat of src/models.py:50: the cross stack on x0 f32 [B, 256]
+ * and both heads on (cross output | deep f32 [B, 128]); cross_w / cross_b f32 [L <= 4, 256], head_w f32 [2, 384], head_b
+ * f32 [2]; rating, ctr f32 [B, 1].  fp32 FMA arithmetic in the reference's order.  (What MultiTaskModel.call uses in fp32
+ * mode at ranking batches: 96 B read per feature row instead of three passes over the concat.)
+ */
+int rs_cross_heads_forward(const DLTensor* x0, const DLTensor* deep, const DLTensor* cross_w, const DLTensor* cross_b,
+                           const DLTensor* head_w, const DLTensor* head_b, DLTensor* rating, DLTensor* ctr, void* stream);
 
 /*
  * K4. faiss.normalize_L2 (src/trainer.py:240, app/recommendation_service.py:71):

@@ -2597,3 +2597,51 @@ extern "C" int rs_ranker_forward_rows(rs_ranker* h, const DLTensor* user_emb, co
                                       DLTensor* rating, DLTensor* ctr, void* stream) {
   return ranker_forward_impl(h, nullptr, nullptr, user_emb, item_emb, combined, rating, ctr, stream);
 }
+
+// K3a + K3b without the [B, 384] concat (src/models.py:38-44,50,119-120,131): DCN-v1 cross stack on x0 and both heads on
+// (cross output | deep output), one warp per row, fp32 FMA arithmetic in the reference's order (bias outside the product).
+extern "C" int rs_cross_heads_forward(const DLTensor* x0, const DLTensor* deep, const DLTensor* cross_w, const DLTensor* cross_b,
+                                      const DLTensor* head_w, const DLTensor* head_b, DLTensor* rating, DLTensor* ctr, void* stream) {
+  return rs::guard([&] {
+    using namespace rs;
+    require(x0, "x0", 2, kDLFloat, 32);
+    require(deep, "deep", 2, kDLFloat, 32);
+    require(cross_w, "cross_w", 2, kDLFloat, 32);
+    require(cross_b, "cross_b", 2, kDLFloat, 32);
+    require(head_w, "head_w", 2, kDLFloat, 32);
+    require(head_b, "head_b", 1, kDLFloat, 32);
+    RS_CHECK(rating != nullptr && ctr != nullptr && is_dtype(rating, kDLFloat, 32) && is_dtype(ctr, kDLFloat, 32), "rating / ctr must be f32 tensors");
+    const int64_t B = x0->shape[0], L = cross_w->shape[0];
+    RS_CHECK(on_device(x0) && on_device(deep) && on_device(cross_w) && on_device(cross_b) && on_device(head_w) && on_device(head_b) &&
+                 on_device(rating) && on_device(ctr), "all tensors must be CUDA tensors");
+    RS_CHECK(x0->shape[1] == 256 && deep->shape[0] == B && deep->shape[1] == 128, "x0 must be [B, 256] and deep [B, 128]");
+    RS_CHECK(L <= 4 && (L == 0 || cross_w->shape[1] == 256) && cross_b->shape[0] == L && (L == 0 || cross_b->shape[1] == 256) &&
+                 is_compact(cross_w) && is_compact(cross_b), "cross_w / cross_b must be contiguous [L <= 4, 256]");
+    RS_CHECK(head_w->shape[0] == 2 && head_w->shape[1] == 384 && is_compact(head_w) && head_b->shape[0] == 2, "head_w [2, 384], head_b [2]");
+    RS_CHECK(rating->shape[0] == B && ctr->shape[0] == B && is_compact(rating) && is_compact(ctr), "rating / ctr must be contiguous with B rows");
+    const int64_t ldx = row_stride_2d(x0, "x0"), ldd = row_stride_2d(deep, "deep");
+    RS_CHECK(ldx % 4 == 0 && ldd % 4 == 0, "row strides must be multiples of 4 floats");
+    require_aligned16(data_ptr<float>(x0), "x0");
+    require_aligned16(data_ptr<float>(deep), "deep");
+    if (L > 0) {
+      require_aligned16(data_ptr<float>(cross_w), "cross_w");
+      require_aligned16(data_ptr<float>(cross_b), "cross_b");
+    }
+    require_aligned16(data_ptr<float>(head_w), "head_w");
+    if (B == 0) return;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int64_t want = (B * 32 + 255) / 256;
+    const int blocks = static_cast<int>(std::min<int64_t>(want, (int64_t)sm_count() * 8));
+    const float *xp = data_ptr<float>(x0), *dp = data_ptr<float>(deep), *cwp = data_ptr<float>(cross_w), *cbp = data_ptr<float>(cross_b);
+    const float *hwp = data_ptr<float>(head_w), *hbp = data_ptr<float>(head_b);
+    float *rp = data_ptr<float>(rating), *cp = data_ptr<float>(ctr);
+    switch (L) {
+      case 0: cross_heads_kernel<0><<<blocks, 256, 0, st>>>(xp, ldx, dp, ldd, cwp, cbp, hwp, hbp, rp, cp, B); break;
+      case 1: cross_heads_kernel<1><<<blocks, 256, 0, st>>>(xp, ldx, dp, ldd, cwp, cbp, hwp, hbp, rp, cp, B); break;
+      case 2: cross_heads_kernel<2><<<blocks, 256, 0, st>>>(xp, ldx, dp, ldd, cwp, cbp, hwp, hbp, rp, cp, B); break;
+      case 3: cross_heads_kernel<3><<<blocks, 256, 0, st>>>(xp, ldx, dp, ldd, cwp, cbp, hwp, hbp, rp, cp, B); break;
+      default: cross_heads_kernel<4><<<blocks, 256, 0, st>>>(xp, ldx, dp, ldd, cwp, cbp, hwp, hbp, rp, cp, B); break;
+    }
+    RS_LAUNCH_CHECK();
+  });
+}

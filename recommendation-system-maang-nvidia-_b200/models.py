@@ -144,26 +144,14 @@ class Dense:
     def __call__(self, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         if self.kernel is None:
             self.build(int(x.shape[-1]))
-        if self._x3_applies(x, out):
-            hi, lo = self.wt_x3()
-            return ops.dense_x3(x, hi, lo, self.bias, self.activation, out=out)
+        if x3_chain_applies([self], int(x.shape[0]), int(x.shape[1]), x=x, out=out):
+            return x3_chain([([self], {"x": x})], [out])[0]
         return ops.dense(x, self.kernel, self.bias, self.activation, out=out)
 
     # fp32 mode has two kernels with the same stated tolerance (1e-5 of tensor scale): the FFMA GEMM (dense.cu) and, from
     # X3_MIN_ROWS rows, the tcgen05 kernel that splits every fp32 operand into two fp16 numbers (dense_x3.cu).
     # RS_FP32_TENSOR=0 keeps everything on the FFMA kernel.
     X3_MIN_ROWS = 512
-
-    def _x3_applies(self, x: torch.Tensor, out: Optional[torch.Tensor]) -> bool:
-        if x.shape[0] < self.X3_MIN_ROWS or os.environ.get("RS_FP32_TENSOR", "1") == "0":
-            return False
-        if not ops.dense_x3_supported(int(x.shape[1]), self.units, self.activation):
-            return False
-        if x.dtype != torch.float32 or x.stride(1) != 1 or x.stride(0) % 4 or x.data_ptr() % 16:
-            return False
-        if out is not None and (out.stride(1) != 1 or out.stride(0) % 8 or out.data_ptr() % 32):
-            return False
-        return True
 
     def wt_x3(self):
         """(hi, lo) fp16 [out, in] images of the kernel for the fp32 tensor mode (cached per weight version)."""
@@ -200,6 +188,60 @@ class Dense:
         self.bias = torch.from_numpy(b).to(self._device)
 
 
+def x3_chain_applies(layers, rows: int, in_dim: int, x: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> bool:
+    """Whether a chain of Dense layers runs on the fp32 tensor kernel (dense_x3.cu): ranking-size batch, every layer shape
+    served, and the fp32 input / output views aligned the way the kernel's 128-bit loads and 256-bit stores need."""
+    if rows < Dense.X3_MIN_ROWS or os.environ.get("RS_FP32_TENSOR", "1") == "0":
+        return False
+    d = in_dim
+    for layer in layers:
+        if layer.kernel is not None and int(layer.kernel.shape[0]) != d:
+            return False
+        if not ops.dense_x3_supported(d, layer.units, layer.activation):
+            return False
+        d = layer.units
+    if x is not None and (x.dtype != torch.float32 or x.stride(1) != 1 or x.stride(0) % 4 or x.data_ptr() % 16):
+        return False
+    if out is not None and (out.stride(1) != 1 or out.stride(0) % 8 or out.data_ptr() % 32):
+        return False
+    return True
+
+
+def x3_chain(problems, outs, split_outs=None):
+    """Dense chains on the fp32 tensor kernel.  problems: one or two (layers, first_input) pairs with identical layer shapes
+    -- both run in the same launches (the two towers); first_input: {"x": f32 rows}, {"x": table, "ids": rows} or {"x_hi",
+    "x_lo"}.  Between layers the activations travel as split fp16 planes (ops.split_planes); the last layer writes fp32 into
+    outs[p] (allocated when None) and, when split_outs[p] = (hi, lo) is given, the split planes for a following chain."""
+    n_layers = len(problems[0][0])
+    cur = [dict(first) for _, first in problems]
+    results = list(outs)
+    for li in range(n_layers):
+        last = li == n_layers - 1
+        batch = []
+        nxt = []
+        for pi, (layers, _) in enumerate(problems):
+            layer = layers[li]
+            if layer.kernel is None:
+                layer.build(int(layers[li - 1].units) if li else int(cur[pi]["x"].shape[1]))
+            hi, lo = layer.wt_x3()
+            src = cur[pi]
+            rows = int(src["ids"].shape[0]) if src.get("ids") is not None else int((src["x"] if "x" in src else src["x_hi"]).shape[0])
+            L = dict(src, wt_hi=hi, wt_lo=lo, bias=layer.bias)
+            if last:
+                if results[pi] is None:
+                    results[pi] = torch.empty((rows, layer.units), dtype=torch.float32, device=hi.device)
+                L["y"] = results[pi]
+                if split_outs is not None and split_outs[pi] is not None:
+                    L["y_hi"], L["y_lo"] = split_outs[pi]
+            else:
+                L["y_hi"], L["y_lo"] = ops.split_planes(rows, layer.units, hi.device)
+                nxt.append({"x_hi": L["y_hi"], "x_lo": L["y_lo"]})
+            batch.append(L)
+        ops.dense_x3_layers(batch, problems[0][0][li].activation)
+        cur = nxt
+    return results
+
+
 class Sequential:
     """keras.Sequential of Dense layers; `out` lets the last layer write into a wider buffer."""
 
@@ -208,9 +250,19 @@ class Sequential:
 
     def __call__(self, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         n = len(self.layers)
+        if n and x3_chain_applies(self.layers, int(x.shape[0]), int(x.shape[1]), x=x, out=out):
+            return x3_chain([(self.layers, {"x": x})], [out])[0]
         for i, layer in enumerate(self.layers):
             x = layer(x, out=out if i == n - 1 else None)
         return x
+
+    def call_on_rows(self, embedding: "Embedding", rows: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """tower(embedding(rows)) (src/models.py:85,89): at ranking batches the gather rides in the first layer's loads."""
+        table = embedding.embeddings
+        if (self.layers and rows.dtype in (torch.int32, torch.int64) and rows.is_contiguous()
+                and x3_chain_applies(self.layers, int(rows.shape[0]), int(table.shape[1]), x=table, out=out)):
+            return x3_chain([(self.layers, {"x": table, "ids": rows})], [out])[0]
+        return self(embedding(rows), out=out)
 
     def call_bf16(self, x_bf16: torch.Tensor, out_f32: Optional[torch.Tensor] = None,
                   out_bf16: Optional[torch.Tensor] = None, want_bf16_out: bool = False):
@@ -333,13 +385,13 @@ class MultiTowerModel:
         rows = self.user_lookup(ids)
         if self._bf16_ok(int(rows.shape[0])):
             return self.user_tower.call_bf16(ops.gather_bf16(self.user_embedding.embeddings, rows), out_f32=out)[0]
-        return self.user_tower(self.user_embedding(rows), out=out)                          # src/models.py:85
+        return self.user_tower.call_on_rows(self.user_embedding, rows, out=out)            # src/models.py:85
 
     def encode_item(self, ids, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         rows = self.item_lookup(ids)
         if self._bf16_ok(int(rows.shape[0])):
             return self.item_tower.call_bf16(ops.gather_bf16(self.item_embedding.embeddings, rows), out_f32=out)[0]
-        return self.item_tower(self.item_embedding(rows), out=out)                          # src/models.py:89
+        return self.item_tower.call_on_rows(self.item_embedding, rows, out=out)            # src/models.py:89
 
     def __call__(self, features: Dict[str, Any], training=None) -> Dict[str, Optional[torch.Tensor]]:
         user_emb = None
@@ -412,7 +464,8 @@ class _FusedRanker:
 
 
 class RankingSession:
-    """MultiTaskModel.call for ONE fixed batch size, replayed as one CUDA graph (bf16 tensor mode).
+    """MultiTaskModel.call for ONE fixed batch size, replayed as one CUDA graph (bf16 tensor mode: two launches; fp32
+    mode: seven launches of the fp32 tensor kernel, whose eager host work is longer than the kernels at batch 65,536).
 
     The eager call costs ~50 us of host work per batch (output allocation, DLPack export, two launches, the stream-
     ordered scratch allocation), which is as long as the two kernels themselves at batch 65,536.  A session owns
@@ -428,8 +481,6 @@ class RankingSession:
     snapshots the model's weights at capture time and re-captures itself when the model's weights_signature() changes."""
 
     def __init__(self, model: "MultiTaskModel", batch: int, ids_dtype=torch.int32):
-        if model.precision != "bf16":
-            raise ValueError("ranking sessions exist for precision='bf16' models (the fused two-kernel forward)")
         self.model, self.batch = model, int(batch)
         dev = model.device
         self.user_rows = torch.zeros((self.batch,), dtype=ids_dtype, device=dev)
@@ -523,11 +574,32 @@ class MultiTaskModel:
             return self._call_bf16(rows_u, rows_i)
         # the towers write straight into the two halves of the DCN input: the concat (:128) is free
         combined = torch.empty((B, 2 * E), dtype=torch.float32, device=self.device)
-        user_emb = enc.user_tower(enc.user_embedding(rows_u), out=combined[:, :E])         # :127 / :85
-        item_emb = enc.item_tower(enc.item_embedding(rows_i), out=combined[:, E:])         # :127 / :89
-        dcn_out = self.dcn(combined, training=training)                                    # :129
         hw, hb = self._heads_packed()
-        rating, ctr = ops.heads(dcn_out, hw, hb)                                           # :131
+        dcn = self.dcn
+        if not dcn.built:
+            dcn.build(combined.shape)
+        cw, cb = dcn._cross(2 * E)
+        ut, it = enc.user_tower.layers, enc.item_tower.layers
+        tables = (enc.user_embedding.embeddings, enc.item_embedding.embeddings)
+        ids_ok = all(r.dtype in (torch.int32, torch.int64) and r.is_contiguous() for r in (rows_u, rows_i)) and int(rows_i.shape[0]) == B
+        if (ids_ok and 2 * E == 256 and dcn.deep_layers[-1] == 128 and cw.shape[0] <= 4
+                and [l.units for l in ut] == [l.units for l in it] and [l.activation for l in ut] == [l.activation for l in it]
+                and x3_chain_applies(ut, B, E, x=tables[0], out=combined[:, :E]) and x3_chain_applies(it, B, E, x=tables[1], out=combined[:, E:])
+                and x3_chain_applies(dcn.deep_nets, B, 2 * E)):
+            # fp32 tensor mode (dense_x3.cu), 7 launches: both towers layer by layer in the same launches (gather fused into
+            # the first, split fp16 planes between layers), the deep net fed from the split copy of the tower outputs, then
+            # cross stack + heads in ONE pass over (x0, deep) -- the [B, 384] concat of :50 is never written
+            chi, clo = ops.split_planes(B, 2 * E, self.device)
+            user_emb, item_emb = x3_chain([(ut, {"x": tables[0], "ids": rows_u}), (it, {"x": tables[1], "ids": rows_i})],
+                                          [combined[:, :E], combined[:, E:]],                       # :127 / :85, :89
+                                          split_outs=[(chi[:, :E], clo[:, :E]), (chi[:, E:], clo[:, E:])])
+            deep = x3_chain([(dcn.deep_nets, {"x_hi": chi, "x_lo": clo})], [None])[0]               # :46-48
+            rating, ctr = ops.cross_heads(combined, deep, cw, cb, hw, hb)                           # :38-44, :131
+        else:
+            user_emb = enc.user_tower.call_on_rows(enc.user_embedding, rows_u, out=combined[:, :E])   # :127 / :85
+            item_emb = enc.item_tower.call_on_rows(enc.item_embedding, rows_i, out=combined[:, E:])   # :127 / :89
+            dcn_out = dcn(combined, training=training)                                     # :129
+            rating, ctr = ops.heads(dcn_out, hw, hb)                                       # :131
         return {"user_embedding": user_emb, "item_embedding": item_emb,
                 "rating_prediction": rating, "ctr_prediction": ctr}
 

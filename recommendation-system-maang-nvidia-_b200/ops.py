@@ -68,16 +68,39 @@ def dense_x3_supported(in_dim: int, out_dim: int, activation=None) -> bool:
     return bool(_lib.load().rs_dense_x3_supported(int(in_dim), int(out_dim), act))
 
 
+def dense_x3_layers(layers, activation=None) -> None:
+    """K2 at fp32 accuracy on tcgen05 (3 x fp16 split products, csrc/dense_x3.cu): one layer, or two independent layers of
+    the same shape in ONE launch (the two towers).  Each layer is a dict with wt_hi, wt_lo (dense_x3_prepare), optional
+    bias, an input -- x (f32 [B, in]; with ids: x is an embedding table and the layer reads x[ids]) or x_hi + x_lo (the
+    split planes a previous layer wrote) -- and outputs y (f32) and / or y_hi + y_lo (split planes for the next layer)."""
+    keys = ("x", "ids", "x_hi", "x_lo", "wt_hi", "wt_lo", "bias", "y", "y_hi", "y_lo")
+    n = len(layers)
+    arr = (_lib.X3Layer * n)()
+    keep = []
+    for i, L in enumerate(layers):
+        for k in keys:
+            t = L.get(k)
+            _require_cuda(t)
+            b = _lib.dl(t)
+            keep.append(b)
+            setattr(arr[i], k, _lib.ptr(b))
+    _lib.check(_lib.load().rs_dense_forward_x3(n, arr, _lib.act_code(activation), _lib.stream_ptr()))
+
+
 def dense_x3(x: torch.Tensor, wt_hi: torch.Tensor, wt_lo: torch.Tensor, bias: Optional[torch.Tensor], activation=None,
-             out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """K2 at fp32 accuracy on tcgen05 (3 x fp16 split products, csrc/dense_x3.cu); same contract as dense()."""
-    _require_cuda(x, wt_hi, wt_lo, bias, out)
+             out: Optional[torch.Tensor] = None, ids: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """One fp32-in / fp32-out layer on the fp32 tensor kernel; same contract as dense().  ids: x is an embedding table
+    and the layer reads x[ids] (K1 fused into the layer)."""
     if out is None:
-        out = torch.empty((x.shape[0], wt_hi.shape[0]), dtype=torch.float32, device=x.device)
-    xb, hb, lb, bb, ob = _lib.dl(x), _lib.dl(wt_hi), _lib.dl(wt_lo), _lib.dl(bias), _lib.dl(out)
-    _lib.check(_lib.load().rs_dense_forward_x3(xb.ptr, hb.ptr, lb.ptr, _lib.ptr(bb), _lib.act_code(activation), ob.ptr,
-                                               _lib.stream_ptr()))
+        out = torch.empty((x.shape[0] if ids is None else ids.shape[0], wt_hi.shape[0]), dtype=torch.float32, device=x.device)
+    dense_x3_layers([{"x": x, "ids": ids, "wt_hi": wt_hi, "wt_lo": wt_lo, "bias": bias, "y": out}], activation)
     return out
+
+
+def split_planes(rows: int, width: int, device) -> tuple:
+    """(hi, lo) fp16 [rows, width] planes: the form activations take between two layers of the fp32 tensor mode."""
+    both = torch.empty((2, rows, width), dtype=torch.float16, device=device)
+    return both[0], both[1]
 
 
 def dense_bf16(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor], activation=None,
@@ -141,6 +164,17 @@ def heads(z: torch.Tensor, head_w: torch.Tensor, head_b: torch.Tensor):
     ctr = torch.empty((z.shape[0], 1), dtype=torch.float32, device=z.device)
     a, w, b, r, c = _lib.dl(z), _lib.dl(head_w), _lib.dl(head_b), _lib.dl(rating), _lib.dl(ctr)
     _lib.check(_lib.load().rs_heads_forward(a.ptr, w.ptr, b.ptr, r.ptr, c.ptr, _lib.stream_ptr()))
+    return rating, ctr
+
+
+def cross_heads(x0: torch.Tensor, deep: torch.Tensor, cross_w: torch.Tensor, cross_b: torch.Tensor, head_w: torch.Tensor,
+                head_b: torch.Tensor):
+    """K3a + K3b in one pass (no [B, 384] concat): cross stack on x0 [B,256], heads on (cross | deep [B,128]) -> ([B,1], [B,1])."""
+    _require_cuda(x0, deep, cross_w, cross_b, head_w, head_b)
+    rating = torch.empty((x0.shape[0], 1), dtype=torch.float32, device=x0.device)
+    ctr = torch.empty((x0.shape[0], 1), dtype=torch.float32, device=x0.device)
+    bs = [_lib.dl(t) for t in (x0, deep, cross_w, cross_b, head_w, head_b, rating, ctr)]
+    _lib.check(_lib.load().rs_cross_heads_forward(*[b.ptr for b in bs], _lib.stream_ptr()))
     return rating, ctr
 
 

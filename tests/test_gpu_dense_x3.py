@@ -94,3 +94,64 @@ def test_fp32_model_forward_uses_x3_and_agrees_with_ffma(rs, monkeypatch):
     assert n_x3 > 0
     # a layer width outside {64,128,256} is not served by the tensor kernel
     assert not rs.ops.dense_x3_supported(100, 128, None) and not rs.ops.dense_x3_supported(128, 128, "sigmoid")
+
+
+def test_split_plane_chain_and_two_problems_per_launch(rs):
+    """What MultiTaskModel's fp32 mode does: two towers of the same shape in the same launches, the Embedding gather fused
+    into the first layer (int32 and int64 ids, an out-of-range id reads zeros), split fp16 planes between the layers, fp32
+    AND split output from the last layer, and a following chain fed from those planes -- against fp64 numpy."""
+    from recsys_b200.models import Dense, x3_chain
+    rng = np.random.default_rng(11)
+    B, E = 5000, 128
+    dims = [256, 128, 64, 128]
+    acts = ["relu", "relu", "relu", None]
+    tables = [rng.standard_normal((700, E)).astype(np.float32) * 0.3, rng.standard_normal((450, E)).astype(np.float32) * 0.3]
+    ids = [rng.integers(0, 700, B).astype(np.int32), rng.integers(0, 450, B).astype(np.int64)]
+    ids[0][7] = 5000                                             # outside the table: a row of zeros
+    towers, weights = [], []
+    for t in range(2):
+        layers, ws, d = [], [], E
+        for u, a in zip(dims, acts):
+            L = Dense(u, activation=a)
+            k, b = rs.synth.glorot_uniform(rng, d, u), rng.normal(0, 0.05, u).astype(np.float32)
+            L.set_weights([k, b])
+            layers.append(L)
+            ws.append((k, b))
+            d = u
+        towers.append(layers)
+        weights.append(ws)
+    combined = torch.zeros((B, 2 * E), device="cuda")
+    chi, clo = rs.ops.split_planes(B, 2 * E, "cuda")
+    outs = x3_chain([(towers[0], {"x": dev(tables[0]), "ids": dev(ids[0])}), (towers[1], {"x": dev(tables[1]), "ids": dev(ids[1])})],
+                    [combined[:, :E], combined[:, E:]], split_outs=[(chi[:, :E], clo[:, :E]), (chi[:, E:], clo[:, E:])])
+    want = []
+    for t in range(2):
+        x = tables[t][np.clip(ids[t], 0, len(tables[t]) - 1)].astype(np.float64)
+        x[ids[t] >= len(tables[t])] = 0
+        for (k, b), a in zip(weights[t], acts):
+            x = x @ k.astype(np.float64) + b
+            x = np.maximum(x, 0) if a == "relu" else x
+        want.append(x)
+    for t in range(2):
+        got = outs[t].cpu().numpy().astype(np.float64)
+        err = np.abs(got - want[t]).max() / np.abs(want[t]).max()
+        print(f"tower {t}: 4-layer chain max err / scale = {err:.2e}")
+        assert err <= 1e-5
+    # the split copy of the outputs reproduces them to 2^-22 relative, and feeds the next chain
+    rec = chi.float().cpu().numpy().astype(np.float64) + clo.float().cpu().numpy().astype(np.float64) / 2048.0
+    assert np.abs(rec - combined.cpu().numpy()).max() <= 2.0 ** -21 * np.abs(combined.cpu().numpy()).max()
+    deep = []
+    d = 2 * E
+    for u in (256, 128):
+        L = Dense(u, activation="relu")
+        k, b = rs.synth.glorot_uniform(rng, d, u), rng.normal(0, 0.05, u).astype(np.float32)
+        L.set_weights([k, b])
+        deep.append((L, k, b))
+        d = u
+    y = x3_chain([([L for L, _, _ in deep], {"x_hi": chi, "x_lo": clo})], [None])[0]
+    x = np.concatenate(want, axis=1)
+    for _, k, b in deep:
+        x = np.maximum(x @ k.astype(np.float64) + b, 0)
+    err = np.abs(y.cpu().numpy().astype(np.float64) - x).max() / np.abs(x).max()
+    print(f"deep chain fed from split planes: max err / scale = {err:.2e}")
+    assert err <= 1e-5

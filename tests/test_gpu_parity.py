@@ -23,9 +23,9 @@ sys.path.insert(0, str(GOLD))
 RTOL32 = 1e-5
 
 
-def close32(got, want64, name=""):
+def close32(got, want64, name="", scale=None):
     got = got.detach().cpu().numpy() if isinstance(got, torch.Tensor) else np.asarray(got)
-    scale = float(np.abs(want64).max())
+    scale = float(np.abs(want64).max()) if scale is None else float(scale)
     err = float(np.abs(got.astype(np.float64) - want64).max())
     assert err <= RTOL32 * scale + 1e-12, f"{name}: max err {err:.3e} vs scale {scale:.3e}"
 
@@ -167,7 +167,9 @@ def test_multitask_forward_config1_shapes(rs):
     close32(enc["user_embedding"], want["user_embedding"][:300], "encoder strings")
     # tuple input (features, labels) is accepted like the reference (src/models.py:126)
     out2 = m(({"user_id": dev(ur[:8]), "movie_id": dev(ir[:8])}, {"rating": None}))
-    np.testing.assert_array_equal(out2["rating_prediction"].cpu().numpy(), out["rating_prediction"][:8].cpu().numpy())
+    # 8 rows run on the FFMA kernels, 4,096 on the fp32 tensor kernel (dense_x3.cu): two implementations of one stated
+    # tolerance, so the same rows agree to that tolerance rather than bit for bit
+    close32(out2["rating_prediction"], want["rating_prediction"][:8], "tuple input", scale=np.abs(want["rating_prediction"]).max())
 
 
 def test_multitask_forward_matches_golden_fixture(rs):
