@@ -1533,14 +1533,27 @@ __global__ void __launch_bounds__(256) cross_heads_kernel(const float* __restric
     s = fmaf(a.x, b.x, s); s = fmaf(a.y, b.y, s); s = fmaf(a.z, b.z, s); s = fmaf(a.w, b.w, s);
     return s;
   };
+  // the next row's three loads are issued before this row's arithmetic (one row in flight per warp left the kernel
+  // latency-bound at ~2.6 TB/s: ~110 registers per thread allow only 16 warps per SM)
+  float4 nx0[2], ndv;
+  if (warp < B) {
+#pragma unroll
+    for (int c = 0; c < 2; ++c) nx0[c] = __ldg(reinterpret_cast<const float4*>(x0p + warp * ldx) + lane + 32 * c);
+    ndv = __ldg(reinterpret_cast<const float4*>(deep + warp * ldd) + lane);
+  }
   for (int64_t r = warp; r < B; r += nwarps) {
     float4 x0[2], xl[2];
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
-      x0[c] = __ldg(reinterpret_cast<const float4*>(x0p + r * ldx) + lane + 32 * c);
+      x0[c] = nx0[c];
       xl[c] = x0[c];
     }
-    const float4 dv = __ldg(reinterpret_cast<const float4*>(deep + r * ldd) + lane);
+    const float4 dv = ndv;
+    if (r + nwarps < B) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c) nx0[c] = __ldg(reinterpret_cast<const float4*>(x0p + (r + nwarps) * ldx) + lane + 32 * c);
+      ndv = __ldg(reinterpret_cast<const float4*>(deep + (r + nwarps) * ldd) + lane);
+    }
 #pragma unroll
     for (int l = 0; l < L; ++l) {
       float s = dot4(xl[1], wv[l][1], dot4(xl[0], wv[l][0], 0.0f));

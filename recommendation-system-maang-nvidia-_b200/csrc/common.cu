@@ -70,11 +70,12 @@ encode_tiled_fn get_encode_tiled() {
   return fn;
 }
 
-CUtensorMap make_tmap_2d(const void* base, CUtensorMapDataType dt, int elem_bytes, uint64_t rows, uint64_t cols,
-                         uint64_t row_stride_bytes, uint32_t box_rows, uint32_t box_cols) {
+static CUtensorMap make_tmap_2d_impl(const void* base, CUtensorMapDataType dt, int elem_bytes, uint64_t rows, uint64_t cols,
+                                     uint64_t row_stride_bytes, uint32_t box_rows, uint32_t box_cols, CUtensorMapSwizzle sw,
+                                     uint32_t inner_bytes) {
   RS_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "tensor map base must be 16-byte aligned");
   RS_CHECK(row_stride_bytes % 16 == 0, "tensor map row stride must be a multiple of 16 bytes");
-  RS_CHECK(box_cols * (uint64_t)elem_bytes == 128, "128-byte swizzle needs a 128-byte inner box");
+  RS_CHECK(box_cols * (uint64_t)elem_bytes == inner_bytes, "the swizzle mode needs an inner box of exactly its width");
   RS_CHECK(box_rows <= 256, "box rows must be <= 256");
   CUtensorMap m;
   cuuint64_t gdim[2] = {cols, rows};
@@ -82,10 +83,20 @@ CUtensorMap make_tmap_2d(const void* base, CUtensorMapDataType dt, int elem_byte
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = get_encode_tiled()(&m, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   RS_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
   return m;
+}
+
+CUtensorMap make_tmap_2d(const void* base, CUtensorMapDataType dt, int elem_bytes, uint64_t rows, uint64_t cols,
+                         uint64_t row_stride_bytes, uint32_t box_rows, uint32_t box_cols) {
+  return make_tmap_2d_impl(base, dt, elem_bytes, rows, cols, row_stride_bytes, box_rows, box_cols, CU_TENSOR_MAP_SWIZZLE_128B, 128);
+}
+
+CUtensorMap make_tmap_2d_sw64(const void* base, CUtensorMapDataType dt, int elem_bytes, uint64_t rows, uint64_t cols,
+                              uint64_t row_stride_bytes, uint32_t box_rows, uint32_t box_cols) {
+  return make_tmap_2d_impl(base, dt, elem_bytes, rows, cols, row_stride_bytes, box_rows, box_cols, CU_TENSOR_MAP_SWIZZLE_64B, 64);
 }
 
 }  // namespace rs

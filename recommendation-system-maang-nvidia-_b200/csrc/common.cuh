@@ -123,6 +123,9 @@ encode_tiled_fn get_encode_tiled();
 // 2-D row-major [rows, cols] tensor map with a [box_rows, box_cols] box and 128-byte swizzle
 CUtensorMap make_tmap_2d(const void* base, CUtensorMapDataType dt, int elem_bytes, uint64_t rows, uint64_t cols,
                          uint64_t row_stride_bytes, uint32_t box_rows, uint32_t box_cols);
+// the same with a 64-byte inner box and the 64-byte swizzle (16-byte chunk index ^= (row >> 1) & 3)
+CUtensorMap make_tmap_2d_sw64(const void* base, CUtensorMapDataType dt, int elem_bytes, uint64_t rows, uint64_t cols,
+                              uint64_t row_stride_bytes, uint32_t box_rows, uint32_t box_cols);
 
 }  // namespace rs
 

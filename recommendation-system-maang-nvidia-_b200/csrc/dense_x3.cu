@@ -22,10 +22,11 @@
 // towers): blockIdx.x % n_prob picks the problem.
 //   * the layer's kernel, pre-split and transposed to [out][in] fp16 hi / lo images (rs_dense_x3_prepare, once per weight
 //     change), is TMA-loaded once per CTA: <= 128 KB (N tile 128 x K 256 x 2 images, or both N halves of a K = 128 layer);
-//   * a [128 rows x 64] K chunk of the input = hi image | lo image, 32 KB, in a 3-stage ring in the 128-byte swizzled
+//   * a [128 rows x 64] K chunk of the input = hi image | lo image, 32 KB, in a 2-4 stage ring in the 128-byte swizzled
 //     K-major layout UMMA reads: filled by TMA (split input) or by 8 converting warps (fp32 / gathered input);
 //   * one thread issues 3 x 4 MMAs per chunk (M128 x N<=128 x K16) into one of two TMEM slots (main | corr, 256 columns);
-//   * 8 epilogue warps combine, add the bias, apply the activation and store fp32 rows and / or the split planes.
+//   * 4 epilogue warps combine, add the bias, apply the activation and hand fp32 rows and / or the split planes to TMA
+//     stores through two 4 KB staging buffers per warp.
 // Per sample and layer: 3 x 2 x in x out tensor flop; bytes: 4 in read + 4 out written.
 #include <algorithm>
 #include <mutex>
@@ -41,18 +42,20 @@ using namespace rsd;
 
 constexpr int BM = 128;
 constexpr int X3_PROD_WARPS = 8;                 // converting kernels: warps 0-7 split fp32 rows
-// Warp roles.  Registers are allocated per four warps, so the warp count is kept at 13 -> 16 (128 registers per thread:
-// the converting producers hold two chunks in flight) and 12 (TMA input).  Epilogue warps start at a multiple of 4: a warp
-// may only touch the TMEM lane quarter warp % 4.
+// Warp roles.  Registers are allocated per four warps: 13 warps -> 16 (128 registers per thread; the converting producers
+// hold two chunks in flight) and 6 -> 8 (TMA input).  Epilogue warps start at a multiple of 4: a warp may only touch the
+// TMEM lane quarter warp % 4.
 template <bool TMA_IN>
 struct X3Roles {
   static constexpr int EPI0 = TMA_IN ? 4 : 8;
-  static constexpr int EPI_WARPS = TMA_IN ? 8 : 4;        // TMA input: two warps per lane quarter, half the N tile each
+  static constexpr int EPI_WARPS = 4;
   static constexpr int ISSUER = TMA_IN ? 1 : 12;          // TMA input: warp 0 = TMA producer, warps 2-3 idle
-  static constexpr int THREADS = TMA_IN ? 12 * 32 : 13 * 32;
+  static constexpr int THREADS = TMA_IN ? 8 * 32 : 13 * 32;
 };
-constexpr int X3_STAGES = 3;
+constexpr int X3_MAX_STAGES = 4;                 // ring depth is a launch parameter: whatever fits beside the kernel images (2..4)
 constexpr int X3_STAGE_BYTES = 2 * BM * 128;     // hi image [128 x 64 fp16] | lo image
+constexpr int X3_OUT_BYTES = 4096;               // one output piece: fp32 [32 rows x 32] or the hi | lo planes of it
+constexpr int X3_OUT_STAGING = 4 * 2 * X3_OUT_BYTES;   // two pieces per epilogue warp
 constexpr float kLoScale = 2048.0f;              // 2^11
 constexpr float kLoInv = 1.0f / 2048.0f;
 
@@ -76,11 +79,14 @@ struct X3Params {
   int n_prob;
   int act;
   int nh;                // N tiles per CTA (1 or 2); grid.y covers the rest
+  int stages;            // ring depth (2..4)
 };
 
 struct X3Maps {
   CUtensorMap w_hi[2], w_lo[2];   // per problem: kernel images [N, K], box [NT, 64]
   CUtensorMap x_hi[2], x_lo[2];   // per problem: split input planes [rows, K], box [128, 64] (TMA input only)
+  CUtensorMap y[2];               // per problem: fp32 output [rows, N], box [32 rows, 32 floats], 128-byte swizzle
+  CUtensorMap y_hi[2], y_lo[2];   // per problem: split output planes [rows, N], box [32 rows, 32 fp16], 64-byte swizzle
 };
 
 // instruction descriptor, kind::f16: D = f32, A = B = fp16 (format 0), both K-major
@@ -88,18 +94,34 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16_f32(int M, int N) {
   return (1u << 4) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+// K = 256 layers keep the 128 KB of kernel images and a 3-stage ring (their MMA time per chunk is long enough that two
+// stages leave bubbles: measured 34 -> 39 us) and store straight from registers; narrower layers have room for the
+// TMA-store staging.
+template <int K>
+constexpr bool x3_out_tma() { return K < 256; }
 template <int K, int NT>
-constexpr int x3_smem(int nh) {
-  return nh * (K / 64) * NT * 128 * 2 + X3_STAGES * X3_STAGE_BYTES + 1024 /*bias*/ + 256 /*barriers*/ + 1024 /*align*/;
+constexpr int x3_smem(int nh, int stages) {
+  return nh * (K / 64) * NT * 128 * 2 + stages * X3_STAGE_BYTES + (x3_out_tma<K>() ? X3_OUT_STAGING : 0) + 1024 /*bias*/ +
+         256 /*barriers*/ + 1024 /*align*/;
 }
 
-// v -> (hi, lo) with v ~= hi + lo * 2^-11
+// v -> (hi, lo) with v ~= hi + lo * 2^-11 (scalar form: the weight-split kernel)
 __device__ __forceinline__ void split16(float v, __half& h, __half& l) {
   h = __float2half_rn(v);
   l = __float2half_rn((v - __half2float(h)) * kLoScale);
 }
-__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
-  return static_cast<uint32_t>(__half_as_ushort(a)) | (static_cast<uint32_t>(__half_as_ushort(b)) << 16);
+// The same for a pair, packed: (a, b) -> hi = {fp16(a), fp16(b)}, lo likewise (a in the low half).  cvt.rn.f16x2.f32 is one
+// full-rate F2FP for two values; the scalar F2F.F16.F32 the compiler emits for __float2half_rn runs at 16 per clock and SM
+// and was the bottleneck of the first version (3 conversions per element in the producers and again in the epilogue).
+__device__ __forceinline__ uint32_t cvt_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ void split16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  hi = cvt_f16x2(a, b);
+  const float2 back = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  lo = cvt_f16x2((a - back.x) * kLoScale, (b - back.y) * kLoScale);
 }
 
 template <int K, int NT, bool TMA_IN>
@@ -115,12 +137,15 @@ dense_x3_kernel(const __grid_constant__ X3Maps maps, const __grid_constant__ X3P
   uint8_t* w_hi = base;
   uint8_t* w_lo = base + w_img;
   uint8_t* ring = base + 2 * w_img;
-  float* bias_s = reinterpret_cast<float*>(ring + X3_STAGES * X3_STAGE_BYTES);   // [nh * NT]
+  const uint32_t X3_STAGES = static_cast<uint32_t>(p.stages);
+  constexpr bool OUT_TMA = x3_out_tma<K>();
+  uint8_t* out_stage = ring + X3_STAGES * X3_STAGE_BYTES;                        // [4 epilogue warps][2][4 KB] (OUT_TMA)
+  float* bias_s = reinterpret_cast<float*>(out_stage + (OUT_TMA ? X3_OUT_STAGING : 0));   // [nh * NT]
   uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + 256);
   uint64_t* wfull = bars;
   uint64_t* full = bars + 1;                     // [STAGES] producers -> issuer
-  uint64_t* empty = full + X3_STAGES;            // [STAGES] commit -> producers
-  uint64_t* tfull = empty + X3_STAGES;           // [2] commit -> epilogue
+  uint64_t* empty = full + X3_MAX_STAGES;        // [STAGES] commit -> producers
+  uint64_t* tfull = empty + X3_MAX_STAGES;       // [2] commit -> epilogue
   uint64_t* tempty = tfull + 2;                  // [2] epilogue -> issuer
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
@@ -143,7 +168,12 @@ dense_x3_kernel(const __grid_constant__ X3Maps maps, const __grid_constant__ X3P
       tma_prefetch_desc(&maps.x_lo[pi]);
     }
     mbar_init(wfull, 1);
-    for (int s = 0; s < X3_STAGES; ++s) {
+    if (pr.y) tma_prefetch_desc(&maps.y[pi]);
+    if (pr.y_hi) {
+      tma_prefetch_desc(&maps.y_hi[pi]);
+      tma_prefetch_desc(&maps.y_lo[pi]);
+    }
+    for (uint32_t s = 0; s < X3_STAGES; ++s) {
       mbar_init(&full[s], TMA_IN ? 1 : X3_PROD_WARPS);
       mbar_init(&empty[s], 1);
     }
@@ -287,15 +317,13 @@ dense_x3_kernel(const __grid_constant__ X3Maps maps, const __grid_constant__ X3P
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const int r = warp * 16 + e * 2 + rsub;                       // row within the tile
-        __half h[4], l[4];
-        split16(buf[e].x, h[0], l[0]);
-        split16(buf[e].y, h[1], l[1]);
-        split16(buf[e].z, h[2], l[2]);
-        split16(buf[e].w, h[3], l[3]);
+        uint2 h2, l2;
+        split16x2(buf[e].x, buf[e].y, h2.x, l2.x);
+        split16x2(buf[e].z, buf[e].w, h2.y, l2.y);
         // 16-byte chunk c = j / 2 of the 128-byte row, XOR-swizzled with the row's position in its 8-row group
         const uint32_t off = static_cast<uint32_t>(r * 128 + (((j >> 1) ^ (r & 7)) << 4) + (j & 1) * 8);
-        *reinterpret_cast<uint2*>(st_hi + off) = make_uint2(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]));
-        *reinterpret_cast<uint2*>(st_lo + off) = make_uint2(pack_h2(l[0], l[1]), pack_h2(l[2], l[3]));
+        *reinterpret_cast<uint2*>(st_hi + off) = h2;
+        *reinterpret_cast<uint2*>(st_lo + off) = l2;
       }
       fence_proxy_async_smem();      // generic-proxy stores -> visible to the tensor core's async-proxy reads
       __syncwarp();
@@ -314,62 +342,105 @@ dense_x3_kernel(const __grid_constant__ X3Maps maps, const __grid_constant__ X3P
     }
   } else if (warp >= X3_EPI0 && warp < X3_EPI0 + X3_EPI_WARPS) {
     // ---- epilogue: main + 2^-11 corr + bias -> activation -> fp32 rows and / or the split planes ----
+    // Every output piece (32 rows x 32 columns of one warp) goes through one of the warp's two 4 KB staging buffers and
+    // leaves as a TMA store; rows past the batch are clipped by the tensor map.  The first version stored straight from
+    // registers, one row per thread: each 256-bit store instruction touched 32 different lines, and the LSU's one tag
+    // lookup per cycle made the stores the longest phase of every layer (128 KB per tile = ~16 k cycles).
     const int quarter = warp & 3;
-    const int half = (warp - X3_EPI0) >> 2;          // which column part of the N tile
-    constexpr int HC = NT / (X3_EPI_WARPS / 4);      // columns per warp and item
+    const int ew = warp - X3_EPI0;
+    uint8_t* const stg0 = out_stage + ew * 2 * X3_OUT_BYTES;
+    uint32_t nst = 0;
+    auto stage_acquire = [&]() -> uint8_t* {
+      if (lane == 0) bulk_wait_read<1>();        // the store that last read this buffer (two pieces ago) is done with it
+      __syncwarp();
+      return stg0 + (nst++ & 1u) * X3_OUT_BYTES;
+    };
     for (int64_t i = 0; i < n_items; ++i) {
       const int hh = static_cast<int>(i % nh);
       const int64_t tile = cta + (i / nh) * ncta;
-      const int64_t row = tile * BM + quarter * 32 + lane;
+      const int row0 = static_cast<int>(tile * BM) + quarter * 32;
       const uint32_t a = static_cast<uint32_t>(i) & 1u, aph = (static_cast<uint32_t>(i) >> 1) & 1u;
       mbar_wait(&tfull[a], aph);
       tc_fence_after_sync();
-      const uint32_t taddr = tmem_base + a * 256 + half * HC + (static_cast<uint32_t>(quarter * 32) << 16);
-      const int col_base = n0 + hh * NT + half * HC;
+      const uint32_t taddr = tmem_base + a * 256 + (static_cast<uint32_t>(quarter * 32) << 16);
+      const int col_base = n0 + hh * NT;
 #pragma unroll 1
-      for (int c = 0; c < HC / 32; ++c) {
+      for (int c = 0; c < NT / 32; ++c) {
         float m[32], cr[32];
         __syncwarp();
         tmem_ld_32x32(taddr + c * 32, m);
         tmem_ld_32x32(taddr + 128 + c * 32, cr);
-        const float* bs = bias_s + hh * NT + half * HC + c * 32;
+        if (c == NT / 32 - 1) {                  // the accumulators are in registers: the issuer may start the next item
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[a]);
+        }
+        const float* bs = bias_s + hh * NT + c * 32;
 #pragma unroll
         for (int e = 0; e < 32; ++e) m[e] = fmaf(cr[e], kLoInv, m[e]) + bs[e];
         if (p.act == RS_ACT_RELU) {
 #pragma unroll
           for (int e = 0; e < 32; ++e) m[e] = fmaxf(m[e], 0.0f);
         }
-        if (row < pr.rows) {
-          const int col = col_base + c * 32;
-          if (pr.y) {
-            float* yrow = pr.y + row * pr.ldy + col;
+        const int col = col_base + c * 32;
+        if constexpr (!OUT_TMA) {
+          const int64_t row = static_cast<int64_t>(row0) + lane;
+          if (row < pr.rows) {
+            if (pr.y) {
+              float* yrow = pr.y + row * pr.ldy + col;
 #pragma unroll
-            for (int e = 0; e < 32; e += 8)
-              st_global_256(yrow + e, m[e], m[e + 1], m[e + 2], m[e + 3], m[e + 4], m[e + 5], m[e + 6], m[e + 7]);
-          }
-          if (pr.y_hi) {
-            uint32_t ph[16], pl[16];
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              __half h0, l0, h1, l1;
-              split16(m[2 * e], h0, l0);
-              split16(m[2 * e + 1], h1, l1);
-              ph[e] = pack_h2(h0, h1);
-              pl[e] = pack_h2(l0, l1);
+              for (int e = 0; e < 32; e += 8)
+                st_global_256(yrow + e, m[e], m[e + 1], m[e + 2], m[e + 3], m[e + 4], m[e + 5], m[e + 6], m[e + 7]);
             }
-            __half* hrow = pr.y_hi + row * pr.ldy16 + col;
-            __half* lrow = pr.y_lo + row * pr.ldy16 + col;
-            st_global_256(hrow, ph[0], ph[1], ph[2], ph[3], ph[4], ph[5], ph[6], ph[7]);
-            st_global_256(hrow + 16, ph[8], ph[9], ph[10], ph[11], ph[12], ph[13], ph[14], ph[15]);
-            st_global_256(lrow, pl[0], pl[1], pl[2], pl[3], pl[4], pl[5], pl[6], pl[7]);
-            st_global_256(lrow + 16, pl[8], pl[9], pl[10], pl[11], pl[12], pl[13], pl[14], pl[15]);
+            if (pr.y_hi) {
+              uint32_t ph[16], pl[16];
+#pragma unroll
+              for (int e = 0; e < 16; ++e) split16x2(m[2 * e], m[2 * e + 1], ph[e], pl[e]);
+              __half* hrow = pr.y_hi + row * pr.ldy16 + col;
+              __half* lrow = pr.y_lo + row * pr.ldy16 + col;
+              st_global_256(hrow, ph[0], ph[1], ph[2], ph[3], ph[4], ph[5], ph[6], ph[7]);
+              st_global_256(hrow + 16, ph[8], ph[9], ph[10], ph[11], ph[12], ph[13], ph[14], ph[15]);
+              st_global_256(lrow, pl[0], pl[1], pl[2], pl[3], pl[4], pl[5], pl[6], pl[7]);
+              st_global_256(lrow + 16, pl[8], pl[9], pl[10], pl[11], pl[12], pl[13], pl[14], pl[15]);
+            }
+          }
+          continue;
+        }
+        if (pr.y) {
+          uint8_t* buf = stage_acquire();
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj)           // row `lane` of the piece: 128 bytes, 16-byte chunks XOR-swizzled
+            *reinterpret_cast<float4*>(buf + lane * 128 + ((jj ^ (lane & 7)) << 4)) =
+                make_float4(m[4 * jj], m[4 * jj + 1], m[4 * jj + 2], m[4 * jj + 3]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&maps.y[pi], buf, col, row0);
+            bulk_commit();
+          }
+        }
+        if (pr.y_hi) {
+          uint32_t ph[16], pl[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) split16x2(m[2 * e], m[2 * e + 1], ph[e], pl[e]);
+          uint8_t* buf = stage_acquire();
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {         // row `lane`: 64 bytes per plane, 64-byte swizzle (chunk ^= (row >> 1) & 3)
+            const uint32_t off = static_cast<uint32_t>(lane * 64 + ((cc ^ ((lane >> 1) & 3)) << 4));
+            *reinterpret_cast<uint4*>(buf + off) = make_uint4(ph[4 * cc], ph[4 * cc + 1], ph[4 * cc + 2], ph[4 * cc + 3]);
+            *reinterpret_cast<uint4*>(buf + 2048 + off) = make_uint4(pl[4 * cc], pl[4 * cc + 1], pl[4 * cc + 2], pl[4 * cc + 3]);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&maps.y_hi[pi], buf, col, row0);
+            tma_store_2d(&maps.y_lo[pi], buf + 2048, col, row0);
+            bulk_commit();
           }
         }
       }
-      tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[a]);
     }
+    if (OUT_TMA && lane == 0) bulk_wait_all();   // the staging buffers (and this CTA) outlive every store
   }
 
   tc_fence_before_sync();
@@ -392,18 +463,20 @@ __global__ void __launch_bounds__(256) x3_split_kernel(const float* __restrict__
 
 template <int K, int NT, bool TMA_IN>
 void launch_x3(const X3Maps& maps, X3Params p, int N, cudaStream_t st) {
-  // N tiles per CTA: as many as keep both weight images within 128 KB
+  // N tiles per CTA: as many as keep both weight images within 128 KB; ring depth: what fits beside them
   const int n_tiles = N / NT;
   const int fit = std::max(1, (128 * 1024) / ((K / 64) * NT * 128 * 2));
   p.nh = std::min(n_tiles, std::min(fit, 2));
   while (n_tiles % p.nh) --p.nh;
-  const int smem = x3_smem<K, NT>(p.nh);
+  p.stages = X3_MAX_STAGES;
+  while (p.stages > 2 && x3_smem<K, NT>(p.nh, p.stages) > 232448) --p.stages;
+  const int smem = x3_smem<K, NT>(p.nh, p.stages);
+  RS_CHECK(smem <= 232448, "fp32 tensor-mode Dense: the layer does not fit the shared memory of an SM");
   static std::once_flag once[64];
   int dev = 0;
   cudaGetDevice(&dev);
   std::call_once(once[dev & 63], [] {
-    cudaFuncSetAttribute(dense_x3_kernel<K, NT, TMA_IN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         x3_smem<K, NT>(2) <= 232448 ? x3_smem<K, NT>(2) : x3_smem<K, NT>(1));
+    cudaFuncSetAttribute(dense_x3_kernel<K, NT, TMA_IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
   });
   int64_t max_tiles = 0;
   for (int i = 0; i < p.n_prob; ++i) max_tiles = std::max<int64_t>(max_tiles, (p.prob[i].rows + BM - 1) / BM);
@@ -529,6 +602,7 @@ extern "C" int rs_dense_forward_x3(int n_layers, const rs_x3_layer_t* layers, in
         q.y = data_ptr<float>(L.y);
         q.ldy = row_stride_2d(L.y, "y");
         RS_CHECK(q.ldy % 8 == 0 && (reinterpret_cast<uintptr_t>(q.y) & 31) == 0, "y must be 32-byte aligned with a row stride that is a multiple of 8");
+        if (B > 0) maps.y[i] = make_tmap_2d(q.y, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)B, (uint64_t)N, (uint64_t)q.ldy * 4, 32, 32);
       }
       if (L.y_hi) {
         require(L.y_hi, "y_hi", 2, kDLFloat, 16);
@@ -540,6 +614,10 @@ extern "C" int rs_dense_forward_x3(int n_layers, const rs_x3_layer_t* layers, in
         q.ldy16 = row_stride_2d(L.y_hi, "y_hi");
         RS_CHECK(row_stride_2d(L.y_lo, "y_lo") == q.ldy16 && q.ldy16 % 16 == 0 && (reinterpret_cast<uintptr_t>(q.y_hi) & 31) == 0 &&
                      (reinterpret_cast<uintptr_t>(q.y_lo) & 31) == 0, "y_hi / y_lo: equal row strides (multiple of 16), 32-byte aligned");
+        if (B > 0) {
+          maps.y_hi[i] = make_tmap_2d_sw64(q.y_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (uint64_t)B, (uint64_t)N, (uint64_t)q.ldy16 * 2, 32, 32);
+          maps.y_lo[i] = make_tmap_2d_sw64(q.y_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (uint64_t)B, (uint64_t)N, (uint64_t)q.ldy16 * 2, 32, 32);
+        }
       }
       if (L.bias) {
         require(L.bias, "bias", 1, kDLFloat, 32);
@@ -552,9 +630,10 @@ extern "C" int rs_dense_forward_x3(int n_layers, const rs_x3_layer_t* layers, in
     }
     if (!any_rows) return;
     for (int i = 0; i < n_layers; ++i)   // an empty problem next to a non-empty one: its CTAs find no tiles, but the maps must be valid
-      if (tma_in && p.prob[i].rows == 0) {
-        maps.x_hi[i] = maps.w_hi[i];
-        maps.x_lo[i] = maps.w_lo[i];
+      if (p.prob[i].rows == 0) {
+        maps.x_hi[i] = maps.x_lo[i] = maps.y[i] = maps.y_hi[i] = maps.y_lo[i] = maps.w_hi[i];
+        p.prob[i].y = nullptr;
+        p.prob[i].y_hi = p.prob[i].y_lo = nullptr;
       }
     sm_count();
     cudaStream_t st = static_cast<cudaStream_t>(stream);
