@@ -551,10 +551,12 @@ int rs_index_search(rs_index_t* h, const DLTensor* q, int k, int64_t id_base, in
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     bool tensor = false;
     if (mode == RS_TENSOR_BF16) {
-      RS_CHECK(tensor_path_supported(h, nq, k), "tensor mode is not applicable to this shape (needs d=128, k<=128, ntotal>=65536)");
+      RS_CHECK(tensor_path_supported(h, nq, k), "tensor mode is not applicable to this shape (needs d=128, k<=128 and ntotal>=65536, or 256<=ntotal<=32768 with k<=ntotal/128)");
       tensor = true;
     } else if (mode == RS_AUTO) {
-      tensor = tensor_path_supported(h, nq, k);   // faster than the fp32 scan at every batch size (bf16 shadow = half the bytes)
+      // large catalogs: faster than the fp32 scan at every batch size (bf16 shadow = half the bytes); small (L2-resident)
+      // ones: from 128 queries -- below that the scan's two launches beat the tensor path's seven (measured, config 1 shape)
+      tensor = tensor_path_supported(h, nq, k) && (h->ntotal >= 65536 || nq >= 128);
     }
     auto run = [&](const float* qp, float* Dp, int64_t ldD, int64_t* Ip, int64_t ldI) {
       if (tensor) search_tensor_device(h, qp, nq, k, id_base, Dp, ldD, Ip, ldI, st);
@@ -617,7 +619,7 @@ int rs_index_search_deferred(rs_index_t* h, const DLTensor* q, int k, int64_t id
     RS_CHECK(q->device.device_id == h->device, "q is on a different device than the index");
     require_aligned16(data_ptr<float>(q), "q");
     const bool supported = tensor_path_supported(h, nq, k);
-    RS_CHECK(mode != RS_TENSOR_BF16 || supported, "tensor mode is not applicable to this shape (needs d=128, k<=128, ntotal>=65536)");
+    RS_CHECK(mode != RS_TENSOR_BF16 || supported, "tensor mode is not applicable to this shape (needs d=128, k<=128 and ntotal>=65536, or 256<=ntotal<=32768 with k<=ntotal/128)");
     if (mode != RS_EXACT_FP32 && supported) {
       search_tensor_device(h, data_ptr<float>(q), nq, k, id_base, data_ptr<float>(D), row_stride_2d(D, "D"),
                            data_ptr<int64_t>(I), row_stride_2d(I, "I"), st, data_ptr<int>(need_exact));

@@ -61,7 +61,7 @@ constexpr int CAND_CAP = 4096;           // candidate list capacity per query
 constexpr int SEL_NT = 256;
 constexpr float C_EPS = 0.00390625f * 1.0625f;
 
-enum { MODE_FILTER = 0, MODE_SAMPLE = 1, MODE_DUMP = 2 };
+enum { MODE_FILTER = 0, MODE_SAMPLE = 1, MODE_DUMP = 2, MODE_SAMPLE_FINE = 3 };
 
 struct TcParams {
   int64_t n_items;
@@ -269,6 +269,18 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             }
           } else if (MODE == MODE_SAMPLE) {
             hmax = fmaxf(hmax, m);
+          } else if (MODE == MODE_SAMPLE_FINE) {
+            // small catalogs: EVERY tile is visited once and every 32-score chunk keeps its own maximum (no sharing of
+            // slots, no atomics); rows past the catalog (zero-filled by TMA: score 0) must not count
+            float mm = m;
+            const int64_t i0 = item0 + c * 32;
+            if (i0 + 32 > p.n_items) {
+              mm = -INFINITY;
+#pragma unroll
+              for (int e = 0; e < 32; ++e)
+                if (i0 + e < p.n_items) mm = fmaxf(mm, v[e]);
+            }
+            p.smax[(int64_t)qrow[r] * p.smax_ld + visit * (BN / 32) + slice * (SLICE_COLS / 32) + c] = f32_to_ordered(mm);
           } else {
             if (qrow[r] < p.nq) {
 #pragma unroll
@@ -417,6 +429,32 @@ __global__ void __launch_bounds__(256) threshold_kernel(const unsigned* __restri
   const uint32_t kth = block_kth_largest<256>([&](int i) { return vals[i]; }, n_vals, rank, hist, state, tid);
   if (tid == 0) {
     thr[qi] = ordered_to_f32(kth);
+    cand_cnt[qi] = 0;
+    flags[qi] = 0;
+  }
+}
+
+// Small catalogs (every tile sampled, one maximum per 32-row chunk): tau_q = (k-th largest chunk maximum) - 2 eps_q.  At
+// least k rows score >= the k-th largest chunk maximum, so s_hat_(k) >= it, and every row of the true top-k has
+// s_hat >= s_hat_(k) - 2 eps >= tau: the candidate list provably holds the top-k (select_rescore_kernel's verification
+// s_hat_(k) - 2 eps >= tau then always passes).  Fewer real chunks than k: no threshold (the catalog is below 4,096 rows).
+__global__ void __launch_bounds__(256) threshold_small_kernel(const unsigned* __restrict__ smax, int n_vals, int n_real, int k,
+                                                              const float* __restrict__ eps2, float* __restrict__ thr,
+                                                              int* __restrict__ cand_cnt, int* __restrict__ flags) {
+  __shared__ unsigned vals[1024];
+  __shared__ unsigned hist[256];
+  __shared__ unsigned state[2];
+  const int tid = threadIdx.x;
+  const int qi = blockIdx.x;
+  for (int i = tid; i < n_vals; i += 256) vals[i] = smax[(int64_t)qi * n_vals + i];
+  __syncthreads();
+  float t = -FLT_MAX;
+  if (k <= n_real) {   // uniform
+    const uint32_t kth = block_kth_largest<256>([&](int i) { return vals[i]; }, n_vals, k, hist, state, tid);
+    t = ordered_to_f32(kth) - eps2[qi];
+  }
+  if (tid == 0) {
+    thr[qi] = t;
     cand_cnt[qi] = 0;
     flags[qi] = 0;
   }
@@ -632,8 +670,15 @@ __global__ void __launch_bounds__(256) bucket_kernel(const uint4* __restrict__ r
 
 namespace rs {
 
+// Catalogs of 256 .. 32,768 rows (the reference's own catalog has 3,706 items): no sampling -- every tile is scored twice
+// (chunk maxima -> threshold, then the filter), both passes out of L2.  The filter's survivor path is built for RARE
+// survivors (64-record staging queue per warp and tile), so the top-k itself must be sparse in the catalog: k <= N / 128
+// (k = 10 over 3,706 rows: 0.27 %); denser requests stay on the exact scan.
+bool tensor_small_catalog(int64_t ntotal, int k) { return ntotal >= 256 && ntotal <= 32768 && ntotal >= 128ll * k; }
+
 bool tensor_path_supported(const rs_index* h, int64_t nq, int k) {
-  return h->d == DK && k >= 1 && k <= 128 && h->ntotal >= 65536 && nq >= 1 && h->ntotal <= 0x7FFFFF00ll;
+  return h->d == DK && k >= 1 && k <= 128 && (h->ntotal >= 65536 || tensor_small_catalog(h->ntotal, k)) && nq >= 1 &&
+         h->ntotal <= 0x7FFFFF00ll;
 }
 
 // flags layout of a search chunk: [0, nq) per-query "guess not verified", [nq_pad] their count, [nq_pad + 1] a staging
@@ -696,9 +741,16 @@ std::unique_ptr<rs_tc_session> tc_begin(rs_index* h, const float* qc, int cq, in
   const int nq_pad = s.nq_pad = (cq + BM - 1) / BM * BM;
   const int n_qtiles = nq_pad / BM;
   s.ntiles = (h->ntotal + BN - 1) / BN;
+  const bool small = h->ntotal < 65536;
   int64_t sample_step;
-  sample_plan(h->ntotal, &s.n_sample, &sample_step);
-  const int n_vals = s.n_vals = static_cast<int>(std::min<int64_t>(s.n_sample, 1024 / EPI_SLICES) * EPI_SLICES);
+  if (small) {
+    s.n_sample = s.ntiles;
+    sample_step = 1;
+  } else {
+    sample_plan(h->ntotal, &s.n_sample, &sample_step);
+  }
+  const int n_vals = s.n_vals = small ? static_cast<int>(s.ntiles * (BN / 32))
+                                      : static_cast<int>(std::min<int64_t>(s.n_sample, 1024 / EPI_SLICES) * EPI_SLICES);
   Workspace& ws = s.ws;
   RS_CUDA(cudaMallocAsync(&ws.qb, sizeof(uint16_t) * (size_t)nq_pad * DK, st));
   RS_CUDA(cudaMallocAsync(&ws.eps2, sizeof(float) * nq_pad, st));
@@ -740,7 +792,8 @@ std::unique_ptr<rs_tc_session> tc_begin(rs_index* h, const float* qc, int cq, in
     TcParams ps = p;
     ps.n_visit = s.n_sample;
     ps.tile_step = sample_step;
-    launch_filter<MODE_SAMPLE>(s.tq, h->tmap_bf16, ps, h->device, st);
+    if (small) launch_filter<MODE_SAMPLE_FINE>(s.tq, h->tmap_bf16, ps, h->device, st);
+    else launch_filter<MODE_SAMPLE>(s.tq, h->tmap_bf16, ps, h->device, st);
   }
   return sp;
 }
@@ -777,9 +830,14 @@ void search_tensor_device(rs_index* h, const float* q, int64_t nq, int k, int64_
     const int nq_pad = s.nq_pad;
     const unsigned rec_cap = s.rec_cap;
     Workspace& ws = s.ws;
-    const double rho = double(s.n_sample * BN) / double(h->ntotal);
-    const int rank = std::max(1, std::min(tensor_threshold_rank(k, rho), s.n_vals / 2));
-    {
+    if (h->ntotal < 65536) {
+      ProfScope prof(RS_PROF_RESCORE, st);
+      threshold_small_kernel<<<cq, 256, 0, st>>>(ws.smax, s.n_vals, static_cast<int>((h->ntotal + 31) / 32), k, ws.eps2, ws.thr,
+                                                 ws.cnt, ws.flags);
+      RS_LAUNCH_CHECK();
+    } else {
+      const double rho = double(s.n_sample * BN) / double(h->ntotal);
+      const int rank = std::max(1, std::min(tensor_threshold_rank(k, rho), s.n_vals / 2));
       ProfScope prof(RS_PROF_RESCORE, st);
       threshold_kernel<<<cq, 256, 0, st>>>(ws.smax, s.n_vals, rank, ws.thr, ws.cnt, ws.flags);
       RS_LAUNCH_CHECK();
@@ -812,6 +870,7 @@ void search_tensor_device(rs_index* h, const float* q, int64_t nq, int k, int64_
 // ---- shared-threshold search of one shard of a partitioned catalog (see rs_index_shared_begin in the header) ----
 rs_tc_session* shared_begin(rs_index* h, const float* q, int64_t nq, int k, int R, float* top, int64_t ld_top, cudaStream_t st) {
   RS_CHECK(nq <= tensor_max_queries(), "too many queries for one shared-threshold search");
+  RS_CHECK(h->ntotal >= 65536, "shared-threshold searches need shards of at least 65,536 rows");
   auto sp = tc_begin(h, q, static_cast<int>(nq), k, st);
   RS_CHECK(R >= 1 && R <= sp->n_vals, "R must be in [1, number of sample maxima]");
   ProfScope prof(RS_PROF_RESCORE, st);

@@ -261,3 +261,45 @@ def test_shared_threshold_protocol_over_simulated_shards(rs):
     assert int(need.sum()) > 0.9 * nq
     ok_rows = (need == 0).cpu().numpy()
     np.testing.assert_array_equal(I.cpu().numpy()[ok_rows], Iw[ok_rows])     # whatever verify lets through is exact
+
+
+@pytest.mark.parametrize("n,nq,k", [(3706, 4096, 10), (3706, 77, 28), (256, 5, 1), (257, 130, 2), (1000, 300, 7),
+                                    (4095, 64, 31), (16384, 64, 128), (32768, 200, 100), (20000, 1, 10)])
+def test_small_catalog_tensor_path_is_bit_exact(rs, n, nq, k):
+    """Catalogs of 256 .. 32,768 rows (the reference's own catalog: 3,706 items, BASELINE configs[0]) on the tensor path:
+    every tile scored twice, threshold = k-th largest 32-row chunk maximum minus 2 eps -- against the oracle's fp32 FMA
+    chain, bit for bit, with no query falling back to the exact scan."""
+    xb = rs.synth.make_unit_rows(n, 128, n + 1)
+    q = rs.synth.make_unit_rows(nq, 128, n + nq)
+    _check(rs, xb, q, k, expect_fallback=False)
+
+
+def test_small_catalog_ties_negative_scores_and_auto_mode(rs):
+    rng = np.random.default_rng(31)
+    base = rs.synth.make_unit_rows(1000, 128, 32)
+    xb = np.ascontiguousarray(np.tile(base, (3, 1)))             # 3,000 rows, every row 3 times: exact ties across chunks
+    q = rs.synth.make_unit_rows(33, 128, 33)
+    _check(rs, xb, q, 20)
+    # all scores negative: the zero-filled rows past the catalog (score 0) must not raise the threshold
+    d = rs.synth.make_unit_rows(1, 128, 34)
+    xb = (-np.abs(rng.standard_normal((3706, 1))).astype(np.float32) - 0.5) * d
+    _check(rs, xb.astype(np.float32), np.repeat(d, 7, axis=0), 10, expect_fallback=False)
+    # auto mode picks the tensor path for the small catalog and equals the exact scan
+    xb = rs.synth.make_unit_rows(3706, 128, 35)
+    index = rs.IndexFlatIP(128)
+    index.add(xb)
+    qq = rs.synth.make_unit_rows(500, 128, 36)
+    De, Ie = index.search(qq, 10, mode="exact")
+    Da, Ia = index.search(qq, 10, mode="auto")
+    np.testing.assert_array_equal(Ia, Ie)
+    np.testing.assert_array_equal(Da, De)
+    with pytest.raises(RuntimeError):                            # the top-k must be sparse in a small catalog: k <= rows / 128
+        index.search(qq, 100, mode="tensor")
+    Da, Ia = index.search(qq, 100, mode="auto")                  # ... auto then stays on the exact scan
+    De, Ie = index.search(qq, 100, mode="exact")
+    np.testing.assert_array_equal(Ia, Ie)
+    tiny = rs.IndexFlatIP(128)
+    tiny.add(xb[:100])
+    Dt, It = tiny.search(qq[:4], 10)                             # auto: exact scan
+    Dw, Iw = tiny.search(qq[:4], 10, mode="exact")
+    np.testing.assert_array_equal(It, Iw)
