@@ -179,6 +179,14 @@ int rs_dcn_cross_forward(const DLTensor* x0, const DLTensor* cross_w, const DLTe
                          DLTensor* out, void* stream);
 
 /*
+ * K3a' (EXTENSION -- named by the north-star, absent from the reference, so there is no reference oracle for it; the
+ * restatement it is tested against is oracle/extensions.py).  DCN-v2 matrix cross layer x_{l+1} = x0 * (x_l W_l + b_l) + x_l:
+ * the d x d product is a Dense layer (rs_dense_forward, or rs_dense_forward_x3 on the tensor cores at ranking batches);
+ * this entry is the elementwise rest, out = x0 * u + xl (one fma per element).  All f32 [B, D], rows may be strided.
+ */
+int rs_cross_v2_combine(const DLTensor* x0, const DLTensor* u, const DLTensor* xl, DLTensor* out, void* stream);
+
+/*
  * K3b. The two ranking heads on the DCN output (src/models.py:119-120,131):
  *   rating = z . w_r + b_r ;  ctr = sigmoid(z . w_c + b_c)
  *   z: f32 [B, W]; head_w: f32 [2, W] (row 0 = rating, row 1 = ctr); head_b: f32 [2];

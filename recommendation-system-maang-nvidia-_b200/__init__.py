@@ -28,6 +28,7 @@ from .models import (  # noqa: F401
 )
 from .service import RecommendationService, export_encoder_npz  # noqa: F401
 from .serving import MicroBatcher, create_app  # noqa: F401
+from .extensions import DeepCrossNetworkV2, ExtendedMultiTaskModel  # noqa: F401  (north-star extensions, no reference counterpart)
 from .catalog import build_item_index, evaluate_recall, get_item_embeddings, ranked_item_ids, save_index_artifacts  # noqa: F401
 
 __version__ = "0.1.0"

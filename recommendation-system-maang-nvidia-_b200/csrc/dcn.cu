@@ -7,6 +7,8 @@
 // warp-per-row streaming kernel (HBM-bound: D*4 bytes in, D*4 bytes out per row): each lane keeps
 // D/32 features of x0 and x_l in registers, the dot is a shuffle tree, and all layers run without
 // touching memory in between.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace {
@@ -53,6 +55,23 @@ __global__ void __launch_bounds__(256) dcn_cross_kernel(const float* __restrict_
     }
 #pragma unroll
     for (int c = 0; c < C; ++c) *(reinterpret_cast<float4*>(out + r * ldo) + lane + 32 * c) = xl[c];
+  }
+}
+
+// DCN-v2 combine (EXTENSION, not in the reference -- see rs_cross_v2_combine in the header): out = x0 * u + xl with
+// u = x_l W_l + b_l from the Dense kernels; one fused multiply-add per element, 128-bit accesses
+__global__ void __launch_bounds__(256) cross_v2_combine_kernel(const float* __restrict__ x0, int64_t ld0, const float* __restrict__ u,
+                                                               int64_t ldu, const float* __restrict__ xl, int64_t ldl,
+                                                               float* __restrict__ out, int64_t ldo, int64_t B, int chunks) {
+  const int64_t total = B * chunks;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / chunks;
+    const int c = static_cast<int>(i - r * chunks);
+    const float4 a = __ldg(reinterpret_cast<const float4*>(x0 + r * ld0) + c);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(u + r * ldu) + c);
+    const float4 d = __ldg(reinterpret_cast<const float4*>(xl + r * ldl) + c);
+    *(reinterpret_cast<float4*>(out + r * ldo) + c) =
+        make_float4(fmaf(a.x, b.x, d.x), fmaf(a.y, b.y, d.y), fmaf(a.z, b.z, d.z), fmaf(a.w, b.w, d.w));
   }
 }
 
@@ -161,6 +180,30 @@ extern "C" int rs_heads_forward(const DLTensor* z, const DLTensor* head_w, const
     heads_kernel<<<static_cast<int>(want < cap ? want : cap), threads, 0, static_cast<cudaStream_t>(stream)>>>(
         data_ptr<float>(z), ldz, (int)W, data_ptr<float>(head_w), data_ptr<float>(head_b), data_ptr<float>(rating),
         ldr, data_ptr<float>(ctr), ldc, B);
+    RS_LAUNCH_CHECK();
+  });
+}
+
+extern "C" int rs_cross_v2_combine(const DLTensor* x0, const DLTensor* u, const DLTensor* xl, DLTensor* out, void* stream) {
+  return rs::guard([&] {
+    using namespace rs;
+    const DLTensor* ts[4] = {x0, u, xl, out};
+    const char* names[4] = {"x0", "u", "xl", "out"};
+    int64_t ld[4];
+    for (int i = 0; i < 4; ++i) {
+      require(ts[i], names[i], 2, kDLFloat, 32);
+      RS_CHECK(on_device(ts[i]) && ts[i]->shape[0] == x0->shape[0] && ts[i]->shape[1] == x0->shape[1], "x0, u, xl, out must be CUDA f32 [B, D] tensors");
+      ld[i] = row_stride_2d(ts[i], names[i]);
+      RS_CHECK(ld[i] % 4 == 0, "row strides must be multiples of 4 floats");
+      require_aligned16(data_ptr<float>(ts[i]), names[i]);
+    }
+    const int64_t B = x0->shape[0], D = x0->shape[1];
+    RS_CHECK(D % 4 == 0, "D must be a multiple of 4");
+    if (B == 0 || D == 0) return;
+    const int chunks = static_cast<int>(D / 4);
+    const int blocks = static_cast<int>(std::min<int64_t>((B * chunks + 255) / 256, (int64_t)sm_count() * 16));
+    cross_v2_combine_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(data_ptr<float>(x0), ld[0], data_ptr<float>(u), ld[1],
+                                                                                  data_ptr<float>(xl), ld[2], data_ptr<float>(out), ld[3], B, chunks);
     RS_LAUNCH_CHECK();
   });
 }

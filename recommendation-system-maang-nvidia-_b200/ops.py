@@ -157,6 +157,16 @@ def dcn_cross(x0: torch.Tensor, cross_w: torch.Tensor, cross_b: torch.Tensor,
     return out
 
 
+def cross_v2_combine(x0: torch.Tensor, u: torch.Tensor, xl: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """DCN-v2 cross layer, elementwise part (EXTENSION, no reference counterpart): out = x0 * u + xl with u = x_l W + b."""
+    _require_cuda(x0, u, xl, out)
+    if out is None:
+        out = torch.empty_like(x0)
+    a, b, c, o = _lib.dl(x0), _lib.dl(u), _lib.dl(xl), _lib.dl(out)
+    _lib.check(_lib.load().rs_cross_v2_combine(a.ptr, b.ptr, c.ptr, o.ptr, _lib.stream_ptr()))
+    return out
+
+
 def heads(z: torch.Tensor, head_w: torch.Tensor, head_b: torch.Tensor):
     """K3b: rating = z.w_r + b_r, ctr = sigmoid(z.w_c + b_c) (src/models.py:119-120,131). -> ([B,1], [B,1])"""
     _require_cuda(z, head_w, head_b)
