@@ -5,8 +5,8 @@
     * extra categorical tables next to the id embeddings (age / gender / occupation codes on the user side, any integer-coded
       item feature on the item side: the columns src/preprocessing.py:47,50-52 emits and the reference model never reads).
 
-There is NO reference oracle for either: the restatement they are tested against is oracle/extensions.py (numpy, fp64,
-written from the formulas above) plus closed-form known-answer cases in tests/test_gpu_extensions.py.  Everything runs on
+There is NO reference counterpart for either: they are tested against a numpy fp64 restatement of the formulas above (test
+infrastructure, named in tests/test_gpu_extensions.py) plus closed-form known-answer cases in the same test file.  Everything runs on
 this repo's existing kernels -- the multi-table gather fused with the concat (rs_gather_concat), Dense on the fp32 tensor
 kernel from 512 rows (rs_dense_forward_x3: the D x D cross products are K = N = 256 GEMMs on tcgen05) or the FFMA kernel
 below that, rs_cross_v2_combine for the elementwise rest, rs_heads_forward -- in fp32 mode (tolerance 1e-5 of tensor scale).
@@ -132,7 +132,7 @@ class ExtendedMultiTaskModel:
         rating, ctr = ops.heads(dcn_out, hw, hb)
         return {"user_embedding": user_emb, "item_embedding": item_emb, "rating_prediction": rating, "ctr_prediction": ctr}
 
-    # weights as one dict of numpy arrays (the oracle takes the same dict)
+    # weights as one dict of numpy arrays (the test restatement takes the same dict)
     def get_weights(self) -> Dict[str, Any]:
         g = lambda layers: [tuple(layer.get_weights()) for layer in layers]   # noqa: E731
         w = {"user_embedding": self.user_embedding.get_weights()[0], "item_embedding": self.item_embedding.get_weights()[0],
