@@ -526,6 +526,7 @@ int rs_index_add(rs_index_t* h, const DLTensor* x, void* stream) {
                               st));
     if (on_host(x)) RS_CUDA(cudaStreamSynchronize(st));
     h->ntotal = need;
+    h->small_tensor_off.store(false, std::memory_order_relaxed);
     rebuild_tmaps(h);
   });
 }
@@ -556,11 +557,17 @@ int rs_index_search(rs_index_t* h, const DLTensor* q, int k, int64_t id_base, in
     } else if (mode == RS_AUTO) {
       // large catalogs: faster than the fp32 scan at every batch size (bf16 shadow = half the bytes); small (L2-resident)
       // ones: from 128 queries -- below that the scan's two launches beat the tensor path's seven (measured, config 1 shape)
-      tensor = tensor_path_supported(h, nq, k) && (h->ntotal >= 65536 || nq >= 128);
+      tensor = tensor_path_supported(h, nq, k) &&
+               (h->ntotal >= 65536 || (nq >= 128 && !h->small_tensor_off.load(std::memory_order_relaxed)));
     }
     auto run = [&](const float* qp, float* Dp, int64_t ldD, int64_t* Ip, int64_t ldI) {
-      if (tensor) search_tensor_device(h, qp, nq, k, id_base, Dp, ldD, Ip, ldI, st);
-      else search_exact_device(h, qp, nq, k, id_base, Dp, ldD, Ip, ldI, st);
+      if (tensor) {
+        search_tensor_device(h, qp, nq, k, id_base, Dp, ldD, Ip, ldI, st);
+        if (mode == RS_AUTO && h->ntotal < 65536 && 2 * h->last_fallbacks.load(std::memory_order_relaxed) >= nq)
+          h->small_tensor_off.store(true, std::memory_order_relaxed);
+      } else {
+        search_exact_device(h, qp, nq, k, id_base, Dp, ldD, Ip, ldI, st);
+      }
     };
     if (dev) {
       RS_CHECK(is_compact(q), "q must be contiguous");

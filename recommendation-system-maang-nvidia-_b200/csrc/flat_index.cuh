@@ -25,6 +25,10 @@ struct rs_index {
   // handle from several host threads are allowed (include/recsys_b200.h)
   std::atomic<int64_t> last_fallbacks{0};
   std::atomic<int64_t> total_fallbacks{0};
+  // AUTO mode on a small catalog: set when a tensor-path search had to repeat most of its queries on the exact scan (scores
+  // packed inside the filter margin, e.g. item embeddings that all point the same way) -- AUTO then stays on the scan until
+  // rows are added; an explicit RS_TENSOR_BF16 request still tries
+  std::atomic<bool> small_tensor_off{false};
   std::mutex mu;                 // serialises add / shadow build
 };
 

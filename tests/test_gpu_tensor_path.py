@@ -303,3 +303,31 @@ def test_small_catalog_ties_negative_scores_and_auto_mode(rs):
     Dt, It = tiny.search(qq[:4], 10)                             # auto: exact scan
     Dw, Iw = tiny.search(qq[:4], 10, mode="exact")
     np.testing.assert_array_equal(It, Iw)
+
+
+def test_small_degenerate_catalog_auto_mode_stays_exact_and_fast(rs):
+    """Item embeddings that all point the same way pack every score inside the bf16 filter's margin: the small-catalog
+    tensor path repeats its queries on the exact scan (results stay exact); AUTO notices and stays on the scan until rows
+    are added; an explicit tensor request still tries."""
+    rng = np.random.default_rng(41)
+    centre = rs.synth.make_unit_rows(1, 128, 42)
+    xb = (centre + 1e-4 * rng.standard_normal((3706, 128))).astype(np.float32)
+    q = rs.synth.make_unit_rows(256, 128, 43)
+    index = rs.IndexFlatIP(128)
+    index.add(xb)
+    De, Ie = index.search(q, 10, mode="exact")
+    total0 = index.fallbacks()[1]
+    D1, I1 = index.search(q, 10)                      # AUTO: tries the tensor path, falls back
+    np.testing.assert_array_equal(I1, Ie)
+    np.testing.assert_array_equal(D1, De)
+    total1 = index.fallbacks()[1]
+    assert total1 > total0
+    D2, I2 = index.search(q, 10)                      # AUTO again: straight to the exact scan, no new fallbacks
+    np.testing.assert_array_equal(I2, Ie)
+    assert index.fallbacks()[1] == total1
+    index.search(q, 10, mode="tensor")                # explicit request: tries again
+    assert index.fallbacks()[1] > total1
+    index.add(rs.synth.make_unit_rows(300, 128, 44))  # new rows: AUTO gives the tensor path another chance
+    t2 = index.fallbacks()[1]
+    index.search(q, 10)
+    assert index.fallbacks()[1] > t2
