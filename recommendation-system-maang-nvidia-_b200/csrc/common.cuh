@@ -290,4 +290,67 @@ __device__ __forceinline__ void block_sort_desc(uint64_t* a, int tid) {
   }
 }
 
+// Block-wide radix select: the k-th largest (1-based, k <= n) of the n 32-bit values v(0..n-1).  Four 8-bit passes
+// from the top byte; per pass a shared-memory histogram and a one-warp scan.  12 barriers in total (a bitonic
+// sort of 1024 keys needs 55), which is what matters for these latency-bound per-query kernels.
+template <int NT, class F>
+__device__ __forceinline__ uint32_t block_kth_largest(F v, int n, int k, unsigned* hist /*[256]*/,
+                                                      unsigned* state /*[2]*/, int tid) {
+  uint32_t prefix = 0, mask = 0;
+  unsigned kk = static_cast<unsigned>(k);
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    for (int i = tid; i < 256; i += NT) hist[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += NT) {
+      const uint32_t x = v(i);
+      if ((x & mask) == prefix) atomicAdd(&hist[(x >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (tid < 32) {   // lane L owns bins 255-8L .. 248-8L (descending), prefix-summed over lanes
+      unsigned loc[8], sum = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        loc[j] = hist[255 - (tid * 8 + j)];
+        sum += loc[j];
+      }
+      unsigned incl = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (tid >= o) incl += t;
+      }
+      const unsigned excl = incl - sum;
+      if (excl < kk && kk <= incl) {
+        unsigned run = excl;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (run < kk && kk <= run + loc[j]) {
+            state[0] = 255u - (tid * 8 + j);
+            state[1] = kk - run;
+          }
+          run += loc[j];
+        }
+      }
+    }
+    __syncthreads();
+    prefix |= state[0] << shift;
+    mask |= 0xFFu << shift;
+    kk = state[1];
+  }
+  return prefix;
+}
+
+
+// CTA-wide descending sort of a[0..n_pow2) for the smallest power of two >= n (entries past n must hold kEmptyKey up to it):
+// the latency of these sorts is barriers, so short lists get short sorts
+template <int CAP, int NT>
+__device__ __forceinline__ void block_sort_desc_upto(uint64_t* a, int n, int tid) {
+  if (CAP >= 4096 && n > 2048) block_sort_desc<(CAP >= 4096 ? 4096 : CAP), NT>(a, tid);
+  else if (CAP >= 2048 && n > 1024) block_sort_desc<(CAP >= 2048 ? 2048 : CAP), NT>(a, tid);
+  else if (CAP >= 1024 && n > 512) block_sort_desc<(CAP >= 1024 ? 1024 : CAP), NT>(a, tid);
+  else if (CAP >= 512 && n > 256) block_sort_desc<(CAP >= 512 ? 512 : CAP), NT>(a, tid);
+  else if (CAP >= 256 && n > 128) block_sort_desc<(CAP >= 256 ? 256 : CAP), NT>(a, tid);
+  else block_sort_desc<(CAP >= 128 ? 128 : CAP), NT>(a, tid);
+}
+
 }  // namespace rsd

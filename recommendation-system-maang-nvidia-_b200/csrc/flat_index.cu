@@ -18,6 +18,8 @@
 // the all-gather) in rank-major order with early termination.
 #include <algorithm>
 #include <cfloat>
+#include <cstdlib>
+#include <mutex>
 
 #include "flat_index.cuh"
 #include "peer.cuh"
@@ -162,6 +164,238 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
 }
 
 // ------------------------------------------------------------------------------------------------
+// scan_bf16_topk_kernel -- the same scan for ONE or TWO queries (the /recommendations path, BASELINE configs[4]) at half
+// the bytes: the catalog is read from the bf16 shadow (what the tensor path keeps anyway); a CTA keeps every row whose
+// low-precision score is within 2 eps of its running k-th low-precision score (eps = c |q| max|x| bounds |s_hat - s|, as
+// in tc_filter.cu), and when its part of the catalog is done re-scores those few rows from the fp32 catalog with the
+// stated FMA chain and emits its exact top-k.  Every row of a CTA's true top-k has s_hat >= s_hat_(k) - 2 eps (the tensor
+// path's argument), so the emitted lists -- and after the merge the results -- are bit-identical to scan_topk_kernel's.
+// Two launches per search (scan, merge) against the tensor path's seven: at batch 1 the launches, not the bytes, were
+// most of the step on a shard of an 8-way split catalog.  A first version re-scored candidates inline: ~80 dependent
+// global loads per CTA, each stalling the whole CTA at the per-tile barrier, made it slower than the fp32 scan.
+// A CTA whose margin holds more rows than its buffer (scores packed inside 2 eps: degenerate catalogs) raises ovf[query];
+// the caller then repeats that query on the fp32 scan.
+// ------------------------------------------------------------------------------------------------
+constexpr int BSCAN_STAGES = 3;
+constexpr int BSCAN_ROWS = 256;                          // rows per stage == threads: 8 warps hide the dot product's latency
+constexpr int BSCAN_NT = 256;
+constexpr int BSCAN_STAGE_BYTES = BSCAN_ROWS * 128 * 2;  // [256 rows x 128 bf16] as two 128-byte-swizzled [256 x 64] boxes
+constexpr int BSCAN_CAP = 1024;                          // candidate buffer per query
+constexpr int BSCAN_SOFT = 512;                          // prune as soon as this many are held: the first prune (after two
+                                                         // tiles) sets the cut, and the sorts stay short; a prune must leave
+                                                         // room for one tile below it, and two tiles fit above it
+
+template <int QT>
+struct BScanSmem {
+  static constexpr int kKeysOff = BSCAN_STAGES * BSCAN_STAGE_BYTES;
+  static constexpr int kQOff = kKeysOff + QT * BSCAN_CAP * 8;
+  static constexpr int kBarOff = kQOff + QT * 128 * 4;
+  static constexpr int kCntOff = kBarOff + BSCAN_STAGES * 8;
+  static constexpr int kEpsOff = kCntOff + QT * 4;
+  static constexpr int kTotal = kEpsOff + QT * 4 + 16;
+  static constexpr int kDynamic = kTotal + 1024;
+};
+
+// Collective.  Sorts the buffer (descending), keeps every entry whose score is within eps2 of the k-th (all entries while
+// fewer than k are held), returns the new k-th key (kEmptyKey while fewer than k).  *cnt = entries kept; more than
+// CAP - 2 tiles' worth: *ovf = 1 and only the best k are kept (the list is no longer trusted).
+__device__ __forceinline__ uint64_t prune_margin(uint64_t* keys, int* cnt, int* kept, int k, float eps2, int* ovf, int tid) {
+  const int n_valid = min(*cnt, BSCAN_CAP);
+  for (int i = n_valid + tid; i < BSCAN_CAP; i += BSCAN_NT) keys[i] = kEmptyKey;
+  if (tid == 0) *kept = 0;
+  __syncthreads();
+  block_sort_desc_upto<BSCAN_CAP, BSCAN_NT>(keys, n_valid, tid);
+  uint64_t thr = kEmptyKey;
+  int m = n_valid;
+  if (n_valid >= k) {   // uniform
+    thr = keys[k - 1];
+    const float cutv = key_score(thr) - eps2;
+    int mine = 0;
+    for (int i = tid; i < n_valid; i += BSCAN_NT) mine += key_score(keys[i]) >= cutv ? 1 : 0;
+    if (mine) atomicAdd(kept, mine);
+    __syncthreads();
+    m = *kept;
+    if (m > BSCAN_SOFT - BSCAN_ROWS) {
+      if (tid == 0) *ovf = 1;
+      m = k;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) *cnt = m;
+  __syncthreads();
+  return thr;
+}
+
+template <int QT>
+__global__ void __launch_bounds__(BSCAN_NT, 1)
+scan_bf16_topk_kernel(const __grid_constant__ CUtensorMap tmap16, const float* __restrict__ xb, const float* __restrict__ q,
+                      int64_t n, int nq, int k, float eps_scale, uint64_t* __restrict__ partial, int* __restrict__ ovf) {
+  using L = BScanSmem<QT>;
+  constexpr int D = 128;
+  constexpr int CAP = BSCAN_CAP;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* keys = reinterpret_cast<uint64_t*>(base + L::kKeysOff);
+  float* qs = reinterpret_cast<float*>(base + L::kQOff);
+  uint64_t* full = reinterpret_cast<uint64_t*>(base + L::kBarOff);
+  int* cnt = reinterpret_cast<int*>(base + L::kCntOff);
+  float* eps_s = reinterpret_cast<float*>(base + L::kEpsOff);   // [QT] 2 eps
+  int* kept = reinterpret_cast<int*>(eps_s + QT);               // scratch of prune_margin
+
+  const int tid = threadIdx.x;
+  const int64_t ntiles = (n + BSCAN_ROWS - 1) / BSCAN_ROWS;
+  const int64_t my_tiles = (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tmap16);
+    for (int s = 0; s < BSCAN_STAGES; ++s) mbar_init(&full[s], 1);
+    fence_mbar_init();
+  }
+  for (int i = tid; i < QT * D; i += BSCAN_NT) {
+    const int g = i / D;
+    qs[i] = (g < nq) ? q[(int64_t)g * D + (i - g * D)] : 0.0f;
+  }
+  for (int i = tid; i < QT * CAP; i += BSCAN_NT) keys[i] = kEmptyKey;
+  if (tid < QT) cnt[tid] = 0;
+  __syncthreads();
+  if (tid < 32) {   // 2 eps_g = 2 eps_scale |q_g| (a hair above: the norm is rounded up)
+    for (int g = 0; g < QT; ++g) {
+      float s = 0.0f;
+      for (int i = tid; i < D; i += 32) s = fmaf(qs[g * D + i], qs[g * D + i], s);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+      if (tid == 0) eps_s[g] = 2.0f * eps_scale * (sqrtf(s) * 1.00001f);
+    }
+  }
+  __syncthreads();
+
+  auto issue = [&](int stage, int64_t it) {
+    const int64_t tile = blockIdx.x + it * gridDim.x;
+    mbar_arrive_expect_tx(&full[stage], BSCAN_STAGE_BYTES);
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+      tma_load_2d(base + stage * BSCAN_STAGE_BYTES + h * (BSCAN_ROWS * 128), &tmap16, &full[stage], h * 64,
+                  static_cast<int>(tile * BSCAN_ROWS), kEvictFirst);
+  };
+  if (tid == 0)
+    for (int s = 0; s < BSCAN_STAGES && s < my_tiles; ++s) issue(s, s);
+
+  float cut[QT];        // keep rows with s_hat >= cut = (running k-th s_hat) - 2 eps (-inf until k rows are held)
+  float eps2[QT];
+#pragma unroll
+  for (int g = 0; g < QT; ++g) {
+    cut[g] = -INFINITY;
+    eps2[g] = eps_s[g];
+  }
+
+  const uint32_t sw = static_cast<uint32_t>(tid & 7) << 4;
+  for (int64_t it = 0; it < my_tiles; ++it) {
+    const int stage = static_cast<int>(it % BSCAN_STAGES);
+    mbar_wait(&full[stage], static_cast<uint32_t>((it / BSCAN_STAGES) & 1));
+
+    // ---- low-precision score of row `tid`: bf16 row x fp32 query, fp32 accumulation ----
+    // four partial sums per query: the order of a low-precision score does not matter, the latency of one 128-long chain does
+    float a4[QT][4];
+#pragma unroll
+    for (int g = 0; g < QT; ++g)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) a4[g][u] = 0.0f;
+    const uint8_t* srow = base + stage * BSCAN_STAGE_BYTES + tid * 128;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint4 xv = *reinterpret_cast<const uint4*>(srow + h * (BSCAN_ROWS * 128) + ((c << 4) ^ sw));
+        const uint32_t w[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+        for (int g = 0; g < QT; ++g) {
+          const float4 qa = *reinterpret_cast<const float4*>(qs + g * D + h * 64 + c * 8);
+          const float4 qb = *reinterpret_cast<const float4*>(qs + g * D + h * 64 + c * 8 + 4);
+          a4[g][0] = fmaf(qa.x, __uint_as_float(w[0] << 16), a4[g][0]);
+          a4[g][1] = fmaf(qa.y, __uint_as_float(w[0] & 0xFFFF0000u), a4[g][1]);
+          a4[g][2] = fmaf(qa.z, __uint_as_float(w[1] << 16), a4[g][2]);
+          a4[g][3] = fmaf(qa.w, __uint_as_float(w[1] & 0xFFFF0000u), a4[g][3]);
+          a4[g][0] = fmaf(qb.x, __uint_as_float(w[2] << 16), a4[g][0]);
+          a4[g][1] = fmaf(qb.y, __uint_as_float(w[2] & 0xFFFF0000u), a4[g][1]);
+          a4[g][2] = fmaf(qb.z, __uint_as_float(w[3] << 16), a4[g][2]);
+          a4[g][3] = fmaf(qb.w, __uint_as_float(w[3] & 0xFFFF0000u), a4[g][3]);
+        }
+      }
+    }
+    float acc[QT];
+#pragma unroll
+    for (int g = 0; g < QT; ++g) acc[g] = (a4[g][0] + a4[g][1]) + (a4[g][2] + a4[g][3]);
+
+    // ---- rows inside the margin go to the candidate buffer with their low-precision key ----
+    const int64_t row = (blockIdx.x + it * gridDim.x) * BSCAN_ROWS + tid;
+    uint32_t pend = 0;
+#pragma unroll
+    for (int g = 0; g < QT; ++g)
+      if (row < n && g < nq && acc[g] >= cut[g]) pend |= 1u << g;
+    for (;;) {
+      bool saw_full = false;
+#pragma unroll
+      for (int g = 0; g < QT; ++g) {
+        if (pend & (1u << g)) {
+          const int pos = atomicAdd(&cnt[g], 1);
+          if (pos < CAP) {
+            keys[g * CAP + pos] = pack_key(acc[g], static_cast<uint32_t>(row));
+            pend &= ~(1u << g);
+          }
+          saw_full |= pos >= BSCAN_SOFT - 1;
+        }
+      }
+      // this barrier also orders every thread's reads of the stage before the refill below
+      if (!__syncthreads_or(pend != 0 || saw_full)) break;
+#pragma unroll
+      for (int g = 0; g < QT; ++g) {
+        if (cnt[g] >= BSCAN_SOFT) {  // uniform: nobody touches cnt between the barrier and the prune
+          const uint64_t thr = prune_margin(keys + g * CAP, &cnt[g], kept, k, eps2[g], ovf + g, tid);
+          if (thr != kEmptyKey) cut[g] = key_score(thr) - eps2[g];
+          if ((pend & (1u << g)) && !(acc[g] >= cut[g])) pend &= ~(1u << g);
+        }
+      }
+      __syncthreads();
+    }
+    if (tid == 0 && it + BSCAN_STAGES < my_tiles) issue(stage, it + BSCAN_STAGES);
+  }
+
+  // ---- exact scores of the kept rows (fp32 catalog, the stated chain: one accumulator, k ascending), exact order, emit ----
+  const int P = gridDim.x;
+#pragma unroll 1
+  for (int g = 0; g < QT; ++g) {
+    if (g >= nq) break;
+    uint64_t* kg = keys + g * CAP;
+    prune_margin(kg, &cnt[g], kept, k, eps2[g], ovf + g, tid);
+    const int m = cnt[g];
+    for (int i = tid; i < CAP; i += BSCAN_NT) {
+      uint64_t key = kEmptyKey;
+      if (i < m) {
+        const uint32_t r = key_row(kg[i]);
+        const float4* xr = reinterpret_cast<const float4*>(xb + static_cast<int64_t>(r) * D);
+        float ex = 0.0f;
+#pragma unroll 16
+        for (int c4 = 0; c4 < D / 4; ++c4) {
+          const float4 xv = __ldg(xr + c4);
+          const float4 qv = *reinterpret_cast<const float4*>(qs + g * D + c4 * 4);
+          ex = fmaf(qv.x, xv.x, ex);
+          ex = fmaf(qv.y, xv.y, ex);
+          ex = fmaf(qv.z, xv.z, ex);
+          ex = fmaf(qv.w, xv.w, ex);
+        }
+        key = pack_key(ex, r);
+      }
+      kg[i] = key;
+    }
+    __syncthreads();
+    block_sort_desc_upto<CAP, BSCAN_NT>(kg, m, tid);
+    uint64_t* dst = partial + ((int64_t)g * P + blockIdx.x) * k;
+    for (int j = tid; j < k; j += BSCAN_NT) dst[j] = kg[j];
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // merge of sorted lists.  Source A: packed keys [nq][P][k] (rows local to the index).
 // Source B: (score, id) pairs [P][nq][k] (global ids, -1 = padding) after an all-gather.
 // ------------------------------------------------------------------------------------------------
@@ -297,6 +531,101 @@ __global__ void __launch_bounds__(128) matvec_kernel(const float* __restrict__ i
   out[r] = acc;
 }
 
+// The same merge for short inputs (P * k <= 4096 keys, k <= 128: the batch-1 path, 148 lists of 10, or 8 shards' lists of
+// 100) without a sort: the lists are sorted, so the element at position r - 1 of a list has r elements at or above it.  With
+// r = ceil(k / P) and m = ceil(k / r), tau = the m-th largest of those elements has m r >= k elements at or above it, hence
+// the k-th largest key overall is >= tau and only keys >= tau can be in the result: a handful, ranked by counting.
+// merge_topk_kernel's rounds of offer / prune cost ~13 us here -- a fifth of the whole catalog scan of a shard; a bitonic
+// sort of all keys 25 us; a radix select 11 us (a thousand shared-memory atomics on two or three histogram bins).
+constexpr int SMALL_MERGE_KEYS = 4096;
+constexpr int SMALL_MERGE_TOP = 512;
+__global__ void __launch_bounds__(MERGE_NT)
+merge_small_kernel(const KeySource src, int P, int k, int64_t id_base, float* __restrict__ D, int64_t ldD,
+                   int64_t* __restrict__ I, int64_t ldI, const MergeExtras ex) {
+  __shared__ uint64_t all[SMALL_MERGE_KEYS];
+  __shared__ uint64_t top[SMALL_MERGE_TOP];
+  __shared__ uint64_t tau_s, kth_s;
+  __shared__ int n_top;
+  const int tid = threadIdx.x;
+  const int64_t qi = blockIdx.x;
+  uint64_t seq = 0;
+  if (ex.peer_bases) seq = rsp::peer_arrived(ex.peer_bases[ex.PL.rank], ex.PL);
+  const int total = P * k;
+  if (tid == 0) {
+    n_top = 0;
+    tau_s = kEmptyKey;
+    kth_s = kEmptyKey;
+  }
+  for (int e = tid; e < total; e += MERGE_NT) {
+    const int p = e / k, r = e - p * k;
+    all[e] = src.load(qi, p, P, r, k);
+  }
+  __syncthreads();
+  const int r = (k + P - 1) / P;
+  const int m = (k + r - 1) / r;                   // <= P
+  for (int p = tid; p < P; p += MERGE_NT) {        // rank of list p's element r - 1 among the P of them (keys are distinct
+    const uint64_t mine = all[p * k + r - 1];      // except for padding, which ranks last in any order)
+    int rank = 0;
+    for (int o = 0; o < P; ++o) {
+      const uint64_t other = all[o * k + r - 1];
+      rank += (other > mine || (other == mine && o < p)) ? 1 : 0;
+    }
+    if (rank == m - 1) tau_s = mine;
+  }
+  __syncthreads();
+  const uint64_t tau = tau_s;
+  for (int e = tid; e < total; e += MERGE_NT) {
+    const uint64_t key = all[e];
+    if (key != kEmptyKey && key >= tau) {
+      const int pos = atomicAdd(&n_top, 1);
+      if (pos < SMALL_MERGE_TOP) top[pos] = key;
+    }
+  }
+  __syncthreads();
+  int nt = n_top;
+  if (nt > SMALL_MERGE_TOP) {   // uniform; lists that are near copies of each other: sort everything (slow, rare)
+    int pow2 = 128;
+    while (pow2 < total) pow2 <<= 1;
+    for (int e = total + tid; e < pow2; e += MERGE_NT) all[e] = kEmptyKey;
+    __syncthreads();
+    block_sort_desc_upto<SMALL_MERGE_KEYS, MERGE_NT>(all, total, tid);
+    for (int j = tid; j < k; j += MERGE_NT) {
+      const uint64_t key = j < total ? all[j] : kEmptyKey;
+      D[qi * ldD + j] = key == kEmptyKey ? -FLT_MAX : key_score(key);
+      I[qi * ldI + j] = key == kEmptyKey ? -1 : id_base + static_cast<int64_t>(key_row(key));
+      if (j == k - 1) kth_s = key;
+    }
+  } else {
+    for (int j = nt + tid; j < k; j += MERGE_NT) {   // fewer than k real keys in all lists together: padding
+      D[qi * ldD + j] = -FLT_MAX;
+      I[qi * ldI + j] = -1;
+    }
+    for (int c = tid; c < nt; c += MERGE_NT) {
+      const uint64_t mine = top[c];
+      int rank = 0;
+      for (int o = 0; o < nt; ++o) rank += top[o] > mine ? 1 : 0;
+      if (rank < k) {
+        D[qi * ldD + rank] = key_score(mine);
+        I[qi * ldI + rank] = id_base + static_cast<int64_t>(key_row(mine));
+        if (rank == k - 1) kth_s = mine;
+      }
+    }
+  }
+  __syncthreads();
+  if (ex.need_exact && tid == 0) {   // verify_topk_kernel's verdict for this query
+    float b = -INFINITY;
+    int f = 0;
+    for (int g = 0; g < P; ++g) {
+      if (ex.bounds) b = fmaxf(b, ex.bounds[g * ex.ld_b + qi]);
+      f |= ex.flags[g * ex.ld_f + qi];
+    }
+    const uint64_t kthk = kth_s;
+    const bool ok = f == 0 && (!ex.bounds || (kthk != kEmptyKey && key_score(kthk) >= b));
+    ex.need_exact[qi] = ok ? 0 : 1;
+  }
+  if (ex.peer_bases) rsp::peer_consumed(ex.peer_bases, ex.PL, seq);
+}
+
 template <int CAP>
 void launch_merge(const KeySource& src, int64_t nq, int P, int k, int64_t id_base, float* D, int64_t ldD, int64_t* I,
                   int64_t ldI, cudaStream_t st, const MergeExtras& ex) {
@@ -309,6 +638,12 @@ void merge_dispatch(const KeySource& src, int64_t nq, int P, int k, int64_t id_b
                     int64_t ldI, cudaStream_t st, const MergeExtras& ex = MergeExtras{}) {
   RS_CHECK(k >= 1 && k <= 1024, "k must be in [1, 1024]");
   RS_CHECK(nq <= 0x7FFFFFFF, "too many queries");
+  if (k <= 128 && (int64_t)P * k <= SMALL_MERGE_KEYS && nq <= 64) {   // few queries, short lists: the latency path
+    rs::ProfScope prof(RS_PROF_MERGE, st);
+    merge_small_kernel<<<static_cast<unsigned>(nq), MERGE_NT, 0, st>>>(src, P, k, id_base, D, ldD, I, ldI, ex);
+    RS_LAUNCH_CHECK();
+    return;
+  }
   if (k <= 128) launch_merge<256>(src, nq, P, k, id_base, D, ldD, I, ldI, st, ex);
   else if (k <= 256) launch_merge<512>(src, nq, P, k, id_base, D, ldD, I, ldI, st, ex);
   else if (k <= 512) launch_merge<1024>(src, nq, P, k, id_base, D, ldD, I, ldI, st, ex);
@@ -406,6 +741,66 @@ void search_exact_device(rs_index* h, const float* q, int64_t nq, int k, int64_t
     throw;
   }
   RS_CUDA(cudaFreeAsync(partial, st));
+}
+
+// exact top-k of one or two queries through the bf16 shadow (scan_bf16_topk_kernel); same results as search_exact_device
+bool bf16_scan_applies(const rs_index* h, int64_t nq, int k) {
+  static const bool on = [] { const char* e = getenv("RS_BF16_SCAN"); return !(e && e[0] == '0'); }();
+  return on && h->d == 128 && nq >= 1 && nq <= 2 && k >= 1 && k <= 128 && h->ntotal >= 65536 && h->ntotal <= 0x7FFFFF00ll;
+}
+
+template <int QT>
+static void launch_bscan(const rs_index* h, const CUtensorMap& tm, const float* q, int nq, int k, int P, float eps_scale,
+                         uint64_t* partial, int* ovf, cudaStream_t st) {
+  using L = BScanSmem<QT>;
+  static std::once_flag once[64];
+  std::call_once(once[h->device & 63], [] {
+    cudaFuncSetAttribute(scan_bf16_topk_kernel<QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic);
+  });
+  rs::ProfScope prof(RS_PROF_SCAN, st);
+  scan_bf16_topk_kernel<QT><<<P, BSCAN_NT, L::kDynamic, st>>>(tm, h->xb, q, h->ntotal, nq, k, eps_scale, partial, ovf);
+  RS_LAUNCH_CHECK();
+}
+
+// need_exact != nullptr (device int32 [nq]): receives the per-query "margin overflowed, list not trusted" flags, nothing is
+// synchronised.  nullptr: the flags are read back (one stream synchronise) and flagged queries repeated on the fp32 scan.
+void search_bf16_scan_device(rs_index* h, const float* q, int64_t nq, int k, int64_t id_base, float* D, int64_t ldD, int64_t* I,
+                             int64_t ldI, cudaStream_t st, int* need_exact) {
+  RS_CHECK(bf16_scan_applies(h, nq, k), "the bf16-shadow scan serves 1-2 queries, d = 128, k <= 128, >= 65,536 rows");
+  ensure_tensor_shadow(h, st);
+  const int64_t ntiles = (h->ntotal + BSCAN_ROWS - 1) / BSCAN_ROWS;
+  const int P = static_cast<int>(std::min<int64_t>(ntiles, sm_count()));
+  const CUtensorMap& tm = h->tmap_bf16;   // box [256 rows, 64 bf16], 128-byte swizzle: the tensor path's own map
+  // |s_hat - s| <= 2^-9 |q| |x| for bf16-rounded rows and fp32 queries; the tensor path's constant (both operands rounded,
+  // 6 % slack for the fp32 accumulations) is used unchanged
+  const float eps_scale = 0.00390625f * 1.0625f * h->max_norm;
+  uint64_t* partial = nullptr;
+  int* ovf = nullptr;
+  RS_CUDA(cudaMallocAsync(&partial, sizeof(uint64_t) * (size_t)nq * P * k + 16, st));
+  ovf = need_exact ? need_exact : reinterpret_cast<int*>(partial + (size_t)nq * P * k);
+  int h_ovf[2] = {0, 0};
+  try {
+    RS_CUDA(cudaMemsetAsync(ovf, 0, sizeof(int) * static_cast<size_t>(nq), st));
+    if (nq == 1) launch_bscan<1>(h, tm, q, 1, k, P, eps_scale, partial, ovf, st);
+    else launch_bscan<2>(h, tm, q, 2, k, P, eps_scale, partial, ovf, st);
+    KeySource src{partial, nullptr, nullptr, nq};
+    merge_dispatch(src, nq, P, k, id_base, D, ldD, I, ldI, st);
+    if (!need_exact) RS_CUDA(cudaMemcpyAsync(h_ovf, ovf, sizeof(int) * static_cast<size_t>(nq), cudaMemcpyDeviceToHost, st));
+  } catch (...) {
+    cudaFreeAsync(partial, st);
+    throw;
+  }
+  RS_CUDA(cudaFreeAsync(partial, st));
+  if (need_exact) return;
+  RS_CUDA(cudaStreamSynchronize(st));
+  int fb = 0;
+  for (int64_t i = 0; i < nq; ++i)
+    if (h_ovf[i]) {
+      search_exact_device(h, q + i * h->d, 1, k, id_base, D + i * ldD, ldD, I + i * ldI, ldI, st);
+      ++fb;
+    }
+  h->last_fallbacks.store(fb, std::memory_order_relaxed);
+  h->total_fallbacks.fetch_add(fb, std::memory_order_relaxed);
 }
 
 }  // namespace rs

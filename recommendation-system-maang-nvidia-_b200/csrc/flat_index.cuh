@@ -79,6 +79,12 @@ void search_tensor_device(rs_index* h, const float* q, int64_t nq, int k, int64_
                           int64_t* I, int64_t ldI, cudaStream_t st, int* need_exact = nullptr);
 // every low-precision score of the tensor path, out [nq, ntotal] (validation of the tcgen05 tiles)
 void tensor_scores_debug(rs_index* h, const float* q, int64_t nq, float* out, cudaStream_t st);
+// one or two queries: exact top-k through the bf16 shadow, two launches (flat_index.cu); same results as the exact scan
+bool bf16_scan_applies(const rs_index* h, int64_t nq, int k);
+void search_bf16_scan_device(rs_index* h, const float* q, int64_t nq, int k, int64_t id_base, float* D, int64_t ldD, int64_t* I,
+                             int64_t ldI, cudaStream_t st, int* need_exact = nullptr);
+// builds / refreshes the bf16 shadow and max row norm of the index (tc_filter.cu)
+void ensure_tensor_shadow(rs_index* h, cudaStream_t st);
 // true when the tensor path is applicable to this shape (d, k, sizes)
 bool tensor_path_supported(const rs_index* h, int64_t nq, int k);
 

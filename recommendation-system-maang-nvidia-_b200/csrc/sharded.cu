@@ -212,7 +212,10 @@ void search_step(rs_index* shard, rs_comm* c, SearchPlan* p, int64_t n_total, co
   int* sF = reinterpret_cast<int*>(p->send + L.off_F);
   float* sB = reinterpret_cast<float*>(p->send + L.off_B);
   const bool tensor_ok = mode != RS_EXACT_FP32 && tensor_path_supported(shard, nq, k) && nq <= tensor_max_queries();
-  const int rank = (mode != RS_EXACT_FP32) ? shared_rank(c, shard->d, n_total, nq, k) : 0;
+  // one or two queries: every shard's own two-launch scan through its bf16 shadow beats the shared-threshold protocol (one
+  // exchange and five launches fewer); the lists exchange + merge below is the same
+  const bool tiny = tensor_ok && bf16_scan_applies(shard, nq, k);
+  const int rank = (mode != RS_EXACT_FP32 && !tiny) ? shared_rank(c, shard->d, n_total, nq, k) : 0;
   const bool shared = rank > 0 && p->tops != nullptr && p->rank_pad >= round_up(rank, 4);
   if (shared) {
     const int R = static_cast<int>(round_up(rank, 4));

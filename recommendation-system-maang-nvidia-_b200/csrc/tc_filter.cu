@@ -365,56 +365,6 @@ __global__ void __launch_bounds__(128) prep_queries_kernel(const float* __restri
   if (lane == 0) eps2[row] = 2.0f * C_EPS * (sqrtf(s) * 1.00001f) * __uint_as_float(*max_norm_bits);
 }
 
-// Block-wide radix select: the k-th largest (1-based, k <= n) of the n 32-bit values v(0..n-1).  Four 8-bit passes
-// from the top byte; per pass a shared-memory histogram and a one-warp scan.  12 barriers in total (a bitonic
-// sort of 1024 keys needs 55), which is what matters for these latency-bound per-query kernels.
-template <int NT, class F>
-__device__ __forceinline__ uint32_t block_kth_largest(F v, int n, int k, unsigned* hist /*[256]*/,
-                                                      unsigned* state /*[2]*/, int tid) {
-  uint32_t prefix = 0, mask = 0;
-  unsigned kk = static_cast<unsigned>(k);
-  for (int shift = 24; shift >= 0; shift -= 8) {
-    for (int i = tid; i < 256; i += NT) hist[i] = 0;
-    __syncthreads();
-    for (int i = tid; i < n; i += NT) {
-      const uint32_t x = v(i);
-      if ((x & mask) == prefix) atomicAdd(&hist[(x >> shift) & 255u], 1u);
-    }
-    __syncthreads();
-    if (tid < 32) {   // lane L owns bins 255-8L .. 248-8L (descending), prefix-summed over lanes
-      unsigned loc[8], sum = 0;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        loc[j] = hist[255 - (tid * 8 + j)];
-        sum += loc[j];
-      }
-      unsigned incl = sum;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const unsigned t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-        if (tid >= o) incl += t;
-      }
-      const unsigned excl = incl - sum;
-      if (excl < kk && kk <= incl) {
-        unsigned run = excl;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (run < kk && kk <= run + loc[j]) {
-            state[0] = 255u - (tid * 8 + j);
-            state[1] = kk - run;
-          }
-          run += loc[j];
-        }
-      }
-    }
-    __syncthreads();
-    prefix |= state[0] << shift;
-    mask |= 0xFFu << shift;
-    kk = state[1];
-  }
-  return prefix;
-}
-
 // tau_q = the `rank`-th largest of the query's sample maxima; also clears the candidate counters
 __global__ void __launch_bounds__(256) threshold_kernel(const unsigned* __restrict__ smax, int n_vals, int rank,
                                                         float* __restrict__ thr, int* __restrict__ cand_cnt,
@@ -676,6 +626,8 @@ namespace rs {
 // (k = 10 over 3,706 rows: 0.27 %); denser requests stay on the exact scan.
 bool tensor_small_catalog(int64_t ntotal, int k) { return ntotal >= 256 && ntotal <= 32768 && ntotal >= 128ll * k; }
 
+void ensure_tensor_shadow(rs_index* h, cudaStream_t st) { ensure_shadow(h, st); }
+
 bool tensor_path_supported(const rs_index* h, int64_t nq, int k) {
   return h->d == DK && k >= 1 && k <= 128 && (h->ntotal >= 65536 || tensor_small_catalog(h->ntotal, k)) && nq >= 1 &&
          h->ntotal <= 0x7FFFFF00ll;
@@ -820,6 +772,10 @@ void tc_finish(rs_tc_session& s, int64_t id_base, float* D, int64_t ldD, int64_t
 void search_tensor_device(rs_index* h, const float* q, int64_t nq, int k, int64_t id_base, float* D, int64_t ldD,
                           int64_t* I, int64_t ldI, cudaStream_t st, int* need_exact) {
   RS_CHECK(tensor_path_supported(h, nq, k), "tensor path does not apply to this shape");
+  if (bf16_scan_applies(h, nq, k)) {   // batch-1 / batch-2: two launches instead of seven, same bytes, always exact
+    search_bf16_scan_device(h, q, nq, k, id_base, D, ldD, I, ldI, st, need_exact);
+    return;
+  }
   // query chunks so that every CTA group gets at least one SM
   const int64_t max_chunk = tensor_max_queries();
   for (int64_t q0 = 0; q0 < nq; q0 += max_chunk) {

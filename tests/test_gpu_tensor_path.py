@@ -331,3 +331,31 @@ def test_small_degenerate_catalog_auto_mode_stays_exact_and_fast(rs):
     t2 = index.fallbacks()[1]
     index.search(q, 10)
     assert index.fallbacks()[1] > t2
+
+
+@pytest.mark.parametrize("nq,k,n", [(1, 10, 200_000), (2, 100, 200_000), (1, 128, 65_536), (2, 1, 100_003), (1, 100, 65_537)])
+def test_bf16_shadow_scan_for_one_or_two_queries_is_bit_exact(rs, nq, k, n, monkeypatch):
+    """The batch-1 / batch-2 path (scan_bf16_topk_kernel: bf16 shadow for the bulk, exact fp32 re-score of every row that
+    could still make the list) against the oracle's FMA chain, and against the seven-launch tensor path it replaces."""
+    xb = rs.synth.make_unit_rows(n, 128, n + k)
+    q = rs.synth.make_unit_rows(nq, 128, n + nq)
+    index = _check(rs, xb, q, k, expect_fallback=False)
+    n0 = rs._lib.launch_count()
+    D, I = index.search(dev(q), k)
+    assert rs._lib.launch_count() - n0 == 2                      # scan + merge
+    monkeypatch.setenv("RS_BF16_SCAN", "0")                      # read once per process: only documents the knob here
+    De, Ie = index.search(dev(q), k, mode="exact")
+    assert torch.equal(I, Ie) and torch.equal(D, De)
+
+
+def test_bf16_shadow_scan_ties_and_non_unit_rows(rs):
+    rng = np.random.default_rng(51)
+    base = rs.synth.make_unit_rows(1000, 128, 52)
+    xb = np.ascontiguousarray(np.tile(base, (80, 1)))            # every row 80 times: exact ties, row-ascending order decides
+    q = rs.synth.make_unit_rows(2, 128, 53)
+    _check(rs, xb, q[:1], 100)
+    _check(rs, xb, q, 10)
+    xb = (rng.standard_normal((90_000, 128)) * rng.lognormal(0, 0.7, (90_000, 1))).astype(np.float32)
+    qq = (rng.standard_normal((1, 128)) * 3.0).astype(np.float32)
+    _check(rs, xb, qq, 50)
+    _check(rs, np.zeros((70_000, 128), np.float32), q[:1], 10)  # all scores 0: rows 0..9 win
