@@ -375,6 +375,7 @@ def main():
     sidx._local_deferred = lambda q_, k_, out: local_deferred(q_, k_, id_base=sidx.row_begin, mode=args.mode, out=out)
     sidx.shared_threshold = args.mode != "exact" and os.environ.get("RS_SHARED_THRESHOLD", "1") != "0"
     sidx.use_graph = world > 1 and os.environ.get("RS_SHARDED_GRAPH", "1") != "0"   # one CUDA-graph replay per step
+    sidx.reuse_outputs = True    # results are graph-owned buffers, valid until the second-next search (no copy-out per step)
     # both exchanges of a step through NVLink peer memory (csrc/peer.cu; "nccl" = two NCCL all-gathers)
     sidx.exchange = os.environ.get("RS_SHARDED_EXCHANGE", "p2p") if world > 1 else "nccl"
 
@@ -544,7 +545,8 @@ def main():
     if rank == 0:
         sharding = "none"
         if world > 1:
-            how = ("stores into NVLink peer memory (rs_peer_publish / wait / ack: this repo's kernels, no NCCL on the step)"
+            how = ("stores into NVLink peer memory by this repo's kernels, sequenced by one C call per step (rs_index_search_sharded: "
+                   "the publishing kernel's last CTA waits for all ranks, threshold / merge kernels acknowledge; no NCCL on the step)"
                    if sidx.exchange == "p2p" else "NCCL all-gathers")
             sharding = (f"rows/{world} contiguous; per step: sample pass -> exchange of each shard's largest sample maxima ({how}) -> "
                         f"shared-threshold filter + exact re-score -> one fused exchange of scores | rows | flags | bounds ({how}) -> "

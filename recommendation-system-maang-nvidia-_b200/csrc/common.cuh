@@ -301,9 +301,18 @@ __device__ __forceinline__ uint32_t block_kth_largest(F v, int n, int k, unsigne
   for (int shift = 24; shift >= 0; shift -= 8) {
     for (int i = tid; i < 256; i += NT) hist[i] = 0;
     __syncthreads();
-    for (int i = tid; i < n; i += NT) {
-      const uint32_t x = v(i);
-      if ((x & mask) == prefix) atomicAdd(&hist[(x >> shift) & 255u], 1u);
+    // Warp-aggregated histogram: the values are scores of one query, so most of them share the top byte (and often the
+    // second) -- plain atomics then all hit one or two shared-memory words and serialise 32 ways inside every warp and
+    // again across the eight CTAs that share an SM.  One atomic per distinct bin and warp instead.
+    for (int i0 = 0; i0 < n; i0 += NT) {
+      const int i = i0 + tid;
+      uint32_t bin = 0xFFFFFFFFu;                 // "no value": inactive lanes group among themselves
+      if (i < n) {
+        const uint32_t x = v(i);
+        if ((x & mask) == prefix) bin = (x >> shift) & 255u;
+      }
+      const unsigned peers = __match_any_sync(0xFFFFFFFFu, bin);
+      if (bin != 0xFFFFFFFFu && (tid & 31) == __ffs(peers) - 1) atomicAdd(&hist[bin], static_cast<unsigned>(__popc(peers)));
     }
     __syncthreads();
     if (tid < 32) {   // lane L owns bins 255-8L .. 248-8L (descending), prefix-summed over lanes

@@ -638,7 +638,9 @@ void merge_dispatch(const KeySource& src, int64_t nq, int P, int k, int64_t id_b
                     int64_t ldI, cudaStream_t st, const MergeExtras& ex = MergeExtras{}) {
   RS_CHECK(k >= 1 && k <= 1024, "k must be in [1, 1024]");
   RS_CHECK(nq <= 0x7FFFFFFF, "too many queries");
-  if (k <= 128 && (int64_t)P * k <= SMALL_MERGE_KEYS && nq <= 64) {   // few queries, short lists: the latency path
+  // short inputs -- the batch-1 scan's 148 lists of 10, the sharded search's G lists of k: position thresholds + rank counting
+  // instead of rounds of offer / prune (a 256-key bitonic sort each)
+  if (k <= 128 && (int64_t)P * k <= SMALL_MERGE_KEYS && (nq <= 64 || P <= 16)) {
     rs::ProfScope prof(RS_PROF_MERGE, st);
     merge_small_kernel<<<static_cast<unsigned>(nq), MERGE_NT, 0, st>>>(src, P, k, id_base, D, ldD, I, ldI, ex);
     RS_LAUNCH_CHECK();

@@ -112,7 +112,7 @@ __device__ __forceinline__ uint64_t peer_begin(const uint8_t* local, const PeerL
 // the same last CTA acknowledges them to every peer (what a separate peer_ack_kernel would do).
 __device__ __forceinline__ void peer_finish(uint8_t* const* bases, const PeerLayout& L, uint64_t seq,
                                             uint8_t* const* consumed = nullptr, const PeerLayout* consumed_L = nullptr,
-                                            uint64_t consumed_seq = 0) {
+                                            uint64_t consumed_seq = 0, int* is_last = nullptr) {
   uint8_t* local = bases[L.rank];
   __threadfence_system();
   __syncthreads();
@@ -123,6 +123,7 @@ __device__ __forceinline__ void peer_finish(uint8_t* const* bases, const PeerLay
       __threadfence_system();
       for (int g = 0; g < L.world; ++g) st_release_sys(reinterpret_cast<uint64_t*>(bases[g] + L.off_flags) + L.rank, seq);
       *reinterpret_cast<uint64_t*>(local + L.off_seq) = seq;
+      if (is_last) *is_last = 1;     // shared-memory word of the calling CTA
       if (consumed)
         for (int g = 0; g < consumed_L->world; ++g)
           st_release_sys(reinterpret_cast<uint64_t*>(consumed[g] + consumed_L->off_acks) + consumed_L->rank, consumed_seq);
@@ -149,5 +150,8 @@ __device__ __forceinline__ void peer_consumed(uint8_t* const* bases, const PeerL
     }
   }
 }
+
+// host side (peer.cu): publish src into every rank's region and wait, in the same launch, for every rank's message
+void publish_and_wait(rs_peer* h, const void* src, int64_t bytes, cudaStream_t st);
 
 }  // namespace rsp

@@ -10,11 +10,11 @@
 // Sharded catalog search (BASELINE config 3; replaces faiss IndexFlatIP.search of app/recommendation_service.py:72 over a
 // catalog too large or too slow for one GPU).  Rank g holds rows [N*g/G, N*(g+1)/G).  One step, all on the caller's stream:
 //   sample pass + top list        rs::shared_begin
-//   tops exchange                 peer_publish_kernel -> every rank's tops region
-//   threshold (waits, acks)       threshold_shared_kernel reads the G lists in place
+//   tops exchange                 peer_publish_kernel -> every rank's tops region; its last CTA waits for all ranks' tops
+//   threshold (acks)              threshold_shared_kernel reads the G lists in place
 //   filter, bucket, re-score      rs::shared_finish, straight into the send buffer [scores | rows | flags | bounds]
-//   lists exchange                peer_publish_kernel -> every rank's lists region
-//   merge (waits, verifies, acks) merge_topk_kernel reads the G parts in place and writes D, I, need_exact
+//   lists exchange                peer_publish_kernel -> every rank's lists region; its last CTA waits for all ranks' lists
+//   merge (verifies, acks)        merge_topk_kernel reads the G parts in place and writes D, I, need_exact
 // 11 kernel launches and 3 memsets per step.  Shapes outside the tensor path (or RS_EXACT_FP32) run every shard's
 // own search (per-shard thresholds or the exact fp32 scan) and share the lists exchange + merge.
 #include <algorithm>
@@ -196,9 +196,15 @@ struct DL {
   operator DLTensor*() { return &t; }
 };
 
+// RS_PEER_WAIT_IN_CONSUMER=1 (A/B knob, read per call): publish without waiting; the consumer kernels then spin themselves
 void publish(rs_peer* region, const void* src, int64_t bytes, cudaStream_t st) {
-  DL m(const_cast<void*>(src), region->device, kDLUInt, 8, bytes);
-  RS_CHECK(rs_peer_publish(region, m, st) == 0, rs_last_error());
+  const char* e = getenv("RS_PEER_WAIT_IN_CONSUMER");
+  if (e && e[0] == '1') {
+    DL m(const_cast<void*>(src), region->device, kDLUInt, 8, bytes);
+    RS_CHECK(rs_peer_publish(region, m, st) == 0, rs_last_error());
+  } else {
+    rsp::publish_and_wait(region, src, bytes, st);
+  }
 }
 
 // one deferred step over `nq` queries (device pointers); need = int32 [nq] device or nullptr (exact mode: nothing to flag)

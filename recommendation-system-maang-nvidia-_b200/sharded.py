@@ -237,6 +237,8 @@ class ShardedIndexFlatIP:
             self._rank = rank            # (k, rho) -> rank of the sample maximum to use as the threshold
         self.shared_threshold = True     # set False to keep per-shard thresholds (one exchange fewer, ~8x the candidates)
         self.use_graph = False           # replay each (nq, k) step as one CUDA graph (CUDA queries only)
+        self.reuse_outputs = False       # graph mode: return graph-owned buffers (two alternating graphs) instead of copies
+        self._flip = {}
         self.exchange = "nccl"           # "p2p": both exchanges of a step through NVLink peer memory (PeerExchange)
         self._peers = {}
         self._peer_factory = None        # tests: nbytes -> object with publish / gathered / done / close
@@ -453,7 +455,13 @@ class ShardedIndexFlatIP:
         """The step as a CUDA graph per (nq, k): ~15 launches and two NCCL collectives cost one graph launch on the
         host, which is what bounds a step once the catalog is split 8 ways (0.37 ms of kernels per step).  The graph
         owns its buffers; results are copied out so that the next replay cannot overwrite what the caller holds."""
-        key = (int(q.shape[0]), k, q.device.index)
+        # reuse_outputs: two graphs per shape, replayed alternately, hand out their own output buffers instead of copies --
+        # a result then stays valid until the second-next search of the same shape (what a serving loop needs)
+        slot = 0
+        if self.reuse_outputs:
+            slot = self._flip.get((int(q.shape[0]), k), 0)
+            self._flip[(int(q.shape[0]), k)] = slot ^ 1
+        key = (int(q.shape[0]), k, q.device.index, slot)
         entry = self._graphs.get(key)
         if entry is None:
             for _ in range(2):                     # warm-up outside capture: lazy one-time setup inside the library
@@ -469,6 +477,8 @@ class ShardedIndexFlatIP:
         static_q.copy_(q)
         graph.replay()
         self._last_need = need
+        if self.reuse_outputs:
+            return D, I, flag
         return D.clone(), I.clone(), flag
 
 
