@@ -304,6 +304,7 @@ __device__ __forceinline__ uint32_t block_kth_largest(F v, int n, int k, unsigne
     // Warp-aggregated histogram: the values are scores of one query, so most of them share the top byte (and often the
     // second) -- plain atomics then all hit one or two shared-memory words and serialise 32 ways inside every warp and
     // again across the eight CTAs that share an SM.  One atomic per distinct bin and warp instead.
+    // (The two low bytes are spread over many bins: there a match costs more than the atomics it saves.)
     for (int i0 = 0; i0 < n; i0 += NT) {
       const int i = i0 + tid;
       uint32_t bin = 0xFFFFFFFFu;                 // "no value": inactive lanes group among themselves
@@ -311,8 +312,12 @@ __device__ __forceinline__ uint32_t block_kth_largest(F v, int n, int k, unsigne
         const uint32_t x = v(i);
         if ((x & mask) == prefix) bin = (x >> shift) & 255u;
       }
-      const unsigned peers = __match_any_sync(0xFFFFFFFFu, bin);
-      if (bin != 0xFFFFFFFFu && (tid & 31) == __ffs(peers) - 1) atomicAdd(&hist[bin], static_cast<unsigned>(__popc(peers)));
+      if (shift >= 16) {
+        const unsigned peers = __match_any_sync(0xFFFFFFFFu, bin);
+        if (bin != 0xFFFFFFFFu && (tid & 31) == __ffs(peers) - 1) atomicAdd(&hist[bin], static_cast<unsigned>(__popc(peers)));
+      } else if (bin != 0xFFFFFFFFu) {
+        atomicAdd(&hist[bin], 1u);
+      }
     }
     __syncthreads();
     if (tid < 32) {   // lane L owns bins 255-8L .. 248-8L (descending), prefix-summed over lanes

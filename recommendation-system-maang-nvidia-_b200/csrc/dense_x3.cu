@@ -157,7 +157,13 @@ dense_x3_kernel(const __grid_constant__ X3Maps maps, const __grid_constant__ X3P
   const X3Problem& pr = p.prob[pi];
   const int64_t ntiles = (pr.rows + BM - 1) / BM;
   const int64_t n_my = cta < ntiles ? (ntiles - cta + ncta - 1) / ncta : 0;
-  const int64_t n_items = n_my * nh;             // work items: (row tile, N tile), the N tiles of a row tile back to back
+  // Work items.  TMA input: (row tile, N tile) pairs, the N tiles of a row tile back to back, two TMEM slots (main | corr
+  // each) so the epilogue of one item overlaps the MMAs of the next.  Converting producers: ONE item per row tile -- both N
+  // tiles are computed from the same converted chunk (the conversion, not the tensor pipe, is what that kernel is short
+  // of: ncu showed it issue-bound with the rows converted once per N tile), into all four accumulators of the one slot.
+  constexpr bool SHARED_A = !TMA_IN;
+  const int halves = SHARED_A ? nh : 1;          // N tiles computed per item
+  const int64_t n_items = SHARED_A ? n_my : n_my * nh;
   const int n0 = blockIdx.y * nh * NT;           // first output column of this CTA
 
   if (warp == X3_ISSUER && lane == 0) {
@@ -208,26 +214,29 @@ dense_x3_kernel(const __grid_constant__ X3Maps maps, const __grid_constant__ X3P
       const uint64_t ring0 = umma_desc_k_sw128(smem_u32(ring));
       uint32_t it = 0;
       for (int64_t i = 0; i < n_items; ++i) {
-        const int hh = static_cast<int>(i % nh);
-        const uint32_t a = static_cast<uint32_t>(i) & 1u, aph = (static_cast<uint32_t>(i) >> 1) & 1u;
+        const uint32_t a = SHARED_A ? 0u : (static_cast<uint32_t>(i) & 1u);
+        const uint32_t aph = SHARED_A ? (static_cast<uint32_t>(i) & 1u) : ((static_cast<uint32_t>(i) >> 1) & 1u);
         mbar_wait(&tempty[a], aph ^ 1u);
         tc_fence_after_sync();
-        const uint32_t d_main = tmem_base + a * 256, d_corr = d_main + 128;
         for (int kc = 0; kc < KC; ++kc, ++it) {
           const uint32_t s = it % X3_STAGES, ph = (it / X3_STAGES) & 1u;
           mbar_wait(&full[s], ph);
           tc_fence_after_sync();
-          const uint32_t woff = static_cast<uint32_t>((hh * KC + kc) * NT * 128);
+          for (int h2 = 0; h2 < halves; ++h2) {
+            const int hh = SHARED_A ? h2 : static_cast<int>(i % nh);
+            const uint32_t d_main = tmem_base + (SHARED_A ? h2 * 256 : a * 256), d_corr = d_main + 128;
+            const uint32_t woff = static_cast<uint32_t>((hh * KC + kc) * NT * 128);
 #pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4) {
-            const uint64_t a_hi = ring0 + static_cast<uint64_t>((s * X3_STAGE_BYTES + k4 * 32) >> 4);
-            const uint64_t a_lo = a_hi + static_cast<uint64_t>((BM * 128) >> 4);
-            const uint64_t b_hi = whi0 + static_cast<uint64_t>((woff + k4 * 32) >> 4);
-            const uint64_t b_lo = wlo0 + static_cast<uint64_t>((woff + k4 * 32) >> 4);
-            const uint32_t acc = (kc | k4) ? 1u : 0u;
-            umma_bf16_ss(d_main, a_hi, b_hi, idesc, acc);
-            umma_bf16_ss(d_corr, a_hi, b_lo, idesc, acc);
-            umma_bf16_ss(d_corr, a_lo, b_hi, idesc, 1u);
+            for (int k4 = 0; k4 < 4; ++k4) {
+              const uint64_t a_hi = ring0 + static_cast<uint64_t>((s * X3_STAGE_BYTES + k4 * 32) >> 4);
+              const uint64_t a_lo = a_hi + static_cast<uint64_t>((BM * 128) >> 4);
+              const uint64_t b_hi = whi0 + static_cast<uint64_t>((woff + k4 * 32) >> 4);
+              const uint64_t b_lo = wlo0 + static_cast<uint64_t>((woff + k4 * 32) >> 4);
+              const uint32_t acc = (kc | k4) ? 1u : 0u;
+              umma_bf16_ss(d_main, a_hi, b_hi, idesc, acc);
+              umma_bf16_ss(d_corr, a_hi, b_lo, idesc, acc);
+              umma_bf16_ss(d_corr, a_lo, b_hi, idesc, 1u);
+            }
           }
           umma_commit(&empty[s]);
         }
@@ -296,7 +305,7 @@ dense_x3_kernel(const __grid_constant__ X3Maps maps, const __grid_constant__ X3P
       }
     };
     auto load_chunk = [&](float4 (&buf)[8], int64_t g) {
-      const int64_t tile = cta + ((g / KC) / nh) * ncta;
+      const int64_t tile = cta + (g / KC) * ncta;     // converting producers: one item (all N tiles) per row tile
       const int kc = static_cast<int>(g % KC);
       if (tile != ld_tile) {
         if (ld_tile < 0) fetch_raw(tile);
@@ -356,13 +365,16 @@ dense_x3_kernel(const __grid_constant__ X3Maps maps, const __grid_constant__ X3P
       return stg0 + (nst++ & 1u) * X3_OUT_BYTES;
     };
     for (int64_t i = 0; i < n_items; ++i) {
-      const int hh = static_cast<int>(i % nh);
-      const int64_t tile = cta + (i / nh) * ncta;
+      const int64_t tile = cta + (SHARED_A ? i : i / nh) * ncta;
       const int row0 = static_cast<int>(tile * BM) + quarter * 32;
-      const uint32_t a = static_cast<uint32_t>(i) & 1u, aph = (static_cast<uint32_t>(i) >> 1) & 1u;
+      const uint32_t a = SHARED_A ? 0u : (static_cast<uint32_t>(i) & 1u);
+      const uint32_t aph = SHARED_A ? (static_cast<uint32_t>(i) & 1u) : ((static_cast<uint32_t>(i) >> 1) & 1u);
       mbar_wait(&tfull[a], aph);
       tc_fence_after_sync();
-      const uint32_t taddr = tmem_base + a * 256 + (static_cast<uint32_t>(quarter * 32) << 16);
+#pragma unroll 1
+      for (int h2 = 0; h2 < halves; ++h2) {
+      const int hh = SHARED_A ? h2 : static_cast<int>(i % nh);
+      const uint32_t taddr = tmem_base + (SHARED_A ? h2 * 256 : a * 256) + (static_cast<uint32_t>(quarter * 32) << 16);
       const int col_base = n0 + hh * NT;
 #pragma unroll 1
       for (int c = 0; c < NT / 32; ++c) {
@@ -370,7 +382,7 @@ dense_x3_kernel(const __grid_constant__ X3Maps maps, const __grid_constant__ X3P
         __syncwarp();
         tmem_ld_32x32(taddr + c * 32, m);
         tmem_ld_32x32(taddr + 128 + c * 32, cr);
-        if (c == NT / 32 - 1) {                  // the accumulators are in registers: the issuer may start the next item
+        if (c == NT / 32 - 1 && h2 == halves - 1) {   // the accumulators are in registers: the issuer may start the next item
           tc_fence_before_sync();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty[a]);
@@ -439,6 +451,7 @@ dense_x3_kernel(const __grid_constant__ X3Maps maps, const __grid_constant__ X3P
           }
         }
       }
+    }
     }
     if (OUT_TMA && lane == 0) bulk_wait_all();   // the staging buffers (and this CTA) outlive every store
   }
