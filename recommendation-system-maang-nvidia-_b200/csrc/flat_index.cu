@@ -177,8 +177,9 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restri
 // the caller then repeats that query on the fp32 scan.
 // ------------------------------------------------------------------------------------------------
 constexpr int BSCAN_STAGES = 3;
-constexpr int BSCAN_ROWS = 256;                          // rows per stage == threads: 8 warps hide the dot product's latency
-constexpr int BSCAN_NT = 256;
+constexpr int BSCAN_ROWS = 256;                          // rows per stage
+constexpr int BSCAN_NT = 512;                            // two threads per row (one per 64-feature half): 16 warps per SM -- with
+                                                         // 8 the kernel was latency-bound at 4.7 TB/s (ncu: 24 % issue utilisation)
 constexpr int BSCAN_STAGE_BYTES = BSCAN_ROWS * 128 * 2;  // [256 rows x 128 bf16] as two 128-byte-swizzled [256 x 64] boxes
 constexpr int BSCAN_CAP = 1024;                          // candidate buffer per query
 constexpr int BSCAN_SOFT = 512;                          // prune as soon as this many are held: the first prune (after two
@@ -192,7 +193,8 @@ struct BScanSmem {
   static constexpr int kBarOff = kQOff + QT * 128 * 4;
   static constexpr int kCntOff = kBarOff + BSCAN_STAGES * 8;
   static constexpr int kEpsOff = kCntOff + QT * 4;
-  static constexpr int kTotal = kEpsOff + QT * 4 + 16;
+  static constexpr int kPartOff = kEpsOff + QT * 4 + 16;
+  static constexpr int kTotal = kPartOff + QT * BSCAN_ROWS * 4;
   static constexpr int kDynamic = kTotal + 1024;
 };
 
@@ -241,8 +243,11 @@ scan_bf16_topk_kernel(const __grid_constant__ CUtensorMap tmap16, const float* _
   int* cnt = reinterpret_cast<int*>(base + L::kCntOff);
   float* eps_s = reinterpret_cast<float*>(base + L::kEpsOff);   // [QT] 2 eps
   int* kept = reinterpret_cast<int*>(eps_s + QT);               // scratch of prune_margin
+  float* part = reinterpret_cast<float*>(base + L::kPartOff);   // [QT][256]: the second half's partial sums
 
   const int tid = threadIdx.x;
+  const int trow = tid & (BSCAN_ROWS - 1);                       // this thread's row of the tile ...
+  const int half = tid >> 8;                                     // ... and 64-feature half (warps 0-7 / 8-15: no bank conflicts)
   const int64_t ntiles = (n + BSCAN_ROWS - 1) / BSCAN_ROWS;
   const int64_t my_tiles = (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
 
@@ -288,50 +293,56 @@ scan_bf16_topk_kernel(const __grid_constant__ CUtensorMap tmap16, const float* _
     eps2[g] = eps_s[g];
   }
 
-  const uint32_t sw = static_cast<uint32_t>(tid & 7) << 4;
   for (int64_t it = 0; it < my_tiles; ++it) {
     const int stage = static_cast<int>(it % BSCAN_STAGES);
     mbar_wait(&full[stage], static_cast<uint32_t>((it / BSCAN_STAGES) & 1));
 
     // ---- low-precision score of row `tid`: bf16 row x fp32 query, fp32 accumulation ----
-    // four partial sums per query: the order of a low-precision score does not matter, the latency of one 128-long chain does
+    // four partial sums per query over this thread's half of the row: the order of a low-precision score does not matter,
+    // the latency of one long chain does
     float a4[QT][4];
 #pragma unroll
     for (int g = 0; g < QT; ++g)
 #pragma unroll
       for (int u = 0; u < 4; ++u) a4[g][u] = 0.0f;
-    const uint8_t* srow = base + stage * BSCAN_STAGE_BYTES + tid * 128;
+    const uint8_t* srow = base + stage * BSCAN_STAGE_BYTES + half * (BSCAN_ROWS * 128) + trow * 128;
+    const uint32_t sw = static_cast<uint32_t>(trow & 7) << 4;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int c = 0; c < 8; ++c) {
+      const uint4 xv = *reinterpret_cast<const uint4*>(srow + ((c << 4) ^ sw));
+      const uint32_t w[4] = {xv.x, xv.y, xv.z, xv.w};
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const uint4 xv = *reinterpret_cast<const uint4*>(srow + h * (BSCAN_ROWS * 128) + ((c << 4) ^ sw));
-        const uint32_t w[4] = {xv.x, xv.y, xv.z, xv.w};
-#pragma unroll
-        for (int g = 0; g < QT; ++g) {
-          const float4 qa = *reinterpret_cast<const float4*>(qs + g * D + h * 64 + c * 8);
-          const float4 qb = *reinterpret_cast<const float4*>(qs + g * D + h * 64 + c * 8 + 4);
-          a4[g][0] = fmaf(qa.x, __uint_as_float(w[0] << 16), a4[g][0]);
-          a4[g][1] = fmaf(qa.y, __uint_as_float(w[0] & 0xFFFF0000u), a4[g][1]);
-          a4[g][2] = fmaf(qa.z, __uint_as_float(w[1] << 16), a4[g][2]);
-          a4[g][3] = fmaf(qa.w, __uint_as_float(w[1] & 0xFFFF0000u), a4[g][3]);
-          a4[g][0] = fmaf(qb.x, __uint_as_float(w[2] << 16), a4[g][0]);
-          a4[g][1] = fmaf(qb.y, __uint_as_float(w[2] & 0xFFFF0000u), a4[g][1]);
-          a4[g][2] = fmaf(qb.z, __uint_as_float(w[3] << 16), a4[g][2]);
-          a4[g][3] = fmaf(qb.w, __uint_as_float(w[3] & 0xFFFF0000u), a4[g][3]);
-        }
+      for (int g = 0; g < QT; ++g) {
+        const float4 qa = *reinterpret_cast<const float4*>(qs + g * D + half * 64 + c * 8);
+        const float4 qb = *reinterpret_cast<const float4*>(qs + g * D + half * 64 + c * 8 + 4);
+        a4[g][0] = fmaf(qa.x, __uint_as_float(w[0] << 16), a4[g][0]);
+        a4[g][1] = fmaf(qa.y, __uint_as_float(w[0] & 0xFFFF0000u), a4[g][1]);
+        a4[g][2] = fmaf(qa.z, __uint_as_float(w[1] << 16), a4[g][2]);
+        a4[g][3] = fmaf(qa.w, __uint_as_float(w[1] & 0xFFFF0000u), a4[g][3]);
+        a4[g][0] = fmaf(qb.x, __uint_as_float(w[2] << 16), a4[g][0]);
+        a4[g][1] = fmaf(qb.y, __uint_as_float(w[2] & 0xFFFF0000u), a4[g][1]);
+        a4[g][2] = fmaf(qb.z, __uint_as_float(w[3] << 16), a4[g][2]);
+        a4[g][3] = fmaf(qb.w, __uint_as_float(w[3] & 0xFFFF0000u), a4[g][3]);
       }
     }
     float acc[QT];
 #pragma unroll
-    for (int g = 0; g < QT; ++g) acc[g] = (a4[g][0] + a4[g][1]) + (a4[g][2] + a4[g][3]);
+    for (int g = 0; g < QT; ++g) {
+      acc[g] = (a4[g][0] + a4[g][1]) + (a4[g][2] + a4[g][3]);
+      if (half == 1) part[g * BSCAN_ROWS + trow] = acc[g];
+    }
+    __syncthreads();
+    if (half == 0) {
+#pragma unroll
+      for (int g = 0; g < QT; ++g) acc[g] += part[g * BSCAN_ROWS + trow];
+    }
 
     // ---- rows inside the margin go to the candidate buffer with their low-precision key ----
-    const int64_t row = (blockIdx.x + it * gridDim.x) * BSCAN_ROWS + tid;
+    const int64_t row = (blockIdx.x + it * gridDim.x) * BSCAN_ROWS + trow;
     uint32_t pend = 0;
 #pragma unroll
     for (int g = 0; g < QT; ++g)
-      if (row < n && g < nq && acc[g] >= cut[g]) pend |= 1u << g;
+      if (half == 0 && row < n && g < nq && acc[g] >= cut[g]) pend |= 1u << g;
     for (;;) {
       bool saw_full = false;
 #pragma unroll
