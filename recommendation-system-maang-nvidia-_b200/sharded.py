@@ -297,7 +297,18 @@ class ShardedIndexFlatIP:
         filter's survivor path and the re-score shrink with it), and the guarantee moves behind the merge
         (ops.topk_verify: the k-th merged score must clear every shard's tau + eps)."""
         if self.world == 1:
-            return self._local_search(q, k)
+            if not (self.use_graph and self._local_deferred is not None and isinstance(q, torch.Tensor) and q.is_cuda):
+                return self._local_search(q, k)
+            # one GPU, graph mode: the deferred local search replayed as one CUDA graph -- the plain call synchronises with
+            # the host inside every search (to look at the tensor path's flags) and pays its ~10 launches and stream-ordered
+            # allocations on the host each time; replayed, a step costs one graph launch and one flag read
+            D, I, need_any = self._replay(q, int(k))
+            if bool(need_any):
+                idx = self._last_need.nonzero().flatten()
+                De, Ie = self._local_exact(q[idx].contiguous(), k)
+                D[idx], I[idx] = De, Ie
+                self.fallbacks += int(idx.numel())
+            return D, I
         if self._local_deferred is None:
             return self._gather_merge(*self._local_search(q, k))
         if self.use_graph and isinstance(q, torch.Tensor) and q.is_cuda:
@@ -382,6 +393,15 @@ class ShardedIndexFlatIP:
 
     def _step(self, q, k: int):
         """Queues one whole search step (no host synchronisation) -> (D, I, need bool [nq])."""
+        if self.world == 1:
+            nq1 = int(q.shape[0])
+            D = torch.empty((nq1, k), dtype=torch.float32, device=q.device)
+            I = torch.empty((nq1, k), dtype=torch.int64, device=q.device)
+            F = torch.zeros((nq1,), dtype=torch.int32, device=q.device)
+            self._local_deferred(q, k, (D, I, F))
+            need = F.ne(0)
+            self._last_need = need
+            return D, I, need
         if self._use_native(q):
             try:
                 D, I, need = self._native_step(q, k)
