@@ -289,7 +289,9 @@ int rs_matvec(const DLTensor* items, const DLTensor* user, DLTensor* out, void* 
 /*
  * K7. Merge of per-shard top-k lists after the all-gather (new in this build; BASELINE
  * config 3).  Dparts: f32 [nparts, nq, k]; Iparts: int64 [nparts, nq, k] (global ids,
- * -1 = padding); D: f32 [nq, k]; I: int64 [nq, k]; device.  Order (score desc, id asc).
+ * -1 = padding; ids must be below 2^32 -- a (score, id) pair is merged as one 64-bit key with a 32-bit id field, so
+ * catalogs above 2^32 rows are refused by the sharded entry points); D: f32 [nq, k]; I: int64 [nq, k]; device.
+ * Order (score desc, id asc).
  * Each part is a contiguous [nq, k] block; the stride between parts is free, so the parts can be
  * slices of one exchange buffer that carries scores, ids and flags of a shard side by side.
  */

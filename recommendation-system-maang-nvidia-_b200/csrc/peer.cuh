@@ -114,9 +114,11 @@ __device__ __forceinline__ void peer_finish(uint8_t* const* bases, const PeerLay
                                             uint8_t* const* consumed = nullptr, const PeerLayout* consumed_L = nullptr,
                                             uint64_t consumed_seq = 0, int* is_last = nullptr) {
   uint8_t* local = bases[L.rank];
-  __threadfence_system();
+  // One system-scope fence per CTA, by the thread that signals: the barrier orders every thread's stores before it and the
+  // fence is cumulative (a fence by each of the 256 threads cost several microseconds per launch for the same guarantee).
   __syncthreads();
   if (threadIdx.x == 0) {
+    __threadfence_system();
     unsigned int* done = reinterpret_cast<unsigned int*>(local + L.off_done);
     if (atomicAdd(done, 1u) == gridDim.x - 1) {
       *done = 0;
@@ -140,9 +142,9 @@ __device__ __forceinline__ uint64_t peer_arrived(const uint8_t* local, const Pee
 }
 // ... and, once every CTA has finished reading it, acknowledge the step to every peer (last CTA).
 __device__ __forceinline__ void peer_consumed(uint8_t* const* bases, const PeerLayout& L, uint64_t seq) {
-  __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
+    __threadfence();
     unsigned int* done = reinterpret_cast<unsigned int*>(bases[L.rank] + L.off_done);
     if (atomicAdd(done, 1u) == gridDim.x - 1) {
       *done = 0;
