@@ -141,8 +141,8 @@ class Comm:
     _live = {}
 
     @classmethod
-    def get(cls, device: torch.device, group: Optional[dist.ProcessGroup] = None) -> "Comm":
-        key = (id(group) if group is not None else 0, torch.device(device).index)
+    def get(cls, device: torch.device, group: Optional[dist.ProcessGroup] = None, lane: int = 0) -> "Comm":
+        key = (id(group) if group is not None else 0, torch.device(device).index, int(lane))
         c = cls._live.get(key)
         if c is None or c._h is None:
             c = cls._live[key] = cls(device, group)
@@ -238,6 +238,7 @@ class ShardedIndexFlatIP:
         self.shared_threshold = True     # set False to keep per-shard thresholds (one exchange fewer, ~8x the candidates)
         self.use_graph = False           # replay each (nq, k) step as one CUDA graph (CUDA queries only)
         self.reuse_outputs = False       # graph mode: return graph-owned buffers (two alternating graphs) instead of copies
+        self.lane = 0                    # lanes of one index (submit / finish on separate streams) use separate peer regions
         self._flip = {}
         self.exchange = "nccl"           # "p2p": both exchanges of a step through NVLink peer memory (PeerExchange)
         self._peers = {}
@@ -296,31 +297,41 @@ class ShardedIndexFlatIP:
         as many candidates as one index over the whole catalog would (~6.6 per cent of that each at G = 8 ... the
         filter's survivor path and the re-score shrink with it), and the guarantee moves behind the merge
         (ops.topk_verify: the k-th merged score must clear every shard's tau + eps)."""
-        if self.world == 1:
-            if not (self.use_graph and self._local_deferred is not None and isinstance(q, torch.Tensor) and q.is_cuda):
-                return self._local_search(q, k)
-            # one GPU, graph mode: the deferred local search replayed as one CUDA graph -- the plain call synchronises with
-            # the host inside every search (to look at the tensor path's flags) and pays its ~10 launches and stream-ordered
-            # allocations on the host each time; replayed, a step costs one graph launch and one flag read
-            D, I, need_any = self._replay(q, int(k))
-            if bool(need_any):
-                idx = self._last_need.nonzero().flatten()
-                De, Ie = self._local_exact(q[idx].contiguous(), k)
-                D[idx], I[idx] = De, Ie
-                self.fallbacks += int(idx.numel())
-            return D, I
-        if self._local_deferred is None:
-            return self._gather_merge(*self._local_search(q, k))
-        if self.use_graph and isinstance(q, torch.Tensor) and q.is_cuda:
-            D, I, need_any = self._replay(q, int(k))
+        return self.finish(self.submit(q, k))
+
+    def submit(self, q, k: int):
+        """Queue one search step on the current stream WITHOUT looking at its flags -> a ticket for finish().  Lets a
+        caller keep two batches in flight (two ShardedIndexFlatIP lanes over the same local index, each on its own
+        stream): the latency-bound selection / exchange / merge kernels of one batch then overlap the tensor-bound filter
+        of the other.  In graph mode with reuse_outputs the ticket's buffers are graph-owned and stay valid until the
+        second-next submit on this lane."""
+        k = int(k)
+        cuda = isinstance(q, torch.Tensor) and q.is_cuda
+        if self.world == 1 and not (self.use_graph and self._local_deferred is not None and cuda):
+            return ("done",) + tuple(self._local_search(q, k))
+        if self.world > 1 and self._local_deferred is None:
+            return ("done",) + tuple(self._gather_merge(*self._local_search(q, k)))
+        if self.use_graph and cuda:
+            # graph mode (also on one GPU: the plain call synchronises with the host inside every search and pays its ~10
+            # launches and stream-ordered allocations on the host each time; replayed, a step costs one graph launch)
+            D, I, need_any = self._replay(q, k)
         else:
-            D, I, need = self._step(q, int(k))
+            D, I, need = self._step(q, k)
             need_any = need.any()
-        if bool(need_any):                                                   # the step's one host synchronisation
-            need = self._last_need
+        return ("open", D, I, need_any, self._last_need, q, k)
+
+    def finish(self, ticket) -> Tuple[torch.Tensor, torch.Tensor]:
+        """The one host synchronisation of a step: read the flags; flagged queries -- the tensor path's rare unverified
+        guesses, the same on every rank -- are re-searched exactly on every shard and merged again."""
+        if ticket[0] == "done":
+            return ticket[1], ticket[2]
+        _, D, I, need_any, need, q, k = ticket
+        if bool(need_any):
             idx = need.nonzero().flatten()
             sub = np.ascontiguousarray(q[idx.cpu().numpy()]) if isinstance(q, np.ndarray) else q[idx].contiguous()
-            if self._use_native(sub):
+            if self.world == 1:
+                De, Ie = self._local_exact(sub, k)
+            elif self._use_native(sub):
                 De, Ie, _ = self._native_step(sub, int(k), mode="exact")    # the flags are the same on every rank
             else:
                 De, Ie = self._gather_merge(*self._local_exact(sub, k))
@@ -338,7 +349,7 @@ class ShardedIndexFlatIP:
         import ctypes
         from . import _lib
         if self._comm is None:
-            self._comm = Comm.get(q.device, self.group)
+            self._comm = Comm.get(q.device, self.group, self.lane)
         nq = int(q.shape[0])
         D = torch.empty((nq, k), dtype=torch.float32, device=q.device)
         I = torch.empty((nq, k), dtype=torch.int64, device=q.device)
