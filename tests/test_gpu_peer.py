@@ -166,3 +166,57 @@ def test_sharded_search_entry_point_single_rank(rs):
         native(q, k, "auto", need, idx=small, n_total=3001)
     torch.cuda.synchronize()
     comm.release()
+
+
+def test_single_gpu_graph_replay_submit_finish_and_reused_outputs(rs):
+    """ShardedIndexFlatIP with a group of one in graph mode (what bench.py times on one GPU): the deferred search replayed as
+    a CUDA graph equals the plain search; submit / finish split the step from its flag read; with reuse_outputs a result
+    stays valid until the second-next search of the same shape."""
+    from recsys_b200.sharded import ShardedIndexFlatIP
+    N, nq, k = 90_000, 40, 20
+    xb = torch.from_numpy(rs.synth.make_unit_rows(N, 128, 61)).cuda()
+    index = rs.IndexFlatIP(128)
+    index.add(xb)
+    qs = [torch.from_numpy(rs.synth.make_unit_rows(nq, 128, 62 + i)).cuda() for i in range(4)]
+    want = [index.search(q, k, mode="exact") for q in qs]
+    sidx = ShardedIndexFlatIP(128, N, local_index=index)
+    sidx.use_graph = True
+    for q, (Dw, Iw) in zip(qs, want):
+        D, I = sidx.search(q, k)
+        assert torch.equal(I, Iw) and torch.equal(D, Dw)
+    sidx.reuse_outputs = True
+    held = []
+    for q in qs:
+        held.append(sidx.finish(sidx.submit(q, k)))
+    # the last two results are still intact (graph-owned buffers of the two alternating graphs); older ones were overwritten
+    for (D, I), (Dw, Iw) in zip(held[-2:], want[-2:]):
+        assert torch.equal(I, Iw) and torch.equal(D, Dw)
+    assert held[0][1].data_ptr() == held[2][1].data_ptr()
+    # two lanes over the same local index on two streams (batches in flight), flags read one step late
+    lanes = [sidx, ShardedIndexFlatIP(128, N, local_index=index)]
+    lanes[1].use_graph, lanes[1].reuse_outputs, lanes[1].lane = True, True, 1
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    for st in streams:
+        st.wait_stream(torch.cuda.current_stream())
+    tickets = [None, None]
+    got = {}
+    for i, q in enumerate(qs * 2):
+        ln = i & 1
+        with torch.cuda.stream(streams[ln]):
+            if tickets[ln] is not None:
+                j, t = tickets[ln]
+                D, I = lanes[ln].finish(t)
+                got[j] = (D.clone(), I.clone())
+            tickets[ln] = (i, lanes[ln].submit(q, k))
+    for ln in range(2):
+        with torch.cuda.stream(streams[ln]):
+            j, t = tickets[ln]
+            D, I = lanes[ln].finish(t)
+            got[j] = (D.clone(), I.clone())
+        torch.cuda.current_stream().wait_stream(streams[ln])
+    torch.cuda.synchronize()
+    for i in range(8):
+        Dw, Iw = want[i % 4]
+        assert torch.equal(got[i][1], Iw) and torch.equal(got[i][0], Dw), i
+    sidx.close()
+    lanes[1].close()
