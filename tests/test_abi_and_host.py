@@ -128,3 +128,11 @@ def test_metrics_consume_recommendations_unchanged(oracle_mod):
     assert ev.map_at_k(preds, truth, 2) == 0.25
     assert ev.mrr(preds, truth) == 0.25
     assert abs(ev.ndcg_at_k(preds, truth, 2) - 0.5 / np.log2(3)) < 1e-12
+
+
+def test_x3_shape_support_is_host_logic(rs):
+    """rs_dense_x3_supported needs no GPU: the fp32 tensor kernel serves in / out widths of 64, 128, 256 with no or relu
+    activation; everything else stays on the FFMA kernel."""
+    ok = rs.ops.dense_x3_supported
+    assert ok(128, 256, "relu") and ok(256, 128, None) and ok(64, 64, "relu") and ok(256, 256, None)
+    assert not ok(100, 128, None) and not ok(128, 512, None) and not ok(128, 128, "sigmoid") and not ok(32, 128, None)

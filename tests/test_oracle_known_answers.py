@@ -208,3 +208,29 @@ def test_service_sequence():
     assert set(sc) == {iv[0], "not-an-item"}                             # unknown item scored via OOV row 0
     with pytest.raises(ValueError):
         svc.score("unknown-user", [iv[0]])
+
+
+def test_extensions_restatement_known_answers():
+    """oracle/extensions.py (the checker of the north-star extensions, which have no reference counterpart): DCN-v2 with
+    W = c I, b = 0 on x0 = 1 gives x_l = (1 + c)^l; with W = 0 the bias sits INSIDE the product (x_L = x0 (1 + L b)); extra
+    tables are concatenated behind the id embedding; out-of-range codes read as zeros."""
+    from oracle import extensions as oext
+    D, E = 8, 4
+    eye_tower = [(np.eye(E), np.zeros(E))]
+    w = {"user_embedding": np.ones((3, E)), "item_embedding": np.ones((3, E)), "extra_user": {}, "extra_item": {},
+         "user_tower": eye_tower, "item_tower": eye_tower, "deep": [(np.zeros((D, 2)), np.zeros(2))],
+         "rating_head": (np.ones((D + 2, 1)), np.zeros(1)), "ctr_head": (np.zeros((D + 2, 1)), np.zeros(1)),
+         "cross_v2": [(0.5 * np.eye(D), np.zeros(D))] * 3}
+    out = oext.forward(w, np.array([1, 2]), np.array([0, 1]))
+    np.testing.assert_allclose(out["rating_prediction"], D * 1.5 ** 3)          # sum of x_3 = 8 * (1.5)^3, deep part is zero
+    np.testing.assert_allclose(out["ctr_prediction"], 0.5)
+    b = np.arange(D) * 0.1
+    w["cross_v2"] = [(np.zeros((D, D)), b)] * 2
+    out = oext.forward(w, np.array([1]), np.array([1]))
+    np.testing.assert_allclose(out["rating_prediction"], (1 + 2 * b).sum())
+    # an extra user table widens the tower input: identity-like tower on the first E inputs, extra columns weighted by 2
+    w["extra_user"] = {"age_id": np.array([[1.0, 1.0], [3.0, 3.0]])}
+    w["user_tower"] = [(np.vstack([np.eye(E), 2 * np.ones((2, E))]), np.zeros(E))]
+    w["cross_v2"] = []
+    out = oext.forward(w, np.array([1, 1, 1]), np.array([1, 1, 1]), {"age_id": np.array([0, 1, 7])})
+    np.testing.assert_allclose(out["user_embedding"][:, 0], [1 + 4, 1 + 12, 1 + 0])   # code 7 is outside the table: zeros
