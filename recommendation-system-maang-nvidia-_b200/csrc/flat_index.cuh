@@ -55,12 +55,19 @@ struct DeviceGuard {
 int64_t tensor_sample_rows(int64_t ntotal);
 int tensor_threshold_rank(int k, double rho);
 int64_t tensor_max_queries();
-rs_tc_session* shared_begin(rs_index* h, const float* q, int64_t nq, int k, int R, float* top, int64_t ld_top, cudaStream_t st);
+// publish_tops != nullptr: the list goes into slot `rank` of every rank's tops region instead of `top` (the kernel that
+// builds it publishes it: no separate publish launch), and the call returns with every rank's list present in the local region
+rs_tc_session* shared_begin(rs_index* h, const float* q, int64_t nq, int k, int R, float* top, int64_t ld_top, cudaStream_t st,
+                            rs_peer* publish_tops = nullptr);
 // tops_region != nullptr: `tops` is that peer-memory region's local data; the threshold kernel waits for every rank's
 // message and acknowledges the step itself (no rs_peer_wait / rs_peer_ack around the call)
 void shared_finish(rs_tc_session* s, const float* tops, int n_parts, int64_t part_ld, int R, int rank, int64_t id_base,
                    float* D, int64_t ldD, int64_t* I, int64_t ldI, int* need_exact, float* bound,
-                   rs_peer* tops_region = nullptr);
+                   rs_peer* tops_region = nullptr, rs_peer* publish_lists = nullptr, int64_t off_I = 0, int64_t off_F = 0,
+                   int64_t off_B = 0);
+// publish_lists != nullptr: D / I / need_exact / bound are ignored; the re-scoring kernel writes this shard's lists message
+// (scores f32 [nq, k] at 0 | rows int64 [nq, k] at off_I | need_exact int32 [nq] at off_F | bounds f32 [nq] at off_B) into
+// slot `rank` of every rank's lists region and waits, in its last CTA, for every rank's message
 
 // G-way merge of per-shard (score, global row) lists -- parts strided by part_ld_* elements, each a packed [nq, k] block --
 // optionally fused with the steps around it in the sharded search (sharded.cu):

@@ -211,15 +211,38 @@ __global__ void __launch_bounds__(256) a2a_rows_kernel(uint8_t* const* __restric
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int chunks = dim >> 2;
   const int64_t row_bytes = (int64_t)dim * 4;
-  for (int64_t t = warp0; t < prefix[LA.world]; t += nwarps) {
-    int r = 0;
-    while (t >= prefix[r + 1]) ++r;
-    const int64_t j = t - prefix[r];
-    const int64_t lr = reinterpret_cast<const int64_t*>(ids_local + r * LA.slot_bytes + kIdsHeader)[j];
-    float4* dst = reinterpret_cast<float4*>(row_bases[r] + LB.rank * LB.slot_bytes + j * row_bytes);
-    const bool ok = lr >= 0 && lr < n_local;
-    const float4* src = reinterpret_cast<const float4*>(table + (ok ? lr : 0) * ld);
-    for (int c = lane; c < chunks; c += 32) dst[c] = ok ? __ldg(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  // four rows per warp in flight: a row is a dependent chain (list entry -> random 512-byte row -> remote store) of ~1.5 us,
+  // and one row at a time per warp left the kernel latency-bound (36 us for 25 k rows)
+  constexpr int UR = 4;
+  const int64_t n_req = prefix[LA.world];
+  for (int64_t t0 = warp0 * UR; t0 < n_req; t0 += nwarps * UR) {
+    float4* dst[UR];
+    const float4* src[UR];
+    bool ok[UR];
+#pragma unroll
+    for (int u = 0; u < UR; ++u) {
+      const int64_t t = t0 + u;
+      dst[u] = nullptr;
+      src[u] = nullptr;
+      ok[u] = false;
+      if (t < n_req) {
+        int r = 0;
+        while (t >= prefix[r + 1]) ++r;
+        const int64_t j = t - prefix[r];
+        const int64_t lr = reinterpret_cast<const int64_t*>(ids_local + r * LA.slot_bytes + kIdsHeader)[j];
+        dst[u] = reinterpret_cast<float4*>(row_bases[r] + LB.rank * LB.slot_bytes + j * row_bytes);
+        ok[u] = lr >= 0 && lr < n_local;
+        src[u] = reinterpret_cast<const float4*>(table + (ok[u] ? lr : 0) * ld);
+      }
+    }
+    for (int c = lane; c < chunks; c += 32) {
+      float4 v[UR];
+#pragma unroll
+      for (int u = 0; u < UR; ++u) v[u] = (dst[u] && ok[u]) ? __ldg(src[u] + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < UR; ++u)
+        if (dst[u]) dst[u][c] = v[u];
+    }
   }
   peer_finish(row_bases, LB, seq, ids_bases, &LA, seq_ids);
 }

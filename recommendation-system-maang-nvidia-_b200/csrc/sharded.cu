@@ -9,13 +9,14 @@
 //
 // Sharded catalog search (BASELINE config 3; replaces faiss IndexFlatIP.search of app/recommendation_service.py:72 over a
 // catalog too large or too slow for one GPU).  Rank g holds rows [N*g/G, N*(g+1)/G).  One step, all on the caller's stream:
-//   sample pass + top list        rs::shared_begin
-//   tops exchange                 peer_publish_kernel -> every rank's tops region; its last CTA waits for all ranks' tops
+//   sample pass + top list        rs::shared_begin; sample_top_kernel stores each query's list into every rank's tops region
+//                                 (tops exchange), its last CTA waits for all ranks' tops
 //   threshold (acks)              threshold_shared_kernel reads the G lists in place
-//   filter, bucket, re-score      rs::shared_finish, straight into the send buffer [scores | rows | flags | bounds]
-//   lists exchange                peer_publish_kernel -> every rank's lists region; its last CTA waits for all ranks' lists
+//   filter, re-score              rs::shared_finish; the filter appends survivors to the per-query lists itself,
+//                                 select_rescore_kernel stores [scores | rows | flags | bounds] of each query into every
+//                                 rank's lists region (lists exchange), its last CTA waits for all ranks' lists
 //   merge (verifies, acks)        merge_topk_kernel reads the G parts in place and writes D, I, need_exact
-// 11 kernel launches and 3 memsets per step.  Shapes outside the tensor path (or RS_EXACT_FP32) run every shard's
+// 7 kernel launches and 2 memsets per step (round 2 started at 17; 11 with separate publish / bucket / flag launches).  Shapes outside the tensor path (or RS_EXACT_FP32) run every shard's
 // own search (per-shard thresholds or the exact fp32 scan) and share the lists exchange + merge.
 #include <algorithm>
 #include <cstdlib>
@@ -223,24 +224,31 @@ void search_step(rs_index* shard, rs_comm* c, SearchPlan* p, int64_t n_total, co
   const bool tiny = tensor_ok && bf16_scan_applies(shard, nq, k);
   const int rank = (mode != RS_EXACT_FP32 && !tiny) ? shared_rank(c, shard->d, n_total, nq, k) : 0;
   const bool shared = rank > 0 && p->tops != nullptr && p->rank_pad >= round_up(rank, 4);
+  bool lists_published = false;   // the re-scoring kernel wrote the lists message into the peers itself
   if (shared) {
     const int R = static_cast<int>(round_up(rank, 4));
-    rs_tc_session* sess = shared_begin(shard, q, nq, k, R, p->top, R, st);
-    try {
-      publish(p->tops, p->top, nq * R * 4, st);
-    } catch (...) {
-      tc_session_free(sess);
-      throw;
+    // RS_PEER_FUSED_PUBLISH=0 (A/B knob, read per call): the round-2 sequence with separate publish launches
+    const char* e = getenv("RS_PEER_FUSED_PUBLISH");
+    const bool fused = !(e && e[0] == '0');
+    rs_tc_session* sess = shared_begin(shard, q, nq, k, R, p->top, R, st, fused ? p->tops : nullptr);
+    if (!fused) {
+      try {
+        publish(p->tops, p->top, nq * R * 4, st);
+      } catch (...) {
+        tc_session_free(sess);
+        throw;
+      }
     }
     shared_finish(sess, reinterpret_cast<const float*>(p->tops->local), G, p->tops->slot_bytes / 4, R, rank, id_base, sD, k,
-                  sI, k, sF, sB, p->tops);
+                  sI, k, sF, sB, p->tops, fused ? p->lists : nullptr, L.off_I, L.off_F, L.off_B);
+    lists_published = fused;
   } else if (tensor_ok) {
     search_tensor_device(shard, q, nq, k, id_base, sD, k, sI, k, st, sF);
   } else {
     search_exact_device(shard, q, nq, k, id_base, sD, k, sI, k, st);
     RS_CUDA(cudaMemsetAsync(sF, 0, sizeof(int) * static_cast<size_t>(nq), st));
   }
-  publish(p->lists, p->send, L.total, st);
+  if (!lists_published) publish(p->lists, p->send, L.total, st);
   const uint8_t* R0 = p->lists->local;
   const int64_t slot = p->lists->slot_bytes;
   merge_lists_device(reinterpret_cast<const float*>(R0), slot / 4, reinterpret_cast<const int64_t*>(R0 + L.off_I), slot / 8, G,

@@ -75,9 +75,6 @@ struct TcParams {
   uint64_t* cand;       // [nq_pad][cap] FILTER
   int* cand_cnt;        // [nq_pad]      FILTER
   int cap;
-  uint4* rec;           // FILTER: global survivor records {key.lo, key.hi, query row, 0}
-  unsigned* rec_cnt;    // FILTER: number of records appended (may exceed rec_cap: overflow)
-  unsigned rec_cap;
   int* overflow;        // FILTER: set when a staging queue overran
   unsigned* smax;       // [nq_pad][smax_ld] SAMPLE: ordered-uint maxima; slot = (visit % (smax_ld/S))*S + slice
   int smax_ld;
@@ -205,14 +202,16 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       if (MODE == MODE_FILTER && r < nr && qrow[r] < p.nq && !(p.debug & 4)) thr[r] = p.thr[qrow[r]];
     }
     // Survivors are rare (~1e-4 of the scores).  They go to a per-warp shared-memory queue with a shared
-    // atomic (no global round trip on the MMA-critical path); a queue is flushed to the global record list
-    // with ONE global atomic per flush once it holds >= 32 records.
+    // atomic (no global round trip on the MMA-critical path); once a queue holds >= 32 records it is flushed straight
+    // into the per-query candidate lists: one global atomic per record, 32 of them in flight per pass, so a flush costs
+    // ONE round trip per 32 records (what appending to a global record list cost -- and no bucketing launch afterwards).
+    // A list that overruns is seen by select_rescore_kernel (count > cap): that query is repeated exactly.
     auto flush = [&](int n) {
-      unsigned base = 0;
-      if (lane == 0) base = atomicAdd(p.rec_cnt, static_cast<unsigned>(n));
-      base = __shfl_sync(0xFFFFFFFFu, base, 0);
-      for (int t = lane; t < n; t += 32)
-        if (base + t < p.rec_cap) p.rec[base + t] = wq[t];
+      for (int t = lane; t < n; t += 32) {
+        const uint4 r = wq[t];
+        const int pos = atomicAdd(&p.cand_cnt[r.z], 1);
+        if (pos < p.cap) p.cand[(int64_t)r.z * p.cap + pos] = (static_cast<uint64_t>(r.y) << 32) | r.x;
+      }
       __syncwarp();
       if (lane == 0) *wq_cnt = 0;
       __syncwarp();
@@ -412,33 +411,61 @@ __global__ void __launch_bounds__(256) threshold_small_kernel(const unsigned* __
 
 constexpr int SEL_MAX_M = 1024;   // most survivors of the margin cut that one query may re-score
 
+// Where the kernels of a sharded step put what the other ranks need.  bases == nullptr: plain local outputs.  Otherwise the
+// kernel PUBLISHES: it writes its part into slot `rank` of every rank's peer-memory region (csrc/peer.cu) -- what a separate
+// peer_publish_kernel launch would copy there -- after the peers have acknowledged the previous step, and its last CTA
+// raises this rank's flag in every region and then waits until every rank's message of this step has arrived here (one
+// warp spins; the consumer kernel queued behind finds its data present).
+struct PeerOut {
+  uint8_t* const* bases = nullptr;
+  rsp::PeerLayout PL{};
+  int64_t off_I = 0, off_F = 0, off_B = 0;   // lists message: scores f32 [nq, k] at 0 | rows int64 [nq, k] | flags | bounds
+};
+
+__device__ __forceinline__ void publish_done(const PeerOut& out, uint64_t seq, int* s_last) {
+  if (threadIdx.x == 0) *s_last = 0;
+  __syncthreads();
+  rsp::peer_finish(out.bases, out.PL, seq, nullptr, nullptr, 0, s_last);
+  __syncthreads();
+  if (*s_last && threadIdx.x < out.PL.world)
+    rsp::spin_until(reinterpret_cast<const uint64_t*>(out.bases[out.PL.rank] + out.PL.off_flags) + threadIdx.x, seq,
+                    out.PL.spin_budget, "a peer's message");
+}
+
 // step 4: verify, cut, exact re-score, final order.  One CTA per query.
 __global__ void __launch_bounds__(SEL_NT) select_rescore_kernel(
     const uint64_t* __restrict__ cand, const int* __restrict__ cand_cnt, int cap, const float* __restrict__ thr,
     const float* __restrict__ eps2, const float* __restrict__ q, const float* __restrict__ xb, int k, int64_t id_base,
     float* __restrict__ D, int64_t ldD, int64_t* __restrict__ I, int64_t ldI, int* __restrict__ flags,
-    int* __restrict__ n_flagged, float* __restrict__ bound) {
+    int* __restrict__ n_flagged, float* __restrict__ bound, const int* __restrict__ overflow, int* __restrict__ need_exact,
+    const PeerOut out) {
   // bound == nullptr: the threshold was this index's own guess and is verified here (s_hat_(k) - 2 eps >= tau).
   // bound != nullptr ("shared threshold" mode of a partitioned catalog): tau came from the union of all shards'
   // samples, so this shard may hold fewer than k survivors.  It returns the exact top-min(c, k) of its survivors
   // (padded with D = -FLT_MAX, I = -1) and bound[q] = tau + eps; the caller verifies AFTER merging the shards that
   // the k-th merged score >= every shard's bound (a row that failed a shard's filter has s_hat < tau, hence an exact
   // score < tau + eps, and cannot belong to the top-k then).
+  // need_exact != nullptr: need_exact[q] = 1 when the row of D / I is not final (the guess was not verified, a list or a
+  // staging queue of the filter overran) -- what the host reads from `flags` in the synchronous form.
+  // out.bases != nullptr: D / I / need_exact / bound are not used; the query's part of the lists message goes to every rank.
   __shared__ uint64_t keys[CAND_CAP];
-  __shared__ uint32_t sel[SEL_MAX_M];
+  __shared__ __align__(16) uint32_t sel[SEL_MAX_M];
   __shared__ __align__(16) float qs[DK];
   __shared__ unsigned hist[256];
   __shared__ unsigned state[2];
   __shared__ int s_m;
+  __shared__ int s_last;
   const int tid = threadIdx.x;
   const int qi = blockIdx.x;
+  uint64_t seq = 0;
+  if (out.bases) seq = rsp::peer_begin(out.bases[out.PL.rank], out.PL);
   const int c_raw = cand_cnt[qi];
   const int c = min(c_raw, cap);
   if (tid < DK) qs[tid] = q[(int64_t)qi * DK + tid];
   if (tid == 0) s_m = 0;
   for (int i = tid; i < c; i += SEL_NT) keys[i] = cand[(int64_t)qi * cap + i];
   __syncthreads();
-  const bool shared_thr = bound != nullptr;
+  const bool shared_thr = bound != nullptr || out.bases != nullptr;
   bool ok = c_raw <= cap && (shared_thr || c >= k);
   float cutoff = -INFINITY;
   if (ok && c >= k) {   // uniform
@@ -447,7 +474,6 @@ __global__ void __launch_bounds__(SEL_NT) select_rescore_kernel(
     cutoff = ordered_to_f32(kth) - eps2[qi];
     if (!shared_thr) ok = cutoff >= thr[qi];   // the guess was low enough: the list provably holds the whole top-k
   }
-  if (shared_thr && tid == 0) bound[qi] = thr[qi] + 0.5f * eps2[qi];
   if (ok) {
     // survivors of the margin cut: s_hat >= s_hat_(k) - 2 eps
     for (int i = tid; i < c; i += SEL_NT)
@@ -458,66 +484,110 @@ __global__ void __launch_bounds__(SEL_NT) select_rescore_kernel(
     __syncthreads();
     ok = s_m <= SEL_MAX_M;
   }
-  if (!ok) {
+  // the sorted list is staged in shared memory (sel[] is free after the re-score) and leaves the CTA in coalesced stores
+  float* oD = reinterpret_cast<float*>(sel);            // [128]
+  int64_t* oI = reinterpret_cast<int64_t*>(sel + 128);  // [128]
+  if (ok) {
+    const int m = s_m;
+    // exact re-score with the stated fp32 FMA chain; keys[] is free again and receives the exact keys
+    for (int i = tid; i < m; i += SEL_NT) {
+      const uint32_t row = sel[i];
+      const float4* xr = reinterpret_cast<const float4*>(xb + (int64_t)row * DK);
+      float acc = 0.0f;
+#pragma unroll 16
+      for (int c4 = 0; c4 < DK / 4; ++c4) {
+        const float4 xv = __ldg(xr + c4);
+        const float4 qv = *reinterpret_cast<const float4*>(qs + c4 * 4);
+        acc = fmaf(qv.x, xv.x, acc);
+        acc = fmaf(qv.y, xv.y, acc);
+        acc = fmaf(qv.z, xv.z, acc);
+        acc = fmaf(qv.w, xv.w, acc);
+      }
+      keys[i] = pack_key(acc, row);
+    }
+    __syncthreads();
+    // final order by counting: keys are distinct (the row is part of the key), so rank = #better keys
+    for (int i = tid; i < m; i += SEL_NT) {
+      const uint64_t mine = keys[i];
+      int rank = 0;
+      for (int jx = 0; jx < m; ++jx) rank += keys[jx] > mine ? 1 : 0;
+      if (rank < k) {
+        oD[rank] = key_score(mine);
+        oI[rank] = id_base + static_cast<int64_t>(key_row(mine));
+      }
+    }
+    for (int i = m + tid; i < k; i += SEL_NT) {   // shared-threshold mode only: fewer than k survivors in this shard
+      oD[i] = -FLT_MAX;
+      oI[i] = -1;
+    }
+    __syncthreads();
+  } else if (tid == 0) {
+    flags[qi] = 1;
+    atomicAdd(n_flagged, 1);
+  }
+  const int need = (!ok || *overflow != 0) ? 1 : 0;
+  const float bnd = thr[qi] + 0.5f * eps2[qi];
+  if (!out.bases) {
+    if (ok)
+      for (int i = tid; i < k; i += SEL_NT) {
+        D[qi * ldD + i] = oD[i];
+        I[qi * ldI + i] = oI[i];
+      }
     if (tid == 0) {
-      flags[qi] = 1;
-      atomicAdd(n_flagged, 1);
+      if (bound) bound[qi] = bnd;
+      if (need_exact) need_exact[qi] = need;
     }
     return;
   }
-  const int m = s_m;
-  // exact re-score with the stated fp32 FMA chain; keys[] is free again and receives the exact keys
-  for (int i = tid; i < m; i += SEL_NT) {
-    const uint32_t row = sel[i];
-    const float4* xr = reinterpret_cast<const float4*>(xb + (int64_t)row * DK);
-    float acc = 0.0f;
-#pragma unroll 16
-    for (int c4 = 0; c4 < DK / 4; ++c4) {
-      const float4 xv = __ldg(xr + c4);
-      const float4 qv = *reinterpret_cast<const float4*>(qs + c4 * 4);
-      acc = fmaf(qv.x, xv.x, acc);
-      acc = fmaf(qv.y, xv.y, acc);
-      acc = fmaf(qv.z, xv.z, acc);
-      acc = fmaf(qv.w, xv.w, acc);
+  for (int g = 0; g < out.PL.world; ++g) {
+    uint8_t* slot = out.bases[g] + out.PL.rank * out.PL.slot_bytes;
+    if (ok) {
+      float* gD = reinterpret_cast<float*>(slot) + (int64_t)qi * k;
+      int64_t* gI = reinterpret_cast<int64_t*>(slot + out.off_I) + (int64_t)qi * k;
+      for (int i = tid; i < k; i += SEL_NT) gD[i] = oD[i];
+      for (int i = tid; i < k; i += SEL_NT) gI[i] = oI[i];
     }
-    keys[i] = pack_key(acc, row);
-  }
-  __syncthreads();
-  // final order by counting: keys are distinct (the row is part of the key), so rank = #better keys
-  for (int i = tid; i < m; i += SEL_NT) {
-    const uint64_t mine = keys[i];
-    int rank = 0;
-    for (int jx = 0; jx < m; ++jx) rank += keys[jx] > mine ? 1 : 0;
-    if (rank < k) {
-      D[qi * ldD + rank] = key_score(mine);
-      I[qi * ldI + rank] = id_base + static_cast<int64_t>(key_row(mine));
+    if (tid == 0) {
+      reinterpret_cast<int*>(slot + out.off_F)[qi] = need;
+      reinterpret_cast<float*>(slot + out.off_B)[qi] = bnd;
     }
   }
-  for (int i = m + tid; i < k; i += SEL_NT) {   // shared-threshold mode only: fewer than k survivors in this shard
-    D[qi * ldD + i] = -FLT_MAX;
-    I[qi * ldI + i] = -1;
-  }
+  publish_done(out, seq, &s_last);
 }
 
 // The `R` largest of each query's sample maxima, as floats, in no particular order (what a shard contributes to the
-// shared threshold of a partitioned catalog).  R <= n_vals <= 1024.
+// shared threshold of a partitioned catalog).  R <= n_vals <= 1024.  pub.bases != nullptr: the list goes
+// into slot `rank` of every rank's tops region (row stride R floats) instead of `out` -- see PeerOut.
 __global__ void __launch_bounds__(256) sample_top_kernel(const unsigned* __restrict__ smax, int n_vals, int R,
-                                                         float* __restrict__ out, int64_t ld_out) {
+                                                         float* __restrict__ out, int64_t ld_out, const PeerOut pub) {
   __shared__ unsigned vals[1024];
   __shared__ unsigned hist[256];
   __shared__ unsigned state[2];
+  __shared__ float top[1024];
   __shared__ int n_gt;
+  __shared__ int s_last;
   const int tid = threadIdx.x;
   const int qi = blockIdx.x;
+  uint64_t seq = 0;
+  if (pub.bases) seq = rsp::peer_begin(pub.bases[pub.PL.rank], pub.PL);
   for (int i = tid; i < n_vals; i += 256) vals[i] = smax[(int64_t)qi * n_vals + i];
   if (tid == 0) n_gt = 0;
   __syncthreads();
   const uint32_t kth = block_kth_largest<256>([&](int i) { return vals[i]; }, n_vals, R, hist, state, tid);
-  float* o = out + (int64_t)qi * ld_out;
   for (int i = tid; i < n_vals; i += 256)
-    if (vals[i] > kth) o[atomicAdd(&n_gt, 1)] = ordered_to_f32(vals[i]);   // fewer than R of these
+    if (vals[i] > kth) top[atomicAdd(&n_gt, 1)] = ordered_to_f32(vals[i]);   // fewer than R of these
   __syncthreads();
-  for (int i = n_gt + tid; i < R; i += 256) o[i] = ordered_to_f32(kth);    // the rest are ties at the R-th value
+  for (int i = n_gt + tid; i < R; i += 256) top[i] = ordered_to_f32(kth);     // the rest are ties at the R-th value
+  __syncthreads();
+  if (!pub.bases) {
+    for (int i = tid; i < R; i += 256) out[(int64_t)qi * ld_out + i] = top[i];
+    return;
+  }
+  for (int g = 0; g < pub.PL.world; ++g) {
+    float* o = reinterpret_cast<float*>(pub.bases[g] + pub.PL.rank * pub.PL.slot_bytes) + (int64_t)qi * R;
+    for (int i = tid; i < R; i += 256) o[i] = top[i];
+  }
+  publish_done(pub, seq, &s_last);
 }
 
 // tau_q = the `rank`-th largest of the union of the shards' top-R lists: tops[g * part_ld + q * R + i]
@@ -553,9 +623,8 @@ struct Workspace {
   float* thr = nullptr;
   unsigned* smax = nullptr;
   int* cnt = nullptr;
-  int* flags = nullptr;   // [nq_pad + 4]: per-query flag, then {n_flagged, queue overflow, record count, -}
+  int* flags = nullptr;   // [nq_pad + 4]: per-query flag, then {n_flagged, queue overflow, -, -}
   uint64_t* cand = nullptr;
-  uint4* rec = nullptr;
   cudaStream_t st;
   explicit Workspace(cudaStream_t s) : st(s) {}
   ~Workspace() {
@@ -566,7 +635,6 @@ struct Workspace {
     cudaFreeAsync(cnt, st);
     cudaFreeAsync(flags, st);
     cudaFreeAsync(cand, st);
-    cudaFreeAsync(rec, st);
   }
 };
 
@@ -604,18 +672,6 @@ void launch_filter(const CUtensorMap& tq, const CUtensorMap& tx, TcParams p, int
   RS_LAUNCH_CHECK();
 }
 
-// survivor records -> per-query candidate lists (the global atomics live here, off the MMA-critical path)
-__global__ void __launch_bounds__(256) bucket_kernel(const uint4* __restrict__ rec, const unsigned* __restrict__ rec_cnt,
-                                                     unsigned rec_cap, uint64_t* __restrict__ cand,
-                                                     int* __restrict__ cand_cnt, int cap) {
-  const unsigned n = min(*rec_cnt, rec_cap);
-  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const uint4 r = rec[i];
-    const int pos = atomicAdd(&cand_cnt[r.z], 1);
-    if (pos < cap) cand[(int64_t)r.z * cap + pos] = (static_cast<uint64_t>(r.y) << 32) | r.x;
-  }
-}
-
 }  // namespace
 
 namespace rs {
@@ -634,14 +690,7 @@ bool tensor_path_supported(const rs_index* h, int64_t nq, int k) {
 }
 
 // flags layout of a search chunk: [0, nq) per-query "guess not verified", [nq_pad] their count, [nq_pad + 1] a staging
-// queue overran, [nq_pad + 2] records written (> rec_cap: the record list overran)
-__global__ void export_flags_kernel(const int* __restrict__ flags, int nq, int nq_pad, unsigned rec_cap,
-                                    int* __restrict__ need_exact) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nq) return;
-  const bool all = flags[nq_pad + 1] != 0 || static_cast<unsigned>(flags[nq_pad + 2]) > rec_cap;
-  need_exact[i] = (all || flags[i] != 0) ? 1 : 0;
-}
+// queue of the filter overran (nothing is trusted then)
 
 // Rows covered by the threshold sample of an index with `ntotal` rows: ~5 % of its 256-row tiles (64..2048 tiles),
 // never the zero-padded tail tile.
@@ -673,7 +722,6 @@ struct rs_tc_session {
   const float* q;
   int nq, k, nq_pad, n_vals;
   int64_t ntiles, n_sample;
-  unsigned rec_cap;
   cudaStream_t st;
   Workspace ws;
   CUtensorMap tq;
@@ -712,8 +760,6 @@ std::unique_ptr<rs_tc_session> tc_begin(rs_index* h, const float* qc, int cq, in
   RS_CUDA(cudaMallocAsync(&ws.cnt, sizeof(int) * nq_pad, st));
   RS_CUDA(cudaMallocAsync(&ws.flags, sizeof(int) * (nq_pad + 4), st));
   RS_CUDA(cudaMallocAsync(&ws.cand, sizeof(uint64_t) * (size_t)nq_pad * CAND_CAP, st));
-  s.rec_cap = static_cast<unsigned>(nq_pad) * CAND_CAP;
-  RS_CUDA(cudaMallocAsync(&ws.rec, sizeof(uint4) * (size_t)s.rec_cap, st));
   RS_CUDA(cudaMemsetAsync(ws.flags + nq_pad, 0, sizeof(int) * 4, st));
   {
     ProfScope prof(RS_PROF_RESCORE, st);
@@ -735,10 +781,7 @@ std::unique_ptr<rs_tc_session> tc_begin(rs_index* h, const float* qc, int cq, in
   p.cap = CAND_CAP;
   p.smax = ws.smax;
   p.smax_ld = n_vals;
-  p.rec = ws.rec;
-  p.rec_cap = s.rec_cap;
   p.overflow = ws.flags + nq_pad + 1;
-  p.rec_cnt = reinterpret_cast<unsigned*>(ws.flags + nq_pad + 2);
   {
     ProfScope prof(RS_PROF_SAMPLE, st);
     TcParams ps = p;
@@ -751,7 +794,8 @@ std::unique_ptr<rs_tc_session> tc_begin(rs_index* h, const float* qc, int cq, in
 }
 
 // the threshold must have been written to s.ws.thr (and cnt / flags cleared) by one of the threshold kernels
-void tc_finish(rs_tc_session& s, int64_t id_base, float* D, int64_t ldD, int64_t* I, int64_t ldI, float* bound) {
+void tc_finish(rs_tc_session& s, int64_t id_base, float* D, int64_t ldD, int64_t* I, int64_t ldI, float* bound, int* need_exact,
+               const PeerOut& out = PeerOut{}) {
   rs_index* h = s.h;
   cudaStream_t st = s.st;
   {
@@ -762,10 +806,9 @@ void tc_finish(rs_tc_session& s, int64_t id_base, float* D, int64_t ldD, int64_t
     launch_filter<MODE_FILTER>(s.tq, h->tmap_bf16, pm, h->device, st);
   }
   ProfScope prof(RS_PROF_RESCORE, st);
-  bucket_kernel<<<sm_count() * 4, 256, 0, st>>>(s.ws.rec, s.p.rec_cnt, s.rec_cap, s.ws.cand, s.ws.cnt, CAND_CAP);
-  RS_LAUNCH_CHECK();
   select_rescore_kernel<<<s.nq, SEL_NT, 0, st>>>(s.ws.cand, s.ws.cnt, CAND_CAP, s.ws.thr, s.ws.eps2, s.q, h->xb, s.k, id_base,
-                                                 D, ldD, I, ldI, s.ws.flags, s.ws.flags + s.nq_pad, bound);
+                                                 D, ldD, I, ldI, s.ws.flags, s.ws.flags + s.nq_pad, bound,
+                                                 s.ws.flags + s.nq_pad + 1, need_exact, out);
   RS_LAUNCH_CHECK();
 }
 
@@ -784,7 +827,6 @@ void search_tensor_device(rs_index* h, const float* q, int64_t nq, int k, int64_
     auto sp = tc_begin(h, qc, cq, k, st);
     rs_tc_session& s = *sp;
     const int nq_pad = s.nq_pad;
-    const unsigned rec_cap = s.rec_cap;
     Workspace& ws = s.ws;
     if (h->ntotal < 65536) {
       ProfScope prof(RS_PROF_RESCORE, st);
@@ -798,18 +840,14 @@ void search_tensor_device(rs_index* h, const float* q, int64_t nq, int k, int64_
       threshold_kernel<<<cq, 256, 0, st>>>(ws.smax, s.n_vals, rank, ws.thr, ws.cnt, ws.flags);
       RS_LAUNCH_CHECK();
     }
-    tc_finish(s, id_base, D + q0 * ldD, ldD, I + q0 * ldI, ldI, nullptr);
-    if (need_exact) {   // deferred: the caller resolves flagged queries (after its own exchange step)
-      export_flags_kernel<<<(cq + 255) / 256, 256, 0, st>>>(ws.flags, cq, nq_pad, rec_cap, need_exact + q0);
-      RS_LAUNCH_CHECK();
-      continue;
-    }
+    tc_finish(s, id_base, D + q0 * ldD, ldD, I + q0 * ldI, ldI, nullptr, need_exact ? need_exact + q0 : nullptr);
+    if (need_exact) continue;   // deferred: the caller resolves flagged queries (after its own exchange step)
     // step 5: the (rare) queries whose guess could not be verified go through the exact scan
     std::vector<int> flags(nq_pad + 4);
     RS_CUDA(cudaMemcpyAsync(flags.data(), ws.flags, sizeof(int) * (nq_pad + 4), cudaMemcpyDeviceToHost, st));
     RS_CUDA(cudaStreamSynchronize(st));
-    if (flags[nq_pad + 1] != 0 || static_cast<unsigned>(flags[nq_pad + 2]) > rec_cap) {
-      // a staging queue or the record list overran (scores packed inside the margin): nothing is trusted
+    if (flags[nq_pad + 1] != 0) {
+      // a staging queue of the filter overran (scores packed inside the margin): nothing is trusted
       search_exact_device(h, qc, cq, k, id_base, D + q0 * ldD, ldD, I + q0 * ldI, ldI, st);
       flags[nq_pad] = cq;
     } else if (flags[nq_pad] > 0) {
@@ -824,19 +862,35 @@ void search_tensor_device(rs_index* h, const float* q, int64_t nq, int k, int64_
 }
 
 // ---- shared-threshold search of one shard of a partitioned catalog (see rs_index_shared_begin in the header) ----
-rs_tc_session* shared_begin(rs_index* h, const float* q, int64_t nq, int k, int R, float* top, int64_t ld_top, cudaStream_t st) {
+static PeerOut peer_out(rs_peer* region, int64_t off_I = 0, int64_t off_F = 0, int64_t off_B = 0) {
+  PeerOut o;
+  if (region) {
+    RS_CHECK(region->connected, "peer region is not connected");
+    o.bases = region->d_bases;
+    o.PL = rsp::layout_of(region);
+    o.off_I = off_I;
+    o.off_F = off_F;
+    o.off_B = off_B;
+  }
+  return o;
+}
+
+rs_tc_session* shared_begin(rs_index* h, const float* q, int64_t nq, int k, int R, float* top, int64_t ld_top, cudaStream_t st,
+                            rs_peer* publish_tops) {
   RS_CHECK(nq <= tensor_max_queries(), "too many queries for one shared-threshold search");
   RS_CHECK(h->ntotal >= 65536, "shared-threshold searches need shards of at least 65,536 rows");
   auto sp = tc_begin(h, q, static_cast<int>(nq), k, st);
   RS_CHECK(R >= 1 && R <= sp->n_vals, "R must be in [1, number of sample maxima]");
+  RS_CHECK(!publish_tops || nq * R * 4 <= publish_tops->slot_bytes, "tops message longer than the region's slot");
   ProfScope prof(RS_PROF_RESCORE, st);
-  sample_top_kernel<<<static_cast<unsigned>(nq), 256, 0, st>>>(sp->ws.smax, sp->n_vals, R, top, ld_top);
+  sample_top_kernel<<<static_cast<unsigned>(nq), 256, 0, st>>>(sp->ws.smax, sp->n_vals, R, top, ld_top, peer_out(publish_tops));
   RS_LAUNCH_CHECK();
   return sp.release();
 }
 
 void shared_finish(rs_tc_session* sp, const float* tops, int n_parts, int64_t part_ld, int R, int rank, int64_t id_base,
-                   float* D, int64_t ldD, int64_t* I, int64_t ldI, int* need_exact, float* bound, rs_peer* tops_region) {
+                   float* D, int64_t ldD, int64_t* I, int64_t ldI, int* need_exact, float* bound, rs_peer* tops_region,
+                   rs_peer* publish_lists, int64_t off_I, int64_t off_F, int64_t off_B) {
   std::unique_ptr<rs_tc_session> own(sp);
   rs_tc_session& s = *sp;
   RS_CHECK(n_parts >= 1 && R >= 1 && n_parts * R <= 1024, "shards x R must be <= 1024");
@@ -848,9 +902,9 @@ void shared_finish(rs_tc_session* sp, const float* tops, int n_parts, int64_t pa
                                                     tops_region ? rsp::layout_of(tops_region) : rsp::PeerLayout{});
     RS_LAUNCH_CHECK();
   }
-  tc_finish(s, id_base, D, ldD, I, ldI, bound);
-  export_flags_kernel<<<(s.nq + 255) / 256, 256, 0, s.st>>>(s.ws.flags, s.nq, s.nq_pad, s.rec_cap, need_exact);
-  RS_LAUNCH_CHECK();
+  RS_CHECK(!publish_lists || off_B + (int64_t)s.nq * 4 <= publish_lists->slot_bytes, "lists message longer than the region's slot");
+  RS_CHECK(publish_lists || bound != nullptr, "bound is NULL");
+  tc_finish(s, id_base, D, ldD, I, ldI, bound, need_exact, peer_out(publish_lists, off_I, off_F, off_B));
 }
 
 void tc_session_free(rs_tc_session* sp) { delete sp; }

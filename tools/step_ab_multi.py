@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """A/B of the sharded search step (10M x 128 catalog, 1,024 queries, top-100; BASELINE configs[2]) under torchrun:
-where the exchange wait sits (the publishing kernel's last CTA vs the consumer kernels), copy-out vs graph-owned outputs.
+the lists / tops published by the kernels that build them (7 launches) vs separate publish launches (9), copy-out vs
+graph-owned outputs.
 Device ms per step, max over ranks, CUDA-graph replay.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29544 tools/step_ab_multi.py
@@ -36,9 +37,9 @@ def main():
     rs.normalize_L2(q)
     res = {}
     ref = None
-    for name, env, reuse in (("wait_in_publish", "0", True), ("wait_in_consumer", "1", True), ("wait_in_publish_copy_out", "0", False),
-                             ("wait_in_publish_again", "0", True)):
-        os.environ["RS_PEER_WAIT_IN_CONSUMER"] = env
+    for name, env, reuse in (("fused_publish", "1", True), ("separate_publish", "0", True), ("fused_publish_copy_out", "1", False),
+                             ("fused_publish_again", "1", True)):
+        os.environ["RS_PEER_FUSED_PUBLISH"] = env
         sidx = ShardedIndexFlatIP(128, N, local_index=base.local)
         sidx.exchange, sidx.use_graph, sidx.reuse_outputs = "p2p", True, reuse
         for _ in range(30):
@@ -66,7 +67,7 @@ def main():
         print(json.dumps({"n_gpus": world, "ms_per_step": res}, indent=1), flush=True)
         out = Path(__file__).resolve().parent.parent / "gpurun_out"
         out.mkdir(exist_ok=True)
-        (out / f"r02_step_ab_{world}gpu.json").write_text(json.dumps({"n_gpus": world, "ms_per_step": res}, indent=1))
+        (out / f"r02_step_ab2_{world}gpu.json").write_text(json.dumps({"n_gpus": world, "ms_per_step": res}, indent=1))
     dist.barrier()
     base.close()
     dist.destroy_process_group()
