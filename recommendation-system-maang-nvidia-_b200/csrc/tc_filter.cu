@@ -55,8 +55,12 @@ constexpr int SLICE_COLS = BN / EPI_SLICES; // accumulator columns per epilogue 
 constexpr int TC_THREADS = 128 + EPI_WARPS * 32;
 constexpr int QTILE_BYTES = BM * DK * 2;  // 32 KB: two [128 x 64] bf16 swizzled halves
 constexpr int STAGE_BYTES = BN * DK * 2;  // 64 KB: two [256 x 64] bf16 swizzled halves
-constexpr int WQ_CAP = 64;               // survivor records per epilogue-warp staging queue
-constexpr int TC_SMEM = R_MAX * QTILE_BYTES + NSTAGE * STAGE_BYTES + 256 + EPI_WARPS * WQ_CAP * 16 + 1024;
+constexpr int WQ_CAP = 64;               // survivor records per extraction-warp staging queue
+constexpr int RING = 8;                  // hit chunks an epilogue warp may have handed over and not yet extracted
+constexpr int RING_ENTRY = 144;          // 32 scores + {query row, first catalog row, threshold, -}
+constexpr int CTRL_BYTES = 512;          // mbarriers, TMEM slot, ring heads / tails
+constexpr int TC_SMEM = R_MAX * QTILE_BYTES + NSTAGE * STAGE_BYTES + CTRL_BYTES + EPI_WARPS * RING * RING_ENTRY +
+                        2 * WQ_CAP * 16 + 1024;
 constexpr int CAND_CAP = 4096;           // candidate list capacity per query
 constexpr int SEL_NT = 256;
 constexpr float C_EPS = 0.00390625f * 1.0625f;
@@ -80,7 +84,7 @@ struct TcParams {
   int smax_ld;
   float* dump;          // [nq_pad][dump_ld] DUMP (debug: every low-precision score)
   int64_t dump_ld;
-  int debug;            // perf experiments only: 1 = epilogue skips TMEM reads, 2 = issuer skips the MMAs
+  int debug;            // perf experiments only: 1 = epilogue skips TMEM reads, 2 = issuer skips the MMAs, 4 = no survivors, 8 = no flush
 };
 
 template <int MODE>
@@ -98,8 +102,12 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   uint64_t* tfull = empty + NSTAGE;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  int* wqueue_cnt = reinterpret_cast<int*>(tmem_slot + 2);             // [EPI_WARPS]
-  uint4* wqueue = reinterpret_cast<uint4*>(bars + 32);                  // [EPI_WARPS][WQ_CAP], 256 B after bars
+  // FILTER: hit chunks travel from the epilogue warps to the two extraction warps through per-warp rings
+  volatile int* heads = reinterpret_cast<volatile int*>(reinterpret_cast<uint8_t*>(bars) + 128);   // [EPI_WARPS] entries written
+  volatile int* tails = reinterpret_cast<volatile int*>(reinterpret_cast<uint8_t*>(bars) + 192);   // [EPI_WARPS] entries consumed
+  volatile int* epi_done = reinterpret_cast<volatile int*>(reinterpret_cast<uint8_t*>(bars) + 256);
+  uint8_t* rings = reinterpret_cast<uint8_t*>(bars) + CTRL_BYTES;       // [EPI_WARPS][RING][RING_ENTRY]
+  uint4* wqueue = reinterpret_cast<uint4*>(rings + EPI_WARPS * RING * RING_ENTRY);   // [2][WQ_CAP]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -125,7 +133,11 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     }
     fence_mbar_init();
   }
-  if (threadIdx.x < EPI_WARPS) wqueue_cnt[threadIdx.x] = 0;
+  if (threadIdx.x < EPI_WARPS) {
+    heads[threadIdx.x] = 0;
+    tails[threadIdx.x] = 0;
+  }
+  if (threadIdx.x == 0) *epi_done = 0;
   if (warp == 1) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
@@ -185,14 +197,75 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         umma_commit(&empty[s]);
       }
     }
+  } else if (MODE == MODE_FILTER && (warp == 2 || warp == 3)) {
+    // ---------------- survivor extraction ----------------
+    // Survivors are rare (~1e-4 of the scores) but finding them inside a 32-score chunk is divergent, branchy code: done
+    // by the epilogue lane that owns the row it cost 15 % of the kernel (a lone active lane walking compare chains between
+    // two TMEM loads).  The epilogue only DETECTS a hit chunk (chunk maximum >= tau) and hands its 32 scores over through a
+    // shared-memory ring; here 32 lanes test one score each, queue the survivors, and append a full queue to the per-query
+    // candidate lists with 32 global atomics in flight (one round trip per 32 records).  A list that overruns is seen by
+    // select_rescore_kernel (count > cap): that query is repeated exactly.
+    const int cw = warp - 2;                       // epilogue warps [8 cw, 8 cw + 8) are this warp's producers
+    uint4* wq = wqueue + cw * WQ_CAP;
+    int qcnt = 0;
+    int tail[EPI_WARPS / 2];
+#pragma unroll
+    for (int pw = 0; pw < EPI_WARPS / 2; ++pw) tail[pw] = 0;
+    auto flush = [&]() {
+      __syncwarp();
+      for (int t = lane; t < qcnt; t += 32) {
+        const uint4 r = wq[t];
+        const int pos = atomicAdd(&p.cand_cnt[r.z], 1);
+        if (pos < p.cap) p.cand[(int64_t)r.z * p.cap + pos] = (static_cast<uint64_t>(r.y) << 32) | r.x;
+      }
+      __syncwarp();
+      qcnt = 0;
+    };
+    for (;;) {
+      const bool finished = *epi_done == EPI_WARPS;   // read BEFORE the scan: nothing is published after it
+      __threadfence_block();
+      bool any = false;
+#pragma unroll
+      for (int pw = 0; pw < EPI_WARPS / 2; ++pw) {
+        const int ew = cw * (EPI_WARPS / 2) + pw;
+        const int head = heads[ew];
+        if (head != tail[pw]) {   // uniform
+          any = true;
+          __threadfence_block();
+          while (tail[pw] != head) {
+            const uint8_t* ent = rings + (ew * RING + (tail[pw] & (RING - 1))) * RING_ENTRY;
+            const float v = reinterpret_cast<const float*>(ent)[lane];
+            const int4 hdr = *reinterpret_cast<const int4*>(ent + 128);
+            const int64_t idx = static_cast<int64_t>(static_cast<uint32_t>(hdr.y)) + lane;
+            const bool hit = v >= __int_as_float(hdr.z) && idx < p.n_items && !(p.debug & 16);
+            const unsigned hb = __ballot_sync(0xFFFFFFFFu, hit);
+            if (hit) {
+              const uint64_t key = pack_key(v, static_cast<uint32_t>(idx));
+              wq[qcnt + __popc(hb & ((1u << lane) - 1u))] =
+                  make_uint4(static_cast<uint32_t>(key), static_cast<uint32_t>(key >> 32), static_cast<uint32_t>(hdr.x), 0u);
+            }
+            qcnt += __popc(hb);
+            ++tail[pw];
+            __syncwarp();
+            if (lane == 0) tails[ew] = tail[pw];      // the slot may be overwritten
+            if (qcnt > WQ_CAP - 32) flush();
+          }
+        }
+      }
+      if (!any) {
+        if (finished) break;
+        __nanosleep(200);
+      }
+    }
+    if (qcnt > 0) flush();
   } else if (warp >= 4) {
     // ---------------- epilogue ----------------
     const int ew = warp - 4;
     const int quarter = warp & 3;          // TMEM lanes [32*quarter, 32*quarter + 32) are this warp's
     const int slice = ew >> 2;             // columns [SLICE_COLS*slice, SLICE_COLS*(slice+1)) of the accumulator
     const int row_in_tile = quarter * 32 + lane;
-    uint4* wq = wqueue + ew * WQ_CAP;      // this warp's staging queue for survivors
-    int* wq_cnt = wqueue_cnt + ew;
+    uint8_t* ring = rings + ew * RING * RING_ENTRY;   // FILTER: this warp's ring of hit chunks
+    int head = 0;                                    // entries written to it (warp-uniform)
     float thr[R_MAX];
     int qrow[R_MAX];
 #pragma unroll
@@ -201,21 +274,6 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       thr[r] = INFINITY;
       if (MODE == MODE_FILTER && r < nr && qrow[r] < p.nq && !(p.debug & 4)) thr[r] = p.thr[qrow[r]];
     }
-    // Survivors are rare (~1e-4 of the scores).  They go to a per-warp shared-memory queue with a shared
-    // atomic (no global round trip on the MMA-critical path); once a queue holds >= 32 records it is flushed straight
-    // into the per-query candidate lists: one global atomic per record, 32 of them in flight per pass, so a flush costs
-    // ONE round trip per 32 records (what appending to a global record list cost -- and no bucketing launch afterwards).
-    // A list that overruns is seen by select_rescore_kernel (count > cap): that query is repeated exactly.
-    auto flush = [&](int n) {
-      for (int t = lane; t < n; t += 32) {
-        const uint4 r = wq[t];
-        const int pos = atomicAdd(&p.cand_cnt[r.z], 1);
-        if (pos < p.cap) p.cand[(int64_t)r.z * p.cap + pos] = (static_cast<uint64_t>(r.y) << 32) | r.x;
-      }
-      __syncwarp();
-      if (lane == 0) *wq_cnt = 0;
-      __syncwarp();
-    };
     uint32_t acc_it = 0;
     for (int64_t i = 0; i < n_my; ++i) {
       const int64_t visit = j + i * cpg;
@@ -245,25 +303,28 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                         fmaxf(v[8 * u + 6], v[8 * u + 7]));
           const float m = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
           if (MODE == MODE_FILTER) {
-            if (m >= thr[r]) {
+            // hit chunks (chunk maximum >= tau: ~7 % of a warp's chunks) go to the extraction warps as they are
+            const bool hit = m >= thr[r] && !((p.debug & 32) && c == 0) && !((p.debug & 64) && c == 1);
+            unsigned rem = __ballot_sync(0xFFFFFFFFu, hit);
+            while (rem) {   // uniform; one pass unless the ring is nearly full
+              const int room = RING - (head - __shfl_sync(0xFFFFFFFFu, tails[ew], 0));
+              if (room <= 0) continue;   // the extraction warp is behind (adversarial data): wait for a slot
+              const int mine = __popc(rem & ((1u << lane) - 1u));
+              if (((rem >> lane) & 1u) && mine < room) {
+                uint8_t* ent = ring + ((head + mine) & (RING - 1)) * RING_ENTRY;
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                if (g[u] >= thr[r]) {
-#pragma unroll
-                  for (int e = 8 * u; e < 8 * u + 8; ++e) {   // unrolled so v[] stays in registers
-                    const int64_t idx = item0 + c * 32 + e;
-                    if (v[e] >= thr[r] && idx < p.n_items) {
-                      const int slot = atomicAdd(wq_cnt, 1);
-                      if (slot < WQ_CAP) {
-                        const uint64_t key = pack_key(v[e], static_cast<uint32_t>(idx));
-                        wq[slot] = make_uint4(static_cast<uint32_t>(key), static_cast<uint32_t>(key >> 32),
-                                              static_cast<uint32_t>(qrow[r]), 0u);
-                      } else {
-                        *p.overflow = 1;   // queue overrun (adversarial data): the host re-runs the chunk exactly
-                      }
-                    }
-                  }
-                }
+                for (int e = 0; e < 32; e += 4)
+                  *reinterpret_cast<float4*>(ent + e * 4) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+                *reinterpret_cast<int4*>(ent + 128) =
+                    make_int4(qrow[r], static_cast<int>(item0 + c * 32), __float_as_int(thr[r]), 0);
+              }
+              const int took = min(__popc(rem), room);
+              for (int t = 0; t < took; ++t) rem &= rem - 1u;
+              head += took;
+              __syncwarp();
+              if (lane == 0) {
+                __threadfence_block();
+                heads[ew] = head;
               }
             }
           } else if (MODE == MODE_SAMPLE) {
@@ -299,16 +360,14 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           if (lane == 0) mbar_arrive(&tempty[a]);
         }
         __syncwarp();
-        if (MODE == MODE_FILTER) {
-          const int n = min(*wq_cnt, WQ_CAP);   // uniform: read after the __syncwarp above
-          if (n >= 32) flush(n);
-        }
       }
     }
-    if (MODE == MODE_FILTER) {
+    if (MODE == MODE_FILTER) {   // every entry of this warp is published: tell the extraction warps
       __syncwarp();
-      const int n = min(*wq_cnt, WQ_CAP);
-      if (n > 0) flush(n);
+      if (lane == 0) {
+        __threadfence_block();
+        atomicAdd(const_cast<int*>(epi_done), 1);
+      }
     }
   }
 

@@ -27,3 +27,13 @@ for _ in range(3):
     torch.cuda.synchronize()
 Dw, Iw = index.search(q, 100, mode="exact")
 assert torch.equal(I, Iw) and torch.equal(D, Dw) and not bool(need.any())
+if len(sys.argv) > 1 and sys.argv[1] == "time":   # device ms per step (eager launches; the step is GPU-bound at this size)
+    for rep in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(100):
+            sidx._native_step(q, 100)
+        e1.record()
+        torch.cuda.synchronize()
+        print("ms per step: %.4f" % (e0.elapsed_time(e1) / 100))
