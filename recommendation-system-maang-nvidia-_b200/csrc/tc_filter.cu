@@ -61,11 +61,12 @@ constexpr int RING_ENTRY = 144;          // 32 scores + {query row, first catalo
 constexpr int CTRL_BYTES = 512;          // mbarriers, TMEM slot, ring heads / tails
 constexpr int TC_SMEM = R_MAX * QTILE_BYTES + NSTAGE * STAGE_BYTES + CTRL_BYTES + EPI_WARPS * RING * RING_ENTRY +
                         2 * WQ_CAP * 16 + 1024;
+static_assert(RING * RING_ENTRY >= WQ_CAP * 16 && (RING & (RING - 1)) == 0, "a warp's ring doubles as its dense-mode queue");
 constexpr int CAND_CAP = 4096;           // candidate list capacity per query
 constexpr int SEL_NT = 256;
 constexpr float C_EPS = 0.00390625f * 1.0625f;
 
-enum { MODE_FILTER = 0, MODE_SAMPLE = 1, MODE_DUMP = 2, MODE_SAMPLE_FINE = 3 };
+enum { MODE_FILTER = 0, MODE_SAMPLE = 1, MODE_DUMP = 2, MODE_SAMPLE_FINE = 3, MODE_FILTER_DENSE = 4 };
 
 struct TcParams {
   int64_t n_items;
@@ -266,13 +267,26 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const int row_in_tile = quarter * 32 + lane;
     uint8_t* ring = rings + ew * RING * RING_ENTRY;   // FILTER: this warp's ring of hit chunks
     int head = 0;                                    // entries written to it (warp-uniform)
+    // FILTER_DENSE: the ring space is this warp's survivor queue instead (WQ_CAP records), its head word the count
+    uint4* dq = reinterpret_cast<uint4*>(ring);
+    int* dq_cnt = const_cast<int*>(heads) + ew;
+    auto dense_flush = [&](int n) {
+      for (int t = lane; t < n; t += 32) {
+        const uint4 r = dq[t];
+        const int pos = atomicAdd(&p.cand_cnt[r.z], 1);
+        if (pos < p.cap) p.cand[(int64_t)r.z * p.cap + pos] = (static_cast<uint64_t>(r.y) << 32) | r.x;
+      }
+      __syncwarp();
+      if (lane == 0) *dq_cnt = 0;
+      __syncwarp();
+    };
     float thr[R_MAX];
     int qrow[R_MAX];
 #pragma unroll
     for (int r = 0; r < R_MAX; ++r) {
       qrow[r] = (qt0 + r) * BM + row_in_tile;
       thr[r] = INFINITY;
-      if (MODE == MODE_FILTER && r < nr && qrow[r] < p.nq && !(p.debug & 4)) thr[r] = p.thr[qrow[r]];
+      if ((MODE == MODE_FILTER || MODE == MODE_FILTER_DENSE) && r < nr && qrow[r] < p.nq && !(p.debug & 4)) thr[r] = p.thr[qrow[r]];
     }
     uint32_t acc_it = 0;
     for (int64_t i = 0; i < n_my; ++i) {
@@ -327,6 +341,30 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 heads[ew] = head;
               }
             }
+          } else if (MODE == MODE_FILTER_DENSE) {
+            // small catalogs (every tile scored, k of a few thousand rows): most chunks hold a survivor, two extraction
+            // warps would be the bottleneck -- every epilogue lane extracts its own and queues them per warp
+            if (m >= thr[r]) {
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                if (g[u] >= thr[r]) {
+#pragma unroll
+                  for (int e = 8 * u; e < 8 * u + 8; ++e) {   // unrolled so v[] stays in registers
+                    const int64_t idx = item0 + c * 32 + e;
+                    if (v[e] >= thr[r] && idx < p.n_items) {
+                      const int slot = atomicAdd(dq_cnt, 1);
+                      if (slot < WQ_CAP) {
+                        const uint64_t key = pack_key(v[e], static_cast<uint32_t>(idx));
+                        dq[slot] = make_uint4(static_cast<uint32_t>(key), static_cast<uint32_t>(key >> 32),
+                                              static_cast<uint32_t>(qrow[r]), 0u);
+                      } else {
+                        *p.overflow = 1;   // queue overrun (adversarial data): the host re-runs the chunk exactly
+                      }
+                    }
+                  }
+                }
+              }
+            }
           } else if (MODE == MODE_SAMPLE) {
             hmax = fmaxf(hmax, m);
           } else if (MODE == MODE_SAMPLE_FINE) {
@@ -360,7 +398,16 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           if (lane == 0) mbar_arrive(&tempty[a]);
         }
         __syncwarp();
+        if (MODE == MODE_FILTER_DENSE) {
+          const int n = min(*dq_cnt, WQ_CAP);   // uniform: read after the __syncwarp above
+          if (n >= 32) dense_flush(n);
+        }
       }
+    }
+    if (MODE == MODE_FILTER_DENSE) {
+      __syncwarp();
+      const int n = min(*dq_cnt, WQ_CAP);
+      if (n > 0) dense_flush(n);
     }
     if (MODE == MODE_FILTER) {   // every entry of this warp is published: tell the extraction warps
       __syncwarp();
@@ -862,7 +909,8 @@ void tc_finish(rs_tc_session& s, int64_t id_base, float* D, int64_t ldD, int64_t
     TcParams pm = s.p;
     pm.n_visit = s.ntiles;
     pm.tile_step = 1;
-    launch_filter<MODE_FILTER>(s.tq, h->tmap_bf16, pm, h->device, st);
+    if (h->ntotal < 65536) launch_filter<MODE_FILTER_DENSE>(s.tq, h->tmap_bf16, pm, h->device, st);
+    else launch_filter<MODE_FILTER>(s.tq, h->tmap_bf16, pm, h->device, st);
   }
   ProfScope prof(RS_PROF_RESCORE, st);
   select_rescore_kernel<<<s.nq, SEL_NT, 0, st>>>(s.ws.cand, s.ws.cnt, CAND_CAP, s.ws.thr, s.ws.eps2, s.q, h->xb, s.k, id_base,
