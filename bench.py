@@ -402,7 +402,7 @@ def main():
             # the drop-in's real host path: numpy in -> numpy out, H2D / D2H staged inside the C call (rs_index_search)
             return sidx.local.search(q_host_np, k, mode=args.mode)
     else:
-        def step_e2e():
+        def step_e2e_serial():
             qd = q_pinned.to(device, non_blocking=True)              # H2D of this step's inputs (pinned)
             D, I = sidx.search(qd, k)
             D_host.copy_(D, non_blocking=True)                       # D2H of this step's result
@@ -410,12 +410,55 @@ def main():
             torch.cuda.current_stream().synchronize()
             return D_host, I_host
 
-    def timed(fn, steps):
+        # The serving loop of the sharded index: submit() queues a step without looking at it, finish() is the step's
+        # one host synchronisation.  Two batches in flight: while step i's (D, I, flag) travel to pinned host memory on a
+        # copy stream, step i+1 (its own H2D included) already runs; the host completes step i after queueing step i+1.
+        # Every step's H2D and D2H are inside the timed region (the last step is drained before the closing event).
+        copy_stream = torch.cuda.Stream(device=device)
+        outs = [(torch.empty((nq, k), dtype=torch.float32).pin_memory(), torch.empty((nq, k), dtype=torch.int64).pin_memory(),
+                 torch.zeros((1,), dtype=torch.bool).pin_memory()) for _ in range(2)]
+        searched = [torch.cuda.Event() for _ in range(2)]
+        landed = [torch.cuda.Event() for _ in range(2)]
+        pipe = {"i": 0, "open": None}
+
+        def complete(entry):
+            ticket, s = entry
+            landed[s].synchronize()
+            if bool(outs[s][2][0]):                                  # a flagged query (never on this data): repair, copy again
+                D, I = sidx.finish(ticket)
+                outs[s][0].copy_(D)
+                outs[s][1].copy_(I)
+            return outs[s][0], outs[s][1]
+
+        def step_e2e():
+            s = pipe["i"] & 1
+            pipe["i"] += 1
+            qd = q_pinned.to(device, non_blocking=True)              # H2D of this step's inputs (pinned)
+            ticket = sidx.submit(qd, k)
+            searched[s].record()
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(searched[s])
+                outs[s][0].copy_(ticket[1], non_blocking=True)       # D2H of this step's result
+                outs[s][1].copy_(ticket[2], non_blocking=True)
+                outs[s][2].copy_(ticket[3].reshape(1), non_blocking=True)
+                landed[s].record()
+            prev, pipe["open"] = pipe["open"], (ticket, s)
+            return complete(prev) if prev is not None else None
+
+        def drain_e2e():
+            prev, pipe["open"] = pipe["open"], None
+            if prev is not None:
+                complete(prev)
+            torch.cuda.current_stream().wait_stream(copy_stream)
+
+    def timed(fn, steps, drain=None):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
         for _ in range(steps):
             fn()
+        if drain is not None:
+            drain()
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
@@ -452,14 +495,25 @@ def main():
     launches = rs._lib.launch_count() - launches0
     prof = {name: rs._lib.prof_read(slot) for name, slot in
             (("scan", rs._lib.PROF_SCAN), ("merge", rs._lib.PROF_MERGE), ("filter", rs._lib.PROF_FILTER),
-             ("rescore", rs._lib.PROF_RESCORE), ("sample", rs._lib.PROF_SAMPLE))}
+             ("rescore", rs._lib.PROF_RESCORE), ("sample", rs._lib.PROF_SAMPLE), ("threshold", rs._lib.PROF_THRESHOLD),
+             ("tops", rs._lib.PROF_TOPS), ("exchange", rs._lib.PROF_EXCHANGE))}
     rs._lib.prof_enable(False)
     if graphed:
         sidx.use_graph = True
 
-    for _ in range(max(3, args.warmup)):
-        step_e2e()
-    e2e_ms = timed(step_e2e, args.steps)
+    e2e_serial_ms = None
+    if world == 1:
+        for _ in range(max(3, args.warmup)):
+            step_e2e()
+        e2e_ms = timed(step_e2e, args.steps)
+    else:
+        for _ in range(max(3, args.warmup)):
+            step_e2e_serial()
+        e2e_serial_ms = timed(step_e2e_serial, args.steps)
+        for _ in range(max(3, args.warmup)):
+            step_e2e()
+        drain_e2e()
+        e2e_ms = timed(step_e2e, args.steps, drain=drain_e2e)
 
     ms_per_step = total_ms / args.steps
     value = nq / (ms_per_step / 1e3)
@@ -576,13 +630,17 @@ def main():
                         "d2h_bytes_per_step": nq * k * 12, "ms_per_step": e2e_ms / args.steps,
                         "path": ("IndexFlatIP.search(numpy float32 [nq, d]) -> numpy (D, I): host buffers in and out, H2D / D2H staged "
                                  "inside rs_index_search (the faiss-shaped drop-in call)") if world == 1 else
-                                ("pinned host queries -> ShardedIndexFlatIP.search (device tensors) -> pinned host (D, I); the numpy "
-                                 "entry point of the single-GPU index is not sharded")},
+                                ("pinned host queries -> ShardedIndexFlatIP.submit (device tensors) -> pinned host (D, I, flag) on a copy "
+                                 "stream -> finish: the sharded index's serving loop with two batches in flight (step i's D2H "
+                                 "overlaps step i+1; every step's H2D and D2H are inside the timed region, the last step is drained "
+                                 "before the closing event); `serial` = the same without overlap (search, copy, synchronise per "
+                                 "step); the numpy entry point of the single-GPU index is not sharded")},
                 "gpu_launches": int(lt.item()), "clocks": clocks, "roofline": roofline, "kernels": kernel_ms,
                 "parity_check": parity, "cpu_baseline": cpu, "ranking": ranking, "batch1_latency": batch1,
                 "config1": config1, "config4": config4}
         if world > 1:
             line["exchange_bytes_per_step_per_rank"] = gather_bytes(world, nq, k)
+            line["e2e"]["serial"] = {"value": nq / (e2e_serial_ms / args.steps / 1e3), "ms_per_step": e2e_serial_ms / args.steps}
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)

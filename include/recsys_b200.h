@@ -403,11 +403,15 @@ int64_t rs_launch_count(void);
 #define RS_PROF_SCAN 0     /* scan_topk_kernel (exact fp32 catalog scan)          */
 #define RS_PROF_MERGE 1    /* merge_topk_kernel                                   */
 #define RS_PROF_FILTER 2   /* tcgen05 bf16 pre-filter                             */
-#define RS_PROF_RESCORE 3  /* candidate select + exact re-score                   */
+#define RS_PROF_RESCORE 3  /* candidate select + exact re-score (in a sharded step: + publishing the lists and the wait
+                              for every rank's lists in the kernel's last CTA)                                        */
 #define RS_PROF_RANK 4     /* fused ranking forward: towers (and unfused chains)  */
 #define RS_PROF_SAMPLE 5   /* tcgen05 pre-filter, threshold-sampling pass         */
 #define RS_PROF_DEEP 6     /* fused ranking forward: deep net + cross + heads     */
-#define RS_PROF_SLOTS 8
+#define RS_PROF_THRESHOLD 7 /* query preparation, per-query threshold kernels (in a sharded step: + the tops exchange) */
+#define RS_PROF_EXCHANGE 8 /* separate publish launches of the peer-memory exchange (copy + wait for every rank)  */
+#define RS_PROF_TOPS 9     /* sharded step: a shard's list of largest sample maxima (+ publishing it, + the wait)     */
+#define RS_PROF_SLOTS 16
 int rs_prof_enable(int on);
 int rs_prof_read(int slot, double* total_ms, int64_t* launches);
 

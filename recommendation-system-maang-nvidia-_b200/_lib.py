@@ -167,7 +167,7 @@ EXPORTED = ["rs_version", "rs_last_error", "rs_launch_count", "rs_device_sm_coun
             "rs_comm_init", "rs_comm_rank", "rs_comm_free", "rs_index_search_sharded", "rs_sharded_table_create", "rs_sharded_table_free",
             "rs_embedding_a2a_lookup", "rs_sharded_table_last_counts"]
 
-PROF_SCAN, PROF_MERGE, PROF_FILTER, PROF_RESCORE, PROF_RANK, PROF_SAMPLE, PROF_DEEP = 0, 1, 2, 3, 4, 5, 6
+PROF_SCAN, PROF_MERGE, PROF_FILTER, PROF_RESCORE, PROF_RANK, PROF_SAMPLE, PROF_DEEP, PROF_THRESHOLD, PROF_EXCHANGE, PROF_TOPS = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9
 
 
 def check(status: int) -> None:

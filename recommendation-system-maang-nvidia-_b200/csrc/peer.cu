@@ -278,6 +278,7 @@ void publish_and_wait(rs_peer* h, const void* src, int64_t bytes, cudaStream_t s
   rs::require_aligned16(src, "src");
   PeerDeviceGuard g(h->device);
   const int blocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((bytes / 16 + 255) / 256, rs::sm_count())));
+  rs::ProfScope prof(RS_PROF_EXCHANGE, st);
   peer_publish_kernel<<<blocks, 256, 0, st>>>(h->d_bases, layout_of(h), static_cast<const uint8_t*>(src), bytes, 1);
   RS_LAUNCH_CHECK();
 }

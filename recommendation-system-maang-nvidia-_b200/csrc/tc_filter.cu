@@ -868,7 +868,7 @@ std::unique_ptr<rs_tc_session> tc_begin(rs_index* h, const float* qc, int cq, in
   RS_CUDA(cudaMallocAsync(&ws.cand, sizeof(uint64_t) * (size_t)nq_pad * CAND_CAP, st));
   RS_CUDA(cudaMemsetAsync(ws.flags + nq_pad, 0, sizeof(int) * 4, st));
   {
-    ProfScope prof(RS_PROF_RESCORE, st);
+    ProfScope prof(RS_PROF_THRESHOLD, st);
     prep_queries_kernel<<<(nq_pad * 32 + 127) / 128, 128, 0, st>>>(qc, cq, nq_pad, ws.qb, ws.eps2,
                                                                   reinterpret_cast<unsigned int*>(h->row_norm));
     RS_LAUNCH_CHECK();
@@ -936,14 +936,14 @@ void search_tensor_device(rs_index* h, const float* q, int64_t nq, int k, int64_
     const int nq_pad = s.nq_pad;
     Workspace& ws = s.ws;
     if (h->ntotal < 65536) {
-      ProfScope prof(RS_PROF_RESCORE, st);
+      ProfScope prof(RS_PROF_THRESHOLD, st);
       threshold_small_kernel<<<cq, 256, 0, st>>>(ws.smax, s.n_vals, static_cast<int>((h->ntotal + 31) / 32), k, ws.eps2, ws.thr,
                                                  ws.cnt, ws.flags);
       RS_LAUNCH_CHECK();
     } else {
       const double rho = double(s.n_sample * BN) / double(h->ntotal);
       const int rank = std::max(1, std::min(tensor_threshold_rank(k, rho), s.n_vals / 2));
-      ProfScope prof(RS_PROF_RESCORE, st);
+      ProfScope prof(RS_PROF_THRESHOLD, st);
       threshold_kernel<<<cq, 256, 0, st>>>(ws.smax, s.n_vals, rank, ws.thr, ws.cnt, ws.flags);
       RS_LAUNCH_CHECK();
     }
@@ -989,7 +989,7 @@ rs_tc_session* shared_begin(rs_index* h, const float* q, int64_t nq, int k, int 
   auto sp = tc_begin(h, q, static_cast<int>(nq), k, st);
   RS_CHECK(R >= 1 && R <= sp->n_vals, "R must be in [1, number of sample maxima]");
   RS_CHECK(!publish_tops || nq * R * 4 <= publish_tops->slot_bytes, "tops message longer than the region's slot");
-  ProfScope prof(RS_PROF_RESCORE, st);
+  ProfScope prof(RS_PROF_TOPS, st);
   sample_top_kernel<<<static_cast<unsigned>(nq), 256, 0, st>>>(sp->ws.smax, sp->n_vals, R, top, ld_top, peer_out(publish_tops));
   RS_LAUNCH_CHECK();
   return sp.release();
@@ -1003,7 +1003,7 @@ void shared_finish(rs_tc_session* sp, const float* tops, int n_parts, int64_t pa
   RS_CHECK(n_parts >= 1 && R >= 1 && n_parts * R <= 1024, "shards x R must be <= 1024");
   RS_CHECK(rank >= 1 && rank <= n_parts * R, "rank must be in [1, shards x R]");
   {
-    ProfScope prof(RS_PROF_RESCORE, s.st);
+    ProfScope prof(RS_PROF_THRESHOLD, s.st);
     threshold_shared_kernel<<<s.nq, 256, 0, s.st>>>(tops, n_parts, part_ld, R, rank, s.ws.thr, s.ws.cnt, s.ws.flags,
                                                     tops_region ? tops_region->d_bases : nullptr,
                                                     tops_region ? rsp::layout_of(tops_region) : rsp::PeerLayout{});
