@@ -92,6 +92,19 @@ def test_tensor_search_ties_and_degenerate_catalogs_fall_back_but_stay_exact(rs)
     _check(rs, np.zeros((70_000, 128), np.float32), q, 10)      # all scores 0: rows 0..9 win
 
 
+def test_every_chunk_a_hit_chunk_stresses_the_extraction_rings(rs):
+    """tc_filter_kernel hands hit chunks (chunk maximum >= tau) to two extraction warps through 8-slot rings per epilogue
+    warp.  With every score equal, every lane of every epilogue warp reports a hit in every chunk: the rings are always
+    full, the producers wait for slots and hand over in several passes -- and the answer must still be the exact scan's
+    (here: the candidate lists overflow, every query is flagged and repeated exactly)."""
+    q = rs.synth.make_unit_rows(300, 128, 21)
+    _check(rs, np.zeros((70_000, 128), np.float32), q, 10)
+    # half of the rows identical to a query's best match: dense hits for some query rows only, sparse for the others
+    xb = rs.synth.make_unit_rows(66_000, 128, 22)
+    xb[::2] = xb[0]
+    _check(rs, xb, q, 100)
+
+
 def test_auto_mode_equals_exact_mode_and_host_path(rs):
     xb = rs.synth.make_unit_rows(120_000, 128, 21)
     q = rs.synth.make_unit_rows(200, 128, 22)
