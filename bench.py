@@ -218,7 +218,7 @@ def cpu_batch1(args, xb, n_queries=8, k=10):
                       f"{args.n_items / xb.shape[0]:.1f} to the full catalog"}
 
 
-def cpu_ranking(rs, B, reps=3):
+def cpu_ranking(rs, B, reps=3, whole_batch=False):
     """configs[1] on the host: the reference's forward (src/models.py:37-50,79-91,125-131) as a torch-CPU fp32 F.linear chain
     with the same synthetic weights, all host cores.  Bounded: `reps` batches of B/4 samples."""
     import torch
@@ -226,7 +226,7 @@ def cpu_ranking(rs, B, reps=3):
     cfg = rs.ModelConfig()
     w = rs.synth.make_weights(cfg, 6040, 3706, seed=10)
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a))     # noqa: E731
-    Bs = max(1024, B // 4)
+    Bs = B if whole_batch else max(1024, B // 4)
     rng = np.random.default_rng(200)
     ur = torch.from_numpy(rs.synth.make_ids(rng, 6040, Bs))
     ir = torch.from_numpy(rs.synth.make_ids(rng, 3706, Bs))
@@ -264,7 +264,7 @@ def cpu_ranking(rs, B, reps=3):
             forward()
         dt = (time.perf_counter() - t0) / reps
     return {"value": Bs / dt, "unit": "samples/s", "cores": host_threads(), "kind": "port",
-            "sample": f"{reps} batches of {Bs:,} samples (a quarter of the {B:,} batch), torch-CPU fp32 F.linear chain following "
+            "sample": f"{reps} batches of {Bs:,} samples ({'the whole' if Bs == B else 'a quarter of the'} {B:,} batch), torch-CPU fp32 F.linear chain following "
                       f"src/models.py:37-50,79-91,125-131 (TensorFlow is not installable here), torch.set_num_threads({host_threads()})"}
 
 
@@ -589,7 +589,7 @@ def main():
     config1 = None
     if world == 1 and not args.no_ranking:
         try:
-            config1 = bench_config1(rs, torch, device, timed)
+            config1 = bench_config1(rs, torch, device, timed, cpu=not args.no_cpu_baseline)
         except Exception as e:  # noqa: BLE001
             config1 = {"error": f"{type(e).__name__}: {e}"}
 
@@ -817,7 +817,26 @@ def bench_ranking(rs, torch, dist, args, device, world, rank, pk, timed, traffic
                           "ffma_kernel": res.get("fp32_ffma")}}
 
 
-def bench_config1(rs, torch, device, timed, steps=20):
+def cpu_config1(rs, n_items=3706, B=4096, k=10, reps=3):
+    """configs[0] on the host -- the one case the reference itself runs on a CPU: the forward as cpu_ranking's torch chain at
+    the whole 4,096 batch, and exact top-10 of 4,096 unit queries over a 3,706-row catalog through the sgemm + heap
+    restatement of faiss-cpu's batched path."""
+    import oracle
+    fwd = cpu_ranking(rs, B, reps=reps, whole_batch=True)
+    xb = rs.synth.make_unit_rows(n_items, 128, 7)
+    q = rs.synth.make_unit_rows(B, 128, 8)
+    with all_host_cores():
+        oracle.search_blas(xb, q[:64], k)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            oracle.search_blas(xb, q, k)
+        dt = (time.perf_counter() - t0) / reps
+    return {"forward_samples_per_s": fwd["value"], "forward_ms": B / fwd["value"] * 1e3, "top10_queries_per_s": B / dt,
+            "top10_ms": dt * 1e3, "cores": host_threads(), "kind": "port",
+            "sample": f"{reps} whole batches each: {fwd['sample']}; top-10: OpenBLAS sgemm + per-query heap over all {n_items:,} rows"}
+
+
+def bench_config1(rs, torch, device, timed, steps=20, cpu=True):
     """BASELINE configs[0]: 6,040 users / 3,706 items, emb 128, batch 4,096 -- MultiTaskModel forward (fp32 exact mode, the
     reference's arithmetic) and exact top-10 over the item-tower catalog for the batch's user embeddings.  The whole
     problem sits in L2, so this is a launch/latency figure, not a roofline one."""
@@ -876,6 +895,7 @@ def bench_config1(rs, torch, device, timed, steps=20):
                                      "fallbacks": spread.fallbacks()[1],
                                      "note": "same shape, unit Gaussian rows and queries: tcgen05 pre-filter + exact re-score, results "
                                              "bit-identical to the scan (tests/test_gpu_tensor_path.py)"},
+            "cpu_baseline": cpu_config1(rs, n_items, B) if cpu else None,
             "note": "problem is L2-resident: launch/latency-bound, no roofline fraction"}
 
 

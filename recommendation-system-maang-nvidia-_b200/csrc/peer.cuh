@@ -84,6 +84,12 @@ __device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t* p) {
 __device__ __forceinline__ void st_release_sys(uint64_t* p, uint64_t v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+// Signal words go out as RELAXED system-scope stores behind ONE system-scope fence of the signalling thread (fence + relaxed
+// store is a release pattern).  A release store per peer made the signalling thread wait for each previous store's round
+// trip before issuing the next one -- `world` NVLink round trips in a row on the critical path of every exchange.
+__device__ __forceinline__ void st_relaxed_sys(uint64_t* p, uint64_t v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 
 // spins until *p >= want
 __device__ __forceinline__ void spin_until(const uint64_t* p, uint64_t want, unsigned long long budget, const char* what) {
@@ -122,13 +128,13 @@ __device__ __forceinline__ void peer_finish(uint8_t* const* bases, const PeerLay
     unsigned int* done = reinterpret_cast<unsigned int*>(local + L.off_done);
     if (atomicAdd(done, 1u) == gridDim.x - 1) {
       *done = 0;
-      __threadfence_system();
-      for (int g = 0; g < L.world; ++g) st_release_sys(reinterpret_cast<uint64_t*>(bases[g] + L.off_flags) + L.rank, seq);
+      __threadfence_system();        // every CTA's stores (ordered before their atomicAdd by their own fences) before the flags
+      for (int g = 0; g < L.world; ++g) st_relaxed_sys(reinterpret_cast<uint64_t*>(bases[g] + L.off_flags) + L.rank, seq);
       *reinterpret_cast<uint64_t*>(local + L.off_seq) = seq;
       if (is_last) *is_last = 1;     // shared-memory word of the calling CTA
       if (consumed)
         for (int g = 0; g < consumed_L->world; ++g)
-          st_release_sys(reinterpret_cast<uint64_t*>(consumed[g] + consumed_L->off_acks) + consumed_L->rank, consumed_seq);
+          st_relaxed_sys(reinterpret_cast<uint64_t*>(consumed[g] + consumed_L->off_acks) + consumed_L->rank, consumed_seq);
     }
   }
 }
@@ -148,7 +154,8 @@ __device__ __forceinline__ void peer_consumed(uint8_t* const* bases, const PeerL
     unsigned int* done = reinterpret_cast<unsigned int*>(bases[L.rank] + L.off_done);
     if (atomicAdd(done, 1u) == gridDim.x - 1) {
       *done = 0;
-      for (int g = 0; g < L.world; ++g) st_release_sys(reinterpret_cast<uint64_t*>(bases[g] + L.off_acks) + L.rank, seq);
+      __threadfence_system();        // all CTAs' reads of the region (ordered before their atomicAdd) before the acknowledgements
+      for (int g = 0; g < L.world; ++g) st_relaxed_sys(reinterpret_cast<uint64_t*>(bases[g] + L.off_acks) + L.rank, seq);
     }
   }
 }
