@@ -544,7 +544,7 @@ __global__ void __launch_bounds__(SEL_NT) select_rescore_kernel(
     const float* __restrict__ eps2, const float* __restrict__ q, const float* __restrict__ xb, int k, int64_t id_base,
     float* __restrict__ D, int64_t ldD, int64_t* __restrict__ I, int64_t ldI, int* __restrict__ flags,
     int* __restrict__ n_flagged, float* __restrict__ bound, const int* __restrict__ overflow, int* __restrict__ need_exact,
-    const PeerOut out) {
+    const PeerOut out, const int debug) {
   // bound == nullptr: the threshold was this index's own guess and is verified here (s_hat_(k) - 2 eps >= tau).
   // bound != nullptr ("shared threshold" mode of a partitioned catalog): tau came from the union of all shards'
   // samples, so this shard may hold fewer than k survivors.  It returns the exact top-min(c, k) of its survivors
@@ -595,13 +595,16 @@ __global__ void __launch_bounds__(SEL_NT) select_rescore_kernel(
   int64_t* oI = reinterpret_cast<int64_t*>(sel + 128);  // [128]
   if (ok) {
     const int m = s_m;
+    // (The re-score is a gather of m random 512-byte rows out of the fp32 catalog: 2/3 of this kernel's time at 10M rows,
+    // ~1.3 TB/s.  Asking L2 for all lines of all rows up front with prefetch.global.L2 measured 5 % slower: the rate of
+    // the random gather itself bounds it, not the per-thread latency chain.)
     // exact re-score with the stated fp32 FMA chain; keys[] is free again and receives the exact keys
     for (int i = tid; i < m; i += SEL_NT) {
       const uint32_t row = sel[i];
       const float4* xr = reinterpret_cast<const float4*>(xb + (int64_t)row * DK);
       float acc = 0.0f;
 #pragma unroll 16
-      for (int c4 = 0; c4 < DK / 4; ++c4) {
+      for (int c4 = 0; c4 < ((debug & 1) ? 0 : DK / 4); ++c4) {   // (experiment 1: no re-score loads / chain)
         const float4 xv = __ldg(xr + c4);
         const float4 qv = *reinterpret_cast<const float4*>(qs + c4 * 4);
         acc = fmaf(qv.x, xv.x, acc);
@@ -615,8 +618,8 @@ __global__ void __launch_bounds__(SEL_NT) select_rescore_kernel(
     // final order by counting: keys are distinct (the row is part of the key), so rank = #better keys
     for (int i = tid; i < m; i += SEL_NT) {
       const uint64_t mine = keys[i];
-      int rank = 0;
-      for (int jx = 0; jx < m; ++jx) rank += keys[jx] > mine ? 1 : 0;
+      int rank = (debug & 2) ? i : 0;                           // (experiment 2: no rank loop)
+      for (int jx = 0; jx < ((debug & 2) ? 0 : m); ++jx) rank += keys[jx] > mine ? 1 : 0;
       if (rank < k) {
         oD[rank] = key_score(mine);
         oI[rank] = id_base + static_cast<int64_t>(key_row(mine));
@@ -900,8 +903,19 @@ std::unique_ptr<rs_tc_session> tc_begin(rs_index* h, const float* qc, int cq, in
 }
 
 // the threshold must have been written to s.ws.thr (and cnt / flags cleared) by one of the threshold kernels
+static int sel_debug() {   // RS_SEL_DEBUG: timing experiments on select_rescore_kernel only (results are then WRONG)
+  const char* e = getenv("RS_SEL_DEBUG");
+  return e ? atoi(e) : 0;
+}
+
+// expect: candidates per query this index is expected to keep (threshold rank / sampled fraction; a shard's share of it
+// under a shared threshold).  It picks the survivor path: a warp's 32 x 32-score chunk holds a hit with probability
+// ~1,024 * expect / rows -- the ring hand-off to the two extraction warps wins while hit chunks are rare (6.8 % for 660
+// candidates over 10M rows, and the same for each shard of a shared-threshold search); from ~15 % on the two warps fall
+// behind the sixteen producers (1.25M rows behind one threshold of their own: 54 %, 0.54 vs 0.385 ms) and every epilogue
+// lane extracts its own hits instead.
 void tc_finish(rs_tc_session& s, int64_t id_base, float* D, int64_t ldD, int64_t* I, int64_t ldI, float* bound, int* need_exact,
-               const PeerOut& out = PeerOut{}) {
+               double expect, const PeerOut& out = PeerOut{}) {
   rs_index* h = s.h;
   cudaStream_t st = s.st;
   {
@@ -909,13 +923,15 @@ void tc_finish(rs_tc_session& s, int64_t id_base, float* D, int64_t ldD, int64_t
     TcParams pm = s.p;
     pm.n_visit = s.ntiles;
     pm.tile_step = 1;
-    if (h->ntotal < 65536) launch_filter<MODE_FILTER_DENSE>(s.tq, h->tmap_bf16, pm, h->device, st);
+    static const int force = [] { const char* e = getenv("RS_TC_SURVIVORS"); return e ? atoi(e) : 0; }();   // 1 = rings, 2 = inline (A/B)
+    const bool dense = force == 2 || (force != 1 && (h->ntotal < 65536 || 1024.0 * expect > 0.15 * double(h->ntotal)));
+    if (dense) launch_filter<MODE_FILTER_DENSE>(s.tq, h->tmap_bf16, pm, h->device, st);
     else launch_filter<MODE_FILTER>(s.tq, h->tmap_bf16, pm, h->device, st);
   }
   ProfScope prof(RS_PROF_RESCORE, st);
   select_rescore_kernel<<<s.nq, SEL_NT, 0, st>>>(s.ws.cand, s.ws.cnt, CAND_CAP, s.ws.thr, s.ws.eps2, s.q, h->xb, s.k, id_base,
                                                  D, ldD, I, ldI, s.ws.flags, s.ws.flags + s.nq_pad, bound,
-                                                 s.ws.flags + s.nq_pad + 1, need_exact, out);
+                                                 s.ws.flags + s.nq_pad + 1, need_exact, out, sel_debug());
   RS_LAUNCH_CHECK();
 }
 
@@ -947,7 +963,9 @@ void search_tensor_device(rs_index* h, const float* q, int64_t nq, int k, int64_
       threshold_kernel<<<cq, 256, 0, st>>>(ws.smax, s.n_vals, rank, ws.thr, ws.cnt, ws.flags);
       RS_LAUNCH_CHECK();
     }
-    tc_finish(s, id_base, D + q0 * ldD, ldD, I + q0 * ldI, ldI, nullptr, need_exact ? need_exact + q0 : nullptr);
+    const double rho_own = double(s.n_sample * BN) / double(h->ntotal);
+    const double expect = h->ntotal < 65536 ? double(h->ntotal) : double(tensor_threshold_rank(k, rho_own)) / rho_own;
+    tc_finish(s, id_base, D + q0 * ldD, ldD, I + q0 * ldI, ldI, nullptr, need_exact ? need_exact + q0 : nullptr, expect);
     if (need_exact) continue;   // deferred: the caller resolves flagged queries (after its own exchange step)
     // step 5: the (rare) queries whose guess could not be verified go through the exact scan
     std::vector<int> flags(nq_pad + 4);
@@ -1011,7 +1029,10 @@ void shared_finish(rs_tc_session* sp, const float* tops, int n_parts, int64_t pa
   }
   RS_CHECK(!publish_lists || off_B + (int64_t)s.nq * 4 <= publish_lists->slot_bytes, "lists message longer than the region's slot");
   RS_CHECK(publish_lists || bound != nullptr, "bound is NULL");
-  tc_finish(s, id_base, D, ldD, I, ldI, bound, need_exact, peer_out(publish_lists, off_I, off_F, off_B));
+  // the union's rank-th sample maximum keeps ~rank / rho candidates in the whole catalog, 1 / n_parts of them here
+  const double rho_own = double(s.n_sample * BN) / double(s.h->ntotal);
+  tc_finish(s, id_base, D, ldD, I, ldI, bound, need_exact, double(rank) / rho_own / n_parts,
+            peer_out(publish_lists, off_I, off_F, off_B));
 }
 
 void tc_session_free(rs_tc_session* sp) { delete sp; }

@@ -30,7 +30,8 @@ def child():
         index.search_deferred(q, 100, mode="tensor")
     torch.cuda.synchronize()
     out = {}
-    for name, slot in (("filter", rs._lib.PROF_FILTER), ("rescore", rs._lib.PROF_RESCORE), ("sample", rs._lib.PROF_SAMPLE)):
+    for name, slot in (("filter", rs._lib.PROF_FILTER), ("rescore", rs._lib.PROF_RESCORE), ("sample", rs._lib.PROF_SAMPLE),
+                       ("threshold", rs._lib.PROF_THRESHOLD)):
         ms, n = rs._lib.prof_read(slot)
         out[name + "_ms"] = round(ms / n_it, 4)
     rs._lib.prof_enable(False)
@@ -43,3 +44,6 @@ if __name__ == "__main__":
         for dbg in os.environ.get("KNOBS", "0,4,8").split(","):
             r = subprocess.run([sys.executable, __file__, "child"], env=dict(os.environ, RS_TC_DEBUG=dbg), capture_output=True, text=True)
             print(f"RS_TC_DEBUG={dbg}", r.stdout.strip() or r.stderr.strip()[-400:], flush=True)
+        for dbg in [x for x in os.environ.get("SEL_KNOBS", "").split(",") if x]:   # select_rescore_kernel: 1 = no re-score, 2 = no rank loop
+            r = subprocess.run([sys.executable, __file__, "child"], env=dict(os.environ, RS_SEL_DEBUG=dbg), capture_output=True, text=True)
+            print(f"RS_SEL_DEBUG={dbg}", r.stdout.strip() or r.stderr.strip()[-400:], flush=True)
