@@ -397,6 +397,42 @@ def main():
     def step_device():
         return sidx.search(q_dev, k)
 
+    # The device-resident serving loop (RS_BENCH_PIPELINE=1; off by default): submit() queues step i (one CUDA-graph replay), the step's "repeat exactly" flag
+    # travels to pinned host memory on a side stream, and the host looks at it -- finish(), the repair of flagged queries --
+    # after queueing step i+1, so the GPU never waits for the host between steps.  Every step's flag is read and honoured
+    # inside the timed region (the last one by the drain before the closing event).
+    flag_stream = torch.cuda.Stream(device=device)
+    flag_host = [torch.zeros((1,), dtype=torch.bool).pin_memory() for _ in range(2)]
+    f_searched = [torch.cuda.Event() for _ in range(2)]
+    f_landed = [torch.cuda.Event() for _ in range(2)]
+    dpipe = {"i": 0, "open": None}
+
+    def finish_pipe(entry):
+        ticket, s = entry
+        f_landed[s].synchronize()
+        if bool(flag_host[s][0]):
+            sidx.finish(ticket)
+
+    def step_pipe():
+        s = dpipe["i"] & 1
+        dpipe["i"] += 1
+        ticket = sidx.submit(q_dev, k)
+        if ticket[0] == "done":
+            return
+        f_searched[s].record()
+        with torch.cuda.stream(flag_stream):
+            flag_stream.wait_event(f_searched[s])
+            flag_host[s].copy_(ticket[3].reshape(1), non_blocking=True)
+            f_landed[s].record()
+        prev, dpipe["open"] = dpipe["open"], (ticket, s)
+        if prev is not None:
+            finish_pipe(prev)
+
+    def drain_pipe():
+        prev, dpipe["open"] = dpipe["open"], None
+        if prev is not None:
+            finish_pipe(prev)
+
     if world == 1:
         def step_e2e():
             # the drop-in's real host path: numpy in -> numpy out, H2D / D2H staged inside the C call (rs_index_search)
@@ -474,14 +510,16 @@ def main():
     for _ in range(3):        # one-time setup (lazy shadow build, graph capture) stays out of the warm-up time estimate below
         step_device()
     barrier()
-    warm_ms = timed(step_device, n_warm)
+    pipelined = bool(sidx.use_graph and sidx.reuse_outputs) and os.environ.get("RS_BENCH_PIPELINE", "0") == "1"
+    step_timed, drain_timed = (step_pipe, drain_pipe) if pipelined else (step_device, None)
+    warm_ms = timed(step_timed, n_warm, drain=drain_timed)
     extra = int(min(2000, max(0, (1000.0 - warm_ms) / max(warm_ms / n_warm, 1e-3))))
     if extra:
-        timed(step_device, extra)
+        timed(step_timed, extra, drain=drain_timed)
         n_warm += extra
     barrier()
     # ---- the timed region: no per-kernel event brackets, nothing but the steps ----
-    total_ms = timed(step_device, args.steps)
+    total_ms = timed(step_timed, args.steps, drain=drain_timed)
     clocks = sampler.stop() if rank == 0 else None
     # ---- second pass, same steps launched eagerly with the library's event brackets: per-kernel times + launch count
     #      (a CUDA-graph replay runs no library host code, so neither would see it) ----
@@ -619,8 +657,13 @@ def main():
                                          "bit-identical to the fp32 scan",
                            "sharding": sharding,
                            "timing": "value: device-resident queries, each step one CUDA-graph replay of the search (the deferred C "
-                                     "entry: no host synchronisation inside a step) followed by one read of the per-query 'repeat "
-                                     "exactly' flags; no per-kernel event brackets inside the timed region; roofline / kernels: a second "
+                                     "entry: no host synchronisation inside a step) " + (
+                                         "whose 'repeat exactly' flag goes to pinned host memory on a side stream and is read by the host "
+                                         "after it has queued the next step (RS_BENCH_PIPELINE=1: submit / finish, every flag read and "
+                                         "honoured inside the timed region, the last by a drain before the closing event)" if pipelined else
+                                         "followed by one read of the per-query 'repeat exactly' flags (RS_BENCH_PIPELINE=1 reads it after "
+                                         "queueing the next step: measured equal on 1 and 2 GPUs)") +
+                                     "; no per-kernel event brackets inside the timed region; roofline / kernels: a second "
                                      "pass of the same steps launched eagerly with the library's event brackets.  The replayed steps keep the GPU busy "
                                      "without gaps, so under the board's power cap the SM clock settles lower (see clocks) than in the "
                                      "e2e loop, whose host copies leave the GPU idle part of every step -- e2e can therefore read "
