@@ -1002,8 +1002,11 @@ def bench_batch1(rs, torch, dist, sidx, args, device, world, rank, pk, xb_h, n_q
     out = {"workload": f"batch-1 top-{k} over {args.n_items:,} x {args.dim} (BASELINE configs[4]), {n_queries} queries one at a time",
            "device_ms_p50": dm[0], "device_ms_p99": dm[1], "e2e_ms_p50": dm[2], "e2e_ms_p99": dm[3],
            "recommend_e2e_ms_p50": dm[4], "recommend_e2e_ms_p99": dm[5],
-           "recommend_path": "RecommendationService.recommend(user_id, 10): dict membership -> StringLookup -> user tower (fp32 kernels) -> "
-                             "normalize_L2 -> IndexFlatIP.search -> D2H of k (score, row) pairs -> result list",
+           "recommend_path": "RecommendationService.recommend(user_id, 10): dict membership -> StringLookup (host) -> row number up -> "
+                             "user tower (fp32 kernels) -> normalize_L2 -> IndexFlatIP search -> D2H of k (score, row) pairs -> "
+                             "result list" + ("; on one GPU the device part is one CUDA-graph replay per request "
+                                              "(service._single_user: same kernels and results as the eager calls)" if world == 1 else
+                                              "; sharded index: eager calls"),
            "queries_per_s_at_p50": 1e3 / dm[2],
            "roofline": {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
                         "algorithmic": "n_local*d*2 bytes per query: one pass over the bf16 shadow of the catalog shard (the fp32 "

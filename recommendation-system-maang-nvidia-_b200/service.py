@@ -18,6 +18,7 @@ user_tower_{i}_kernel/bias, item_tower_{i}_kernel/bias; `export_encoder_npz` doc
 
 import json
 import logging
+import threading
 from pathlib import Path
 from typing import Dict, List, Optional
 
@@ -62,6 +63,9 @@ class RecommendationService:
         self.encoder_model: Optional[MultiTowerModel] = None
         self.faiss_index: Optional[IndexFlatIP] = None
         self._user_set = frozenset()
+        self.single_user_graph = True          # recommend(): one CUDA-graph replay per request (see _single_user)
+        self._graphs: Dict[int, dict] = {}
+        self._graph_lock = threading.Lock()
 
     @classmethod
     def from_parts(cls, encoder: MultiTowerModel, index: IndexFlatIP, user_vocab: List[str], item_map: Dict[str, str],
@@ -116,16 +120,75 @@ class RecommendationService:
             return contextlib.nullcontext()
         return torch.cuda.device(dev)
 
+    def _single_user(self, user_id: str, k: int):
+        """The /recommendations request (app/recommendation_service.py:64-72 for ONE known user) as one CUDA-graph replay:
+        row number up (8 bytes, pinned), gather -> user tower -> normalize_L2 -> catalog search as captured launches, k
+        scores + k rows + the search's "not final" flag down in one synchronisation.  Same kernels, same arithmetic and
+        the same results as the eager calls below -- it removes their ~ten launches' host work and two of the three
+        host synchronisations from the request's latency.  Returns None when it does not apply (no CUDA index, another
+        thread is inside it, a flagged query): the caller then takes the eager path."""
+        enc, index = self.encoder_model, self.faiss_index
+        if not self.single_user_graph or not isinstance(index, IndexFlatIP) or k < 1 or index.ntotal == 0:
+            return None
+        if not self._graph_lock.acquire(blocking=False):
+            return None
+        try:
+            import torch
+            sig = (id(enc), id(index), int(index.ntotal), enc.user_embedding._version,
+                   tuple(layer._version for layer in enc.user_tower.layers))
+            entry = self._graphs.get(k)
+            if entry is None or entry["sig"] != sig:
+                dev = enc.device
+                rows_host = torch.zeros((1,), dtype=torch.int64).pin_memory()
+                rows = torch.zeros((1,), dtype=torch.int64, device=dev)
+
+                def step():
+                    q = enc.user_tower.call_on_rows(enc.user_embedding, rows)          # src/models.py:85
+                    normalize_L2(q)
+                    return index.search_deferred(q, k)
+
+                side = torch.cuda.Stream(device=dev)                # capture off the legacy default stream
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):
+                    for _ in range(2):                              # lazy one-time setup (bf16 shadow) outside the capture
+                        step()
+                    side.synchronize()
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph, stream=side):
+                        D, I, need = step()
+                torch.cuda.current_stream(dev).wait_stream(side)
+                entry = self._graphs[k] = {
+                    "sig": sig, "graph": graph, "rows_host": rows_host, "rows": rows, "D": D, "I": I, "need": need,
+                    "D_host": torch.empty((1, k), dtype=torch.float32).pin_memory(),
+                    "I_host": torch.empty((1, k), dtype=torch.int64).pin_memory(),
+                    "need_host": torch.zeros((1,), dtype=torch.int32).pin_memory()}
+            entry["rows_host"][0] = int(enc.user_lookup.lookup_host([user_id])[0])
+            entry["rows"].copy_(entry["rows_host"], non_blocking=True)
+            entry["graph"].replay()
+            entry["D_host"].copy_(entry["D"], non_blocking=True)
+            entry["I_host"].copy_(entry["I"], non_blocking=True)
+            entry["need_host"].copy_(entry["need"], non_blocking=True)
+            torch.cuda.current_stream(enc.device).synchronize()
+            if int(entry["need_host"][0]) != 0:
+                return None
+            return entry["D_host"].numpy().copy(), entry["I_host"].numpy().copy()
+        finally:
+            self._graph_lock.release()
+
     def recommend(self, user_id: str, k: int = 10) -> List[Dict]:
         if user_id not in self._user_set:          # dict/set membership instead of the reference's O(V) list scan
             logger.warning(f"User '{user_id}' not in vocabulary. Applying cold-start strategy.")
             return self._get_popular_items(k)
         with self._device_ctx():
-            q = self.encoder_model({"user_id": [user_id]}, training=False)["user_embedding"]   # [1, E] on device
-            normalize_L2(q)
-            distances, indices = self.faiss_index.search(q, k)
-            distances = distances.cpu().numpy()        # the only device -> host traffic: k scores + k rows
-            indices = indices.cpu().numpy()
+            fast = self._single_user(user_id, int(k))
+            if fast is not None:
+                distances, indices = fast
+            else:
+                q = self.encoder_model({"user_id": [user_id]}, training=False)["user_embedding"]   # [1, E] on device
+                normalize_L2(q)
+                distances, indices = self.faiss_index.search(q, k)
+                distances = distances.cpu().numpy()        # the only device -> host traffic: k scores + k rows
+                indices = indices.cpu().numpy()
         recommendations = []
         for i, idx in enumerate(indices[0]):
             if idx != -1:

@@ -391,6 +391,59 @@ def test_service_matches_oracle_service(rs):
         assert b["recommendations"] == svc.recommend(b["user_id"], 5)
 
 
+def test_recommend_graph_replay_equals_the_eager_calls(rs):
+    """recommend() for one known user runs as one CUDA-graph replay (service._single_user); it must return exactly what the
+    eager call sequence returns, re-capture itself after the user tower's weights or the catalog change, and stay
+    correct when several threads call in at once (a busy graph sends the caller down the eager path)."""
+    import threading
+    cfg = rs.ModelConfig()
+    n_users, n_items = 300, 70_000                       # >= 65,536 rows: the batch-1 bf16-shadow scan path
+    w = rs.synth.make_weights(cfg, n_users, 64, seed=31)
+    uv, iv = rs.synth.make_vocab(n_users), rs.synth.make_vocab(64)
+    enc = rs.MultiTowerModel(cfg, uv, iv, {})
+    rs.load_weights(enc, w)
+    index = rs.IndexFlatIP(cfg.embedding_dim)
+    index.add(dev(rs.synth.make_unit_rows(n_items, cfg.embedding_dim, 32)))
+    item_map = {str(i): f"item-{i}" for i in range(n_items + 1000)}
+    svc = rs.RecommendationService.from_parts(enc, index, uv, item_map)
+
+    def eager(u, k):
+        svc.single_user_graph = False
+        try:
+            return svc.recommend(u, k)
+        finally:
+            svc.single_user_graph = True
+
+    for u in uv[:12]:
+        assert svc.recommend(u, 10) == eager(u, 10)
+    assert svc.recommend(uv[3], 7) == eager(uv[3], 7) and set(svc._graphs) == {10, 7}
+    # Keras-style weight assignment on a tower layer: the captured graph snapshots nothing stale
+    layer = enc.user_tower.layers[0]
+    layer.set_weights([layer.kernel.cpu().numpy() * 0.5, layer.bias.cpu().numpy() + 0.25])
+    assert svc.recommend(uv[5], 10) == eager(uv[5], 10)
+    # more rows in the catalog
+    index.add(dev(rs.synth.make_unit_rows(1000, cfg.embedding_dim, 33)))
+    assert svc.recommend(uv[6], 10) == eager(uv[6], 10)
+    # concurrent callers
+    want = {u: eager(u, 10) for u in uv[:16]}
+    got, errs = {}, []
+
+    def worker(us):
+        try:
+            for _ in range(5):
+                for u in us:
+                    got[u] = svc.recommend(u, 10)
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    ts = [threading.Thread(target=worker, args=(uv[i:16:4],)) for i in range(4)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs and got == want
+
+
 def test_service_load_from_artifacts(rs, tmp_path):
     import json
     cfg = rs.ModelConfig(embedding_dim=64, user_tower_dims=[64], item_tower_dims=[64])
