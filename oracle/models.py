@@ -6,7 +6,8 @@ numpy restatement of /root/reference/src/models.py, line by line:
   MultiTaskModel     src/models.py:106-131   (call only; compute_loss is training)
 
 Third-party (Keras/TF) semantics restated from their public documentation,
-because TensorFlow cannot be imported here (PARITY UNPINNED):
+because TensorFlow cannot be imported here (primitive arithmetic UNPINNED; the
+composition below is held to a run of src/models.py itself, tests/test_reference_run.py):
   StringLookup(vocabulary=v, mask_token=None): OOV -> 0, v[i] -> i+1, int64
   Embedding(V, E): row gather
   Dense(units, activation): x @ kernel + bias, kernel stored (in, out)

@@ -3,8 +3,8 @@
     python tests/golden/make_golden.py
 
 The reference's own stack (TensorFlow, faiss) cannot be imported in this image, so these fixtures are
-outputs of the CPU restatement in oracle/ (PARITY UNPINNED against the real reference; see
-oracle/__init__.py).  Inputs and weights are regenerated from seeds by recsys_b200.synth; only ids and
+outputs of the CPU restatement in oracle/ (see oracle/__init__.py; the fixtures that come from the
+reference's own files are made by make_reference_golden.py).  Inputs and weights are regenerated from seeds by recsys_b200.synth; only ids and
 expected outputs are stored, which keeps the files small.  The fixtures (a) freeze the oracle so a later
 edit cannot silently change it, and (b) travel to the GPU box, where the CUDA path is checked against them.
 """

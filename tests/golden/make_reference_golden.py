@@ -1,0 +1,180 @@
+"""Generate tests/golden/reference_run.{npz,json} by running the REFERENCE'S OWN files.  TEST INFRASTRUCTURE ONLY.
+
+    python tests/golden/make_reference_golden.py          (needs /root/reference; runs in this container only)
+
+Executed unmodified, from where they lie under /root/reference:
+  src/config.py                  ModelConfig
+  src/models.py                  MultiTaskModel / MultiTowerModel / DeepCrossNetwork . call
+  src/trainer.py:221-246         ProductionTrainer._get_item_embeddings, _save_artifacts, _build_faiss
+  app/recommendation_service.py  RecommendationService . load / recommend / score / _get_popular_items / get_model_info
+  src/evaluation.py:25-81        AdvancedMetrics
+over the numpy stand-ins of tensorflow / keras / tensorflow_recommenders / faiss in tf_faiss_standin.py (none of the
+four is installed here).  So the fixtures pin the reference's COMPOSITION -- which layers, in which order, on which
+tensors, the control flow of the service, the artifact files it exchanges -- while every primitive (Dense, Embedding,
+StringLookup, IndexFlatIP.search, normalize_L2) computes in float64 by the stand-in's statement of its documented
+behaviour.  Weights, vocabularies and ids are regenerated from seeds by recsys_b200.synth, so the files stay small.
+`generate()` returns the same content without writing, which the CPU suite uses to check the committed files.
+"""
+
+import json
+import sys
+import tempfile
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+ROOT = HERE.parents[1]
+for p in (str(ROOT), str(HERE)):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+SPEC = dict(n_users=300, n_items=200, batch=96, weight_seed=62, id_seed=52, table_scale=40.0,
+            users=["1", "10", "137", "299", "42"], k=10, k_over=250, score_items=40)
+
+
+def synth_inputs():
+    """Weights, vocabularies and the ranking batch (strings, with out-of-vocabulary ids on both sides)."""
+    import recsys_b200 as rs
+    cfg = rs.ModelConfig()
+    w = rs.synth.make_weights(cfg, SPEC["n_users"], SPEC["n_items"], seed=SPEC["weight_seed"])
+    # Keras-initialised towers map every row to nearly the same direction; wider tables spread the catalog out so that the
+    # top-k order is decided by gaps far above fp32 rounding
+    w["user_embedding"] = (w["user_embedding"] * np.float32(SPEC["table_scale"])).astype(np.float32)
+    w["item_embedding"] = (w["item_embedding"] * np.float32(SPEC["table_scale"])).astype(np.float32)
+    uv, iv = rs.synth.make_vocab(SPEC["n_users"]), rs.synth.make_vocab(SPEC["n_items"])
+    rng = np.random.default_rng(SPEC["id_seed"])
+    users = [uv[i] for i in rng.integers(0, len(uv), SPEC["batch"])]
+    items = [iv[i] for i in rng.integers(0, len(iv), SPEC["batch"])]
+    for pos, s in ((3, "nobody"), (17, "0"), (40, "")):
+        users[pos] = s
+    for pos, s in ((5, "no-such-movie"), (17, "9999")):
+        items[pos] = s
+    return cfg, w, uv, iv, users, items
+
+
+def _set_dense(layer, kb):
+    assert layer.kernel.shape == kb[0].shape and layer.bias.shape == kb[1].shape
+    layer.kernel, layer.bias = np.array(kb[0]), np.array(kb[1])
+
+
+def build_reference_model(ref, cfg_dict, w, uv, iv, users, items):
+    """The reference's MultiTaskModel with the synthetic weights put into the layers it created itself."""
+    tf = sys.modules["tensorflow"]
+    M = ref["src.models"]
+    cfg = ref["src.config"].ModelConfig(**cfg_dict)
+    model = M.MultiTaskModel(cfg, list(uv), list(iv), {})
+    model({"user_id": tf.constant(users[:2]), "movie_id": tf.constant(items[:2])}, training=False)   # builds the layers
+    enc = model.encoder
+    enc.user_embedding.embeddings = np.array(w["user_embedding"])
+    enc.item_embedding.embeddings = np.array(w["item_embedding"])
+    for side in ("user", "item"):
+        layers = getattr(enc, f"{side}_tower").layers
+        assert len(layers) == len(w[f"{side}_tower"])
+        for layer, kb in zip(layers, w[f"{side}_tower"]):
+            _set_dense(layer, kb)
+    assert len(model.dcn.cross_weights) == len(w["cross_w"]) == cfg.cross_layers
+    for i in range(cfg.cross_layers):
+        model.dcn.cross_weights[i][...] = w["cross_w"][i]
+        model.dcn.cross_biases[i][...] = w["cross_b"][i]
+    for layer, kb in zip(model.dcn.deep_nets, w["deep"]):
+        _set_dense(layer, kb)
+    _set_dense(model.rating_head, w["rating_head"])
+    _set_dense(model.ctr_head, w["ctr_head"])
+    return cfg, model
+
+
+def generate(reference_root="/root/reference"):
+    import tf_faiss_standin as standin
+    standin.install()
+    standin.set_compute_dtype(np.float64)
+    ref = standin.import_reference(reference_root)
+    try:
+        tf = sys.modules["tensorflow"]
+        cfg0, w, uv, iv, users, items = synth_inputs()
+        cfg, model = build_reference_model(ref, cfg0.to_dict(), w, uv, iv, users, items)
+
+        arrays, doc = {}, {"spec": SPEC, "users_batch": users, "items_batch": items}
+        # 1. ranking forward (src/models.py:125-131), float64 and float32 arithmetic
+        for tag, dt in (("f64", np.float64), ("f32", np.float32)):
+            standin.set_compute_dtype(dt)
+            out = model({"user_id": tf.constant(users), "movie_id": tf.constant(items)}, training=False)
+            assert list(out) == ["user_embedding", "item_embedding", "rating_prediction", "ctr_prediction"]
+            for key, v in out.items():
+                arrays[f"{tag}_{key}"] = v.numpy().astype(dt)
+        standin.set_compute_dtype(np.float64)
+        one_side = model.encoder({"user_id": tf.constant(users[:4])}, training=False)
+        assert one_side["item_embedding"] is None                       # src/models.py:80-91: a missing side stays None
+
+        # 2. artifacts the way the trainer leaves them (src/trainer.py:228-246), then the service loads them (:35-59)
+        T = ref["src.trainer"].ProductionTrainer
+        with tempfile.TemporaryDirectory() as tmp:
+            fake = type("TrainerState", (), {})()
+            fake.output_dir, fake.config = Path(tmp), cfg
+            fake._get_item_embeddings = lambda m, vocab: T._get_item_embeddings(fake, m, vocab)
+            T._save_artifacts(fake, model, {"user_vocab": list(uv), "item_vocab": list(iv)})
+            T._build_faiss(fake, model, list(iv))
+            doc["artifact_files"] = sorted(p.name for p in Path(tmp).iterdir())
+            doc["config_json"] = json.loads((Path(tmp) / "config.json").read_text())
+            svc = ref["app.recommendation_service"].RecommendationService(tmp)
+            assert not svc.is_ready()
+            svc.load()
+            assert svc.is_ready()
+            info = svc.get_model_info()
+            info["model_path"] = "<tmp>"
+            doc["model_info"] = info
+            arrays["catalog"] = np.array(svc.faiss_index._xb)           # the normalised rows _build_faiss added
+
+            # 3. recommend / score / cold start (app/recommendation_service.py:64-102)
+            doc["recommend"] = {u: svc.recommend(u, SPEC["k"]) for u in SPEC["users"]}
+            doc["recommend_over"] = svc.recommend(SPEC["users"][0], SPEC["k_over"])      # k > ntotal: the -1 slots are dropped
+            full = {u: svc.recommend(u, SPEC["n_items"]) for u in SPEC["users"]}          # every item's score, ranked
+            pos = {it: i for i, it in enumerate(iv)}
+            s64 = np.zeros((len(SPEC["users"]), SPEC["n_items"]))
+            for r, u in enumerate(SPEC["users"]):
+                uq = model.encoder({"user_id": tf.constant([u])}, training=False)["user_embedding"].numpy()
+                uq = uq / np.linalg.norm(uq)
+                s64[r] = arrays["catalog"].astype(np.float64) @ uq[0]
+                assert [pos[x["item_id"]] for x in full[u]] == list(np.lexsort((np.arange(SPEC["n_items"]), -s64[r])))
+            arrays["scores_f64"] = s64                                   # exact scores behind the float32 ones reported
+            doc["cold_start"] = svc.recommend("nobody", 7)
+            doc["cold_start_over"] = len(svc.recommend("nobody", 1000))
+            score_ids = list(iv[:SPEC["score_items"]]) + ["no-such-movie"]
+            doc["score_ids"] = score_ids
+            doc["score"] = svc.score(SPEC["users"][2], score_ids)
+            try:
+                svc.score("nobody", score_ids[:2])
+                doc["score_unknown_user"] = None
+            except ValueError as e:
+                doc["score_unknown_user"] = str(e)
+
+        # 4. the ranked lists through AdvancedMetrics (src/evaluation.py:25-81)
+        A = ref["src.evaluation"].AdvancedMetrics
+        preds = [[x["item_id"] for x in doc["recommend"][u]] for u in SPEC["users"]]
+        truth = [preds[0][0], preds[1][3], "no-such-movie", preds[3][9], preds[4][1]]
+        doc["metrics_truth"] = truth
+        doc["metrics"] = {
+            "recall@5": float(A.recall_at_k(preds, truth, 5)), "recall@10": float(A.recall_at_k(preds, truth, 10)),
+            "precision@5": float(A.precision_at_k(preds, truth, 5)), "ndcg@10": float(A.ndcg_at_k(preds, truth, 10)),
+            "map@10": float(A.map_at_k(preds, truth, 10)), "mrr": float(A.mrr(preds, truth)),
+            "coverage": float(A.coverage(preds, list(iv))), "diversity": float(A.diversity(preds))}
+        return arrays, doc
+    finally:
+        standin.drop_reference()
+        standin.uninstall()
+
+
+def load_committed():
+    with np.load(HERE / "reference_run.npz") as z:
+        arrays = {k: z[k] for k in z.files}
+    return arrays, json.loads((HERE / "reference_run.json").read_text())
+
+
+if __name__ == "__main__":
+    arrays, doc = generate()
+    np.savez_compressed(HERE / "reference_run.npz", **arrays)
+    (HERE / "reference_run.json").write_text(json.dumps(doc, indent=1, sort_keys=True) + "\n")
+    top = doc["recommend"][SPEC["users"][0]]
+    gaps = -np.diff(np.sort(arrays["scores_f64"], axis=1)[:, ::-1][:, :SPEC["k"] + 1], axis=1)
+    print("wrote reference_run.npz / .json;", "first list:", [x["item_id"] for x in top][:5],
+          "smallest gap among the top-(k+1) scores: %.3g" % gaps.min())

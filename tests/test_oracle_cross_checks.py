@@ -1,7 +1,7 @@
 """The oracle (numpy / C restatement of the reference's TF + FAISS path) against an INDEPENDENT implementation of the
 same layer semantics: PyTorch's CPU operators -- the only other implementation importable in this image (TensorFlow,
-Keras and faiss are absent, so the oracle stays "parity unpinned" with respect to the reference itself; this narrows
-the room for a restatement error, it does not close it).  torch.nn.functional.{embedding, linear, relu}, torch.sigmoid
+Keras and faiss are absent, so the primitives' arithmetic stays unpinned with respect to those binaries; this narrows
+the room for a restatement error, it does not close it -- the composition is pinned separately, test_reference_run.py).  torch.nn.functional.{embedding, linear, relu}, torch.sigmoid
 and torch.topk are written by other people against the same definitions (Embedding = row gather, Dense = x @ W + b
 with W stored (in, out) in Keras and (out, in) in torch, DCN-v1 cross per the paper's formula)."""
 
