@@ -637,6 +637,14 @@ def main():
         except Exception as e:  # noqa: BLE001
             config1 = {"error": f"{type(e).__name__}: {e}"}
 
+    # K0: StringLookup on the device, rank 0 at N=1; reported, never allowed to take the line down
+    string_lookup = None
+    if world == 1 and not args.no_ranking:
+        try:
+            string_lookup = bench_string_lookup(rs, torch, device, timed, pk, cpu=not args.no_cpu_baseline)
+        except Exception as e:  # noqa: BLE001
+            string_lookup = {"error": f"{type(e).__name__}: {e}"}
+
     # configs[3]: sharded embedding tables feeding the ranking forward (needs >= 2 GPUs).  Every rank runs it (it is
     # collective); a failure is reported, not raised -- but it is raised on EVERY rank or on none (the flag is reduced)
     config4 = None
@@ -687,7 +695,7 @@ def main():
                                  "step); the numpy entry point of the single-GPU index is not sharded")},
                 "gpu_launches": int(lt.item()), "clocks": clocks, "roofline": roofline, "kernels": kernel_ms,
                 "parity_check": parity, "cpu_baseline": cpu, "ranking": ranking, "batch1_latency": batch1,
-                "config1": config1, "config4": config4}
+                "config1": config1, "config4": config4, "string_lookup": string_lookup}
         if world > 1:
             line["exchange_bytes_per_step_per_rank"] = gather_bytes(world, nq, k)
             line["e2e"]["serial"] = {"value": nq / (e2e_serial_ms / args.steps / 1e3), "ms_per_step": e2e_serial_ms / args.steps}
@@ -947,6 +955,61 @@ def bench_config1(rs, torch, device, timed, steps=20, cpu=True):
                                              "bit-identical to the scan (tests/test_gpu_tensor_path.py)"},
             "cpu_baseline": cpu_config1(rs, n_items, B) if cpu else None,
             "note": "problem is L2-resident: launch/latency-bound, no roofline fraction"}
+
+
+def bench_string_lookup(rs, torch, device, timed, pk, n_words=1 << 20, B=1 << 22, steps=20, cpu=True):
+    """K0: keras.layers.StringLookup (src/models.py:70,73,85,89) on the device -- 4M string ids (16-byte rows, 1 % out of
+    vocabulary) against a 1M-word vocabulary.  HBM-bound byte work: per id 16 B read + 8 B written (the table -- 8 MB of
+    slots + 16 MB of words -- stays in L2); checked id for id against the host dict the models use otherwise."""
+    vocab = rs.synth.make_vocab(n_words)
+    words = rs.ops.pack_strings(vocab)
+    rng = np.random.default_rng(500)
+    pick = rng.integers(0, n_words, B)
+    ids_h = words[pick]                                            # uint8 [B, 16]
+    oov = rng.random(B) < 0.01
+    ids_h[oov, 0] = ord("x")                                       # no word starts with a letter
+    want = np.where(oov, 0, pick + 1).astype(np.int64)
+    dv = rs.ops.DeviceVocabulary(vocab, device=device)
+    ids_pin = torch.from_numpy(ids_h).pin_memory()
+    ids_d = ids_pin.to(device)
+    rows_d = torch.empty((B,), dtype=torch.int64, device=device)
+    rows_pin = torch.empty((B,), dtype=torch.int64).pin_memory()
+
+    def step():
+        dv.lookup(ids_d, out=rows_d)
+
+    def step_e2e():
+        ids_d.copy_(ids_pin, non_blocking=True)
+        dv.lookup(ids_d, out=rows_d)
+        rows_pin.copy_(rows_d, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(3):
+        step_e2e()
+    equal = bool(np.array_equal(rows_pin.numpy(), want))
+    d_ms = timed(step, steps) / steps
+    e_ms = timed(step_e2e, steps) / steps
+    alg = B * (ids_h.shape[1] + 8)
+    out = {"workload": f"{B:,} string ids (uint8 [B, {ids_h.shape[1]}], 1 % out of vocabulary) -> int64 rows, vocabulary of {n_words:,} words",
+           "ids_per_s": B / (d_ms / 1e3), "ms_per_step": d_ms,
+           "e2e": {"ids_per_s": B / (e_ms / 1e3), "ms_per_step": e_ms, "h2d_bytes_per_step": int(ids_h.nbytes),
+                   "d2h_bytes_per_step": B * 8, "path": "pinned byte matrix -> device -> DeviceVocabulary.lookup -> pinned int64 rows"},
+           "roofline": {"bound": "hbm", "achieved": alg / (d_ms / 1e3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                        "frac": alg / (d_ms / 1e3) / 1e9 / pk["hbm_gbs"], "traffic": None,
+                        "note": "algorithmic bytes = ids read + rows written; the 24 MB table is L2-resident and not counted"},
+           "parity": {"ids": B, "equal_to_host_dict": equal}, "gpu_launches_per_step": 1}
+    if cpu:
+        look = rs.StringLookup(vocab, device=device)
+        n = 1 << 18
+        sample = [vocab[i] if not o else "x" + vocab[i] for i, o in zip(pick[:n], oov[:n])]
+        t0 = time.perf_counter()
+        got = look.lookup_host(sample)
+        dt = time.perf_counter() - t0
+        out["parity"]["sample_equal_to_lookup_host"] = bool(np.array_equal(got, want[:n]))
+        out["cpu_baseline"] = {"value": n / dt, "unit": "ids/s", "cores": 1, "kind": "port",
+                               "sample": f"{n:,} of the same ids as Python strings through the host dict (the lookup the models use "
+                                         f"for string lists; stands for the TF hash-table op)"}
+    return out
 
 
 def bench_batch1(rs, torch, dist, sidx, args, device, world, rank, pk, xb_h, n_queries=200, k=10):

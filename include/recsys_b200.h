@@ -63,6 +63,22 @@ const char* rs_last_error(void);
 int rs_device_sm_count(int* out);
 
 /*
+ * K0. StringLookup on the device (the default models keep the lookup in a host dict).
+ * Replaces keras.layers.StringLookup(vocabulary=v, mask_token=None) (src/models.py:70,73; called at :85,89):
+ * v[i] -> i + 1, every other string -> 0 (the single out-of-vocabulary bucket), int64.
+ *   rs_vocab_create: words = HOST bytes [n_words, width], each row one word, NUL-padded (numpy `S<width>` layout;
+ *                    a row is the string before its first NUL, so words cannot contain NUL).  Builds the hash table
+ *                    on the current device.  A repeated word keeps its last position (as a dict built in order does).
+ *   rs_vocab_lookup: ids uint8 [B, W] device (same row layout, any W; rows longer than every word are out of
+ *                    vocabulary), rows int64 [B] device.  Matches are decided on the bytes, never on the hash alone.
+ */
+typedef struct rs_vocab rs_vocab_t;
+int rs_vocab_create(const uint8_t* words, int64_t n_words, int64_t width, rs_vocab_t** out);
+int rs_vocab_free(rs_vocab_t* v);
+int rs_vocab_size(const rs_vocab_t* v, int64_t* n_words);
+int rs_vocab_lookup(const rs_vocab_t* v, const DLTensor* ids, DLTensor* rows, void* stream);
+
+/*
  * K1. Embedding row gather fused with the concat.
  * Replaces keras.layers.Embedding lookups (src/models.py:71,74,85,89) and, when several
  * tables are given, the tf.concat that follows (src/models.py:128).

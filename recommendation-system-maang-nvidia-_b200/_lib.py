@@ -84,6 +84,10 @@ def load():
     lib.rs_launch_count.restype = i64
     sigs = {
         "rs_device_sm_count": [ctypes.POINTER(i32)],
+        "rs_vocab_create": [vp, i64, i64, ctypes.POINTER(vp)],
+        "rs_vocab_free": [vp],
+        "rs_vocab_size": [vp, ctypes.POINTER(i64)],
+        "rs_vocab_lookup": [vp, _DLP, _DLP, vp],
         "rs_gather_concat": [i32, ctypes.POINTER(_DLP), ctypes.POINTER(_DLP), _DLP, vp],
         "rs_a2a_count": [_DLP, i32, _DLP, vp],
         "rs_a2a_scatter": [_DLP, i32, _DLP, _DLP, _DLP, _DLP, vp],
@@ -156,7 +160,7 @@ def load():
     return lib
 
 
-EXPORTED = ["rs_version", "rs_last_error", "rs_launch_count", "rs_device_sm_count", "rs_gather_concat", "rs_a2a_count", "rs_a2a_scatter", "rs_hash_table_fill",
+EXPORTED = ["rs_version", "rs_last_error", "rs_launch_count", "rs_device_sm_count", "rs_vocab_create", "rs_vocab_free", "rs_vocab_size", "rs_vocab_lookup", "rs_gather_concat", "rs_a2a_count", "rs_a2a_scatter", "rs_hash_table_fill",
             "rs_dense_forward", "rs_dense_forward_bf16", "rs_dense_x3_prepare", "rs_dense_x3_supported", "rs_dense_forward_x3", "rs_gather_bf16", "rs_chain_forward_bf16", "rs_ranker_create", "rs_ranker_free", "rs_ranker_forward", "rs_ranker_forward_rows", "rs_dcn_cross_forward", "rs_heads_forward", "rs_cross_v2_combine", "rs_cross_heads_forward", "rs_normalize_l2", "rs_index_create",
             "rs_index_free", "rs_index_add", "rs_index_ntotal", "rs_index_dim", "rs_index_reconstruct", "rs_index_search", "rs_index_search_deferred",
             "rs_tensor_plan", "rs_tensor_threshold_rank", "rs_index_shared_begin", "rs_index_shared_finish", "rs_tc_session_free", "rs_topk_verify",

@@ -43,6 +43,7 @@ class StringLookup:
         self.vocabulary = list(vocabulary)
         self._index = {s: i + 1 for i, s in enumerate(self.vocabulary)}
         self.device = _dev(device)
+        self._device_vocab = None          # K0 table, built by the first lookup_device call
 
     def vocabulary_size(self) -> int:
         return len(self.vocabulary) + 1
@@ -54,11 +55,30 @@ class StringLookup:
         return np.fromiter((get(s.decode() if isinstance(s, bytes) else str(s), 0) for s in ids), dtype=np.int64,
                            count=len(ids))
 
+    def lookup_device(self, ids) -> torch.Tensor:
+        """The same mapping computed on the GPU (K0, csrc/string_lookup.cu) for ids that arrive as bytes: a numpy `S`
+        array, or a uint8 [B, W] byte matrix (numpy or torch, host or device; NUL-padded rows, ops.pack_strings).  The
+        table is built on first use.  int64 [B] on the device, equal to lookup_host element for element."""
+        if self._device_vocab is None:
+            self._device_vocab = ops.DeviceVocabulary(self.vocabulary, device=self.device)
+        if isinstance(ids, np.ndarray) and ids.dtype.kind in "SU":
+            ids = ops.pack_strings(ids)
+        if isinstance(ids, np.ndarray):
+            ids = torch.from_numpy(np.ascontiguousarray(ids))
+        if not isinstance(ids, torch.Tensor) or ids.dtype != torch.uint8 or ids.dim() != 2:
+            raise TypeError("lookup_device takes a numpy S array or a uint8 [B, W] byte matrix")
+        with torch.cuda.device(self.device):
+            return self._device_vocab.lookup(ids.to(self.device, non_blocking=True))
+
     def __call__(self, ids) -> torch.Tensor:
         if isinstance(ids, torch.Tensor):
+            if ids.dtype == torch.uint8 and ids.dim() == 2:
+                return self.lookup_device(ids)
             if ids.dtype not in (torch.int32, torch.int64):
-                raise TypeError("tensor ids must be int32/int64 row numbers")
+                raise TypeError("tensor ids must be int32/int64 row numbers or a uint8 [B, W] byte matrix")
             return ids.to(self.device)
+        if isinstance(ids, np.ndarray) and ids.dtype.kind == "S":
+            return self.lookup_device(ids)
         rows = self.lookup_host(ids)
         return torch.from_numpy(rows).to(self.device, non_blocking=True)
 

@@ -19,6 +19,67 @@ def _require_cuda(*ts):
             raise TypeError("expected CUDA torch tensors (no CPU path exists)")
 
 
+def pack_strings(ids, width: Optional[int] = None):
+    """Strings -> the fixed-width byte matrix the device lookup reads: uint8 [n, W] numpy, one NUL-padded row per string
+    (UTF-8), W a multiple of 16.  Accepts a sequence of str / bytes or a numpy `S` / `U` array.  Pure host code."""
+    import numpy as np
+    if isinstance(ids, np.ndarray) and ids.dtype.kind == "S":
+        a = ids.reshape(-1)
+    elif isinstance(ids, np.ndarray) and ids.dtype.kind == "U":
+        a = np.char.encode(ids.reshape(-1), "utf-8")
+    else:
+        a = np.array([s if isinstance(s, bytes) else str(s).encode("utf-8") for s in ids], dtype=np.bytes_)
+        if a.size == 0:
+            a = np.zeros((0,), dtype="S1")
+    w = max(int(a.dtype.itemsize), 1)
+    want = int(width) if width is not None else (w + 15) // 16 * 16
+    if want < w:
+        raise ValueError(f"width {want} is smaller than the longest string ({w} bytes)")
+    out = np.zeros((a.shape[0], want), dtype=np.uint8)
+    if a.shape[0]:
+        out[:, :w] = np.ascontiguousarray(a).view(np.uint8).reshape(a.shape[0], w)
+    return out
+
+
+class DeviceVocabulary:
+    """K0 handle: the StringLookup table on the device (csrc/string_lookup.cu).  `lookup(ids)` takes a CUDA uint8 [B, W]
+    byte matrix (see pack_strings) and returns int64 [B] rows: vocabulary[i] -> i + 1, anything else -> 0."""
+
+    def __init__(self, vocabulary, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("recsys_b200 needs a CUDA (sm_100a) device; there is no CPU fallback")
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        words = pack_strings(vocabulary)
+        self._lib = _lib.load()
+        self._h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.rs_vocab_create(words.ctypes.data_as(ctypes.c_void_p), int(words.shape[0]),
+                                                 int(words.shape[1]), ctypes.byref(self._h)))
+
+    def __len__(self) -> int:
+        n = ctypes.c_int64()
+        _lib.check(self._lib.rs_vocab_size(self._h, ctypes.byref(n)))
+        return int(n.value)
+
+    def lookup(self, ids: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        _require_cuda(ids, out)
+        if ids.dtype != torch.uint8 or ids.dim() != 2:
+            raise TypeError("ids must be a uint8 [B, W] byte matrix (ops.pack_strings)")
+        if out is None:
+            out = torch.empty((ids.shape[0],), dtype=torch.int64, device=ids.device)
+        ib, ob = _lib.dl(ids), _lib.dl(out)
+        _lib.check(self._lib.rs_vocab_lookup(self._h, ib.ptr, ob.ptr, _lib.stream_ptr()))
+        return out
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                self._lib.rs_vocab_free(h)
+            except Exception:  # noqa: BLE001 -- interpreter shutdown
+                pass
+
+
 def gather_concat(tables: Sequence[torch.Tensor], ids: Sequence[torch.Tensor],
                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """K1: out[b] = concat_t tables[t][ids[t][b]]  (Embedding lookups + tf.concat, src/models.py:85,89,128)."""
