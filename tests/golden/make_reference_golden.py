@@ -33,6 +33,29 @@ SPEC = dict(n_users=300, n_items=200, batch=96, weight_seed=62, id_seed=52, tabl
             users=["1", "10", "137", "299", "42"], k=10, k_over=250, score_items=40)
 
 
+# other ModelConfig values through the same reference code (ranking forward only): narrower embeddings, towers of unequal
+# depth, two / zero cross layers, deeper / shallower deep nets
+VARIANTS = {
+    "B": dict(cfg=dict(embedding_dim=64, user_tower_dims=[96, 48], item_tower_dims=[32], cross_layers=2, dnn_dims=[64, 32, 16]),
+              n_users=50, n_items=70, batch=40, weight_seed=71, id_seed=72),
+    "C": dict(cfg=dict(embedding_dim=64, user_tower_dims=[], item_tower_dims=[128], cross_layers=0, dnn_dims=[32]),
+              n_users=20, n_items=30, batch=24, weight_seed=81, id_seed=82),
+}
+
+
+def variant_inputs(name):
+    import recsys_b200 as rs
+    v = VARIANTS[name]
+    cfg = rs.ModelConfig(**v["cfg"])
+    w = rs.synth.make_weights(cfg, v["n_users"], v["n_items"], seed=v["weight_seed"])
+    uv, iv = rs.synth.make_vocab(v["n_users"]), rs.synth.make_vocab(v["n_items"])
+    rng = np.random.default_rng(v["id_seed"])
+    users = [uv[i] for i in rng.integers(0, len(uv), v["batch"])]
+    items = [iv[i] for i in rng.integers(0, len(iv), v["batch"])]
+    users[1], items[2] = "nobody", "no-such-movie"
+    return cfg, w, uv, iv, users, items
+
+
 def synth_inputs():
     """Weights, vocabularies and the ranking batch (strings, with out-of-vocabulary ids on both sides)."""
     import recsys_b200 as rs
@@ -105,6 +128,13 @@ def generate(reference_root="/root/reference"):
         standin.set_compute_dtype(np.float64)
         one_side = model.encoder({"user_id": tf.constant(users[:4])}, training=False)
         assert one_side["item_embedding"] is None                       # src/models.py:80-91: a missing side stays None
+
+        for name in VARIANTS:
+            vcfg, vw, vuv, viv, vusers, vitems = variant_inputs(name)
+            _, vmodel = build_reference_model(ref, vcfg.to_dict(), vw, vuv, viv, vusers, vitems)
+            vout = vmodel({"user_id": tf.constant(vusers), "movie_id": tf.constant(vitems)}, training=False)
+            for key, val in vout.items():
+                arrays[f"v{name}_f64_{key}"] = val.numpy().astype(np.float64)
 
         # 2. artifacts the way the trainer leaves them (src/trainer.py:228-246), then the service loads them (:35-59)
         T = ref["src.trainer"].ProductionTrainer

@@ -97,6 +97,20 @@ def test_oracle_ranking_matches_the_reference_run(ref_run, oracle_mod):
     assert _close(only_user["user_embedding"], r["arrays"]["f64_user_embedding"][:4], 1e-12)
 
 
+@pytest.mark.parametrize("name", sorted(mrg.VARIANTS))
+def test_oracle_ranking_matches_the_reference_run_on_other_configs(name, oracle_mod):
+    from oracle.models import MultiTaskModel as OracleMultiTask
+    arrays, _ = mrg.load_committed()
+    cfg, w, uv, iv, users, items = mrg.variant_inputs(name)
+    out = OracleMultiTask(w, uv, iv, np.float64)({"user_id": users, "movie_id": items})
+    for key in RANK_KEYS:
+        want = arrays[f"v{name}_f64_{key}"]
+        assert want.shape[0] == len(users) and _close(out[key], want, 1e-12), (name, key)
+    E, deep = cfg.embedding_dim, cfg.dnn_dims[-1]
+    assert arrays[f"v{name}_f64_user_embedding"].shape == (len(users), E)
+    assert len(w["cross_w"]) == cfg.cross_layers and w["rating_head"][0].shape == (2 * E + deep, 1)
+
+
 def test_oracle_service_matches_the_reference_run(ref_run, oracle_mod):
     from oracle import flat_ip
     from oracle.models import MultiTowerModel as OMT
@@ -161,6 +175,20 @@ def test_cuda_ranking_matches_the_reference_run(ref_run, rs):
     one = model.encoder({"user_id": r["users"][:4]}, training=False)
     assert one["item_embedding"] is None
     assert _close(one["user_embedding"].cpu().numpy(), r["arrays"]["f64_user_embedding"][:4], 1e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(mrg.VARIANTS))
+def test_cuda_ranking_matches_the_reference_run_on_other_configs(name, rs):
+    arrays, _ = mrg.load_committed()
+    cfg, w, uv, iv, users, items = mrg.variant_inputs(name)
+    model = rs.MultiTaskModel(cfg, uv, iv, {})
+    rs.load_weights(model, w)
+    for reps in (1, 25):                                       # 25x: past 512 rows, where the fp32 tensor kernel takes the layers it supports
+        out = model({"user_id": users * reps, "movie_id": items * reps}, training=False)
+        for key in RANK_KEYS:
+            want = np.tile(arrays[f"v{name}_f64_{key}"], (reps, 1))
+            assert _close(out[key].cpu().numpy(), want, 1e-5), (name, reps, key)
 
 
 @pytest.mark.gpu
