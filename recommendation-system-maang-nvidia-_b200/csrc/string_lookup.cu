@@ -5,9 +5,10 @@
 // column) -- byte and integer work only.  The vocabulary is an open-addressing table in HBM built once on the host:
 //   slots uint32 [cap]      cap = power of two >= 2 * n_words; 0 = empty, else word number + 1
 //   pool  uint8  [n, Wv]    the words themselves, NUL-padded, Wv a multiple of 16 (16-byte loads)
-// One thread per id: FNV-1a (64 bit) over the bytes up to the first NUL, linear probing from hash & (cap - 1), and every
-// occupied slot on the way is settled by comparing the WORD BYTES (16 at a time), never the hash alone -- so a hash
-// collision can cost a probe but cannot return a wrong row.  Load factor <= 0.5 -> 1.5 probes expected.
+// One thread per id: the row is read 16 bytes at a time, everything from the first NUL on is masked off with word-wide bit
+// tricks (registers only), the masked chunks are hashed by a 64-bit multiply-xorshift chain, then linear probing from
+// hash & (cap - 1) -- and every occupied slot on the way is settled by comparing the WORD BYTES (16 at a time), never
+// the hash alone, so a hash collision can cost a probe but cannot return a wrong row.  Load factor <= 0.5 -> ~1.5 probes.
 // Algorithmic bytes per id: W read + 8 written + ~1.5 x (4 + Wv) of table (L2-resident up to ~2M words; beyond that
 // each probe is a random 32-byte HBM sector pair).  A warp reads 32 consecutive rows of the id matrix: coalesced.
 #include <cstring>
@@ -28,28 +29,62 @@ struct rs_vocab {
 
 namespace {
 
-constexpr uint64_t kFnvOffset = 0xCBF29CE484222325ull;
-constexpr uint64_t kFnvPrime = 0x100000001B3ull;
+constexpr uint64_t kSeed = 0xCBF29CE484222325ull;
+constexpr uint64_t kMulLo = 0x9E3779B97F4A7C15ull;
+constexpr uint64_t kMulHi = 0xC2B2AE3D27D4EB4Full;
 
 __host__ __device__ __forceinline__ uint32_t fold(uint64_t h) { return static_cast<uint32_t>(h ^ (h >> 32)); }
 
-// bytes of one word up to the first NUL (host side of the very same hash)
-inline uint64_t fnv1a_host(const uint8_t* s, int64_t width) {
-  uint64_t h = kFnvOffset;
-  for (int64_t i = 0; i < width && s[i]; ++i) h = (h ^ s[i]) * kFnvPrime;
-  return h;
+// The per-id routine is __host__ __device__ so that tests/native/string_lookup_check.cu can run the very same masking,
+// hashing, probing and comparison code on the host (no GPU in the build container); the product only launches the kernel.
+__host__ __device__ __forceinline__ uint4 load16(const uint8_t* row, int c) {
+#ifdef __CUDA_ARCH__
+  return __ldg(reinterpret_cast<const uint4*>(row) + c);
+#else
+  uint4 v;
+  std::memcpy(&v, row + 16 * c, 16);
+  return v;
+#endif
 }
 
-// The per-id routine is __host__ __device__ so that tests/native/string_lookup_check.cu can run the very same probing and
-// comparison code on the host (no GPU in the build container); the product only ever launches it as a kernel.
+__host__ __device__ __forceinline__ int first_set_bit(uint32_t x) {   // index of the lowest set bit, x != 0
 #ifdef __CUDA_ARCH__
-#define RS_LD(ptr) __ldg(ptr)
+  return __ffs(static_cast<int>(x)) - 1;
 #else
-#define RS_LD(ptr) (*(ptr))
+  return __builtin_ctz(x);
 #endif
+}
 
-__host__ __device__ __forceinline__ uint4 load16(const uint8_t* row, int c) {
-  return RS_LD(reinterpret_cast<const uint4*>(row) + c);
+// One 32-bit word of a row (4 bytes, little endian).  Keeps the bytes before the first NUL, zeroes the rest; `ended`
+// carries "a NUL was seen" from word to word.  The zero-byte detector (w - 0x01010101) & ~w & 0x80808080 can flag
+// bytes ABOVE the first zero byte by borrow, never below it, so its lowest set bit is exact.
+__host__ __device__ __forceinline__ uint32_t keep_before_nul(uint32_t w, bool& ended) {
+  if (ended) return 0u;
+  const uint32_t z = (w - 0x01010101u) & ~w & 0x80808080u;
+  if (z == 0u) return w;
+  ended = true;
+  const int byte = first_set_bit(z) >> 3;               // 0..3
+  return byte == 0 ? 0u : (w & (0xFFFFFFFFu >> (8 * (4 - byte))));
+}
+
+__host__ __device__ __forceinline__ uint4 keep_before_nul(uint4 v, bool& ended) {
+  v.x = keep_before_nul(v.x, ended);
+  v.y = keep_before_nul(v.y, ended);
+  v.z = keep_before_nul(v.z, ended);
+  v.w = keep_before_nul(v.w, ended);
+  return v;
+}
+
+// Hash of a string = a multiply-xorshift chain over its NUL-masked 16-byte chunks (two 64-bit lanes per chunk).  Only
+// chunks that hold string bytes take part, so the value does not depend on how wide the row around the string is.
+__host__ __device__ __forceinline__ uint64_t mix_chunk(uint64_t h, const uint4& v) {
+  const uint64_t lo = static_cast<uint64_t>(v.x) | (static_cast<uint64_t>(v.y) << 32);
+  const uint64_t hi = static_cast<uint64_t>(v.z) | (static_cast<uint64_t>(v.w) << 32);
+  h = (h ^ lo) * kMulLo;
+  h ^= h >> 32;
+  h = (h ^ hi) * kMulHi;
+  h ^= h >> 29;
+  return h;
 }
 
 struct LookupParams {
@@ -57,8 +92,8 @@ struct LookupParams {
   int64_t ld;
   int64_t B;
   int W;                  // bytes per id row
-  int id_chunks;          // ceil(W / 16) when vec == 0 the tail chunk is assembled bytewise with bounds
-  int vec;                // rows are 16-byte aligned and W % 16 == 0
+  int id_chunks;          // ceil(W / 16)
+  int vec;                // rows are 16-byte aligned and W % 16 == 0: 128-bit loads
   const uint32_t* slots;
   const uint8_t* pool;
   int word_chunks;        // Wv / 16
@@ -68,58 +103,64 @@ struct LookupParams {
 
 __host__ __device__ __forceinline__ uint4 id_chunk(const LookupParams& p, const uint8_t* row, int c) {
   if (p.vec) return load16(row, c);
-  uint32_t w[4] = {0u, 0u, 0u, 0u};             // unaligned / odd-width id matrices: byte loads, zero past the row
+  uint32_t w0 = 0u, w1 = 0u, w2 = 0u, w3 = 0u;    // unaligned / odd-width id matrices: byte loads, zero past the row
+#pragma unroll
   for (int b = 0; b < 16; ++b) {
     const int at = 16 * c + b;
-    if (at < p.W) w[b >> 2] |= static_cast<uint32_t>(row[at]) << (8 * (b & 3));
+    const uint32_t byte = at < p.W ? static_cast<uint32_t>(row[at]) << (8 * (b & 3)) : 0u;
+    if ((b >> 2) == 0) w0 |= byte;
+    else if ((b >> 2) == 1) w1 |= byte;
+    else if ((b >> 2) == 2) w2 |= byte;
+    else w3 |= byte;
   }
-  return make_uint4(w[0], w[1], w[2], w[3]);
+  return make_uint4(w0, w1, w2, w3);
 }
 
-// zeroes everything from the first NUL byte on (a row is compared as the string before its first NUL); returns true
-// when the chunk holds a NUL
-__host__ __device__ __forceinline__ bool cut_at_nul(uint32_t (&w)[4]) {
-  for (int b = 0; b < 16; ++b) {
-    if (((w[b >> 2] >> (8 * (b & 3))) & 0xFFu) == 0u) {
-      for (int z = b; z < 16; ++z) w[z >> 2] &= ~(0xFFu << (8 * (z & 3)));
-      return true;
-    }
+__host__ __device__ __forceinline__ bool any_byte(const uint4& v) { return (v.x | v.y | v.z | v.w) != 0u; }
+
+// hash and chunk count of a NUL-padded row of n_chunks aligned chunks (the table build hashes the pool rows with it)
+__host__ __device__ __forceinline__ uint64_t hash_row(const uint8_t* row, int n_chunks) {
+  uint64_t h = kSeed;
+  bool ended = false;
+  for (int c = 0; c < n_chunks && !ended; ++c) {
+    const uint4 v = keep_before_nul(load16(row, c), ended);
+    if (!any_byte(v)) break;
+    h = mix_chunk(h, v);
   }
-  return false;
+  return h;
 }
 
 __host__ __device__ __forceinline__ int64_t lookup_one(const LookupParams& p, int64_t i) {
   const uint8_t* row = p.ids + i * p.ld;
-  // pass 1: hash and length in chunks (bytes after the first NUL do not belong to the string)
-  uint64_t h = kFnvOffset;
+  // pass 1: hash and length in chunks (bytes from the first NUL on do not belong to the string)
+  uint64_t h = kSeed;
   int n_used = 0;                                   // chunks holding string bytes
   bool ended = false;
+  uint4 first = make_uint4(0u, 0u, 0u, 0u);         // chunk 0, masked: most ids end inside it
   for (int c = 0; c < p.id_chunks && !ended; ++c) {
-    const uint4 v = id_chunk(p, row, c);
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-    for (int b = 0; b < 16; ++b) {
-      const uint32_t byte = (w[b >> 2] >> (8 * (b & 3))) & 0xFFu;
-      if (byte == 0u) { ended = true; break; }
-      h = (h ^ byte) * kFnvPrime;
-    }
-    if (!ended || (w[0] & 0xFFu) != 0u) n_used = c + 1;
+    const uint4 v = keep_before_nul(id_chunk(p, row, c), ended);
+    if (!any_byte(v)) break;
+    h = mix_chunk(h, v);
+    n_used = c + 1;
+    if (c == 0) first = v;
   }
   if (n_used > p.word_chunks) return 0;             // longer than every word: out of vocabulary
   uint32_t slot = fold(h) & p.mask;
   for (uint32_t probe = 0; probe <= p.mask; ++probe, slot = (slot + 1) & p.mask) {
-    const uint32_t e = RS_LD(p.slots + slot);
+#ifdef __CUDA_ARCH__
+    const uint32_t e = __ldg(p.slots + slot);
+#else
+    const uint32_t e = p.slots[slot];
+#endif
     if (e == 0u) return 0;                          // an empty slot ends the probe sequence: not in the vocabulary
     const uint8_t* word = p.pool + static_cast<int64_t>(e - 1) * (16 * (int64_t)p.word_chunks);
     bool same = true;
+    bool tail_ended = false;
     for (int c = 0; c < p.word_chunks && same; ++c) {
       const uint4 a = load16(word, c);
       uint4 b = make_uint4(0u, 0u, 0u, 0u);
-      if (c < n_used) {
-        const uint4 v = id_chunk(p, row, c);
-        uint32_t w[4] = {v.x, v.y, v.z, v.w};
-        cut_at_nul(w);
-        b = make_uint4(w[0], w[1], w[2], w[3]);
-      }
+      if (c == 0) b = first;
+      else if (c < n_used) b = keep_before_nul(id_chunk(p, row, c), tail_ended);
       same = a.x == b.x && a.y == b.y && a.z == b.z && a.w == b.w;
     }
     if (same) return static_cast<int64_t>(e);
@@ -146,7 +187,7 @@ void build_table(const uint8_t* words, int64_t n_words, int64_t width, int64_t w
     while (len < width && s[len]) ++len;
     uint8_t* dst = pool.data() + i * wv;
     std::memcpy(dst, s, static_cast<size_t>(len));                    // bytes after the first NUL stay zero
-    uint32_t slot = fold(fnv1a_host(s, width)) & mask;
+    uint32_t slot = fold(hash_row(dst, static_cast<int>(wv / 16))) & mask;
     for (;; slot = (slot + 1) & mask) {
       if (slots[slot] == 0u) { slots[slot] = static_cast<uint32_t>(i + 1); break; }
       // a repeated word keeps its LAST position, as the host dict {word: i + 1} does
@@ -220,6 +261,7 @@ extern "C" int rs_vocab_lookup(const rs_vocab_t* v, const DLTensor* ids, DLTenso
     RS_CHECK(ids->device.device_id == v->device && rows->device.device_id == v->device,
              "ids / rows live on another device than the vocabulary");
     RS_CHECK(rows->shape[0] == ids->shape[0], "rows length must equal the number of ids");
+    if (ids->shape[0] == 0) return;                 // nothing to do (an empty tensor's strides carry no meaning)
     RS_CHECK(rows->shape[0] <= 1 || stride_of(rows, 0) == 1, "rows must be contiguous");
     RS_CHECK(ids->shape[1] >= 1 && ids->shape[1] <= 4096, "id width must be in [1, 4096] bytes");
     LookupParams p{};
