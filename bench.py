@@ -762,7 +762,7 @@ def bench_ranking(rs, torch, dist, args, device, world, rank, pk, timed, traffic
     ir = torch.from_numpy(rs.synth.make_ids(rng, n_items, B).astype(np.int32)).pin_memory()
     ur_d, ir_d = ur.to(device), ir.to(device)
     out_host = torch.empty((2, B), dtype=torch.float32).pin_memory()
-    emb_host = torch.empty((B, 256), dtype=torch.float32).pin_memory()
+    emb_host = torch.empty((2, B, 128), dtype=torch.float32).pin_memory()   # one contiguous pinned block per embedding
     flops = 524288.0 * B
     res = {}
     for precision in ("bf16", "fp32"):
@@ -788,8 +788,8 @@ def bench_ranking(rs, torch, dist, args, device, world, rank, pk, timed, traffic
             out_host[0].copy_(o["rating_prediction"].view(-1), non_blocking=True)
             out_host[1].copy_(o["ctr_prediction"].view(-1), non_blocking=True)
             if full:     # what MultiTaskModel.call returns in full: the two [B,128] embeddings as well
-                emb_host[:, :128].copy_(o["user_embedding"], non_blocking=True)
-                emb_host[:, 128:].copy_(o["item_embedding"], non_blocking=True)
+                emb_host[0].copy_(o["user_embedding"], non_blocking=True)
+                emb_host[1].copy_(o["item_embedding"], non_blocking=True)
             torch.cuda.current_stream().synchronize()
 
         if sess is not None:

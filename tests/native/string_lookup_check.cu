@@ -10,7 +10,7 @@ extern "C" int string_lookup_host_check(const uint8_t* words, int64_t n_words, i
   const int64_t wv = (width + 15) / 16 * 16;
   std::vector<uint32_t> slots;
   std::vector<uint8_t> pool;
-  build_table(words, n_words, width, wv, slots, pool);
+  const uint32_t mask = build_table(words, n_words, width, wv, slots, pool);
   // 16-byte aligned copies, as cudaMalloc would hand out
   std::vector<uint4> slots_al((slots.size() * 4 + 15) / 16), pool_al((pool.size() + 15) / 16 + 1);
   std::memcpy(slots_al.data(), slots.data(), slots.size() * 4);
@@ -25,8 +25,15 @@ extern "C" int string_lookup_host_check(const uint8_t* words, int64_t n_words, i
   p.slots = reinterpret_cast<const uint32_t*>(slots_al.data());
   p.pool = reinterpret_cast<const uint8_t*>(pool_al.data());
   p.word_chunks = static_cast<int>(wv / 16);
-  p.mask = static_cast<uint32_t>(slots.size() - 1);
+  p.mask = mask;
   p.rows = rows;
-  for (int64_t i = 0; i < B; ++i) rows[i] = lookup_one(p, i);
+  // the kernel's own pairing: ids i and i + n_threads together, a single id when the partner is past the end
+  const int64_t n_threads = B > 7 ? (B + 2) / 3 : 1;
+  for (int64_t base = 0; base < B; base += 2 * n_threads)
+    for (int64_t t = 0; t < n_threads && base + t < B; ++t) {
+      const int64_t i = base + t, i1 = i + n_threads;
+      if (i1 < B) lookup_two(p, i, i1);
+      else rows[i] = lookup_one(p, i);
+    }
   return p.vec;
 }

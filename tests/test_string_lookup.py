@@ -39,9 +39,11 @@ def _want(vocab, ids):
     return string_lookup(make_vocab_index(list(vocab)), ids)
 
 
-@pytest.fixture(scope="module")
-def host_check():
-    out = NATIVE / "_build" / "libstring_lookup_check.so"
+@pytest.fixture(scope="module", params=["tags32", "tags2"])
+def host_check(request):
+    """The product's lookup routine compiled for the host: once as shipped, once with 2-bit tags (different words then share
+    tags all the time, so the one-shot candidate is often the wrong word and the sequential byte-checked walk takes over)."""
+    out = NATIVE / "_build" / f"libstring_lookup_check_{request.param}.so"
     src = NATIVE / "string_lookup_check.cu"
     prod = ROOT / "recommendation-system-maang-nvidia-_b200" / "csrc" / "string_lookup.cu"
     if not out.exists() or out.stat().st_mtime < max(src.stat().st_mtime, prod.stat().st_mtime):
@@ -49,8 +51,10 @@ def host_check():
         if not Path(nvcc).exists():
             pytest.skip("nvcc is not available to build the host check")
         out.parent.mkdir(exist_ok=True)
+        extra = ["-DRS_STRING_LOOKUP_TAG_MASK=0x3u"] if request.param == "tags2" else []
         subprocess.run([nvcc, "-O2", "-std=c++17", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
-                        "-Wno-deprecated-gpu-targets", "-shared", "-o", str(out), str(src)], check=True, capture_output=True)
+                        "-Wno-deprecated-gpu-targets", *extra, "-shared", "-o", str(out), str(src)], check=True,
+                       capture_output=True)
     lib = ctypes.CDLL(str(out))
     lib.string_lookup_host_check.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p,
                                              ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p]
