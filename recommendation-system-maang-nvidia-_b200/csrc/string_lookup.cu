@@ -4,16 +4,16 @@
 // Ids arrive as a fixed-width byte matrix uint8 [B, W] (NUL-padded rows: numpy's `S` dtype, an Arrow fixed-size binary
 // column) -- byte and integer work only.  The vocabulary is a bucketed open-addressing table in HBM built once on the host:
 //   slots uint32 [cap][2]   (word number + 1, 32-bit tag of the hash); 0 = empty.  cap = power of two >= 4 * n_words,
-//                           grouped into buckets of 4 slots = one 32-byte sector; a bucket fills left to right
+//                           grouped into buckets of 2 slots = 16 bytes (one 128-bit load); a bucket fills left to right
 //   pool  uint8  [n, Wv]    the words themselves, NUL-padded, Wv a multiple of 16 (16-byte loads)
 // Per id: the row is read 16 bytes at a time, everything from the first NUL on is masked off with word-wide bit tricks
-// (registers only), the masked chunks are hashed by a 64-bit multiply-xorshift chain; ONE 32-byte load fetches the id's
+// (registers only), the masked chunks are hashed by a 64-bit multiply-xorshift chain; ONE 16-byte load fetches the id's
 // home bucket, slots whose tag matches are settled by comparing the WORD BYTES (16 at a time) -- never the hash alone, so a
 // collision can cost a load but cannot return a wrong row -- and the first empty slot ends the search.  At load <= 0.25 a
-// bucket overflows into the next one for 0.4 % of the words.  A thread works on two ids at once (their row loads and
+// bucket overflows into the next one for 1.4 % of the words.  A thread works on two ids at once (their row loads and
 // their bucket loads are issued back to back): the kernel is bound by the latency of the dependent loads
 // (row -> bucket -> word), not by bytes.
-// Algorithmic bytes per id: W read + 8 written; + 32 B of bucket and Wv of word, L2-resident up to ~2M words.
+// Algorithmic bytes per id: W read + 8 written; + 16 B of bucket and Wv of word, L2-resident up to ~2M words.
 #include <cstring>
 #include <vector>
 
@@ -104,17 +104,15 @@ struct LookupParams {
   int64_t* rows;
 };
 
-constexpr int kBucketSlots = 4;                        // 4 x (row + 1, tag) = 32 bytes
+constexpr int kBucketSlots = 2;                        // 2 x (row + 1, tag) = 16 bytes = one 128-bit load
 
 struct Bucket {
-  uint4 lo, hi;                                        // slots 0,1 | slots 2,3
+  uint4 v;                                             // x, y = slot 0 (row + 1, tag); z, w = slot 1
 };
 
 __host__ __device__ __forceinline__ Bucket load_bucket(const LookupParams& p, uint32_t b) {
   Bucket k;
-  const uint8_t* at = reinterpret_cast<const uint8_t*>(p.slots) + static_cast<int64_t>(b) * 32;
-  k.lo = load16(at, 0);
-  k.hi = load16(at, 1);
+  k.v = load16(reinterpret_cast<const uint8_t*>(p.slots) + static_cast<int64_t>(b) * 16, 0);
   return k;
 }
 
@@ -211,14 +209,16 @@ __host__ __device__ __forceinline__ bool word_equals(const LookupParams& p, cons
 
 // Sequential walk from the id's home bucket: every slot whose tag matches is settled on the bytes; the first empty slot
 // ends the search.  Complete on its own -- the kernel only comes here when the one-shot pick below does not settle an id
-// (home bucket full without a match: 0.4 % of the words; a tag that matched another word: ~1e-9).
-__host__ __device__ __noinline__ int64_t finish_seq(const LookupParams& p, const uint8_t* row, const Prepared& q) {
+// (home bucket full without a match: 1.4 % of the words; a tag that matched another word: ~1e-9).  Inlined on purpose: as
+// a call it forced the prepared id through a stack frame, and that local-memory traffic cost more than the walk saves.
+__host__ __device__ __forceinline__ int64_t finish_seq(const LookupParams& p, const uint8_t* row, const Prepared& q) {
   const uint32_t tag = tag_of(q.h);
   uint32_t b = fold(q.h) & p.mask;
   for (uint32_t probe = 0; probe <= p.mask; ++probe, b = (b + 1) & p.mask) {
     const Bucket k = load_bucket(p, b);
-    const uint32_t e[kBucketSlots] = {k.lo.x, k.lo.z, k.hi.x, k.hi.z};
-    const uint32_t t[kBucketSlots] = {k.lo.y, k.lo.w, k.hi.y, k.hi.w};
+    const uint32_t e[kBucketSlots] = {k.v.x, k.v.z};
+    const uint32_t t[kBucketSlots] = {k.v.y, k.v.w};
+#pragma unroll
     for (int j = 0; j < kBucketSlots; ++j) {
       if (e[j] == 0u) return 0;                     // slots fill left to right: nothing further on
       if (t[j] == tag && word_equals(p, row, q, e[j])) return static_cast<int64_t>(e[j]);
@@ -238,8 +238,8 @@ __host__ __device__ __forceinline__ Pick pick(const Bucket& k, uint32_t tag) {
   Pick r;
   r.cand = 0u;
   r.state = 2;
-  const uint32_t e[kBucketSlots] = {k.lo.x, k.lo.z, k.hi.x, k.hi.z};
-  const uint32_t t[kBucketSlots] = {k.lo.y, k.lo.w, k.hi.y, k.hi.w};
+  const uint32_t e[kBucketSlots] = {k.v.x, k.v.z};
+  const uint32_t t[kBucketSlots] = {k.v.y, k.v.w};
 #pragma unroll
   for (int j = kBucketSlots - 1; j >= 0; --j) {     // right to left, so the leftmost event wins
     if (e[j] == 0u) { r.state = 0; r.cand = 0u; }
