@@ -8,6 +8,8 @@ Executed unmodified, from where they lie under /root/reference:
   src/trainer.py:221-246         ProductionTrainer._get_item_embeddings, _save_artifacts, _build_faiss
   app/recommendation_service.py  RecommendationService . load / recommend / score / _get_popular_items / get_model_info
   src/evaluation.py:25-81        AdvancedMetrics
+  src/trainer.py:194-219         ProductionTrainer._evaluate (offline recall@k by raw dot + argpartition)
+  app/main.py                    the FastAPI application: /health, /, /recommend, /score, /model/info (a request transcript)
 over the numpy stand-ins of tensorflow / keras / tensorflow_recommenders / faiss in tf_faiss_standin.py (none of the
 four is installed here).  So the fixtures pin the reference's COMPOSITION -- which layers, in which order, on which
 tensors, the control flow of the service, the artifact files it exchanges -- while every primitive (Dense, Embedding,
@@ -41,6 +43,16 @@ VARIANTS = {
     "C": dict(cfg=dict(embedding_dim=64, user_tower_dims=[], item_tower_dims=[128], cross_layers=0, dnn_dims=[32]),
               n_users=20, n_items=30, batch=24, weight_seed=81, id_seed=82),
 }
+
+
+HTTP_REQUESTS = [
+    ("GET", "/health"), ("GET", "/"), ("GET", "/model/info"),
+    ("POST", "/recommend", {"user_id": "1", "k": 5}), ("POST", "/recommend", {"user_id": "10"}),
+    ("POST", "/recommend", {"user_id": "nobody", "k": 3}), ("POST", "/recommend", {"user_id": "1", "k": 0}),
+    ("POST", "/recommend", {"user_id": "1", "k": 101}), ("POST", "/recommend", {"k": 3}),
+    ("POST", "/score", {"user_id": "137", "item_ids": ["1", "2", "no-such-movie"]}),
+    ("POST", "/score", {"user_id": "nobody", "item_ids": ["1"]}), ("POST", "/score", {"user_id": "1", "item_ids": []}),
+]
 
 
 def variant_inputs(name):
@@ -177,6 +189,46 @@ def generate(reference_root="/root/reference"):
                 doc["score_unknown_user"] = None
             except ValueError as e:
                 doc["score_unknown_user"] = str(e)
+
+            # 5. offline evaluation as the trainer does it (src/trainer.py:194-219): recall@k of the true item among the k
+            #    largest RAW dots (no normalisation), over (user, true item) pairs; the true items are planted at known ranks
+            import pandas as pd
+            rng = np.random.default_rng(SPEC["id_seed"] + 1)
+            val_users = [uv[i] for i in rng.integers(0, len(uv), 64)]
+            item_embs = T._get_item_embeddings(fake, model, list(iv))
+            user_embs = model.encoder({"user_id": tf.constant(val_users)}, training=False)["user_embedding"].numpy()
+            raw = user_embs @ item_embs.T
+            planted = [1, 3, 8, 15, 30, 70]
+            true_items = [iv[int(np.lexsort((np.arange(len(iv)), -raw[r]))[planted[r % len(planted)] - 1])]
+                          for r in range(len(val_users))]
+            T._evaluate(fake, model, {"val_ds": object(), "item_vocab": list(iv),
+                                      "val_df": pd.DataFrame({"user_id": val_users, "movie_id": true_items})})
+            doc["offline_eval"] = {"users": val_users, "true_items": true_items, "planted_ranks": planted,
+                                   "metrics": json.loads((Path(tmp) / "metrics.json").read_text())}
+
+            # 6. the FastAPI application (app/main.py) over that service: a transcript of requests and answers
+            from fastapi.testclient import TestClient
+            import importlib
+            main = importlib.import_module("app.main")
+            client = TestClient(main.app)                                # no lifespan: start-up would look for outputs/models/...
+            transcript = []
+
+            def call(method, path, body=None):
+                r = client.request(method, path, json=body)
+                rec = {"method": method, "path": path, "json": body, "status": r.status_code}
+                if r.status_code != 422:                                 # validation bodies are pydantic's wording, not the app's
+                    rec["body"] = r.json()
+                    if path == "/model/info" and r.status_code == 200:
+                        rec["body"]["model_path"] = "<tmp>"
+                transcript.append(rec)
+
+            call("POST", "/recommend", {"user_id": "1", "k": 5})          # before a service is set: 503
+            call("GET", "/health")
+            main.recommendation_service = svc
+            for req in HTTP_REQUESTS:
+                call(*req)
+            main.recommendation_service = None
+            doc["http"] = transcript
 
         # 4. the ranked lists through AdvancedMetrics (src/evaluation.py:25-81)
         A = ref["src.evaluation"].AdvancedMetrics

@@ -286,6 +286,7 @@ def import_reference(root="/root/reference"):
     return out
 
 
-def drop_reference():
+def drop_reference(root="/root/reference"):
     for name in [n for n in sys.modules if n == "src" or n == "app" or n.startswith("src.") or n.startswith("app.")]:
         del sys.modules[name]
+    sys.path[:] = [p for p in sys.path if p != str(root)]          # app/main.py:18 puts the reference root on sys.path

@@ -39,6 +39,17 @@ def _close(got, want, tol):
     return got.shape == want.shape and np.abs(got - want).max() <= tol * max(np.abs(want).max(), 1e-30)
 
 
+def _same_json(got, want, tol=1e-5, skip=("model_path",)):
+    if isinstance(want, dict):
+        return isinstance(got, dict) and set(got) == set(want) and all(     # key order is not part of a JSON contract
+            k in skip or _same_json(got[k], want[k], tol, skip) for k in want)
+    if isinstance(want, list):
+        return isinstance(got, list) and len(got) == len(want) and all(_same_json(a, b, tol, skip) for a, b in zip(got, want))
+    if isinstance(want, float):
+        return isinstance(got, (int, float)) and abs(got - want) <= tol * max(1.0, abs(want))
+    return got == want
+
+
 @pytest.mark.skipif(not Path("/root/reference/src/models.py").exists(), reason="the reference tree is not on this box")
 def test_committed_fixture_is_what_the_reference_produces_today():
     arrays, doc = mrg.generate()
@@ -56,6 +67,8 @@ def test_committed_fixture_is_what_the_reference_produces_today():
         assert _close([r["score"] for r in doc["recommend"][u]], [r["score"] for r in c_doc["recommend"][u]], 1e-6)
     assert list(doc["score"]) == list(c_doc["score"])
     assert _close(list(doc["score"].values()), list(c_doc["score"].values()), 1e-12)
+    assert doc["offline_eval"] == c_doc["offline_eval"]
+    assert _same_json(doc["http"], c_doc["http"], tol=1e-6, skip=())
     # the stand-ins and the reference modules are gone again: nothing else in the session sees them
     assert "tensorflow" not in sys.modules and "faiss" not in sys.modules and "src.models" not in sys.modules
 
@@ -111,20 +124,38 @@ def test_oracle_ranking_matches_the_reference_run_on_other_configs(name, oracle_
     assert len(w["cross_w"]) == cfg.cross_layers and w["rating_head"][0].shape == (2 * E + deep, 1)
 
 
-def test_oracle_service_matches_the_reference_run(ref_run, oracle_mod):
+def _oracle_service(r, oracle_mod):
+    """The oracle's service over a catalog built the way the trainer builds it (src/trainer.py:221-226,239-242): item tower
+    in 512-id batches, float32, normalise, add."""
     from oracle import flat_ip
     from oracle.models import MultiTowerModel as OMT
-    r, doc = ref_run, ref_run["doc"]
     enc = OMT(r["w"], r["uv"], r["iv"], np.float32)
-    # catalog build restated (src/trainer.py:221-226,239-242): item tower in 512-id batches, float32, normalise, add
     embs = np.vstack([enc({"movie_id": r["iv"][i:i + 512]})["item_embedding"] for i in range(0, len(r["iv"]), 512)])
     embs = np.ascontiguousarray(embs, dtype=np.float32)
     flat_ip.normalize_L2(embs)
-    assert _close(embs, r["arrays"]["catalog"], 2e-6)
     index = flat_ip.IndexFlatIP(embs.shape[1])
     index.add(embs)
     item_map = {str(i): it for i, it in enumerate(r["iv"])}
-    svc = oracle_mod.RecommendationService(enc, index, r["uv"], item_map)
+    return oracle_mod.RecommendationService(enc, index, r["uv"], item_map), embs
+
+
+def _replay_transcript(app, doc, svc):
+    """The requests the reference's app/main.py answered (tests/golden/reference_run.json: http), sent to `app`."""
+    from fastapi.testclient import TestClient
+    client = TestClient(app)                                   # no lifespan: the service is put in place by hand, as recorded
+    for n, rec in enumerate(doc["http"]):
+        if n == 2:
+            app.state.recsys["service"] = svc                  # the first two requests were answered without a service
+        r = client.request(rec["method"], rec["path"], json=rec["json"])
+        assert r.status_code == rec["status"], (rec, r.text)
+        if "body" in rec:
+            assert _same_json(r.json(), rec["body"]), (rec, r.json())
+
+
+def test_oracle_service_matches_the_reference_run(ref_run, oracle_mod):
+    r, doc = ref_run, ref_run["doc"]
+    svc, embs = _oracle_service(r, oracle_mod)
+    assert _close(embs, r["arrays"]["catalog"], 2e-6)
     info = svc.get_model_info()
     assert (info["version"], info["num_users"], info["faiss_index_items"]) == ("1.2.0", len(r["uv"]), len(r["iv"]))
     for u in mrg.SPEC["users"]:
@@ -141,6 +172,36 @@ def test_oracle_service_matches_the_reference_run(ref_run, oracle_mod):
     with pytest.raises(ValueError) as e:
         svc.score("nobody", doc["score_ids"][:2])
     assert str(e.value) == doc["score_unknown_user"]
+
+
+def test_oracle_offline_eval_matches_the_reference_run(ref_run, oracle_mod):
+    """src/trainer.py:194-219 restated on the oracle encoder: raw dots, the k largest per user, recall of the true item."""
+    from oracle.models import MultiTowerModel as OMT
+    r, ev = ref_run, ref_run["doc"]["offline_eval"]
+    enc = OMT(r["w"], r["uv"], r["iv"], np.float64)
+    items = enc({"movie_id": r["iv"]})["item_embedding"]
+    users = enc({"user_id": ev["users"]})["user_embedding"]
+    sims = users @ items.T
+    pos = {it: i for i, it in enumerate(r["iv"])}
+    truth = np.array([pos[t] for t in ev["true_items"]])
+    order = np.stack([np.lexsort((np.arange(sims.shape[1]), -row)) for row in sims])
+    ranks = np.array([int(np.where(order[u] == truth[u])[0][0]) + 1 for u in range(len(truth))])
+    assert list(ranks) == [ev["planted_ranks"][u % len(ev["planted_ranks"])] for u in range(len(truth))]
+    for k in r["cfg"].eval_topk:
+        assert float(np.mean(ranks <= k)) == ev["metrics"][f"recall@{k}"]
+
+
+def test_serving_app_replays_the_reference_http_transcript(ref_run, oracle_mod, rs):
+    """recsys_b200.create_app (serving.py, host code) against app/main.py itself: the recorded requests get the same status
+    codes and the same JSON when the product's application runs over a service with the reference's semantics (here the
+    oracle's; over the CUDA service under -m gpu below), with and without the micro-batching queue."""
+    r = ref_run
+    svc, _ = _oracle_service(r, oracle_mod)
+    svc.recommend_batch = lambda ids, k=10: [{"user_id": u, "recommendations": svc.recommend(u, k), "status": "success"}
+                                             for u in ids]
+    for micro in (False, True):
+        app = rs.create_app(service=None, micro_batch=micro, max_wait_ms=0.5)
+        _replay_transcript(app, r["doc"], svc)
 
 
 def test_oracle_metrics_match_the_reference_run(ref_run):
@@ -225,3 +286,18 @@ def test_cuda_service_matches_the_reference_run(ref_run, rs, tmp_path):
     for b, u in zip(batch, mrg.SPEC["users"]):
         assert [x["item_id"] for x in b["recommendations"]] == [x["item_id"] for x in doc["recommend"][u]]
     assert batch[-1]["recommendations"] == svc.recommend("nobody", mrg.SPEC["k"])
+
+
+@pytest.mark.gpu
+def test_cuda_offline_eval_and_http_match_the_reference_run(ref_run, rs):
+    r, doc = ref_run, ref_run["doc"]
+    enc = rs.MultiTowerModel(r["cfg"], r["uv"], r["iv"], {})
+    rs.load_weights(enc, r["w"])
+    ev = doc["offline_eval"]
+    got = rs.evaluate_recall(enc, r["iv"], ev["users"], ev["true_items"], ks=r["cfg"].eval_topk)   # src/trainer.py:194-219
+    assert got == {k: float(v) for k, v in ev["metrics"].items()}
+    index, item_map = rs.build_item_index(enc, r["iv"])
+    svc = rs.RecommendationService.from_parts(enc, index, r["uv"], item_map)
+    for micro in (False, True):
+        app = rs.create_app(service=None, micro_batch=micro, max_wait_ms=0.5)
+        _replay_transcript(app, doc, svc)
