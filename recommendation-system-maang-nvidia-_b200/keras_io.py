@@ -9,8 +9,10 @@ Two layers:
   with compact link messages, chunked datasets through a B-tree v1 index with no filter or deflate(+shuffle).
   Dense (fractal-heap) groups and version-4 chunk indexes raise NotImplementedError.  `write_hdf5` produces the
   h5py-default subset and exists so that the reader has something to be tested against here.
-  PARITY UNPINNED: both were written from the HDF5 file-format specification; no file produced by h5py / Keras was
-  available to check them against.
+  PARITY: both were written from the HDF5 file-format specification.  The reader's generic layer (user block, superblock
+  v0, version-1 object headers, symbol-table groups, contiguous IEEE datasets) is checked against ONE file the genuine
+  HDF5 library wrote (a MATLAB "-v7.3" file from scipy's test data, tests/test_keras_io.py); no file produced by h5py /
+  Keras was available, so the Keras weight-path layout below stays UNPINNED.
 
 * `load_keras_encoder(path) -> weights` -- maps the Keras-v3 weight paths of the reference's MultiTowerModel
   (src/models.py:59-77: attributes user_embedding / item_embedding = Embedding, user_tower / item_tower =

@@ -1,7 +1,10 @@
 """CPU tests of the HDF5 / Keras-v3 archive reader (recsys_b200.keras_io) that lets the service load the reference's
 `encoder.keras` (src/trainer.py:230) without h5py.  The fixtures are produced by the module's own writer (h5py is not
-available here, so conformance with files written by h5py itself is NOT pinned -- see the module docstring); a few
-hand-assembled variants cover structures the writer does not emit (compact layout, version-2 dataspace)."""
+available here, so conformance with files written by h5py / Keras themselves is NOT pinned -- see the module docstring); a
+few hand-assembled variants cover structures the writer does not emit (compact layout, version-2 dataspace), and ONE file
+written by the genuine HDF5 library is read: tests/golden/libhdf5_written_matlab73.mat, a MATLAB 7.4 "-v7.3" file (HDF5
+behind a 512-byte user block, superblock v0, symbol-table groups -- the structures h5py's defaults also produce) copied
+from scipy's test data (scipy/io/matlab/tests/data/testhdf5_7.4_GLNX86.mat, BSD-3-Clause)."""
 
 import struct
 import zipfile
@@ -142,3 +145,16 @@ def test_hdf5_roundtrip_random_trees():
             np.testing.assert_array_equal(got[k], v)
 
     check()
+
+
+def test_reader_parses_a_file_written_by_the_real_hdf5_library():
+    """The one independent check of the reader: a file libhdf5 itself wrote (through MATLAB 7.4).  Its single variable is
+    scipy's `testdouble` case, the row 0 : pi/4 : 2*pi stored as a [9, 1] float64 dataset."""
+    path = Path(__file__).resolve().parent / "golden" / "libhdf5_written_matlab73.mat"
+    data = path.read_bytes()
+    assert data[:19] == b"MATLAB 7.0 MAT-file" and data[512:520] == b"\x89HDF\r\n\x1a\n"     # user block, then the superblock
+    ds = keras_io.read_hdf5(data)
+    assert list(ds) == ["testdouble"]
+    x = ds["testdouble"]
+    assert x.dtype == np.float64 and x.shape == (9, 1)
+    np.testing.assert_allclose(x[:, 0], np.arange(9) * np.pi / 4, rtol=0, atol=1e-15)
