@@ -1016,6 +1016,24 @@ def bench_string_lookup(rs, torch, device, timed, pk, n_words=1 << 20, B=1 << 22
         got = look.lookup_host(sample)
         dt = time.perf_counter() - t0
         out["parity"]["sample_equal_to_lookup_host"] = bool(np.array_equal(got, want[:n]))
+        # the model-facing call on a LIST of Python strings (65,536 ids): Arrow packing + device table (the automatic path
+        # for large batches against large vocabularies) against the host dict, both ending with the rows on the device
+        m = 1 << 16
+        times = {}
+        for label, env in (("device_table_ms", "1"), ("host_dict_ms", "0")):
+            os.environ["RS_DEVICE_LOOKUP"] = env
+            best = None
+            for _ in range(4):
+                t0 = time.perf_counter()
+                rows = look(sample[:m])
+                torch.cuda.synchronize()
+                dt_ = time.perf_counter() - t0
+                best = dt_ if best is None else min(best, dt_)
+            times[label] = best * 1e3
+            times[label.replace("_ms", "_equal")] = bool(np.array_equal(rows.cpu().numpy(), want[:m]))
+        os.environ.pop("RS_DEVICE_LOOKUP", None)
+        out["str_list_call"] = dict(times, ids=m, note="StringLookup.__call__(list of str): best of 4, host wall time incl. the "
+                                                        "upload; the first device call also builds the table (excluded by best-of)")
         out["cpu_baseline"] = {"value": n / dt, "unit": "ids/s", "cores": 1, "kind": "port",
                                "sample": f"{n:,} of the same ids as Python strings through the host dict (the lookup the models use "
                                          f"for string lists; stands for the TF hash-table op)"}

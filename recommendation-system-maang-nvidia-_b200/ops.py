@@ -41,6 +41,35 @@ def pack_strings(ids, width: Optional[int] = None):
     return out
 
 
+def pack_str_list(ids):
+    """Fast packing of a list / tuple of Python `str` through an Arrow string array (one C-level pass instead of a Python
+    loop): the same uint8 [n, W] matrix pack_strings gives, or None when that is not possible -- pyarrow missing, entries
+    that are not `str`, or a string with a NUL byte inside (the byte layout ends a row at its first NUL, a dict key does
+    not: such ids must go through the host dict to keep the two lookups identical)."""
+    import numpy as np
+    try:
+        import pyarrow as pa
+        a = pa.array(ids, type=pa.string())
+    except Exception:  # noqa: BLE001 -- ImportError, ArrowInvalid / ArrowTypeError for non-str entries
+        return None
+    if a.null_count:
+        return None
+    n = len(a)
+    bufs = a.buffers()
+    off = np.frombuffer(bufs[1], dtype=np.int32, count=n + 1, offset=a.offset * 4).astype(np.int64)
+    lens = np.diff(off)
+    w = int(lens.max()) if n else 1
+    out = np.zeros((n, max(16, (w + 15) // 16 * 16)), dtype=np.uint8)
+    if n and off[-1] > off[0]:
+        data = np.frombuffer(bufs[2], dtype=np.uint8)
+        rows = np.repeat(np.arange(n), lens)
+        cols = np.arange(off[0], off[-1]) - np.repeat(off[:-1], lens)
+        out[rows, cols] = data[off[0]:off[-1]]
+        if not np.array_equal((out != 0).sum(axis=1), lens):
+            return None
+    return out
+
+
 class DeviceVocabulary:
     """K0 handle: the StringLookup table on the device (csrc/string_lookup.cu).  `lookup(ids)` takes a CUDA uint8 [B, W]
     byte matrix (see pack_strings) and returns int64 [B] rows: vocabulary[i] -> i + 1, anything else -> 0."""
@@ -49,7 +78,9 @@ class DeviceVocabulary:
         if not torch.cuda.is_available():
             raise RuntimeError("recsys_b200 needs a CUDA (sm_100a) device; there is no CPU fallback")
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
-        words = pack_strings(vocabulary)
+        words = pack_str_list(vocabulary) if isinstance(vocabulary, (list, tuple)) else None
+        if words is None:
+            words = pack_strings(vocabulary)
         self._lib = _lib.load()
         self._h = ctypes.c_void_p()
         with torch.cuda.device(self.device):

@@ -89,6 +89,18 @@ def test_pack_strings_layout(rs):
         rs.ops.pack_strings(["x" * 20], width=16)
 
 
+def test_pack_str_list_equals_pack_strings_or_declines(rs):
+    for _, vocab, ids in _cases():
+        for seq in (list(vocab), list(ids), tuple(ids)):
+            got = rs.ops.pack_str_list(seq)
+            assert got is not None and got.dtype == np.uint8 and np.array_equal(got, rs.ops.pack_strings(seq))
+    # a NUL inside a string, entries that are not str, missing values: the caller must keep the host dict
+    assert rs.ops.pack_str_list(["ab", "a\0b"]) is None and rs.ops.pack_str_list(["a\0"]) is None
+    assert rs.ops.pack_str_list(["a", 7]) is None
+    assert np.array_equal(rs.ops.pack_str_list(["a", b"b"]), rs.ops.pack_strings(["a", b"b"]))   # bytes are taken as UTF-8, as lookup_host does
+    assert rs.ops.pack_str_list(["a", None]) is None
+
+
 @pytest.mark.parametrize("case", _cases(), ids=lambda c: c[0])
 def test_lookup_routine_on_the_host_matches_the_reference_semantics(rs, host_check, case):
     _, vocab, ids = case
@@ -178,3 +190,26 @@ def test_model_call_with_byte_ids_equals_the_string_call(rs):
     with pytest.raises(RuntimeError):
         rs.ops.DeviceVocabulary(["a"]).lookup(torch.zeros((2, 16), dtype=torch.uint8, device="cuda"),
                                               out=torch.zeros((3,), dtype=torch.int64, device="cuda"))
+
+
+@pytest.mark.gpu
+def test_large_string_batches_against_large_vocabularies_take_the_device_path(rs, monkeypatch):
+    """StringLookup.__call__ on a list of str: host dict by default, the device table for >= DEVICE_MIN_IDS ids against
+    >= DEVICE_MIN_WORDS words (where the dict misses the CPU caches on every probe) -- same rows either way, and ids the
+    byte layout cannot carry (a NUL inside) keep the whole call on the dict."""
+    vocab = rs.synth.make_vocab(250_000)
+    look = rs.StringLookup(vocab)
+    rng = np.random.default_rng(3)
+    ids = [vocab[i] for i in rng.integers(0, len(vocab), 9000)] + ["nobody", "", "héllo", "250001"]
+    want = look.lookup_host(ids)
+    small = look(ids[:100])
+    assert look._device_vocab is None and np.array_equal(small.cpu().numpy(), want[:100])       # short list: host dict
+    got = look(ids)
+    assert look._device_vocab is not None and np.array_equal(got.cpu().numpy(), want)            # long list: device table
+    odd = ids + ["1\x002"]
+    assert np.array_equal(look(odd).cpu().numpy(), look.lookup_host(odd))                         # NUL inside: dict, 0 for that id
+    monkeypatch.setenv("RS_DEVICE_LOOKUP", "0")
+    assert np.array_equal(look(ids).cpu().numpy(), want)
+    few_words = rs.StringLookup(vocab[:1000])
+    few_words(ids)
+    assert few_words._device_vocab is None                                                       # small vocabulary: host dict
