@@ -119,6 +119,52 @@ def build_reference_model(ref, cfg_dict, w, uv, iv, users, items):
     return cfg, model
 
 
+API_SCRIPT_FUNCTIONS = ("test_health", "test_root", "test_model_info", "test_recommendations", "test_scoring",
+                        "test_batch_recommendations")
+
+
+def run_reference_api_script(client, reference_root="/root/reference"):
+    """app/test_api.py is a script for a live server (requests against http://localhost:8000).  Its functions are called
+    unmodified; only the transport is swapped: the module's `requests` name is bound to an object that sends the same
+    calls through a FastAPI TestClient.  Per function: how it ended, the status codes it printed, whether it printed its
+    own pass line."""
+    import contextlib
+    import importlib.util
+    import io
+    import re
+    import requests
+
+    spec = importlib.util.spec_from_file_location("reference_app_test_api", Path(reference_root) / "app" / "test_api.py")
+    api = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(api)
+    base = api.BASE_URL
+
+    class ViaTestClient:
+        exceptions = requests.exceptions
+
+        @staticmethod
+        def get(url, **kw):
+            return client.get(url[len(base):] or "/", **kw)
+
+        @staticmethod
+        def post(url, **kw):
+            return client.post(url[len(base):] or "/", **kw)
+
+    api.requests = ViaTestClient
+    outcomes = {}
+    for name in API_SCRIPT_FUNCTIONS:
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            try:
+                getattr(api, name)()
+                ended = "returned"
+            except Exception as e:  # noqa: BLE001 -- the outcome is the data
+                ended = f"{type(e).__name__}: {e}"
+        text = buf.getvalue()
+        outcomes[name] = {"ended": ended, "status": re.findall(r"Status: (\d+)", text), "pass_line": "\u2705" in text}
+    return outcomes
+
+
 def generate(reference_root="/root/reference"):
     import tf_faiss_standin as standin
     standin.install()
@@ -227,8 +273,10 @@ def generate(reference_root="/root/reference"):
             main.recommendation_service = svc
             for req in HTTP_REQUESTS:
                 call(*req)
-            main.recommendation_service = None
             doc["http"] = transcript
+            # 7. the reference's own API test script (app/test_api.py), its functions run as they are against that app
+            doc["test_api"] = run_reference_api_script(client, reference_root)
+            main.recommendation_service = None
 
         # 4. the ranked lists through AdvancedMetrics (src/evaluation.py:25-81)
         A = ref["src.evaluation"].AdvancedMetrics

@@ -67,7 +67,7 @@ def test_committed_fixture_is_what_the_reference_produces_today():
         assert _close([r["score"] for r in doc["recommend"][u]], [r["score"] for r in c_doc["recommend"][u]], 1e-6)
     assert list(doc["score"]) == list(c_doc["score"])
     assert _close(list(doc["score"].values()), list(c_doc["score"].values()), 1e-12)
-    assert doc["offline_eval"] == c_doc["offline_eval"]
+    assert doc["offline_eval"] == c_doc["offline_eval"] and doc["test_api"] == c_doc["test_api"]
     assert _same_json(doc["http"], c_doc["http"], tol=1e-6, skip=())
     # the stand-ins and the reference modules are gone again: nothing else in the session sees them
     assert "tensorflow" not in sys.modules and "faiss" not in sys.modules and "src.models" not in sys.modules
@@ -202,6 +202,28 @@ def test_serving_app_replays_the_reference_http_transcript(ref_run, oracle_mod, 
     for micro in (False, True):
         app = rs.create_app(service=None, micro_batch=micro, max_wait_ms=0.5)
         _replay_transcript(app, r["doc"], svc)
+
+
+@pytest.mark.skipif(not Path("/root/reference/app/test_api.py").exists(), reason="the reference tree is not on this box")
+def test_the_references_own_api_test_script_ends_the_same_way_on_this_app(ref_run, oracle_mod, rs):
+    """app/test_api.py -- the only test the reference holds for this path -- called function by function against
+    recsys_b200.create_app: every function ends as it does against app/main.py itself (tests/golden/reference_run.json:
+    test_api; that includes its stale /model/info expectations failing the same way), except the batch endpoint, which
+    app/main.py does not have (404) and this application serves."""
+    from fastapi.testclient import TestClient
+    r = ref_run
+    svc, _ = _oracle_service(r, oracle_mod)
+    svc.recommend_batch = lambda ids, k=10: [{"user_id": u, "recommendations": svc.recommend(u, k), "status": "success"}
+                                             for u in ids]
+    app = rs.create_app(service=svc, micro_batch=False)
+    got = mrg.run_reference_api_script(TestClient(app))
+    want = r["doc"]["test_api"]
+    assert set(got) == set(want) == set(mrg.API_SCRIPT_FUNCTIONS)
+    for name in mrg.API_SCRIPT_FUNCTIONS:
+        if name == "test_batch_recommendations":
+            assert want[name]["status"] == ["404"] and got[name] == {"ended": "returned", "status": ["200"], "pass_line": True}
+        else:
+            assert got[name] == want[name], name
 
 
 def test_oracle_metrics_match_the_reference_run(ref_run):
