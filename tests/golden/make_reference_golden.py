@@ -9,6 +9,7 @@ Executed unmodified, from where they lie under /root/reference:
   app/recommendation_service.py  RecommendationService . load / recommend / score / _get_popular_items / get_model_info
   src/evaluation.py:25-81        AdvancedMetrics
   src/trainer.py:194-219         ProductionTrainer._evaluate (offline recall@k by raw dot + argpartition)
+  app/model_service.py           the alternate service: raw-dot recommend (:104-150), score (:152-198), recommend_batch (:200-228)
   app/main.py                    the FastAPI application: /health, /, /recommend, /score, /model/info (a request transcript)
 over the numpy stand-ins of tensorflow / keras / tensorflow_recommenders / faiss in tf_faiss_standin.py (none of the
 four is installed here).  So the fixtures pin the reference's COMPOSITION -- which layers, in which order, on which
@@ -274,6 +275,21 @@ def generate(reference_root="/root/reference"):
             for req in HTTP_REQUESTS:
                 call(*req)
             doc["http"] = transcript
+            # 8. the alternate service the reference keeps beside it (app/model_service.py:72-90,104-150,200-228): item
+            #    embeddings precomputed in 512-id batches, RAW dots (no normalisation), argpartition + argsort, and the
+            #    batch call with its per-user status entries
+            alt_mod = importlib.import_module("app.model_service")
+            alt = alt_mod.RecommendationService(tmp)
+            alt.model, alt.user_vocab, alt.item_vocab, alt.config = model.encoder, list(uv), list(iv), cfg.to_dict()
+            alt._precompute_item_embeddings()
+            assert alt.is_ready()
+            batch_ids = [SPEC["users"][0], "nobody", SPEC["users"][1], SPEC["users"][0]]
+            doc["alt_service"] = {"recommend": {u: alt.recommend(u, SPEC["k"]) for u in SPEC["users"]},
+                                  "batch_ids": batch_ids, "batch": alt.recommend_batch(batch_ids, 5),
+                                  "score": alt.score(SPEC["users"][2], score_ids),
+                                  "user_norms": {u: float(np.linalg.norm(model.encoder(
+                                      {"user_id": tf.constant([u])}, training=False)["user_embedding"].numpy())) for u in SPEC["users"]}}
+
             # 7. the reference's own API test script (app/test_api.py), its functions run as they are against that app
             doc["test_api"] = run_reference_api_script(client, reference_root)
             main.recommendation_service = None

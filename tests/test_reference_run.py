@@ -68,6 +68,7 @@ def test_committed_fixture_is_what_the_reference_produces_today():
     assert list(doc["score"]) == list(c_doc["score"])
     assert _close(list(doc["score"].values()), list(c_doc["score"].values()), 1e-12)
     assert doc["offline_eval"] == c_doc["offline_eval"] and doc["test_api"] == c_doc["test_api"]
+    assert _same_json(doc["alt_service"], c_doc["alt_service"], tol=1e-9, skip=())
     assert _same_json(doc["http"], c_doc["http"], tol=1e-6, skip=())
     # the stand-ins and the reference modules are gone again: nothing else in the session sees them
     assert "tensorflow" not in sys.modules and "faiss" not in sys.modules and "src.models" not in sys.modules
@@ -226,6 +227,32 @@ def test_the_references_own_api_test_script_ends_the_same_way_on_this_app(ref_ru
             assert got[name] == want[name], name
 
 
+def test_oracle_raw_dot_search_matches_the_references_alternate_service(ref_run, oracle_mod):
+    """app/model_service.py:104-150: raw dots against the un-normalised item embeddings,
+    argpartition + argsort.  The oracle's flat index over un-normalised rows with an un-normalised query is that search."""
+    from oracle import flat_ip
+    from oracle.models import MultiTowerModel as OMT
+    r, alt = ref_run, ref_run["doc"]["alt_service"]
+    enc = OMT(r["w"], r["uv"], r["iv"], np.float32)
+    items = np.ascontiguousarray(enc({"movie_id": r["iv"]})["item_embedding"], dtype=np.float32)
+    index = flat_ip.IndexFlatIP(items.shape[1])
+    index.add(items)
+    for u in mrg.SPEC["users"]:
+        q = np.ascontiguousarray(enc({"user_id": [u]})["user_embedding"], dtype=np.float32)
+        D, I = index.search(q, mrg.SPEC["k"])
+        want = alt["recommend"][u]
+        assert [r["iv"][i] for i in I[0]] == [x["item_id"] for x in want]
+        assert _close(D[0], [x["score"] for x in want], 1e-5)
+        assert abs(float(np.linalg.norm(q.astype(np.float64))) - alt["user_norms"][u]) <= 1e-5 * alt["user_norms"][u]
+    sc = flat_ip.matvec(items[:mrg.SPEC["score_items"]], np.ascontiguousarray(
+        enc({"user_id": [mrg.SPEC["users"][2]]})["user_embedding"][0], dtype=np.float32))
+    assert list(alt["score"]) == r["iv"][:mrg.SPEC["score_items"]]        # the alternate drops ids outside the vocabulary
+    assert _close(sc, list(alt["score"].values()), 1e-5)
+    # the batch call's shape (app/model_service.py:200-228): one entry per input id, in order, duplicates kept
+    assert [b["user_id"] for b in alt["batch"]] == alt["batch_ids"]
+    assert all(set(b) == {"user_id", "recommendations", "status"} and b["status"] == "success" for b in alt["batch"])
+
+
 def test_oracle_metrics_match_the_reference_run(ref_run):
     from oracle import evaluation as ev
     doc = ref_run["doc"]
@@ -323,3 +350,26 @@ def test_cuda_offline_eval_and_http_match_the_reference_run(ref_run, rs):
     for micro in (False, True):
         app = rs.create_app(service=None, micro_batch=micro, max_wait_ms=0.5)
         _replay_transcript(app, doc, svc)
+
+
+@pytest.mark.gpu
+def test_cuda_raw_dot_index_and_batch_call_match_the_references_alternate_service(ref_run, rs):
+    """Row a16: the un-normalised index (build_item_index(normalize=False)) ranks as app/model_service.py's raw-dot search
+    does, and recommend_batch answers in that file's shape (:200-228)."""
+    r, alt = ref_run, ref_run["doc"]["alt_service"]
+    enc = rs.MultiTowerModel(r["cfg"], r["uv"], r["iv"], {})
+    rs.load_weights(enc, r["w"])
+    index, item_map = rs.build_item_index(enc, r["iv"], normalize=False)
+    svc = rs.RecommendationService.from_parts(enc, index, r["uv"], item_map)
+    for u in mrg.SPEC["users"]:
+        got, want = svc.recommend(u, mrg.SPEC["k"]), alt["recommend"][u]
+        assert [x["item_id"] for x in got] == [x["item_id"] for x in want]
+        # recommend() normalises the query (app/recommendation_service.py:71): its scores are the raw dots / |user embedding|
+        assert _close([x["score"] * alt["user_norms"][u] for x in got], [x["score"] for x in want], 1e-5)
+    batch = svc.recommend_batch(alt["batch_ids"], 5)
+    assert [b["user_id"] for b in batch] == [b["user_id"] for b in alt["batch"]]
+    for b, w in zip(batch, alt["batch"]):
+        assert set(b) == set(w) and b["status"] == w["status"] and len(b["recommendations"]) == len(w["recommendations"])
+        assert all(set(x) == {"item_id", "score", "rank"} for x in b["recommendations"])
+        if b["user_id"] in r["uv"]:
+            assert [x["item_id"] for x in b["recommendations"]] == [x["item_id"] for x in w["recommendations"]]
