@@ -611,6 +611,11 @@ def main():
             parity = check_parity(rs, torch, dist, sidx, args, device, world, rank, q_dev)
         except Exception as e:  # noqa: BLE001
             parity = {"error": f"{type(e).__name__}: {e}"}
+        if rank == 0 and isinstance(parity, dict):
+            try:
+                parity["reference_run"] = reference_run_check(rs, torch, device)
+            except Exception as e:  # noqa: BLE001
+                parity["reference_run"] = {"error": f"{type(e).__name__}: {e}"}
 
     # ---- second headline: DCN ranking forward at batch 65,536 (configs[1]) ----
     ranking = None
@@ -747,6 +752,37 @@ def check_parity(rs, torch, dist, sidx, args, device, world, rank, q_dev, n_q=16
                                "bit_equal": bool(np.array_equal(Ds.cpu().numpy(), Dw) and np.array_equal(Is.cpu().numpy(), Iw)),
                                "against": "oracle.flat_ip.search_chain (single fp32 FMA chain per score, tie-break score desc / row asc) on the host"}
     return out
+
+
+def reference_run_check(rs, torch, device):
+    """The CUDA path against tests/golden/reference_run.*: outputs of the reference's OWN files (src/models.py,
+    src/trainer.py's catalog build, app/recommendation_service.py) run over numpy stand-ins of TF / faiss by
+    tests/golden/make_reference_golden.py (the same checks as tests/test_reference_run.py, here as a flag in the line)."""
+    golden = ROOT / "tests" / "golden"
+    if str(golden) not in sys.path:
+        sys.path.insert(0, str(golden))
+    import make_reference_golden as mrg
+    arrays, doc = mrg.load_committed()
+    cfg, w, uv, iv, users, items = mrg.synth_inputs()
+    model = rs.MultiTaskModel(cfg, uv, iv, {}, device=device)
+    rs.load_weights(model, w)
+    out = model({"user_id": users, "movie_id": items}, training=False)
+    worst = 0.0
+    for key in ("user_embedding", "item_embedding", "rating_prediction", "ctr_prediction"):
+        want = arrays[f"f64_{key}"]
+        worst = max(worst, float(np.abs(out[key].cpu().numpy().astype(np.float64) - want).max() / np.abs(want).max()))
+    index, item_map = rs.build_item_index(model.encoder, iv)
+    svc = rs.RecommendationService.from_parts(model.encoder, index, uv, item_map)
+    same_items, score_err = True, 0.0
+    for u in mrg.SPEC["users"]:
+        got, want = svc.recommend(u, mrg.SPEC["k"]), doc["recommend"][u]
+        same_items = same_items and [x["item_id"] for x in got] == [x["item_id"] for x in want]
+        score_err = max(score_err, max(abs(a["score"] - b["score"]) for a, b in zip(got, want)))
+    return {"against": "tests/golden/reference_run.*: the reference's own src/models.py / trainer catalog build / "
+                       "recommendation_service.py run over numpy stand-ins of TF and faiss (float64 primitives)",
+            "ranking_max_err_over_scale": worst, "ranking_within_1e-5": bool(worst <= 1e-5),
+            "recommend_users": len(mrg.SPEC["users"]), "recommend_items_equal": bool(same_items),
+            "recommend_max_score_err": score_err, "cold_start_equal": svc.recommend("nobody", 7) == doc["cold_start"]}
 
 
 def bench_ranking(rs, torch, dist, args, device, world, rank, pk, timed, traffic_db):
