@@ -44,7 +44,7 @@ def pack_strings(ids, width: Optional[int] = None):
 def pack_str_list(ids):
     """Fast packing of a list / tuple of Python `str` through an Arrow string array (one C-level pass instead of a Python
     loop): the same uint8 [n, W] matrix pack_strings gives, or None when that is not possible -- pyarrow missing, entries
-    that are not `str`, or a string with a NUL byte inside (the byte layout ends a row at its first NUL, a dict key does
+    that are not `str`, a string longer than 4,096 bytes, or a string with a NUL byte inside (the byte layout ends a row at its first NUL, a dict key does
     not: such ids must go through the host dict to keep the two lookups identical)."""
     import numpy as np
     try:
@@ -59,6 +59,8 @@ def pack_str_list(ids):
     off = np.frombuffer(bufs[1], dtype=np.int32, count=n + 1, offset=a.offset * 4).astype(np.int64)
     lens = np.diff(off)
     w = int(lens.max()) if n else 1
+    if w > 4096:                                   # wider than the device lookup accepts (rs_vocab_lookup): host dict
+        return None
     out = np.zeros((n, max(16, (w + 15) // 16 * 16)), dtype=np.uint8)
     if n and off[-1] > off[0]:
         data = np.frombuffer(bufs[2], dtype=np.uint8)

@@ -98,7 +98,8 @@ def test_pack_str_list_equals_pack_strings_or_declines(rs):
     assert rs.ops.pack_str_list(["ab", "a\0b"]) is None and rs.ops.pack_str_list(["a\0"]) is None
     assert rs.ops.pack_str_list(["a", 7]) is None
     assert np.array_equal(rs.ops.pack_str_list(["a", b"b"]), rs.ops.pack_strings(["a", b"b"]))   # bytes are taken as UTF-8, as lookup_host does
-    assert rs.ops.pack_str_list(["a", None]) is None
+    assert rs.ops.pack_str_list(["a", None]) is None and rs.ops.pack_str_list(["a", "x" * 4097]) is None
+    assert rs.ops.pack_str_list(["a", "x" * 4096]).shape == (2, 4096)
 
 
 @pytest.mark.parametrize("case", _cases(), ids=lambda c: c[0])
