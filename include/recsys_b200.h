@@ -69,6 +69,8 @@ int rs_device_sm_count(int* out);
  *   rs_vocab_create: words = HOST bytes [n_words, width], each row one word, NUL-padded (numpy `S<width>` layout;
  *                    a row is the string before its first NUL, so words cannot contain NUL).  Builds the hash table
  *                    on the current device.  A repeated word keeps its last position (as a dict built in order does).
+ *                    Limits: n_words <= 2^28, 1 <= width <= 4096.  Table memory: 32 B per word (tagged slots at load
+ *                    <= 0.25) + the words padded to a multiple of 16 bytes.
  *   rs_vocab_lookup: ids uint8 [B, W] device (same row layout, any W; rows longer than every word are out of
  *                    vocabulary), rows int64 [B] device.  Matches are decided on the bytes, never on the hash alone.
  */
