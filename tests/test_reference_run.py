@@ -262,6 +262,8 @@ def test_oracle_metrics_match_the_reference_run(ref_run):
     assert ev.precision_at_k(preds, truth, 5) == m["precision@5"]
     assert ev.ndcg_at_k(preds, truth, 10) == m["ndcg@10"]
     assert ev.map_at_k(preds, truth, 10) == m["map@10"] and ev.mrr(preds, truth) == m["mrr"]
+    assert ev.coverage(preds, ref_run["iv"]) == m["coverage"] and ev.diversity(preds) == m["diversity"]
+    assert ev.coverage(preds, []) == 0.0 and ev.diversity([]) == 0.0 and ev.diversity([["a"]]) == 0.0
 
 
 # ----------------------------------------------------------------------------------------------------------------------
