@@ -611,7 +611,7 @@ def main():
             parity = check_parity(rs, torch, dist, sidx, args, device, world, rank, q_dev)
         except Exception as e:  # noqa: BLE001
             parity = {"error": f"{type(e).__name__}: {e}"}
-        if rank == 0 and isinstance(parity, dict):
+        if world == 1 and isinstance(parity, dict):     # single-GPU models and index: one line (N=1) carries it
             try:
                 parity["reference_run"] = reference_run_check(rs, torch, device)
             except Exception as e:  # noqa: BLE001
